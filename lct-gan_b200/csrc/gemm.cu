@@ -1,0 +1,162 @@
+// Skinny fp32 GEMMs of the generator bottleneck (nn.Linear, GRU input projections, attention
+// in/out projections) and their gradients.
+//
+// Replaces (reference file:line): GRUblockf/GRUblockt linear algebra, models/generator.py:104,
+// :133, :138, :219, :245, :248 (aten::linear / addmm inside nn.GRU, nn.MultiheadAttention,
+// nn.Linear -> cuBLAS).  M = B*T'*F' = 34 056 rows at B=8, N and K are 16..192: AI < 50 flop/B,
+// HBM/L2 bound, so a register-tiled SIMT kernel is the right tool (one pass over A, weights
+// resident in L1/L2).  Three operand layouts cover forward, dgrad and wgrad; wgrad splits the
+// long row dimension across CTAs and finishes with atomics.
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4;
+constexpr int kThreads = (BM / TM) * (BN / TN);   // 256
+
+struct GemmParams {
+    const float* A; const float* B; float* C;
+    const float* bias; const float* res; float* out2;
+    int M, N, K;
+    int lda, ldb, ldc, ldr, ldo;
+    int ta, tb;          // ta: A(m,k) = A[k*lda+m];  tb: B(k,n) = B[k*ldb+n], else B[n*ldb+k]
+    int act; float slope; float alpha;
+    int accumulate;      // C += result (no atomics)
+    int ksplit;          // >1: split K across blockIdx.z, atomicAdd epilogue (C pre-zeroed / accumulated)
+    int nbatch, a_div, b_div;
+    int64_t sA, sB, sC, sBias, sRes, sOut2;
+};
+
+__global__ void __launch_bounds__(kThreads) gemm_kernel(const GemmParams p) {
+    __shared__ __align__(16) float As[BK][BM + 4];
+    __shared__ __align__(16) float Bs[BK][BN + 4];
+    const int tid = threadIdx.x;
+    const int z = blockIdx.z;
+    const int batch = z / p.ksplit, ks = z - batch * p.ksplit;
+    const float* A = p.A + (int64_t)(batch / p.a_div) * p.sA;
+    const float* B = p.B + (int64_t)(batch / p.b_div) * p.sB;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int kchunk = ((p.K + p.ksplit - 1) / p.ksplit + BK - 1) / BK * BK;
+    const int k_begin = ks * kchunk;
+    const int k_end = min(p.K, k_begin + kchunk);
+    const int tx = tid % (BN / TN), ty = tid / (BN / TN);
+
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = k_begin; k0 < k_end; k0 += BK) {
+        // A tile: BM x BK
+#pragma unroll
+        for (int i = 0; i < (BM * BK) / kThreads; ++i) {
+            int e = tid + i * kThreads;
+            int m, k;
+            if (p.ta) { m = e % BM; k = e / BM; } else { k = e % BK; m = e / BK; }
+            int gm = m0 + m, gk = k0 + k;
+            float v = 0.f;
+            if (gm < p.M && gk < k_end) v = p.ta ? A[(int64_t)gk * p.lda + gm] : A[(int64_t)gm * p.lda + gk];
+            As[k][m] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < (BN * BK) / kThreads; ++i) {
+            int e = tid + i * kThreads;
+            int n, k;
+            if (p.tb) { n = e % BN; k = e / BN; } else { k = e % BK; n = e / BK; }
+            int gn = n0 + n, gk = k0 + k;
+            float v = 0.f;
+            if (gn < p.N && gk < k_end) v = p.tb ? B[(int64_t)gk * p.ldb + gn] : B[(int64_t)gn * p.ldb + gk];
+            Bs[k][n] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * TM]);
+            float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * TN]);
+            float a[TM] = {a4.x, a4.y, a4.z, a4.w};
+            float b[TN] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+
+    float* C = p.C + (int64_t)batch * p.sC;
+    const float* bias = p.bias ? p.bias + (int64_t)batch * p.sBias : nullptr;
+    const float* res = p.res ? p.res + (int64_t)batch * p.sRes : nullptr;
+    float* out2 = p.out2 ? p.out2 + (int64_t)batch * p.sOut2 : nullptr;
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        int gm = m0 + ty * TM + i;
+        if (gm >= p.M) continue;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            int gn = n0 + tx * TN + j;
+            if (gn >= p.N) continue;
+            float v = acc[i][j] * p.alpha;
+            float* c = C + (int64_t)gm * p.ldc + gn;
+            if (p.ksplit > 1) {
+                atomicAdd(c, v);
+            } else {
+                if (bias) v += bias[gn];
+                v = apply_act(v, p.act, p.slope);
+                if (p.accumulate) v += *c;
+                *c = v;
+                if (out2) out2[(int64_t)gm * p.ldo + gn] = v + (res ? res[(int64_t)gm * p.ldr + gn] : 0.f);
+            }
+        }
+    }
+}
+
+// out[n] += sum_m X[m, n]
+__global__ void colsum_kernel(const float* __restrict__ X, float* __restrict__ out, int M, int N, int ld,
+                              int rows_per_cta) {
+    const int n = blockIdx.y * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const int r0 = blockIdx.x * rows_per_cta;
+    const int r1 = min(M, r0 + rows_per_cta);
+    float a = 0.f;
+    for (int r = r0; r < r1; ++r) a += X[(int64_t)r * ld + n];
+    atomicAdd(&out[n], a);
+}
+
+}  // namespace
+
+// C[M,N] = act(alpha * op(A) op(B) + bias)  (+ C if accumulate);  out2 = C + res  (optional).
+// Batched over blockIdx.z: A += (z / a_div) * sA, B += (z / b_div) * sB, C/bias/res/out2 += z * s*.
+// ksplit > 1 splits K over CTAs and atomically adds into C (bias/act/res/out2 must then be unset).
+LCT_API int lct_gemm(const float* A, const float* B, float* C, const float* bias, const float* res, float* out2,
+                     int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int64_t ldr,
+                     int64_t ldo, int ta, int tb, int act, float slope, float alpha, int accumulate, int64_t ksplit,
+                     int64_t nbatch, int64_t a_div, int64_t b_div, int64_t sA, int64_t sB, int64_t sC, int64_t sBias,
+                     int64_t sRes, int64_t sOut2, cudaStream_t st) {
+    if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0 || nbatch <= 0 || ksplit <= 0 || a_div <= 0 || b_div <= 0)
+        return LCT_EINVAL;
+    if (ksplit > 1 && (bias || res || out2 || act != LCT_ACT_NONE || accumulate)) return LCT_EINVAL;
+    if (nbatch * ksplit >= 65536) return LCT_EINVAL;
+    GemmParams p;
+    p.A = A; p.B = B; p.C = C; p.bias = bias; p.res = res; p.out2 = out2;
+    p.M = (int)M; p.N = (int)N; p.K = (int)K;
+    p.lda = (int)lda; p.ldb = (int)ldb; p.ldc = (int)ldc; p.ldr = (int)ldr; p.ldo = (int)ldo;
+    p.ta = ta; p.tb = tb; p.act = act; p.slope = slope; p.alpha = alpha; p.accumulate = accumulate;
+    p.ksplit = (int)ksplit; p.nbatch = (int)nbatch; p.a_div = (int)a_div; p.b_div = (int)b_div;
+    p.sA = sA; p.sB = sB; p.sC = sC; p.sBias = sBias; p.sRes = sRes; p.sOut2 = sOut2;
+    dim3 grid((unsigned)ceil_div64(M, BM), (unsigned)ceil_div64(N, BN), (unsigned)(nbatch * ksplit));
+    gemm_kernel<<<grid, kThreads, 0, st>>>(p);
+    LCT_RETURN_IF_LAUNCH_FAILED();
+    return 0;
+}
+
+// out[N] += column sums of X[M,N] (row stride ld); `out` zeroed / accumulated by the caller
+LCT_API int lct_colsum(const float* X, float* out, int64_t M, int64_t N, int64_t ld, cudaStream_t st) {
+    if (!X || !out || M <= 0 || N <= 0) return LCT_EINVAL;
+    const int rows = 256;
+    int threads = N >= 128 ? 128 : (N >= 64 ? 64 : 32);
+    dim3 grid((unsigned)ceil_div64(M, rows), (unsigned)ceil_div64(N, threads));
+    colsum_kernel<<<grid, threads, 0, st>>>(X, out, (int)M, (int)N, (int)ld, rows);
+    LCT_RETURN_IF_LAUNCH_FAILED();
+    return 0;
+}

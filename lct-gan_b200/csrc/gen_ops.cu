@@ -1,0 +1,584 @@
+// Generator bottleneck operators on channels-last rows [M = B*T'*F', C = 64].
+//
+// Replaces (reference file:line):
+//   nn.LayerNorm(64)                           models/generator.py:126, :132, :238, :244, :577
+//   4 x nn.GRU(16,16) per block (bi/uni)       models/generator.py:52-75, :94-110, :169-192, :211-222
+//   nn.MultiheadAttention(64, 4 heads)         models/generator.py:78-82, :133, :194-198, :245
+// The reference permutes [B,C,T,F] into [B*T,F,C] / [B*F,T,C] copies for every block; here the
+// activations stay in one channels-last buffer and a sequence is described by strides
+// (outer/inner/step), so the frequency and time blocks read the same memory without a transpose.
+//
+// The GRU recurrences are latency bound (33 or 129 dependent steps of a 16-wide cell): one
+// 16-lane group per (sequence, GRU, direction) keeps W_hh rows in registers and exchanges the
+// hidden state with warp shuffles; BPTT recomputes the gates from the saved hidden states and
+// accumulates dW_hh in registers.  Attention is one CTA per (sequence, head) with K/V in shared
+// memory and an online softmax; the backward recomputes probabilities from the saved
+// log-sum-exp (no L x L matrix is ever written).
+#include "common.cuh"
+
+namespace {
+
+struct SeqGeom {
+    int nseq, L, inner;
+    int64_t outer_stride, inner_stride, step_stride;   // in rows
+};
+
+__device__ __forceinline__ int64_t seq_row0(const SeqGeom& g, int seq) {
+    return (int64_t)(seq / g.inner) * g.outer_stride + (int64_t)(seq % g.inner) * g.inner_stride;
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm over the last dim (C <= 256), one warp per row
+// ------------------------------------------------------------------------------------------
+constexpr int kLnMaxPerLane = 8;
+
+__global__ void ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                              const float* __restrict__ beta, float* __restrict__ y, float* __restrict__ mean,
+                              float* __restrict__ rstd, int M, int C, float eps) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= M) return;
+    const float* xr = x + (int64_t)warp * C;
+    float v[kLnMaxPerLane];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxPerLane; ++i) {
+        int c = lane + 32 * i;
+        v[i] = c < C ? xr[c] : 0.f;
+        s += v[i];
+    }
+    const float mu = warp_sum(s) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxPerLane; ++i) {
+        int c = lane + 32 * i;
+        float d = c < C ? v[i] - mu : 0.f;
+        q += d * d;
+    }
+    const float rs = rsqrtf(warp_sum(q) / (float)C + eps);
+#pragma unroll
+    for (int i = 0; i < kLnMaxPerLane; ++i) {
+        int c = lane + 32 * i;
+        if (c < C) y[(int64_t)warp * C + c] = (v[i] - mu) * rs * gamma[c] + beta[c];
+    }
+    if (lane == 0) {
+        mean[warp] = mu;
+        rstd[warp] = rs;
+    }
+}
+
+__global__ void ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                              const float* __restrict__ gamma, const float* __restrict__ mean,
+                              const float* __restrict__ rstd, const float* __restrict__ dres,
+                              float* __restrict__ dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                              int M, int C) {
+    const int lane = threadIdx.x & 31;
+    const int warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    float ag[kLnMaxPerLane], ab[kLnMaxPerLane], gm[kLnMaxPerLane];
+#pragma unroll
+    for (int i = 0; i < kLnMaxPerLane; ++i) {
+        ag[i] = ab[i] = 0.f;
+        int c = lane + 32 * i;
+        gm[i] = c < C ? gamma[c] : 0.f;
+    }
+    for (int row = warp0; row < M; row += nwarps) {
+        const float mu = mean[row], rs = rstd[row];
+        float xh[kLnMaxPerLane], g[kLnMaxPerLane];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < kLnMaxPerLane; ++i) {
+            int c = lane + 32 * i;
+            if (c < C) {
+                float d = dy[(int64_t)row * C + c];
+                xh[i] = (x[(int64_t)row * C + c] - mu) * rs;
+                ag[i] += d * xh[i];
+                ab[i] += d;
+                g[i] = d * gm[i];
+                s1 += g[i];
+                s2 += g[i] * xh[i];
+            } else {
+                xh[i] = g[i] = 0.f;
+            }
+        }
+        s1 = warp_sum(s1) / (float)C;
+        s2 = warp_sum(s2) / (float)C;
+#pragma unroll
+        for (int i = 0; i < kLnMaxPerLane; ++i) {
+            int c = lane + 32 * i;
+            if (c < C) {
+                float v = rs * (g[i] - s1 - xh[i] * s2);
+                if (dres) v += dres[(int64_t)row * C + c];
+                dx[(int64_t)row * C + c] = v;
+            }
+        }
+    }
+    // block-level reduction of the parameter gradients, then one atomic per channel per CTA
+    __shared__ float sg[256], sb[256];
+    for (int c = threadIdx.x; c < 256; c += blockDim.x) sg[c] = sb[c] = 0.f;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kLnMaxPerLane; ++i) {
+        int c = lane + 32 * i;
+        if (c < C) {
+            atomicAdd(&sg[c], ag[i]);
+            atomicAdd(&sb[c], ab[i]);
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        atomicAdd(&dgamma[c], sg[c]);
+        atomicAdd(&dbeta[c], sb[c]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// GRU recurrence.  gi: [rows, GD, 48] = W_ih x + b_ih (gates r,z,n), whh: [GD,48,16], bhh: [GD,48],
+// hs: [rows, GD, 16].  GD = groups * dirs, dir = gd % D, dir 1 runs the sequence backwards.
+// ------------------------------------------------------------------------------------------
+constexpr int kH = 16;
+constexpr int kGruThreads = 256;
+constexpr int kUnitsPerCta = kGruThreads / kH;
+
+__global__ void __launch_bounds__(kGruThreads) gru_fwd_kernel(const float* __restrict__ gi,
+                                                              const float* __restrict__ whh,
+                                                              const float* __restrict__ bhh, float* __restrict__ hs,
+                                                              SeqGeom geo, int GD, int D) {
+    const int j = threadIdx.x % kH;
+    const int seq = blockIdx.x * kUnitsPerCta + threadIdx.x / kH;
+    const int gd = blockIdx.y;
+    const bool valid = seq < geo.nseq;
+    const bool rev = (gd % D) == 1;
+    float wr[kH], wz[kH], wn[kH];
+    const float* w = whh + (size_t)gd * 3 * kH * kH;
+#pragma unroll
+    for (int i = 0; i < kH; ++i) {
+        wr[i] = w[(0 * kH + j) * kH + i];
+        wz[i] = w[(1 * kH + j) * kH + i];
+        wn[i] = w[(2 * kH + j) * kH + i];
+    }
+    const float br = bhh[gd * 3 * kH + j], bz = bhh[gd * 3 * kH + kH + j], bn = bhh[gd * 3 * kH + 2 * kH + j];
+    const int64_t row0 = valid ? seq_row0(geo, seq) : 0;
+    const int64_t gstride = (int64_t)GD * 3 * kH;
+    float h = 0.f;
+    int step = rev ? geo.L - 1 : 0;
+    const int dstep = rev ? -1 : 1;
+    float gr = 0.f, gz = 0.f, gn = 0.f;
+    if (valid) {
+        const float* g0 = gi + (row0 + (int64_t)step * geo.step_stride) * gstride + gd * 3 * kH;
+        gr = g0[j]; gz = g0[kH + j]; gn = g0[2 * kH + j];
+    }
+    for (int s = 0; s < geo.L; ++s, step += dstep) {
+        const int64_t row = row0 + (int64_t)step * geo.step_stride;
+        float ngr = 0.f, ngz = 0.f, ngn = 0.f;
+        if (valid && s + 1 < geo.L) {   // prefetch the next step's input projection
+            const float* g1 = gi + (row + (int64_t)dstep * geo.step_stride) * gstride + gd * 3 * kH;
+            ngr = g1[j]; ngz = g1[kH + j]; ngn = g1[2 * kH + j];
+        }
+        float hr = br, hz = bz, hn = bn;
+#pragma unroll
+        for (int i = 0; i < kH; ++i) {
+            const float hi = __shfl_sync(0xffffffffu, h, i, kH);
+            hr = fmaf(wr[i], hi, hr);
+            hz = fmaf(wz[i], hi, hz);
+            hn = fmaf(wn[i], hi, hn);
+        }
+        const float r = sigmoidf_(gr + hr);
+        const float z = sigmoidf_(gz + hz);
+        const float n = tanhf(gn + r * hn);
+        h = (1.f - z) * n + z * h;
+        if (valid) hs[(row * GD + gd) * kH + j] = h;
+        gr = ngr; gz = ngz; gn = ngn;
+    }
+}
+
+// BPTT.  dh_in: [rows, ldd] gradient of the GRU output (column (gd/D)*16 + j, shared by both
+// directions).  Writes dgi [rows, GD, 48]; accumulates dwhh [GD,48,16], dbih [GD,48], dbhh [GD,48].
+__global__ void __launch_bounds__(kGruThreads) gru_bwd_kernel(
+    const float* __restrict__ gi, const float* __restrict__ hs, const float* __restrict__ whh,
+    const float* __restrict__ bhh, const float* __restrict__ dh_in, int ldd, float* __restrict__ dgi,
+    float* __restrict__ dwhh, float* __restrict__ dbih, float* __restrict__ dbhh, SeqGeom geo, int GD, int D) {
+    __shared__ float sW[3 * kH * kH];
+    __shared__ float sB[6 * kH];
+    const int j = threadIdx.x % kH;
+    const int seq = blockIdx.x * kUnitsPerCta + threadIdx.x / kH;
+    const int gd = blockIdx.y;
+    const bool valid = seq < geo.nseq;
+    const bool rev = (gd % D) == 1;
+    for (int i = threadIdx.x; i < 3 * kH * kH; i += kGruThreads) sW[i] = 0.f;
+    for (int i = threadIdx.x; i < 6 * kH; i += kGruThreads) sB[i] = 0.f;
+    float wr[kH], wz[kH], wn[kH];
+    const float* w = whh + (size_t)gd * 3 * kH * kH;
+#pragma unroll
+    for (int i = 0; i < kH; ++i) {
+        wr[i] = w[(0 * kH + j) * kH + i];
+        wz[i] = w[(1 * kH + j) * kH + i];
+        wn[i] = w[(2 * kH + j) * kH + i];
+    }
+    const float br = bhh[gd * 3 * kH + j], bz = bhh[gd * 3 * kH + kH + j], bn = bhh[gd * 3 * kH + 2 * kH + j];
+    float ar[kH], az[kH], an[kH];
+#pragma unroll
+    for (int i = 0; i < kH; ++i) ar[i] = az[i] = an[i] = 0.f;
+    float sbr = 0.f, sbz = 0.f, sbn_i = 0.f, sbn_h = 0.f;
+    const int64_t row0 = valid ? seq_row0(geo, seq) : 0;
+    const int64_t gstride = (int64_t)GD * 3 * kH;
+    const int col = (gd / D) * kH + j;
+    // walk the recurrence backwards: forward order was step = rev ? L-1..0 : 0..L-1
+    int step = rev ? 0 : geo.L - 1;
+    const int dstep = rev ? 1 : -1;   // direction of "previous forward step"
+    float dh = 0.f;
+    for (int s = geo.L - 1; s >= 0; --s, step += dstep) {
+        const int64_t row = row0 + (int64_t)step * geo.step_stride;
+        float gr = 0.f, gz = 0.f, gn = 0.f, hp = 0.f, dout = 0.f;
+        if (valid) {
+            const float* g0 = gi + row * gstride + gd * 3 * kH;
+            gr = g0[j]; gz = g0[kH + j]; gn = g0[2 * kH + j];
+            if (s > 0) hp = hs[((row + (int64_t)dstep * geo.step_stride) * GD + gd) * kH + j];
+            dout = dh_in[row * ldd + col];
+        }
+        float hpv[kH];
+        float hr = br, hz = bz, hn = bn;
+#pragma unroll
+        for (int i = 0; i < kH; ++i) {
+            hpv[i] = __shfl_sync(0xffffffffu, hp, i, kH);
+            hr = fmaf(wr[i], hpv[i], hr);
+            hz = fmaf(wz[i], hpv[i], hz);
+            hn = fmaf(wn[i], hpv[i], hn);
+        }
+        const float r = sigmoidf_(gr + hr);
+        const float z = sigmoidf_(gz + hz);
+        const float n = tanhf(gn + r * hn);
+        const float dht = dh + dout;
+        const float dn_pre = dht * (1.f - z) * (1.f - n * n);
+        const float dz_pre = dht * (hp - n) * z * (1.f - z);
+        const float dr_pre = dn_pre * hn * r * (1.f - r);
+        const float dhn = dn_pre * r;
+        if (valid) {
+            float* d0 = dgi + row * gstride + gd * 3 * kH;
+            d0[j] = dr_pre; d0[kH + j] = dz_pre; d0[2 * kH + j] = dn_pre;
+        }
+        sbr += dr_pre; sbz += dz_pre; sbn_i += dn_pre; sbn_h += dhn;
+        float c[kH];
+#pragma unroll
+        for (int i = 0; i < kH; ++i) {
+            ar[i] = fmaf(dr_pre, hpv[i], ar[i]);
+            az[i] = fmaf(dz_pre, hpv[i], az[i]);
+            an[i] = fmaf(dhn, hpv[i], an[i]);
+            c[i] = wr[i] * dr_pre + wz[i] * dz_pre + wn[i] * dhn;
+        }
+        // reduce-scatter c[] over the 16 lanes of the unit: lane i ends with sum_j c_j[i]
+#pragma unroll
+        for (int off = kH / 2, len = kH / 2; off >= 1; off >>= 1, len >>= 1) {
+            const bool upper = (j & off) != 0;
+#pragma unroll
+            for (int t = 0; t < kH / 2; ++t) {
+                if (t < len) {
+                    const float send = upper ? c[t] : c[t + len];
+                    const float keep = upper ? c[t + len] : c[t];
+                    c[t] = keep + __shfl_xor_sync(0xffffffffu, send, off, kH);
+                }
+            }
+        }
+        dh = dht * z + c[0];
+    }
+    __syncthreads();
+    if (valid) {
+#pragma unroll
+        for (int i = 0; i < kH; ++i) {
+            atomicAdd(&sW[(0 * kH + j) * kH + i], ar[i]);
+            atomicAdd(&sW[(1 * kH + j) * kH + i], az[i]);
+            atomicAdd(&sW[(2 * kH + j) * kH + i], an[i]);
+        }
+        atomicAdd(&sB[j], sbr);
+        atomicAdd(&sB[kH + j], sbz);
+        atomicAdd(&sB[2 * kH + j], sbn_i);
+        atomicAdd(&sB[3 * kH + j], sbr);
+        atomicAdd(&sB[4 * kH + j], sbz);
+        atomicAdd(&sB[5 * kH + j], sbn_h);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * kH * kH; i += kGruThreads) atomicAdd(&dwhh[(size_t)gd * 3 * kH * kH + i], sW[i]);
+    for (int i = threadIdx.x; i < 3 * kH; i += kGruThreads) {
+        atomicAdd(&dbih[gd * 3 * kH + i], sB[i]);
+        atomicAdd(&dbhh[gd * 3 * kH + i], sB[3 * kH + i]);
+    }
+}
+
+// seq[row,c] = x[row,c] + sum_d hs[row,(g,d),j];  gsum (optional, row stride ldg) = the GRU sum alone
+__global__ void gru_combine_kernel(const float* __restrict__ x, const float* __restrict__ hs,
+                                   float* __restrict__ seq, float* __restrict__ gsum, int ldg, int64_t M, int G,
+                                   int D) {
+    const int C = G * kH;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * C) return;
+    int64_t row = i / C;
+    int c = (int)(i - row * C);
+    int g = c / kH, j = c - g * kH;
+    float s = 0.f;
+    for (int d = 0; d < D; ++d) s += hs[((row * G + g) * D + d) * kH + j];
+    seq[i] = x[i] + s;
+    if (gsum) gsum[row * ldg + c] = s;
+}
+
+// ------------------------------------------------------------------------------------------
+// Multi-head self-attention core: qkv [rows, 3E] (q | k | v, head h at columns h*16), E = H*16
+// ------------------------------------------------------------------------------------------
+constexpr int kHd = 16;
+constexpr int kAttnThreads = 128;
+
+__global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const float* __restrict__ qkv,
+                                                                float* __restrict__ out, float* __restrict__ lse,
+                                                                SeqGeom geo, int H, float scale) {
+    extern __shared__ __align__(16) float sm[];
+    const int L = geo.L, E = H * kHd;
+    float* Ks = sm;                 // [L][16]
+    float* Vs = sm + (size_t)L * kHd;
+    const int seq = blockIdx.x, h = blockIdx.y;
+    const int64_t row0 = seq_row0(geo, seq);
+    for (int idx = threadIdx.x; idx < L * kHd; idx += kAttnThreads) {
+        int t = idx / kHd, d = idx - t * kHd;
+        const float* r = qkv + (row0 + (int64_t)t * geo.step_stride) * 3 * E;
+        Ks[idx] = r[E + h * kHd + d];
+        Vs[idx] = r[2 * E + h * kHd + d];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < L; i += kAttnThreads) {
+        const int64_t row = row0 + (int64_t)i * geo.step_stride;
+        float q[kHd], acc[kHd];
+#pragma unroll
+        for (int d = 0; d < kHd; ++d) {
+            q[d] = qkv[row * 3 * E + h * kHd + d] * scale;
+            acc[d] = 0.f;
+        }
+        float m = -INFINITY, l = 0.f;
+        for (int t = 0; t < L; ++t) {
+            const float4* k4 = reinterpret_cast<const float4*>(Ks + t * kHd);
+            float s = 0.f;
+#pragma unroll
+            for (int d4 = 0; d4 < kHd / 4; ++d4) {
+                float4 kk = k4[d4];
+                s += q[4 * d4] * kk.x + q[4 * d4 + 1] * kk.y + q[4 * d4 + 2] * kk.z + q[4 * d4 + 3] * kk.w;
+            }
+            const float mn = fmaxf(m, s);
+            const float corr = expf(m - mn);
+            const float pr = expf(s - mn);
+            l = l * corr + pr;
+            const float4* v4 = reinterpret_cast<const float4*>(Vs + t * kHd);
+#pragma unroll
+            for (int d4 = 0; d4 < kHd / 4; ++d4) {
+                float4 vv = v4[d4];
+                acc[4 * d4] = acc[4 * d4] * corr + pr * vv.x;
+                acc[4 * d4 + 1] = acc[4 * d4 + 1] * corr + pr * vv.y;
+                acc[4 * d4 + 2] = acc[4 * d4 + 2] * corr + pr * vv.z;
+                acc[4 * d4 + 3] = acc[4 * d4 + 3] * corr + pr * vv.w;
+            }
+            m = mn;
+        }
+        const float inv = 1.f / l;
+#pragma unroll
+        for (int d = 0; d < kHd; ++d) out[row * E + h * kHd + d] = acc[d] * inv;
+        lse[row * H + h] = m + logf(l);
+    }
+}
+
+__global__ void __launch_bounds__(kAttnThreads) attn_bwd_kernel(const float* __restrict__ qkv,
+                                                                const float* __restrict__ out,
+                                                                const float* __restrict__ lse,
+                                                                const float* __restrict__ dout,
+                                                                float* __restrict__ dqkv, SeqGeom geo, int H,
+                                                                float scale) {
+    extern __shared__ __align__(16) float sm[];
+    const int L = geo.L, E = H * kHd;
+    float* Qs = sm;                          // [L][16] (pre-scaled)
+    float* Ks = Qs + (size_t)L * kHd;
+    float* Vs = Ks + (size_t)L * kHd;
+    float* dOs = Vs + (size_t)L * kHd;
+    float* Ls = dOs + (size_t)L * kHd;       // [L] log-sum-exp
+    float* Ds = Ls + L;                      // [L] rowsum(dO * O)
+    const int seq = blockIdx.x, h = blockIdx.y;
+    const int64_t row0 = seq_row0(geo, seq);
+    for (int idx = threadIdx.x; idx < L * kHd; idx += kAttnThreads) {
+        int t = idx / kHd, d = idx - t * kHd;
+        const int64_t row = row0 + (int64_t)t * geo.step_stride;
+        const float* r = qkv + row * 3 * E;
+        Qs[idx] = r[h * kHd + d] * scale;
+        Ks[idx] = r[E + h * kHd + d];
+        Vs[idx] = r[2 * E + h * kHd + d];
+        dOs[idx] = dout[row * E + h * kHd + d];
+    }
+    for (int t = threadIdx.x; t < L; t += kAttnThreads) {
+        const int64_t row = row0 + (int64_t)t * geo.step_stride;
+        float dsum = 0.f;
+#pragma unroll
+        for (int d = 0; d < kHd; ++d) dsum += dout[row * E + h * kHd + d] * out[row * E + h * kHd + d];
+        Ds[t] = dsum;
+        Ls[t] = lse[row * H + h];
+    }
+    __syncthreads();
+    // pass A: one query per thread -> dQ
+    for (int i = threadIdx.x; i < L; i += kAttnThreads) {
+        float q[kHd], go[kHd], dq[kHd];
+#pragma unroll
+        for (int d = 0; d < kHd; ++d) { q[d] = Qs[i * kHd + d]; go[d] = dOs[i * kHd + d]; dq[d] = 0.f; }
+        const float li = Ls[i], di = Ds[i];
+        for (int t = 0; t < L; ++t) {
+            float s = 0.f, dp = 0.f;
+#pragma unroll
+            for (int d = 0; d < kHd; ++d) { s += q[d] * Ks[t * kHd + d]; dp += go[d] * Vs[t * kHd + d]; }
+            const float ds = expf(s - li) * (dp - di);
+#pragma unroll
+            for (int d = 0; d < kHd; ++d) dq[d] += ds * Ks[t * kHd + d];
+        }
+        const int64_t row = row0 + (int64_t)i * geo.step_stride;
+#pragma unroll
+        for (int d = 0; d < kHd; ++d) dqkv[row * 3 * E + h * kHd + d] = dq[d] * scale;
+    }
+    // pass B: one key per thread -> dK, dV
+    for (int t = threadIdx.x; t < L; t += kAttnThreads) {
+        float k[kHd], v[kHd], dk[kHd], dv[kHd];
+#pragma unroll
+        for (int d = 0; d < kHd; ++d) { k[d] = Ks[t * kHd + d]; v[d] = Vs[t * kHd + d]; dk[d] = dv[d] = 0.f; }
+        for (int i = 0; i < L; ++i) {
+            float s = 0.f, dp = 0.f;
+#pragma unroll
+            for (int d = 0; d < kHd; ++d) { s += Qs[i * kHd + d] * k[d]; dp += dOs[i * kHd + d] * v[d]; }
+            const float pr = expf(s - Ls[i]);
+            const float ds = pr * (dp - Ds[i]);
+#pragma unroll
+            for (int d = 0; d < kHd; ++d) {
+                dv[d] += pr * dOs[i * kHd + d];
+                dk[d] += ds * Qs[i * kHd + d];   // Qs is pre-scaled, so this already carries `scale`
+            }
+        }
+        const int64_t row = row0 + (int64_t)t * geo.step_stride;
+#pragma unroll
+        for (int d = 0; d < kHd; ++d) {
+            dqkv[row * 3 * E + E + h * kHd + d] = dk[d];
+            dqkv[row * 3 * E + 2 * E + h * kHd + d] = dv[d];
+        }
+    }
+}
+
+__global__ void act_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy, float* __restrict__ dpre,
+                               int64_t n, int act, float slope) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dpre[i] = dy[i] * act_grad_from_out(y[i], act, slope);
+}
+
+bool geom_ok(SeqGeom& g, int64_t nseq, int64_t L, int64_t inner, int64_t outer_stride, int64_t inner_stride,
+             int64_t step_stride) {
+    if (nseq <= 0 || L <= 0 || inner <= 0 || nseq >= (1LL << 31) || L >= (1 << 20)) return false;
+    g.nseq = (int)nseq; g.L = (int)L; g.inner = (int)inner;
+    g.outer_stride = outer_stride; g.inner_stride = inner_stride; g.step_stride = step_stride;
+    return true;
+}
+
+}  // namespace
+
+LCT_API int lct_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean,
+                              float* rstd, int64_t M, int64_t C, float eps, cudaStream_t st) {
+    if (!x || !gamma || !beta || !y || !mean || !rstd || M <= 0 || C <= 0 || C > 32 * kLnMaxPerLane) return LCT_EINVAL;
+    ln_fwd_kernel<<<(unsigned)ceil_div64(M * 32, 256), 256, 0, st>>>(x, gamma, beta, y, mean, rstd, (int)M, (int)C, eps);
+    LCT_RETURN_IF_LAUNCH_FAILED();
+    return 0;
+}
+
+// dx = dres (optional) + LN backward; dgamma/dbeta are accumulated (caller zeroes)
+LCT_API int lct_layernorm_bwd(const float* dy, const float* x, const float* gamma, const float* mean,
+                              const float* rstd, const float* dres, float* dx, float* dgamma, float* dbeta,
+                              int64_t M, int64_t C, cudaStream_t st) {
+    if (!dy || !x || !gamma || !mean || !rstd || !dx || !dgamma || !dbeta || M <= 0 || C <= 0 ||
+        C > 32 * kLnMaxPerLane)
+        return LCT_EINVAL;
+    int64_t blocks = ceil_div64(M * 32, 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    ln_bwd_kernel<<<(unsigned)blocks, 256, 0, st>>>(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, (int)M, (int)C);
+    LCT_RETURN_IF_LAUNCH_FAILED();
+    return 0;
+}
+
+LCT_API int lct_gru_fwd(const float* gi, const float* whh, const float* bhh, float* hs, int64_t nseq, int64_t L,
+                        int64_t GD, int64_t D, int64_t inner, int64_t outer_stride, int64_t inner_stride,
+                        int64_t step_stride, cudaStream_t st) {
+    SeqGeom g;
+    if (!gi || !whh || !bhh || !hs || GD <= 0 || D <= 0 || GD % D || GD >= 65536 ||
+        !geom_ok(g, nseq, L, inner, outer_stride, inner_stride, step_stride))
+        return LCT_EINVAL;
+    dim3 grid((unsigned)ceil_div64(nseq, kUnitsPerCta), (unsigned)GD);
+    gru_fwd_kernel<<<grid, kGruThreads, 0, st>>>(gi, whh, bhh, hs, g, (int)GD, (int)D);
+    LCT_RETURN_IF_LAUNCH_FAILED();
+    return 0;
+}
+
+LCT_API int lct_gru_bwd(const float* gi, const float* hs, const float* whh, const float* bhh, const float* dh_in,
+                        int64_t ldd, float* dgi, float* dwhh, float* dbih, float* dbhh, int64_t nseq, int64_t L,
+                        int64_t GD, int64_t D, int64_t inner, int64_t outer_stride, int64_t inner_stride,
+                        int64_t step_stride, cudaStream_t st) {
+    SeqGeom g;
+    if (!gi || !hs || !whh || !bhh || !dh_in || !dgi || !dwhh || !dbih || !dbhh || GD <= 0 || D <= 0 || GD % D ||
+        GD >= 65536 || !geom_ok(g, nseq, L, inner, outer_stride, inner_stride, step_stride))
+        return LCT_EINVAL;
+    dim3 grid((unsigned)ceil_div64(nseq, kUnitsPerCta), (unsigned)GD);
+    gru_bwd_kernel<<<grid, kGruThreads, 0, st>>>(gi, hs, whh, bhh, dh_in, (int)ldd, dgi, dwhh, dbih, dbhh, g, (int)GD,
+                                                 (int)D);
+    LCT_RETURN_IF_LAUNCH_FAILED();
+    return 0;
+}
+
+LCT_API int lct_gru_combine(const float* x, const float* hs, float* seq, float* gsum, int64_t ldg, int64_t M,
+                            int64_t G, int64_t D, cudaStream_t st) {
+    if (!x || !hs || !seq || M <= 0 || G <= 0 || D <= 0) return LCT_EINVAL;
+    int64_t n = M * G * kH;
+    gru_combine_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(x, hs, seq, gsum, (int)ldg, M, (int)G, (int)D);
+    LCT_RETURN_IF_LAUNCH_FAILED();
+    return 0;
+}
+
+LCT_API int lct_attn_fwd(const float* qkv, float* out, float* lse, int64_t heads, int64_t nseq, int64_t L,
+                         int64_t inner, int64_t outer_stride, int64_t inner_stride, int64_t step_stride,
+                         cudaStream_t st) {
+    SeqGeom g;
+    if (!qkv || !out || !lse || heads <= 0 || heads >= 65536 ||
+        !geom_ok(g, nseq, L, inner, outer_stride, inner_stride, step_stride))
+        return LCT_EINVAL;
+    size_t smem = (size_t)2 * L * kHd * sizeof(float);
+    if (smem > 200 * 1024) return LCT_EUNSUPPORTED;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    dim3 grid((unsigned)nseq, (unsigned)heads);
+    attn_fwd_kernel<<<grid, kAttnThreads, smem, st>>>(qkv, out, lse, g, (int)heads, 1.f / sqrtf((float)kHd));
+    LCT_RETURN_IF_LAUNCH_FAILED();
+    return 0;
+}
+
+LCT_API int lct_attn_bwd(const float* qkv, const float* out, const float* lse, const float* dout, float* dqkv,
+                         int64_t heads, int64_t nseq, int64_t L, int64_t inner, int64_t outer_stride,
+                         int64_t inner_stride, int64_t step_stride, cudaStream_t st) {
+    SeqGeom g;
+    if (!qkv || !out || !lse || !dout || !dqkv || heads <= 0 || heads >= 65536 ||
+        !geom_ok(g, nseq, L, inner, outer_stride, inner_stride, step_stride))
+        return LCT_EINVAL;
+    size_t smem = ((size_t)4 * L * kHd + 2 * L) * sizeof(float);
+    if (smem > 200 * 1024) return LCT_EUNSUPPORTED;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    dim3 grid((unsigned)nseq, (unsigned)heads);
+    attn_bwd_kernel<<<grid, kAttnThreads, smem, st>>>(qkv, out, lse, dout, dqkv, g, (int)heads,
+                                                      1.f / sqrtf((float)kHd));
+    LCT_RETURN_IF_LAUNCH_FAILED();
+    return 0;
+}
+
+// dpre = dy * act'(y) with y the post-activation value
+LCT_API int lct_act_bwd(const float* y, const float* dy, float* dpre, int64_t n, int act, float slope,
+                        cudaStream_t st) {
+    if (!y || !dy || !dpre || n <= 0) return LCT_EINVAL;
+    act_bwd_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(y, dy, dpre, n, act, slope);
+    LCT_RETURN_IF_LAUNCH_FAILED();
+    return 0;
+}

@@ -1,0 +1,92 @@
+"""One waveform sub-discriminator (a PeriodDiscriminator or a ScaleDiscriminator conv stack) as a
+single autograd node: weight-norm -> grouped strided conv -> bias -> LeakyReLU per layer,
+returning every (post-activation) feature map like the reference does
+(models/discriminators.py:69-103, :199-224).
+
+Backward, per layer from the top: the data-gradient kernel of layer i+1 adds the
+feature-matching gradient that arrived for map i and multiplies by LeakyReLU'(map i) in its
+epilogue, so the pre-activation gradient of every layer is produced exactly once and feeds both
+the weight-gradient and the next data-gradient kernel.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import torch
+
+from . import ops
+
+LRELU_SLOPE = 0.2
+
+# (kernel, stride, padding, groups) per conv; the last entry is conv_post (no activation)
+LayerSpec = Tuple[int, int, int, int]
+
+
+class ConvStackFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x4, specs: Sequence[LayerSpec], skip_param_grads: bool, *params):
+        """x4: [B, 1, L, P]; params: (bias, weight_g, weight_v) per layer.  Returns all feature maps."""
+        if not x4.is_cuda:
+            raise RuntimeError("lctgan discriminators are CUDA only (sm_100a); there is no CPU fallback")
+        n = len(specs)
+        assert len(params) == 3 * n
+        x4 = x4.contiguous()
+        fmaps: List[torch.Tensor] = []
+        weights: List[torch.Tensor] = []
+        h = x4
+        for i, (k, s, pad, g) in enumerate(specs):
+            bias, wg, wv = params[3 * i], params[3 * i + 1], params[3 * i + 2]
+            w = ops.weight_norm_fwd(wg.contiguous(), wv.contiguous())
+            last = i == n - 1
+            h = ops.conv1d_fwd(h, w, bias, g, s, pad, act=ops.ACT_NONE if last else ops.ACT_LRELU, slope=LRELU_SLOPE)
+            fmaps.append(h)
+            weights.append(w)
+        ctx.specs = list(specs)
+        ctx.skip_param_grads = skip_param_grads
+        ctx.save_for_backward(x4, *fmaps, *weights, *params)
+        return tuple(fmaps)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        specs = ctx.specs
+        n = len(specs)
+        saved = ctx.saved_tensors
+        x4 = saved[0]
+        fmaps = saved[1:1 + n]
+        weights = saved[1 + n:1 + 2 * n]
+        params = saved[1 + 2 * n:]
+        need_x = ctx.needs_input_grad[0]
+        need_p = [ctx.needs_input_grad[3 + j] for j in range(3 * n)]
+        want_params = any(need_p) and not (ctx.skip_param_grads and need_x)
+        gparams: List = [None] * (3 * n)
+        gouts = [g.contiguous() if g is not None else None for g in gouts]
+
+        dpre = gouts[n - 1]      # conv_post has no activation
+        gx = None
+        for i in range(n - 1, -1, -1):
+            k, s, pad, g = specs[i]
+            inp = x4 if i == 0 else fmaps[i - 1]
+            if dpre is not None:
+                if want_params:
+                    dw, db = ops.conv1d_wgrad(inp, dpre, weights[i].shape, g, s, pad, want_bias=True)
+                    dg, dv = ops.weight_norm_bwd(params[3 * i + 1].contiguous(), params[3 * i + 2].contiguous(), dw)
+                    gparams[3 * i], gparams[3 * i + 1], gparams[3 * i + 2] = db, dg, dv
+                if i > 0:
+                    dpre = ops.conv1d_dgrad(dpre, weights[i], inp.shape, g, s, pad, gextra=gouts[i - 1], xact=inp,
+                                            act=ops.ACT_LRELU, slope=LRELU_SLOPE)
+                elif need_x:
+                    gx = ops.conv1d_dgrad(dpre, weights[i], inp.shape, g, s, pad)
+            elif i > 0 and gouts[i - 1] is not None:
+                dpre = ops.act_bwd(inp, gouts[i - 1], ops.ACT_LRELU, LRELU_SLOPE)
+        if want_params:
+            for j in range(3 * n):
+                if gparams[j] is None and need_p[j]:
+                    gparams[j] = torch.zeros_like(params[j])
+                elif not need_p[j]:
+                    gparams[j] = None
+        return (gx, None, None, *gparams)
+
+
+def conv_stack(x4: torch.Tensor, specs: Sequence[LayerSpec], params: Sequence[torch.Tensor],
+               skip_param_grads: bool = False) -> List[torch.Tensor]:
+    return list(ConvStackFn.apply(x4, tuple(specs), skip_param_grads, *params))

@@ -1,0 +1,417 @@
+"""Thin tensor-level wrappers over the C ABI (no autograd).  Each function allocates its outputs
+with torch (memory plumbing only) and enqueues the lctgan kernels on the current stream.
+
+Layouts: spectrograms are physically [B, Tf, F] complex64 (``spec_view`` gives the reference's
+[B, F, Tf] view); generator activations are channels-last [B, T, F, C]; discriminator
+activations are [B, C, L, P].
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from ._lib import call, call_ret
+
+ACT_NONE, ACT_LRELU, ACT_RELU = 0, 1, 2
+
+_TW: Dict[Tuple[int, int], torch.Tensor] = {}
+_ENV: Dict[Tuple[int, int, int, int, int], torch.Tensor] = {}
+
+
+def _dev_index(t: torch.Tensor) -> int:
+    return t.device.index if t.device.index is not None else torch.cuda.current_device()
+
+
+def fft_supported(n_fft: int) -> bool:
+    return bool(call_ret("lct_fft_supported", n_fft))
+
+
+def twiddles(n_fft: int, like: torch.Tensor) -> torch.Tensor:
+    """exp(-2 pi i m / N) table, a pure function of (N, device): cached."""
+    key = (n_fft, _dev_index(like))
+    tw = _TW.get(key)
+    if tw is None:
+        if not fft_supported(n_fft):
+            raise RuntimeError(f"n_fft={n_fft} unsupported (need even, 8..2048, prime factors 2/3/5)")
+        tw = torch.empty(n_fft, 2, device=like.device, dtype=torch.float32)
+        call("lct_fft_twiddles", tw, n_fft)
+        _TW[key] = tw
+    return tw
+
+
+def ola_envelope(window: torch.Tensor, n_fft: int, hop: int, n_frames: int) -> torch.Tensor:
+    """Overlap-added squared window; cached per (window storage, version, geometry)."""
+    key = (window.data_ptr(), window._version, n_fft, hop, n_frames)
+    env = _ENV.get(key)
+    if env is None:
+        if len(_ENV) > 64:
+            _ENV.clear()
+        env = torch.empty(n_fft + hop * (n_frames - 1), device=window.device, dtype=torch.float32)
+        call("lct_ola_envelope", window, env, n_fft, hop, n_frames)
+        _ENV[key] = env
+    return env
+
+
+def spec_view(phys: torch.Tensor) -> torch.Tensor:
+    """[B, Tf, F] physical -> the reference's [B, F, Tf] view (same memory, like torch.stft)."""
+    return phys.transpose(1, 2)
+
+
+def spec_phys(spec: torch.Tensor) -> torch.Tensor:
+    """[B, F, Tf] (any strides) -> contiguous [B, Tf, F]."""
+    p = spec.transpose(1, 2)
+    return p if p.is_contiguous() else p.contiguous()
+
+
+def _check_wave(x: torch.Tensor) -> torch.Tensor:
+    if x.dtype != torch.float32:
+        raise RuntimeError(f"expected float32 waveform, got {x.dtype}")
+    return x if x.is_contiguous() else x.contiguous()
+
+
+# ----------------------------------------------------------------------------- STFT family
+def stft_fwd(x, window, n_fft, hop, want_mag=False, eps=1e-12):
+    x = _check_wave(x)
+    B, T = x.shape
+    Tf, F = 1 + T // hop, n_fft // 2 + 1
+    spec = torch.empty(B, Tf, F, dtype=torch.complex64, device=x.device)
+    mag = torch.empty(B, Tf, F, dtype=torch.float32, device=x.device) if want_mag else None
+    call("lct_stft_fwd", x, window, twiddles(n_fft, x), spec, mag, B, T, n_fft, hop, eps)
+    return spec, mag
+
+
+def stft_bwd(gspec, window, T, n_fft, hop):
+    B, Tf, F = gspec.shape
+    work = torch.empty(B, n_fft + hop * (Tf - 1), dtype=torch.float32, device=gspec.device)
+    gx = torch.empty(B, T, dtype=torch.float32, device=gspec.device)
+    call("lct_stft_bwd", gspec, window, twiddles(n_fft, gspec), work, gx, B, T, n_fft, hop)
+    return gx
+
+
+def istft_fwd(spec, window, n_fft, hop, length, mask_c=None, c=0.3, eps=1e-12):
+    B, Tf, F = spec.shape
+    env = ola_envelope(window, n_fft, hop, Tf)
+    y = torch.empty(B, length, dtype=torch.float32, device=spec.device)
+    call("lct_istft_fwd", spec, mask_c, window, twiddles(n_fft, spec), env, y, B, Tf, n_fft, hop, length, c, eps)
+    return y
+
+
+def istft_bwd(gy, window, n_fft, hop, Tf, xspec=None, mask_c=None, want_gspec=True, c=0.3, eps=1e-12):
+    gy = _check_wave(gy)
+    B, length = gy.shape
+    F = n_fft // 2 + 1
+    env = ola_envelope(window, n_fft, hop, Tf)
+    gspec = torch.empty(B, Tf, F, dtype=torch.complex64, device=gy.device) if want_gspec else None
+    gmask = torch.empty(B, Tf, F, dtype=torch.float32, device=gy.device) if mask_c is not None else None
+    call("lct_istft_bwd", gy, window, twiddles(n_fft, gy), env, gspec, xspec, mask_c, gmask, B, Tf, n_fft, hop,
+         length, c, eps)
+    return gspec, gmask
+
+
+def tf_features_fwd(noisy, clean, window, n_fft, hop, c=0.3, gamma=1e-12, eps=1e-12, want_specs=False):
+    noisy, clean = _check_wave(noisy), _check_wave(clean)
+    B, T = noisy.shape
+    Tf, F = 1 + T // hop, n_fft // 2 + 1
+    mk = lambda dt: torch.empty(B, Tf, F, dtype=dt, device=noisy.device)
+    nmag, irm, nmagc = mk(torch.float32), mk(torch.float32), mk(torch.float32)
+    ns = mk(torch.complex64) if want_specs else None
+    cs = mk(torch.complex64) if want_specs else None
+    call("lct_tf_features_fwd", noisy, clean, window, twiddles(n_fft, noisy), nmag, irm, nmagc, ns, cs, B, T, n_fft,
+         hop, c, gamma, eps)
+    return nmag, irm, nmagc, ns, cs
+
+
+def mrstft_sums(y_hat, y, window, n_fft, hop, acc, eps=1e-12):
+    B, T = y_hat.shape
+    call("lct_mrstft_sums", y_hat, y, window, twiddles(n_fft, y_hat), acc, B, T, n_fft, hop, eps)
+
+
+def mrstft_grad_spec(spec_hat, spec_ref, k_mag, k_cplx, upstream=None, eps=1e-12):
+    g = torch.empty_like(spec_hat)
+    call("lct_mrstft_grad_spec", spec_hat, spec_ref, g, spec_hat.numel(), eps, k_mag, k_cplx, upstream)
+    return g
+
+
+# ----------------------------------------------------------------------------- spectral elementwise
+def magnitude_fwd(spec, power=1.0, eps=1e-12):
+    mag = torch.empty(spec.shape, dtype=torch.float32, device=spec.device)
+    call("lct_magnitude_fwd", spec, mag, spec.numel(), power, eps)
+    return mag
+
+
+def magnitude_bwd(spec, gmag, power=1.0, eps=1e-12):
+    g = torch.empty_like(spec)
+    call("lct_magnitude_bwd", spec, gmag, g, spec.numel(), power, eps)
+    return g
+
+
+def powclamp_fwd(x, e, eps=1e-12):
+    y = torch.empty_like(x)
+    call("lct_powclamp_fwd", x, y, x.numel(), e, eps)
+    return y
+
+
+def powclamp_bwd(x, gy, e, eps=1e-12):
+    gx = torch.empty_like(x)
+    call("lct_powclamp_bwd", x, gy, gx, x.numel(), e, eps)
+    return gx
+
+
+def irm_fwd(clean_spec, noisy_spec, c=0.3, gamma=1e-12, eps=1e-12):
+    out = torch.empty(clean_spec.shape, dtype=torch.float32, device=clean_spec.device)
+    call("lct_irm_fwd", clean_spec, noisy_spec, out, clean_spec.numel(), c, gamma, eps)
+    return out
+
+
+def apply_mask_fwd(spec, mask, compressed, c=0.3, eps=1e-12):
+    out = torch.empty_like(spec)
+    call("lct_apply_mask_fwd", spec, mask, out, spec.numel(), int(compressed), c, eps)
+    return out
+
+
+def apply_mask_bwd(spec, mask, gout, compressed, want_gmask=True, want_gspec=False, c=0.3, eps=1e-12):
+    gmask = torch.empty_like(mask) if want_gmask else None
+    gspec = torch.empty_like(spec) if want_gspec else None
+    call("lct_apply_mask_bwd", spec, mask, gout, gmask, gspec, spec.numel(), int(compressed), c, eps)
+    return gmask, gspec
+
+
+# ----------------------------------------------------------------------------- discriminator pieces
+def reflect_pad_right_fwd(x, pad):
+    B, T = x.shape
+    y = torch.empty(B, T + pad, dtype=torch.float32, device=x.device)
+    call("lct_reflect_pad_right_fwd", x, y, B, T, pad)
+    return y
+
+
+def reflect_pad_right_bwd(gy, T, pad):
+    B = gy.shape[0]
+    gx = torch.empty(B, T, dtype=torch.float32, device=gy.device)
+    call("lct_reflect_pad_right_bwd", gy, gx, B, T, pad)
+    return gx
+
+
+def avgpool4_fwd(x):
+    B, L = x.shape
+    y = torch.empty(B, L // 2 + 1, dtype=torch.float32, device=x.device)
+    call("lct_avgpool4_fwd", x, y, B, L)
+    return y
+
+
+def avgpool4_bwd(gy, L):
+    B = gy.shape[0]
+    gx = torch.empty(B, L, dtype=torch.float32, device=gy.device)
+    call("lct_avgpool4_bwd", gy, gx, B, L)
+    return gx
+
+
+def weight_norm_fwd(g, v):
+    cout = v.shape[0]
+    row = v.numel() // cout
+    w = torch.empty_like(v)
+    call("lct_weight_norm_fwd", g, v, w, None, cout, row)
+    return w
+
+
+def weight_norm_bwd(g, v, dw):
+    cout = v.shape[0]
+    row = v.numel() // cout
+    dg = torch.empty_like(g)
+    dv = torch.empty_like(v)
+    call("lct_weight_norm_bwd", g, v, dw, dg, dv, cout, row)
+    return dg, dv
+
+
+def conv_out_len(lin, k, s, pad):
+    return (lin + 2 * pad - k) // s + 1
+
+
+def conv1d_fwd(x, w, bias, groups, stride, pad, act=ACT_NONE, slope=0.2):
+    """x [B,Cin,Lin,P], w [Cout,Cin/G,K] (any trailing singleton dims) -> [B,Cout,Lout,P]."""
+    B, Cin, Lin, P = x.shape
+    Cout, K = w.shape[0], w.shape[2]
+    Lout = conv_out_len(Lin, K, stride, pad)
+    y = torch.empty(B, Cout, Lout, P, dtype=torch.float32, device=x.device)
+    call("lct_conv1d_fwd", x, w, bias, y, B, Cin, Cout, groups, K, stride, pad, Lin, P, act, slope)
+    return y
+
+
+def conv1d_dgrad(dy, w, x_shape, groups, stride, pad, gextra=None, xact=None, act=ACT_NONE, slope=0.2):
+    B, Cin, Lin, P = x_shape
+    Cout, K = w.shape[0], w.shape[2]
+    dx = torch.empty(B, Cin, Lin, P, dtype=torch.float32, device=dy.device)
+    call("lct_conv1d_dgrad", dy, w, dx, gextra, xact, B, Cin, Cout, groups, K, stride, pad, Lin, P, act, slope)
+    return dx
+
+
+def conv1d_wgrad(x, dy, w_shape, groups, stride, pad, want_bias=True):
+    B, Cin, Lin, P = x.shape
+    Cout, K = w_shape[0], w_shape[2]
+    dw = torch.zeros(w_shape, dtype=torch.float32, device=x.device)
+    db = torch.zeros(Cout, dtype=torch.float32, device=x.device) if want_bias else None
+    call("lct_conv1d_wgrad", x, dy, dw, db, B, Cin, Cout, groups, K, stride, pad, Lin, P)
+    return dw, db
+
+
+# ----------------------------------------------------------------------------- generator pieces
+def gemm(A, B, C, M, N, K, lda, ldb, ldc, ta=False, tb=False, bias=None, act=ACT_NONE, slope=0.2, alpha=1.0,
+         accumulate=False, res=None, ldr=0, out2=None, ldo=0, ksplit=1, nbatch=1, a_div=1, b_div=1, sA=0, sB=0, sC=0,
+         sBias=0, sRes=0, sOut2=0, a_off=0, b_off=0, c_off=0):
+    """Raw strided GEMM on flat fp32 buffers; *_off are element offsets into A/B/C."""
+    a = A.view(-1)[a_off:] if a_off else A
+    b = B.view(-1)[b_off:] if b_off else B
+    c = C.view(-1)[c_off:] if c_off else C
+    call("lct_gemm", _raw(a), _raw(b), _raw(c), bias, res, out2, M, N, K, lda, ldb, ldc, ldr, ldo, int(ta), int(tb),
+         act, slope, alpha, int(accumulate), ksplit, nbatch, a_div, b_div, sA, sB, sC, sBias, sRes, sOut2)
+
+
+def _raw(t):
+    if t is None:
+        return None
+    if not t.is_cuda or t.dtype != torch.float32:
+        raise RuntimeError("lctgan gemm operands must be CUDA float32")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def gemm_free_add(a, b, out, M, N, ldb):
+    """out[M,N] = a[M,N] + b[:, :N] where b has row stride ldb."""
+    call("lct_add2d", a, N, _raw(b), ldb, out, N, M, N)
+
+
+def colsum(X, out, M, N, ld):
+    call("lct_colsum", _raw(X), out, M, N, ld)
+
+
+def layernorm_fwd(x, gamma, beta, eps=1e-5):
+    C = x.shape[-1]
+    M = x.numel() // C
+    y = torch.empty_like(x)
+    mean = torch.empty(M, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(M, dtype=torch.float32, device=x.device)
+    call("lct_layernorm_fwd", x, gamma, beta, y, mean, rstd, M, C, eps)
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, dres=None):
+    C = x.shape[-1]
+    M = x.numel() // C
+    dx = torch.empty_like(x)
+    call("lct_layernorm_bwd", dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, M, C)
+    return dx
+
+
+def act_bwd(y, dy, act=ACT_LRELU, slope=0.2):
+    d = torch.empty_like(y)
+    call("lct_act_bwd", y, dy, d, y.numel(), act, slope)
+    return d
+
+
+def gconv(x, w, bias, out_tf, cd, transposed, act=ACT_NONE, slope=0.2, gmul=None, gact=ACT_NONE, gslope=0.2):
+    """x [B,Ti,Fi,Cs] -> [B,To,Fo,Cd] with (To,Fo) = out_tf."""
+    B, Ti, Fi, Cs = x.shape
+    To, Fo = out_tf
+    out = torch.empty(B, To, Fo, cd, dtype=torch.float32, device=x.device)
+    call("lct_gconv", x, w, bias, out, gmul, int(transposed), B, Ti, Fi, Cs, To, Fo, cd, act, slope, gact, gslope)
+    return out
+
+
+def gconv_wgrad(S, Lg, w_shape):
+    B, Ts, Fs, Ca = S.shape
+    _, Tl, Fl, Cc = Lg.shape
+    dW = torch.zeros(w_shape, dtype=torch.float32, device=S.device)
+    call("lct_gconv_wgrad", S, Lg, dW, B, Ts, Fs, Ca, Tl, Fl, Cc)
+    return dW
+
+
+def skip_add_fwd(h, mag, w, bias):
+    B, Th, Fh, C = h.shape
+    _, Tm, Fm = mag.shape
+    out = torch.empty(B, min(Th, Tm), min(Fh, Fm), C, dtype=torch.float32, device=h.device)
+    call("lct_skip_add_fwd", h, mag, w, bias, out, B, Th, Fh, Tm, Fm, C)
+    return out
+
+
+def skip_add_bwd(g, mag, h_shape, dw, db, want_dh=True):
+    B, Th, Fh, C = h_shape
+    _, Tm, Fm = mag.shape
+    same = (g.shape[1] == Th and g.shape[2] == Fh)
+    dh = None
+    if want_dh and not same:
+        dh = torch.empty(h_shape, dtype=torch.float32, device=g.device)
+    call("lct_skip_add_bwd", g, mag, dh, dw, db, B, Th, Fh, Tm, Fm, C)
+    if want_dh and same:
+        dh = g
+    return dh
+
+
+def final_mask_fwd(y, T, F, use_sigmoid=True):
+    B, Ty, Fy = y.shape[0], y.shape[1], y.shape[2]
+    mask = torch.empty(B, T, F, dtype=torch.float32, device=y.device)
+    call("lct_final_mask_fwd", y, mask, B, Ty, Fy, T, F, int(use_sigmoid))
+    return mask
+
+
+def final_mask_bwd(y, mask, gmask, use_sigmoid=True, act=ACT_RELU, slope=0.0):
+    B, Ty, Fy = y.shape[0], y.shape[1], y.shape[2]
+    _, T, F = mask.shape
+    dpre = torch.empty_like(y)
+    call("lct_final_mask_bwd", y, mask, gmask, dpre, B, Ty, Fy, T, F, int(use_sigmoid), act, slope)
+    return dpre
+
+
+# ----------------------------------------------------------------------------- multi-tensor losses
+OP_SQ_CONST, OP_SQ_DIFF, OP_ABS_DIFF, OP_RELU_AFFINE, OP_SUM = 0, 1, 2, 3, 4
+
+
+def _flat_ok(t):
+    if not t.is_cuda or t.dtype != torch.float32:
+        raise RuntimeError("loss inputs must be CUDA float32 tensors (no CPU fallback)")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _ptr_array(ts):
+    return (ctypes.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+
+
+def mt_reduce(a: Sequence[torch.Tensor], b: Optional[Sequence[torch.Tensor]], scale: Sequence[float], op: int,
+              k0: float = 0.0, k1: float = 0.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[0] += sum_i scale_i * sum op(a_i, b_i).  Returns the 1-element accumulator."""
+    a = [_flat_ok(t) for t in a]
+    b = [_flat_ok(t) for t in b] if b is not None else None
+    if out is None:
+        out = torch.zeros(1, dtype=torch.float32, device=a[0].device)
+    maxseg = call_ret("lct_mt_max_segments")
+    for s in range(0, len(a), maxseg):
+        aa = a[s:s + maxseg]
+        n = (ctypes.c_int64 * len(aa))(*[t.numel() for t in aa])
+        sc = (ctypes.c_float * len(aa))(*scale[s:s + maxseg])
+        call("lct_mt_reduce", _ptr_array(aa), _ptr_array(b[s:s + maxseg]) if b is not None else None, n, sc, len(aa),
+             op, k0, k1, out)
+    return out
+
+
+def mt_grad(a: Sequence[torch.Tensor], b: Optional[Sequence[torch.Tensor]], scale: Sequence[float], op: int,
+            k0: float = 0.0, k1: float = 0.0, upstream: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
+    a = [_flat_ok(t) for t in a]
+    b = [_flat_ok(t) for t in b] if b is not None else None
+    g = [torch.empty_like(t) for t in a]
+    maxseg = call_ret("lct_mt_max_segments")
+    for s in range(0, len(a), maxseg):
+        aa = a[s:s + maxseg]
+        n = (ctypes.c_int64 * len(aa))(*[t.numel() for t in aa])
+        sc = (ctypes.c_float * len(aa))(*scale[s:s + maxseg])
+        call("lct_mt_grad", _ptr_array(aa), _ptr_array(b[s:s + maxseg]) if b is not None else None,
+             _ptr_array(g[s:s + maxseg]), n, sc, len(aa), op, k0, k1, upstream)
+    return g
+
+
+def mt_copy(srcs: Sequence[torch.Tensor], dsts: Sequence[torch.Tensor]) -> None:
+    """dst_i <- src_i (flat), one launch per 64 tensors."""
+    maxseg = call_ret("lct_mt_max_segments")
+    for s in range(0, len(srcs), maxseg):
+        ss, dd = srcs[s:s + maxseg], dsts[s:s + maxseg]
+        n = (ctypes.c_int64 * len(ss))(*[t.numel() for t in ss])
+        call("lct_mt_copy", _ptr_array(ss), _ptr_array(dd), n, len(ss))

@@ -1,0 +1,150 @@
+"""Multi-period and multi-scale waveform discriminators with the reference's API
+(jqshang/LCT-GAN models/discriminators.py), executing on the lctgan sm_100a kernels.
+
+Parameters live in ``weight_norm(nn.Conv2d/Conv1d)`` containers built in the reference's order, so
+``state_dict`` keys (``discriminators.i.convs.j.{bias,weight_g,weight_v}``, ``conv_post.*``), shapes,
+iteration order and seeded initial values are identical; the containers' forward (and the
+weight-norm pre-hook) is never invoked - each sub-discriminator is one autograd node
+(``lctgan.disc_impl.ConvStackFn``) that returns every feature map like the reference.
+
+Reference anchors: PeriodDiscriminator :9-103, MultiPeriodDiscriminator :106-147,
+ScaleDiscriminator :150-224, MultiScaleDiscriminator :227-286.
+"""
+from typing import List, Tuple
+
+import torch
+import torch.nn as nn
+from torch.nn.utils import spectral_norm, weight_norm
+
+from lctgan import functional as LF
+from lctgan.disc_impl import conv_stack
+
+# (out_channels, kernel, stride, groups)
+_PERIOD_LAYERS = ((32, 5, 3, 1), (128, 5, 3, 4), (512, 5, 3, 16), (1024, 5, 3, 64), (1024, 5, 1, 64))
+_SCALE_LAYERS = ((16, 15, 1, 1), (64, 41, 4, 4), (256, 41, 4, 16), (1024, 41, 4, 64), (1024, 41, 4, 256),
+                 (1024, 5, 1, 1))
+
+
+def _stack_params(mod: nn.Module) -> List[torch.Tensor]:
+    """(bias, weight_g, weight_v) of every conv then conv_post - the parameter order of the reference."""
+    out: List[torch.Tensor] = []
+    for conv in list(mod.convs) + [mod.conv_post]:
+        out += [conv.bias, conv.weight_g, conv.weight_v]
+    return out
+
+
+class _SubDiscriminator(nn.Module):
+    #: when True, the (discarded) discriminator weight gradients of the generator step are not computed
+    #: if the input waveform itself requires grad.  Default False = the reference's exact behaviour.
+    skip_param_grads_when_input_requires_grad = False
+
+    def _run(self, x4: torch.Tensor) -> Tuple[torch.Tensor, List[torch.Tensor]]:
+        if self._spectral:
+            raise RuntimeError("use_spectral_norm=True is not supported by the lctgan kernels "
+                               "(the reference's train.py never enables it)")
+        fmaps = conv_stack(x4, self._specs, _stack_params(self), self.skip_param_grads_when_input_requires_grad)
+        return fmaps[-1], fmaps
+
+
+class PeriodDiscriminator(_SubDiscriminator):
+    """[B, T] or [B, 1, T] -> (logits [B, 1, H, P], [6 feature maps]); the waveform is right-reflect-padded
+    to a multiple of the period and folded to [B, 1, T/P, P]."""
+
+    def __init__(self, period: int, use_spectral_norm: bool = False):
+        super().__init__()
+        self.period = period
+        self._spectral = bool(use_spectral_norm)
+        norm_f = spectral_norm if use_spectral_norm else weight_norm
+        convs, in_ch, specs = [], 1, []
+        for out_ch, k, s, g in _PERIOD_LAYERS:
+            convs.append(norm_f(nn.Conv2d(in_ch, out_ch, kernel_size=(k, 1), stride=(s, 1), padding=(k // 2, 0),
+                                          groups=g)))
+            specs.append((k, s, k // 2, g))
+            in_ch = out_ch
+        self.convs = nn.ModuleList(convs)
+        self.conv_post = norm_f(nn.Conv2d(in_ch, 1, kernel_size=(3, 1), stride=(1, 1), padding=(1, 0)))
+        specs.append((3, 1, 1, 1))
+        self._specs = tuple(specs)
+        self.activation = nn.LeakyReLU(0.2, inplace=True)
+
+    def forward(self, x: torch.Tensor) -> Tuple[torch.Tensor, List[torch.Tensor]]:
+        if x.dim() == 2:
+            x = x.unsqueeze(1)
+        B, C, T = x.shape
+        assert C == 1, "PeriodDiscriminator expects shape [B, 1, T] or [B, T]."
+        x2 = x.reshape(B, T)
+        if T % self.period != 0:
+            pad = self.period - (T % self.period)
+            x2 = LF.ReflectPadRightFn.apply(x2, pad)
+            T = T + pad
+        return self._run(x2.reshape(B, 1, T // self.period, self.period))
+
+
+class MultiPeriodDiscriminator(nn.Module):
+    def __init__(self, periods: List[int] = (2, 3, 5, 7, 11), use_spectral_norm: bool = False):
+        super().__init__()
+        self.discriminators = nn.ModuleList(
+            [PeriodDiscriminator(p, use_spectral_norm=use_spectral_norm) for p in periods])
+
+    def forward(self, x: torch.Tensor) -> Tuple[List[torch.Tensor], List[List[torch.Tensor]]]:
+        logits_list: List[torch.Tensor] = []
+        fmaps_list: List[List[torch.Tensor]] = []
+        for disc in self.discriminators:
+            logits, fmaps = disc(x)
+            logits_list.append(logits)
+            fmaps_list.append(fmaps)
+        return logits_list, fmaps_list
+
+
+class ScaleDiscriminator(_SubDiscriminator):
+    """[B, T] or [B, 1, T] -> (logits [B, 1, L], [7 feature maps])."""
+
+    def __init__(self, use_spectral_norm: bool = False):
+        super().__init__()
+        self._spectral = bool(use_spectral_norm)
+        norm_f = spectral_norm if use_spectral_norm else weight_norm
+        convs, in_ch, specs = [], 1, []
+        for out_ch, k, s, g in _SCALE_LAYERS:
+            convs.append(norm_f(nn.Conv1d(in_ch, out_ch, kernel_size=k, stride=s, padding=k // 2, groups=g)))
+            specs.append((k, s, k // 2, g))
+            in_ch = out_ch
+        self.convs = nn.ModuleList(convs)
+        self.conv_post = norm_f(nn.Conv1d(in_ch, 1, kernel_size=3, stride=1, padding=1))
+        specs.append((3, 1, 1, 1))
+        self._specs = tuple(specs)
+        self.activation = nn.LeakyReLU(0.2, inplace=True)
+
+    def forward(self, x: torch.Tensor) -> Tuple[torch.Tensor, List[torch.Tensor]]:
+        if x.dim() == 2:
+            x = x.unsqueeze(1)
+        B, C, T = x.shape
+        assert C == 1, "ScaleDiscriminator expects shape [B, 1, T] or [B, T]."
+        logits, fmaps = self._run(x.reshape(B, 1, T, 1))
+        # the kernels carry a trailing period axis of 1; hand back the reference's [B, C, L] shapes
+        fmaps = [f.squeeze(-1) for f in fmaps]
+        return fmaps[-1], fmaps
+
+
+class MultiScaleDiscriminator(nn.Module):
+    def __init__(self, num_scales: int = 3, use_spectral_norm: bool = False):
+        super().__init__()
+        assert num_scales >= 1, "num_scales must be >= 1"
+        self.num_scales = num_scales
+        self.discriminators = nn.ModuleList(
+            [ScaleDiscriminator(use_spectral_norm=(use_spectral_norm and i == 0)) for i in range(num_scales)])
+        self.avg_pool = nn.AvgPool1d(kernel_size=4, stride=2, padding=2, count_include_pad=False)
+
+    def forward(self, x: torch.Tensor) -> Tuple[List[torch.Tensor], List[List[torch.Tensor]]]:
+        if x.dim() == 2:
+            x = x.unsqueeze(1)
+        B, C, T = x.shape
+        x_scale = x.reshape(B, T) if C == 1 else x
+        logits_list: List[torch.Tensor] = []
+        fmaps_list: List[List[torch.Tensor]] = []
+        for i, disc in enumerate(self.discriminators):
+            logits, fmaps = disc(x_scale if x_scale.dim() == 3 else x_scale.unsqueeze(1))
+            logits_list.append(logits)
+            fmaps_list.append(fmaps)
+            if i + 1 < len(self.discriminators):   # the reference pools once more and discards the result
+                x_scale = LF.AvgPool4Fn.apply(x_scale)
+        return logits_list, fmaps_list
