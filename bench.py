@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py -- LCT-GAN adversarial training step on B200 (metric of BASELINE.json: train samples/s,
+2 s @ 16 kHz segments).
+
+    python bench.py --gpus 1 --steps 20 --warmup 5            # this framework (lctgan sm_100a kernels)
+    python bench.py --impl reference --steps 3 --warmup 1     # the reference's CPU path (oracle port), host cores
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" is one full D+G iteration of the reference's train_one_epoch loop body (train.py:165-249)
+on one synthetic batch of 8 segments per GPU (configs[2] of BASELINE.json; weak scaling).  Rank 0
+prints ONE JSON line.  See DESIGN.md section "Measurement" for the definition of every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (os.path.join(ROOT, "lct-gan_b200"), ROOT):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "train samples/sec (2 s @16 kHz)"
+UNIT = "samples/s"
+BATCH = 8
+SEGMENT = 32000
+WORKLOAD = "LCT-GAN D+G training step, batch 8 per GPU, 2.0 s @ 16 kHz segments, LS loss, reference hyperparameters (BASELINE configs[2])"
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return {"hbm": float(p["hbm_gbs"]), "tensor": float(p["bf16_tflops"]), "tensor_sustained":
+                float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "src": "measured"}
+    except Exception:
+        return {"hbm": 6650.0, "tensor": 1590.0, "tensor_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# the reference arm / CPU baseline: the oracle port of the reference's step on the host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_steps(steps, warmup, budget_s=150.0, batch=BATCH):
+    """Time `steps` D+G steps of the CPU oracle (reference algorithm, torch CPU ops, all host threads).
+    Returns (samples_per_s, ms_per_step, sample_batch, cores)."""
+    import torch
+    from oracle import lct_oracle as O
+    from lctgan.training import build_models
+    cores = torch.get_num_threads()
+    enh, mpd, msd, _tf, _mr, _g, _d = build_models("cpu", gan_seed=42)
+    cp = lambda m: {k: v.detach().clone() for k, v in m.state_dict().items()}
+    st = O.StepState(cp(enh), cp(mpd), cp(msd), order_g=[k for k, _ in enh.named_parameters()],
+                     order_d=([k for k, _ in mpd.named_parameters()], [k for k, _ in msd.named_parameters()]))
+    wins = [O.hann_window(n) for n in O.MR_FFT_SIZES]
+    b = batch
+    noisy, clean = O.synthetic_batch(b, SEGMENT, seed=1234)
+    t0 = time.perf_counter()
+    O.train_step(st, noisy, clean, wins, gan_loss="ls", aten_gru=True)     # first (cold) step sizes the sample
+    t_first = time.perf_counter() - t0
+    while b > 1 and (steps + max(warmup - 1, 0)) * t_first * (b / batch) > budget_s:
+        b //= 2
+    noisy, clean = noisy[:b], clean[:b]
+    for _ in range(max(warmup - 1, 0)):
+        O.train_step(st, noisy, clean, wins, gan_loss="ls", aten_gru=True)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.train_step(st, noisy, clean, wins, gan_loss="ls", aten_gru=True)
+    dt = (time.perf_counter() - t0) / steps
+    return b / dt, dt * 1e3, b, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sps, ms, b, cores = cpu_reference_steps(args.steps, args.warmup)
+    sample = f"{args.steps} timed D+G steps of {b} x 2 s segments (batch {BATCH} workload" + \
+             (", bounded to fit the time budget)" if b != BATCH else ")")
+    line = {"impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "device": "host CPU"},
+            "cpu_baseline": {"value": sps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# roofline of the dominant kernel, timed live
+# --------------------------------------------------------------------------------------------------
+def measure_roofline(dev, peaks):
+    """Dominant kernel of the step: the dense 1024->1024, k=5 convolution of the scale discriminators
+    (MSD convs.5, the one layer above the ridge: SURVEY.md section 8a D3).  Timed alone with CUDA
+    events on the launching stream, L2 flushed between launches."""
+    import torch
+    from lctgan import ops
+    B, L, C, K = BATCH, 125, 1024, 5
+    g = torch.Generator(device="cpu").manual_seed(0)
+    x = torch.randn(B, C, L, 1, generator=g).to(dev)
+    w = (torch.randn(C, C, K, generator=g) / (C * K) ** 0.5).to(dev)
+    bias = torch.zeros(C, device=dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    flops = 2.0 * B * L * C * C * K
+    for _ in range(3):
+        ops.conv1d_fwd(x, w, bias, 1, 1, K // 2, act=ops.ACT_LRELU)
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(10):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.conv1d_fwd(x, w, bias, 1, 1, K // 2, act=ops.ACT_LRELU)
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    ms = sum(times) / len(times)
+    achieved = flops / (ms * 1e-3) / 1e12
+    return {"kernel": "conv_fwd_kernel (MSD convs.5: 1024->1024, k=5, B=8, L=125)", "bound": "tensor",
+            "achieved": achieved, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": achieved / peaks["tensor"],
+            "traffic": None, "ms_per_launch": ms, "peak_source": peaks["src"] + " (burst: kernel timed alone)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--gan_loss", default="ls", choices=["ls", "hinge"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl ours) needs a CUDA device: the lctgan kernels have no CPU fallback")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from lctgan import _lib
+    from lctgan.parallel import FlatGradAllReduce, broadcast_parameters
+    from lctgan.training import StepArgs, build_models, train_step
+    from oracle import lct_oracle as O
+
+    enh, mpd, msd, tf, mr, g_opt, d_opt = build_models(dev, gan_seed=42)
+    if world > 1:
+        broadcast_parameters([enh, mpd, msd])
+    sync_d = FlatGradAllReduce(list(mpd.parameters()) + list(msd.parameters())) if world > 1 else None
+    sync_g = FlatGradAllReduce(list(enh.parameters())) if world > 1 else None
+    sargs = StepArgs(gan_loss=args.gan_loss)
+
+    noisy_h, clean_h = O.synthetic_batch(BATCH, SEGMENT, seed=1234 + rank)      # synthetic data generator only
+    noisy_h, clean_h = noisy_h.pin_memory(), clean_h.pin_memory()
+    noisy_d, clean_d = noisy_h.to(dev), clean_h.to(dev)
+    res_h = torch.empty(6, dtype=torch.float32).pin_memory()
+
+    def step(n, c):
+        return train_step(enh, mpd, msd, tf, mr, g_opt, d_opt, n, c, sargs, after_d_backward=sync_d,
+                          after_g_backward=sync_g)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return t.item()
+        return ms
+
+    for _ in range(args.warmup):
+        out = step(noisy_d, clean_d)
+    barrier()
+
+    # ---- device-resident throughput
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    _lib.reset_kernel_launches()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = step(noisy_d, clean_d)
+    e1.record()
+    barrier()
+    launches = _lib.kernel_launches()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+    value = BATCH * world * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end: pinned host inputs -> H2D -> step -> D2H of the step's losses, every step
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        n = noisy_h.to(dev, non_blocking=True)
+        c = clean_h.to(dev, non_blocking=True)
+        out = step(n, c)
+        res = torch.stack([out[k] for k in ("d_loss", "g_loss", "mr", "mask", "adv", "fm")])
+        res_h.copy_(res, non_blocking=True)
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    e2e_value = BATCH * world * args.steps / (ms_e2e * 1e-3)
+    losses = {k: float(v) for k, v in zip(("d_loss", "g_loss", "mr", "mask", "adv", "fm"), res_h.tolist())}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = _peaks()
+    roof = None if args.no_roofline else measure_roofline(dev, peaks)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        sps, ms, b, cores = cpu_reference_steps(steps=1, warmup=1, budget_s=30.0)
+        cpu = {"value": sps, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"1 timed D+G step of {b} x 2 s segments after 1 warm-up step (oracle port of train.py:165-249, "
+                         f"torch CPU ops, {cores} threads)", "ms_per_step": ms}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "gan_loss": args.gan_loss, "parallelism": f"dp{world}",
+                   "l2": "no explicit flush: one step streams > 2 GB of activations (>> 126 MB L2)"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": int(noisy_h.numel() * 4 * 2), "d2h_bytes_per_step": int(res_h.numel() * 4)},
+        "gpu_launches": launches,
+        "roofline": roof,
+        "cpu_baseline": cpu,
+        "losses_last_step": losses,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

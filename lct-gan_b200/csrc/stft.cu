@@ -453,7 +453,7 @@ __global__ void mrloss_grad_kernel(const float2* __restrict__ A, const float2* _
 
 template <typename K>
 int set_smem(K kernel, size_t bytes) {
-    if (bytes > 48 * 1024) {
+    if (bytes > 40 * 1024) {   // static __shared__ of the kernel counts against the 48 KB default too
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         if (e != cudaSuccess) return (int)e;
     }

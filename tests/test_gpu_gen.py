@@ -264,12 +264,18 @@ def test_generator_and_enhancer(dev, T):
     assert mg.min().item() >= 0.5
     assert torch.all(mg[..., -3:] == 0.5)
     ((eg * gw.to(dev)).sum() + (mg * gm.to(dev)).sum()).backward()
-    worst = 0.0
+    # float64 run of the oracle = ground truth.  Gradients of the attention q/k projections are sums with
+    # heavy cancellation (softmax shift invariance: dL/db_k == 0 analytically), so the bar is "within 5e-4
+    # of the truth, or no worse than 4x the fp32 CPU oracle's own distance from the truth".
+    P64 = {k: (v.detach().double().requires_grad_(v.requires_grad)) for k, v in P.items()}
+    e64, m64 = O.enhancer_forward(P64, noisy.double())
+    ((e64 * gw.double()).sum() + (m64 * gm.double()).sum()).backward()
     for k, p in enh.named_parameters():
         assert p.grad is not None, k
-        e = rel_err(p.grad, P[k].grad)
-        worst = max(worst, e)
-        assert e < 5e-4, (k, e)
+        truth = P64[k].grad
+        e_mine = rel_err(p.grad.double(), truth)
+        e_ref = rel_err(P[k].grad.double(), truth)
+        assert e_mine < max(5e-4, 4.0 * e_ref), (k, e_mine, e_ref)
     # LCTGenerator on its own, through the reference's [B,1,F,T] interface
     mag = O.magnitude(O.stft(noisy, P["stft.window"], 512, 256)).unsqueeze(1)
     with torch.no_grad():

@@ -109,10 +109,11 @@ def test_training_step_matches_oracle(dev, gan_loss):
         for k in ("d_loss", "g_loss", "mr", "mask", "adv", "fm"):
             r, g = ref[k], got[k].item()
             assert abs(g - r) <= tol * max(abs(r), 1e-3), (step, k, g, r)
-    # post-step weights
-    for k, p in enh.named_parameters():
-        assert rel_err(p, st.enh[k]) < 2e-3, k
-    for k, p in msd.named_parameters():
-        assert rel_err(p, st.msd[k]) < 2e-3, k
-    for k, p in mpd.named_parameters():
-        assert rel_err(p, st.mpd[k]) < 2e-3, k
+    # post-step weights.  AdamW turns a gradient of any size into a step of ~lr, so entries whose gradient is
+    # pure rounding noise (e.g. the attention key bias, analytically zero) can differ by a fraction of
+    # lr * steps; the bound is 5 % of the total possible movement 2 * lr.
+    lr, nsteps = 2e-4, 2
+    for mod, ref in ((enh, st.enh), (msd, st.msd), (mpd, st.mpd)):
+        for k, p in mod.named_parameters():
+            diff = (p.detach().cpu() - ref[k].detach()).abs().max().item()
+            assert diff <= 0.05 * lr * nsteps, (k, diff)
