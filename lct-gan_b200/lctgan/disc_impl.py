@@ -14,9 +14,15 @@ from typing import List, Sequence, Tuple
 
 import torch
 
-from . import ops
+from . import config, ops
 
 LRELU_SLOPE = 0.2
+
+
+def _use_dense(x_shape, w_shape, k, s, g) -> bool:
+    """MSD convs.5-like layers (dense, stride 1, P == 1) go to the tcgen05 kernel in bf16 mode."""
+    return (config.dense_tensor_cores and g == 1 and s == 1 and x_shape[3] == 1 and w_shape[0] > 1
+            and ops.dense_supported(w_shape[1], w_shape[0], k))
 
 # (kernel, stride, padding, groups) per conv; the last entry is conv_post (no activation)
 LayerSpec = Tuple[int, int, int, int]
@@ -34,14 +40,23 @@ class ConvStackFn(torch.autograd.Function):
         fmaps: List[torch.Tensor] = []
         weights: List[torch.Tensor] = []
         h = x4
+        dense: List[int] = []
         for i, (k, s, pad, g) in enumerate(specs):
             bias, wg, wv = params[3 * i], params[3 * i + 1], params[3 * i + 2]
             w = ops.weight_norm_fwd(wg.contiguous(), wv.contiguous())
             last = i == n - 1
-            h = ops.conv1d_fwd(h, w, bias, g, s, pad, act=ops.ACT_NONE if last else ops.ACT_LRELU, slope=LRELU_SLOPE)
+            act = ops.ACT_NONE if last else ops.ACT_LRELU
+            if _use_dense(h.shape, w.shape, k, s, g) and pad == k // 2:
+                wt, _ = ops.stage_dense_weights(w, want_wt=True, want_wd=False)
+                h = ops.dense_conv(ops.stage_nlc_bf16(h, pad), wt, h.shape[0], h.shape[2], w.shape[1], w.shape[0], k,
+                                   bias=bias, act=act, slope=LRELU_SLOPE)
+                dense.append(i)
+            else:
+                h = ops.conv1d_fwd(h, w, bias, g, s, pad, act=act, slope=LRELU_SLOPE)
             fmaps.append(h)
             weights.append(w)
         ctx.specs = list(specs)
+        ctx.dense = dense
         ctx.skip_param_grads = skip_param_grads
         ctx.save_for_backward(x4, *fmaps, *weights, *params)
         return tuple(fmaps)
@@ -66,7 +81,22 @@ class ConvStackFn(torch.autograd.Function):
         for i in range(n - 1, -1, -1):
             k, s, pad, g = specs[i]
             inp = x4 if i == 0 else fmaps[i - 1]
-            if dpre is not None:
+            if dpre is not None and i in ctx.dense:
+                # tcgen05 path: bf16 staged operands, fp32 accumulation
+                B_, Ci_, L_ = inp.shape[0], inp.shape[1], inp.shape[2]
+                Co_ = weights[i].shape[0]
+                if want_params:
+                    db = torch.zeros(Co_, dtype=torch.float32, device=inp.device)
+                    Lp = L_ + k - 1
+                    dyq = ops.stage_ncl_bf16(dpre, Lp, 0, rowsum=db)
+                    xq = ops.stage_ncl_bf16(inp, Lp, pad)
+                    dw = ops.dense_wgrad(dyq, xq, Co_, Ci_, k, weights[i].shape)
+                    dg, dv = ops.weight_norm_bwd(params[3 * i + 1].contiguous(), params[3 * i + 2].contiguous(), dw)
+                    gparams[3 * i], gparams[3 * i + 1], gparams[3 * i + 2] = db, dg, dv
+                _, wd = ops.stage_dense_weights(weights[i], want_wt=False, want_wd=True)
+                dpre = ops.dense_conv(ops.stage_nlc_bf16(dpre, pad), wd, B_, L_, Co_, Ci_, k, gextra=gouts[i - 1],
+                                      xact=inp, act=ops.ACT_LRELU, slope=LRELU_SLOPE)
+            elif dpre is not None:
                 if want_params:
                     dw, db = ops.conv1d_wgrad(inp, dpre, weights[i].shape, g, s, pad, want_bias=True)
                     dg, dv = ops.weight_norm_bwd(params[3 * i + 1].contiguous(), params[3 * i + 2].contiguous(), dw)

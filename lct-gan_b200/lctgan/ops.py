@@ -225,6 +225,11 @@ def weight_norm_bwd(g, v, dw):
     return dg, dv
 
 
+def _is_post(cout, k, groups, stride, pad):
+    """conv_post shape: one output channel, "same" odd kernel -> dedicated channel-reduction kernels."""
+    return cout == 1 and groups == 1 and stride == 1 and (k & 1) and k <= 8 and pad == k // 2
+
+
 def conv_out_len(lin, k, s, pad):
     return (lin + 2 * pad - k) // s + 1
 
@@ -234,6 +239,10 @@ def conv1d_fwd(x, w, bias, groups, stride, pad, act=ACT_NONE, slope=0.2):
     B, Cin, Lin, P = x.shape
     Cout, K = w.shape[0], w.shape[2]
     Lout = conv_out_len(Lin, K, stride, pad)
+    if _is_post(Cout, K, groups, stride, pad) and act == ACT_NONE:
+        y = torch.zeros(B, 1, Lin, P, dtype=torch.float32, device=x.device)
+        call("lct_conv_post_fwd", x, w, bias, y, B, Cin, Lin, P, K)
+        return y
     y = torch.empty(B, Cout, Lout, P, dtype=torch.float32, device=x.device)
     call("lct_conv1d_fwd", x, w, bias, y, B, Cin, Cout, groups, K, stride, pad, Lin, P, act, slope)
     return y
@@ -243,6 +252,9 @@ def conv1d_dgrad(dy, w, x_shape, groups, stride, pad, gextra=None, xact=None, ac
     B, Cin, Lin, P = x_shape
     Cout, K = w.shape[0], w.shape[2]
     dx = torch.empty(B, Cin, Lin, P, dtype=torch.float32, device=dy.device)
+    if _is_post(Cout, K, groups, stride, pad):
+        call("lct_conv_post_dgrad", dy, w, dx, gextra, xact, B, Cin, Lin, P, K, act, slope)
+        return dx
     call("lct_conv1d_dgrad", dy, w, dx, gextra, xact, B, Cin, Cout, groups, K, stride, pad, Lin, P, act, slope)
     return dx
 
@@ -252,6 +264,9 @@ def conv1d_wgrad(x, dy, w_shape, groups, stride, pad, want_bias=True):
     Cout, K = w_shape[0], w_shape[2]
     dw = torch.zeros(w_shape, dtype=torch.float32, device=x.device)
     db = torch.zeros(Cout, dtype=torch.float32, device=x.device) if want_bias else None
+    if _is_post(Cout, K, groups, stride, pad):
+        call("lct_conv_post_wgrad", x, dy, dw, db, B, Cin, Lin, P, K)
+        return dw, db
     call("lct_conv1d_wgrad", x, dy, dw, db, B, Cin, Cout, groups, K, stride, pad, Lin, P)
     return dw, db
 
@@ -415,3 +430,45 @@ def mt_copy(srcs: Sequence[torch.Tensor], dsts: Sequence[torch.Tensor]) -> None:
         ss, dd = srcs[s:s + maxseg], dsts[s:s + maxseg]
         n = (ctypes.c_int64 * len(ss))(*[t.numel() for t in ss])
         call("lct_mt_copy", _ptr_array(ss), _ptr_array(dd), n, len(ss))
+
+
+# ----------------------------------------------------------------------------- dense tcgen05 convolution
+def dense_supported(cin: int, cout: int, k: int) -> bool:
+    return bool(call_ret("lct_dense_supported", cin, cout, k))
+
+
+def stage_nlc_bf16(x, pad):
+    """[B,C,L,1] / [B,C,L] fp32 -> [B, L+2*pad, C] bf16 (zero rows around every batch)."""
+    B, C, L = x.shape[0], x.shape[1], x.shape[2]
+    out = torch.empty(B, L + 2 * pad, C, dtype=torch.bfloat16, device=x.device)
+    call("lct_stage_nlc_bf16", x, out, B, C, L, pad)
+    return out
+
+
+def stage_ncl_bf16(x, Lp, shift, rowsum=None):
+    """[B,C,L] fp32 -> [C, pitch] bf16 with out[c][b*Lp + shift + l] = x[b,c,l]; pitch = B*Lp rounded up to 8."""
+    B, C, L = x.shape[0], x.shape[1], x.shape[2]
+    pitch = (B * Lp + 7) // 8 * 8
+    out = torch.empty(C, pitch, dtype=torch.bfloat16, device=x.device)
+    call("lct_stage_ncl_bf16", x, out, rowsum, B, C, L, Lp, shift, pitch)
+    return out
+
+
+def stage_dense_weights(w, want_wt=True, want_wd=True):
+    Co, Ci, K = w.shape[0], w.shape[1], w.shape[2]
+    wt = torch.empty(K, Co, Ci, dtype=torch.bfloat16, device=w.device) if want_wt else None
+    wd = torch.empty(K, Ci, Co, dtype=torch.bfloat16, device=w.device) if want_wd else None
+    call("lct_stage_dense_weights", w, wt, wd, Co, Ci, K)
+    return wt, wd
+
+
+def dense_conv(a_staged, w_staged, B, L, Ca, Cn, K, bias=None, gextra=None, xact=None, act=ACT_NONE, slope=0.2):
+    out = torch.empty(B, Cn, L, 1, dtype=torch.float32, device=a_staged.device)
+    call("lct_dense_conv", a_staged, w_staged, bias, gextra, xact, out, B, L, Ca, Cn, K, act, slope)
+    return out
+
+
+def dense_wgrad(dyq, xq, Co, Ci, K, w_shape):
+    dw = torch.empty(w_shape, dtype=torch.float32, device=dyq.device)
+    call("lct_dense_wgrad", dyq, xq, dw, Co, Ci, K, dyq.shape[1])
+    return dw

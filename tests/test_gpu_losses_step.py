@@ -111,9 +111,12 @@ def test_training_step_matches_oracle(dev, gan_loss):
             assert abs(g - r) <= tol * max(abs(r), 1e-3), (step, k, g, r)
     # post-step weights.  AdamW turns a gradient of any size into a step of ~lr, so entries whose gradient is
     # pure rounding noise (e.g. the attention key bias, analytically zero) can differ by a fraction of
-    # lr * steps; the bound is 5 % of the total possible movement 2 * lr.
+    # lr * steps (a sign flip of a ~0 gradient moves a weight by up to 2 * lr).  Bound: at most 0.1 % of a
+    # tensor's entries may differ by more than 5 % of lr * steps, none by more than 2 * lr * steps.
     lr, nsteps = 2e-4, 2
     for mod, ref in ((enh, st.enh), (msd, st.msd), (mpd, st.mpd)):
         for k, p in mod.named_parameters():
-            diff = (p.detach().cpu() - ref[k].detach()).abs().max().item()
-            assert diff <= 0.05 * lr * nsteps, (k, diff)
+            diff = (p.detach().cpu() - ref[k].detach()).abs()
+            assert diff.max().item() <= 2.0 * lr * nsteps, (k, diff.max().item())
+            bad = (diff > 0.05 * lr * nsteps).float().mean().item()
+            assert bad <= 1e-3, (k, bad)
