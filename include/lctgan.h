@@ -110,12 +110,13 @@ LCT_API int lct_conv_post_dgrad(const float* dy, const float* w, float* dx, cons
  * bf16 operands staged once per call, fp32 accumulation in TMEM, TMA-fed implicit GEMM (no im2col).
  * lct_dense_supported: 1 if (Cin, Cout multiples of 128, odd K <= 8) and the driver exposes cuTensorMapEncodeTiled. */
 LCT_API int lct_dense_supported(int64_t Cin, int64_t Cout, int64_t K);
+LCT_API int lct_dense_debug(int stage);   /* bring-up aid: 0 = normal; 1..3 run only the first stages of the kernel */
 LCT_API int lct_stage_nlc_bf16(const float* x, void* out, int64_t B, int64_t C, int64_t L, int64_t pad, cudaStream_t stream);   /* [B,C,L] f32 -> [B,L+2pad,C] bf16, zero rows between batches */
-LCT_API int lct_stage_ncl_bf16(const float* x, void* out, float* rowsum, int64_t B, int64_t C, int64_t L, int64_t Lp, int64_t shift, int64_t pitch, cudaStream_t stream);   /* [B,C,L] f32 -> [C,pitch] bf16, out[c][b*Lp+shift+l]; rowsum[C] += sums (bias grad) */
+LCT_API int lct_stage_ncl_bf16(const float* x, void* out, float* rowsum, int64_t B, int64_t C, int64_t L, int64_t Lp, int64_t shift, int64_t pitch, int64_t copies, cudaStream_t stream);   /* [B,C,L] f32 -> [copies,C,pitch] bf16, out[k][c][b*Lp+shift-k+l]; rowsum[C] += sums (bias grad) */
 LCT_API int lct_stage_dense_weights(const float* w, void* wt, void* wd, int64_t Co, int64_t Ci, int64_t K, cudaStream_t stream);   /* [Co,Ci,K] f32 -> wt [K,Co,Ci], wd [K,Ci,Co] taps flipped (bf16) */
 /* out f32 [B,Cn,L] = epilogue(sum_{tap,ca} a[b*(L+K-1)+l+tap, ca] * w[tap][cn][ca]); forward: bias+act; dgrad: (acc+gextra)*act'(xact). */
 LCT_API int lct_dense_conv(const void* a, const void* w, const float* bias, const float* gextra, const float* xact, float* out, int64_t B, int64_t L, int64_t Ca, int64_t Cn, int64_t K, int act, float slope, cudaStream_t stream);
-/* dw f32 [Co,Ci,K] = sum_r dyq[co][r] * xq[ci][r+tap]  (operands from lct_stage_ncl_bf16). */
+/* dw f32 [Co,Ci,K] = sum_r dyq[co][r] * xq[tap][ci][r]  (dyq: 1 copy, shift 0; xq: K copies, shift K/2, from lct_stage_ncl_bf16). */
 LCT_API int lct_dense_wgrad(const void* dyq, const void* xq, float* dw, int64_t Co, int64_t Ci, int64_t K, int64_t pitch, cudaStream_t stream);
 
 /* ---------------------------------------------------------------- generator (models/generator.py) */

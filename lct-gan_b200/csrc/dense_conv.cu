@@ -5,7 +5,9 @@
 // tcgen05 implicit GEMM, no im2col:
 //   forward  Y[r, co]  = sum_{tap, ci} Xp[r + tap, ci] * Wt[tap][co][ci]       r = padded (batch, position) row
 //   dgrad    dX[r, ci] = sum_{tap, co} dYp[r + tap, co] * Wd[tap][ci][co]      Wd[tap] = W[:, :, K-1-tap]^T
-//   wgrad    dW[co, ci, tap] = sum_r dYq[co][r] * Xq[ci][r + tap]              positions are the contraction dim
+//   wgrad    dW[co, ci, tap] = sum_r dYq[co][r] * Xq[tap][ci][r]                positions are the contraction dim;
+//            Xq[tap] is X shifted by `tap` positions (one staged copy per tap: a TMA box must start on a
+//            16-byte boundary of the innermost dimension, so the shift cannot ride in the box coordinate)
 // Operands are bf16 copies staged once per call (channels-last rows with K/2 zero rows between batches for
 // fwd/dgrad, position-major rows for wgrad); accumulation is fp32 in TMEM.  Because a convolution tap is a
 // pure row (or column) offset in these layouts, every A/B tile is a single TMA box load with the tap folded
@@ -106,7 +108,7 @@ enum { EPI_CONV = 0, EPI_WGRAD = 1 };
 struct DenseParams {
     // k-block schedule: kb -> A box (a0 + (kb % kdiv) * BK, m0 + (kb / kdiv) * a_step1)
     //                        B box (b0 + (kb % kdiv) * BK, n0 + (kb / kdiv) * b_step1)
-    int nkb, kdiv, a0, a_step1, b0, b_step1;
+    int nkb, kdiv, a0, a_step1, b0, b_step1, b_tap_rows;
     // EPI_CONV: rows are padded (batch, position) pairs; out is fp32 [B, Cn, L]
     int R, Lp, L, Cn;
     const float* bias;      // forward
@@ -116,6 +118,7 @@ struct DenseParams {
     float* out;
     // EPI_WGRAD: out is dW [M_total, N_total, K]; tap = blockIdx.z
     int Ntot, Ktaps;
+    int debug;   // bring-up bisection (lct_dense_debug): 1 alloc only, 2 + TMA ring, 3 + MMA, 0 everything
 };
 
 template <int BN, int STAGES, int EPI>
@@ -154,7 +157,9 @@ dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0 && lane == 0) {
+    if (p.debug == 1) {
+        // allocation / barrier setup only
+    } else if (warp == 0 && lane == 0) {
         // ===== TMA producer =====
         for (int kb = 0; kb < p.nkb; ++kb) {
             const int s = kb % STAGES;
@@ -164,7 +169,7 @@ dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             const int kin = kb % p.kdiv, kout = kb / p.kdiv;
             uint8_t* sa = tiles + (size_t)s * STAGE_BYTES;
             tma_load_2d(sa, &tmA, &full[s], p.a0 + kin * BK, m0 + kout * p.a_step1);
-            tma_load_2d(sa + A_BYTES, &tmB, &full[s], p.b0 + tap + kin * BK, n0 + kout * p.b_step1);
+            tma_load_2d(sa + A_BYTES, &tmB, &full[s], p.b0 + kin * BK, n0 + kout * p.b_step1 + tap * p.b_tap_rows);
         }
     } else if (warp == 1 && lane == 0) {
         // ===== MMA issuer =====
@@ -174,6 +179,10 @@ dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             const uint32_t ph = (kb / STAGES) & 1;
             mbar_wait(&full[s], ph);
             tc_fence_after();
+            if (p.debug == 2) {   // consume without the tensor core
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[s])) : "memory");
+                continue;
+            }
             const uint32_t sa = smem_u32(tiles + (size_t)s * STAGE_BYTES);
             const uint32_t sb = sa + A_BYTES;
 #pragma unroll
@@ -184,15 +193,15 @@ dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
             umma_commit(&empty[s]);          // arrives once these MMAs have consumed the smem slot
         }
-        umma_commit(tmem_full);              // accumulator complete
-    } else if (warp >= 4) {
+        if (p.debug != 2) umma_commit(tmem_full);              // accumulator complete
+    } else if (warp >= 4 && (p.debug == 0 || p.debug == 3)) {
         // ===== epilogue: TMEM lane = tile row; warp (w % 4) owns lanes [32 (w%4), +32) =====
         mbar_wait(tmem_full, 0);
         tc_fence_after();
         const int q = warp & 3;
         const int row = m0 + q * 32 + lane;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = 0; c0 < (p.debug == 3 ? 0 : BN); c0 += 32) {
             uint32_t v[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
             if (EPI == EPI_CONV) {
@@ -262,8 +271,11 @@ int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uin
     return r == CUDA_SUCCESS ? 0 : LCT_EINVAL;
 }
 
+int g_dense_debug = 0;
+
 template <int BN, int STAGES, int EPI>
-int launch_dense(const CUtensorMap& a, const CUtensorMap& b, const DenseParams& p, dim3 grid, cudaStream_t st) {
+int launch_dense(const CUtensorMap& a, const CUtensorMap& b, DenseParams& p, dim3 grid, cudaStream_t st) {
+    p.debug = g_dense_debug;
     constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 + 256;
     cudaError_t e = cudaFuncSetAttribute(dense_kernel<BN, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
@@ -295,21 +307,23 @@ __global__ void stage_nlc_kernel(const float* __restrict__ x, __nv_bfloat16* __r
     }
 }
 
-// x fp32 [B, C, L] -> out bf16 [C, pitch]: out[c][b * Lp + shift + l] = x[b, c, l], zeros elsewhere;
-// rowsum (optional) [C] += sum_{b,l} x   (the bias gradient when x is dY)
+// x fp32 [B, C, L] -> out bf16 [copies, C, pitch]: out[k][c][b * Lp + (shift - k) + l] = x[b, c, l], zeros elsewhere
+// (copy k read at position r equals copy 0 read at r + k); rowsum (optional) [C] += sum_{b,l} x (bias gradient)
 __global__ void stage_ncl_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int C, int L,
                                  int Lp, int shift, int pitch, float* __restrict__ rowsum) {
     __shared__ float red[32];
-    const int c = blockIdx.x;
+    const int c = blockIdx.x, k = blockIdx.y;
+    const int sh = shift - k;
+    __nv_bfloat16* o = out + ((size_t)k * C + c) * pitch;
     float s = 0.f;
     for (int i = threadIdx.x; i < pitch; i += blockDim.x) {
-        int b = i / Lp, j = i - b * Lp, l = j - shift;
+        int b = i / Lp, j = i - b * Lp, l = j - sh;
         float v = 0.f;
         if (b < B && l >= 0 && l < L) v = x[((size_t)b * C + c) * L + l];
         s += v;
-        out[(size_t)c * pitch + i] = __float2bfloat16(v);
+        o[i] = __float2bfloat16(v);
     }
-    if (rowsum) {
+    if (rowsum && k == 0) {
         float tot = block_sum(s, red);
         if (threadIdx.x == 0) atomicAdd(&rowsum[c], tot);
     }
@@ -338,6 +352,11 @@ __global__ void stage_weights_kernel(const float* __restrict__ w, __nv_bfloat16*
 
 }  // namespace
 
+LCT_API int lct_dense_debug(int stage) {
+    g_dense_debug = stage;
+    return 0;
+}
+
 LCT_API int lct_dense_supported(int64_t Cin, int64_t Cout, int64_t K) {
     return (Cin % 128 == 0 && Cout % 128 == 0 && K >= 1 && K <= 8 && (K & 1) && get_encode() != nullptr) ? 1 : 0;
 }
@@ -353,10 +372,11 @@ LCT_API int lct_stage_nlc_bf16(const float* x, void* out, int64_t B, int64_t C, 
 
 // x fp32 [B,C,L] -> bf16 [C, pitch] position-major (see stage_ncl_kernel); rowsum optional
 LCT_API int lct_stage_ncl_bf16(const float* x, void* out, float* rowsum, int64_t B, int64_t C, int64_t L, int64_t Lp,
-                               int64_t shift, int64_t pitch, cudaStream_t st) {
-    if (!x || !out || B <= 0 || C <= 0 || C >= (1LL << 31) || L <= 0 || Lp < L + shift || pitch < B * Lp || pitch % 8)
+                               int64_t shift, int64_t pitch, int64_t copies, cudaStream_t st) {
+    if (!x || !out || B <= 0 || C <= 0 || C >= (1LL << 31) || L <= 0 || Lp < L + shift || pitch < B * Lp || pitch % 8 ||
+        copies < 1 || copies > 64)
         return LCT_EINVAL;
-    stage_ncl_kernel<<<(unsigned)C, 256, 0, st>>>(x, (__nv_bfloat16*)out, (int)B, (int)C, (int)L, (int)Lp, (int)shift,
+    stage_ncl_kernel<<<dim3((unsigned)C, (unsigned)copies), 256, 0, st>>>(x, (__nv_bfloat16*)out, (int)B, (int)C, (int)L, (int)Lp, (int)shift,
                                                   (int)pitch, rowsum);
     LCT_RETURN_IF_LAUNCH_FAILED();
     return 0;
@@ -395,18 +415,19 @@ LCT_API int lct_dense_conv(const void* a, const void* w, const float* bias, cons
     return launch_dense<64, 6, EPI_CONV>(ma, mb, p, grid, st);
 }
 
-// dw fp32 [Co, Ci, K] = sum_r dyq[co][r] * xq[ci][r + tap]   (both staged by lct_stage_ncl_bf16, row pitch `pitch`)
+// dw fp32 [Co, Ci, K] = sum_r dyq[co][r] * xq[tap][ci][r]   (dyq: 1 copy, shift 0; xq: K copies, shift K/2; both from
+// lct_stage_ncl_bf16 with the same Lp = L + K - 1 and row pitch `pitch`)
 LCT_API int lct_dense_wgrad(const void* dyq, const void* xq, float* dw, int64_t Co, int64_t Ci, int64_t K,
                             int64_t pitch, cudaStream_t st) {
     if (!dyq || !xq || !dw || pitch <= 0 || pitch % 8 || !lct_dense_supported(Ci, Co, K)) return LCT_EINVAL;
     CUtensorMap ma, mb;
     int rc = make_map(&ma, dyq, (uint64_t)Co, (uint64_t)pitch, (uint64_t)pitch, BM);
     if (rc) return rc;
-    rc = make_map(&mb, xq, (uint64_t)Ci, (uint64_t)pitch, (uint64_t)pitch, 128);
+    rc = make_map(&mb, xq, (uint64_t)(K * Ci), (uint64_t)pitch, (uint64_t)pitch, 128);
     if (rc) return rc;
     DenseParams p = {};
     p.nkb = (int)ceil_div64(pitch, BK); p.kdiv = p.nkb;
-    p.a0 = 0; p.a_step1 = 0; p.b0 = 0; p.b_step1 = 0;
+    p.a0 = 0; p.a_step1 = 0; p.b0 = 0; p.b_step1 = 0; p.b_tap_rows = (int)Ci;
     p.out = dw; p.Ntot = (int)Ci; p.Ktaps = (int)K;
     dim3 grid((unsigned)(Co / BM), (unsigned)(Ci / 128), (unsigned)K);
     return launch_dense<128, 5, EPI_WGRAD>(ma, mb, p, grid, st);

@@ -89,7 +89,7 @@ class ConvStackFn(torch.autograd.Function):
                     db = torch.zeros(Co_, dtype=torch.float32, device=inp.device)
                     Lp = L_ + k - 1
                     dyq = ops.stage_ncl_bf16(dpre, Lp, 0, rowsum=db)
-                    xq = ops.stage_ncl_bf16(inp, Lp, pad)
+                    xq = ops.stage_ncl_bf16(inp, Lp, pad, copies=k)
                     dw = ops.dense_wgrad(dyq, xq, Co_, Ci_, k, weights[i].shape)
                     dg, dv = ops.weight_norm_bwd(params[3 * i + 1].contiguous(), params[3 * i + 2].contiguous(), dw)
                     gparams[3 * i], gparams[3 * i + 1], gparams[3 * i + 2] = db, dg, dv

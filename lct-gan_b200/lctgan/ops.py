@@ -445,12 +445,13 @@ def stage_nlc_bf16(x, pad):
     return out
 
 
-def stage_ncl_bf16(x, Lp, shift, rowsum=None):
-    """[B,C,L] fp32 -> [C, pitch] bf16 with out[c][b*Lp + shift + l] = x[b,c,l]; pitch = B*Lp rounded up to 8."""
+def stage_ncl_bf16(x, Lp, shift, rowsum=None, copies=1):
+    """[B,C,L] fp32 -> [copies, C, pitch] bf16 with out[k][c][b*Lp + shift - k + l] = x[b,c,l] (copy k is copy 0
+    advanced by k positions); pitch = B*Lp rounded up to 8."""
     B, C, L = x.shape[0], x.shape[1], x.shape[2]
     pitch = (B * Lp + 7) // 8 * 8
-    out = torch.empty(C, pitch, dtype=torch.bfloat16, device=x.device)
-    call("lct_stage_ncl_bf16", x, out, rowsum, B, C, L, Lp, shift, pitch)
+    out = torch.empty(copies, C, pitch, dtype=torch.bfloat16, device=x.device)
+    call("lct_stage_ncl_bf16", x, out, rowsum, B, C, L, Lp, shift, pitch, copies)
     return out
 
 
@@ -470,5 +471,5 @@ def dense_conv(a_staged, w_staged, B, L, Ca, Cn, K, bias=None, gextra=None, xact
 
 def dense_wgrad(dyq, xq, Co, Ci, K, w_shape):
     dw = torch.empty(w_shape, dtype=torch.float32, device=dyq.device)
-    call("lct_dense_wgrad", dyq, xq, dw, Co, Ci, K, dyq.shape[1])
+    call("lct_dense_wgrad", dyq, xq, dw, Co, Ci, K, dyq.shape[-1])
     return dw
