@@ -144,9 +144,9 @@ def run_reference(args):
 # roofline of the dominant kernel, timed live
 # --------------------------------------------------------------------------------------------------
 def measure_roofline(dev, peaks):
-    """Dominant kernel of the step: the dense 1024->1024, k=5 convolution of the scale discriminators
-    (MSD convs.5, the one layer above the ridge: SURVEY.md section 8a D3).  Timed alone with CUDA
-    events on the launching stream, L2 flushed between launches."""
+    """Dominant kernel of the step by FLOPs: the dense 1024->1024, k=5 convolution of the scale discriminators
+    (MSD convs.5, the one layer above the ridge: SURVEY.md section 8a D3) on tcgen05.  Timed alone with CUDA
+    events on the launching stream, L2 flushed between launches; algorithmic FLOPs = 2*B*L*Cin*Cout*K."""
     import torch
     from lctgan import ops
     B, L, C, K = BATCH, 125, 1024, 5
@@ -154,25 +154,29 @@ def measure_roofline(dev, peaks):
     x = torch.randn(B, C, L, 1, generator=g).to(dev)
     w = (torch.randn(C, C, K, generator=g) / (C * K) ** 0.5).to(dev)
     bias = torch.zeros(C, device=dev)
+    wt, _ = ops.stage_dense_weights(w, want_wd=False)
+    xp = ops.stage_nlc_bf16(x, K // 2)
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
     flops = 2.0 * B * L * C * C * K
+    run = lambda: ops.dense_conv(xp, wt, B, L, C, C, K, bias=bias, act=ops.ACT_LRELU)
     for _ in range(3):
-        ops.conv1d_fwd(x, w, bias, 1, 1, K // 2, act=ops.ACT_LRELU)
+        run()
     torch.cuda.synchronize()
     times = []
     for _ in range(10):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        ops.conv1d_fwd(x, w, bias, 1, 1, K // 2, act=ops.ACT_LRELU)
+        run()
         e1.record()
         torch.cuda.synchronize()
         times.append(e0.elapsed_time(e1))
     ms = sum(times) / len(times)
     achieved = flops / (ms * 1e-3) / 1e12
-    return {"kernel": "conv_fwd_kernel (MSD convs.5: 1024->1024, k=5, B=8, L=125)", "bound": "tensor",
-            "achieved": achieved, "peak": peaks["tensor"], "unit": "TFLOP/s", "frac": achieved / peaks["tensor"],
-            "traffic": None, "ms_per_launch": ms, "peak_source": peaks["src"] + " (burst: kernel timed alone)"}
+    return {"kernel": "dense_kernel<64,6,conv> (MSD convs.5 forward: 1024->1024, k=5, B=8, L=125, tcgen05 bf16)",
+            "bound": "tensor", "achieved": achieved, "peak": peaks["tensor"], "unit": "TFLOP/s",
+            "frac": achieved / peaks["tensor"], "traffic": None, "ms_per_launch": ms,
+            "peak_source": peaks["src"] + " (burst: kernel timed alone)"}
 
 
 def main():
@@ -184,6 +188,7 @@ def main():
     ap.add_argument("--gan_loss", default="ls", choices=["ls", "hinge"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -204,10 +209,11 @@ def main():
 
     from lctgan import _lib
     from lctgan.parallel import FlatGradAllReduce, broadcast_parameters
-    from lctgan.training import StepArgs, build_models, train_step
+    from lctgan.training import GraphedTrainStep, StepArgs, build_models, train_step
     from oracle import lct_oracle as O
 
-    enh, mpd, msd, tf, mr, g_opt, d_opt = build_models(dev, gan_seed=42)
+    use_graph = (not args.no_graph) and world == 1
+    enh, mpd, msd, tf, mr, g_opt, d_opt = build_models(dev, gan_seed=42, capturable=use_graph)
     if world > 1:
         broadcast_parameters([enh, mpd, msd])
     sync_d = FlatGradAllReduce(list(mpd.parameters()) + list(msd.parameters())) if world > 1 else None
@@ -219,7 +225,17 @@ def main():
     noisy_d, clean_d = noisy_h.to(dev), clean_h.to(dev)
     res_h = torch.empty(6, dtype=torch.float32).pin_memory()
 
+    graphed = None
+    if use_graph:
+        # the whole D+G step (forward, backward, clip, both AdamW updates) as one CUDA graph over static buffers
+        graphed = GraphedTrainStep(enh, mpd, msd, tf, mr, g_opt, d_opt, noisy_d, clean_d, sargs, warmup=3)
+
     def step(n, c):
+        if graphed is not None:
+            if n is not noisy_d:
+                noisy_d.copy_(n, non_blocking=True)
+                clean_d.copy_(c, non_blocking=True)
+            return graphed()
         return train_step(enh, mpd, msd, tf, mr, g_opt, d_opt, n, c, sargs, after_d_backward=sync_d,
                           after_g_backward=sync_g)
 
@@ -251,7 +267,7 @@ def main():
         out = step(noisy_d, clean_d)
     e1.record()
     barrier()
-    launches = _lib.kernel_launches()
+    launches = _lib.kernel_launches() if graphed is None else graphed.launches_per_step * args.steps
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
@@ -262,9 +278,10 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        n = noisy_h.to(dev, non_blocking=True)
-        c = clean_h.to(dev, non_blocking=True)
-        out = step(n, c)
+        if graphed is not None:
+            out = step(noisy_h, clean_h)              # H2D from pinned memory into the graph's static inputs
+        else:
+            out = step(noisy_h.to(dev, non_blocking=True), clean_h.to(dev, non_blocking=True))
         res = torch.stack([out[k] for k in ("d_loss", "g_loss", "mr", "mask", "adv", "fm")])
         res_h.copy_(res, non_blocking=True)
     e1.record()
@@ -287,9 +304,9 @@ def main():
                          f"torch CPU ops, {cores} threads)", "ms_per_step": ms}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 tensor-core operands for the dense contraction (fp32 accumulate), f32 elsewhere",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "gan_loss": args.gan_loss, "parallelism": f"dp{world}",
+        "config": {"workload": WORKLOAD, "gan_loss": args.gan_loss, "parallelism": f"dp{world}", "cuda_graph": graphed is not None,
                    "l2": "no explicit flush: one step streams > 2 GB of activations (>> 126 MB L2)"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,

@@ -67,34 +67,84 @@ def test_dense_conv_fwd_dgrad_wgrad(dev, B, L, Ci, Co):
     assert rel_err(db, dy.sum((0, 2))) < 1e-4
 
 
+class _BF16DenseConv(torch.autograd.Function):
+    """CPU emulation of the tensor-core layer's arithmetic contract: every GEMM operand (x, w, dy) is rounded to
+    bf16, products are accumulated exactly (fp64 here, fp32 on the GPU); bias and its gradient stay fp32."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, pad):
+        ctx.save_for_backward(x, w)
+        ctx.pad = pad
+        return (F.conv1d(_bf(x), _bf(w), None, padding=pad) + b.double()[None, :, None]).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        gq = _bf(g)
+        dx = F.conv_transpose1d(gq, _bf(w), padding=ctx.pad)
+        dw = torch.nn.grad.conv1d_weight(_bf(x), w.shape, gq, padding=ctx.pad)
+        return dx.to(x.dtype), dw.to(w.dtype), g.sum((0, 2)), None
+
+
+def _msd_forward_emulated(O, P, x):
+    """oracle.msd_forward with convs.5 replaced by the bf16-operand emulation above."""
+    x = x.unsqueeze(1)
+    logits, fmaps = [], []
+    for i in range(3):
+        pre = f"discriminators.{i}."
+        h, fm = x, []
+        for j, (_, k, s, g) in enumerate(O.MSD_LAYERS):
+            w = O.weight_norm_weight(P[f"{pre}convs.{j}.weight_g"], P[f"{pre}convs.{j}.weight_v"])
+            b = P[f"{pre}convs.{j}.bias"]
+            if j == 5:
+                h = F.leaky_relu(_BF16DenseConv.apply(h, w, b, k // 2), 0.2)
+            else:
+                h = F.leaky_relu(F.conv1d(h, w, b, stride=s, padding=k // 2, groups=g), 0.2)
+            fm.append(h)
+        w = O.weight_norm_weight(P[pre + "conv_post.weight_g"], P[pre + "conv_post.weight_v"])
+        h = F.conv1d(h, w, P[pre + "conv_post.bias"], padding=1)
+        fm.append(h)
+        logits.append(h)
+        fmaps.append(fm)
+        x = O.msd_pool(x)
+    return logits, fmaps
+
+
 def test_msd_bf16_matches_oracle(dev):
-    """Whole MultiScaleDiscriminator with the tensor-core layer on: forward maps, input gradient and parameter
-    gradients against the fp32 CPU oracle at the stated bf16 tolerance (2e-2 relative to each tensor's max)."""
+    """Whole MultiScaleDiscriminator with the tensor-core layer on.
+    (1) against the oracle with convs.5's operands rounded to bf16 (same arithmetic contract): 2e-3 relative L2
+        on every feature map, the input gradient and every parameter gradient;
+    (2) against the plain fp32 oracle: 2e-2 relative to the max on the feature maps and the input gradient
+        (bf16 has 8 mantissa bits; stated tolerance of the bf16 training configuration)."""
     from models.discriminators import MultiScaleDiscriminator
     O = oracle()
     torch.manual_seed(1)
     msd = MultiScaleDiscriminator()
     P = leaf_params(cpu_params(msd))
+    P32 = leaf_params(cpu_params(msd))
     msd = msd.to(dev)
     x = torch.randn(2, 8000, generator=torch.Generator().manual_seed(10)) * 0.1
     xr = x.clone().requires_grad_(True)
-    lr, fr = O.msd_forward(P, xr)
+    x32 = x.clone().requires_grad_(True)
+    lr, fr = _msd_forward_emulated(O, P, xr)
+    l32, f32 = O.msd_forward(P32, x32)
     xg = x.to(dev).requires_grad_(True)
     lg, fg = msd(xg)
-    loss_r, loss_g = 0.0, 0.0
+    loss_r, loss_g, loss_32 = 0.0, 0.0, 0.0
     gen = torch.Generator().manual_seed(11)
+    l2 = lambda a, b: ((a.detach().cpu().double() - b.detach().double()).norm() / b.detach().double().norm()).item()
     for i in range(3):
-        for a, b in zip(fg[i], fr[i]):
-            assert rel_err(a, b) < 2e-2
+        for a, b, c in zip(fg[i], fr[i], f32[i]):
+            assert l2(a, b) < 2e-3
+            assert rel_err(a, c) < 2e-2
             gw = torch.randn(b.shape, generator=gen) / b.numel() ** 0.5
             loss_r = loss_r + (b * gw).sum()
+            loss_32 = loss_32 + (c * gw).sum()
             loss_g = loss_g + (a * gw.to(dev)).sum()
     loss_r.backward()
+    loss_32.backward()
     loss_g.backward()
-    assert rel_err(xg.grad, xr.grad) < 2e-2
-    # parameter gradients: relative L2 error.  (A max-norm bar is not meaningful here: a bf16-sized change of a
-    # pre-activation that sits at ~0 flips LeakyReLU' between 1 and 0.2 for that element, which moves a 64-term
-    # bias-gradient sum by several percent - the same happens under torch autocast.)
+    assert l2(xg.grad, xr.grad) < 2e-3
+    assert rel_err(xg.grad, x32.grad) < 2e-2
     for k, p in msd.named_parameters():
-        a, b = p.grad.detach().cpu().double(), P[k].grad.double()
-        assert ((a - b).norm() / b.norm()).item() < 2e-2, k
+        assert l2(p.grad, P[k].grad) < 2e-3, k
