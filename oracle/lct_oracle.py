@@ -47,9 +47,9 @@ MSD_LAYERS = ((16, 15, 1, 1), (64, 41, 4, 4), (256, 41, 4, 16), (1024, 41, 4, 64
 # --------------------------------------------------------------------------------------
 
 def hann_window(n: int) -> torch.Tensor:
-    """Periodic Hann, fp32, as registered by ComplexSTFT.__init__ (stft.py:56-57)."""
-    k = torch.arange(n, dtype=torch.float64)
-    return (0.5 - 0.5 * torch.cos(2.0 * math.pi * k / n)).to(torch.float32)
+    """Periodic Hann as registered by ComplexSTFT.__init__ (stft.py:56-57): torch.hann_window evaluates
+    0.5 - 0.5 cos(2 pi k / n) in fp32, and the reference uses exactly that buffer (golden: window_*)."""
+    return torch.hann_window(n)
 
 
 def stft(x: torch.Tensor, window: torch.Tensor, n_fft: int, hop: int) -> torch.Tensor:

@@ -1,0 +1,127 @@
+"""The CUDA path against the golden vectors produced by the UNMODIFIED REFERENCE (tests/golden/golden_v1.pt),
+without the oracle in between: same seed -> same initial weights -> same outputs and training losses."""
+import os
+
+import pytest
+import torch
+
+from util import rel_err
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v1.pt")
+
+
+@pytest.fixture(scope="module")
+def G():
+    return torch.load(GOLD, weights_only=False)
+
+
+def _sub(t, n=4096):
+    f = t.detach().reshape(-1)
+    if f.numel() <= n:
+        return f.clone()
+    return f[torch.linspace(0, f.numel() - 1, n).long().to(f.device)].clone()
+
+
+def test_front_end_vs_reference_vectors(dev, G):
+    from datasets.stft import ComplexSTFT, STFTConfig, apply_mask, compress, compute_compressed_irm, magnitude
+    from datasets.tf_features import TFFeatures, TFFeaturesConfig
+    noisy, clean = (t.to(dev) for t in G["front_inputs"])
+    for n_fft, hop in ((512, 256), (320, 160), (768, 384)):
+        m = ComplexSTFT(STFTConfig(n_fft=n_fft, hop_length=hop)).to(dev)
+        assert torch.equal(m.window.cpu(), G[f"window_{n_fft}"])
+        s = m(noisy)
+        assert rel_err(torch.view_as_real(s.contiguous()), G[f"stft_{n_fft}"]) < 1e-5
+        assert rel_err(m.istft(s * 0.7, length=3900), G[f"istft_{n_fft}"]) < 1e-5
+    st = ComplexSTFT(STFTConfig()).to(dev)
+    s, c = st(noisy), st(clean)
+    assert rel_err(magnitude(s), G["magnitude"]) < 1e-5
+    assert rel_err(compress(magnitude(s)), G["compress"]) < 1e-5
+    assert rel_err(compute_compressed_irm(c, s), G["irm_c"]) < 5e-5
+    assert rel_err(torch.view_as_real(apply_mask(s, G["mask_in"].to(dev), compressed=True).contiguous()),
+                   G["apply_mask_c"]) < 1e-5
+    tf = TFFeatures(TFFeaturesConfig(return_stfts=False)).to(dev)(noisy, clean)
+    for k, v in G["tf_features"].items():
+        assert rel_err(tf[k], v) < 5e-5, k
+
+
+def test_models_vs_reference_vectors(dev, G):
+    from lctgan.training import build_models
+    import losses as L
+    enh, mpd, msd, tf, mr, _, _ = build_models(dev, gan_seed=42)
+    noisy, clean = (t.to(dev) for t in G["model_inputs"])
+    with torch.no_grad():
+        e, mask = enh(noisy)
+        assert rel_err(e, G["enhanced"]) < 5e-5
+        assert rel_err(_sub(mask.contiguous()), G["mask_c_sub"]) < 5e-5
+        assert torch.equal(mask[..., -3:].cpu(), G["mask_c_tail"])
+        pl, pf = mpd(clean)
+        sl, sf = msd(clean)
+        for a, b in zip(pl + sl, G["mpd_logits"] + G["msd_logits"]):
+            assert a.shape == b.shape and rel_err(a, b) < 5e-5
+        assert [[tuple(t.shape) for t in f] for f in pf] == G["mpd_fmap_shapes"]
+        assert [[tuple(t.shape) for t in f] for f in sf] == G["msd_fmap_shapes"]
+        for fa, fb in zip(pf + sf, G["mpd_fmap_sub"] + G["msd_fmap_sub"]):
+            for a, b in zip(fa, fb):
+                assert rel_err(_sub(a, 512), b) < 5e-5
+        eg = G["enhanced"].to(dev)
+        fl, ff = mpd(eg)
+        fsl, _ = msd(eg)
+        assert abs(L.feature_matching_loss(pf, ff).item() - G["fm_loss"]) < 1e-6
+        assert abs(L.discriminator_loss(pl + sl, fl + fsl, "ls").item() - G["d_loss_ls"]) < 1e-5
+        assert abs(L.discriminator_loss(pl + sl, fl + fsl, "hinge").item() - G["d_loss_hinge"]) < 1e-5
+        assert abs(L.generator_adv_loss(fl, "ls").item() - G["g_adv_ls"]) < 1e-5
+        assert abs(L.generator_adv_loss(fl, "hinge").item() - G["g_adv_hinge"]) < 1e-5
+        mrl, det = mr(eg, clean)
+        assert abs(mrl.item() - G["mrstft"][0]) < 2e-5
+        for k, v in G["mrstft"][1].items():
+            assert abs(det[k].item() - v) < 2e-5
+
+
+@pytest.mark.parametrize("gan_loss", ["ls", "hinge"])
+def test_training_step_vs_reference_train_one_epoch(dev, G, gan_loss):
+    """Two D+G steps vs the reference's own train_one_epoch log (values printed with 4 decimals)."""
+    from lctgan.training import StepArgs, build_models, train_step
+    enh, mpd, msd, tf, mr, g_opt, d_opt = build_models(dev, gan_seed=42)
+    noisy, clean = (t.to(dev) for t in G["model_inputs"])
+    names = {"D_loss": "d_loss", "G_loss": "g_loss", "MR": "mr", "Mask": "mask", "Adv": "adv", "FM": "fm"}
+    for step in range(2):
+        got = train_step(enh, mpd, msd, tf, mr, g_opt, d_opt, noisy, clean, StepArgs(gan_loss=gan_loss))
+        for ref_k, k in names.items():
+            ref = G[f"train_{gan_loss}"]["logs"][step][ref_k]
+            assert abs(got[k].item() - ref) <= 1.01e-4 + 1e-3 * abs(ref) * step, (step, k, got[k].item(), ref)
+    ref = G[f"train_{gan_loss}"]
+    assert abs(float(sum(p.double().sum() for p in enh.parameters())) - ref["enh_checksum"]) < 5e-3
+
+
+@pytest.mark.bf16
+def test_training_step_bf16_vs_reference_log(dev, G):
+    """Same two steps with the tcgen05 bf16 dense layer on (BASELINE configs[2]): losses within 5e-3 relative
+    (stated bf16 tolerance; only MSD convs.5 changes precision) of the reference's fp32 log."""
+    from lctgan.training import StepArgs, build_models, train_step
+    enh, mpd, msd, tf, mr, g_opt, d_opt = build_models(dev, gan_seed=42)
+    noisy, clean = (t.to(dev) for t in G["model_inputs"])
+    names = {"D_loss": "d_loss", "G_loss": "g_loss", "MR": "mr", "Mask": "mask", "Adv": "adv", "FM": "fm"}
+    for step in range(2):
+        got = train_step(enh, mpd, msd, tf, mr, g_opt, d_opt, noisy, clean, StepArgs(gan_loss="ls"))
+        for ref_k, k in names.items():
+            ref = G["train_ls"]["logs"][step][ref_k]
+            assert abs(got[k].item() - ref) <= 1.01e-4 + 5e-3 * abs(ref), (step, k, got[k].item(), ref)
+
+
+def test_graphed_step_equals_eager(dev):
+    """The CUDA-graph replay of the step produces the same losses as eager launches (same kernels, same order)."""
+    from lctgan.training import GraphedTrainStep, StepArgs, build_models, train_step
+    from util import oracle
+    O = oracle()
+    noisy, clean = (t.to(dev) for t in O.synthetic_batch(2, 8000, seed=5))
+    a = build_models(dev, gan_seed=3, capturable=True)
+    b = build_models(dev, gan_seed=3, capturable=True)
+    args = StepArgs(gan_loss="ls")
+    eager = [train_step(*a, noisy, clean, args) for _ in range(5)]
+    eager = [{k: v.item() for k, v in d.items()} for d in eager]
+    g = GraphedTrainStep(*b, noisy.clone(), clean.clone(), args, warmup=3)      # 3 eager warm-up steps + capture
+    assert g.launches_per_step > 500
+    got = {k: v.item() for k, v in g().items()}                                  # first replay = step 5
+    for k in got:
+        assert abs(got[k] - eager[4][k]) <= 2e-3 * max(abs(eager[4][k]), 1e-3), (k, got[k], eager[4][k])
