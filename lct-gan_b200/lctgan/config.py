@@ -12,3 +12,22 @@ def set_precision(mode: str) -> None:
     if mode not in ("bf16", "fp32"):
         raise ValueError(f"unknown precision mode {mode!r}")
     dense_tensor_cores = (mode == "bf16")
+
+
+#: Run the independent sub-discriminators (5 periods, 3 scales) on parallel CUDA streams (forked from and joined
+#: to the caller's stream; autograd replays the same streams in backward).  Each sub-discriminator is a chain of
+#: kernels that fill at most one wave of the 148 SMs at batch 8, so the chains are overlapped; inside a captured
+#: CUDA graph they become parallel branches.
+concurrent_discriminators = True
+
+_STREAMS = {}
+
+
+def side_streams(n: int, device):
+    """n persistent side streams for `device` (created once)."""
+    import torch
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    pool = _STREAMS.setdefault(key, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=device))
+    return pool[:n]

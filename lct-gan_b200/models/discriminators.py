@@ -16,8 +16,26 @@ import torch
 import torch.nn as nn
 from torch.nn.utils import spectral_norm, weight_norm
 
+from lctgan import config as _cfg
 from lctgan import functional as LF
 from lctgan.disc_impl import conv_stack
+
+
+def _run_concurrently(discs, inputs):
+    """Evaluate discs[i](inputs[i]) for all i, each on its own CUDA stream (fork/join around the caller's stream)."""
+    x0 = inputs[0]
+    if not (_cfg.concurrent_discriminators and x0.is_cuda and len(discs) > 1):
+        return [d(x) for d, x in zip(discs, inputs)]
+    cur = torch.cuda.current_stream(x0.device)
+    streams = _cfg.side_streams(len(discs), x0.device)
+    out = [None] * len(discs)
+    for i, (d, x, s) in enumerate(zip(discs, inputs, streams)):
+        s.wait_stream(cur)
+        with torch.cuda.stream(s):
+            out[i] = d(x)
+    for s in streams:
+        cur.wait_stream(s)
+    return out
 
 # (out_channels, kernel, stride, groups)
 _PERIOD_LAYERS = ((32, 5, 3, 1), (128, 5, 3, 4), (512, 5, 3, 16), (1024, 5, 3, 64), (1024, 5, 1, 64))
@@ -87,13 +105,8 @@ class MultiPeriodDiscriminator(nn.Module):
             [PeriodDiscriminator(p, use_spectral_norm=use_spectral_norm) for p in periods])
 
     def forward(self, x: torch.Tensor) -> Tuple[List[torch.Tensor], List[List[torch.Tensor]]]:
-        logits_list: List[torch.Tensor] = []
-        fmaps_list: List[List[torch.Tensor]] = []
-        for disc in self.discriminators:
-            logits, fmaps = disc(x)
-            logits_list.append(logits)
-            fmaps_list.append(fmaps)
-        return logits_list, fmaps_list
+        res = _run_concurrently(list(self.discriminators), [x] * len(self.discriminators))
+        return [r[0] for r in res], [r[1] for r in res]
 
 
 class ScaleDiscriminator(_SubDiscriminator):
@@ -139,12 +152,10 @@ class MultiScaleDiscriminator(nn.Module):
             x = x.unsqueeze(1)
         B, C, T = x.shape
         x_scale = x.reshape(B, T) if C == 1 else x
-        logits_list: List[torch.Tensor] = []
-        fmaps_list: List[List[torch.Tensor]] = []
-        for i, disc in enumerate(self.discriminators):
-            logits, fmaps = disc(x_scale if x_scale.dim() == 3 else x_scale.unsqueeze(1))
-            logits_list.append(logits)
-            fmaps_list.append(fmaps)
+        inputs = []
+        for i in range(len(self.discriminators)):
+            inputs.append(x_scale if x_scale.dim() == 3 else x_scale.unsqueeze(1))
             if i + 1 < len(self.discriminators):   # the reference pools once more and discards the result
                 x_scale = LF.AvgPool4Fn.apply(x_scale)
-        return logits_list, fmaps_list
+        res = _run_concurrently(list(self.discriminators), inputs)
+        return [r[0] for r in res], [r[1] for r in res]
