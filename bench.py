@@ -212,7 +212,7 @@ def main():
     from lctgan.training import GraphedTrainStep, StepArgs, build_models, train_step
     from oracle import lct_oracle as O
 
-    use_graph = (not args.no_graph) and world == 1
+    use_graph = not args.no_graph
     enh, mpd, msd, tf, mr, g_opt, d_opt = build_models(dev, gan_seed=42, capturable=use_graph)
     if world > 1:
         broadcast_parameters([enh, mpd, msd])
@@ -228,7 +228,9 @@ def main():
     graphed = None
     if use_graph:
         # the whole D+G step (forward, backward, clip, both AdamW updates) as one CUDA graph over static buffers
-        graphed = GraphedTrainStep(enh, mpd, msd, tf, mr, g_opt, d_opt, noisy_d, clean_d, sargs, warmup=3)
+        # (with N > 1: three graphs with the two NCCL gradient all-reduces launched eagerly in between)
+        graphed = GraphedTrainStep(enh, mpd, msd, tf, mr, g_opt, d_opt, noisy_d, clean_d, sargs, after_d_backward=sync_d,
+                                   after_g_backward=sync_g, warmup=3)
 
     def step(n, c):
         if graphed is not None:

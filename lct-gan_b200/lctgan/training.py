@@ -34,14 +34,10 @@ def _align_tf_targets(irm_c: torch.Tensor, pred_mask_c: torch.Tensor):
     return irm_c[..., :t], pred_mask_c[..., :t]
 
 
-def train_step(enhancer, mpd, msd, tf_features, mrstft_loss, g_opt, d_opt, noisy: torch.Tensor,
-               clean: torch.Tensor, args: StepArgs, after_d_backward=None,
-               after_g_backward=None) -> Dict[str, torch.Tensor]:
-    """One D step + one G step.  Returns the loss tensors (on device; no host sync happens here).
-    ``after_*_backward`` are the data-parallel hooks (gradient all-reduce) of lctgan.parallel."""
-    irm_c = tf_features(noisy, clean)["irm_c"]
-
-    # ---- discriminator step (train.py:177-200)
+def _phase_d(M, noisy, clean, args: StepArgs, st: dict) -> None:
+    """TF features + discriminator forward/backward (train.py:171-199)."""
+    enhancer, mpd, msd, tf_features, mrstft_loss, g_opt, d_opt = M
+    st["irm_c"] = tf_features(noisy, clean)["irm_c"]
     d_opt.zero_grad(set_to_none=True)
     with torch.no_grad():
         enhanced_for_d, _ = enhancer(noisy)
@@ -52,15 +48,17 @@ def train_step(enhancer, mpd, msd, tf_features, mrstft_loss, g_opt, d_opt, noisy
     d_loss = L.discriminator_loss(L._flatten_logits_lists(mpd_real, msd_real),
                                   L._flatten_logits_lists(mpd_fake, msd_fake), args.gan_loss)
     d_loss.backward()
-    if after_d_backward is not None:
-        after_d_backward()
-    d_opt.step()
+    st["d_loss"] = d_loss.detach()
 
-    # ---- generator step (train.py:205-249)
+
+def _phase_g(M, noisy, clean, args: StepArgs, st: dict) -> None:
+    """Discriminator update + generator forward/backward (train.py:200-245)."""
+    enhancer, mpd, msd, tf_features, mrstft_loss, g_opt, d_opt = M
+    d_opt.step()
     g_opt.zero_grad(set_to_none=True)
     enhanced, mask_c = enhancer(noisy)
     mr_loss, _ = mrstft_loss(enhanced, clean)
-    irm_al, pred_al = _align_tf_targets(irm_c, mask_c[:, 0])
+    irm_al, pred_al = _align_tf_targets(st["irm_c"], mask_c[:, 0])
     m_loss = L.mask_mse_loss(pred_al, irm_al)
     mpd_fake_g, mpd_fake_f = mpd(enhanced)
     msd_fake_g, msd_fake_f = msd(enhanced)
@@ -71,13 +69,36 @@ def train_step(enhancer, mpd, msd, tf_features, mrstft_loss, g_opt, d_opt, noisy
     fm_loss = L.feature_matching_loss(mpd_real_f + msd_real_f, mpd_fake_f + msd_fake_f)
     g_loss = mr_loss + args.lambda_mask * m_loss + args.lambda_adv * (adv_loss + args.lambda_fm * fm_loss)
     g_loss.backward()
-    if after_g_backward is not None:
-        after_g_backward()
+    st.update(g_loss=g_loss.detach(), mr=mr_loss.detach(), mask=m_loss.detach(), adv=adv_loss.detach(),
+              fm=fm_loss.detach())
+
+
+def _phase_opt_g(M, args: StepArgs) -> None:
+    """Gradient clipping + generator update (train.py:246-249)."""
+    enhancer, g_opt = M[0], M[5]
     if args.grad_clip > 0.0:
         torch.nn.utils.clip_grad_norm_(enhancer.parameters(), args.grad_clip)
     g_opt.step()
-    return {"d_loss": d_loss.detach(), "g_loss": g_loss.detach(), "mr": mr_loss.detach(), "mask": m_loss.detach(),
-            "adv": adv_loss.detach(), "fm": fm_loss.detach()}
+
+
+_OUT_KEYS = ("d_loss", "g_loss", "mr", "mask", "adv", "fm")
+
+
+def train_step(enhancer, mpd, msd, tf_features, mrstft_loss, g_opt, d_opt, noisy: torch.Tensor,
+               clean: torch.Tensor, args: StepArgs, after_d_backward=None,
+               after_g_backward=None) -> Dict[str, torch.Tensor]:
+    """One D step + one G step.  Returns the loss tensors (on device; no host sync happens here).
+    ``after_*_backward`` are the data-parallel hooks (gradient all-reduce) of lctgan.parallel."""
+    M = (enhancer, mpd, msd, tf_features, mrstft_loss, g_opt, d_opt)
+    st: dict = {}
+    _phase_d(M, noisy, clean, args, st)
+    if after_d_backward is not None:
+        after_d_backward()
+    _phase_g(M, noisy, clean, args, st)
+    if after_g_backward is not None:
+        after_g_backward()
+    _phase_opt_g(M, args)
+    return {k: st[k] for k in _OUT_KEYS}
 
 
 def build_models(device, gan_seed: Optional[int] = 42, max_time_context: Optional[int] = 200,
@@ -101,34 +122,68 @@ def build_models(device, gan_seed: Optional[int] = 42, max_time_context: Optiona
 
 
 class GraphedTrainStep:
-    """The whole D+G step captured once into a CUDA graph and replayed.
+    """The whole D+G step captured once into CUDA graphs and replayed.
 
     At batch 8 the step is ~1100 small kernel launches; replaying a graph removes the per-launch host cost
-    (Python, ctypes, autograd bookkeeping, allocator) and lets the GPU run the kernels back to back.
-    Inputs live in static device buffers (`noisy`, `clean`): copy new data into them, then call the object.
-    The optimisers must have been built with ``capturable=True``.
+    (Python, ctypes, autograd bookkeeping, allocator) and lets the GPU run the kernels back to back, the
+    sub-discriminators as parallel branches.  Inputs live in static device buffers (`noisy`, `clean`): copy new
+    data into them, then call the object.  The optimisers must have been built with ``capturable=True``.
+
+    Single GPU: one graph.  Data parallel (hooks given): three graphs sharing one memory pool - [D forward +
+    backward] | [D update, G forward + backward] | [clip, G update] - with the two NCCL gradient all-reduces
+    launched eagerly in between (the collectives themselves are not captured).
     """
 
     def __init__(self, enhancer, mpd, msd, tf_features, mrstft_loss, g_opt, d_opt, noisy, clean, args: StepArgs,
                  after_d_backward=None, after_g_backward=None, warmup: int = 3):
+        from . import _lib
         self.noisy, self.clean = noisy, clean
-        run = lambda: train_step(enhancer, mpd, msd, tf_features, mrstft_loss, g_opt, d_opt, self.noisy, self.clean,
-                                 args, after_d_backward=after_d_backward, after_g_backward=after_g_backward)
+        self.hooks = (after_d_backward, after_g_backward)
+        M = (enhancer, mpd, msd, tf_features, mrstft_loss, g_opt, d_opt)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):
-                run()
+                train_step(*M, self.noisy, self.clean, args, after_d_backward=after_d_backward,
+                           after_g_backward=after_g_backward)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        from . import _lib
-        self.graph = torch.cuda.CUDAGraph()
         n0 = _lib.kernel_launches()
-        with torch.cuda.graph(self.graph):
-            self.out = run()
-        #: lctgan kernel launches recorded in the graph (= launches per replayed step)
+        st: dict = {}
+        if after_d_backward is None and after_g_backward is None:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                _phase_d(M, self.noisy, self.clean, args, st)
+                _phase_g(M, self.noisy, self.clean, args, st)
+                _phase_opt_g(M, args)
+            self.graphs = [g]
+        else:
+            pool = torch.cuda.graph_pool_handle()
+            g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1, pool=pool):
+                _phase_d(M, self.noisy, self.clean, args, st)
+            if after_d_backward is not None:
+                after_d_backward()
+            with torch.cuda.graph(g2, pool=pool):
+                _phase_g(M, self.noisy, self.clean, args, st)
+            if after_g_backward is not None:
+                after_g_backward()
+            with torch.cuda.graph(g3, pool=pool):
+                _phase_opt_g(M, args)
+            self.graphs = [g1, g2, g3]
+        self.out = {k: st[k] for k in _OUT_KEYS}
+        #: lctgan kernel launches recorded in the graphs (+ the eager gradient gather/scatter) = per replayed step
         self.launches_per_step = _lib.kernel_launches() - n0
 
     def __call__(self) -> Dict[str, torch.Tensor]:
-        self.graph.replay()
+        if len(self.graphs) == 1:
+            self.graphs[0].replay()
+        else:
+            self.graphs[0].replay()
+            if self.hooks[0] is not None:
+                self.hooks[0]()
+            self.graphs[1].replay()
+            if self.hooks[1] is not None:
+                self.hooks[1]()
+            self.graphs[2].replay()
         return self.out

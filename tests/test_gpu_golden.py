@@ -125,3 +125,24 @@ def test_graphed_step_equals_eager(dev):
     got = {k: v.item() for k, v in g().items()}                # capture executes nothing: first replay = 4th step
     for k in got:
         assert abs(got[k] - eager[3][k]) <= 2e-3 * max(abs(eager[3][k]), 1e-3), (k, got[k], eager[3][k])
+
+
+def test_segmented_graphs_equal_eager(dev):
+    """The data-parallel variant (three graphs, hooks run eagerly in between) also reproduces eager execution."""
+    from lctgan.training import GraphedTrainStep, StepArgs, build_models, train_step
+    from util import oracle
+    O = oracle()
+    noisy, clean = (t.to(dev) for t in O.synthetic_batch(2, 8000, seed=6))
+    a = build_models(dev, gan_seed=4, capturable=True)
+    b = build_models(dev, gan_seed=4, capturable=True)
+    args = StepArgs(gan_loss="hinge")
+    calls = []
+    eager = [{k: v.item() for k, v in train_step(*a, noisy, clean, args).items()} for _ in range(5)]
+    g = GraphedTrainStep(*b, noisy.clone(), clean.clone(), args, after_d_backward=lambda: calls.append("d"),
+                         after_g_backward=lambda: calls.append("g"), warmup=3)
+    assert len(g.graphs) == 3
+    for step in (3, 4):
+        got = {k: v.item() for k, v in g().items()}
+        for k in got:
+            assert abs(got[k] - eager[step][k]) <= 2e-3 * max(abs(eager[step][k]), 1e-3), (step, k, got[k], eager[step][k])
+    assert calls == ["d", "g"] * 6     # 3 warm-up + 1 capture + 2 replays
