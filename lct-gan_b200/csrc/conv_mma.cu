@@ -1,0 +1,574 @@
+// Grouped strided convolutions of the waveform discriminators on the tensor cores (TF32 mma.sync,
+// fp32 accumulate), forward + data gradient + weight gradient.
+//
+// Same operator as conv_disc.cu (reference models/discriminators.py:37-67, :93-98, :166-196, :215-220):
+// a convolution along L of [B, C, L, P] with groups, stride S, "same" padding.  conv_disc.cu is the
+// fp32 SIMT version (kept for exact-fp32 mode); profiling showed it latency/issue bound (fma pipe 18-41 %,
+// top stall long_scoreboard, < 1 wave per launch), so this file restructures the work as an implicit GEMM:
+//
+//   * per group:  D[position, n] = sum_kk A[position, kk] * W[kk, n]   with A gathered on the fly from a
+//     shared-memory window of the input (no im2col buffer).  Forward: kk = (ci, tap), n = out channel.
+//     Data gradient in polyphase form: kk = (co, t), n = in channel, one weight set per stride phase r
+//     (k = r + S t), all S phases share the same A fragments.
+//   * persistent CTAs (one group each, looping over (batch, position tile)) with the next tile's window
+//     prefetched by cp.async (4-byte copies, zero-fill for the padding) while the current one is multiplied:
+//     the staging latency that dominated the SIMT kernels is overlapped.
+//   * m16n8k8 TF32 fragments are read straight from the window (rows = 8 consecutive positions, columns =
+//     4 consecutive taps -> 32 consecutive words for S <= 4: conflict free) and rounded with cvt.rna; weights
+//     are rounded once when the CTA stages them.
+//   * weight gradient: M = out channels, N = (ci, tap), K = positions; each warp keeps the whole dW tile of
+//     its group in registers over its share of the positions and finishes with atomics.
+//
+// Precision: TF32 operands (10-bit mantissa), fp32 accumulation - the "bf16 training" configuration of
+// BASELINE.json (configs[2]) at higher operand precision than bf16.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 128;   // 4 warps
+enum { MODE_FWD = 0, MODE_DGRAD = 1 };
+
+struct MmaParams {
+    const float* x;        // gathered tensor  [B][Cx][Lx][P]   (fwd: input, dgrad: dY)
+    const float* w;        // conv weight      [Cout][Cin_g][K]
+    float* out;            // fwd: y [B][Cout][Lout][P];  dgrad: dx [B][Cin][Lin][P]
+    const float* bias;     // fwd
+    const float* gextra;   // dgrad (optional)
+    const float* xact;     // dgrad (optional)
+    int B, Cx, Cxg, Lx, P, Co, N, Lo;      // Co = channels of `out`, N = real out-channels per group
+    int K, S, pad, Tmax;                   // conv geometry (Tmax = ceil(K / S))
+    int Sg, pad_eff, Tspan, opad, Q;       // gather stride, window origin shift, taps spanned, output shift, rows
+    int KK, KKpad, Npad, NS, WS;
+    int act; float slope;
+    int tiles_per_b, ntiles;
+};
+
+__device__ __forceinline__ uint32_t f2tf32(float v) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+    return u;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                         uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async4(float* dst, const float* src, bool valid) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(dst);
+    const int n = valid ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(s), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// stage the input window of `tile` (all Cxg channels of group g) into `buf` with cp.async
+__device__ __forceinline__ void stage_window(const MmaParams& p, int g, int tile, int TP, float* buf) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = tile / p.tiles_per_b, jt = tile - b * p.tiles_per_b;
+    const int j0 = jt * TP;
+    const int jend = min(j0 + TP, p.Q * p.P);
+    const int row_first = j0 / p.P, row_last = (jend - 1) / p.P;
+    const int n_e = ((row_last - row_first) * p.Sg + p.Tspan) * p.P;
+    const int e0 = (row_first * p.Sg - p.pad_eff) * p.P;   // flat start inside a channel (may be negative)
+    const int lim = p.Lx * p.P;
+    for (int ch = warp; ch < p.Cxg; ch += kThreads / 32) {
+        const float* src = p.x + ((size_t)b * p.Cx + (size_t)g * p.Cxg + ch) * lim;
+        float* dst = buf + ch * p.WS;
+        for (int e = lane; e < n_e; e += 32) {
+            const int f = e0 + e;
+            const bool ok = f >= 0 && f < lim;
+            cp_async4(dst + e, ok ? src + f : p.x, ok);
+        }
+    }
+}
+
+template <int MODE, int NT, int NPH, int MTW>
+__global__ void __launch_bounds__(kThreads) conv_mma_kernel(const MmaParams p) {
+    extern __shared__ __align__(16) float sm[];
+    constexpr int TP = 32 * MTW * (kThreads / 32) / 2;   // MTW m-tiles of 16 positions per warp
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int gq = lane >> 2, tq = lane & 3;
+    const int g = blockIdx.x;
+    float* wsm = sm;                                              // [NPH][KKpad][NS]
+    int* lut = reinterpret_cast<int*>(wsm + NPH * p.KKpad * p.NS);  // [KKpad]
+    float* win0 = reinterpret_cast<float*>(lut + p.KKpad);
+    const int winsz = p.Cxg * p.WS;
+    float* win1 = win0 + winsz;
+
+    // ---- prologue: this group's weights (tf32-rounded, [phase][kk][n]) and the gather LUT
+    for (int idx = tid; idx < NPH * p.KKpad * p.Npad; idx += kThreads) {
+        const int n = idx % p.Npad;
+        const int t2 = idx / p.Npad;
+        const int kk = t2 % p.KKpad;
+        const int r = t2 / p.KKpad;
+        float v = 0.f;
+        if (kk < p.KK && n < p.N) {
+            if (MODE == MODE_FWD) {
+                // kk = ci*K + tap; w[(g*N + n)][ci][tap] is contiguous in kk
+                v = p.w[((size_t)g * p.N + n) * p.KK + kk];
+            } else {
+                const int co = kk / p.Tmax, t = kk - co * p.Tmax;
+                const int k = r + p.S * t;
+                if (k < p.K) v = p.w[(((size_t)g * p.Cxg + co) * p.N + n) * p.K + k];
+            }
+        }
+        wsm[(r * p.KKpad + kk) * p.NS + n] = __uint_as_float(f2tf32(v));
+    }
+    for (int kk = tid; kk < p.KKpad; kk += kThreads) {
+        int off = 0;
+        if (kk < p.KK) {
+            if (MODE == MODE_FWD) {
+                const int ci = kk / p.K, tap = kk - ci * p.K;
+                off = ci * p.WS + tap * p.P;
+            } else {
+                const int co = kk / p.Tmax, t = kk - co * p.Tmax;
+                off = co * p.WS + (p.Tmax - 1 - t) * p.P;
+            }
+        }
+        lut[kk] = off;
+    }
+    int tile = blockIdx.y;
+    if (tile < p.ntiles) stage_window(p, g, tile, TP, win0);
+    cp_async_commit();
+
+    int cur = 0;
+    for (; tile < p.ntiles; tile += gridDim.y, cur ^= 1) {
+        float* win = cur ? win1 : win0;
+        cp_async_wait_all();
+        __syncthreads();                       // window `cur` (and, first time, weights/LUT) visible to all
+        const int nxt = tile + gridDim.y;
+        if (nxt < p.ntiles) stage_window(p, g, nxt, TP, cur ? win0 : win1);
+        cp_async_commit();
+
+        const int b = tile / p.tiles_per_b, jt = tile - b * p.tiles_per_b;
+        const int j0 = jt * TP;
+        const int jtot = p.Q * p.P;
+        const int row_first = j0 / p.P;
+        // per-thread rows: m-tile mt, half h -> position j0 + warp*16*MTW + mt*16 + gq + 8h
+        int base[MTW][2], rowq[MTW][2], ppos[MTW][2];
+#pragma unroll
+        for (int mt = 0; mt < MTW; ++mt)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = j0 + warp * 16 * MTW + mt * 16 + gq + 8 * h;
+                if (j < jtot) {
+                    const int rq = j / p.P, pp = j - rq * p.P;
+                    rowq[mt][h] = rq;
+                    ppos[mt][h] = pp;
+                    base[mt][h] = (rq - row_first) * p.Sg * p.P + pp;
+                } else {
+                    rowq[mt][h] = -1;
+                    ppos[mt][h] = 0;
+                    base[mt][h] = 0;
+                }
+            }
+        float acc[NPH][MTW][NT][4];
+#pragma unroll
+        for (int r = 0; r < NPH; ++r)
+#pragma unroll
+            for (int mt = 0; mt < MTW; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc[r][mt][nt][i] = 0.f;
+
+        for (int k0 = 0; k0 < p.KKpad; k0 += 8) {
+            const int l0 = lut[k0 + tq], l1 = lut[k0 + tq + 4];
+            uint32_t a[MTW][4];
+#pragma unroll
+            for (int mt = 0; mt < MTW; ++mt) {
+                a[mt][0] = f2tf32(win[l0 + base[mt][0]]);
+                a[mt][1] = f2tf32(win[l0 + base[mt][1]]);
+                a[mt][2] = f2tf32(win[l1 + base[mt][0]]);
+                a[mt][3] = f2tf32(win[l1 + base[mt][1]]);
+            }
+#pragma unroll
+            for (int r = 0; r < NPH; ++r) {
+                const float* wr = wsm + (r * p.KKpad + k0) * p.NS;
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    const uint32_t b0 = __float_as_uint(wr[tq * p.NS + nt * 8 + gq]);
+                    const uint32_t b1 = __float_as_uint(wr[(tq + 4) * p.NS + nt * 8 + gq]);
+#pragma unroll
+                    for (int mt = 0; mt < MTW; ++mt)
+                        mma_tf32(acc[r][mt][nt], a[mt][0], a[mt][1], a[mt][2], a[mt][3], b0, b1);
+                }
+            }
+        }
+        // ---- epilogue
+        const int lo_p = p.Lo * p.P;
+#pragma unroll
+        for (int r = 0; r < NPH; ++r)
+#pragma unroll
+            for (int mt = 0; mt < MTW; ++mt)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (rowq[mt][h] < 0) continue;
+                    const int row_o = NPH * rowq[mt][h] + r - p.opad;
+                    if (row_o < 0 || row_o >= p.Lo) continue;
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            const int n = nt * 8 + 2 * tq + c;
+                            if (n >= p.N) continue;
+                            const int ch = g * p.N + n;
+                            const size_t idx = ((size_t)b * p.Co + ch) * lo_p + (size_t)row_o * p.P + ppos[mt][h];
+                            float v = acc[r][mt][nt][2 * h + c];
+                            if (MODE == MODE_FWD) {
+                                if (p.bias) v += __ldg(&p.bias[ch]);
+                                v = apply_act(v, p.act, p.slope);
+                            } else {
+                                if (p.gextra) v += p.gextra[idx];
+                                if (p.xact) v *= act_grad_from_out(p.xact[idx], p.act, p.slope);
+                            }
+                            p.out[idx] = v;
+                        }
+                }
+    }
+    cp_async_wait_all();
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight gradient:  dW[g*N + n][ci][tap] += sum_{b, pos} dY[b][g*N + n][pos] * X[b][g*Cig + ci][row(pos)*S + tap - pad]
+// mma roles: M = out channel (MT m-tiles of 16), N = kk = (ci, tap) (NT n-tiles of 8), K = positions
+// ---------------------------------------------------------------------------------------------
+struct MmaWgradParams {
+    const float* x;     // [B][Cin][Lin][P]
+    const float* dy;    // [B][Cout][Lout][P]
+    float* dw;          // [Cout][Cin_g][K]  (accumulated)
+    float* db;          // [Cout] (accumulated, optional)
+    int B, Cin, Cig, Lin, P, Cout, N, Lout;
+    int K, S, pad;
+    int KK, WS, DS;
+    int tiles_per_b, ntiles;
+};
+
+template <int MT, int NT>
+__global__ void __launch_bounds__(kThreads) conv_mma_wgrad_kernel(const MmaWgradParams p) {
+    extern __shared__ __align__(16) float sm[];
+    constexpr int TP = 128;                       // positions per tile; each warp takes 32 of them
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int gq = lane >> 2, tq = lane & 3;
+    const int g = blockIdx.x;
+    const int winsz = p.Cig * p.WS;
+    const int dysz = 16 * MT * p.DS;
+    float* win0 = sm;
+    float* win1 = win0 + winsz;
+    float* dy0 = win1 + winsz;
+    float* dy1 = dy0 + dysz;
+
+    // LUT of this thread's B columns (kk = nt*8 + gq), constant over tiles
+    int lutn[NT];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        const int kk = nt * 8 + gq;
+        int off = 0;
+        if (kk < p.KK) {
+            const int ci = kk / p.K, tap = kk - ci * p.K;
+            off = ci * p.WS + tap * p.P;
+        }
+        lutn[nt] = off;
+    }
+    float acc[MT][NT][4];
+    float sdy[MT][2];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+        sdy[mt][0] = sdy[mt][1] = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
+    }
+    const int jtot = p.Lout * p.P;
+
+    auto stage = [&](int tile, float* wbuf, float* dbuf) {
+        const int b = tile / p.tiles_per_b, jt = tile - b * p.tiles_per_b;
+        const int j0 = jt * TP;
+        const int jend = min(j0 + TP, jtot);
+        const int row_first = j0 / p.P, row_last = (jend - 1) / p.P;
+        const int n_e = ((row_last - row_first) * p.S + p.K) * p.P;
+        const int e0 = (row_first * p.S - p.pad) * p.P;
+        const int lim = p.Lin * p.P;
+        for (int ch = warp; ch < p.Cig; ch += kThreads / 32) {
+            const float* src = p.x + ((size_t)b * p.Cin + (size_t)g * p.Cig + ch) * lim;
+            float* dst = wbuf + ch * p.WS;
+            for (int e = lane; e < n_e; e += 32) {
+                const int f = e0 + e;
+                const bool ok = f >= 0 && f < lim;
+                cp_async4(dst + e, ok ? src + f : p.x, ok);
+            }
+        }
+        for (int oc = warp; oc < 16 * MT; oc += kThreads / 32) {
+            const bool chok = oc < p.N;
+            const float* src = p.dy + ((size_t)b * p.Cout + (size_t)g * p.N + (chok ? oc : 0)) * jtot;
+            float* dst = dbuf + oc * p.DS;
+            for (int e = lane; e < TP; e += 32) {
+                const bool ok = chok && (j0 + e) < jtot;
+                cp_async4(dst + e, ok ? src + j0 + e : p.dy, ok);
+            }
+        }
+    };
+
+    int tile = blockIdx.y;
+    if (tile < p.ntiles) stage(tile, win0, dy0);
+    cp_async_commit();
+    int cur = 0;
+    for (; tile < p.ntiles; tile += gridDim.y, cur ^= 1) {
+        const float* win = cur ? win1 : win0;
+        const float* dyt = cur ? dy1 : dy0;
+        cp_async_wait_all();
+        __syncthreads();
+        const int nxt = tile + gridDim.y;
+        if (nxt < p.ntiles) stage(nxt, cur ? win0 : win1, cur ? dy0 : dy1);
+        cp_async_commit();
+
+        const int b = tile / p.tiles_per_b, jt = tile - b * p.tiles_per_b;
+        const int j0 = jt * TP;
+        const int row_first = j0 / p.P;
+        (void)b;
+        // this warp's 32 positions: 4 k-steps of 8
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            const int pl = warp * 32 + ks * 8;               // tile-local position of this k-step
+            int bs[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = j0 + pl + tq + 4 * h;
+                if (j < jtot) {
+                    const int rq = j / p.P, pp = j - rq * p.P;
+                    bs[h] = (rq - row_first) * p.S * p.P + pp;
+                } else {
+                    bs[h] = 0;                               // dY is zero there
+                }
+            }
+            uint32_t a[MT][4];
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                const float* d0 = dyt + (mt * 16 + gq) * p.DS + pl;
+                const float* d1 = d0 + 8 * p.DS;
+                const float v0 = d0[tq], v1 = d1[tq], v2 = d0[tq + 4], v3 = d1[tq + 4];
+                sdy[mt][0] += v0 + v2;
+                sdy[mt][1] += v1 + v3;
+                a[mt][0] = f2tf32(v0); a[mt][1] = f2tf32(v1); a[mt][2] = f2tf32(v2); a[mt][3] = f2tf32(v3);
+            }
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const uint32_t b0 = f2tf32(win[lutn[nt] + bs[0]]);
+                const uint32_t b1 = f2tf32(win[lutn[nt] + bs[1]]);
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) mma_tf32(acc[mt][nt], a[mt][0], a[mt][1], a[mt][2], a[mt][3], b0, b1);
+            }
+        }
+    }
+    cp_async_wait_all();
+    // ---- flush: reduce the 4 warps' partial tiles in shared memory (the window buffers are free now),
+    // then one atomic per (weight, CTA)
+    __syncthreads();
+    float* red = sm;                                   // [16*MT][NT*8]
+    constexpr int RS = NT * 8;
+    for (int wv = 0; wv < kThreads / 32; ++wv) {
+        if (warp == wv) {
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int oc = mt * 16 + gq + 8 * h;
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            const int kk = nt * 8 + 2 * tq + c;
+                            if (wv == 0) red[oc * RS + kk] = acc[mt][nt][2 * h + c];
+                            else red[oc * RS + kk] += acc[mt][nt][2 * h + c];
+                        }
+                }
+        }
+        __syncthreads();
+    }
+    for (int idx = tid; idx < p.N * p.KK; idx += kThreads) {
+        const int oc = idx / p.KK, kk = idx - oc * p.KK;
+        atomicAdd(&p.dw[((size_t)g * p.N + oc) * p.KK + kk], red[oc * RS + kk]);
+    }
+    if (p.db) {
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float s = sdy[mt][h];
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                const int oc = mt * 16 + gq + 8 * h;
+                if (tq == 0 && oc < p.N) atomicAdd(&p.db[g * p.N + oc], s);
+            }
+    }
+}
+
+int grid_y(int G, int ntiles) {
+    int per = (148 * 3 + G - 1) / G;     // ~3 resident CTAs per SM in total
+    if (per < 1) per = 1;
+    if (per > ntiles) per = ntiles;
+    return per;
+}
+
+template <int MODE, int NT, int NPH, int MTW>
+int launch_mma(MmaParams& p, cudaStream_t st) {
+    constexpr int TP = 32 * MTW * (kThreads / 32) / 2;
+    const int rows_max = TP / p.P + 2;
+    const int nr_max = (rows_max - 1) * p.Sg + p.Tspan;
+    p.WS = (nr_max * p.P + 3) & ~3;
+    p.tiles_per_b = (int)ceil_div64((int64_t)p.Q * p.P, TP);
+    p.ntiles = p.B * p.tiles_per_b;
+    size_t smem = ((size_t)NPH * p.KKpad * p.NS + p.KKpad + (size_t)2 * p.Cxg * p.WS) * sizeof(float);
+    if (smem > 200 * 1024) return LCT_EUNSUPPORTED;
+    if (smem > 40 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(conv_mma_kernel<MODE, NT, NPH, MTW>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    const int G = p.Cx / p.Cxg;
+    dim3 grid((unsigned)G, (unsigned)grid_y(G, p.ntiles));
+    conv_mma_kernel<MODE, NT, NPH, MTW><<<grid, kThreads, smem, st>>>(p);
+    LCT_RETURN_IF_LAUNCH_FAILED();
+    return 0;
+}
+
+template <int MODE, int NT, int NPH>
+int launch_mma_mtw(MmaParams& p, cudaStream_t st) {
+    // short layers: 128-position tiles keep more CTAs busy; big register tiles also stay at MTW = 2
+    if constexpr (NT * NPH >= 8) {
+        return launch_mma<MODE, NT, NPH, 2>(p, st);
+    } else {
+        if ((int64_t)p.Q * p.P * p.B * (p.Cx / p.Cxg) < 148 * 256) return launch_mma<MODE, NT, NPH, 2>(p, st);
+        return launch_mma<MODE, NT, NPH, 4>(p, st);
+    }
+}
+
+bool shape_ok(int64_t B, int64_t Cin, int64_t Cout, int64_t G, int64_t K, int64_t S, int64_t pad, int64_t Lin,
+              int64_t P) {
+    return B > 0 && B < 65536 && Cin > 0 && Cout > 0 && G > 0 && G < 65536 && Cin % G == 0 && Cout % G == 0 &&
+           K > 0 && K <= 64 && S >= 1 && S <= 4 && pad >= 0 && Lin > 0 && P > 0 && P <= 16 &&
+           Lin + 2 * pad >= K && Lin * P < (1LL << 28);
+}
+
+}  // namespace
+
+// 1 if the tensor-core kernels cover this layer (otherwise use lct_conv1d_*)
+LCT_API int lct_conv_mma_supported(int64_t Cin, int64_t Cout, int64_t G, int64_t K, int64_t S, int64_t P) {
+    if (G <= 0 || Cin % G || Cout % G) return 0;
+    const int64_t cig = Cin / G, cog = Cout / G;
+    if (K > 64 || S < 1 || S > 4 || S == 2 || P < 1 || P > 16) return 0;
+    if (cog > 32 || cig > 16) return 0;                 // dense layers have their own tcgen05 kernel
+    if (cig * K > 168) return 0;                        // wgrad keeps <= 21 n-tiles of dW in registers
+    return 1;
+}
+
+LCT_API int lct_conv_mma_fwd(const float* x, const float* w, const float* bias, float* y, int64_t B, int64_t Cin,
+                             int64_t Cout, int64_t G, int64_t K, int64_t S, int64_t pad, int64_t Lin, int64_t P,
+                             int act, float slope, cudaStream_t st) {
+    if (!x || !w || !y || !shape_ok(B, Cin, Cout, G, K, S, pad, Lin, P) ||
+        !lct_conv_mma_supported(Cin, Cout, G, K, S, P))
+        return LCT_EINVAL;
+    MmaParams p = {};
+    p.x = x; p.w = w; p.out = y; p.bias = bias; p.act = act; p.slope = slope;
+    p.B = (int)B; p.Cx = (int)Cin; p.Cxg = (int)(Cin / G); p.Lx = (int)Lin; p.P = (int)P;
+    p.Co = (int)Cout; p.N = (int)(Cout / G); p.Lo = (int)((Lin + 2 * pad - K) / S + 1);
+    p.K = (int)K; p.S = (int)S; p.pad = (int)pad; p.Tmax = (int)((K + S - 1) / S);
+    p.Sg = (int)S; p.pad_eff = (int)pad; p.Tspan = (int)K; p.opad = 0; p.Q = p.Lo;
+    p.KK = p.Cxg * p.K; p.KKpad = (p.KK + 7) & ~7;
+    p.Npad = (p.N + 7) & ~7; p.NS = p.Npad == 8 ? 8 : p.Npad + 8;
+    switch (p.Npad) {
+        case 8: return launch_mma_mtw<MODE_FWD, 1, 1>(p, st);
+        case 16: return launch_mma_mtw<MODE_FWD, 2, 1>(p, st);
+        case 32: return launch_mma_mtw<MODE_FWD, 4, 1>(p, st);
+        default: return LCT_EUNSUPPORTED;
+    }
+}
+
+LCT_API int lct_conv_mma_dgrad(const float* dy, const float* w, float* dx, const float* gextra, const float* xact,
+                               int64_t B, int64_t Cin, int64_t Cout, int64_t G, int64_t K, int64_t S, int64_t pad,
+                               int64_t Lin, int64_t P, int act, float slope, cudaStream_t st) {
+    if (!dy || !w || !dx || !shape_ok(B, Cin, Cout, G, K, S, pad, Lin, P) ||
+        !lct_conv_mma_supported(Cin, Cout, G, K, S, P))
+        return LCT_EINVAL;
+    MmaParams p = {};
+    p.x = dy; p.w = w; p.out = dx; p.gextra = gextra; p.xact = xact; p.act = act; p.slope = slope;
+    const int Lout = (int)((Lin + 2 * pad - K) / S + 1);
+    p.B = (int)B; p.Cx = (int)Cout; p.Cxg = (int)(Cout / G); p.Lx = Lout; p.P = (int)P;
+    p.Co = (int)Cin; p.N = (int)(Cin / G); p.Lo = (int)Lin;
+    p.K = (int)K; p.S = (int)S; p.pad = (int)pad; p.Tmax = (int)((K + S - 1) / S);
+    p.Sg = 1; p.pad_eff = p.Tmax - 1; p.Tspan = p.Tmax; p.opad = (int)pad; p.Q = (int)((Lin + pad + S - 1) / S);
+    p.KK = p.Cxg * p.Tmax; p.KKpad = (p.KK + 7) & ~7;
+    p.Npad = (p.N + 7) & ~7; p.NS = p.Npad == 8 ? 8 : p.Npad + 8;
+    if (p.Npad == 8) {
+        switch (p.S) {
+            case 1: return launch_mma_mtw<MODE_DGRAD, 1, 1>(p, st);
+            case 3: return launch_mma_mtw<MODE_DGRAD, 1, 3>(p, st);
+            case 4: return launch_mma_mtw<MODE_DGRAD, 1, 4>(p, st);
+        }
+    } else if (p.Npad == 16) {
+        switch (p.S) {
+            case 1: return launch_mma_mtw<MODE_DGRAD, 2, 1>(p, st);
+            case 3: return launch_mma_mtw<MODE_DGRAD, 2, 3>(p, st);
+            case 4: return launch_mma_mtw<MODE_DGRAD, 2, 4>(p, st);
+        }
+    }
+    return LCT_EUNSUPPORTED;
+}
+
+template <int MT, int NT>
+int launch_wgrad(MmaWgradParams& p, cudaStream_t st) {
+    const int TP = 128;
+    const int rows_max = TP / p.P + 2;
+    const int nr_max = (rows_max - 1) * p.S + p.K;
+    p.WS = (nr_max * p.P + 3) & ~3;
+    p.DS = TP + 4;
+    p.tiles_per_b = (int)ceil_div64((int64_t)p.Lout * p.P, TP);
+    p.ntiles = p.B * p.tiles_per_b;
+    size_t smem = ((size_t)2 * p.Cig * p.WS + (size_t)2 * 16 * MT * p.DS) * sizeof(float);
+    if (smem < (size_t)16 * MT * NT * 8 * sizeof(float)) smem = (size_t)16 * MT * NT * 8 * sizeof(float);
+    if (smem > 200 * 1024) return LCT_EUNSUPPORTED;
+    if (smem > 40 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(conv_mma_wgrad_kernel<MT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    const int G = p.Cin / p.Cig;
+    dim3 grid((unsigned)G, (unsigned)grid_y(G, p.ntiles));
+    conv_mma_wgrad_kernel<MT, NT><<<grid, kThreads, smem, st>>>(p);
+    LCT_RETURN_IF_LAUNCH_FAILED();
+    return 0;
+}
+
+// dw [Cout][Cin/G][K] and db [Cout] (optional) are accumulated (caller zeroes)
+LCT_API int lct_conv_mma_wgrad(const float* x, const float* dy, float* dw, float* db, int64_t B, int64_t Cin,
+                               int64_t Cout, int64_t G, int64_t K, int64_t S, int64_t pad, int64_t Lin, int64_t P,
+                               cudaStream_t st) {
+    if (!x || !dy || !dw || !shape_ok(B, Cin, Cout, G, K, S, pad, Lin, P) ||
+        !lct_conv_mma_supported(Cin, Cout, G, K, S, P))
+        return LCT_EINVAL;
+    MmaWgradParams p = {};
+    p.x = x; p.dy = dy; p.dw = dw; p.db = db;
+    p.B = (int)B; p.Cin = (int)Cin; p.Cig = (int)(Cin / G); p.Lin = (int)Lin; p.P = (int)P;
+    p.Cout = (int)Cout; p.N = (int)(Cout / G); p.Lout = (int)((Lin + 2 * pad - K) / S + 1);
+    p.K = (int)K; p.S = (int)S; p.pad = (int)pad;
+    p.KK = p.Cig * p.K;
+    const int nt = (p.KK + 7) / 8;
+    const int mt = (p.N + 15) / 16;
+#define LCT_WG(MTV, NTV) return launch_wgrad<MTV, NTV>(p, st)
+    if (mt == 1) {
+        if (nt <= 1) LCT_WG(1, 1);
+        if (nt <= 2) LCT_WG(1, 2);
+        if (nt <= 5) LCT_WG(1, 5);
+        if (nt <= 10) LCT_WG(1, 10);
+        if (nt <= 21) LCT_WG(1, 21);
+    } else if (mt == 2) {
+        if (nt <= 1) LCT_WG(2, 1);
+        if (nt <= 5) LCT_WG(2, 5);
+        if (nt <= 10) LCT_WG(2, 10);
+    }
+#undef LCT_WG
+    return LCT_EUNSUPPORTED;
+}

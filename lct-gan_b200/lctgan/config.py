@@ -1,8 +1,8 @@
 """Run-time switches of the lctgan kernels."""
 
-#: Run the dense 1024->1024 convolution (MSD convs.5) on the tcgen05 tensor cores with bf16 operands and fp32
-#: accumulation (BASELINE.json configs[2]: "LCT-GAN training bf16").  False = the fp32 SIMT kernels everywhere
-#: (used by the tight fp32 parity tests).
+#: Tensor-core mode (BASELINE.json configs[2]: "LCT-GAN training bf16"): the dense 1024->1024 convolution (MSD
+#: convs.5) runs on tcgen05 with bf16 operands and the grouped discriminator convolutions on TF32 mma.sync, all
+#: with fp32 accumulation.  False = the fp32 SIMT kernels everywhere (used by the tight fp32 parity tests).
 dense_tensor_cores = True
 
 

@@ -13,6 +13,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 
+from . import config
 from ._lib import call, call_ret
 
 ACT_NONE, ACT_LRELU, ACT_RELU = 0, 1, 2
@@ -225,6 +226,12 @@ def weight_norm_bwd(g, v, dw):
     return dg, dv
 
 
+def _use_mma(cin, cout, k, groups, stride, pad, P):
+    """Grouped layers go to the TF32 tensor-core kernels unless exact-fp32 mode is selected."""
+    return (config.dense_tensor_cores and pad == k // 2 and
+            bool(call_ret("lct_conv_mma_supported", cin, cout, groups, k, stride, P)))
+
+
 def _is_post(cout, k, groups, stride, pad):
     """conv_post shape: one output channel, "same" odd kernel -> dedicated channel-reduction kernels."""
     return cout == 1 and groups == 1 and stride == 1 and (k & 1) and k <= 8 and pad == k // 2
@@ -244,6 +251,9 @@ def conv1d_fwd(x, w, bias, groups, stride, pad, act=ACT_NONE, slope=0.2):
         call("lct_conv_post_fwd", x, w, bias, y, B, Cin, Lin, P, K)
         return y
     y = torch.empty(B, Cout, Lout, P, dtype=torch.float32, device=x.device)
+    if _use_mma(Cin, Cout, K, groups, stride, pad, P):
+        call("lct_conv_mma_fwd", x, w, bias, y, B, Cin, Cout, groups, K, stride, pad, Lin, P, act, slope)
+        return y
     call("lct_conv1d_fwd", x, w, bias, y, B, Cin, Cout, groups, K, stride, pad, Lin, P, act, slope)
     return y
 
@@ -254,6 +264,9 @@ def conv1d_dgrad(dy, w, x_shape, groups, stride, pad, gextra=None, xact=None, ac
     dx = torch.empty(B, Cin, Lin, P, dtype=torch.float32, device=dy.device)
     if _is_post(Cout, K, groups, stride, pad):
         call("lct_conv_post_dgrad", dy, w, dx, gextra, xact, B, Cin, Lin, P, K, act, slope)
+        return dx
+    if _use_mma(Cin, Cout, K, groups, stride, pad, P):
+        call("lct_conv_mma_dgrad", dy, w, dx, gextra, xact, B, Cin, Cout, groups, K, stride, pad, Lin, P, act, slope)
         return dx
     call("lct_conv1d_dgrad", dy, w, dx, gextra, xact, B, Cin, Cout, groups, K, stride, pad, Lin, P, act, slope)
     return dx
@@ -266,6 +279,9 @@ def conv1d_wgrad(x, dy, w_shape, groups, stride, pad, want_bias=True):
     db = torch.zeros(Cout, dtype=torch.float32, device=x.device) if want_bias else None
     if _is_post(Cout, K, groups, stride, pad):
         call("lct_conv_post_wgrad", x, dy, dw, db, B, Cin, Lin, P, K)
+        return dw, db
+    if _use_mma(Cin, Cout, K, groups, stride, pad, P):
+        call("lct_conv_mma_wgrad", x, dy, dw, db, B, Cin, Cout, groups, K, stride, pad, Lin, P)
         return dw, db
     call("lct_conv1d_wgrad", x, dy, dw, db, B, Cin, Cout, groups, K, stride, pad, Lin, P)
     return dw, db
