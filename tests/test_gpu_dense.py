@@ -67,27 +67,38 @@ def test_dense_conv_fwd_dgrad_wgrad(dev, B, L, Ci, Co):
     assert rel_err(db, dy.sum((0, 2))) < 1e-4
 
 
-class _BF16DenseConv(torch.autograd.Function):
-    """CPU emulation of the tensor-core layer's arithmetic contract: every GEMM operand (x, w, dy) is rounded to
-    bf16, products are accumulated exactly (fp64 here, fp32 on the GPU); bias and its gradient stay fp32."""
+def _tf32(t):
+    """round-to-nearest to 10 mantissa bits (cvt.rna.tf32.f32)"""
+    i = t.detach().contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32).double()
+
+
+class _QuantConv(torch.autograd.Function):
+    """CPU emulation of a tensor-core layer's arithmetic contract: every GEMM operand (x, w, dy) is rounded by `q`
+    (bf16 for the tcgen05 dense layer, TF32 for the mma.sync grouped layers), products are accumulated exactly
+    (fp64 here, fp32 on the GPU); bias and its gradient stay fp32."""
 
     @staticmethod
-    def forward(ctx, x, w, b, pad):
+    def forward(ctx, x, w, b, stride, pad, groups, q):
         ctx.save_for_backward(x, w)
-        ctx.pad = pad
-        return (F.conv1d(_bf(x), _bf(w), None, padding=pad) + b.double()[None, :, None]).to(x.dtype)
+        ctx.cfg = (stride, pad, groups, q)
+        return (F.conv1d(q(x), q(w), None, stride=stride, padding=pad, groups=groups) +
+                b.double()[None, :, None]).to(x.dtype)
 
     @staticmethod
     def backward(ctx, g):
         x, w = ctx.saved_tensors
-        gq = _bf(g)
-        dx = F.conv_transpose1d(gq, _bf(w), padding=ctx.pad)
-        dw = torch.nn.grad.conv1d_weight(_bf(x), w.shape, gq, padding=ctx.pad)
-        return dx.to(x.dtype), dw.to(w.dtype), g.sum((0, 2)), None
+        stride, pad, groups, q = ctx.cfg
+        gq = q(g)
+        opad = x.shape[2] - ((g.shape[2] - 1) * stride - 2 * pad + w.shape[2])
+        dx = F.conv_transpose1d(gq, q(w), stride=stride, padding=pad, output_padding=opad, groups=groups)
+        dw = torch.nn.grad.conv1d_weight(q(x), w.shape, gq, stride=stride, padding=pad, groups=groups)
+        return dx.to(x.dtype), dw.to(w.dtype), g.sum((0, 2)), None, None, None, None
 
 
 def _msd_forward_emulated(O, P, x):
-    """oracle.msd_forward with convs.5 replaced by the bf16-operand emulation above."""
+    """oracle.msd_forward with the tensor-core layers replaced by the operand-rounding emulation above
+    (convs.0-4: TF32, convs.5: bf16; conv_post stays fp32 like on the GPU)."""
     x = x.unsqueeze(1)
     logits, fmaps = [], []
     for i in range(3):
@@ -96,10 +107,7 @@ def _msd_forward_emulated(O, P, x):
         for j, (_, k, s, g) in enumerate(O.MSD_LAYERS):
             w = O.weight_norm_weight(P[f"{pre}convs.{j}.weight_g"], P[f"{pre}convs.{j}.weight_v"])
             b = P[f"{pre}convs.{j}.bias"]
-            if j == 5:
-                h = F.leaky_relu(_BF16DenseConv.apply(h, w, b, k // 2), 0.2)
-            else:
-                h = F.leaky_relu(F.conv1d(h, w, b, stride=s, padding=k // 2, groups=g), 0.2)
+            h = F.leaky_relu(_QuantConv.apply(h, w, b, s, k // 2, g, _bf if j == 5 else _tf32), 0.2)
             fm.append(h)
         w = O.weight_norm_weight(P[pre + "conv_post.weight_g"], P[pre + "conv_post.weight_v"])
         h = F.conv1d(h, w, P[pre + "conv_post.bias"], padding=1)
@@ -112,7 +120,8 @@ def _msd_forward_emulated(O, P, x):
 
 def test_msd_bf16_matches_oracle(dev):
     """Whole MultiScaleDiscriminator with the tensor-core layer on.
-    (1) against the oracle with convs.5's operands rounded to bf16 (same arithmetic contract): 2e-3 relative L2
+    (1) against the oracle with the tensor-core layers' operands rounded the same way (TF32 for convs.0-4, bf16 for
+        convs.5: same arithmetic contract): 2e-3 relative L2
         on every feature map, the input gradient and every parameter gradient;
     (2) against the plain fp32 oracle: 2e-2 relative to the max on the feature maps and the input gradient
         (bf16 has 8 mantissa bits; stated tolerance of the bf16 training configuration)."""
@@ -148,3 +157,35 @@ def test_msd_bf16_matches_oracle(dev):
     assert rel_err(xg.grad, x32.grad) < 2e-2
     for k, p in msd.named_parameters():
         assert l2(p.grad, P[k].grad) < 2e-3, k
+
+
+def test_mpd_tensor_core_mode_matches_oracle(dev):
+    """MultiPeriodDiscriminator with the TF32 mma.sync grouped convolutions on, against the fp32 CPU oracle:
+    feature maps 5e-3 relative to each map's max, input gradient 1e-2, parameter gradients 1e-2 relative L2
+    (TF32 = 10 mantissa bits; stated tolerance of the tensor-core configuration)."""
+    from models.discriminators import MultiPeriodDiscriminator
+    O = oracle()
+    torch.manual_seed(0)
+    mpd = MultiPeriodDiscriminator()
+    P = leaf_params(cpu_params(mpd))
+    mpd = mpd.to(dev)
+    x = torch.randn(2, 6001, generator=torch.Generator().manual_seed(8)) * 0.1
+    xr = x.clone().requires_grad_(True)
+    lr, fr = O.mpd_forward(P, xr)
+    xg = x.to(dev).requires_grad_(True)
+    lg, fg = mpd(xg)
+    loss_r, loss_g = 0.0, 0.0
+    gen = torch.Generator().manual_seed(9)
+    for i in range(5):
+        for a, b in zip(fg[i], fr[i]):
+            assert a.shape == b.shape
+            assert rel_err(a, b) < 5e-3
+            gw = torch.randn(b.shape, generator=gen) / b.numel() ** 0.5
+            loss_r = loss_r + (b * gw).sum()
+            loss_g = loss_g + (a * gw.to(dev)).sum()
+    loss_r.backward()
+    loss_g.backward()
+    assert rel_err(xg.grad, xr.grad) < 1e-2
+    for k, p in mpd.named_parameters():
+        a, b = p.grad.detach().cpu().double(), P[k].grad.double()
+        assert ((a - b).norm() / b.norm()).item() < 1e-2, k
