@@ -8,8 +8,9 @@
 //
 //   * per group:  D[position, n] = sum_kk A[position, kk] * W[kk, n]   with A gathered on the fly from a
 //     shared-memory window of the input (no im2col buffer).  Forward: kk = (ci, tap), n = out channel.
-//     Data gradient in polyphase form: kk = (co, t), n = in channel, one weight set per stride phase r
-//     (k = r + S t), all S phases share the same A fragments.
+//     Data gradient in polyphase form: kk = (co, t), n = (in channel, stride phase r) with r fastest
+//     (weight tap k = r + S t), so one GEMM produces all S phases and a thread's two accumulator columns are
+//     two consecutive output rows: stores stay coalesced.
 //   * persistent CTAs (one group each, looping over (batch, position tile)) with the next tile's window
 //     prefetched by cp.async (4-byte copies, zero-fill for the padding) while the current one is multiplied:
 //     the staging latency that dominated the SIMT kernels is overlapped.
@@ -35,7 +36,8 @@ struct MmaParams {
     const float* bias;     // fwd
     const float* gextra;   // dgrad (optional)
     const float* xact;     // dgrad (optional)
-    int B, Cx, Cxg, Lx, P, Co, N, Lo;      // Co = channels of `out`, N = real out-channels per group
+    int B, Cx, Cxg, Lx, P, Co, N, Lo;      // Co = channels of `out`, N = GEMM columns per group (fwd: Cout/G; dgrad: Cin/G * S)
+    int Cig;                               // dgrad: in-channels per group
     int K, S, pad, Tmax;                   // conv geometry (Tmax = ceil(K / S))
     int Sg, pad_eff, Tspan, opad, Q;       // gather stride, window origin shift, taps spanned, output shift, rows
     int KK, KKpad, Npad, NS, WS;
@@ -84,37 +86,37 @@ __device__ __forceinline__ void stage_window(const MmaParams& p, int g, int tile
     }
 }
 
-template <int MODE, int NT, int NPH, int MTW>
+template <int MODE, int NT, int MTW>
 __global__ void __launch_bounds__(kThreads) conv_mma_kernel(const MmaParams p) {
     extern __shared__ __align__(16) float sm[];
     constexpr int TP = 32 * MTW * (kThreads / 32) / 2;   // MTW m-tiles of 16 positions per warp
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int gq = lane >> 2, tq = lane & 3;
     const int g = blockIdx.x;
-    float* wsm = sm;                                              // [NPH][KKpad][NS]
-    int* lut = reinterpret_cast<int*>(wsm + NPH * p.KKpad * p.NS);  // [KKpad]
+    float* wsm = sm;                                              // [KKpad][NS]
+    int* lut = reinterpret_cast<int*>(wsm + p.KKpad * p.NS);        // [KKpad]
     float* win0 = reinterpret_cast<float*>(lut + p.KKpad);
     const int winsz = p.Cxg * p.WS;
     float* win1 = win0 + winsz;
 
-    // ---- prologue: this group's weights (tf32-rounded, [phase][kk][n]) and the gather LUT
-    for (int idx = tid; idx < NPH * p.KKpad * p.Npad; idx += kThreads) {
+    // ---- prologue: this group's weights (tf32-rounded, [kk][n]) and the gather LUT
+    for (int idx = tid; idx < p.KKpad * p.Npad; idx += kThreads) {
         const int n = idx % p.Npad;
-        const int t2 = idx / p.Npad;
-        const int kk = t2 % p.KKpad;
-        const int r = t2 / p.KKpad;
+        const int kk = idx / p.Npad;
         float v = 0.f;
         if (kk < p.KK && n < p.N) {
             if (MODE == MODE_FWD) {
                 // kk = ci*K + tap; w[(g*N + n)][ci][tap] is contiguous in kk
                 v = p.w[((size_t)g * p.N + n) * p.KK + kk];
             } else {
+                // kk = co*Tmax + t;  n = ci*S + r;  tap k = r + S*t
                 const int co = kk / p.Tmax, t = kk - co * p.Tmax;
+                const int ci = n / p.S, r = n - ci * p.S;
                 const int k = r + p.S * t;
-                if (k < p.K) v = p.w[(((size_t)g * p.Cxg + co) * p.N + n) * p.K + k];
+                if (k < p.K) v = p.w[(((size_t)g * p.Cxg + co) * p.Cig + ci) * p.K + k];
             }
         }
-        wsm[(r * p.KKpad + kk) * p.NS + n] = __uint_as_float(f2tf32(v));
+        wsm[kk * p.NS + n] = __uint_as_float(f2tf32(v));
     }
     for (int kk = tid; kk < p.KKpad; kk += kThreads) {
         int off = 0;
@@ -164,15 +166,13 @@ __global__ void __launch_bounds__(kThreads) conv_mma_kernel(const MmaParams p) {
                     base[mt][h] = 0;
                 }
             }
-        float acc[NPH][MTW][NT][4];
+        float acc[MTW][NT][4];
 #pragma unroll
-        for (int r = 0; r < NPH; ++r)
+        for (int mt = 0; mt < MTW; ++mt)
 #pragma unroll
-            for (int mt = 0; mt < MTW; ++mt)
+            for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-                for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) acc[r][mt][nt][i] = 0.f;
+                for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
 
         for (int k0 = 0; k0 < p.KKpad; k0 += 8) {
             const int l0 = lut[k0 + tq], l1 = lut[k0 + tq + 4];
@@ -184,49 +184,50 @@ __global__ void __launch_bounds__(kThreads) conv_mma_kernel(const MmaParams p) {
                 a[mt][2] = f2tf32(win[l1 + base[mt][0]]);
                 a[mt][3] = f2tf32(win[l1 + base[mt][1]]);
             }
+            const float* wr = wsm + k0 * p.NS;
 #pragma unroll
-            for (int r = 0; r < NPH; ++r) {
-                const float* wr = wsm + (r * p.KKpad + k0) * p.NS;
+            for (int nt = 0; nt < NT; ++nt) {
+                const uint32_t b0 = __float_as_uint(wr[tq * p.NS + nt * 8 + gq]);
+                const uint32_t b1 = __float_as_uint(wr[(tq + 4) * p.NS + nt * 8 + gq]);
 #pragma unroll
-                for (int nt = 0; nt < NT; ++nt) {
-                    const uint32_t b0 = __float_as_uint(wr[tq * p.NS + nt * 8 + gq]);
-                    const uint32_t b1 = __float_as_uint(wr[(tq + 4) * p.NS + nt * 8 + gq]);
-#pragma unroll
-                    for (int mt = 0; mt < MTW; ++mt)
-                        mma_tf32(acc[r][mt][nt], a[mt][0], a[mt][1], a[mt][2], a[mt][3], b0, b1);
-                }
+                for (int mt = 0; mt < MTW; ++mt) mma_tf32(acc[mt][nt], a[mt][0], a[mt][1], a[mt][2], a[mt][3], b0, b1);
             }
         }
         // ---- epilogue
         const int lo_p = p.Lo * p.P;
 #pragma unroll
-        for (int r = 0; r < NPH; ++r)
+        for (int mt = 0; mt < MTW; ++mt)
 #pragma unroll
-            for (int mt = 0; mt < MTW; ++mt)
+            for (int h = 0; h < 2; ++h) {
+                if (rowq[mt][h] < 0) continue;
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    if (rowq[mt][h] < 0) continue;
-                    const int row_o = NPH * rowq[mt][h] + r - p.opad;
-                    if (row_o < 0 || row_o >= p.Lo) continue;
+                for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-                    for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-                        for (int c = 0; c < 2; ++c) {
-                            const int n = nt * 8 + 2 * tq + c;
-                            if (n >= p.N) continue;
-                            const int ch = g * p.N + n;
-                            const size_t idx = ((size_t)b * p.Co + ch) * lo_p + (size_t)row_o * p.P + ppos[mt][h];
-                            float v = acc[r][mt][nt][2 * h + c];
-                            if (MODE == MODE_FWD) {
-                                if (p.bias) v += __ldg(&p.bias[ch]);
-                                v = apply_act(v, p.act, p.slope);
-                            } else {
-                                if (p.gextra) v += p.gextra[idx];
-                                if (p.xact) v *= act_grad_from_out(p.xact[idx], p.act, p.slope);
-                            }
-                            p.out[idx] = v;
+                    for (int c = 0; c < 2; ++c) {
+                        const int n = nt * 8 + 2 * tq + c;
+                        if (n >= p.N) continue;
+                        int ch, row_o;
+                        if (MODE == MODE_FWD) {
+                            ch = g * p.N + n;
+                            row_o = rowq[mt][h];
+                        } else {
+                            const int ci = n / p.S, r = n - ci * p.S;
+                            ch = g * p.Cig + ci;
+                            row_o = p.S * rowq[mt][h] + r - p.opad;
+                            if (row_o < 0 || row_o >= p.Lo) continue;
                         }
-                }
+                        const size_t idx = ((size_t)b * p.Co + ch) * lo_p + (size_t)row_o * p.P + ppos[mt][h];
+                        float v = acc[mt][nt][2 * h + c];
+                        if (MODE == MODE_FWD) {
+                            if (p.bias) v += __ldg(&p.bias[ch]);
+                            v = apply_act(v, p.act, p.slope);
+                        } else {
+                            if (p.gextra) v += p.gextra[idx];
+                            if (p.xact) v *= act_grad_from_out(p.xact[idx], p.act, p.slope);
+                        }
+                        p.out[idx] = v;
+                    }
+            }
     }
     cp_async_wait_all();
 }
@@ -406,6 +407,13 @@ __global__ void __launch_bounds__(kThreads) conv_mma_wgrad_kernel(const MmaWgrad
     }
 }
 
+// row stride of the staged weights: (t * NS + g) mod 32 must be distinct for t < 4, g < 8  ->  NS = 8 or 24 (mod 32)
+int pick_ns(int npad) {
+    int ns = npad;
+    while (ns % 32 != 8 && ns % 32 != 24) ns += 8;
+    return ns;
+}
+
 int grid_y(int G, int ntiles) {
     int per = (148 * 3 + G - 1) / G;     // ~3 resident CTAs per SM in total
     if (per < 1) per = 1;
@@ -413,7 +421,7 @@ int grid_y(int G, int ntiles) {
     return per;
 }
 
-template <int MODE, int NT, int NPH, int MTW>
+template <int MODE, int NT, int MTW>
 int launch_mma(MmaParams& p, cudaStream_t st) {
     constexpr int TP = 32 * MTW * (kThreads / 32) / 2;
     const int rows_max = TP / p.P + 2;
@@ -421,29 +429,25 @@ int launch_mma(MmaParams& p, cudaStream_t st) {
     p.WS = (nr_max * p.P + 3) & ~3;
     p.tiles_per_b = (int)ceil_div64((int64_t)p.Q * p.P, TP);
     p.ntiles = p.B * p.tiles_per_b;
-    size_t smem = ((size_t)NPH * p.KKpad * p.NS + p.KKpad + (size_t)2 * p.Cxg * p.WS) * sizeof(float);
+    size_t smem = ((size_t)p.KKpad * p.NS + p.KKpad + (size_t)2 * p.Cxg * p.WS) * sizeof(float);
     if (smem > 200 * 1024) return LCT_EUNSUPPORTED;
     if (smem > 40 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(conv_mma_kernel<MODE, NT, NPH, MTW>,
+        cudaError_t e = cudaFuncSetAttribute(conv_mma_kernel<MODE, NT, MTW>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
     const int G = p.Cx / p.Cxg;
     dim3 grid((unsigned)G, (unsigned)grid_y(G, p.ntiles));
-    conv_mma_kernel<MODE, NT, NPH, MTW><<<grid, kThreads, smem, st>>>(p);
+    conv_mma_kernel<MODE, NT, MTW><<<grid, kThreads, smem, st>>>(p);
     LCT_RETURN_IF_LAUNCH_FAILED();
     return 0;
 }
 
-template <int MODE, int NT, int NPH>
+template <int MODE, int NT>
 int launch_mma_mtw(MmaParams& p, cudaStream_t st) {
-    // short layers: 128-position tiles keep more CTAs busy; big register tiles also stay at MTW = 2
-    if constexpr (NT * NPH >= 8) {
-        return launch_mma<MODE, NT, NPH, 2>(p, st);
-    } else {
-        if ((int64_t)p.Q * p.P * p.B * (p.Cx / p.Cxg) < 148 * 256) return launch_mma<MODE, NT, NPH, 2>(p, st);
-        return launch_mma<MODE, NT, NPH, 4>(p, st);
-    }
+    // short layers: 128-position tiles keep more CTAs busy
+    if ((int64_t)p.Q * p.P * p.B * (p.Cx / p.Cxg) < 148 * 256) return launch_mma<MODE, NT, 2>(p, st);
+    return launch_mma<MODE, NT, 4>(p, st);
 }
 
 bool shape_ok(int64_t B, int64_t Cin, int64_t Cout, int64_t G, int64_t K, int64_t S, int64_t pad, int64_t Lin,
@@ -478,11 +482,11 @@ LCT_API int lct_conv_mma_fwd(const float* x, const float* w, const float* bias, 
     p.K = (int)K; p.S = (int)S; p.pad = (int)pad; p.Tmax = (int)((K + S - 1) / S);
     p.Sg = (int)S; p.pad_eff = (int)pad; p.Tspan = (int)K; p.opad = 0; p.Q = p.Lo;
     p.KK = p.Cxg * p.K; p.KKpad = (p.KK + 7) & ~7;
-    p.Npad = (p.N + 7) & ~7; p.NS = p.Npad == 8 ? 8 : p.Npad + 8;
+    p.Npad = (p.N + 7) & ~7; p.NS = pick_ns(p.Npad);
     switch (p.Npad) {
-        case 8: return launch_mma_mtw<MODE_FWD, 1, 1>(p, st);
-        case 16: return launch_mma_mtw<MODE_FWD, 2, 1>(p, st);
-        case 32: return launch_mma_mtw<MODE_FWD, 4, 1>(p, st);
+        case 8: return launch_mma_mtw<MODE_FWD, 1>(p, st);
+        case 16: return launch_mma_mtw<MODE_FWD, 2>(p, st);
+        case 32: return launch_mma_mtw<MODE_FWD, 4>(p, st);
         default: return LCT_EUNSUPPORTED;
     }
 }
@@ -497,25 +501,20 @@ LCT_API int lct_conv_mma_dgrad(const float* dy, const float* w, float* dx, const
     p.x = dy; p.w = w; p.out = dx; p.gextra = gextra; p.xact = xact; p.act = act; p.slope = slope;
     const int Lout = (int)((Lin + 2 * pad - K) / S + 1);
     p.B = (int)B; p.Cx = (int)Cout; p.Cxg = (int)(Cout / G); p.Lx = Lout; p.P = (int)P;
-    p.Co = (int)Cin; p.N = (int)(Cin / G); p.Lo = (int)Lin;
+    p.Co = (int)Cin; p.Cig = (int)(Cin / G); p.N = p.Cig * (int)S; p.Lo = (int)Lin;
     p.K = (int)K; p.S = (int)S; p.pad = (int)pad; p.Tmax = (int)((K + S - 1) / S);
     p.Sg = 1; p.pad_eff = p.Tmax - 1; p.Tspan = p.Tmax; p.opad = (int)pad; p.Q = (int)((Lin + pad + S - 1) / S);
     p.KK = p.Cxg * p.Tmax; p.KKpad = (p.KK + 7) & ~7;
-    p.Npad = (p.N + 7) & ~7; p.NS = p.Npad == 8 ? 8 : p.Npad + 8;
-    if (p.Npad == 8) {
-        switch (p.S) {
-            case 1: return launch_mma_mtw<MODE_DGRAD, 1, 1>(p, st);
-            case 3: return launch_mma_mtw<MODE_DGRAD, 1, 3>(p, st);
-            case 4: return launch_mma_mtw<MODE_DGRAD, 1, 4>(p, st);
-        }
-    } else if (p.Npad == 16) {
-        switch (p.S) {
-            case 1: return launch_mma_mtw<MODE_DGRAD, 2, 1>(p, st);
-            case 3: return launch_mma_mtw<MODE_DGRAD, 2, 3>(p, st);
-            case 4: return launch_mma_mtw<MODE_DGRAD, 2, 4>(p, st);
-        }
+    p.Npad = (p.N + 7) & ~7; p.NS = pick_ns(p.Npad);
+    switch (p.Npad) {
+        case 8: return launch_mma_mtw<MODE_DGRAD, 1>(p, st);
+        case 16: return launch_mma_mtw<MODE_DGRAD, 2>(p, st);
+        case 24: return launch_mma_mtw<MODE_DGRAD, 3>(p, st);
+        case 32: return launch_mma_mtw<MODE_DGRAD, 4>(p, st);
+        case 48: return launch_mma<MODE_DGRAD, 6, 2>(p, st);
+        case 64: return launch_mma<MODE_DGRAD, 8, 2>(p, st);
+        default: return LCT_EUNSUPPORTED;
     }
-    return LCT_EUNSUPPORTED;
 }
 
 template <int MT, int NT>
