@@ -188,6 +188,8 @@ def main():
     ap.add_argument("--gan_loss", default="ls", choices=["ls", "hinge"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-reuse", action="store_true", help="run the enhancer forward twice per step like train.py does "
+                    "(default: one forward serves the D and the G step: identical values, SURVEY 8f N1)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -218,7 +220,7 @@ def main():
         broadcast_parameters([enh, mpd, msd])
     sync_d = FlatGradAllReduce(list(mpd.parameters()) + list(msd.parameters())) if world > 1 else None
     sync_g = FlatGradAllReduce(list(enh.parameters())) if world > 1 else None
-    sargs = StepArgs(gan_loss=args.gan_loss)
+    sargs = StepArgs(gan_loss=args.gan_loss, reuse_enhancer_forward=not args.no_reuse)
 
     noisy_h, clean_h = O.synthetic_batch(BATCH, SEGMENT, seed=1234 + rank)      # synthetic data generator only
     noisy_h, clean_h = noisy_h.pin_memory(), clean_h.pin_memory()
@@ -308,7 +310,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 tensor-core operands for the dense contraction (fp32 accumulate), f32 elsewhere",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "gan_loss": args.gan_loss, "parallelism": f"dp{world}", "cuda_graph": graphed is not None,
+        "config": {"workload": WORKLOAD, "gan_loss": args.gan_loss, "parallelism": f"dp{world}", "cuda_graph": graphed is not None, "reuse_enhancer_forward": sargs.reuse_enhancer_forward,
                    "l2": "no explicit flush: one step streams > 2 GB of activations (>> 126 MB L2)"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,

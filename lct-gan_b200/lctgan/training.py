@@ -12,6 +12,7 @@ from typing import Dict, Optional
 import torch
 
 import losses as L
+from . import config
 
 
 @dataclass
@@ -22,6 +23,11 @@ class StepArgs:
     lambda_mask: float = 1.0
     lambda_adv: float = 1e-2
     grad_clip: float = 5.0
+    #: SURVEY.md section 8f N1.  train.py runs the enhancer twice per step on the same input with the same weights
+    #: (no_grad at :180-181 for the D step, with grad at :208 for the G step; only D weights change in between).
+    #: With this switch one forward (with grad) serves both - bit-identical values, one forward less - and it runs
+    #: on a side stream concurrently with the discriminators' forward on the clean batch (no data dependence).
+    reuse_enhancer_forward: bool = False
 
 
 def _align_tf_targets(irm_c: torch.Tensor, pred_mask_c: torch.Tensor):
@@ -37,14 +43,29 @@ def _align_tf_targets(irm_c: torch.Tensor, pred_mask_c: torch.Tensor):
 def _phase_d(M, noisy, clean, args: StepArgs, st: dict) -> None:
     """TF features + discriminator forward/backward (train.py:171-199)."""
     enhancer, mpd, msd, tf_features, mrstft_loss, g_opt, d_opt = M
-    st["irm_c"] = tf_features(noisy, clean)["irm_c"]
     d_opt.zero_grad(set_to_none=True)
-    with torch.no_grad():
-        enhanced_for_d, _ = enhancer(noisy)
-    mpd_real, _ = mpd(clean)
-    mpd_fake, _ = mpd(enhanced_for_d)
-    msd_real, _ = msd(clean)
-    msd_fake, _ = msd(enhanced_for_d)
+    if args.reuse_enhancer_forward and noisy.is_cuda:
+        g_opt.zero_grad(set_to_none=True)
+        cur = torch.cuda.current_stream()
+        side = config.side_streams(9, noisy.device)[8]
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):                   # generator forward (with grad), overlapped with D(clean)
+            st["enhanced"], st["mask_c"] = enhancer(noisy)
+        st["irm_c"] = tf_features(noisy, clean)["irm_c"]
+        mpd_real, _ = mpd(clean)
+        msd_real, _ = msd(clean)
+        cur.wait_stream(side)
+        enhanced_for_d = st["enhanced"].detach()
+        mpd_fake, _ = mpd(enhanced_for_d)
+        msd_fake, _ = msd(enhanced_for_d)
+    else:
+        st["irm_c"] = tf_features(noisy, clean)["irm_c"]
+        with torch.no_grad():
+            enhanced_for_d, _ = enhancer(noisy)
+        mpd_real, _ = mpd(clean)
+        mpd_fake, _ = mpd(enhanced_for_d)
+        msd_real, _ = msd(clean)
+        msd_fake, _ = msd(enhanced_for_d)
     d_loss = L.discriminator_loss(L._flatten_logits_lists(mpd_real, msd_real),
                                   L._flatten_logits_lists(mpd_fake, msd_fake), args.gan_loss)
     d_loss.backward()
@@ -55,16 +76,19 @@ def _phase_g(M, noisy, clean, args: StepArgs, st: dict) -> None:
     """Discriminator update + generator forward/backward (train.py:200-245)."""
     enhancer, mpd, msd, tf_features, mrstft_loss, g_opt, d_opt = M
     d_opt.step()
-    g_opt.zero_grad(set_to_none=True)
-    enhanced, mask_c = enhancer(noisy)
+    if "enhanced" in st:
+        enhanced, mask_c = st.pop("enhanced"), st.pop("mask_c")
+    else:
+        g_opt.zero_grad(set_to_none=True)
+        enhanced, mask_c = enhancer(noisy)
+    with torch.no_grad():                  # real feature maps first: independent of the generator's output
+        _, mpd_real_f = mpd(clean)
+        _, msd_real_f = msd(clean)
     mr_loss, _ = mrstft_loss(enhanced, clean)
     irm_al, pred_al = _align_tf_targets(st["irm_c"], mask_c[:, 0])
     m_loss = L.mask_mse_loss(pred_al, irm_al)
     mpd_fake_g, mpd_fake_f = mpd(enhanced)
     msd_fake_g, msd_fake_f = msd(enhanced)
-    with torch.no_grad():
-        _, mpd_real_f = mpd(clean)
-        _, msd_real_f = msd(clean)
     adv_loss = L.generator_adv_loss(L._flatten_logits_lists(mpd_fake_g, msd_fake_g), args.gan_loss)
     fm_loss = L.feature_matching_loss(mpd_real_f + msd_real_f, mpd_fake_f + msd_fake_f)
     g_loss = mr_loss + args.lambda_mask * m_loss + args.lambda_adv * (adv_loss + args.lambda_fm * fm_loss)

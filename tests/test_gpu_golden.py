@@ -146,3 +146,22 @@ def test_segmented_graphs_equal_eager(dev):
         for k in got:
             assert abs(got[k] - eager[step][k]) <= 2e-3 * max(abs(eager[step][k]), 1e-3), (step, k, got[k], eager[step][k])
     assert calls == ["d", "g"] * 6     # 3 warm-up + 1 capture + 2 replays
+
+
+def test_reused_enhancer_forward_is_identical(dev, G):
+    """StepArgs.reuse_enhancer_forward (one generator forward serves the D and the G step, on a side stream)
+    reproduces the reference's train_one_epoch log exactly like the literal two-forward schedule does."""
+    from lctgan.training import StepArgs, build_models, train_step
+    noisy, clean = (t.to(dev) for t in G["model_inputs"])
+    a = build_models(dev, gan_seed=42)
+    b = build_models(dev, gan_seed=42)
+    names = {"D_loss": "d_loss", "G_loss": "g_loss", "MR": "mr", "Mask": "mask", "Adv": "adv", "FM": "fm"}
+    for step in range(2):
+        lit = train_step(*a, noisy, clean, StepArgs(gan_loss="ls"))
+        reu = train_step(*b, noisy, clean, StepArgs(gan_loss="ls", reuse_enhancer_forward=True))
+        for ref_k, k in names.items():
+            assert abs(reu[k].item() - lit[k].item()) <= 1e-6 * max(1.0, abs(lit[k].item())), (step, k)
+            ref = G["train_ls"]["logs"][step][ref_k]
+            assert abs(reu[k].item() - ref) <= 1.01e-4 + 1e-3 * abs(ref) * step, (step, k, reu[k].item(), ref)
+    for (k, p), q in zip(a[0].named_parameters(), b[0].parameters()):
+        assert torch.allclose(p, q, atol=1e-7), k
