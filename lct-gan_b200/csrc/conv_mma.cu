@@ -62,11 +62,47 @@ __device__ __forceinline__ void cp_async4(float* dst, const float* src, bool val
     const int n = valid ? 4 : 0;
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(s), "l"(src), "r"(n) : "memory");
 }
+__device__ __forceinline__ void cp_async16(float* dst, const float* src) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(src) : "memory");
+}
+// Copy n_e floats src[f0 .. f0+n_e) (zero outside [0, lim)) to dst[0 .. n_e) with one warp.  dst and src + f0 must
+// have the same alignment phase modulo 16 bytes (the caller shifts dst by ((src + f0) & 3) floats), so the body
+// moves 16 bytes per cp.async: the per-element 4-byte version was the bottleneck of these kernels.
+__device__ __forceinline__ void warp_copy_row(float* dst, const float* src, int f0, int n_e, int lim, int phase,
+                                              const float* safe, int lane) {
+    const int h0 = min((4 - phase) & 3, n_e);
+    if (lane < h0) {
+        const int f = f0 + lane;
+        const bool ok = f >= 0 && f < lim;
+        cp_async4(dst + lane, ok ? src + f : safe, ok);
+    }
+    const int nvec = (n_e - h0) >> 2;
+    for (int v = lane; v < nvec; v += 32) {
+        const int e = h0 + 4 * v, f = f0 + e;
+        if (f >= 0 && f + 3 < lim) {
+            cp_async16(dst + e, src + f);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const bool ok = (f + i) >= 0 && (f + i) < lim;
+                cp_async4(dst + e + i, ok ? src + f + i : safe, ok);
+            }
+        }
+    }
+    for (int e = h0 + 4 * nvec + lane; e < n_e; e += 32) {
+        const int f = f0 + e;
+        const bool ok = f >= 0 && f < lim;
+        cp_async4(dst + e, ok ? src + f : safe, ok);
+    }
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// stage the input window of `tile` (all Cxg channels of group g) into `buf` with cp.async
-__device__ __forceinline__ void stage_window(const MmaParams& p, int g, int tile, int TP, float* buf) {
+// stage the input window of `tile` (all Cxg channels of group g) into `buf` with cp.async and write the tile's
+// gather LUT: lutd[kk] = lut0[kk] + (alignment shift of kk's channel)
+__device__ __forceinline__ void stage_window(const MmaParams& p, int g, int tile, int TP, float* buf, int* lutd,
+                                             const int* lut0, const int* chk) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = tile / p.tiles_per_b, jt = tile - b * p.tiles_per_b;
     const int j0 = jt * TP;
@@ -75,14 +111,15 @@ __device__ __forceinline__ void stage_window(const MmaParams& p, int g, int tile
     const int n_e = ((row_last - row_first) * p.Sg + p.Tspan) * p.P;
     const int e0 = (row_first * p.Sg - p.pad_eff) * p.P;   // flat start inside a channel (may be negative)
     const int lim = p.Lx * p.P;
+    const int64_t cb0 = ((int64_t)b * p.Cx + (int64_t)g * p.Cxg) * lim;
     for (int ch = warp; ch < p.Cxg; ch += kThreads / 32) {
-        const float* src = p.x + ((size_t)b * p.Cx + (size_t)g * p.Cxg + ch) * lim;
-        float* dst = buf + ch * p.WS;
-        for (int e = lane; e < n_e; e += 32) {
-            const int f = e0 + e;
-            const bool ok = f >= 0 && f < lim;
-            cp_async4(dst + e, ok ? src + f : p.x, ok);
-        }
+        const int64_t cb = cb0 + (int64_t)ch * lim;
+        const int phase = (int)((cb + e0) & 3);
+        warp_copy_row(buf + ch * p.WS + phase, p.x + cb, e0, n_e, lim, phase, p.x, lane);
+    }
+    for (int kk = threadIdx.x; kk < p.KKpad; kk += kThreads) {
+        const int64_t cb = cb0 + (int64_t)chk[kk] * lim;
+        lutd[kk] = lut0[kk] + (int)((cb + e0) & 3);
     }
 }
 
@@ -94,8 +131,11 @@ __global__ void __launch_bounds__(kThreads) conv_mma_kernel(const MmaParams p) {
     const int gq = lane >> 2, tq = lane & 3;
     const int g = blockIdx.x;
     float* wsm = sm;                                              // [KKpad][NS]
-    int* lut = reinterpret_cast<int*>(wsm + p.KKpad * p.NS);        // [KKpad]
-    float* win0 = reinterpret_cast<float*>(lut + p.KKpad);
+    int* lut0 = reinterpret_cast<int*>(wsm + p.KKpad * p.NS);       // [KKpad] static part of the gather LUT
+    int* chk = lut0 + p.KKpad;                                    // [KKpad] window channel of kk
+    int* lutd0 = chk + p.KKpad;                                   // [2][KKpad] per-buffer LUT (with alignment shift)
+    int* lutd1 = lutd0 + p.KKpad;
+    float* win0 = reinterpret_cast<float*>(lutd1 + p.KKpad);
     const int winsz = p.Cxg * p.WS;
     float* win1 = win0 + winsz;
 
@@ -119,29 +159,34 @@ __global__ void __launch_bounds__(kThreads) conv_mma_kernel(const MmaParams p) {
         wsm[kk * p.NS + n] = __uint_as_float(f2tf32(v));
     }
     for (int kk = tid; kk < p.KKpad; kk += kThreads) {
-        int off = 0;
+        int off = 0, chn = 0;
         if (kk < p.KK) {
             if (MODE == MODE_FWD) {
                 const int ci = kk / p.K, tap = kk - ci * p.K;
                 off = ci * p.WS + tap * p.P;
+                chn = ci;
             } else {
                 const int co = kk / p.Tmax, t = kk - co * p.Tmax;
                 off = co * p.WS + (p.Tmax - 1 - t) * p.P;
+                chn = co;
             }
         }
-        lut[kk] = off;
+        lut0[kk] = off;
+        chk[kk] = chn;
     }
+    __syncthreads();
     int tile = blockIdx.y;
-    if (tile < p.ntiles) stage_window(p, g, tile, TP, win0);
+    if (tile < p.ntiles) stage_window(p, g, tile, TP, win0, lutd0, lut0, chk);
     cp_async_commit();
 
     int cur = 0;
     for (; tile < p.ntiles; tile += gridDim.y, cur ^= 1) {
         float* win = cur ? win1 : win0;
+        const int* lut = cur ? lutd1 : lutd0;
         cp_async_wait_all();
-        __syncthreads();                       // window `cur` (and, first time, weights/LUT) visible to all
+        __syncthreads();                       // window + LUT `cur` (and, first time, the weights) visible to all
         const int nxt = tile + gridDim.y;
-        if (nxt < p.ntiles) stage_window(p, g, nxt, TP, cur ? win0 : win1);
+        if (nxt < p.ntiles) stage_window(p, g, nxt, TP, cur ? win0 : win1, cur ? lutd0 : lutd1, lut0, chk);
         cp_async_commit();
 
         const int b = tile / p.tiles_per_b, jt = tile - b * p.tiles_per_b;
@@ -260,18 +305,23 @@ __global__ void __launch_bounds__(kThreads) conv_mma_wgrad_kernel(const MmaWgrad
     float* win1 = win0 + winsz;
     float* dy0 = win1 + winsz;
     float* dy1 = dy0 + dysz;
+    int* shw0 = reinterpret_cast<int*>(dy1 + dysz);   // [2][Cig]   alignment shift of every window channel
+    int* shw1 = shw0 + p.Cig;
+    int* shd0 = shw1 + p.Cig;                         // [2][16*MT] alignment shift of every dY row
+    int* shd1 = shd0 + 16 * MT;
 
-    // LUT of this thread's B columns (kk = nt*8 + gq), constant over tiles
-    int lutn[NT];
+    // LUT of this thread's B columns (kk = nt*8 + gq), constant over tiles (the per-tile shift is added below)
+    int lutn[NT], cin[NT];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
         const int kk = nt * 8 + gq;
-        int off = 0;
+        int off = 0, ci = 0;
         if (kk < p.KK) {
-            const int ci = kk / p.K, tap = kk - ci * p.K;
-            off = ci * p.WS + tap * p.P;
+            ci = kk / p.K;
+            off = ci * p.WS + (kk - ci * p.K) * p.P;
         }
         lutn[nt] = off;
+        cin[nt] = ci;
     }
     float acc[MT][NT][4];
     float sdy[MT][2];
@@ -285,7 +335,7 @@ __global__ void __launch_bounds__(kThreads) conv_mma_wgrad_kernel(const MmaWgrad
     }
     const int jtot = p.Lout * p.P;
 
-    auto stage = [&](int tile, float* wbuf, float* dbuf) {
+    auto stage = [&](int tile, float* wbuf, float* dbuf, int* shw, int* shd) {
         const int b = tile / p.tiles_per_b, jt = tile - b * p.tiles_per_b;
         const int j0 = jt * TP;
         const int jend = min(j0 + TP, jtot);
@@ -294,37 +344,43 @@ __global__ void __launch_bounds__(kThreads) conv_mma_wgrad_kernel(const MmaWgrad
         const int e0 = (row_first * p.S - p.pad) * p.P;
         const int lim = p.Lin * p.P;
         for (int ch = warp; ch < p.Cig; ch += kThreads / 32) {
-            const float* src = p.x + ((size_t)b * p.Cin + (size_t)g * p.Cig + ch) * lim;
-            float* dst = wbuf + ch * p.WS;
-            for (int e = lane; e < n_e; e += 32) {
-                const int f = e0 + e;
-                const bool ok = f >= 0 && f < lim;
-                cp_async4(dst + e, ok ? src + f : p.x, ok);
-            }
+            const int64_t cb = ((int64_t)b * p.Cin + (int64_t)g * p.Cig + ch) * lim;
+            const int phase = (int)((cb + e0) & 3);
+            warp_copy_row(wbuf + ch * p.WS + phase, p.x + cb, e0, n_e, lim, phase, p.x, lane);
+            if (lane == 0) shw[ch] = phase;
         }
         for (int oc = warp; oc < 16 * MT; oc += kThreads / 32) {
             const bool chok = oc < p.N;
-            const float* src = p.dy + ((size_t)b * p.Cout + (size_t)g * p.N + (chok ? oc : 0)) * jtot;
-            float* dst = dbuf + oc * p.DS;
-            for (int e = lane; e < TP; e += 32) {
-                const bool ok = chok && (j0 + e) < jtot;
-                cp_async4(dst + e, ok ? src + j0 + e : p.dy, ok);
-            }
+            const int64_t cb = ((int64_t)b * p.Cout + (int64_t)g * p.N + (chok ? oc : 0)) * jtot;
+            const int phase = (int)((cb + j0) & 3);
+            // rows of padded out-channels are zero: give them an empty valid range
+            warp_copy_row(dbuf + oc * p.DS + phase, p.dy + cb, j0, TP, chok ? jtot : 0, phase, p.dy, lane);
+            if (lane == 0) shd[oc] = phase;
         }
     };
 
     int tile = blockIdx.y;
-    if (tile < p.ntiles) stage(tile, win0, dy0);
+    if (tile < p.ntiles) stage(tile, win0, dy0, shw0, shd0);
     cp_async_commit();
     int cur = 0;
     for (; tile < p.ntiles; tile += gridDim.y, cur ^= 1) {
         const float* win = cur ? win1 : win0;
         const float* dyt = cur ? dy1 : dy0;
+        const int* shw = cur ? shw1 : shw0;
+        const int* shd = cur ? shd1 : shd0;
         cp_async_wait_all();
         __syncthreads();
         const int nxt = tile + gridDim.y;
-        if (nxt < p.ntiles) stage(nxt, cur ? win0 : win1, cur ? dy0 : dy1);
+        if (nxt < p.ntiles) stage(nxt, cur ? win0 : win1, cur ? dy0 : dy1, cur ? shw0 : shw1, cur ? shd0 : shd1);
         cp_async_commit();
+        int lc[NT], sd[MT][2];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) lc[nt] = lutn[nt] + shw[cin[nt]];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            sd[mt][0] = shd[mt * 16 + gq];
+            sd[mt][1] = shd[mt * 16 + gq + 8];
+        }
 
         const int b = tile / p.tiles_per_b, jt = tile - b * p.tiles_per_b;
         const int j0 = jt * TP;
@@ -348,8 +404,8 @@ __global__ void __launch_bounds__(kThreads) conv_mma_wgrad_kernel(const MmaWgrad
             uint32_t a[MT][4];
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) {
-                const float* d0 = dyt + (mt * 16 + gq) * p.DS + pl;
-                const float* d1 = d0 + 8 * p.DS;
+                const float* d0 = dyt + (mt * 16 + gq) * p.DS + sd[mt][0] + pl;
+                const float* d1 = dyt + (mt * 16 + gq + 8) * p.DS + sd[mt][1] + pl;
                 const float v0 = d0[tq], v1 = d1[tq], v2 = d0[tq + 4], v3 = d1[tq + 4];
                 sdy[mt][0] += v0 + v2;
                 sdy[mt][1] += v1 + v3;
@@ -357,8 +413,8 @@ __global__ void __launch_bounds__(kThreads) conv_mma_wgrad_kernel(const MmaWgrad
             }
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
-                const uint32_t b0 = f2tf32(win[lutn[nt] + bs[0]]);
-                const uint32_t b1 = f2tf32(win[lutn[nt] + bs[1]]);
+                const uint32_t b0 = f2tf32(win[lc[nt] + bs[0]]);
+                const uint32_t b1 = f2tf32(win[lc[nt] + bs[1]]);
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) mma_tf32(acc[mt][nt], a[mt][0], a[mt][1], a[mt][2], a[mt][3], b0, b1);
             }
@@ -426,10 +482,10 @@ int launch_mma(MmaParams& p, cudaStream_t st) {
     constexpr int TP = 32 * MTW * (kThreads / 32) / 2;
     const int rows_max = TP / p.P + 2;
     const int nr_max = (rows_max - 1) * p.Sg + p.Tspan;
-    p.WS = (nr_max * p.P + 3) & ~3;
+    p.WS = (nr_max * p.P + 3 + 3) & ~3;      // + up to 3 floats of alignment shift
     p.tiles_per_b = (int)ceil_div64((int64_t)p.Q * p.P, TP);
     p.ntiles = p.B * p.tiles_per_b;
-    size_t smem = ((size_t)p.KKpad * p.NS + p.KKpad + (size_t)2 * p.Cxg * p.WS) * sizeof(float);
+    size_t smem = ((size_t)p.KKpad * p.NS + (size_t)4 * p.KKpad + (size_t)2 * p.Cxg * p.WS) * sizeof(float);
     if (smem > 200 * 1024) return LCT_EUNSUPPORTED;
     if (smem > 40 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(conv_mma_kernel<MODE, NT, MTW>,
@@ -522,11 +578,11 @@ int launch_wgrad(MmaWgradParams& p, cudaStream_t st) {
     const int TP = 128;
     const int rows_max = TP / p.P + 2;
     const int nr_max = (rows_max - 1) * p.S + p.K;
-    p.WS = (nr_max * p.P + 3) & ~3;
-    p.DS = TP + 4;
+    p.WS = (nr_max * p.P + 3 + 3) & ~3;      // + up to 3 floats of alignment shift
+    p.DS = TP + 4;                           // 132: holds the shift, and 132 mod 32 = 4 spreads the A rows over banks
     p.tiles_per_b = (int)ceil_div64((int64_t)p.Lout * p.P, TP);
     p.ntiles = p.B * p.tiles_per_b;
-    size_t smem = ((size_t)2 * p.Cig * p.WS + (size_t)2 * 16 * MT * p.DS) * sizeof(float);
+    size_t smem = ((size_t)2 * p.Cig * p.WS + (size_t)2 * 16 * MT * p.DS + 2 * p.Cig + 2 * 16 * MT) * sizeof(float);
     if (smem < (size_t)16 * MT * NT * 8 * sizeof(float)) smem = (size_t)16 * MT * NT * 8 * sizeof(float);
     if (smem > 200 * 1024) return LCT_EUNSUPPORTED;
     if (smem > 40 * 1024) {
