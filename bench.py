@@ -190,6 +190,8 @@ def main():
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-reuse", action="store_true", help="run the enhancer forward twice per step like train.py does "
                     "(default: one forward serves the D and the G step: identical values, SURVEY 8f N1)")
+    ap.add_argument("--torch-optim", action="store_true", help="use torch.optim.AdamW (as train.py builds it) instead of "
+                    "the fused multi-tensor AdamW kernel (same update rule; SURVEY 8f N2)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -210,12 +212,16 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     from lctgan import _lib
+    if os.environ.get("LCT_MMA_TUNE"):
+        a, b = os.environ["LCT_MMA_TUNE"].split(",")
+        _lib.call_ret("lct_conv_mma_tune", int(a), int(b))
     from lctgan.parallel import FlatGradAllReduce, broadcast_parameters
     from lctgan.training import GraphedTrainStep, StepArgs, build_models, train_step
     from oracle import lct_oracle as O
 
     use_graph = not args.no_graph
-    enh, mpd, msd, tf, mr, g_opt, d_opt = build_models(dev, gan_seed=42, capturable=use_graph)
+    enh, mpd, msd, tf, mr, g_opt, d_opt = build_models(dev, gan_seed=42, capturable=use_graph,
+                                                       fused_optim=not args.torch_optim)
     if world > 1:
         broadcast_parameters([enh, mpd, msd])
     sync_d = FlatGradAllReduce(list(mpd.parameters()) + list(msd.parameters())) if world > 1 else None
@@ -310,7 +316,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 tensor-core operands for the dense contraction (fp32 accumulate), f32 elsewhere",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "gan_loss": args.gan_loss, "parallelism": f"dp{world}", "cuda_graph": graphed is not None, "reuse_enhancer_forward": sargs.reuse_enhancer_forward,
+        "config": {"workload": WORKLOAD, "gan_loss": args.gan_loss, "parallelism": f"dp{world}", "cuda_graph": graphed is not None, "reuse_enhancer_forward": sargs.reuse_enhancer_forward, "fused_adamw": not args.torch_optim,
                    "l2": "no explicit flush: one step streams > 2 GB of activations (>> 126 MB L2)"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,

@@ -91,6 +91,9 @@ LCT_API int lct_avgpool4_bwd(const float* gy, float* gx, int64_t B, int64_t L, c
 /* weight_norm (torch.nn.utils.weight_norm, dim 0; discriminators.py:46-66, :176-196): w = g * v / ||v||, rows of length `row`. */
 LCT_API int lct_weight_norm_fwd(const float* g, const float* v, float* w, float* norm, int64_t Cout, int64_t row, cudaStream_t stream);
 LCT_API int lct_weight_norm_bwd(const float* g, const float* v, const float* dw, float* dg, float* dv, int64_t Cout, int64_t row, cudaStream_t stream);
+/* The same for up to 16 layers in one launch (g/v/w/dw/dg/dv: HOST arrays of device pointers; rows = Cout, rowlen per layer). */
+LCT_API int lct_mt_weight_norm_fwd(const void* const* g, const void* const* v, void* const* w, const int64_t* rows, const int64_t* rowlen, int64_t nseg, cudaStream_t stream);
+LCT_API int lct_mt_weight_norm_bwd(const void* const* g, const void* const* v, const void* const* dw, void* const* dg, void* const* dv, const int64_t* rows, const int64_t* rowlen, int64_t nseg, cudaStream_t stream);
 /* Conv2d(k=(K,1), stride=(S,1), pad=(pad,0), groups=G) / Conv1d(K,S,pad,G) + bias + activation
  * (discriminators.py:93-98, :215-220).  x [B,Cin,Lin,P] -> y [B,Cout,Lout,P], w [Cout,Cin/G,K]. */
 LCT_API int lct_conv1d_fwd(const float* x, const float* w, const float* bias, float* y, int64_t B, int64_t Cin, int64_t Cout, int64_t G, int64_t K, int64_t S, int64_t pad, int64_t Lin, int64_t P, int act, float slope, cudaStream_t stream);
@@ -103,6 +106,7 @@ LCT_API int lct_conv1d_wgrad(const float* x, const float* dy, float* dw, float* 
 /* The same grouped convolutions on the tensor cores: TF32 mma.sync implicit GEMM, fp32 accumulation, persistent CTAs with
  * cp.async double-buffered input windows (conv_mma.cu).  Same arguments as lct_conv1d_*; lct_conv_mma_supported says
  * whether a layer shape is covered (groups with <= 16 in / <= 32 out channels, stride 1/3/4, Cin/G * K <= 168). */
+LCT_API int lct_conv_mma_tune(int ctas_per_sm, int force_mtw);   /* tuning: CTAs per SM of the persistent grids (default 3); force 2 or 4 m-tiles per warp (0 = auto) */
 LCT_API int lct_conv_mma_supported(int64_t Cin, int64_t Cout, int64_t G, int64_t K, int64_t S, int64_t P);
 LCT_API int lct_conv_mma_fwd(const float* x, const float* w, const float* bias, float* y, int64_t B, int64_t Cin, int64_t Cout, int64_t G, int64_t K, int64_t S, int64_t pad, int64_t Lin, int64_t P, int act, float slope, cudaStream_t stream);
 LCT_API int lct_conv_mma_dgrad(const float* dy, const float* w, float* dx, const float* gextra, const float* xact, int64_t B, int64_t Cin, int64_t Cout, int64_t G, int64_t K, int64_t S, int64_t pad, int64_t Lin, int64_t P, int act, float slope, cudaStream_t stream);
@@ -173,5 +177,11 @@ LCT_API int lct_mt_grad(const void* const* a, const void* const* b, void* const*
 /* dst_i[j] = src_i[j] for nseg tensors in one launch (packs the 16/32 GRU parameter tensors of a block). */
 LCT_API int lct_mt_copy(const void* const* src, void* const* dst, const int64_t* n, int64_t nseg, cudaStream_t stream);
 LCT_API int lct_mt_max_segments(void);
+/* Fused multi-tensor AdamW (the optimiser train.py:601-610 builds): p/g/m/v are HOST arrays of device
+ * pointers (<= lct_mt_adamw_max_segments() tensors per launch), n HOST element counts, step a device float that already
+ * holds this update's step number (lct_add_scalar increments it on the stream: CUDA-graph friendly). */
+LCT_API int lct_mt_adamw(void* const* p, const void* const* g, void* const* m, void* const* v, const int64_t* n, int64_t nseg, const float* step, float lr, float beta1, float beta2, float eps, float weight_decay, cudaStream_t stream);
+LCT_API int lct_mt_adamw_max_segments(void);
+LCT_API int lct_add_scalar(float* x, float v, cudaStream_t stream);
 
 #endif /* LCTGAN_H_ */

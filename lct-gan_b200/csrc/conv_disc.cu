@@ -509,7 +509,90 @@ __global__ void wnorm_bwd_kernel(const float* __restrict__ g, const float* __res
     for (int i = threadIdx.x; i < row; i += blockDim.x) dv[(size_t)co * row + i] = k1 * (dr[i] - k2 * vr[i]);
 }
 
+// ---- all layers of a stack in one launch (the per-layer launches sat on the critical path of every chain) ----
+constexpr int kMaxWn = 16;
+struct WnSegs {
+    const float* g[kMaxWn];
+    const float* v[kMaxWn];
+    const float* dw[kMaxWn];
+    float* w[kMaxWn];      // fwd: w;  bwd: dv
+    float* dg[kMaxWn];
+    int row0[kMaxWn + 1];  // prefix sum of rows (out channels)
+    int rowlen[kMaxWn];
+    int nseg;
+};
+
+template <bool BWD>
+__global__ void __launch_bounds__(128) mt_wnorm_kernel(const WnSegs S) {
+    __shared__ float red[32];
+    int seg = 0;
+    while (seg + 1 < S.nseg && (int)blockIdx.x >= S.row0[seg + 1]) ++seg;
+    const int co = blockIdx.x - S.row0[seg];
+    const int row = S.rowlen[seg];
+    const float* vr = S.v[seg] + (size_t)co * row;
+    float a = 0.f, d = 0.f;
+    if (BWD) {
+        const float* dr = S.dw[seg] + (size_t)co * row;
+        for (int i = threadIdx.x; i < row; i += blockDim.x) {
+            float vv = vr[i];
+            a += vv * vv;
+            d += vv * dr[i];
+        }
+        const float n2 = block_sum(a, red);
+        const float dot = block_sum(d, red);
+        const float nrm = sqrtf(n2);
+        const float gg = S.g[seg][co];
+        if (threadIdx.x == 0) S.dg[seg][co] = dot / nrm;
+        const float k1 = gg / nrm, k2 = dot / n2;
+        float* dv = S.w[seg] + (size_t)co * row;
+        for (int i = threadIdx.x; i < row; i += blockDim.x) dv[i] = k1 * (dr[i] - k2 * vr[i]);
+    } else {
+        for (int i = threadIdx.x; i < row; i += blockDim.x) a += vr[i] * vr[i];
+        const float sc = S.g[seg][co] / sqrtf(block_sum(a, red));
+        float* w = S.w[seg] + (size_t)co * row;
+        for (int i = threadIdx.x; i < row; i += blockDim.x) w[i] = vr[i] * sc;
+    }
+}
+
+int fill_wn(WnSegs& S, const void* const* g, const void* const* v, const void* const* dw, void* const* w,
+            void* const* dg, const int64_t* rows, const int64_t* rowlen, int64_t nseg, bool bwd) {
+    if (!g || !v || !w || !rows || !rowlen || nseg <= 0 || nseg > kMaxWn || (bwd && (!dw || !dg))) return LCT_EINVAL;
+    int tot = 0;
+    for (int i = 0; i < nseg; ++i) {
+        if (!g[i] || !v[i] || !w[i] || rows[i] <= 0 || rowlen[i] <= 0 || (bwd && (!dw[i] || !dg[i]))) return LCT_EINVAL;
+        S.g[i] = (const float*)g[i]; S.v[i] = (const float*)v[i]; S.w[i] = (float*)w[i];
+        S.dw[i] = bwd ? (const float*)dw[i] : nullptr; S.dg[i] = bwd ? (float*)dg[i] : nullptr;
+        S.row0[i] = tot; S.rowlen[i] = (int)rowlen[i];
+        tot += (int)rows[i];
+    }
+    S.row0[nseg] = tot;
+    S.nseg = (int)nseg;
+    return tot;
+}
+
 }  // namespace
+
+// weight norm of up to 16 layers in one launch; g/v/w: HOST arrays of device pointers, rows/rowlen: HOST arrays
+LCT_API int lct_mt_weight_norm_fwd(const void* const* g, const void* const* v, void* const* w, const int64_t* rows,
+                                   const int64_t* rowlen, int64_t nseg, cudaStream_t st) {
+    WnSegs S;
+    int tot = fill_wn(S, g, v, nullptr, w, nullptr, rows, rowlen, nseg, false);
+    if (tot < 0) return tot;
+    mt_wnorm_kernel<false><<<tot, 128, 0, st>>>(S);
+    LCT_RETURN_IF_LAUNCH_FAILED();
+    return 0;
+}
+
+LCT_API int lct_mt_weight_norm_bwd(const void* const* g, const void* const* v, const void* const* dw, void* const* dg,
+                                   void* const* dv, const int64_t* rows, const int64_t* rowlen, int64_t nseg,
+                                   cudaStream_t st) {
+    WnSegs S;
+    int tot = fill_wn(S, g, v, dw, dv, dg, rows, rowlen, nseg, true);
+    if (tot < 0) return tot;
+    mt_wnorm_kernel<true><<<tot, 128, 0, st>>>(S);
+    LCT_RETURN_IF_LAUNCH_FAILED();
+    return 0;
+}
 
 // y[B,Cout,Lout,P] = act(conv_L(x[B,Cin,Lin,P], w[Cout,Cin/G,K]) + bias)
 LCT_API int lct_conv1d_fwd(const float* x, const float* w, const float* bias, float* y, int64_t B, int64_t Cin,

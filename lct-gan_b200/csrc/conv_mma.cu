@@ -470,8 +470,11 @@ int pick_ns(int npad) {
     return ns;
 }
 
+int g_ctas_per_sm = 3;
+int g_force_mtw = 0;
+
 int grid_y(int G, int ntiles) {
-    int per = (148 * 3 + G - 1) / G;     // ~3 resident CTAs per SM in total
+    int per = (148 * g_ctas_per_sm + G - 1) / G;     // resident CTAs per SM in total
     if (per < 1) per = 1;
     if (per > ntiles) per = ntiles;
     return per;
@@ -502,6 +505,8 @@ int launch_mma(MmaParams& p, cudaStream_t st) {
 template <int MODE, int NT>
 int launch_mma_mtw(MmaParams& p, cudaStream_t st) {
     // short layers: 128-position tiles keep more CTAs busy
+    if (g_force_mtw == 2) return launch_mma<MODE, NT, 2>(p, st);
+    if (g_force_mtw == 4) return launch_mma<MODE, NT, 4>(p, st);
     if ((int64_t)p.Q * p.P * p.B * (p.Cx / p.Cxg) < 148 * 256) return launch_mma<MODE, NT, 2>(p, st);
     return launch_mma<MODE, NT, 4>(p, st);
 }
@@ -514,6 +519,13 @@ bool shape_ok(int64_t B, int64_t Cin, int64_t Cout, int64_t G, int64_t K, int64_
 }
 
 }  // namespace
+
+// tuning knobs (bring-up / experiments): resident CTAs per SM targeted by the persistent grids, forced m-tiles per warp
+LCT_API int lct_conv_mma_tune(int ctas_per_sm, int force_mtw) {
+    if (ctas_per_sm > 0) g_ctas_per_sm = ctas_per_sm;
+    g_force_mtw = force_mtw;
+    return 0;
+}
 
 // 1 if the tensor-core kernels cover this layer (otherwise use lct_conv1d_*)
 LCT_API int lct_conv_mma_supported(int64_t Cin, int64_t Cout, int64_t G, int64_t K, int64_t S, int64_t P) {

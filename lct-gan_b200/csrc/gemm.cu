@@ -111,16 +111,26 @@ __global__ void __launch_bounds__(kThreads) gemm_kernel(const GemmParams p) {
     }
 }
 
-// out[n] += sum_m X[m, n]
-__global__ void colsum_kernel(const float* __restrict__ X, float* __restrict__ out, int M, int N, int ld,
-                              int rows_per_cta) {
-    const int n = blockIdx.y * blockDim.x + threadIdx.x;
-    if (n >= N) return;
+// out[n] += sum_m X[m, n]: a 32-column x 8-row-group CTA walks 256 rows, reduces the row groups in shared memory
+// and issues one atomic per column
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, float* __restrict__ out, int M, int N,
+                                                     int ld, int rows_per_cta) {
+    __shared__ float red[8][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int n = blockIdx.y * 32 + tx;
     const int r0 = blockIdx.x * rows_per_cta;
     const int r1 = min(M, r0 + rows_per_cta);
     float a = 0.f;
-    for (int r = r0; r < r1; ++r) a += X[(int64_t)r * ld + n];
-    atomicAdd(&out[n], a);
+    if (n < N)
+        for (int r = r0 + ty; r < r1; r += 8) a += X[(int64_t)r * ld + n];
+    red[ty][tx] = a;
+    __syncthreads();
+    if (ty == 0 && n < N) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += red[i][tx];
+        atomicAdd(&out[n], s);
+    }
 }
 
 }  // namespace
@@ -154,9 +164,8 @@ LCT_API int lct_gemm(const float* A, const float* B, float* C, const float* bias
 LCT_API int lct_colsum(const float* X, float* out, int64_t M, int64_t N, int64_t ld, cudaStream_t st) {
     if (!X || !out || M <= 0 || N <= 0) return LCT_EINVAL;
     const int rows = 256;
-    int threads = N >= 128 ? 128 : (N >= 64 ? 64 : 32);
-    dim3 grid((unsigned)ceil_div64(M, rows), (unsigned)ceil_div64(N, threads));
-    colsum_kernel<<<grid, threads, 0, st>>>(X, out, (int)M, (int)N, (int)ld, rows);
+    dim3 grid((unsigned)ceil_div64(M, rows), (unsigned)ceil_div64(N, 32));
+    colsum_kernel<<<grid, 256, 0, st>>>(X, out, (int)M, (int)N, (int)ld, rows);
     LCT_RETURN_IF_LAUNCH_FAILED();
     return 0;
 }

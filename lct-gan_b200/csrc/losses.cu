@@ -143,7 +143,87 @@ int build(Segs& S, const void* const* a, const void* const* b, void* const* g, c
     return chunks;
 }
 
+// ---- fused multi-tensor AdamW (torch.optim.AdamW semantics, train.py:601-610) ----
+constexpr int kMaxAdam = 48;
+struct AdamSegs {
+    float* p[kMaxAdam];
+    const float* g[kMaxAdam];
+    float* m[kMaxAdam];
+    float* v[kMaxAdam];
+    int64_t n[kMaxAdam];
+    int chunk0[kMaxAdam + 1];
+    int nseg;
+};
+
+__global__ void __launch_bounds__(kThreads) mt_adamw_kernel(const AdamSegs S, const float* __restrict__ step_ptr,
+                                                            float lr, float b1, float b2, float eps, float wd) {
+    int lo = 0, hi = S.nseg - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (S.chunk0[mid] <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    const int seg = lo;
+    const int64_t start = (int64_t)(blockIdx.x - S.chunk0[seg]) * kChunk;
+    const int64_t end = min(start + (int64_t)kChunk, S.n[seg]);
+    const double t = (double)step_ptr[0];                       // already incremented for this step
+    const float bc1 = (float)(1.0 - pow((double)b1, t));
+    const float bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, t));
+    const float step_size = lr / bc1;
+    const float decay = 1.f - lr * wd;
+    float* __restrict__ pp = S.p[seg];
+    const float* __restrict__ gg = S.g[seg];
+    float* __restrict__ mm = S.m[seg];
+    float* __restrict__ vv = S.v[seg];
+    for (int64_t i = start + threadIdx.x; i < end; i += kThreads) {
+        const float g = gg[i];
+        float p = pp[i] * decay;
+        float m = mm[i];
+        m = m + (g - m) * (1.f - b1);
+        const float v = b2 * vv[i] + (1.f - b2) * g * g;
+        const float denom = sqrtf(v) / bc2_sqrt + eps;
+        p -= step_size * (m / denom);
+        pp[i] = p;
+        mm[i] = m;
+        vv[i] = v;
+    }
+}
+
+__global__ void add_scalar_kernel(float* x, float v) { x[0] += v; }
+
 }  // namespace
+
+// x[0] += v  (device-side step counter of the fused optimiser, CUDA-graph friendly)
+LCT_API int lct_add_scalar(float* x, float v, cudaStream_t st) {
+    if (!x) return LCT_EINVAL;
+    add_scalar_kernel<<<1, 1, 0, st>>>(x, v);
+    LCT_RETURN_IF_LAUNCH_FAILED();
+    return 0;
+}
+
+// One AdamW update (decoupled weight decay, bias correction, torch.optim.AdamW defaults' formulas) of up to 48 tensors
+// per launch.  p/g/m/v: HOST arrays of device pointers, n: HOST array of element counts; step: device float holding
+// the (already incremented) step number.
+LCT_API int lct_mt_adamw(void* const* p, const void* const* g, void* const* m, void* const* v, const int64_t* n,
+                         int64_t nseg, const float* step, float lr, float beta1, float beta2, float eps,
+                         float weight_decay, cudaStream_t st) {
+    if (!p || !g || !m || !v || !n || !step || nseg <= 0 || nseg > kMaxAdam) return LCT_EINVAL;
+    AdamSegs S;
+    int chunks = 0;
+    for (int i = 0; i < nseg; ++i) {
+        if (!p[i] || !g[i] || !m[i] || !v[i] || n[i] <= 0) return LCT_EINVAL;
+        S.p[i] = (float*)p[i]; S.g[i] = (const float*)g[i]; S.m[i] = (float*)m[i]; S.v[i] = (float*)v[i];
+        S.n[i] = n[i];
+        S.chunk0[i] = chunks;
+        chunks += (int)ceil_div64(n[i], kChunk);
+    }
+    S.chunk0[nseg] = chunks;
+    S.nseg = (int)nseg;
+    mt_adamw_kernel<<<chunks, kThreads, 0, st>>>(S, step, lr, beta1, beta2, eps, weight_decay);
+    LCT_RETURN_IF_LAUNCH_FAILED();
+    return 0;
+}
+
+LCT_API int lct_mt_adamw_max_segments(void) { return kMaxAdam; }
 
 // out[0] += sum_i scale[i] * sum_j op(a_i[j], b_i[j]);  `out` must be zeroed by the caller.
 //   op 0: (a-k0)^2   1: (a-b)^2   2: |a-b|   3: relu(k0 + k1*a)   4: a

@@ -7,6 +7,11 @@ Backward, per layer from the top: the data-gradient kernel of layer i+1 adds the
 feature-matching gradient that arrived for map i and multiplies by LeakyReLU'(map i) in its
 epilogue, so the pre-activation gradient of every layer is produced exactly once and feeds both
 the weight-gradient and the next data-gradient kernel.
+
+Chain length matters at batch 8 (every kernel of a sub-discriminator depends on the previous one and
+fills at most one wave of the GPU), so everything that does not depend on the activations is batched:
+the weight norms of all layers are ONE launch in forward and ONE in backward, and all weight / bias
+gradient accumulators of a stack are views of one zero-filled buffer (one fill).
 """
 from __future__ import annotations
 
@@ -20,9 +25,10 @@ LRELU_SLOPE = 0.2
 
 
 def _use_dense(x_shape, w_shape, k, s, g) -> bool:
-    """MSD convs.5-like layers (dense, stride 1, P == 1) go to the tcgen05 kernel in bf16 mode."""
+    """MSD convs.5-like layers (dense, stride 1, P == 1) go to the tcgen05 kernel in tensor-core mode."""
     return (config.dense_tensor_cores and g == 1 and s == 1 and x_shape[3] == 1 and w_shape[0] > 1
             and ops.dense_supported(w_shape[1], w_shape[0], k))
+
 
 # (kernel, stride, padding, groups) per conv; the last entry is conv_post (no activation)
 LayerSpec = Tuple[int, int, int, int]
@@ -37,13 +43,14 @@ class ConvStackFn(torch.autograd.Function):
         n = len(specs)
         assert len(params) == 3 * n
         x4 = x4.contiguous()
+        gs = [params[3 * i + 1].contiguous() for i in range(n)]
+        vs = [params[3 * i + 2].contiguous() for i in range(n)]
+        weights = ops.mt_weight_norm_fwd(gs, vs)
         fmaps: List[torch.Tensor] = []
-        weights: List[torch.Tensor] = []
         h = x4
         dense: List[int] = []
         for i, (k, s, pad, g) in enumerate(specs):
-            bias, wg, wv = params[3 * i], params[3 * i + 1], params[3 * i + 2]
-            w = ops.weight_norm_fwd(wg.contiguous(), wv.contiguous())
+            bias, w = params[3 * i], weights[i]
             last = i == n - 1
             act = ops.ACT_NONE if last else ops.ACT_LRELU
             if _use_dense(h.shape, w.shape, k, s, g) and pad == k // 2:
@@ -54,7 +61,6 @@ class ConvStackFn(torch.autograd.Function):
             else:
                 h = ops.conv1d_fwd(h, w, bias, g, s, pad, act=act, slope=LRELU_SLOPE)
             fmaps.append(h)
-            weights.append(w)
         ctx.specs = list(specs)
         ctx.dense = dense
         ctx.skip_param_grads = skip_param_grads
@@ -75,6 +81,11 @@ class ConvStackFn(torch.autograd.Function):
         want_params = any(need_p) and not (ctx.skip_param_grads and need_x)
         gparams: List = [None] * (3 * n)
         gouts = [g.contiguous() if g is not None else None for g in gouts]
+        dws = dbs = None
+        if want_params:   # all accumulators of the stack in one zero-filled allocation
+            bufs = ops._flat_views([tuple(w.shape) for w in weights] + [(w.shape[0],) for w in weights], x4.device,
+                                   zero=True)
+            dws, dbs = bufs[:n], bufs[n:]
 
         dpre = gouts[n - 1]      # conv_post has no activation
         gx = None
@@ -86,21 +97,16 @@ class ConvStackFn(torch.autograd.Function):
                 B_, Ci_, L_ = inp.shape[0], inp.shape[1], inp.shape[2]
                 Co_ = weights[i].shape[0]
                 if want_params:
-                    db = torch.zeros(Co_, dtype=torch.float32, device=inp.device)
                     Lp = L_ + k - 1
-                    dyq = ops.stage_ncl_bf16(dpre, Lp, 0, rowsum=db)
+                    dyq = ops.stage_ncl_bf16(dpre, Lp, 0, rowsum=dbs[i])
                     xq = ops.stage_ncl_bf16(inp, Lp, pad, copies=k)
-                    dw = ops.dense_wgrad(dyq, xq, Co_, Ci_, k, weights[i].shape)
-                    dg, dv = ops.weight_norm_bwd(params[3 * i + 1].contiguous(), params[3 * i + 2].contiguous(), dw)
-                    gparams[3 * i], gparams[3 * i + 1], gparams[3 * i + 2] = db, dg, dv
+                    ops.dense_wgrad(dyq, xq, Co_, Ci_, k, weights[i].shape, out=dws[i])
                 _, wd = ops.stage_dense_weights(weights[i], want_wt=False, want_wd=True)
                 dpre = ops.dense_conv(ops.stage_nlc_bf16(dpre, pad), wd, B_, L_, Co_, Ci_, k, gextra=gouts[i - 1],
                                       xact=inp, act=ops.ACT_LRELU, slope=LRELU_SLOPE)
             elif dpre is not None:
                 if want_params:
-                    dw, db = ops.conv1d_wgrad(inp, dpre, weights[i].shape, g, s, pad, want_bias=True)
-                    dg, dv = ops.weight_norm_bwd(params[3 * i + 1].contiguous(), params[3 * i + 2].contiguous(), dw)
-                    gparams[3 * i], gparams[3 * i + 1], gparams[3 * i + 2] = db, dg, dv
+                    ops.conv1d_wgrad(inp, dpre, weights[i].shape, g, s, pad, want_bias=True, dw=dws[i], db=dbs[i])
                 if i > 0:
                     dpre = ops.conv1d_dgrad(dpre, weights[i], inp.shape, g, s, pad, gextra=gouts[i - 1], xact=inp,
                                             act=ops.ACT_LRELU, slope=LRELU_SLOPE)
@@ -109,11 +115,13 @@ class ConvStackFn(torch.autograd.Function):
             elif i > 0 and gouts[i - 1] is not None:
                 dpre = ops.act_bwd(inp, gouts[i - 1], ops.ACT_LRELU, LRELU_SLOPE)
         if want_params:
-            for j in range(3 * n):
-                if gparams[j] is None and need_p[j]:
-                    gparams[j] = torch.zeros_like(params[j])
-                elif not need_p[j]:
-                    gparams[j] = None
+            gs = [params[3 * i + 1].contiguous() for i in range(n)]
+            vs = [params[3 * i + 2].contiguous() for i in range(n)]
+            dgs, dvs = ops.mt_weight_norm_bwd(gs, vs, dws)
+            for i in range(n):
+                gparams[3 * i] = dbs[i] if need_p[3 * i] else None
+                gparams[3 * i + 1] = dgs[i] if need_p[3 * i + 1] else None
+                gparams[3 * i + 2] = dvs[i] if need_p[3 * i + 2] else None
         return (gx, None, None, *gparams)
 
 

@@ -237,6 +237,36 @@ def _is_post(cout, k, groups, stride, pad):
     return cout == 1 and groups == 1 and stride == 1 and (k & 1) and k <= 8 and pad == k // 2
 
 
+def _flat_views(shapes, device, zero=False):
+    """One allocation (optionally zero-filled: one fill kernel) carved into contiguous tensors of `shapes`."""
+    sizes = [int(math.prod(s)) for s in shapes]
+    offs, tot = [], 0
+    for n in sizes:
+        offs.append(tot)
+        tot += (n + 3) // 4 * 4            # keep every view 16-byte aligned
+    flat = (torch.zeros if zero else torch.empty)(tot, dtype=torch.float32, device=device)
+    return [flat[o:o + n].view(s) for o, n, s in zip(offs, sizes, shapes)]
+
+
+def mt_weight_norm_fwd(gs, vs):
+    """w_i = g_i * v_i / ||v_i|| for all layers of a stack in one launch."""
+    ws = _flat_views([tuple(v.shape) for v in vs], vs[0].device)
+    rows = (ctypes.c_int64 * len(vs))(*[v.shape[0] for v in vs])
+    rowlen = (ctypes.c_int64 * len(vs))(*[v.numel() // v.shape[0] for v in vs])
+    call("lct_mt_weight_norm_fwd", _ptr_array(gs), _ptr_array(vs), _ptr_array(ws), rows, rowlen, len(vs))
+    return ws
+
+
+def mt_weight_norm_bwd(gs, vs, dws):
+    dgs = _flat_views([tuple(g.shape) for g in gs], gs[0].device)
+    dvs = _flat_views([tuple(v.shape) for v in vs], vs[0].device)
+    rows = (ctypes.c_int64 * len(vs))(*[v.shape[0] for v in vs])
+    rowlen = (ctypes.c_int64 * len(vs))(*[v.numel() // v.shape[0] for v in vs])
+    call("lct_mt_weight_norm_bwd", _ptr_array(gs), _ptr_array(vs), _ptr_array(dws), _ptr_array(dgs), _ptr_array(dvs),
+         rows, rowlen, len(vs))
+    return dgs, dvs
+
+
 def conv_out_len(lin, k, s, pad):
     return (lin + 2 * pad - k) // s + 1
 
@@ -272,11 +302,14 @@ def conv1d_dgrad(dy, w, x_shape, groups, stride, pad, gextra=None, xact=None, ac
     return dx
 
 
-def conv1d_wgrad(x, dy, w_shape, groups, stride, pad, want_bias=True):
+def conv1d_wgrad(x, dy, w_shape, groups, stride, pad, want_bias=True, dw=None, db=None):
+    """dw/db may be passed in pre-zeroed (views of one flat buffer: one fill per stack instead of two per layer)."""
     B, Cin, Lin, P = x.shape
     Cout, K = w_shape[0], w_shape[2]
-    dw = torch.zeros(w_shape, dtype=torch.float32, device=x.device)
-    db = torch.zeros(Cout, dtype=torch.float32, device=x.device) if want_bias else None
+    if dw is None:
+        dw = torch.zeros(w_shape, dtype=torch.float32, device=x.device)
+    if db is None and want_bias:
+        db = torch.zeros(Cout, dtype=torch.float32, device=x.device)
     if _is_post(Cout, K, groups, stride, pad):
         call("lct_conv_post_wgrad", x, dy, dw, db, B, Cin, Lin, P, K)
         return dw, db
@@ -485,7 +518,7 @@ def dense_conv(a_staged, w_staged, B, L, Ca, Cn, K, bias=None, gextra=None, xact
     return out
 
 
-def dense_wgrad(dyq, xq, Co, Ci, K, w_shape):
-    dw = torch.empty(w_shape, dtype=torch.float32, device=dyq.device)
+def dense_wgrad(dyq, xq, Co, Ci, K, w_shape, out=None):
+    dw = out if out is not None else torch.empty(w_shape, dtype=torch.float32, device=dyq.device)
     call("lct_dense_wgrad", dyq, xq, dw, Co, Ci, K, dyq.shape[-1])
     return dw

@@ -126,7 +126,7 @@ def train_step(enhancer, mpd, msd, tf_features, mrstft_loss, g_opt, d_opt, noisy
 
 
 def build_models(device, gan_seed: Optional[int] = 42, max_time_context: Optional[int] = 200,
-                 capturable: bool = False):
+                 capturable: bool = False, fused_optim: bool = False):
     """Construct the five modules in the reference's order (train.py:569-598) so that a given seed
     yields the reference's initial weights, and the two AdamW optimisers (train.py:601-610)."""
     from datasets.tf_features import TFFeatures, TFFeaturesConfig
@@ -139,6 +139,11 @@ def build_models(device, gan_seed: Optional[int] = 42, max_time_context: Optiona
     msd = MultiScaleDiscriminator().to(device)
     tf = TFFeatures(TFFeaturesConfig(n_fft=512, c=0.3, compress_input=False, return_stfts=False)).to(device)
     mr = L.MultiResolutionSTFTLoss(L.MRSTFTLossConfig()).to(device)
+    if fused_optim:   # same hyper-parameters and update rule, one multi-tensor kernel
+        from .optim import FusedAdamW
+        g_opt = FusedAdamW(enhancer.parameters(), lr=2e-4, betas=(0.8, 0.99))
+        d_opt = FusedAdamW(list(mpd.parameters()) + list(msd.parameters()), lr=2e-4, betas=(0.8, 0.99))
+        return enhancer, mpd, msd, tf, mr, g_opt, d_opt
     g_opt = torch.optim.AdamW(enhancer.parameters(), lr=2e-4, betas=(0.8, 0.99), capturable=capturable)
     d_opt = torch.optim.AdamW(list(mpd.parameters()) + list(msd.parameters()), lr=2e-4, betas=(0.8, 0.99),
                               capturable=capturable)

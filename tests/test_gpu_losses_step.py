@@ -120,3 +120,29 @@ def test_training_step_matches_oracle(dev, gan_loss):
             assert diff.max().item() <= 2.0 * lr * nsteps, (k, diff.max().item())
             bad = (diff > 0.05 * lr * nsteps).float().mean().item()
             assert bad <= 1e-3, (k, bad)
+
+
+def test_fused_adamw_matches_torch(dev):
+    """lctgan.optim.FusedAdamW against torch.optim.AdamW (the optimiser train.py:601-610 builds): same updates."""
+    from lctgan.optim import FusedAdamW
+    g = torch.Generator().manual_seed(0)
+    shapes = [(1024, 4, 41), (64,), (3, 5, 2, 1), (1,), (100001,)] * 12       # > 48 tensors: several launches
+    pa = [torch.randn(s, generator=g).to(dev).requires_grad_(True) for s in shapes]
+    pb = [p.detach().clone().requires_grad_(True) for p in pa]
+    oa = torch.optim.AdamW(pa, lr=2e-4, betas=(0.8, 0.99))
+    ob = FusedAdamW(pb, lr=2e-4, betas=(0.8, 0.99))
+    for step in range(4):
+        for a, b in zip(pa, pb):
+            gr = torch.randn(a.shape, generator=g).to(dev) * (10.0 ** (step - 2))
+            a.grad = gr.clone()
+            b.grad = gr.clone()
+        oa.step()
+        ob.step()
+    for a, b in zip(pa, pb):
+        assert rel_err(b, a) < 2e-6
+    st = ob.state[pb[0]]
+    assert set(st) == {"step", "exp_avg", "exp_avg_sq"} and float(st["step"]) == 4.0
+    assert rel_err(st["exp_avg"], oa.state[pa[0]]["exp_avg"]) < 2e-6
+    assert rel_err(st["exp_avg_sq"], oa.state[pa[0]]["exp_avg_sq"]) < 2e-6
+    with pytest.raises(ValueError):
+        FusedAdamW(pb, lr=-1.0)
