@@ -175,6 +175,28 @@ __global__ void __launch_bounds__(kThreads) conv_mma_kernel(const MmaParams p) {
         chk[kk] = chn;
     }
     __syncthreads();
+    // this thread's accumulator columns: n = nt*8 + 2*tq + c  ->  output channel, row shift (dgrad: phase - pad), bias
+    int col_ch[NT][2], col_r[NT][2];
+    float col_bias[NT][2];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int n = nt * 8 + 2 * tq + c;
+            col_ch[nt][c] = -1;
+            col_r[nt][c] = 0;
+            col_bias[nt][c] = 0.f;
+            if (n < p.N) {
+                if (MODE == MODE_FWD) {
+                    col_ch[nt][c] = g * p.N + n;
+                    if (p.bias) col_bias[nt][c] = p.bias[g * p.N + n];
+                } else {
+                    const int ci = n / p.S;
+                    col_ch[nt][c] = g * p.Cig + ci;
+                    col_r[nt][c] = n - ci * p.S - p.opad;
+                }
+            }
+        }
     int tile = blockIdx.y;
     if (tile < p.ntiles) stage_window(p, g, tile, TP, win0, lutd0, lut0, chk);
     cp_async_commit();
@@ -238,34 +260,26 @@ __global__ void __launch_bounds__(kThreads) conv_mma_kernel(const MmaParams p) {
                 for (int mt = 0; mt < MTW; ++mt) mma_tf32(acc[mt][nt], a[mt][0], a[mt][1], a[mt][2], a[mt][3], b0, b1);
             }
         }
-        // ---- epilogue
+        // ---- epilogue (column -> channel / phase mapping hoisted out of the tile loop: col_ch, col_r)
         const int lo_p = p.Lo * p.P;
+        const int bbase = b * p.Co * lo_p;
 #pragma unroll
         for (int mt = 0; mt < MTW; ++mt)
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 if (rowq[mt][h] < 0) continue;
+                const int rbase = (MODE == MODE_FWD ? rowq[mt][h] : p.S * rowq[mt][h]);
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
                     for (int c = 0; c < 2; ++c) {
-                        const int n = nt * 8 + 2 * tq + c;
-                        if (n >= p.N) continue;
-                        int ch, row_o;
-                        if (MODE == MODE_FWD) {
-                            ch = g * p.N + n;
-                            row_o = rowq[mt][h];
-                        } else {
-                            const int ci = n / p.S, r = n - ci * p.S;
-                            ch = g * p.Cig + ci;
-                            row_o = p.S * rowq[mt][h] + r - p.opad;
-                            if (row_o < 0 || row_o >= p.Lo) continue;
-                        }
-                        const size_t idx = ((size_t)b * p.Co + ch) * lo_p + (size_t)row_o * p.P + ppos[mt][h];
+                        if (col_ch[nt][c] < 0) continue;
+                        const int row_o = rbase + col_r[nt][c];
+                        if (MODE != MODE_FWD && (row_o < 0 || row_o >= p.Lo)) continue;
+                        const int idx = bbase + col_ch[nt][c] * lo_p + row_o * p.P + ppos[mt][h];
                         float v = acc[mt][nt][2 * h + c];
                         if (MODE == MODE_FWD) {
-                            if (p.bias) v += __ldg(&p.bias[ch]);
-                            v = apply_act(v, p.act, p.slope);
+                            v = apply_act(v + col_bias[nt][c], p.act, p.slope);
                         } else {
                             if (p.gextra) v += p.gextra[idx];
                             if (p.xact) v *= act_grad_from_out(p.xact[idx], p.act, p.slope);
@@ -470,8 +484,8 @@ int pick_ns(int npad) {
     return ns;
 }
 
-int g_ctas_per_sm = 3;
-int g_force_mtw = 0;
+int g_ctas_per_sm = 6;
+int g_force_mtw = 2;
 
 int grid_y(int G, int ntiles) {
     int per = (148 * g_ctas_per_sm + G - 1) / G;     // resident CTAs per SM in total
@@ -515,7 +529,8 @@ bool shape_ok(int64_t B, int64_t Cin, int64_t Cout, int64_t G, int64_t K, int64_
               int64_t P) {
     return B > 0 && B < 65536 && Cin > 0 && Cout > 0 && G > 0 && G < 65536 && Cin % G == 0 && Cout % G == 0 &&
            K > 0 && K <= 64 && S >= 1 && S <= 4 && pad >= 0 && Lin > 0 && P > 0 && P <= 16 &&
-           Lin + 2 * pad >= K && Lin * P < (1LL << 28);
+           Lin + 2 * pad >= K && Lin * P < (1LL << 28) && B * Cin * Lin * P < (1LL << 31) &&
+           B * Cout * ((Lin + 2 * pad - K) / S + 1) * P < (1LL << 31);
 }
 
 }  // namespace

@@ -338,7 +338,7 @@ LCT_API int lct_gconv_wgrad(const float* S, const float* Lg, float* dW, int64_t 
     GWgradParams p;
     p.S = S; p.Lg = Lg; p.dW = dW;
     p.B = (int)B; p.Ts = (int)Ts; p.Fs = (int)Fs; p.Ca = (int)Ca; p.Tl = (int)Tl; p.Fl = (int)Fl; p.Cc = (int)Cc;
-    p.rows_per_cta = 8;
+    p.rows_per_cta = 2;
     size_t smem = ((size_t)Fs * Ca + (size_t)2 * (Fl + 2) * Cc) * sizeof(float);
     if (smem > 200 * 1024) return LCT_EUNSUPPORTED;
     if (smem > 48 * 1024) {

@@ -325,9 +325,9 @@ __global__ void gru_combine_kernel(const float* __restrict__ x, const float* __r
 // Multi-head self-attention core: qkv [rows, 3E] (q | k | v, head h at columns h*16), E = H*16
 // ------------------------------------------------------------------------------------------
 constexpr int kHd = 16;
-constexpr int kAttnThreads = 128;
+constexpr int kAttnMaxThreads = 256;   // block = sequence length rounded up to a warp (one query/key per thread)
 
-__global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const float* __restrict__ qkv,
+__global__ void __launch_bounds__(kAttnMaxThreads) attn_fwd_kernel(const float* __restrict__ qkv,
                                                                 float* __restrict__ out, float* __restrict__ lse,
                                                                 SeqGeom geo, int H, float scale) {
     extern __shared__ __align__(16) float sm[];
@@ -336,14 +336,14 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const float* __r
     float* Vs = sm + (size_t)L * kHd;
     const int seq = blockIdx.x, h = blockIdx.y;
     const int64_t row0 = seq_row0(geo, seq);
-    for (int idx = threadIdx.x; idx < L * kHd; idx += kAttnThreads) {
+    for (int idx = threadIdx.x; idx < L * kHd; idx += (int)blockDim.x) {
         int t = idx / kHd, d = idx - t * kHd;
         const float* r = qkv + (row0 + (int64_t)t * geo.step_stride) * 3 * E;
         Ks[idx] = r[E + h * kHd + d];
         Vs[idx] = r[2 * E + h * kHd + d];
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < L; i += kAttnThreads) {
+    for (int i = threadIdx.x; i < L; i += (int)blockDim.x) {
         const int64_t row = row0 + (int64_t)i * geo.step_stride;
         float q[kHd], acc[kHd];
 #pragma unroll
@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_fwd_kernel(const float* __r
     }
 }
 
-__global__ void __launch_bounds__(kAttnThreads) attn_bwd_kernel(const float* __restrict__ qkv,
+__global__ void __launch_bounds__(kAttnMaxThreads) attn_bwd_kernel(const float* __restrict__ qkv,
                                                                 const float* __restrict__ out,
                                                                 const float* __restrict__ lse,
                                                                 const float* __restrict__ dout,
@@ -398,7 +398,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_kernel(const float* __r
     float* Ds = Ls + L;                      // [L] rowsum(dO * O)
     const int seq = blockIdx.x, h = blockIdx.y;
     const int64_t row0 = seq_row0(geo, seq);
-    for (int idx = threadIdx.x; idx < L * kHd; idx += kAttnThreads) {
+    for (int idx = threadIdx.x; idx < L * kHd; idx += (int)blockDim.x) {
         int t = idx / kHd, d = idx - t * kHd;
         const int64_t row = row0 + (int64_t)t * geo.step_stride;
         const float* r = qkv + row * 3 * E;
@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_kernel(const float* __r
         Vs[idx] = r[2 * E + h * kHd + d];
         dOs[idx] = dout[row * E + h * kHd + d];
     }
-    for (int t = threadIdx.x; t < L; t += kAttnThreads) {
+    for (int t = threadIdx.x; t < L; t += (int)blockDim.x) {
         const int64_t row = row0 + (int64_t)t * geo.step_stride;
         float dsum = 0.f;
 #pragma unroll
@@ -417,7 +417,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_kernel(const float* __r
     }
     __syncthreads();
     // pass A: one query per thread -> dQ
-    for (int i = threadIdx.x; i < L; i += kAttnThreads) {
+    for (int i = threadIdx.x; i < L; i += (int)blockDim.x) {
         float q[kHd], go[kHd], dq[kHd];
 #pragma unroll
         for (int d = 0; d < kHd; ++d) { q[d] = Qs[i * kHd + d]; go[d] = dOs[i * kHd + d]; dq[d] = 0.f; }
@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_bwd_kernel(const float* __r
         for (int d = 0; d < kHd; ++d) dqkv[row * 3 * E + h * kHd + d] = dq[d] * scale;
     }
     // pass B: one key per thread -> dK, dV
-    for (int t = threadIdx.x; t < L; t += kAttnThreads) {
+    for (int t = threadIdx.x; t < L; t += (int)blockDim.x) {
         float k[kHd], v[kHd], dk[kHd], dv[kHd];
 #pragma unroll
         for (int d = 0; d < kHd; ++d) { k[d] = Ks[t * kHd + d]; v[d] = Vs[t * kHd + d]; dk[d] = dv[d] = 0.f; }
@@ -464,6 +464,11 @@ __global__ void act_bwd_kernel(const float* __restrict__ y, const float* __restr
                                int64_t n, int act, float slope) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dpre[i] = dy[i] * act_grad_from_out(y[i], act, slope);
+}
+
+int attn_threads(int64_t L) {
+    int64_t t = (L + 31) / 32 * 32;
+    return (int)(t < 32 ? 32 : (t > kAttnMaxThreads ? kAttnMaxThreads : t));
 }
 
 bool geom_ok(SeqGeom& g, int64_t nseq, int64_t L, int64_t inner, int64_t outer_stride, int64_t inner_stride,
@@ -549,7 +554,7 @@ LCT_API int lct_attn_fwd(const float* qkv, float* out, float* lse, int64_t heads
         if (e != cudaSuccess) return (int)e;
     }
     dim3 grid((unsigned)nseq, (unsigned)heads);
-    attn_fwd_kernel<<<grid, kAttnThreads, smem, st>>>(qkv, out, lse, g, (int)heads, 1.f / sqrtf((float)kHd));
+    attn_fwd_kernel<<<grid, attn_threads(L), smem, st>>>(qkv, out, lse, g, (int)heads, 1.f / sqrtf((float)kHd));
     LCT_RETURN_IF_LAUNCH_FAILED();
     return 0;
 }
@@ -568,7 +573,7 @@ LCT_API int lct_attn_bwd(const float* qkv, const float* out, const float* lse, c
         if (e != cudaSuccess) return (int)e;
     }
     dim3 grid((unsigned)nseq, (unsigned)heads);
-    attn_bwd_kernel<<<grid, kAttnThreads, smem, st>>>(qkv, out, lse, dout, dqkv, g, (int)heads,
+    attn_bwd_kernel<<<grid, attn_threads(L), smem, st>>>(qkv, out, lse, dout, dqkv, g, (int)heads,
                                                       1.f / sqrtf((float)kHd));
     LCT_RETURN_IF_LAUNCH_FAILED();
     return 0;

@@ -12,6 +12,7 @@ from typing import Dict, Optional
 import torch
 
 import losses as L
+from models.discriminators import run_discriminators
 from . import config
 
 
@@ -47,17 +48,15 @@ def _phase_d(M, noisy, clean, args: StepArgs, st: dict) -> None:
     if args.reuse_enhancer_forward and noisy.is_cuda:
         g_opt.zero_grad(set_to_none=True)
         cur = torch.cuda.current_stream()
-        side = config.side_streams(9, noisy.device)[8]
+        side = config.side_streams(17, noisy.device)[16]
         side.wait_stream(cur)
         with torch.cuda.stream(side):                   # generator forward (with grad), overlapped with D(clean)
             st["enhanced"], st["mask_c"] = enhancer(noisy)
         st["irm_c"] = tf_features(noisy, clean)["irm_c"]
-        mpd_real, _ = mpd(clean)
-        msd_real, _ = msd(clean)
+        (mpd_real, _, msd_real, _), = run_discriminators(mpd, msd, [clean])          # all 8 chains at once
         cur.wait_stream(side)
         enhanced_for_d = st["enhanced"].detach()
-        mpd_fake, _ = mpd(enhanced_for_d)
-        msd_fake, _ = msd(enhanced_for_d)
+        (mpd_fake, _, msd_fake, _), = run_discriminators(mpd, msd, [enhanced_for_d])
     else:
         st["irm_c"] = tf_features(noisy, clean)["irm_c"]
         with torch.no_grad():
@@ -81,14 +80,22 @@ def _phase_g(M, noisy, clean, args: StepArgs, st: dict) -> None:
     else:
         g_opt.zero_grad(set_to_none=True)
         enhanced, mask_c = enhancer(noisy)
-    with torch.no_grad():                  # real feature maps first: independent of the generator's output
-        _, mpd_real_f = mpd(clean)
-        _, msd_real_f = msd(clean)
-    mr_loss, _ = mrstft_loss(enhanced, clean)
-    irm_al, pred_al = _align_tf_targets(st["irm_c"], mask_c[:, 0])
-    m_loss = L.mask_mse_loss(pred_al, irm_al)
-    mpd_fake_g, mpd_fake_f = mpd(enhanced)
-    msd_fake_g, msd_fake_f = msd(enhanced)
+    if args.reuse_enhancer_forward and noisy.is_cuda:
+        # real feature maps (no grad) and the generator's fake pass are independent: 16 chains at once
+        (_, mpd_real_f, _, msd_real_f), (mpd_fake_g, mpd_fake_f, msd_fake_g, msd_fake_f) = \
+            run_discriminators(mpd, msd, [clean, enhanced], no_grad=[True, False])
+        mr_loss, _ = mrstft_loss(enhanced, clean)
+        irm_al, pred_al = _align_tf_targets(st["irm_c"], mask_c[:, 0])
+        m_loss = L.mask_mse_loss(pred_al, irm_al)
+    else:
+        mr_loss, _ = mrstft_loss(enhanced, clean)
+        irm_al, pred_al = _align_tf_targets(st["irm_c"], mask_c[:, 0])
+        m_loss = L.mask_mse_loss(pred_al, irm_al)
+        mpd_fake_g, mpd_fake_f = mpd(enhanced)
+        msd_fake_g, msd_fake_f = msd(enhanced)
+        with torch.no_grad():
+            _, mpd_real_f = mpd(clean)
+            _, msd_real_f = msd(clean)
     adv_loss = L.generator_adv_loss(L._flatten_logits_lists(mpd_fake_g, msd_fake_g), args.gan_loss)
     fm_loss = L.feature_matching_loss(mpd_real_f + msd_real_f, mpd_fake_f + msd_fake_f)
     g_loss = mr_loss + args.lambda_mask * m_loss + args.lambda_adv * (adv_loss + args.lambda_fm * fm_loss)

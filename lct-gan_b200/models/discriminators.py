@@ -21,20 +21,69 @@ from lctgan import functional as LF
 from lctgan.disc_impl import conv_stack
 
 
-def _run_concurrently(discs, inputs):
-    """Evaluate discs[i](inputs[i]) for all i, each on its own CUDA stream (fork/join around the caller's stream)."""
+def _run_concurrently(discs, inputs, no_grad=None, first_stream=0):
+    """Evaluate discs[i](inputs[i]) for all i, each on its own CUDA stream (fork/join around the caller's stream).
+    no_grad[i] evaluates that call under torch.no_grad()."""
     x0 = inputs[0]
+    flags = no_grad if no_grad is not None else [False] * len(discs)
+
+    def call(d, x, ng):
+        if ng:
+            with torch.no_grad():
+                return d(x)
+        return d(x)
+
     if not (_cfg.concurrent_discriminators and x0.is_cuda and len(discs) > 1):
-        return [d(x) for d, x in zip(discs, inputs)]
+        return [call(d, x, ng) for d, x, ng in zip(discs, inputs, flags)]
     cur = torch.cuda.current_stream(x0.device)
-    streams = _cfg.side_streams(len(discs), x0.device)
+    streams = _cfg.side_streams(first_stream + len(discs), x0.device)[first_stream:]
     out = [None] * len(discs)
-    for i, (d, x, s) in enumerate(zip(discs, inputs, streams)):
+    for i, (d, x, s, ng) in enumerate(zip(discs, inputs, streams, flags)):
         s.wait_stream(cur)
         with torch.cuda.stream(s):
-            out[i] = d(x)
+            out[i] = call(d, x, ng)
     for s in streams:
         cur.wait_stream(s)
+    return out
+
+
+def _msd_inputs(msd, x):
+    if x.dim() == 2:
+        x = x.unsqueeze(1)
+    B, C, T = x.shape
+    x_scale = x.reshape(B, T) if C == 1 else x
+    inputs = []
+    for i in range(len(msd.discriminators)):
+        inputs.append(x_scale if x_scale.dim() == 3 else x_scale.unsqueeze(1))
+        if i + 1 < len(msd.discriminators):   # the reference pools once more and discards the result
+            x_scale = LF.AvgPool4Fn.apply(x_scale)
+    return inputs
+
+
+def run_discriminators(mpd, msd, waves, no_grad=None):
+    """Scheduling helper (not part of the reference API): evaluate `mpd(w)` and `msd(w)` for every waveform w in
+    `waves` with ALL 8 * len(waves) sub-discriminators forked at once instead of one module call after the other.
+    Returns [(mpd_logits, mpd_fmaps, msd_logits, msd_fmaps) per waveform]; values are identical to the module calls."""
+    flags = no_grad if no_grad is not None else [False] * len(waves)
+    discs, inputs, ng = [], [], []
+    for w, f in zip(waves, flags):
+        discs += list(mpd.discriminators)
+        inputs += [w] * len(mpd.discriminators)
+        ng += [f] * len(mpd.discriminators)
+        if f:
+            with torch.no_grad():
+                mi = _msd_inputs(msd, w)
+        else:
+            mi = _msd_inputs(msd, w)
+        discs += list(msd.discriminators)
+        inputs += mi
+        ng += [f] * len(msd.discriminators)
+    res = _run_concurrently(discs, inputs, ng)
+    out, per = [], len(mpd.discriminators) + len(msd.discriminators)
+    for k in range(len(waves)):
+        r = res[k * per:(k + 1) * per]
+        np_ = len(mpd.discriminators)
+        out.append(([t[0] for t in r[:np_]], [t[1] for t in r[:np_]], [t[0] for t in r[np_:]], [t[1] for t in r[np_:]]))
     return out
 
 # (out_channels, kernel, stride, groups)
@@ -148,14 +197,5 @@ class MultiScaleDiscriminator(nn.Module):
         self.avg_pool = nn.AvgPool1d(kernel_size=4, stride=2, padding=2, count_include_pad=False)
 
     def forward(self, x: torch.Tensor) -> Tuple[List[torch.Tensor], List[List[torch.Tensor]]]:
-        if x.dim() == 2:
-            x = x.unsqueeze(1)
-        B, C, T = x.shape
-        x_scale = x.reshape(B, T) if C == 1 else x
-        inputs = []
-        for i in range(len(self.discriminators)):
-            inputs.append(x_scale if x_scale.dim() == 3 else x_scale.unsqueeze(1))
-            if i + 1 < len(self.discriminators):   # the reference pools once more and discards the result
-                x_scale = LF.AvgPool4Fn.apply(x_scale)
-        res = _run_concurrently(list(self.discriminators), inputs)
+        res = _run_concurrently(list(self.discriminators), _msd_inputs(self, x))
         return [r[0] for r in res], [r[1] for r in res]
