@@ -133,7 +133,137 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// TF32 tensor-core version (mma.sync m16n8k8, fp32 accumulate) of the same GEMM: 128 x 64 x 16 CTA tile, four warps
+// of 32 x 64, operands rounded to TF32 while they are staged into shared memory.  Used in tensor-core mode
+// (lct_set_tensor_core_gemm); the SIMT kernel above stays for exact-fp32 mode.
+// ------------------------------------------------------------------------------------------------
+constexpr int MB_M = 128, MB_N = 64, MB_K = 16, MB_THREADS = 128;
+constexpr int MB_AS = MB_K + 4;     // A tile row stride:  (g * 20 + t) mod 32 distinct for g < 8, t < 4
+constexpr int MB_BS = MB_N + 8;     // B tile row stride:  (t * 72 + g) mod 32 distinct
+
+__device__ __forceinline__ uint32_t to_tf32(float v) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+    return u;
+}
+
+__global__ void __launch_bounds__(MB_THREADS, 4) gemm_mma_kernel(const GemmParams p) {
+    __shared__ __align__(16) uint32_t As[MB_M * MB_AS];
+    __shared__ __align__(16) uint32_t Bs[MB_K * MB_BS];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int gq = lane >> 2, tq = lane & 3;
+    const int z = blockIdx.z;
+    const int batch = z / p.ksplit, ks = z - batch * p.ksplit;
+    const float* A = p.A + (int64_t)(batch / p.a_div) * p.sA;
+    const float* B = p.B + (int64_t)(batch / p.b_div) * p.sB;
+    const int m0 = blockIdx.x * MB_M, n0 = blockIdx.y * MB_N;
+    const int kchunk = ((p.K + p.ksplit - 1) / p.ksplit + MB_K - 1) / MB_K * MB_K;
+    const int k_begin = ks * kchunk;
+    const int k_end = min(p.K, k_begin + kchunk);
+    const int ntiles = min(MB_N / 8, (p.N - n0 + 7) / 8);      // n-tiles that hold real columns (CTA uniform)
+
+    float acc[2][MB_N / 8][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < MB_N / 8; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
+
+    for (int k0 = k_begin; k0 < k_end; k0 += MB_K) {
+#pragma unroll
+        for (int i = 0; i < (MB_M * MB_K) / MB_THREADS; ++i) {
+            const int e = tid + i * MB_THREADS;
+            int m, k;
+            if (p.ta) { m = e % MB_M; k = e / MB_M; } else { k = e % MB_K; m = e / MB_K; }
+            const int gm = m0 + m, gk = k0 + k;
+            float v = 0.f;
+            if (gm < p.M && gk < k_end) v = p.ta ? A[(int64_t)gk * p.lda + gm] : A[(int64_t)gm * p.lda + gk];
+            As[m * MB_AS + k] = to_tf32(v);
+        }
+#pragma unroll
+        for (int i = 0; i < (MB_N * MB_K) / MB_THREADS; ++i) {
+            const int e = tid + i * MB_THREADS;
+            int n, k;
+            if (p.tb) { n = e % MB_N; k = e / MB_N; } else { k = e % MB_K; n = e / MB_K; }
+            const int gn = n0 + n, gk = k0 + k;
+            float v = 0.f;
+            if (gn < p.N && gk < k_end) v = p.tb ? B[(int64_t)gk * p.ldb + gn] : B[(int64_t)gn * p.ldb + gk];
+            Bs[k * MB_BS + n] = to_tf32(v);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < MB_K; kk += 8) {
+            uint32_t a[2][4];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                const uint32_t* ar = As + (warp * 32 + mt * 16 + gq) * MB_AS + kk + tq;
+                a[mt][0] = ar[0];
+                a[mt][1] = ar[8 * MB_AS];
+                a[mt][2] = ar[4];
+                a[mt][3] = ar[8 * MB_AS + 4];
+            }
+#pragma unroll
+            for (int nt = 0; nt < MB_N / 8; ++nt) {
+                if (nt < ntiles) {
+                    const uint32_t b0 = Bs[(kk + tq) * MB_BS + nt * 8 + gq];
+                    const uint32_t b1 = Bs[(kk + tq + 4) * MB_BS + nt * 8 + gq];
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) {
+                        asm volatile(
+                            "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+                            "{%0,%1,%2,%3};"
+                            : "+f"(acc[mt][nt][0]), "+f"(acc[mt][nt][1]), "+f"(acc[mt][nt][2]), "+f"(acc[mt][nt][3])
+                            : "r"(a[mt][0]), "r"(a[mt][1]), "r"(a[mt][2]), "r"(a[mt][3]), "r"(b0), "r"(b1));
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    float* C = p.C + (int64_t)batch * p.sC;
+    const float* bias = p.bias ? p.bias + (int64_t)batch * p.sBias : nullptr;
+    const float* res = p.res ? p.res + (int64_t)batch * p.sRes : nullptr;
+    float* out2 = p.out2 ? p.out2 + (int64_t)batch * p.sOut2 : nullptr;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int gm = m0 + warp * 32 + mt * 16 + gq + 8 * h;
+            if (gm >= p.M) continue;
+#pragma unroll
+            for (int nt = 0; nt < MB_N / 8; ++nt)
+#pragma unroll
+                for (int c2 = 0; c2 < 2; ++c2) {
+                    const int gn = n0 + nt * 8 + 2 * tq + c2;
+                    if (gn >= p.N) continue;
+                    float v = acc[mt][nt][2 * h + c2] * p.alpha;
+                    float* c = C + (int64_t)gm * p.ldc + gn;
+                    if (p.ksplit > 1) {
+                        atomicAdd(c, v);
+                    } else {
+                        if (bias) v += bias[gn];
+                        v = apply_act(v, p.act, p.slope);
+                        if (p.accumulate) v += *c;
+                        *c = v;
+                        if (out2) out2[(int64_t)gm * p.ldo + gn] = v + (res ? res[(int64_t)gm * p.ldr + gn] : 0.f);
+                    }
+                }
+        }
+}
+
+int g_gemm_tensor_cores = 1;
+
 }  // namespace
+
+// 0: fp32 SIMT GEMM; 1 (default): TF32 mma.sync GEMM
+LCT_API int lct_set_tensor_core_gemm(int on) {
+    g_gemm_tensor_cores = on ? 1 : 0;
+    return 0;
+}
 
 // C[M,N] = act(alpha * op(A) op(B) + bias)  (+ C if accumulate);  out2 = C + res  (optional).
 // Batched over blockIdx.z: A += (z / a_div) * sA, B += (z / b_div) * sB, C/bias/res/out2 += z * s*.
@@ -154,6 +284,12 @@ LCT_API int lct_gemm(const float* A, const float* B, float* C, const float* bias
     p.ta = ta; p.tb = tb; p.act = act; p.slope = slope; p.alpha = alpha; p.accumulate = accumulate;
     p.ksplit = (int)ksplit; p.nbatch = (int)nbatch; p.a_div = (int)a_div; p.b_div = (int)b_div;
     p.sA = sA; p.sB = sB; p.sC = sC; p.sBias = sBias; p.sRes = sRes; p.sOut2 = sOut2;
+    if (g_gemm_tensor_cores) {
+        dim3 grid((unsigned)ceil_div64(M, MB_M), (unsigned)ceil_div64(N, MB_N), (unsigned)(nbatch * ksplit));
+        gemm_mma_kernel<<<grid, MB_THREADS, 0, st>>>(p);
+        LCT_RETURN_IF_LAUNCH_FAILED();
+        return 0;
+    }
     dim3 grid((unsigned)ceil_div64(M, BM), (unsigned)ceil_div64(N, BN), (unsigned)(nbatch * ksplit));
     gemm_kernel<<<grid, kThreads, 0, st>>>(p);
     LCT_RETURN_IF_LAUNCH_FAILED();
