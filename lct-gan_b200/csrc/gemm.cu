@@ -255,11 +255,11 @@ __global__ void __launch_bounds__(MB_THREADS, 4) gemm_mma_kernel(const GemmParam
         }
 }
 
-int g_gemm_tensor_cores = 1;
+int g_gemm_tensor_cores = 0;   // measured slower than the SIMT kernel on the generator's shapes (tools/bench_gemm.py): opt-in
 
 }  // namespace
 
-// 0: fp32 SIMT GEMM; 1 (default): TF32 mma.sync GEMM
+// 0 (default): fp32 SIMT GEMM; 1: TF32 mma.sync GEMM (experimental: slower on the generator's skinny shapes)
 LCT_API int lct_set_tensor_core_gemm(int on) {
     g_gemm_tensor_cores = on ? 1 : 0;
     return 0;

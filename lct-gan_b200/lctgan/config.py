@@ -12,8 +12,6 @@ def set_precision(mode: str) -> None:
     if mode not in ("bf16", "fp32"):
         raise ValueError(f"unknown precision mode {mode!r}")
     dense_tensor_cores = (mode == "bf16")
-    from ._lib import call_ret
-    call_ret("lct_set_tensor_core_gemm", 1 if dense_tensor_cores else 0)
 
 
 #: Run the independent sub-discriminators (5 periods, 3 scales) on parallel CUDA streams (forked from and joined
