@@ -143,27 +143,14 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------------
 # roofline of the dominant kernel, timed live
 # --------------------------------------------------------------------------------------------------
-def measure_roofline(dev, peaks):
-    """Dominant kernel of the step by FLOPs: the dense 1024->1024, k=5 convolution of the scale discriminators
-    (MSD convs.5, the one layer above the ridge: SURVEY.md section 8a D3) on tcgen05.  Timed alone with CUDA
-    events on the launching stream, L2 flushed between launches; algorithmic FLOPs = 2*B*L*Cin*Cout*K."""
+def _time_kernel(run, flush, iters=10):
+    """Average CUDA-event duration (ms) of one launch, L2 flushed (256 MB write) before every timed launch."""
     import torch
-    from lctgan import ops
-    B, L, C, K = BATCH, 125, 1024, 5
-    g = torch.Generator(device="cpu").manual_seed(0)
-    x = torch.randn(B, C, L, 1, generator=g).to(dev)
-    w = (torch.randn(C, C, K, generator=g) / (C * K) ** 0.5).to(dev)
-    bias = torch.zeros(C, device=dev)
-    wt, _ = ops.stage_dense_weights(w, want_wd=False)
-    xp = ops.stage_nlc_bf16(x, K // 2)
-    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
-    flops = 2.0 * B * L * C * C * K
-    run = lambda: ops.dense_conv(xp, wt, B, L, C, C, K, bias=bias, act=ops.ACT_LRELU)
     for _ in range(3):
         run()
     torch.cuda.synchronize()
     times = []
-    for _ in range(10):
+    for _ in range(iters):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -171,12 +158,84 @@ def measure_roofline(dev, peaks):
         e1.record()
         torch.cuda.synchronize()
         times.append(e0.elapsed_time(e1))
-    ms = sum(times) / len(times)
-    achieved = flops / (ms * 1e-3) / 1e12
-    return {"kernel": "dense_kernel<64,6,conv> (MSD convs.5 forward: 1024->1024, k=5, B=8, L=125, tcgen05 bf16)",
-            "bound": "tensor", "achieved": achieved, "peak": peaks["tensor"], "unit": "TFLOP/s",
-            "frac": achieved / peaks["tensor"], "traffic": None, "ms_per_launch": ms,
-            "peak_source": peaks["src"] + " (burst: kernel timed alone)"}
+    return sum(times) / len(times)
+
+
+def measure_roofline(dev, peaks):
+    """Rooflines of the two kernels that matter, each timed alone with CUDA events on the launching stream:
+
+    roofline        - the kernel family that dominates the step's GPU time (profiles/): the grouped discriminator
+                      convolutions on TF32 mma.sync, here the heaviest instance, the data gradient of MSD convs.1
+                      (16 -> 64 channels, k 41, stride 4, 4 groups, B = 8, L = 32000).  HBM bound (AI ~ 40 flop/B):
+                      algorithmic bytes = dY + FM gradient + saved activation read, dX written = 4 x 16.4 MB.
+    roofline_tensor - the one contraction above the ridge, MSD convs.5 (1024 -> 1024, k 5) on tcgen05:
+                      algorithmic FLOPs = 2 B L Cin Cout K = 10.49 GFLOP.
+    """
+    import torch
+    from lctgan import ops
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    g = torch.Generator(device="cpu").manual_seed(0)
+    # ---- grouped conv dgrad (MSD convs.1)
+    B, Cin, Cout, K, S, G, L = BATCH, 16, 64, 41, 4, 4, 32000
+    Lout = (L + 2 * (K // 2) - K) // S + 1
+    dy = torch.randn(B, Cout, Lout, 1, generator=g).to(dev)
+    w = (torch.randn(Cout, Cin // G, K, generator=g) / 13.0).to(dev)
+    xact = torch.randn(B, Cin, L, 1, generator=g).to(dev)
+    gextra = torch.randn(B, Cin, L, 1, generator=g).to(dev)
+    ms = _time_kernel(lambda: ops.conv1d_dgrad(dy, w, (B, Cin, L, 1), G, S, K // 2, gextra=gextra, xact=xact,
+                                                act=ops.ACT_LRELU), flush)
+    nbytes = 4.0 * (dy.numel() + 3 * xact.numel())
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    roof = {"kernel": "conv_mma_kernel<dgrad> (MSD convs.1 data gradient: 64->16 ch, k=41, s=4, groups=4, B=8, L=32000, "
+                      "TF32 mma.sync + fused FM-gradient/LeakyReLU' epilogue)",
+            "bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
+            "traffic": 66.9e6, "traffic_note": "dram read+write per launch from ncu --set full (profiles/), warm L2",
+            "algorithmic_bytes": nbytes, "ms_per_launch": ms, "peak_source": peaks["src"] + " (STREAM-style copy)"}
+    # ---- dense conv forward on tcgen05 (MSD convs.5)
+    B, L, C, K = BATCH, 125, 1024, 5
+    x = torch.randn(B, C, L, 1, generator=g).to(dev)
+    w = (torch.randn(C, C, K, generator=g) / (C * K) ** 0.5).to(dev)
+    bias = torch.zeros(C, device=dev)
+    wt, _ = ops.stage_dense_weights(w, want_wd=False)
+    xp = ops.stage_nlc_bf16(x, K // 2)
+    flops = 2.0 * B * L * C * C * K
+    ms = _time_kernel(lambda: ops.dense_conv(xp, wt, B, L, C, C, K, bias=bias, act=ops.ACT_LRELU), flush)
+    tf = flops / (ms * 1e-3) / 1e12
+    roof_t = {"kernel": "dense_kernel<64,6,conv> (MSD convs.5 forward: 1024->1024, k=5, B=8, L=125, tcgen05 bf16)",
+              "bound": "tensor", "achieved": tf, "peak": peaks["tensor"], "unit": "TFLOP/s",
+              "frac": tf / peaks["tensor"], "traffic": 12.6e6, "ms_per_launch": ms,
+              "peak_source": peaks["src"] + " (burst: kernel timed alone)"}
+    return roof, roof_t
+
+
+def measure_enhance_rtf(dev):
+    """BASELINE.json configs[1]: full-utterance enhancement, synthetic 16 kHz utterances of 1-10 s zero-padded to the
+    batch maximum like datasets.py:210-221, batch 1 and 16, eval + no_grad; real-time factor = (enhancer wall time
+    incl. the D2H copy of the waveforms) / (seconds of audio in the batch)."""
+    import torch
+    from lctgan.training import build_models
+    enh = build_models(dev, gan_seed=42)[0].eval()
+    gl = torch.Generator().manual_seed(7)
+    out = {}
+    for bs in (1, 16):
+        lens = torch.randint(16000, 160001, (bs,), generator=gl)
+        T = int(lens.max())
+        x = torch.zeros(bs, T)
+        for i, n in enumerate(lens.tolist()):
+            x[i, :n] = torch.randn(n, generator=gl) * 0.1
+        xh = x.pin_memory()
+        with torch.no_grad():
+            for _ in range(2):
+                enh(xh.to(dev, non_blocking=True))[0].cpu()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            reps = 5
+            for _ in range(reps):
+                y = enh(xh.to(dev, non_blocking=True))[0].cpu()
+            dt = (time.perf_counter() - t0) / reps
+        out[f"batch{bs}"] = {"rtf": dt / (float(lens.sum()) / 16000.0), "ms": dt * 1e3,
+                             "audio_s": float(lens.sum()) / 16000.0, "padded_to_s": T / 16000.0}
+    return out
 
 
 def main():
@@ -305,7 +364,8 @@ def main():
             dist.destroy_process_group()
         return
     peaks = _peaks()
-    roof = None if args.no_roofline else measure_roofline(dev, peaks)
+    roof, roof_t = (None, None) if args.no_roofline else measure_roofline(dev, peaks)
+    rtf = None if args.no_roofline else measure_enhance_rtf(dev)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         sps, ms, b, cores = cpu_reference_steps(steps=1, warmup=1, budget_s=30.0)
@@ -323,6 +383,8 @@ def main():
                 "h2d_bytes_per_step": int(noisy_h.numel() * 4 * 2), "d2h_bytes_per_step": int(res_h.numel() * 4)},
         "gpu_launches": launches,
         "roofline": roof,
+        "roofline_tensor": roof_t,
+        "enhance_rtf": rtf,
         "cpu_baseline": cpu,
         "losses_last_step": losses,
     }

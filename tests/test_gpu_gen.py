@@ -285,3 +285,22 @@ def test_generator_and_enhancer(dev, T):
         enh.gen(mag.to(dev)[:, 0])
     with pytest.raises(ValueError):
         enh(noisy.to(dev)[0])
+
+
+@pytest.mark.parametrize("B,T", [(1, 160000), (2, 16000), (3, 40123)])
+def test_enhancer_full_utterance_inference(dev, B, T):
+    """infer.py:147 path (BASELINE configs[1]): eval + no_grad enhancement of 1 - 10 s utterances (time attention
+    over up to 629 frames) against the CPU oracle."""
+    from models.generator import LCTEnhancer, LCTGeneratorConfig
+    O = oracle()
+    torch.manual_seed(3)
+    enh = LCTEnhancer(LCTGeneratorConfig(), c=0.3).eval()
+    P = cpu_params(enh)
+    enh = enh.to(dev)
+    noisy, _ = O.synthetic_batch(B, T, seed=T)
+    with torch.no_grad():
+        er, mr = O.enhancer_forward(P, noisy, aten_gru=True)
+        eg, mg = enh(noisy.to(dev))
+    assert eg.shape == (B, T) and mg.shape == mr.shape
+    assert rel_err(eg, er) < 5e-5
+    assert rel_err(mg, mr) < 5e-5
