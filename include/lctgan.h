@@ -92,7 +92,9 @@ LCT_API int lct_avgpool4_bwd(const float* gy, float* gx, int64_t B, int64_t L, c
 LCT_API int lct_weight_norm_fwd(const float* g, const float* v, float* w, float* norm, int64_t Cout, int64_t row, cudaStream_t stream);
 LCT_API int lct_weight_norm_bwd(const float* g, const float* v, const float* dw, float* dg, float* dv, int64_t Cout, int64_t row, cudaStream_t stream);
 /* The same for up to 16 layers in one launch (g/v/w/dw/dg/dv: HOST arrays of device pointers; rows = Cout, rowlen per layer). */
-LCT_API int lct_mt_weight_norm_fwd(const void* const* g, const void* const* v, void* const* w, const int64_t* rows, const int64_t* rowlen, int64_t nseg, cudaStream_t stream);
+/* img_f/img_d (optional HOST arrays, NULL entries allowed): also write the zero-padded TF32 weight images the tensor-core conv
+ * kernels stage (caller zero-fills them); geo: HOST int64[nseg][8] = {Cout/G, K, S, ceil(K/S), KKpad_f, NS_f, KKpad_d, NS_d}. */
+LCT_API int lct_mt_weight_norm_fwd(const void* const* g, const void* const* v, void* const* w, const int64_t* rows, const int64_t* rowlen, void* const* img_f, void* const* img_d, const int64_t* geo, int64_t nseg, cudaStream_t stream);
 LCT_API int lct_mt_weight_norm_bwd(const void* const* g, const void* const* v, const void* const* dw, void* const* dg, void* const* dv, const int64_t* rows, const int64_t* rowlen, int64_t nseg, cudaStream_t stream);
 /* Conv2d(k=(K,1), stride=(S,1), pad=(pad,0), groups=G) / Conv1d(K,S,pad,G) + bias + activation
  * (discriminators.py:93-98, :215-220).  x [B,Cin,Lin,P] -> y [B,Cout,Lout,P], w [Cout,Cin/G,K]. */
@@ -108,8 +110,9 @@ LCT_API int lct_conv1d_wgrad(const float* x, const float* dy, float* dw, float* 
  * whether a layer shape is covered (groups with <= 16 in / <= 32 out channels, stride 1/3/4, Cin/G * K <= 168). */
 LCT_API int lct_conv_mma_tune(int ctas_per_sm, int force_mtw);   /* tuning: CTAs per SM of the persistent grids (default 3); force 2 or 4 m-tiles per warp (0 = auto) */
 LCT_API int lct_conv_mma_supported(int64_t Cin, int64_t Cout, int64_t G, int64_t K, int64_t S, int64_t P);
-LCT_API int lct_conv_mma_fwd(const float* x, const float* w, const float* bias, float* y, int64_t B, int64_t Cin, int64_t Cout, int64_t G, int64_t K, int64_t S, int64_t pad, int64_t Lin, int64_t P, int act, float slope, cudaStream_t stream);
-LCT_API int lct_conv_mma_dgrad(const float* dy, const float* w, float* dx, const float* gextra, const float* xact, int64_t B, int64_t Cin, int64_t Cout, int64_t G, int64_t K, int64_t S, int64_t pad, int64_t Lin, int64_t P, int act, float slope, cudaStream_t stream);
+LCT_API int lct_conv_mma_image_geometry(int64_t Cin, int64_t Cout, int64_t G, int64_t K, int64_t S, int mode, int64_t* out);   /* out (HOST) = {KKpad, NS} of the staged weight image; mode 0 fwd, 1 dgrad */
+LCT_API int lct_conv_mma_fwd(const float* x, const float* w, const float* wimg, const float* bias, float* y, int64_t B, int64_t Cin, int64_t Cout, int64_t G, int64_t K, int64_t S, int64_t pad, int64_t Lin, int64_t P, int act, float slope, cudaStream_t stream);
+LCT_API int lct_conv_mma_dgrad(const float* dy, const float* w, const float* wimg, float* dx, const float* gextra, const float* xact, int64_t B, int64_t Cin, int64_t Cout, int64_t G, int64_t K, int64_t S, int64_t pad, int64_t Lin, int64_t P, int act, float slope, cudaStream_t stream);
 LCT_API int lct_conv_mma_wgrad(const float* x, const float* dy, float* dw, float* db, int64_t B, int64_t Cin, int64_t Cout, int64_t G, int64_t K, int64_t S, int64_t pad, int64_t Lin, int64_t P, cudaStream_t stream);
 
 /* conv_post (C -> 1 channel, odd K <= 8, stride 1, pad K/2; discriminators.py:59-66, :188-196): channel-reduction kernels.

@@ -519,8 +519,19 @@ struct WnSegs {
     float* dg[kMaxWn];
     int row0[kMaxWn + 1];  // prefix sum of rows (out channels)
     int rowlen[kMaxWn];
+    // optional staged weight images for the tensor-core conv kernels (conv_mma.cu); geo = {Cog, K, S, Tmax,
+    // KKpad_f, NS_f, KKpad_d, NS_d}
+    float* img_f[kMaxWn];
+    float* img_d[kMaxWn];
+    int geo[kMaxWn][8];
     int nseg;
 };
+
+__device__ __forceinline__ float round_tf32(float v) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+    return __uint_as_float(u);
+}
 
 template <bool BWD>
 __global__ void __launch_bounds__(128) mt_wnorm_kernel(const WnSegs S) {
@@ -550,12 +561,30 @@ __global__ void __launch_bounds__(128) mt_wnorm_kernel(const WnSegs S) {
         for (int i = threadIdx.x; i < row; i += blockDim.x) a += vr[i] * vr[i];
         const float sc = S.g[seg][co] / sqrtf(block_sum(a, red));
         float* w = S.w[seg] + (size_t)co * row;
-        for (int i = threadIdx.x; i < row; i += blockDim.x) w[i] = vr[i] * sc;
+        float* imf = S.img_f[seg];
+        float* imd = S.img_d[seg];
+        const int Cog = S.geo[seg][0], K = S.geo[seg][1], St = S.geo[seg][2], Tmax = S.geo[seg][3];
+        const int KKf = S.geo[seg][4], NSf = S.geo[seg][5], KKd = S.geo[seg][6], NSd = S.geo[seg][7];
+        const int g = imf ? co / Cog : 0, col = imf ? co - g * Cog : 0;
+        for (int i = threadIdx.x; i < row; i += blockDim.x) {
+            const float v = vr[i] * sc;
+            w[i] = v;
+            if (imf) {
+                // forward image  [g][kk = ci*K + k][n = co within group]
+                const float q = round_tf32(v);
+                imf[((size_t)g * KKf + i) * NSf + col] = q;
+                // data-gradient image  [g][kk = co*Tmax + t][n = ci*S + r],  k = r + S*t
+                const int ci = i / K, k = i - ci * K;
+                const int t = k / St, r = k - t * St;
+                imd[((size_t)g * KKd + col * Tmax + t) * NSd + ci * St + r] = q;
+            }
+        }
     }
 }
 
 int fill_wn(WnSegs& S, const void* const* g, const void* const* v, const void* const* dw, void* const* w,
             void* const* dg, const int64_t* rows, const int64_t* rowlen, int64_t nseg, bool bwd) {
+    for (int i = 0; i < kMaxWn; ++i) S.img_f[i] = S.img_d[i] = nullptr;
     if (!g || !v || !w || !rows || !rowlen || nseg <= 0 || nseg > kMaxWn || (bwd && (!dw || !dg))) return LCT_EINVAL;
     int tot = 0;
     for (int i = 0; i < nseg; ++i) {
@@ -574,10 +603,19 @@ int fill_wn(WnSegs& S, const void* const* g, const void* const* v, const void* c
 
 // weight norm of up to 16 layers in one launch; g/v/w: HOST arrays of device pointers, rows/rowlen: HOST arrays
 LCT_API int lct_mt_weight_norm_fwd(const void* const* g, const void* const* v, void* const* w, const int64_t* rows,
-                                   const int64_t* rowlen, int64_t nseg, cudaStream_t st) {
+                                   const int64_t* rowlen, void* const* img_f, void* const* img_d, const int64_t* geo,
+                                   int64_t nseg, cudaStream_t st) {
     WnSegs S;
     int tot = fill_wn(S, g, v, nullptr, w, nullptr, rows, rowlen, nseg, false);
     if (tot < 0) return tot;
+    if (img_f && img_d && geo) {
+        for (int i = 0; i < nseg; ++i) {
+            S.img_f[i] = (float*)img_f[i];
+            S.img_d[i] = (float*)img_d[i];
+            if ((S.img_f[i] == nullptr) != (S.img_d[i] == nullptr)) return LCT_EINVAL;
+            for (int j = 0; j < 8; ++j) S.geo[i][j] = (int)geo[i * 8 + j];
+        }
+    }
     mt_wnorm_kernel<false><<<tot, 128, 0, st>>>(S);
     LCT_RETURN_IF_LAUNCH_FAILED();
     return 0;

@@ -32,6 +32,8 @@ enum { MODE_FWD = 0, MODE_DGRAD = 1 };
 struct MmaParams {
     const float* x;        // gathered tensor  [B][Cx][Lx][P]   (fwd: input, dgrad: dY)
     const float* w;        // conv weight      [Cout][Cin_g][K]
+    const float* wimg;     // optional: the staged image [G][KKpad][NS] (tf32-rounded, zero padded) built by the
+                           // weight-norm kernel (lct_mt_weight_norm_fwd); skips the in-kernel arrangement
     float* out;            // fwd: y [B][Cout][Lout][P];  dgrad: dx [B][Cin][Lin][P]
     const float* bias;     // fwd
     const float* gextra;   // dgrad (optional)
@@ -140,6 +142,10 @@ __global__ void __launch_bounds__(kThreads) conv_mma_kernel(const MmaParams p) {
     float* win1 = win0 + winsz;
 
     // ---- prologue: this group's weights (tf32-rounded, [kk][n]) and the gather LUT
+    if (p.wimg) {
+        const float* src = p.wimg + (size_t)g * p.KKpad * p.NS;     // 16-byte aligned: KKpad * NS is a multiple of 64
+        for (int idx = tid * 4; idx < p.KKpad * p.NS; idx += kThreads * 4) cp_async16(wsm + idx, src + idx);
+    } else
     for (int idx = tid; idx < p.KKpad * p.Npad; idx += kThreads) {
         const int n = idx % p.Npad;
         const int kk = idx / p.Npad;
@@ -542,6 +548,19 @@ LCT_API int lct_conv_mma_tune(int ctas_per_sm, int force_mtw) {
     return 0;
 }
 
+// geometry of the staged weight images: mode 0 forward ([Cin/G*K -> pad 8] x NS), mode 1 data gradient
+// ([Cout/G*ceil(K/S) -> pad 8] x NS); out[0] = KKpad, out[1] = NS  (HOST pointer)
+LCT_API int lct_conv_mma_image_geometry(int64_t Cin, int64_t Cout, int64_t G, int64_t K, int64_t S, int mode,
+                                        int64_t* out) {
+    if (!out || G <= 0 || Cin % G || Cout % G || S < 1) return LCT_EINVAL;
+    const int64_t cig = Cin / G, cog = Cout / G, tmax = (K + S - 1) / S;
+    const int64_t kk = mode ? cog * tmax : cig * K;
+    const int64_t n = mode ? cig * S : cog;
+    out[0] = (kk + 7) & ~(int64_t)7;
+    out[1] = pick_ns((int)((n + 7) & ~(int64_t)7));
+    return 0;
+}
+
 // 1 if the tensor-core kernels cover this layer (otherwise use lct_conv1d_*)
 LCT_API int lct_conv_mma_supported(int64_t Cin, int64_t Cout, int64_t G, int64_t K, int64_t S, int64_t P) {
     if (G <= 0 || Cin % G || Cout % G) return 0;
@@ -552,14 +571,14 @@ LCT_API int lct_conv_mma_supported(int64_t Cin, int64_t Cout, int64_t G, int64_t
     return 1;
 }
 
-LCT_API int lct_conv_mma_fwd(const float* x, const float* w, const float* bias, float* y, int64_t B, int64_t Cin,
-                             int64_t Cout, int64_t G, int64_t K, int64_t S, int64_t pad, int64_t Lin, int64_t P,
-                             int act, float slope, cudaStream_t st) {
+LCT_API int lct_conv_mma_fwd(const float* x, const float* w, const float* wimg, const float* bias, float* y, int64_t B,
+                             int64_t Cin, int64_t Cout, int64_t G, int64_t K, int64_t S, int64_t pad, int64_t Lin,
+                             int64_t P, int act, float slope, cudaStream_t st) {
     if (!x || !w || !y || !shape_ok(B, Cin, Cout, G, K, S, pad, Lin, P) ||
         !lct_conv_mma_supported(Cin, Cout, G, K, S, P))
         return LCT_EINVAL;
     MmaParams p = {};
-    p.x = x; p.w = w; p.out = y; p.bias = bias; p.act = act; p.slope = slope;
+    p.x = x; p.w = w; p.wimg = wimg; p.out = y; p.bias = bias; p.act = act; p.slope = slope;
     p.B = (int)B; p.Cx = (int)Cin; p.Cxg = (int)(Cin / G); p.Lx = (int)Lin; p.P = (int)P;
     p.Co = (int)Cout; p.N = (int)(Cout / G); p.Lo = (int)((Lin + 2 * pad - K) / S + 1);
     p.K = (int)K; p.S = (int)S; p.pad = (int)pad; p.Tmax = (int)((K + S - 1) / S);
@@ -574,14 +593,14 @@ LCT_API int lct_conv_mma_fwd(const float* x, const float* w, const float* bias, 
     }
 }
 
-LCT_API int lct_conv_mma_dgrad(const float* dy, const float* w, float* dx, const float* gextra, const float* xact,
-                               int64_t B, int64_t Cin, int64_t Cout, int64_t G, int64_t K, int64_t S, int64_t pad,
-                               int64_t Lin, int64_t P, int act, float slope, cudaStream_t st) {
+LCT_API int lct_conv_mma_dgrad(const float* dy, const float* w, const float* wimg, float* dx, const float* gextra,
+                               const float* xact, int64_t B, int64_t Cin, int64_t Cout, int64_t G, int64_t K, int64_t S,
+                               int64_t pad, int64_t Lin, int64_t P, int act, float slope, cudaStream_t st) {
     if (!dy || !w || !dx || !shape_ok(B, Cin, Cout, G, K, S, pad, Lin, P) ||
         !lct_conv_mma_supported(Cin, Cout, G, K, S, P))
         return LCT_EINVAL;
     MmaParams p = {};
-    p.x = dy; p.w = w; p.out = dx; p.gextra = gextra; p.xact = xact; p.act = act; p.slope = slope;
+    p.x = dy; p.w = w; p.wimg = wimg; p.out = dx; p.gextra = gextra; p.xact = xact; p.act = act; p.slope = slope;
     const int Lout = (int)((Lin + 2 * pad - K) / S + 1);
     p.B = (int)B; p.Cx = (int)Cout; p.Cxg = (int)(Cout / G); p.Lx = Lout; p.P = (int)P;
     p.Co = (int)Cin; p.Cig = (int)(Cin / G); p.N = p.Cig * (int)S; p.Lo = (int)Lin;

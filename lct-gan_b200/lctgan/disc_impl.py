@@ -45,7 +45,7 @@ class ConvStackFn(torch.autograd.Function):
         x4 = x4.contiguous()
         gs = [params[3 * i + 1].contiguous() for i in range(n)]
         vs = [params[3 * i + 2].contiguous() for i in range(n)]
-        weights = ops.mt_weight_norm_fwd(gs, vs)
+        weights, imgs_f, imgs_d = ops.mt_weight_norm_fwd(gs, vs, specs, x4.shape[3])
         fmaps: List[torch.Tensor] = []
         h = x4
         dense: List[int] = []
@@ -59,11 +59,12 @@ class ConvStackFn(torch.autograd.Function):
                                    bias=bias, act=act, slope=LRELU_SLOPE)
                 dense.append(i)
             else:
-                h = ops.conv1d_fwd(h, w, bias, g, s, pad, act=act, slope=LRELU_SLOPE)
+                h = ops.conv1d_fwd(h, w, bias, g, s, pad, act=act, slope=LRELU_SLOPE, wimg=imgs_f[i])
             fmaps.append(h)
         ctx.specs = list(specs)
         ctx.dense = dense
         ctx.skip_param_grads = skip_param_grads
+        ctx.imgs_d = imgs_d       # (internal buffers, not outputs: safe to keep on ctx)
         ctx.save_for_backward(x4, *fmaps, *weights, *params)
         return tuple(fmaps)
 
@@ -109,9 +110,9 @@ class ConvStackFn(torch.autograd.Function):
                     ops.conv1d_wgrad(inp, dpre, weights[i].shape, g, s, pad, want_bias=True, dw=dws[i], db=dbs[i])
                 if i > 0:
                     dpre = ops.conv1d_dgrad(dpre, weights[i], inp.shape, g, s, pad, gextra=gouts[i - 1], xact=inp,
-                                            act=ops.ACT_LRELU, slope=LRELU_SLOPE)
+                                            act=ops.ACT_LRELU, slope=LRELU_SLOPE, wimg=ctx.imgs_d[i])
                 elif need_x:
-                    gx = ops.conv1d_dgrad(dpre, weights[i], inp.shape, g, s, pad)
+                    gx = ops.conv1d_dgrad(dpre, weights[i], inp.shape, g, s, pad, wimg=ctx.imgs_d[i])
             elif i > 0 and gouts[i - 1] is not None:
                 dpre = ops.act_bwd(inp, gouts[i - 1], ops.ACT_LRELU, LRELU_SLOPE)
         if want_params:

@@ -248,13 +248,39 @@ def _flat_views(shapes, device, zero=False):
     return [flat[o:o + n].view(s) for o, n, s in zip(offs, sizes, shapes)]
 
 
-def mt_weight_norm_fwd(gs, vs):
-    """w_i = g_i * v_i / ||v_i|| for all layers of a stack in one launch."""
+def mt_weight_norm_fwd(gs, vs, specs=None, P=1):
+    """w_i = g_i * v_i / ||v_i|| for all layers of a stack in one launch.  With `specs` ((k, stride, pad, groups) per
+    layer) the same launch also writes, for every layer the tensor-core conv kernels cover, the zero-padded TF32
+    weight images they stage (forward and data-gradient arrangement).  Returns (ws, imgs_f, imgs_d)."""
+    n = len(vs)
     ws = _flat_views([tuple(v.shape) for v in vs], vs[0].device)
-    rows = (ctypes.c_int64 * len(vs))(*[v.shape[0] for v in vs])
-    rowlen = (ctypes.c_int64 * len(vs))(*[v.numel() // v.shape[0] for v in vs])
-    call("lct_mt_weight_norm_fwd", _ptr_array(gs), _ptr_array(vs), _ptr_array(ws), rows, rowlen, len(vs))
-    return ws
+    rows = (ctypes.c_int64 * n)(*[v.shape[0] for v in vs])
+    rowlen = (ctypes.c_int64 * n)(*[v.numel() // v.shape[0] for v in vs])
+    imgs_f, imgs_d = [None] * n, [None] * n
+    pf = pd = geo = None
+    if specs is not None and config.dense_tensor_cores:
+        shapes, idxs, geos = [], [], [0] * (8 * n)
+        buf = (ctypes.c_int64 * 2)()
+        for i, (k, s, pad, g) in enumerate(specs):
+            cout, cig = vs[i].shape[0], vs[i].shape[1]
+            cin = cig * g
+            if not _use_mma(cin, cout, k, g, s, pad, P):
+                continue
+            call_ret("lct_conv_mma_image_geometry", cin, cout, g, k, s, 0, buf)
+            kkf, nsf = int(buf[0]), int(buf[1])
+            call_ret("lct_conv_mma_image_geometry", cin, cout, g, k, s, 1, buf)
+            kkd, nsd = int(buf[0]), int(buf[1])
+            geos[8 * i:8 * i + 8] = [cout // g, k, s, (k + s - 1) // s, kkf, nsf, kkd, nsd]
+            shapes += [(g, kkf, nsf), (g, kkd, nsd)]
+            idxs.append(i)
+        if idxs:
+            views = _flat_views(shapes, vs[0].device, zero=True)
+            for j, i in enumerate(idxs):
+                imgs_f[i], imgs_d[i] = views[2 * j], views[2 * j + 1]
+            arr = lambda ts: (ctypes.c_void_p * n)(*[t.data_ptr() if t is not None else None for t in ts])
+            pf, pd, geo = arr(imgs_f), arr(imgs_d), (ctypes.c_int64 * (8 * n))(*geos)
+    call("lct_mt_weight_norm_fwd", _ptr_array(gs), _ptr_array(vs), _ptr_array(ws), rows, rowlen, pf, pd, geo, n)
+    return ws, imgs_f, imgs_d
 
 
 def mt_weight_norm_bwd(gs, vs, dws):
@@ -271,7 +297,7 @@ def conv_out_len(lin, k, s, pad):
     return (lin + 2 * pad - k) // s + 1
 
 
-def conv1d_fwd(x, w, bias, groups, stride, pad, act=ACT_NONE, slope=0.2):
+def conv1d_fwd(x, w, bias, groups, stride, pad, act=ACT_NONE, slope=0.2, wimg=None):
     """x [B,Cin,Lin,P], w [Cout,Cin/G,K] (any trailing singleton dims) -> [B,Cout,Lout,P]."""
     B, Cin, Lin, P = x.shape
     Cout, K = w.shape[0], w.shape[2]
@@ -282,13 +308,13 @@ def conv1d_fwd(x, w, bias, groups, stride, pad, act=ACT_NONE, slope=0.2):
         return y
     y = torch.empty(B, Cout, Lout, P, dtype=torch.float32, device=x.device)
     if _use_mma(Cin, Cout, K, groups, stride, pad, P):
-        call("lct_conv_mma_fwd", x, w, bias, y, B, Cin, Cout, groups, K, stride, pad, Lin, P, act, slope)
+        call("lct_conv_mma_fwd", x, w, wimg, bias, y, B, Cin, Cout, groups, K, stride, pad, Lin, P, act, slope)
         return y
     call("lct_conv1d_fwd", x, w, bias, y, B, Cin, Cout, groups, K, stride, pad, Lin, P, act, slope)
     return y
 
 
-def conv1d_dgrad(dy, w, x_shape, groups, stride, pad, gextra=None, xact=None, act=ACT_NONE, slope=0.2):
+def conv1d_dgrad(dy, w, x_shape, groups, stride, pad, gextra=None, xact=None, act=ACT_NONE, slope=0.2, wimg=None):
     B, Cin, Lin, P = x_shape
     Cout, K = w.shape[0], w.shape[2]
     dx = torch.empty(B, Cin, Lin, P, dtype=torch.float32, device=dy.device)
@@ -296,7 +322,7 @@ def conv1d_dgrad(dy, w, x_shape, groups, stride, pad, gextra=None, xact=None, ac
         call("lct_conv_post_dgrad", dy, w, dx, gextra, xact, B, Cin, Lin, P, K, act, slope)
         return dx
     if _use_mma(Cin, Cout, K, groups, stride, pad, P):
-        call("lct_conv_mma_dgrad", dy, w, dx, gextra, xact, B, Cin, Cout, groups, K, stride, pad, Lin, P, act, slope)
+        call("lct_conv_mma_dgrad", dy, w, wimg, dx, gextra, xact, B, Cin, Cout, groups, K, stride, pad, Lin, P, act, slope)
         return dx
     call("lct_conv1d_dgrad", dy, w, dx, gextra, xact, B, Cin, Cout, groups, K, stride, pad, Lin, P, act, slope)
     return dx
