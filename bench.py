@@ -182,8 +182,10 @@ def measure_roofline(dev, peaks):
     w = (torch.randn(Cout, Cin // G, K, generator=g) / 13.0).to(dev)
     xact = torch.randn(B, Cin, L, 1, generator=g).to(dev)
     gextra = torch.randn(B, Cin, L, 1, generator=g).to(dev)
+    gw = torch.ones(Cout, 1, 1, device=dev)
+    _, _, imgs_d = ops.mt_weight_norm_fwd([gw], [w], [(K, S, K // 2, G)], 1)       # staged weight image, as in the step
     ms = _time_kernel(lambda: ops.conv1d_dgrad(dy, w, (B, Cin, L, 1), G, S, K // 2, gextra=gextra, xact=xact,
-                                                act=ops.ACT_LRELU), flush)
+                                                act=ops.ACT_LRELU, wimg=imgs_d[0]), flush)
     nbytes = 4.0 * (dy.numel() + 3 * xact.numel())
     gbs = nbytes / (ms * 1e-3) / 1e9
     roof = {"kernel": "conv_mma_kernel<dgrad> (MSD convs.1 data gradient: 64->16 ch, k=41, s=4, groups=4, B=8, L=32000, "

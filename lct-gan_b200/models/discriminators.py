@@ -60,7 +60,7 @@ def _msd_inputs(msd, x):
     return inputs
 
 
-def run_discriminators(mpd, msd, waves, no_grad=None):
+def run_discriminators(mpd, msd, waves, no_grad=None, first_stream=0):
     """Scheduling helper (not part of the reference API): evaluate `mpd(w)` and `msd(w)` for every waveform w in
     `waves` with ALL 8 * len(waves) sub-discriminators forked at once instead of one module call after the other.
     Returns [(mpd_logits, mpd_fmaps, msd_logits, msd_fmaps) per waveform]; values are identical to the module calls."""
@@ -78,7 +78,7 @@ def run_discriminators(mpd, msd, waves, no_grad=None):
         discs += list(msd.discriminators)
         inputs += mi
         ng += [f] * len(msd.discriminators)
-    res = _run_concurrently(discs, inputs, ng)
+    res = _run_concurrently(discs, inputs, ng, first_stream)
     out, per = [], len(mpd.discriminators) + len(msd.discriminators)
     for k in range(len(waves)):
         r = res[k * per:(k + 1) * per]
