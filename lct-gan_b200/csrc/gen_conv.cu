@@ -135,7 +135,9 @@ __global__ void __launch_bounds__(kThreads) gconv_wgrad_kernel(const GWgradParam
     const int t0 = blockIdx.x * p.rows_per_cta;
     const int nab = CaP / kWgA;                        // a-blocks
     const int nb = nab * p.Cc;                         // (a-block, c) work items
-    const int nslice = max(1, kThreads / nb);
+    // (at most 8 f-slices: every slice ends in global atomics on the same dW entries - 128 slices of a 1-channel
+    // layer serialised 6 M atomics on 96 addresses)
+    const int nslice = max(1, min(8, kThreads / nb));
     const int item = threadIdx.x % nb, slice = threadIdx.x / nb;
     const bool active = threadIdx.x < nb * nslice;
     const int c = item % p.Cc, ab = item / p.Cc;
