@@ -287,7 +287,8 @@ def main():
         broadcast_parameters([enh, mpd, msd])
     sync_d = FlatGradAllReduce(list(mpd.parameters()) + list(msd.parameters())) if world > 1 else None
     sync_g = FlatGradAllReduce(list(enh.parameters())) if world > 1 else None
-    sargs = StepArgs(gan_loss=args.gan_loss, reuse_enhancer_forward=not args.no_reuse)
+    sargs = StepArgs(gan_loss=args.gan_loss, reuse_enhancer_forward=not args.no_reuse,
+                     fake_streams=bool(int(os.environ.get("LCT_FAKE_STREAMS", "0"))))
 
     noisy_h, clean_h = O.synthetic_batch(BATCH, SEGMENT, seed=1234 + rank)      # synthetic data generator only
     noisy_h, clean_h = noisy_h.pin_memory(), clean_h.pin_memory()

@@ -637,7 +637,10 @@ int launch_wgrad(MmaWgradParams& p, cudaStream_t st) {
         if (e != cudaSuccess) return (int)e;
     }
     const int G = p.Cin / p.Cig;
-    dim3 grid((unsigned)G, (unsigned)grid_y(G, p.ntiles));
+    int gy = (148 * 3 + G - 1) / G;      // fewer, longer-lived CTAs than fwd/dgrad: every CTA ends with N x KK atomics
+    if (gy > p.ntiles) gy = p.ntiles;
+    if (gy < 1) gy = 1;
+    dim3 grid((unsigned)G, (unsigned)gy);
     conv_mma_wgrad_kernel<MT, NT><<<grid, kThreads, smem, st>>>(p);
     LCT_RETURN_IF_LAUNCH_FAILED();
     return 0;

@@ -12,7 +12,7 @@
 namespace {
 
 constexpr int kT = 256;
-constexpr int kCC = 64;     // input channels per CTA (forward)
+constexpr int kCC = 16;     // input channels per CTA (forward): 64 chunks of the 1024 channels keep 1000+ CTAs in flight
 constexpr int kMaxK = 8;
 
 // y[b, j] += sum_{ci in chunk} sum_k w[ci][k] * x[b, ci, l + k - pad, p]   (+ bias once); y pre-zeroed
@@ -34,11 +34,12 @@ __global__ void __launch_bounds__(kT) post_fwd_kernel(const float* __restrict__ 
     bool ok[kMaxK];
 #pragma unroll
     for (int k = 0; k < kMaxK; ++k) ok[k] = k < K && (l + k - pad) >= 0 && (l + k - pad) < L;
+#pragma unroll 4
     for (int c = 0; c < cc; ++c) {
         const float* xc = xb + (size_t)c * jtot;
 #pragma unroll
         for (int k = 0; k < kMaxK; ++k)
-            if (ok[k]) acc = fmaf(ws[c * K + k], xc[(k - pad) * P], acc);
+            if (ok[k]) acc = fmaf(ws[c * K + k], __ldg(xc + (k - pad) * P), acc);
     }
     atomicAdd(&y[(size_t)b * jtot + j], acc);
 }

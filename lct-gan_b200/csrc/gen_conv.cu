@@ -122,75 +122,68 @@ struct GWgradParams {
     int rows_per_cta;
 };
 
-constexpr int kWgA = 8;   // S-channels per thread (register block)
+constexpr int kWgMaxPairs = 8;   // (a,c) pairs per thread
 
-// thread = (Lg channel c, block of 8 S channels, f-slice): per position 2 float4 loads of S and 6 loads of Lg feed
-// 48 FMAs; the f range of a row is split over `nslice` thread groups, partial sums meet in the global atomics
 __global__ void __launch_bounds__(kThreads) gconv_wgrad_kernel(const GWgradParams p) {
     extern __shared__ __align__(16) float sm[];
-    const int CaP = (p.Ca + kWgA - 1) / kWgA * kWgA;   // S row stride padded to the register block
-    float* Ssm = sm;                                   // [Fs][CaP]
-    float* Lsm = sm + (size_t)p.Fs * CaP;              // [2][Fl + 2][Cc]   (one zero column on each side)
+    float* Ssm = sm;                                   // [Fs][Ca]
+    float* Lsm = sm + (size_t)p.Fs * p.Ca;             // [2][Fl + 2][Cc]   (one zero column on each side)
     const int b = blockIdx.y;
     const int t0 = blockIdx.x * p.rows_per_cta;
-    const int nab = CaP / kWgA;                        // a-blocks
-    const int nb = nab * p.Cc;                         // (a-block, c) work items
-    // (at most 8 f-slices: every slice ends in global atomics on the same dW entries - 128 slices of a 1-channel
-    // layer serialised 6 M atomics on 96 addresses)
-    const int nslice = max(1, min(8, kThreads / nb));
-    const int item = threadIdx.x % nb, slice = threadIdx.x / nb;
-    const bool active = threadIdx.x < nb * nslice;
-    const int c = item % p.Cc, ab = item / p.Cc;
-    float acc[kWgA][6];
+    const int npairs = p.Ca * p.Cc;
+    float acc[kWgMaxPairs][6];
 #pragma unroll
-    for (int i = 0; i < kWgA; ++i)
+    for (int i = 0; i < kWgMaxPairs; ++i)
 #pragma unroll
         for (int k = 0; k < 6; ++k) acc[i][k] = 0.f;
     const int lrow = (p.Fl + 2) * p.Cc;
     for (int t = t0; t < min(t0 + p.rows_per_cta, p.Ts); ++t) {
         __syncthreads();
-        for (int idx = threadIdx.x; idx < p.Fs * CaP; idx += kThreads) {
-            const int f = idx / CaP, a = idx - f * CaP;
-            Ssm[idx] = a < p.Ca ? p.S[(((size_t)b * p.Ts + t) * p.Fs + f) * p.Ca + a] : 0.f;
-        }
+        for (int idx = threadIdx.x; idx < p.Fs * p.Ca; idx += kThreads)
+            Ssm[idx] = p.S[((size_t)b * p.Ts + t) * p.Fs * p.Ca + idx];
         for (int idx = threadIdx.x; idx < 2 * lrow; idx += kThreads) {
             int kt = idx / lrow;
             int rem = idx - kt * lrow;
-            int fc = rem / p.Cc, cc = rem - fc * p.Cc;
+            int fc = rem / p.Cc, c = rem - fc * p.Cc;
             int fl = fc - 1, tl = t + kt - 1;
             float v = 0.f;
-            if (fl >= 0 && fl < p.Fl && tl >= 0 && tl < p.Tl) v = p.Lg[(((size_t)b * p.Tl + tl) * p.Fl + fl) * p.Cc + cc];
+            if (fl >= 0 && fl < p.Fl && tl >= 0 && tl < p.Tl) v = p.Lg[(((size_t)b * p.Tl + tl) * p.Fl + fl) * p.Cc + c];
             Lsm[idx] = v;
         }
         __syncthreads();
-        if (active) {
-            for (int f = slice; f < p.Fs; f += nslice) {
-                const float4 s0 = *reinterpret_cast<const float4*>(Ssm + f * CaP + ab * kWgA);
-                const float4 s1 = *reinterpret_cast<const float4*>(Ssm + f * CaP + ab * kWgA + 4);
-                const float sv[kWgA] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-                float lv[6];
 #pragma unroll
-                for (int kt = 0; kt < 2; ++kt)
+        for (int i = 0; i < kWgMaxPairs; ++i) {
+            const int pr = threadIdx.x + i * kThreads;
+            if (pr >= npairs) break;
+            const int a = pr / p.Cc, c = pr - a * p.Cc;
+            for (int f = 0; f < p.Fs; ++f) {
+                const float sv = Ssm[f * p.Ca + a];
+                const int fb = 2 * f;   // smem column of Lg index 2f-1  (shifted by the zero column)
+                if (fb + 2 >= p.Fl + 2) {
+                    // guarded tail (Lg narrower than 2*Fs+1)
 #pragma unroll
-                    for (int kf = 0; kf < 3; ++kf) {
-                        const int col = 2 * f + kf;       // smem column of Lg index 2f + kf - 1
-                        lv[kt * 3 + kf] = col < p.Fl + 2 ? Lsm[kt * lrow + col * p.Cc + c] : 0.f;
-                    }
+                    for (int kt = 0; kt < 2; ++kt)
 #pragma unroll
-                for (int i = 0; i < kWgA; ++i)
+                        for (int kf = 0; kf < 3; ++kf) {
+                            int col = fb + kf;
+                            if (col < p.Fl + 2) acc[i][kt * 3 + kf] = fmaf(sv, Lsm[kt * lrow + col * p.Cc + c], acc[i][kt * 3 + kf]);
+                        }
+                } else {
 #pragma unroll
-                    for (int k = 0; k < 6; ++k) acc[i][k] = fmaf(sv[i], lv[k], acc[i][k]);
+                    for (int kt = 0; kt < 2; ++kt)
+#pragma unroll
+                        for (int kf = 0; kf < 3; ++kf)
+                            acc[i][kt * 3 + kf] = fmaf(sv, Lsm[kt * lrow + (fb + kf) * p.Cc + c], acc[i][kt * 3 + kf]);
+                }
             }
         }
     }
-    if (active) {
 #pragma unroll
-        for (int i = 0; i < kWgA; ++i) {
-            const int a = ab * kWgA + i;
-            if (a >= p.Ca) continue;
+    for (int i = 0; i < kWgMaxPairs; ++i) {
+        const int pr = threadIdx.x + i * kThreads;
+        if (pr >= npairs) break;
 #pragma unroll
-            for (int k = 0; k < 6; ++k) atomicAdd(&p.dW[((size_t)a * p.Cc + c) * 6 + k], acc[i][k]);
-        }
+        for (int k = 0; k < 6; ++k) atomicAdd(&p.dW[(size_t)pr * 6 + k], acc[i][k]);
     }
 }
 
@@ -341,12 +334,12 @@ LCT_API int lct_gconv_wgrad(const float* S, const float* Lg, float* dW, int64_t 
                             int64_t Tl, int64_t Fl, int64_t Cc, cudaStream_t st) {
     if (!S || !Lg || !dW || B <= 0 || B >= 65536 || Ts <= 0 || Fs <= 0 || Ca <= 0 || Tl <= 0 || Fl <= 0 || Cc <= 0)
         return LCT_EINVAL;
-    if (((Ca + kWgA - 1) / kWgA) * Cc > kThreads) return LCT_EUNSUPPORTED;
+    if (Ca * Cc > (int64_t)kWgMaxPairs * kThreads) return LCT_EUNSUPPORTED;
     GWgradParams p;
     p.S = S; p.Lg = Lg; p.dW = dW;
     p.B = (int)B; p.Ts = (int)Ts; p.Fs = (int)Fs; p.Ca = (int)Ca; p.Tl = (int)Tl; p.Fl = (int)Fl; p.Cc = (int)Cc;
     p.rows_per_cta = 2;
-    size_t smem = ((size_t)Fs * ((Ca + kWgA - 1) / kWgA * kWgA) + (size_t)2 * (Fl + 2) * Cc) * sizeof(float);
+    size_t smem = ((size_t)Fs * Ca + (size_t)2 * (Fl + 2) * Cc) * sizeof(float);
     if (smem > 200 * 1024) return LCT_EUNSUPPORTED;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(gconv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

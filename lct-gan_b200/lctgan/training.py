@@ -29,6 +29,8 @@ class StepArgs:
     #: With this switch one forward (with grad) serves both - bit-identical values, one forward less - and it runs
     #: on a side stream concurrently with the discriminators' forward on the clean batch (no data dependence).
     reuse_enhancer_forward: bool = False
+    #: (with reuse_enhancer_forward) run the D step's fake chains on streams 8..15 instead of sharing the real chains' streams
+    fake_streams: bool = False
 
 
 def _align_tf_targets(irm_c: torch.Tensor, pred_mask_c: torch.Tensor):
@@ -58,7 +60,8 @@ def _phase_d(M, noisy, clean, args: StepArgs, st: dict) -> None:
         enhanced_for_d = st["enhanced"].detach()
         # (same 8 streams as the real pass: giving the fake chains their own streams was measured 30 % slower - the
         # autograd engine then has to synchronise the two streams at every shared parameter's AccumulateGrad)
-        (mpd_fake, _, msd_fake, _), = run_discriminators(mpd, msd, [enhanced_for_d])
+        (mpd_fake, _, msd_fake, _), = run_discriminators(mpd, msd, [enhanced_for_d],
+                                                         first_stream=8 if args.fake_streams else 0)
     else:
         st["irm_c"] = tf_features(noisy, clean)["irm_c"]
         with torch.no_grad():
