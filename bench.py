@@ -191,7 +191,8 @@ def measure_roofline(dev, peaks):
     roof = {"kernel": "conv_mma_kernel<dgrad> (MSD convs.1 data gradient: 64->16 ch, k=41, s=4, groups=4, B=8, L=32000, "
                       "TF32 mma.sync + fused FM-gradient/LeakyReLU' epilogue)",
             "bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
-            "traffic": 66.9e6, "traffic_note": "dram read+write per launch from ncu --set full (profiles/), warm L2",
+            "traffic": 49.9e6, "traffic_note": "dram__bytes_read+write per launch, ncu --set full "
+            "(profiles/ncu_full_r1_roofline_kernels_raw.csv); the 16.4 MB output is still in the 126 MB L2 when the kernel ends",
             "algorithmic_bytes": nbytes, "ms_per_launch": ms, "peak_source": peaks["src"] + " (STREAM-style copy)"}
     # ---- dense conv forward on tcgen05 (MSD convs.5)
     B, L, C, K = BATCH, 125, 1024, 5
@@ -288,7 +289,8 @@ def main():
     sync_d = FlatGradAllReduce(list(mpd.parameters()) + list(msd.parameters())) if world > 1 else None
     sync_g = FlatGradAllReduce(list(enh.parameters())) if world > 1 else None
     sargs = StepArgs(gan_loss=args.gan_loss, reuse_enhancer_forward=not args.no_reuse,
-                     fake_streams=bool(int(os.environ.get("LCT_FAKE_STREAMS", "0"))))
+                     fake_streams=bool(int(os.environ.get("LCT_FAKE_STREAMS", "0"))),
+                     batch_d_step=not args.no_reuse and bool(int(os.environ.get("LCT_BATCH_D", "1"))))
 
     noisy_h, clean_h = O.synthetic_batch(BATCH, SEGMENT, seed=1234 + rank)      # synthetic data generator only
     noisy_h, clean_h = noisy_h.pin_memory(), clean_h.pin_memory()
@@ -379,7 +381,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 tensor-core operands for the dense contraction (fp32 accumulate), f32 elsewhere",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "gan_loss": args.gan_loss, "parallelism": f"dp{world}", "cuda_graph": graphed is not None, "reuse_enhancer_forward": sargs.reuse_enhancer_forward, "fused_adamw": not args.torch_optim,
+        "config": {"workload": WORKLOAD, "gan_loss": args.gan_loss, "parallelism": f"dp{world}", "cuda_graph": graphed is not None, "reuse_enhancer_forward": sargs.reuse_enhancer_forward, "batch_d_step": sargs.batch_d_step, "fused_adamw": not args.torch_optim,
                    "l2": "no explicit flush: one step streams > 2 GB of activations (>> 126 MB L2)"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,

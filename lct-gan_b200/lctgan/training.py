@@ -31,6 +31,10 @@ class StepArgs:
     reuse_enhancer_forward: bool = False
     #: (with reuse_enhancer_forward) run the D step's fake chains on streams 8..15 instead of sharing the real chains' streams
     fake_streams: bool = False
+    #: D step: push clean and enhanced through the discriminators as ONE batch of 2B (no BatchNorm / cross-sample op in
+    #: the networks, SURVEY 8e, so logits and parameter gradients are identical to two passes): half the launches and
+    #: no gradient-accumulation adds; costs the overlap of D(clean) with the enhancer forward.
+    batch_d_step: bool = False
 
 
 def _align_tf_targets(irm_c: torch.Tensor, pred_mask_c: torch.Tensor):
@@ -47,7 +51,16 @@ def _phase_d(M, noisy, clean, args: StepArgs, st: dict) -> None:
     """TF features + discriminator forward/backward (train.py:171-199)."""
     enhancer, mpd, msd, tf_features, mrstft_loss, g_opt, d_opt = M
     d_opt.zero_grad(set_to_none=True)
-    if args.reuse_enhancer_forward and noisy.is_cuda:
+    if args.reuse_enhancer_forward and args.batch_d_step and noisy.is_cuda:
+        g_opt.zero_grad(set_to_none=True)
+        st["enhanced"], st["mask_c"] = enhancer(noisy)
+        st["irm_c"] = tf_features(noisy, clean)["irm_c"]
+        both = torch.cat([clean, st["enhanced"].detach()], dim=0)
+        nb = clean.shape[0]
+        (pl, _, sl, _), = run_discriminators(mpd, msd, [both])
+        mpd_real, mpd_fake = [t[:nb] for t in pl], [t[nb:] for t in pl]
+        msd_real, msd_fake = [t[:nb] for t in sl], [t[nb:] for t in sl]
+    elif args.reuse_enhancer_forward and noisy.is_cuda:
         g_opt.zero_grad(set_to_none=True)
         cur = torch.cuda.current_stream()
         side = config.side_streams(17, noisy.device)[16]
