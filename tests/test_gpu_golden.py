@@ -169,3 +169,27 @@ def test_reused_enhancer_forward_is_identical(dev, G):
         diff = (p.detach() - q.detach()).abs()
         assert diff.max().item() <= 2.0 * lr * nsteps, k
         assert (diff > 0.05 * lr * nsteps).float().mean().item() <= 1e-3, k
+
+
+@pytest.mark.parametrize("gan_loss", ["ls", "hinge"])
+def test_batched_d_step_is_identical(dev, G, gan_loss):
+    """StepArgs.batch_d_step (clean and enhanced pushed through the discriminators as one batch of 2B in the D step)
+    reproduces the literal schedule: same losses as the reference log, same weights up to Adam-amplified atomics noise."""
+    from lctgan.training import StepArgs, build_models, train_step
+    noisy, clean = (t.to(dev) for t in G["model_inputs"])
+    a = build_models(dev, gan_seed=42)
+    b = build_models(dev, gan_seed=42)
+    names = {"D_loss": "d_loss", "G_loss": "g_loss", "MR": "mr", "Mask": "mask", "Adv": "adv", "FM": "fm"}
+    for step in range(2):
+        lit = train_step(*a, noisy, clean, StepArgs(gan_loss=gan_loss))
+        bat = train_step(*b, noisy, clean, StepArgs(gan_loss=gan_loss, reuse_enhancer_forward=True, batch_d_step=True))
+        for ref_k, k in names.items():
+            assert abs(bat[k].item() - lit[k].item()) <= 2e-6 * max(1.0, abs(lit[k].item())) + 1e-4 * step, (step, k)
+            ref = G[f"train_{gan_loss}"]["logs"][step][ref_k]
+            assert abs(bat[k].item() - ref) <= 1.01e-4 + 1e-3 * abs(ref) * step, (step, k, bat[k].item(), ref)
+    lr, nsteps = 2e-4, 2
+    for ma, mb in zip(a[:3], b[:3]):
+        for (k, p), q in zip(ma.named_parameters(), mb.parameters()):
+            diff = (p.detach() - q.detach()).abs()
+            assert diff.max().item() <= 2.0 * lr * nsteps, k
+            assert (diff > 0.05 * lr * nsteps).float().mean().item() <= 1e-3, k
