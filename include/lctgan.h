@@ -63,7 +63,8 @@ LCT_API int lct_istft_bwd(const float* gy, const float* window, const float* tw,
 /* TFFeatures.forward, tf_features.py:85-146: both STFTs, |X|, IRM^c and |X|^c in one kernel. */
 LCT_API int lct_tf_features_fwd(const float* noisy, const float* clean, const float* window, const float* tw, float* noisy_mag, float* irm_c, float* noisy_mag_c, float* noisy_spec, float* clean_spec, int64_t B, int64_t T, int64_t n_fft, int64_t hop, float c, float gamma, float eps, cudaStream_t stream);
 /* One resolution of MultiResolutionSTFTLoss, losses.py:66-80, without materialising spectrograms:
- * acc[0] += sum (|Yh|_eps - |Y|_eps)^2, acc[1] += sum |Yh - Y|^2. */
+ * acc is [2][64] (zeroed by the caller): acc[0][s] += partial sums of (|Yh|_eps - |Y|_eps)^2, acc[1][s] += partial sums of
+ * |Yh - Y|^2 (64 slots each so that thousands of CTAs do not serialise on one address; the caller adds the slots). */
 LCT_API int lct_mrstft_sums(const float* y_hat, const float* y, const float* window, const float* tw, float* acc, int64_t B, int64_t T, int64_t n_fft, int64_t hop, float eps, cudaStream_t stream);
 /* dL/dYh for that resolution: k_mag * d/dYh (|Yh|_eps-|Y|_eps)^2 + k_cplx * d/dYh |Yh-Y|^2, times upstream[0]. */
 LCT_API int lct_mrstft_grad_spec(const float* spec_hat, const float* spec_ref, float* gspec, int64_t n_bins, float eps, float k_mag, float k_cplx, const float* upstream, cudaStream_t stream);

@@ -6,7 +6,7 @@
 //           TFFeatures.forward  (datasets/tf_features.py:85-146).
 //
 // Design: these kernels are HBM/latency bound (387 KB per 2 s sample for an STFT-512), so the
-// FFT is a shared-memory Stockham autosort (radix 4/2/3/5, fp32, double-generated twiddles)
+// FFT is a shared-memory Stockham autosort (radix 8/4/2/3/5, fp32, double-generated twiddles staged in smem)
 // with the real-input "two for one" trick: two real sequences ride in the real and imaginary
 // lane of one complex transform.  Framing, reflect padding, windowing, |.|, power-law
 // compression, the compressed IRM, mask application, overlap-add and the window-envelope
@@ -24,6 +24,10 @@ constexpr int kSlots = 4;     // concurrent complex FFTs per CTA
 constexpr int kGroup = 64;    // threads cooperating on one FFT
 constexpr int kThreads = kSlots * kGroup;
 constexpr int kMaxPass = 12;
+// FFT buffers are padded by one element per 8 (index i lives at i + i/8): the radix-8 / radix-4 Stockham scatter
+// dst[j0 + r*Ns] has stride 8 (or 4) across lanes for the first passes, which without padding is a 16-way bank conflict
+#define FIDX(i) ((i) + ((i) >> 3))
+__host__ __device__ constexpr int fft_padded(int n) { return n + (n >> 3) + 1; }
 constexpr int kMaxN = 2048;
 
 struct FftPlan {
@@ -37,8 +41,8 @@ bool make_plan(int64_t n, FftPlan* p) {
     p->n = (int)n;
     p->npass = 0;
     int m = (int)n;
-    const int cand[4] = {4, 2, 3, 5};
-    for (int c = 0; c < 4; ++c) {
+    const int cand[5] = {8, 4, 2, 3, 5};   // power-of-two radices first: Ns is a power of two while they run
+    for (int c = 0; c < 5; ++c) {
         while (m % cand[c] == 0) {
             if (p->npass == kMaxPass) return false;
             p->radix[p->npass++] = cand[c];
@@ -75,6 +79,27 @@ __device__ __forceinline__ void dft_small<4>(float2* v) {
     v[3] = csub(b, d);
 }
 template <>
+__device__ __forceinline__ void dft_small<8>(float2* v) {
+    // decimation in frequency: X[2m] = DFT4(v[j] + v[j+4]), X[2m+1] = DFT4((v[j] - v[j+4]) * W8^j)
+    const float h = 0.70710678118654752440f;
+    float2 e[4], o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        e[j] = cadd(v[j], v[j + 4]);
+        o[j] = csub(v[j], v[j + 4]);
+    }
+    o[1] = make_float2(h * (o[1].x + o[1].y), h * (o[1].y - o[1].x));      // * (1 - i)/sqrt2
+    o[2] = mul_mi(o[2]);                                                   // * (-i)
+    o[3] = make_float2(h * (o[3].y - o[3].x), -h * (o[3].x + o[3].y));     // * (-1 - i)/sqrt2
+    dft_small<4>(e);
+    dft_small<4>(o);
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        v[2 * m] = e[m];
+        v[2 * m + 1] = o[m];
+    }
+}
+template <>
 __device__ __forceinline__ void dft_small<3>(float2* v) {
     const float s = 0.86602540378443864676f;
     float2 t1 = cadd(v[1], v[2]), t2 = csub(v[1], v[2]);
@@ -108,20 +133,21 @@ __device__ __forceinline__ void fft_pass(const float2* __restrict__ src, float2*
                                          const float2* __restrict__ tw, int N, int Ns, int g) {
     const int nb = N / R;
     const int tscale = N / (Ns * R);
+    const bool pow2 = (Ns & (Ns - 1)) == 0;
     for (int j = g; j < nb; j += kGroup) {
-        const int k = j % Ns;
+        const int k = pow2 ? (j & (Ns - 1)) : (j % Ns);
         float2 v[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) v[r] = src[j + r * nb];
+        for (int r = 0; r < R; ++r) v[r] = src[FIDX(j + r * nb)];
         if (Ns > 1) {
             const int ts = k * tscale;
 #pragma unroll
-            for (int r = 1; r < R; ++r) v[r] = cmul(v[r], __ldg(&tw[r * ts]));
+            for (int r = 1; r < R; ++r) v[r] = cmul(v[r], tw[r * ts]);
         }
         dft_small<R>(v);
         const int j0 = (j - k) * R + k;
 #pragma unroll
-        for (int r = 0; r < R; ++r) dst[j0 + r * Ns] = v[r];
+        for (int r = 0; r < R; ++r) dst[FIDX(j0 + r * Ns)] = v[r];
     }
 }
 
@@ -132,7 +158,8 @@ __device__ __forceinline__ float2* fft_forward(float2* a, float2* b, const float
     int Ns = 1;
     for (int p = 0; p < plan.npass; ++p) {
         const int R = plan.radix[p];
-        if (R == 4) fft_pass<4>(a, b, tw, plan.n, Ns, g);
+        if (R == 8) fft_pass<8>(a, b, tw, plan.n, Ns, g);
+        else if (R == 4) fft_pass<4>(a, b, tw, plan.n, Ns, g);
         else if (R == 2) fft_pass<2>(a, b, tw, plan.n, Ns, g);
         else if (R == 3) fft_pass<3>(a, b, tw, plan.n, Ns, g);
         else fft_pass<5>(a, b, tw, plan.n, Ns, g);
@@ -170,6 +197,11 @@ __global__ void envelope_kernel(const float* __restrict__ w, float* __restrict__
 // ------------------------------------------------------------------------------------
 // real frames -> one-sided spectrum
 // ------------------------------------------------------------------------------------
+// |z| and x^e for the fused epilogues: sqrt(fma) and exp2(e * lg2.approx(x)) (x > 0; relative error ~1e-7, far inside
+// the 1e-5 front-end tolerance) instead of hypotf / powf, whose ~100-instruction slow paths dominated these kernels
+__device__ __forceinline__ float cabs_fast(float x, float y) { return sqrtf(fmaf(x, x, y * y)); }
+__device__ __forceinline__ float pow_fast(float x, float e) { return exp2f(e * __log2f(x)); }
+
 enum { R2C_STFT = 0, R2C_TFF = 1, R2C_ISTFT_BWD = 2, R2C_MRLOSS = 3 };
 
 struct R2CParams {
@@ -186,7 +218,7 @@ struct R2CParams {
     const float2* xspec;   // ISTFT_BWD with mask: the spectrum the mask was applied to
     const float* mask;     // ISTFT_BWD with mask: mask_c
     float* gmask;          // ISTFT_BWD with mask: grad of mask_c
-    float* acc;            // MRLOSS: [2] (sum of squared magnitude error, sum of |diff|^2)
+    float* acc;            // MRLOSS: [2][64] partial sums (squared magnitude error, |diff|^2), 64 slots each
     int B, T, N, hop, Tf, F;
     float c, gamma, eps, sc_int, sc_edge;
     FftPlan plan;
@@ -204,8 +236,11 @@ __global__ void __launch_bounds__(kThreads) r2c_kernel(const R2CParams P) {
     const int tid = threadIdx.x;
     const int slot = tid / kGroup, g = tid % kGroup;
     const int N = P.N, F = P.F, half = N / 2;
-    float2* buf0 = smem + (size_t)slot * 2 * N;
-    float2* buf1 = buf0 + N;
+    const int NP = fft_padded(N);
+    float2* buf0 = smem + (size_t)slot * 2 * NP;
+    float2* buf1 = buf0 + NP;
+    float2* stw = smem + (size_t)kSlots * 2 * NP;    // twiddle table staged once per CTA
+    for (int i = tid; i < N; i += kThreads) stw[i] = __ldg(&P.tw[i]);
     const int b = blockIdx.y;
     constexpr bool kPairSig = (MODE == R2C_TFF || MODE == R2C_MRLOSS);
     int ma, mb;
@@ -239,46 +274,46 @@ __global__ void __launch_bounds__(kThreads) r2c_kernel(const R2CParams P) {
                 if (va) fa = reflect_load(xa, P.T, ma * P.hop + n - half);
                 if (vb) fb = reflect_load(xb, P.T, mb * P.hop + n - half);
             }
-            buf0[n] = make_float2(fa * w, fb * w);
+            buf0[FIDX(n)] = make_float2(fa * w, fb * w);
         }
     }
     __syncthreads();
-    const float2* Z = fft_forward(buf0, buf1, P.tw, P.plan, g);
+    const float2* Z = fft_forward(buf0, buf1, stw, P.plan, g);
 
     // ---- epilogue: split the two real transforms, fuse the elementwise consumers
     float acc_mag = 0.f, acc_cplx = 0.f;
     for (int k = g; k <= half; k += kGroup) {
-        const float2 zk = Z[k];
-        const float2 zn = Z[k == 0 ? 0 : N - k];
+        const float2 zk = Z[FIDX(k)];
+        const float2 zn = Z[k == 0 ? 0 : FIDX(N - k)];
         float2 A = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
         float2 Bv = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
         if (MODE == R2C_STFT) {
             if (va) {
                 size_t o = ((size_t)b * P.Tf + ma) * F + k;
                 P.spec_a[o] = A;
-                if (P.o0) P.o0[o] = fmaxf(hypotf(A.x, A.y), P.eps);
+                if (P.o0) P.o0[o] = fmaxf(cabs_fast(A.x, A.y), P.eps);
             }
             if (vb) {
                 size_t o = ((size_t)b * P.Tf + mb) * F + k;
                 P.spec_a[o] = Bv;
-                if (P.o0) P.o0[o] = fmaxf(hypotf(Bv.x, Bv.y), P.eps);
+                if (P.o0) P.o0[o] = fmaxf(cabs_fast(Bv.x, Bv.y), P.eps);
             }
         } else if (MODE == R2C_TFF) {
             if (va) {
                 size_t o = ((size_t)b * P.Tf + ma) * F + k;
-                const float nm = fmaxf(hypotf(A.x, A.y), P.eps);
-                const float cm = fmaxf(hypotf(Bv.x, Bv.y), P.eps);
-                const float nmc = powf(nm, P.c);
+                const float nm = fmaxf(cabs_fast(A.x, A.y), P.eps);
+                const float cm = fmaxf(cabs_fast(Bv.x, Bv.y), P.eps);
+                const float nmc = pow_fast(nm, P.c);
                 P.o0[o] = nm;
-                P.o1[o] = powf(cm, P.c) / (nmc + P.gamma);
+                P.o1[o] = pow_fast(cm, P.c) / (nmc + P.gamma);
                 P.o2[o] = nmc;
                 if (P.spec_a) P.spec_a[o] = A;
                 if (P.spec_b) P.spec_b[o] = Bv;
             }
         } else if (MODE == R2C_MRLOSS) {
             if (va) {
-                const float ma_ = fmaxf(hypotf(A.x, A.y), P.eps);
-                const float mb_ = fmaxf(hypotf(Bv.x, Bv.y), P.eps);
+                const float ma_ = fmaxf(cabs_fast(A.x, A.y), P.eps);
+                const float mb_ = fmaxf(cabs_fast(Bv.x, Bv.y), P.eps);
                 const float dm = ma_ - mb_;
                 const float dx = A.x - Bv.x, dy = A.y - Bv.y;
                 acc_mag += dm * dm;
@@ -299,8 +334,8 @@ __global__ void __launch_bounds__(kThreads) r2c_kernel(const R2CParams P) {
                     const float mk = P.mask[o];
                     const float mc = fmaxf(mk, P.eps);
                     const float inv_c = 1.f / P.c;
-                    const float lin = powf(mc, inv_c);
-                    const float dlin = (mk >= P.eps) ? inv_c * powf(mc, inv_c - 1.f) : 0.f;
+                    const float lin = pow_fast(mc, inv_c);
+                    const float dlin = (mk >= P.eps) ? inv_c * pow_fast(mc, inv_c - 1.f) : 0.f;
                     P.gmask[o] = (X.x * G.x + X.y * G.y) * dlin;
                     if (P.spec_a) P.spec_a[o] = make_float2(G.x * lin, G.y * lin);
                 } else {
@@ -313,9 +348,10 @@ __global__ void __launch_bounds__(kThreads) r2c_kernel(const R2CParams P) {
         __shared__ float red[32];
         float s0 = block_sum(acc_mag, red);
         float s1 = block_sum(acc_cplx, red);
-        if (tid == 0) {
-            atomicAdd(&P.acc[0], s0);
-            atomicAdd(&P.acc[1], s1);
+        if (tid == 0) {   // 64 accumulator slots per sum: thousands of CTAs on one address serialise in L2
+            const int slot_id = (blockIdx.x + blockIdx.y * gridDim.x) & 63;
+            atomicAdd(&P.acc[slot_id], s0);
+            atomicAdd(&P.acc[64 + slot_id], s1);
         }
     }
 }
@@ -343,7 +379,7 @@ __device__ __forceinline__ float2 load_bin(const C2RParams& P, size_t base, int 
     float sc = (k == 0 || k == half) ? P.sc_edge : P.sc_int;
     if (P.mask) {
         float mk = fmaxf(P.mask[base + k], P.eps);
-        sc *= fmaxf(powf(mk, 1.f / P.c), 0.f);
+        sc *= fmaxf(pow_fast(mk, 1.f / P.c), 0.f);
     }
     v.x *= sc;
     v.y *= sc;
@@ -358,9 +394,12 @@ __global__ void __launch_bounds__(kThreads) c2r_kernel(const C2RParams P) {
     const int slot = tid / kGroup, g = tid % kGroup;
     const int N = P.N, F = P.F, half = N / 2;
     constexpr int NF = 2 * kSlots;
-    float2* buf0 = smem + (size_t)slot * 2 * N;
-    float2* buf1 = buf0 + N;
-    float* tfr = reinterpret_cast<float*>(smem + (size_t)kSlots * 2 * N);   // [NF][N]
+    const int NP = fft_padded(N);
+    float2* buf0 = smem + (size_t)slot * 2 * NP;
+    float2* buf1 = buf0 + NP;
+    float* tfr = reinterpret_cast<float*>(smem + (size_t)kSlots * 2 * NP);  // [NF][N]
+    float2* stw = reinterpret_cast<float2*>(tfr + (size_t)NF * N);          // twiddle table staged once per CTA
+    for (int i = tid; i < N; i += kThreads) stw[i] = __ldg(&P.tw[i]);
     const int b = blockIdx.y;
     const int m0 = blockIdx.x * P.FR;
     const int mfirst = m0 - (P.R - 1);
@@ -375,13 +414,13 @@ __global__ void __launch_bounds__(kThreads) c2r_kernel(const C2RParams P) {
         const float2 p = load_bin(P, base_a, k, half, va);
         const float2 q = load_bin(P, base_b, k, half, vb);
         // Z[k] = (p.x - q.y, p.y + q.x);  Z[N-k] = (p.x + q.y, -p.y + q.x)
-        buf0[k] = make_float2(p.x - q.y, -(p.y + q.x));
-        if (k != 0 && k != half) buf0[N - k] = make_float2(p.x + q.y, -(-p.y + q.x));
+        buf0[FIDX(k)] = make_float2(p.x - q.y, -(p.y + q.x));
+        if (k != 0 && k != half) buf0[FIDX(N - k)] = make_float2(p.x + q.y, -(-p.y + q.x));
     }
     __syncthreads();
-    const float2* Z = fft_forward(buf0, buf1, P.tw, P.plan, g);
+    const float2* Z = fft_forward(buf0, buf1, stw, P.plan, g);
     for (int n = g; n < N; n += kGroup) {
-        const float2 r = Z[n];
+        const float2 r = Z[FIDX(n)];
         const float w = __ldg(&P.window[n]);
         tfr[(2 * slot) * N + n] = r.x * w;
         tfr[(2 * slot + 1) * N + n] = -r.y * w;
@@ -465,7 +504,7 @@ int launch_r2c(R2CParams& P, cudaStream_t st) {
     const bool pair_sig = (MODE == R2C_TFF || MODE == R2C_MRLOSS);
     const int per = pair_sig ? kSlots : 2 * kSlots;
     dim3 grid((unsigned)ceil_div64(P.Tf, per), (unsigned)P.B);
-    size_t smem = (size_t)kSlots * 2 * P.N * sizeof(float2);
+    size_t smem = ((size_t)kSlots * 2 * fft_padded(P.N) + P.N) * sizeof(float2);
     int rc = set_smem(r2c_kernel<MODE>, smem);
     if (rc) return rc;
     r2c_kernel<MODE><<<grid, kThreads, smem, st>>>(P);
@@ -480,7 +519,7 @@ int launch_c2r(C2RParams& P, cudaStream_t st) {
     if (P.FR < 1) return LCT_EUNSUPPORTED;   // hop < n_fft / 8
     P.Ltot = P.N + P.hop * (P.Tf - 1);
     dim3 grid((unsigned)ceil_div64(P.Tf, P.FR), (unsigned)P.B);
-    size_t smem = (size_t)kSlots * 2 * P.N * sizeof(float2) + (size_t)2 * kSlots * P.N * sizeof(float);
+    size_t smem = ((size_t)kSlots * 2 * fft_padded(P.N) + P.N) * sizeof(float2) + (size_t)2 * kSlots * P.N * sizeof(float);
     int rc = set_smem(c2r_kernel<MODE>, smem);
     if (rc) return rc;
     c2r_kernel<MODE><<<grid, kThreads, smem, st>>>(P);
@@ -545,7 +584,8 @@ LCT_API int lct_tf_features_fwd(const float* noisy, const float* clean, const fl
     return launch_r2c<R2C_TFF>(P, stream);
 }
 
-// acc[0] += sum (|A|_eps - |B|_eps)^2, acc[1] += sum |A - B|^2 over the STFTs of y_hat and y;
+// acc[0..63] += partial sums of (|A|_eps - |B|_eps)^2, acc[64..127] += partial sums of |A - B|^2 (the caller adds the
+// 64 slots of each) over the STFTs of y_hat and y;
 // no spectrogram is written.
 LCT_API int lct_mrstft_sums(const float* y_hat, const float* y, const float* window, const float* tw, float* acc,
                             int64_t B, int64_t T, int64_t n_fft, int64_t hop, float eps, cudaStream_t stream) {

@@ -234,7 +234,7 @@ class MRSTFTLossFn(torch.autograd.Function):
         y = y.contiguous()
         B, T = y_hat.shape
         nres = len(res_cfg)
-        acc = torch.zeros(nres, 2, dtype=torch.float32, device=y_hat.device)
+        acc = torch.zeros(nres, 2, 64, dtype=torch.float32, device=y_hat.device)   # 64 partial-sum slots per sum
         wsum = sum(w for (_, _, w) in res_cfg)
         k_total, k_mag, k_cplx = [], [], []
         for i, ((n_fft, hop, w), win) in enumerate(zip(res_cfg, windows)):
@@ -243,7 +243,7 @@ class MRSTFTLossFn(torch.autograd.Function):
             norm = w / (wsum * n) if wsum > 0 else w / n
             k_mag.append(norm)
             k_cplx.append(norm)
-        segs = [acc[i, j:j + 1] for i in range(nres) for j in range(2)]
+        segs = [acc[i, j] for i in range(nres) for j in range(2)]
         sc_total = [k * (mag_weight if j == 0 else complex_weight) for i, k in enumerate(k_mag) for j in range(2)]
         sc_mag = [k if j == 0 else 0.0 for k in k_mag for j in range(2)]
         sc_cplx = [k if j == 1 else 0.0 for k in k_cplx for j in range(2)]
