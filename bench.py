@@ -254,6 +254,8 @@ def main():
                     "(default: one forward serves the D and the G step: identical values, SURVEY 8f N1)")
     ap.add_argument("--torch-optim", action="store_true", help="use torch.optim.AdamW (as train.py builds it) instead of "
                     "the fused multi-tensor AdamW kernel (same update rule; SURVEY 8f N2)")
+    ap.add_argument("--skip-dead-d-grads", action="store_true", help="do not compute the discriminator weight gradients "
+                    "of the G step (the reference computes and discards them); off by default = the reference's work")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -290,7 +292,8 @@ def main():
     sync_g = FlatGradAllReduce(list(enh.parameters())) if world > 1 else None
     sargs = StepArgs(gan_loss=args.gan_loss, reuse_enhancer_forward=not args.no_reuse,
                      fake_streams=bool(int(os.environ.get("LCT_FAKE_STREAMS", "0"))),
-                     batch_d_step=not args.no_reuse and bool(int(os.environ.get("LCT_BATCH_D", "1"))))
+                     batch_d_step=not args.no_reuse and bool(int(os.environ.get("LCT_BATCH_D", "1"))),
+                     skip_dead_d_grads=args.skip_dead_d_grads)
 
     noisy_h, clean_h = O.synthetic_batch(BATCH, SEGMENT, seed=1234 + rank)      # synthetic data generator only
     noisy_h, clean_h = noisy_h.pin_memory(), clean_h.pin_memory()
@@ -381,7 +384,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 tensor-core operands for the dense contraction (fp32 accumulate), f32 elsewhere",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "gan_loss": args.gan_loss, "parallelism": f"dp{world}", "cuda_graph": graphed is not None, "reuse_enhancer_forward": sargs.reuse_enhancer_forward, "batch_d_step": sargs.batch_d_step, "fused_adamw": not args.torch_optim,
+        "config": {"workload": WORKLOAD, "gan_loss": args.gan_loss, "parallelism": f"dp{world}", "cuda_graph": graphed is not None, "reuse_enhancer_forward": sargs.reuse_enhancer_forward, "batch_d_step": sargs.batch_d_step, "skip_dead_d_grads": sargs.skip_dead_d_grads, "fused_adamw": not args.torch_optim,
                    "l2": "no explicit flush: one step streams > 2 GB of activations (>> 126 MB L2)"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,

@@ -525,6 +525,7 @@ int launch_mma(MmaParams& p, cudaStream_t st) {
 template <int MODE, int NT>
 int launch_mma_mtw(MmaParams& p, cudaStream_t st) {
     // short layers: 128-position tiles keep more CTAs busy
+    if (g_force_mtw == 1) return launch_mma<MODE, NT, 1>(p, st);
     if (g_force_mtw == 2) return launch_mma<MODE, NT, 2>(p, st);
     if (g_force_mtw == 4) return launch_mma<MODE, NT, 4>(p, st);
     if ((int64_t)p.Q * p.P * p.B * (p.Cx / p.Cxg) < 148 * 256) return launch_mma<MODE, NT, 2>(p, st);

@@ -35,6 +35,10 @@ class StepArgs:
     #: the networks, SURVEY 8e, so logits and parameter gradients are identical to two passes): half the launches and
     #: no gradient-accumulation adds; costs the overlap of D(clean) with the enhancer forward.
     batch_d_step: bool = False
+    #: G step: do not compute the discriminators' parameter gradients (train.py computes them only because autograd
+    #: cannot know they are dead: the next d_opt.zero_grad discards them).  Changes no weight and no
+    #: loss, but it does change the (unused) .grad the D parameters hold after the step, hence opt-in, default off.
+    skip_dead_d_grads: bool = False
 
 
 def _align_tf_targets(irm_c: torch.Tensor, pred_mask_c: torch.Tensor):
@@ -133,12 +137,18 @@ def _phase_opt_g(M, args: StepArgs) -> None:
 _OUT_KEYS = ("d_loss", "g_loss", "mr", "mask", "adv", "fm")
 
 
+def _set_skip_dead(mpd, msd, flag: bool) -> None:
+    for d in list(mpd.discriminators) + list(msd.discriminators):
+        d.skip_param_grads_when_input_requires_grad = flag
+
+
 def train_step(enhancer, mpd, msd, tf_features, mrstft_loss, g_opt, d_opt, noisy: torch.Tensor,
                clean: torch.Tensor, args: StepArgs, after_d_backward=None,
                after_g_backward=None) -> Dict[str, torch.Tensor]:
     """One D step + one G step.  Returns the loss tensors (on device; no host sync happens here).
     ``after_*_backward`` are the data-parallel hooks (gradient all-reduce) of lctgan.parallel."""
     M = (enhancer, mpd, msd, tf_features, mrstft_loss, g_opt, d_opt)
+    _set_skip_dead(mpd, msd, args.skip_dead_d_grads)
     st: dict = {}
     _phase_d(M, noisy, clean, args, st)
     if after_d_backward is not None:
@@ -194,6 +204,7 @@ class GraphedTrainStep:
         self.noisy, self.clean = noisy, clean
         self.hooks = (after_d_backward, after_g_backward)
         M = (enhancer, mpd, msd, tf_features, mrstft_loss, g_opt, d_opt)
+        _set_skip_dead(mpd, msd, args.skip_dead_d_grads)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
