@@ -120,9 +120,36 @@ def _split_k(M: int) -> int:
     return max(1, min(256, (M + 511) // 512))
 
 
-def _block_bwd(P, pre, dout, B, T, F, freq, S, GR):
+class _Side:
+    """Runs parameter-gradient kernels of the generator backward on a forked stream: they are off the critical
+    data-gradient chain and the chain's kernels are too small to fill the GPU on their own.  `fork()` orders the
+    side stream after everything enqueued so far; tensors handed to it are kept alive until `join()`."""
+
+    def __init__(self, device):
+        from . import config
+        self.cur = torch.cuda.current_stream(device)
+        self.side = config.side_streams(18, device)[17] if config.concurrent_discriminators else None
+        self.keep = []
+
+    def fork(self, *tensors):
+        self.keep.extend(tensors)
+        if self.side is None:
+            return torch.cuda.stream(self.cur)
+        self.side.wait_stream(self.cur)
+        return torch.cuda.stream(self.side)
+
+    def join(self):
+        if self.side is not None:
+            self.cur.wait_stream(self.side)
+        self.keep.clear()
+
+
+def _block_bwd(P, pre, dout, B, T, F, freq, S, GR, side=None):
     """dout: [M,64] gradient of the block output.  Fills GR[name] for the block's parameters and
     returns the gradient of the block input."""
+    own = side is None
+    if own:
+        side = _Side(dout.device)
     s = S[pre]
     M = dout.shape[0]
     D = s["D"]
@@ -136,20 +163,22 @@ def _block_bwd(P, pre, dout, B, T, F, freq, S, GR):
     # out = seq + lrelu(lin(lin_in))
     dmix = ops.act_bwd(s["mix"], dout, ACT_LRELU, SLOPE)
     kin = 2 * C if freq else C
-    dlin_w = z(C, kin)
-    ops.gemm(dmix, s["lin_in"], dlin_w, C, kin, M, lda=C, ldb=kin, ldc=kin, ta=True, tb=True, ksplit=ks)
-    dlin_b = z(C)
-    ops.colsum(dmix, dlin_b, M, C, C)
+    with side.fork(dmix):          # parameter gradients of `lin`
+        dlin_w = z(C, kin)
+        ops.gemm(dmix, s["lin_in"], dlin_w, C, kin, M, lda=C, ldb=kin, ldc=kin, ta=True, tb=True, ksplit=ks)
+        dlin_b = z(C)
+        ops.colsum(dmix, dlin_b, M, C, C)
     dlin_in = torch.empty(M, kin, **f32)
     ops.gemm(dmix, P[f"{pre}.lin.weight"], dlin_in, M, kin, C, lda=C, ldb=kin, ldc=kin, tb=True)
     GR[f"{pre}.lin.weight"], GR[f"{pre}.lin.bias"] = dlin_w, dlin_b
 
     # attention out-projection: its output is lin_in (t block) or the right half of cat (f block)
     a_off = C if freq else 0
-    dwo = z(C, C)
-    ops.gemm(dlin_in, s["ao"], dwo, C, C, M, lda=kin, ldb=C, ldc=C, ta=True, tb=True, ksplit=ks, a_off=a_off)
-    dbo = z(C)
-    ops.colsum(dlin_in.view(-1)[a_off:], dbo, M, C, kin)
+    with side.fork(dlin_in):
+        dwo = z(C, C)
+        ops.gemm(dlin_in, s["ao"], dwo, C, C, M, lda=kin, ldb=C, ldc=C, ta=True, tb=True, ksplit=ks, a_off=a_off)
+        dbo = z(C)
+        ops.colsum(dlin_in.view(-1)[a_off:], dbo, M, C, kin)
     dao = torch.empty(M, C, **f32)
     ops.gemm(dlin_in, P[f"{pre}.attn.out_proj.weight"], dao, M, C, C, lda=kin, ldb=C, ldc=C, tb=True, a_off=a_off)
     GR[f"{pre}.attn.out_proj.weight"], GR[f"{pre}.attn.out_proj.bias"] = dwo, dbo
@@ -157,10 +186,11 @@ def _block_bwd(P, pre, dout, B, T, F, freq, S, GR):
     dqkv = torch.empty(M, 3 * C, **f32)
     ops.call("lct_attn_bwd", s["qkv"], s["ao"], s["lse"], dao, dqkv, HEADS, geo[0], geo[1], geo[2], geo[3], geo[4],
              geo[5])
-    dwi = z(3 * C, C)
-    ops.gemm(dqkv, s["sn"], dwi, 3 * C, C, M, lda=3 * C, ldb=C, ldc=C, ta=True, tb=True, ksplit=ks)
-    dbi = z(3 * C)
-    ops.colsum(dqkv, dbi, M, 3 * C, 3 * C)
+    with side.fork(dqkv):
+        dwi = z(3 * C, C)
+        ops.gemm(dqkv, s["sn"], dwi, 3 * C, C, M, lda=3 * C, ldb=C, ldc=C, ta=True, tb=True, ksplit=ks)
+        dbi = z(3 * C)
+        ops.colsum(dqkv, dbi, M, 3 * C, 3 * C)
     dsn = torch.empty(M, C, **f32)
     ops.gemm(dqkv, P[f"{pre}.attn.in_proj_weight"], dsn, M, C, 3 * C, lda=3 * C, ldb=C, ldc=C, tb=True)
     GR[f"{pre}.attn.in_proj_weight"], GR[f"{pre}.attn.in_proj_bias"] = dwi, dbi
@@ -182,9 +212,10 @@ def _block_bwd(P, pre, dout, B, T, F, freq, S, GR):
     ops.call("lct_gru_bwd", s["gi"], s["hs"], s["whh"], s["bhh"], dgru, C, dgi, dwhh, dbih, dbhh, geo[0], geo[1], GD, D,
              geo[2], geo[3], geo[4], geo[5])
     # dW_ih[gd] = dgi[:, gd, :]^T @ xn[:, g*16:(g+1)*16]
-    dwih = z(GD, 3 * H, H)
-    ops.gemm(dgi, s["xn"], dwih, 3 * H, H, M, lda=GD * 3 * H, ldb=C, ldc=H, ta=True, tb=True, ksplit=ks, nbatch=GD,
-             a_div=1, b_div=D, sA=3 * H, sB=H, sC=3 * H * H)
+    with side.fork(dgi):
+        dwih = z(GD, 3 * H, H)
+        ops.gemm(dgi, s["xn"], dwih, 3 * H, H, M, lda=GD * 3 * H, ldb=C, ldc=H, ta=True, tb=True, ksplit=ks,
+                 nbatch=GD, a_div=1, b_div=D, sA=3 * H, sB=H, sC=3 * H * H)
     # dxn[:, g] = dgi[:, g, (d,48)] @ [W_ih(g,0); W_ih(g,1)]
     dxn = torch.empty(M, C, **f32)
     ops.gemm(dgi, s["wih"], dxn, M, H, D * 3 * H, lda=GD * 3 * H, ldb=H, ldc=C, tb=True, nbatch=G, sA=D * 3 * H,
@@ -200,6 +231,8 @@ def _block_bwd(P, pre, dout, B, T, F, freq, S, GR):
     dg1, db1 = z(C), z(C)
     dx = ops.layernorm_bwd(dxn, s["x"], P[f"{pre}.layernorm1.weight"], s["mean1"], s["rstd1"], dg1, db1, dres=dseq)
     GR[f"{pre}.layernorm1.weight"], GR[f"{pre}.layernorm1.bias"] = dg1, db1
+    if own:
+        side.join()
     return dx
 
 
@@ -260,6 +293,7 @@ def generator_backward(P, mag, mask, gmask, use_sigmoid, S, need_mag_grad=False)
     enc, dec_in, dec_out = top["enc"], top["dec_in"], top["dec_out"]
     T3, F3 = top["T3"], top["F3"]
     M = B * T3 * F3
+    side = _Side(dev)
 
     # ---- decoder
     dpre = ops.final_mask_bwd(dec_out[2], mask, gmask.contiguous(), use_sigmoid, act=ACT_RELU)
@@ -270,10 +304,11 @@ def generator_backward(P, mag, mask, gmask, use_sigmoid, S, need_mag_grad=False)
         d_in = dec_in[j]
         Bq, Ti, Fi, Ci = d_in.shape
         Co = w.shape[1]
-        GR[f"deconv{i}.weight"] = ops.gconv_wgrad(d_in, dpre, w.shape)
-        db = z(Co)
-        ops.colsum(dpre, db, dpre.numel() // Co, Co, Co)
-        GR[f"deconv{i}.bias"] = db
+        with side.fork(dpre):
+            GR[f"deconv{i}.weight"] = ops.gconv_wgrad(d_in, dpre, w.shape)
+            db = z(Co)
+            ops.colsum(dpre, db, dpre.numel() // Co, Co, Co)
+            GR[f"deconv{i}.bias"] = db
         g_in = ops.gconv(dpre, w, None, (Ti, Fi), Ci, transposed=False)
         dw, dbs = z(Ci), z(Ci)
         src = prev_outs[j]
@@ -289,7 +324,7 @@ def generator_backward(P, mag, mask, gmask, use_sigmoid, S, need_mag_grad=False)
     # ---- bottleneck
     dh = dh3.view(M, C)
     for name, freq in reversed(BLOCKS):
-        dh = _block_bwd(P, name, dh, B, T3, F3, freq, S, GR)
+        dh = _block_bwd(P, name, dh, B, T3, F3, freq, S, GR, side)
     dg0, db0 = z(C), z(C)
     dx3 = ops.layernorm_bwd(dh, enc[2].view(M, C), P["layernorm.weight"], top["mean0"], top["rstd0"], dg0, db0)
     GR["layernorm.weight"], GR["layernorm.bias"] = dg0, db0
@@ -302,13 +337,15 @@ def generator_backward(P, mag, mask, gmask, use_sigmoid, S, need_mag_grad=False)
         w = P[f"conv{i}.weight"]
         xin = inputs[i - 1]
         Co = w.shape[0]
-        GR[f"conv{i}.weight"] = ops.gconv_wgrad(dpre, xin, w.shape)
-        db = z(Co)
-        ops.colsum(dpre, db, dpre.numel() // Co, Co, Co)
-        GR[f"conv{i}.bias"] = db
+        with side.fork(dpre):
+            GR[f"conv{i}.weight"] = ops.gconv_wgrad(dpre, xin, w.shape)
+            db = z(Co)
+            ops.colsum(dpre, db, dpre.numel() // Co, Co, Co)
+            GR[f"conv{i}.bias"] = db
         if i > 1:
             dpre = ops.gconv(dpre, w, None, (xin.shape[1], xin.shape[2]), xin.shape[3], transposed=True, gmul=xin,
                              gact=ACT_LRELU, gslope=SLOPE)
+    side.join()
     return GR
 
 
