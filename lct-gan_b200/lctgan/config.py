@@ -31,3 +31,18 @@ def side_streams(n: int, device):
     while len(pool) < n:
         pool.append(torch.cuda.Stream(device=device))
     return pool[:n]
+
+
+_AUX = {}
+
+
+def aux_stream_for(stream):
+    """A persistent helper stream paired with `stream` (used to run weight-gradient kernels beside the data-gradient
+    chain of the same sub-discriminator)."""
+    import torch
+    key = (stream.device.index, stream.cuda_stream)
+    aux = _AUX.get(key)
+    if aux is None:
+        aux = torch.cuda.Stream(device=stream.device)
+        _AUX[key] = aux
+    return aux

@@ -90,6 +90,18 @@ class ConvStackFn(torch.autograd.Function):
 
         dpre = gouts[n - 1]      # conv_post has no activation
         gx = None
+        # weight gradients run on a helper stream beside the data-gradient chain (joined before returning)
+        cur = torch.cuda.current_stream(x4.device)
+        aux = config.aux_stream_for(cur) if (want_params and config.concurrent_discriminators) else None
+        keep = []
+
+        def on_aux(t):
+            keep.append(t)
+            if aux is None:
+                return torch.cuda.stream(cur)
+            aux.wait_stream(cur)
+            return torch.cuda.stream(aux)
+
         for i in range(n - 1, -1, -1):
             k, s, pad, g = specs[i]
             inp = x4 if i == 0 else fmaps[i - 1]
@@ -98,16 +110,18 @@ class ConvStackFn(torch.autograd.Function):
                 B_, Ci_, L_ = inp.shape[0], inp.shape[1], inp.shape[2]
                 Co_ = weights[i].shape[0]
                 if want_params:
-                    Lp = L_ + k - 1
-                    dyq = ops.stage_ncl_bf16(dpre, Lp, 0, rowsum=dbs[i])
-                    xq = ops.stage_ncl_bf16(inp, Lp, pad, copies=k)
-                    ops.dense_wgrad(dyq, xq, Co_, Ci_, k, weights[i].shape, out=dws[i])
+                    with on_aux(dpre):
+                        Lp = L_ + k - 1
+                        dyq = ops.stage_ncl_bf16(dpre, Lp, 0, rowsum=dbs[i])
+                        xq = ops.stage_ncl_bf16(inp, Lp, pad, copies=k)
+                        ops.dense_wgrad(dyq, xq, Co_, Ci_, k, weights[i].shape, out=dws[i])
                 _, wd = ops.stage_dense_weights(weights[i], want_wt=False, want_wd=True)
                 dpre = ops.dense_conv(ops.stage_nlc_bf16(dpre, pad), wd, B_, L_, Co_, Ci_, k, gextra=gouts[i - 1],
                                       xact=inp, act=ops.ACT_LRELU, slope=LRELU_SLOPE)
             elif dpre is not None:
                 if want_params:
-                    ops.conv1d_wgrad(inp, dpre, weights[i].shape, g, s, pad, want_bias=True, dw=dws[i], db=dbs[i])
+                    with on_aux(dpre):
+                        ops.conv1d_wgrad(inp, dpre, weights[i].shape, g, s, pad, want_bias=True, dw=dws[i], db=dbs[i])
                 if i > 0:
                     dpre = ops.conv1d_dgrad(dpre, weights[i], inp.shape, g, s, pad, gextra=gouts[i - 1], xact=inp,
                                             act=ops.ACT_LRELU, slope=LRELU_SLOPE, wimg=ctx.imgs_d[i])
@@ -116,6 +130,9 @@ class ConvStackFn(torch.autograd.Function):
             elif i > 0 and gouts[i - 1] is not None:
                 dpre = ops.act_bwd(inp, gouts[i - 1], ops.ACT_LRELU, LRELU_SLOPE)
         if want_params:
+            if aux is not None:
+                cur.wait_stream(aux)
+            keep.clear()
             gs = [params[3 * i + 1].contiguous() for i in range(n)]
             vs = [params[3 * i + 2].contiguous() for i in range(n)]
             dgs, dvs = ops.mt_weight_norm_bwd(gs, vs, dws)
