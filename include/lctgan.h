@@ -45,8 +45,14 @@ LCT_API int lct_reset_kernel_launches(void);
 /* ---------------------------------------------------------------- STFT / iSTFT  (datasets/stft.py) */
 /* 1 if n_fft is supported (even, 8..2048, prime factors 2/3/5). */
 LCT_API int lct_fft_supported(int64_t n_fft);
-/* tw[n_fft][2] = exp(-2 pi i m / n_fft), generated in double precision on the device. */
+/* Number of complex entries of the twiddle buffer for n_fft (2 n_fft + 64). */
+LCT_API int lct_fft_twiddle_len(int64_t n_fft);
+/* tw[lct_fft_twiddle_len(n_fft)][2], generated in double precision on the device:
+ * [0, N) exp(-2 pi i m / N) | [N, N+64) W_64^(m0 k1) at m0*8+k1 | [N+64, 2N+64) W_N^(q j) at q*64+j
+ * (the last two feed the register-resident warp FFT used for n_fft = 320 / 512 / 768). */
 LCT_API int lct_fft_twiddles(float* tw, int64_t n_fft, cudaStream_t stream);
+/* 1: force the generic shared-memory Stockham kernels for every n_fft (A/B measurements); 0: default dispatch. */
+LCT_API int lct_fft_force_generic(int on);
 /* env[n_fft + hop*(n_frames-1)] = overlap-added squared window (torch.istft's window_envelop). */
 LCT_API int lct_ola_envelope(const float* window, float* env, int64_t n_fft, int64_t hop, int64_t n_frames, cudaStream_t stream);
 /* ComplexSTFT.forward, stft.py:59-88 (torch.stft: center, reflect, onesided, unnormalised).

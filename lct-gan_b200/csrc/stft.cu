@@ -170,13 +170,24 @@ __device__ __forceinline__ float2* fft_forward(float2* a, float2* b, const float
     return a;
 }
 
+// tw: [0, n) W_n^m | [n, n + 64) W_64^{m0 k1} at m0 * 8 + k1 | [n + 64, 2n + 64) W_n^{q j} at q * 64 + j  (stft_warp.cuh)
 __global__ void twiddle_kernel(float2* tw, int n) {
-    int m = blockIdx.x * blockDim.x + threadIdx.x;
-    if (m < n) {
-        double s, c;
-        sincospi(-2.0 * (double)m / (double)n, &s, &c);
-        tw[m] = make_float2((float)c, (float)s);
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * n + 64) return;
+    double num, den = (double)n;
+    if (i < n) {
+        num = (double)i;
+    } else if (i < n + 64) {
+        const int e = i - n;
+        num = (double)((e >> 3) * (e & 7));
+        den = 64.0;
+    } else {
+        const int e = i - n - 64;
+        num = (double)((e >> 6) * (e & 63));
     }
+    double s, c;
+    sincospi(-2.0 * num / den, &s, &c);
+    tw[i] = make_float2((float)c, (float)s);
 }
 
 __global__ void envelope_kernel(const float* __restrict__ w, float* __restrict__ env, int N, int hop,
@@ -387,6 +398,10 @@ __device__ __forceinline__ float2 load_bin(const C2RParams& P, size_t base, int 
     return v;
 }
 
+}  // namespace
+#include "stft_warp.cuh"
+namespace {
+
 template <int MODE>
 __global__ void __launch_bounds__(kThreads) c2r_kernel(const C2RParams P) {
     extern __shared__ float2 smem[];
@@ -499,8 +514,46 @@ int set_smem(K kernel, size_t bytes) {
     return 0;
 }
 
+// register-resident warp FFT (stft_warp.cuh) for n_fft = 64 R, R in {5, 8, 12}; g_fft_generic forces the generic kernels
+int g_fft_generic = 0;
+
+template <int R, int MODE>
+int launch_r2c_warp(R2CParams& P, cudaStream_t st) {
+    const bool pair_sig = (MODE == R2C_TFF || MODE == R2C_MRLOSS);
+    const int units = pair_sig ? P.Tf : (P.Tf + 1) / 2;
+    dim3 grid((unsigned)ceil_div64(units, wf::kR2CWarps), (unsigned)P.B);
+    const size_t smem = (size_t)wf::kR2CWarps * wf::Cfg<R>::BUF * sizeof(float2);
+    wf::r2c_warp_kernel<R, MODE><<<grid, wf::kR2CWarps * 32, smem, st>>>(P);
+    LCT_RETURN_IF_LAUNCH_FAILED();
+    return 0;
+}
+
+template <int R, int MODE, int WARPS>
+int launch_c2r_warp_w(C2RParams& P, cudaStream_t st) {
+    dim3 grid((unsigned)ceil_div64(P.Tf + 1, 2 * WARPS - 1), (unsigned)P.B);
+    const size_t smem = (size_t)WARPS * wf::Cfg<R>::BUF * sizeof(float2) + (size_t)WARPS * wf::Cfg<R>::HALF * sizeof(float);
+    int rc = set_smem(wf::c2r_warp_kernel<R, MODE, WARPS>, smem);
+    if (rc) return rc;
+    wf::c2r_warp_kernel<R, MODE, WARPS><<<grid, WARPS * 32, smem, st>>>(P);
+    LCT_RETURN_IF_LAUNCH_FAILED();
+    return 0;
+}
+
+template <int R, int MODE>
+int launch_c2r_warp(C2RParams& P, cudaStream_t st) {
+    P.Ltot = P.N + P.hop * (P.Tf - 1);
+    // small problems: 4-warp CTAs (7 segments each) spread over more SMs; large ones: 8 warps (1 redundant frame in 16)
+    if ((int64_t)P.B * (P.Tf + 1) < 148 * 15 * 2) return launch_c2r_warp_w<R, MODE, 4>(P, st);
+    return launch_c2r_warp_w<R, MODE, 8>(P, st);
+}
+
 template <int MODE>
 int launch_r2c(R2CParams& P, cudaStream_t st) {
+    if (!g_fft_generic) {
+        if (P.N == 320) return launch_r2c_warp<5, MODE>(P, st);
+        if (P.N == 512) return launch_r2c_warp<8, MODE>(P, st);
+        if (P.N == 768) return launch_r2c_warp<12, MODE>(P, st);
+    }
     const bool pair_sig = (MODE == R2C_TFF || MODE == R2C_MRLOSS);
     const int per = pair_sig ? kSlots : 2 * kSlots;
     dim3 grid((unsigned)ceil_div64(P.Tf, per), (unsigned)P.B);
@@ -514,6 +567,11 @@ int launch_r2c(R2CParams& P, cudaStream_t st) {
 
 template <int MODE>
 int launch_c2r(C2RParams& P, cudaStream_t st) {
+    if (!g_fft_generic && 2 * P.hop == P.N) {
+        if (P.N == 320) return launch_c2r_warp<5, MODE>(P, st);
+        if (P.N == 512) return launch_c2r_warp<8, MODE>(P, st);
+        if (P.N == 768) return launch_c2r_warp<12, MODE>(P, st);
+    }
     P.R = (int)ceil_div64(P.N, P.hop);
     P.FR = 2 * kSlots - (P.R - 1);
     if (P.FR < 1) return LCT_EUNSUPPORTED;   // hop < n_fft / 8
@@ -538,10 +596,20 @@ LCT_API int lct_fft_supported(int64_t n_fft) {
     return make_plan(n_fft, &p) ? 1 : 0;
 }
 
+// number of complex (float2) entries of the twiddle buffer lct_fft_twiddles fills for n_fft
+LCT_API int lct_fft_twiddle_len(int64_t n_fft) { return (int)(2 * n_fft + 64); }
+
+// 1: use the generic shared-memory Stockham kernels for every size (bring-up / A-B measurements); 0 (default): the
+// register-resident warp FFT for n_fft in {320, 512, 768}
+LCT_API int lct_fft_force_generic(int on) {
+    g_fft_generic = on ? 1 : 0;
+    return 0;
+}
+
 LCT_API int lct_fft_twiddles(float* tw, int64_t n_fft, cudaStream_t stream) {
     FftPlan p;
     if (!tw || !make_plan(n_fft, &p)) return LCT_EINVAL;
-    twiddle_kernel<<<(unsigned)ceil_div64(n_fft, 128), 128, 0, stream>>>(reinterpret_cast<float2*>(tw), (int)n_fft);
+    twiddle_kernel<<<(unsigned)ceil_div64(2 * n_fft + 64, 128), 128, 0, stream>>>(reinterpret_cast<float2*>(tw), (int)n_fft);
     LCT_RETURN_IF_LAUNCH_FAILED();
     return 0;
 }

@@ -1,0 +1,468 @@
+// Register-resident warp FFT for the STFT / iSTFT front end (included by stft.cu).
+//
+// One warp transforms one complex sequence of N = 64 R points (R = 5, 8, 12: n_fft = 320, 512, 768, the three
+// resolutions the reference uses, losses.py:11-19 / datasets/stft.py:10-34), i.e. two real frames with the
+// "two for one" trick.  The transform is three passes 8 x 8 x R; every thread keeps its butterflies in registers
+// and the warp only meets in shared memory twice (2 x N float2 written + read, bank-conflict free, __syncwarp
+// only - no CTA barrier).  Framing/windowing is fused into the loads of the first pass and the spectrum
+// consumers into the last pass, straight from registers:
+//
+//   n = q + R (m0 + 8 m1)       k = (k1 + 8 k2) + 64 r                                   W_M = exp(-2 pi i / M)
+//   X[k] = sum_q W_R^{q r} W_N^{q j} sum_{m0} W_8^{m0 k2} W_64^{m0 k1} sum_{m1} W_8^{m1 k1} x[n],   j = k1 + 8 k2
+//
+//   pass 1: thread <-> id = R m0 + q = lane + 32 u   radix-8 over m1 (inputs x[id + 8 R m1]: coalesced loads)
+//   pass 2: thread <-> (q, k1) = lane + 32 u         twiddle W_64^{m0 k1}, radix-8 over m0
+//   pass 3: thread <-> j = lane and j' = 64 - lane   twiddle W_N^{q j},  radix-R over q  ->  X[j + 64 r]
+//
+// Bins k and N - k are produced by butterflies j and 64 - j, which pass 3 gives to the SAME thread (lane 0 takes the
+// two self-paired butterflies 0 and 32), so the split of the two real spectra is thread local and each lane writes
+// consecutive bins (coalesced).  The inverse direction runs the transposed flow graph (radix-R first, natural order
+// last) on conj(Z), so the Hermitian extension is thread local as well and the frames come out in coalesced order.
+//
+// Shared-memory layouts (float2 units, found by exhaustive search, conflict free for the writer and the reader):
+//   exchange 1: id + (8 R + 2) k1        exchange 2: 72 q + j
+#pragma once
+
+namespace wf {
+
+template <int R> struct Cfg {
+    static constexpr int N = 64 * R;
+    static constexpr int HALF = 32 * R;
+    static constexpr int NB = 8 * R;                  // radix-8 butterflies per pass
+    static constexpr int U = (NB + 31) / 32;          // ... per thread
+    static constexpr bool FULL = (NB % 32) == 0;      // every (lane, u) slot holds a butterfly
+    static constexpr int S1 = 8 * R + 2;
+    static constexpr int BUF = 72 * R - 8;            // float2 per warp (covers both exchanges)
+    static constexpr int NA = (R % 2 == 0) ? R / 2 : (R + 1) / 2;   // bins j + 64 r <= N/2 of butterfly j = lane (lane >= 1)
+    static constexpr int NBN = (R % 2 == 0) ? R / 2 : (R - 1) / 2;  // bins of butterfly 64 - lane
+    // lane 0 (butterflies 0 and 32) owns one more bin: the Nyquist bin (A side for even R, B side for odd R)
+    static constexpr bool XTRA_A = (R % 2 == 0);
+};
+
+// twiddle buffer layout (float2): [0, N) W_N^m | [N, N + 64) T2[m0][k1] = W_64^{m0 k1} | [N + 64, 2N + 64) T3[q][j] = W_N^{q j}
+__host__ __device__ constexpr int tw_len(int n) { return 2 * n + 64; }
+
+template <int R> __device__ __forceinline__ void dft_r(float2* v);
+template <> __device__ __forceinline__ void dft_r<5>(float2* v) { dft_small<5>(v); }
+template <> __device__ __forceinline__ void dft_r<8>(float2* v) { dft_small<8>(v); }
+template <> __device__ __forceinline__ void dft_r<12>(float2* v) {
+    // 12 = 3 x 4:  X[j + 4 r] = sum_q W_3^{q r} W_12^{q j} sum_m x[q + 3 m] W_4^{m j}
+    const float c = 0.86602540378443864676f;
+    float2 y[3][4];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m) y[q][m] = v[q + 3 * m];
+        dft_small<4>(y[q]);
+    }
+    // W_12^{q j}: q = 1: j = 1, 2, 3 -> W^1, W^2, W^3;  q = 2: j = 1, 2, 3 -> W^2, W^4, W^6
+    y[1][1] = cmul(y[1][1], make_float2(c, -0.5f));
+    y[1][2] = cmul(y[1][2], make_float2(0.5f, -c));
+    y[1][3] = mul_mi(y[1][3]);
+    y[2][1] = cmul(y[2][1], make_float2(0.5f, -c));
+    y[2][2] = cmul(y[2][2], make_float2(-0.5f, -c));
+    y[2][3] = make_float2(-y[2][3].x, -y[2][3].y);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float2 t[3] = {y[0][j], y[1][j], y[2][j]};
+        dft_small<3>(t);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) v[j + 4 * r] = t[r];
+    }
+}
+
+// v[u][m1] = x[lane + 32 u + 8 R m1]  ->  XA[r] = X[jA + 64 r], XB[r] = X[jB + 64 r]   (jA = lane, jB = lane ? 64 - lane : 32)
+template <int R>
+__device__ __forceinline__ void fft_dit(float2 (&v)[Cfg<R>::U][8], float2 (&XA)[R], float2 (&XB)[R], float2* buf,
+                                        const float2* __restrict__ tw, int lane) {
+    using C = Cfg<R>;
+    const float2* T2 = tw + C::N;
+    const float2* T3 = tw + C::N + 64;
+#pragma unroll
+    for (int u = 0; u < C::U; ++u) {
+        if (C::FULL || lane + 32 * u < C::NB) {
+            dft_small<8>(v[u]);
+#pragma unroll
+            for (int k1 = 0; k1 < 8; ++k1) buf[lane + 32 * u + C::S1 * k1] = v[u][k1];
+        }
+    }
+    __syncwarp();
+    const int k1 = lane & 7;
+    float2 t2[8];
+#pragma unroll
+    for (int m0 = 1; m0 < 8; ++m0) t2[m0] = __ldg(&T2[m0 * 8 + k1]);
+#pragma unroll
+    for (int u = 0; u < C::U; ++u) {
+        if (C::FULL || lane + 32 * u < C::NB) {
+            const int q = (lane + 32 * u) >> 3;
+#pragma unroll
+            for (int m0 = 0; m0 < 8; ++m0) v[u][m0] = buf[q + C::S1 * k1 + R * m0];
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < C::U; ++u) {
+        if (C::FULL || lane + 32 * u < C::NB) {
+            const int q = (lane + 32 * u) >> 3;
+#pragma unroll
+            for (int m0 = 1; m0 < 8; ++m0) v[u][m0] = cmul(v[u][m0], t2[m0]);
+            dft_small<8>(v[u]);
+#pragma unroll
+            for (int k2 = 0; k2 < 8; ++k2) buf[72 * q + k1 + 8 * k2] = v[u][k2];
+        }
+    }
+    __syncwarp();
+    const int jA = lane, jB = lane ? 64 - lane : 32;
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+        XA[q] = buf[72 * q + jA];
+        XB[q] = buf[72 * q + jB];
+    }
+#pragma unroll
+    for (int q = 1; q < R; ++q) {
+        XA[q] = cmul(XA[q], __ldg(&T3[64 * q + jA]));
+        XB[q] = cmul(XB[q], __ldg(&T3[64 * q + jB]));
+    }
+    dft_r<R>(XA);
+    dft_r<R>(XB);
+    __syncwarp();     // buf may be rewritten by the caller's next transform
+}
+
+// transposed flow graph: UA[r] = u[jA + 64 r], UB[r] = u[jB + 64 r]  ->  v[u][m1] = FFT(u)[lane + 32 u + 8 R m1]
+template <int R>
+__device__ __forceinline__ void fft_dif(float2 (&UA)[R], float2 (&UB)[R], float2 (&v)[Cfg<R>::U][8], float2* buf,
+                                        const float2* __restrict__ tw, int lane) {
+    using C = Cfg<R>;
+    const float2* T2 = tw + C::N;
+    const float2* T3 = tw + C::N + 64;
+    const int jA = lane, jB = lane ? 64 - lane : 32;
+    dft_r<R>(UA);
+    dft_r<R>(UB);
+#pragma unroll
+    for (int q = 1; q < R; ++q) {
+        UA[q] = cmul(UA[q], __ldg(&T3[64 * q + jA]));
+        UB[q] = cmul(UB[q], __ldg(&T3[64 * q + jB]));
+    }
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+        buf[72 * q + jA] = UA[q];
+        buf[72 * q + jB] = UB[q];
+    }
+    __syncwarp();
+    const int k1 = lane & 7;
+    float2 t2[8];
+#pragma unroll
+    for (int m0 = 1; m0 < 8; ++m0) t2[m0] = __ldg(&T2[m0 * 8 + k1]);
+#pragma unroll
+    for (int u = 0; u < C::U; ++u) {
+        if (C::FULL || lane + 32 * u < C::NB) {
+            const int q = (lane + 32 * u) >> 3;
+#pragma unroll
+            for (int k2 = 0; k2 < 8; ++k2) v[u][k2] = buf[72 * q + k1 + 8 * k2];
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < C::U; ++u) {
+        if (C::FULL || lane + 32 * u < C::NB) {
+            const int q = (lane + 32 * u) >> 3;
+            dft_small<8>(v[u]);
+#pragma unroll
+            for (int m0 = 1; m0 < 8; ++m0) v[u][m0] = cmul(v[u][m0], t2[m0]);
+#pragma unroll
+            for (int m0 = 0; m0 < 8; ++m0) buf[q + C::S1 * k1 + R * m0] = v[u][m0];
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int u = 0; u < C::U; ++u) {
+        if (C::FULL || lane + 32 * u < C::NB) {
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) v[u][kk] = buf[lane + 32 * u + C::S1 * kk];
+            dft_small<8>(v[u]);
+        }
+    }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------
+// real frames -> one-sided spectra (STFT, TFFeatures, iSTFT adjoint, MR-STFT loss sums)
+// ------------------------------------------------------------------------------------------------
+constexpr int kR2CWarps = 4;
+
+template <int R, int MODE>
+__global__ void __launch_bounds__(kR2CWarps * 32) r2c_warp_kernel(const R2CParams P) {
+    using C = Cfg<R>;
+    constexpr int N = C::N, HALF = C::HALF, F = HALF + 1;
+    extern __shared__ float2 smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float2* buf = smem + (size_t)warp * C::BUF;
+    const int b = blockIdx.y;
+    constexpr bool kPairSig = (MODE == R2C_TFF || MODE == R2C_MRLOSS);
+    const int unit = blockIdx.x * kR2CWarps + warp;
+    const int ma = kPairSig ? unit : 2 * unit;
+    const int mb = kPairSig ? unit : ma + 1;
+    if (ma >= P.Tf) return;                      // warp uniform; no CTA barrier below
+    const bool vb = mb < P.Tf;
+    const float* xa = P.a + (size_t)b * P.T;
+    const float* xb = kPairSig ? P.b + (size_t)b * P.T : xa;
+
+    // ---- framing + window (0.5 of the two-for-one split folded in: exact)
+    float2 v[C::U][8];
+    {
+        const int sa = ma * P.hop - HALF, sb = mb * P.hop - HALF;
+        const bool fast = (MODE != R2C_ISTFT_BWD) && sa >= 0 && sa + N <= P.T && (!vb || (sb >= 0 && sb + N <= P.T));
+#pragma unroll
+        for (int u = 0; u < C::U; ++u) {
+#pragma unroll
+            for (int m1 = 0; m1 < 8; ++m1) {
+                const int n = lane + 32 * u + C::NB * m1;
+                float fa = 0.f, fb = 0.f;
+                if (C::FULL || lane + 32 * u < C::NB) {
+                    const float w = 0.5f * __ldg(&P.window[n]);
+                    if (MODE == R2C_ISTFT_BWD) {
+                        // adjoint of "slice [N/2, N/2 + T) of the overlap-add buffer, divided by the envelope"
+                        const int Ltot = N + P.hop * (P.Tf - 1);
+                        const int tpa = ma * P.hop + n, ta = tpa - HALF;
+                        if (ta >= 0 && ta < P.T && tpa < Ltot) fa = __fdividef(xa[ta], __ldg(&P.env[tpa]));
+                        const int tpb = mb * P.hop + n, tb = tpb - HALF;
+                        if (vb && tb >= 0 && tb < P.T && tpb < Ltot) fb = __fdividef(xa[tb], __ldg(&P.env[tpb]));
+                    } else if (fast) {
+                        fa = xa[sa + n];
+                        if (vb) fb = xb[sb + n];
+                    } else {
+                        fa = reflect_load(xa, P.T, sa + n);
+                        if (vb) fb = reflect_load(xb, P.T, sb + n);
+                    }
+                    fa *= w;
+                    fb *= w;
+                }
+                v[u][m1] = make_float2(fa, fb);
+            }
+        }
+    }
+    float2 XA[R], XB[R];
+    fft_dit<R>(v, XA, XB, buf, P.tw, lane);
+
+    // ---- split the two real spectra (thread local) and feed the fused consumers
+    const int jA = lane, jB = lane ? 64 - lane : 32;
+    const size_t row_a = ((size_t)b * P.Tf + ma) * F;
+    const size_t row_b = ((size_t)b * P.Tf + mb) * F;
+    float acc_mag = 0.f, acc_cplx = 0.f;
+    auto emit = [&](int k, float2 zk, float2 zn) {
+        float2 A = make_float2(zk.x + zn.x, zk.y - zn.y);
+        float2 Bv = make_float2(zk.y + zn.y, zn.x - zk.x);
+        if (MODE == R2C_STFT) {
+            P.spec_a[row_a + k] = A;
+            if (P.o0) P.o0[row_a + k] = fmaxf(cabs_fast(A.x, A.y), P.eps);
+            if (vb) {
+                P.spec_a[row_b + k] = Bv;
+                if (P.o0) P.o0[row_b + k] = fmaxf(cabs_fast(Bv.x, Bv.y), P.eps);
+            }
+        } else if (MODE == R2C_TFF) {
+            const float nm = fmaxf(cabs_fast(A.x, A.y), P.eps);
+            const float cm = fmaxf(cabs_fast(Bv.x, Bv.y), P.eps);
+            const float nmc = pow_fast(nm, P.c);
+            P.o0[row_a + k] = nm;
+            P.o1[row_a + k] = __fdividef(pow_fast(cm, P.c), nmc + P.gamma);
+            P.o2[row_a + k] = nmc;
+            if (P.spec_a) P.spec_a[row_a + k] = A;
+            if (P.spec_b) P.spec_b[row_a + k] = Bv;
+        } else if (MODE == R2C_MRLOSS) {
+            const float ma_ = fmaxf(cabs_fast(A.x, A.y), P.eps);
+            const float mb_ = fmaxf(cabs_fast(Bv.x, Bv.y), P.eps);
+            const float dm = ma_ - mb_;
+            const float dx = A.x - Bv.x, dy = A.y - Bv.y;
+            acc_mag = fmaf(dm, dm, acc_mag);
+            acc_cplx += fmaf(dx, dx, dy * dy);
+        } else {   // R2C_ISTFT_BWD: grad of irfft = (c_k / N) * FFT, c_k = 1 at DC / Nyquist else 2
+            const float sc = (k == 0 || k == HALF) ? P.sc_edge : P.sc_int;
+            A.x *= sc; A.y *= sc; Bv.x *= sc; Bv.y *= sc;
+#pragma unroll
+            for (int qf = 0; qf < 2; ++qf) {
+                if (qf && !vb) continue;
+                const float2 G = qf ? Bv : A;
+                const size_t o = (qf ? row_b : row_a) + k;
+                if (P.mask) {
+                    // E = X * max(mask, eps)^(1/c)  (apply_mask(compressed=True), stft.py:282-289)
+                    const float2 X = P.xspec[o];
+                    const float mk = P.mask[o];
+                    const float mc = fmaxf(mk, P.eps);
+                    const float inv_c = 1.f / P.c;
+                    const float lin = pow_fast(mc, inv_c);
+                    const float dlin = (mk >= P.eps) ? inv_c * pow_fast(mc, inv_c - 1.f) : 0.f;
+                    P.gmask[o] = (X.x * G.x + X.y * G.y) * dlin;
+                    if (P.spec_a) P.spec_a[o] = make_float2(G.x * lin, G.y * lin);
+                } else {
+                    P.spec_a[o] = G;
+                }
+            }
+        }
+    };
+    const bool l0 = (lane == 0);
+#pragma unroll
+    for (int r = 0; r < C::NA; ++r) {
+        // partner of bin jA + 64 r: butterfly 64 - lane, slot R - 1 - r  (lane 0: own butterfly, slot (R - r) % R)
+        const float2 p0 = XA[(R - r) % R], p1 = XB[R - 1 - r];
+        emit(jA + 64 * r, XA[r], make_float2(l0 ? p0.x : p1.x, l0 ? p0.y : p1.y));
+    }
+#pragma unroll
+    for (int r = 0; r < C::NBN; ++r) {
+        const float2 p0 = XB[R - 1 - r], p1 = XA[R - 1 - r];
+        emit(jB + 64 * r, XB[r], make_float2(l0 ? p0.x : p1.x, l0 ? p0.y : p1.y));
+    }
+    if (l0) {   // the Nyquist bin (self paired)
+        if (C::XTRA_A) emit(64 * C::NA, XA[C::NA], XA[(R - C::NA) % R]);
+        else emit(32 + 64 * C::NBN, XB[C::NBN], XB[R - 1 - C::NBN]);
+    }
+    if (MODE == R2C_MRLOSS) {
+        const float s0 = warp_sum(acc_mag), s1 = warp_sum(acc_cplx);
+        if (l0) {   // 64 accumulator slots per sum: thousands of warps on one address would serialise in L2
+            const int slot_id = (unit + b * 7) & 63;
+            atomicAdd(&P.acc[slot_id], s0);
+            atomicAdd(&P.acc[64 + slot_id], s1);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// one-sided spectra -> windowed real frames -> overlap-add   (hop = N / 2)
+// ------------------------------------------------------------------------------------------------
+template <int R>
+__device__ __forceinline__ void c2r_load_bin(const C2RParams& P, size_t row_a, size_t row_b, bool va, bool vb, int k,
+                                             float2& d, float2& pn) {
+    constexpr int HALF = Cfg<R>::HALF;
+    float2 p = make_float2(0.f, 0.f), q = p;
+    const bool edge = (k == 0 || k == HALF);
+    const float sc0 = edge ? P.sc_edge : P.sc_int;
+    if (va) {
+        p = P.spec[row_a + k];
+        float sc = sc0;
+        if (P.mask) sc *= pow_fast(fmaxf(P.mask[row_a + k], P.eps), 1.f / P.c);
+        p.x *= sc; p.y *= sc;
+    }
+    if (vb) {
+        q = P.spec[row_b + k];
+        float sc = sc0;
+        if (P.mask) sc *= pow_fast(fmaxf(P.mask[row_b + k], P.eps), 1.f / P.c);
+        q.x *= sc; q.y *= sc;
+    }
+    if (edge) { p.y = 0.f; q.y = 0.f; }      // c2r ignores the imaginary part of DC / Nyquist
+    // Z = P + iQ (Hermitian extensions); we transform conj(Z) forward and conjugate the result
+    d = make_float2(p.x - q.y, -(p.y + q.x));     // conj Z[k]
+    pn = make_float2(p.x + q.y, p.y - q.x);       // conj Z[N - k]
+}
+
+template <int R, int MODE, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) c2r_warp_kernel(const C2RParams P) {
+    using C = Cfg<R>;
+    constexpr int N = C::N, HALF = C::HALF, F = HALF + 1;
+    extern __shared__ float2 smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float2* buf = smem + (size_t)warp * C::BUF;
+    float* tails = reinterpret_cast<float*>(smem + (size_t)WARPS * C::BUF);     // [WARPS][HALF]
+    const int b = blockIdx.y;
+    const int s0 = blockIdx.x * (2 * WARPS - 1);      // first overlap-add segment (of HALF samples) this CTA writes
+    const int fa = s0 - 1 + 2 * warp, fb = fa + 1;    // this warp's two frames
+    const bool va = fa >= 0 && fa < P.Tf, vb = fb >= 0 && fb < P.Tf;
+    const size_t row_a = ((size_t)b * P.Tf + (va ? fa : 0)) * F;
+    const size_t row_b = ((size_t)b * P.Tf + (vb ? fb : 0)) * F;
+
+    float2 v[C::U][8];
+    if (va || vb) {
+        float2 UA[R], UB[R];
+        const int jA = lane, jB = lane ? 64 - lane : 32;
+        const bool l0 = (lane == 0);
+        float2 DA[C::NA + 1], PA[C::NA + 1], DB[C::NBN + 1], PB[C::NBN + 1];
+#pragma unroll
+        for (int r = 0; r < C::NA; ++r) c2r_load_bin<R>(P, row_a, row_b, va, vb, jA + 64 * r, DA[r], PA[r]);
+#pragma unroll
+        for (int r = 0; r < C::NBN; ++r) c2r_load_bin<R>(P, row_a, row_b, va, vb, jB + 64 * r, DB[r], PB[r]);
+        DA[C::NA] = PA[C::NA] = DB[C::NBN] = PB[C::NBN] = make_float2(0.f, 0.f);
+        if (l0) {
+            if (C::XTRA_A) c2r_load_bin<R>(P, row_a, row_b, va, vb, 64 * C::NA, DA[C::NA], PA[C::NA]);
+            else c2r_load_bin<R>(P, row_a, row_b, va, vb, 32 + 64 * C::NBN, DB[C::NBN], PB[C::NBN]);
+        }
+        // lanes >= 1: UA[r] = DA[r], UB[R-1-r] = PA[r];  UB[r] = DB[r], UA[R-1-r] = PB[r]
+        // lane 0:     UA[r] = DA[r], UA[R-r]   = PA[r];  UB[r] = DB[r], UB[R-1-r] = PB[r]   (butterflies 0 and 32)
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+            // UA[i]
+            if (i < C::NA) {
+                UA[i] = DA[i];
+            } else {
+                // lanes >= 1: PB[R-1-i];  lane 0: i == NA (even R only): DA[NA] (Nyquist), else PA[R-i]
+                const float2 g = PB[R - 1 - i];
+                const float2 z = (C::XTRA_A && i == C::NA) ? DA[C::NA] : PA[R - i];
+                UA[i] = make_float2(l0 ? z.x : g.x, l0 ? z.y : g.y);
+            }
+            // UB[i]
+            if (i < C::NBN) {
+                UB[i] = DB[i];
+            } else {
+                // lanes >= 1: PA[R-1-i];  lane 0: i == NBN (odd R only): DB[NBN] (Nyquist), else PB[R-1-i]
+                const float2 g = PA[R - 1 - i];
+                const float2 z = (!C::XTRA_A && i == C::NBN) ? DB[C::NBN] : PB[R - 1 - i];
+                UB[i] = make_float2(l0 ? z.x : g.x, l0 ? z.y : g.y);
+            }
+        }
+        fft_dif<R>(UA, UB, v, buf, P.tw, lane);
+    } else {
+#pragma unroll
+        for (int u = 0; u < C::U; ++u)
+#pragma unroll
+            for (int m1 = 0; m1 < 8; ++m1) v[u][m1] = make_float2(0.f, 0.f);
+    }
+    // windowed frames: frame a = Re(conj y) w, frame b = Im(conj y) w = -y.y w.  A missing frame contributes exactly
+    // zero (not the rounding noise of the other frame's transform: the envelope division amplifies it at the edges)
+    const float wsa = va ? 1.f : 0.f, wsb = vb ? -1.f : 0.f;
+#pragma unroll
+    for (int u = 0; u < C::U; ++u)
+#pragma unroll
+        for (int m1 = 0; m1 < 8; ++m1) {
+            if (C::FULL || lane + 32 * u < C::NB) {
+                const float w = __ldg(&P.window[lane + 32 * u + C::NB * m1]);
+                v[u][m1].x *= w * wsa;
+                v[u][m1].y *= w * wsb;
+            }
+        }
+    // second half of frame b is the tail the next warp's first segment needs
+    float* my_tail = tails + (size_t)warp * HALF;
+#pragma unroll
+    for (int u = 0; u < C::U; ++u)
+#pragma unroll
+        for (int m1 = 4; m1 < 8; ++m1)
+            if (C::FULL || lane + 32 * u < C::NB) my_tail[lane + 32 * u + C::NB * (m1 - 4)] = v[u][m1].y;
+    __syncthreads();
+    const float* prev_tail = tails + (size_t)(warp > 0 ? warp - 1 : 0) * HALF;
+    // segment s covers padded positions [s HALF, (s + 1) HALF); sum = first half of frame s + second half of frame s - 1
+#pragma unroll
+    for (int sg = 0; sg < 2; ++sg) {
+        const int s = sg ? fb : fa;
+        if (!sg && warp == 0) continue;                 // belongs to the previous CTA
+        if (s < 0 || s > P.Tf) continue;
+#pragma unroll
+        for (int u = 0; u < C::U; ++u)
+#pragma unroll
+            for (int m1 = 0; m1 < 4; ++m1) {
+                if (!(C::FULL || lane + 32 * u < C::NB)) continue;
+                const int i = lane + 32 * u + C::NB * m1;
+                const float tot = sg ? (v[u][m1].y + v[u][m1 + 4].x) : (v[u][m1].x + prev_tail[i]);
+                const int tp = s * HALF + i;
+                if (MODE == C2R_ISTFT) {
+                    const int t = tp - HALF;
+                    if (t >= 0 && t < P.length) P.out[(size_t)b * P.length + t] = __fdividef(tot, __ldg(&P.env[tp]));
+                } else {
+                    P.out[(size_t)b * P.Ltot + tp] = tot;
+                }
+            }
+    }
+    if (MODE == C2R_ISTFT && s0 + 2 * WARPS - 1 > P.Tf) {
+        // torch.istft zero-fills when `length` runs past the overlap-add buffer
+        for (int t = P.Ltot - HALF + (int)threadIdx.x; t < P.length; t += WARPS * 32)
+            if (t >= 0) P.out[(size_t)b * P.length + t] = 0.f;
+    }
+    (void)N;
+}
+
+}  // namespace wf

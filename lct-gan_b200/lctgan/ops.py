@@ -31,13 +31,13 @@ def fft_supported(n_fft: int) -> bool:
 
 
 def twiddles(n_fft: int, like: torch.Tensor) -> torch.Tensor:
-    """exp(-2 pi i m / N) table, a pure function of (N, device): cached."""
+    """Twiddle tables (see lct_fft_twiddles in include/lctgan.h), a pure function of (N, device): cached."""
     key = (n_fft, _dev_index(like))
     tw = _TW.get(key)
     if tw is None:
         if not fft_supported(n_fft):
             raise RuntimeError(f"n_fft={n_fft} unsupported (need even, 8..2048, prime factors 2/3/5)")
-        tw = torch.empty(n_fft, 2, device=like.device, dtype=torch.float32)
+        tw = torch.empty(call_ret("lct_fft_twiddle_len", n_fft), 2, device=like.device, dtype=torch.float32)
         call("lct_fft_twiddles", tw, n_fft)
         _TW[key] = tw
     return tw
