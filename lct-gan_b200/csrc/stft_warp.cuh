@@ -190,6 +190,25 @@ __device__ __forceinline__ void fft_dif(float2 (&UA)[R], float2 (&UB)[R], float2
 // ------------------------------------------------------------------------------------------------
 constexpr int kR2CWarps = 4;
 
+__device__ __forceinline__ float sqrt_approx(float x) {     // MUFU.SQRT, <= 2 ulp: far inside the 1e-5 front-end tolerance
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float cabs_w(float x, float y) { return sqrt_approx(fmaf(x, x, y * y)); }
+// raw MUFU.EX2 / MUFU.LG2 (no denormal fix-up code: every argument here is >= eps = 1e-12 or a moderate exponent)
+__device__ __forceinline__ float ex2_w(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_w(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float pow_w(float x, float e) { return ex2_w(e * lg2_w(x)); }
+
 template <int R, int MODE>
 __global__ void __launch_bounds__(kR2CWarps * 32) r2c_warp_kernel(const R2CParams P) {
     using C = Cfg<R>;
@@ -211,35 +230,70 @@ __global__ void __launch_bounds__(kR2CWarps * 32) r2c_warp_kernel(const R2CParam
     float2 v[C::U][8];
     {
         const int sa = ma * P.hop - HALF, sb = mb * P.hop - HALF;
-        const bool fast = (MODE != R2C_ISTFT_BWD) && sa >= 0 && sa + N <= P.T && (!vb || (sb >= 0 && sb + N <= P.T));
+        const bool fast = sa >= 0 && sa + N <= P.T && (!vb || (sb >= 0 && sb + N <= P.T));
+        float fa[C::U][8], fb[C::U][8];
+        if (MODE == R2C_ISTFT_BWD) {
+            // adjoint of "slice [N/2, N/2 + T) of the overlap-add buffer, divided by the envelope"
+            const int Ltot = N + P.hop * (P.Tf - 1);
 #pragma unroll
-        for (int u = 0; u < C::U; ++u) {
+            for (int u = 0; u < C::U; ++u)
+#pragma unroll
+                for (int m1 = 0; m1 < 8; ++m1) {
+                    const int n = lane + 32 * u + C::NB * m1;
+                    fa[u][m1] = fb[u][m1] = 0.f;
+                    if (C::FULL || lane + 32 * u < C::NB) {
+                        const int tpa = ma * P.hop + n, ta = tpa - HALF;
+                        if (ta >= 0 && ta < P.T && tpa < Ltot) fa[u][m1] = __fdividef(xa[ta], __ldg(&P.env[tpa]));
+                        const int tpb = mb * P.hop + n, tb = tpb - HALF;
+                        if (vb && tb >= 0 && tb < P.T && tpb < Ltot) fb[u][m1] = __fdividef(xa[tb], __ldg(&P.env[tpb]));
+                    }
+                }
+        } else if (fast) {
+            const float* pa = xa + sa + lane;
+            const float* pb = xb + sb + lane;
+            if (!kPairSig && vb && P.hop == HALF) {
+                // consecutive frames of one signal overlap by half: frame b = [second half of frame a | HALF new samples]
+#pragma unroll
+                for (int u = 0; u < C::U; ++u) {
+                    const bool ok = C::FULL || lane + 32 * u < C::NB;
+#pragma unroll
+                    for (int m1 = 0; m1 < 8; ++m1) fa[u][m1] = ok ? pa[32 * u + C::NB * m1] : 0.f;
+#pragma unroll
+                    for (int m1 = 0; m1 < 4; ++m1) {
+                        fb[u][m1] = fa[u][m1 + 4];
+                        fb[u][m1 + 4] = ok ? pa[32 * u + C::NB * (m1 + 8)] : 0.f;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < C::U; ++u) {
+                    const bool ok = C::FULL || lane + 32 * u < C::NB;
+#pragma unroll
+                    for (int m1 = 0; m1 < 8; ++m1) {
+                        fa[u][m1] = ok ? pa[32 * u + C::NB * m1] : 0.f;
+                        fb[u][m1] = (ok && vb) ? pb[32 * u + C::NB * m1] : 0.f;
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < C::U; ++u)
+#pragma unroll
+                for (int m1 = 0; m1 < 8; ++m1) {
+                    const int n = lane + 32 * u + C::NB * m1;
+                    const bool ok = C::FULL || lane + 32 * u < C::NB;
+                    fa[u][m1] = ok ? reflect_load(xa, P.T, sa + n) : 0.f;
+                    fb[u][m1] = (ok && vb) ? reflect_load(xb, P.T, sb + n) : 0.f;
+                }
+        }
+        const float* pw = P.window + lane;
+#pragma unroll
+        for (int u = 0; u < C::U; ++u)
 #pragma unroll
             for (int m1 = 0; m1 < 8; ++m1) {
-                const int n = lane + 32 * u + C::NB * m1;
-                float fa = 0.f, fb = 0.f;
-                if (C::FULL || lane + 32 * u < C::NB) {
-                    const float w = 0.5f * __ldg(&P.window[n]);
-                    if (MODE == R2C_ISTFT_BWD) {
-                        // adjoint of "slice [N/2, N/2 + T) of the overlap-add buffer, divided by the envelope"
-                        const int Ltot = N + P.hop * (P.Tf - 1);
-                        const int tpa = ma * P.hop + n, ta = tpa - HALF;
-                        if (ta >= 0 && ta < P.T && tpa < Ltot) fa = __fdividef(xa[ta], __ldg(&P.env[tpa]));
-                        const int tpb = mb * P.hop + n, tb = tpb - HALF;
-                        if (vb && tb >= 0 && tb < P.T && tpb < Ltot) fb = __fdividef(xa[tb], __ldg(&P.env[tpb]));
-                    } else if (fast) {
-                        fa = xa[sa + n];
-                        if (vb) fb = xb[sb + n];
-                    } else {
-                        fa = reflect_load(xa, P.T, sa + n);
-                        if (vb) fb = reflect_load(xb, P.T, sb + n);
-                    }
-                    fa *= w;
-                    fb *= w;
-                }
-                v[u][m1] = make_float2(fa, fb);
+                const float w = (C::FULL || lane + 32 * u < C::NB) ? 0.5f * __ldg(pw + 32 * u + C::NB * m1) : 0.f;
+                v[u][m1] = make_float2(fa[u][m1] * w, fb[u][m1] * w);
             }
-        }
     }
     float2 XA[R], XB[R];
     fft_dit<R>(v, XA, XB, buf, P.tw, lane);
@@ -247,73 +301,78 @@ __global__ void __launch_bounds__(kR2CWarps * 32) r2c_warp_kernel(const R2CParam
     // ---- split the two real spectra (thread local) and feed the fused consumers
     const int jA = lane, jB = lane ? 64 - lane : 32;
     const size_t row_a = ((size_t)b * P.Tf + ma) * F;
-    const size_t row_b = ((size_t)b * P.Tf + mb) * F;
+    const size_t dfb = kPairSig ? 0 : F;          // frame b sits one row further (mb = ma + 1)
     float acc_mag = 0.f, acc_cplx = 0.f;
-    auto emit = [&](int k, float2 zk, float2 zn) {
+    const bool l0 = (lane == 0);
+    // o: element offset of the bin in frame a's row;  sc: iSTFT-adjoint scale of the bin
+    auto emit = [&](const size_t o, float2 zk, float2 zn, float sc) {
         float2 A = make_float2(zk.x + zn.x, zk.y - zn.y);
         float2 Bv = make_float2(zk.y + zn.y, zn.x - zk.x);
         if (MODE == R2C_STFT) {
-            P.spec_a[row_a + k] = A;
-            if (P.o0) P.o0[row_a + k] = fmaxf(cabs_fast(A.x, A.y), P.eps);
+            P.spec_a[o] = A;
+            if (P.o0) P.o0[o] = fmaxf(cabs_w(A.x, A.y), P.eps);
             if (vb) {
-                P.spec_a[row_b + k] = Bv;
-                if (P.o0) P.o0[row_b + k] = fmaxf(cabs_fast(Bv.x, Bv.y), P.eps);
+                P.spec_a[o + dfb] = Bv;
+                if (P.o0) P.o0[o + dfb] = fmaxf(cabs_w(Bv.x, Bv.y), P.eps);
             }
         } else if (MODE == R2C_TFF) {
-            const float nm = fmaxf(cabs_fast(A.x, A.y), P.eps);
-            const float cm = fmaxf(cabs_fast(Bv.x, Bv.y), P.eps);
-            const float nmc = pow_fast(nm, P.c);
-            P.o0[row_a + k] = nm;
-            P.o1[row_a + k] = __fdividef(pow_fast(cm, P.c), nmc + P.gamma);
-            P.o2[row_a + k] = nmc;
-            if (P.spec_a) P.spec_a[row_a + k] = A;
-            if (P.spec_b) P.spec_b[row_a + k] = Bv;
+            const float nm = fmaxf(cabs_w(A.x, A.y), P.eps);
+            const float cm = fmaxf(cabs_w(Bv.x, Bv.y), P.eps);
+            const float nmc = pow_w(nm, P.c);
+            P.o0[o] = nm;
+            P.o1[o] = __fdividef(pow_w(cm, P.c), nmc + P.gamma);
+            P.o2[o] = nmc;
+            if (P.spec_a) P.spec_a[o] = A;
+            if (P.spec_b) P.spec_b[o] = Bv;
         } else if (MODE == R2C_MRLOSS) {
-            const float ma_ = fmaxf(cabs_fast(A.x, A.y), P.eps);
-            const float mb_ = fmaxf(cabs_fast(Bv.x, Bv.y), P.eps);
+            const float ma_ = fmaxf(cabs_w(A.x, A.y), P.eps);
+            const float mb_ = fmaxf(cabs_w(Bv.x, Bv.y), P.eps);
             const float dm = ma_ - mb_;
             const float dx = A.x - Bv.x, dy = A.y - Bv.y;
             acc_mag = fmaf(dm, dm, acc_mag);
-            acc_cplx += fmaf(dx, dx, dy * dy);
+            acc_cplx = fmaf(dx, dx, fmaf(dy, dy, acc_cplx));
         } else {   // R2C_ISTFT_BWD: grad of irfft = (c_k / N) * FFT, c_k = 1 at DC / Nyquist else 2
-            const float sc = (k == 0 || k == HALF) ? P.sc_edge : P.sc_int;
             A.x *= sc; A.y *= sc; Bv.x *= sc; Bv.y *= sc;
 #pragma unroll
             for (int qf = 0; qf < 2; ++qf) {
                 if (qf && !vb) continue;
                 const float2 G = qf ? Bv : A;
-                const size_t o = (qf ? row_b : row_a) + k;
+                const size_t oo = qf ? o + dfb : o;
                 if (P.mask) {
                     // E = X * max(mask, eps)^(1/c)  (apply_mask(compressed=True), stft.py:282-289)
-                    const float2 X = P.xspec[o];
-                    const float mk = P.mask[o];
+                    const float2 X = P.xspec[oo];
+                    const float mk = P.mask[oo];
                     const float mc = fmaxf(mk, P.eps);
                     const float inv_c = 1.f / P.c;
-                    const float lin = pow_fast(mc, inv_c);
-                    const float dlin = (mk >= P.eps) ? inv_c * pow_fast(mc, inv_c - 1.f) : 0.f;
-                    P.gmask[o] = (X.x * G.x + X.y * G.y) * dlin;
-                    if (P.spec_a) P.spec_a[o] = make_float2(G.x * lin, G.y * lin);
+                    const float lg = lg2_w(mc);
+                    const float dlin = (mk >= P.eps) ? inv_c * ex2_w((inv_c - 1.f) * lg) : 0.f;
+                    P.gmask[oo] = (X.x * G.x + X.y * G.y) * dlin;
+                    if (P.spec_a) {
+                        const float lin = ex2_w(inv_c * lg);
+                        P.spec_a[oo] = make_float2(G.x * lin, G.y * lin);
+                    }
                 } else {
-                    P.spec_a[o] = G;
+                    P.spec_a[oo] = G;
                 }
             }
         }
     };
-    const bool l0 = (lane == 0);
+    const size_t oA = row_a + (size_t)jA, oB = row_a + (size_t)jB;
 #pragma unroll
     for (int r = 0; r < C::NA; ++r) {
         // partner of bin jA + 64 r: butterfly 64 - lane, slot R - 1 - r  (lane 0: own butterfly, slot (R - r) % R)
         const float2 p0 = XA[(R - r) % R], p1 = XB[R - 1 - r];
-        emit(jA + 64 * r, XA[r], make_float2(l0 ? p0.x : p1.x, l0 ? p0.y : p1.y));
+        emit(oA + 64 * r, XA[r], make_float2(l0 ? p0.x : p1.x, l0 ? p0.y : p1.y),
+             (r == 0 && l0) ? P.sc_edge : P.sc_int);
     }
 #pragma unroll
     for (int r = 0; r < C::NBN; ++r) {
         const float2 p0 = XB[R - 1 - r], p1 = XA[R - 1 - r];
-        emit(jB + 64 * r, XB[r], make_float2(l0 ? p0.x : p1.x, l0 ? p0.y : p1.y));
+        emit(oB + 64 * r, XB[r], make_float2(l0 ? p0.x : p1.x, l0 ? p0.y : p1.y), P.sc_int);
     }
     if (l0) {   // the Nyquist bin (self paired)
-        if (C::XTRA_A) emit(64 * C::NA, XA[C::NA], XA[(R - C::NA) % R]);
-        else emit(32 + 64 * C::NBN, XB[C::NBN], XB[R - 1 - C::NBN]);
+        if (C::XTRA_A) emit(oA + 64 * C::NA, XA[C::NA], XA[(R - C::NA) % R], P.sc_edge);
+        else emit(oB + 64 * C::NBN, XB[C::NBN], XB[R - 1 - C::NBN], P.sc_edge);
     }
     if (MODE == R2C_MRLOSS) {
         const float s0 = warp_sum(acc_mag), s1 = warp_sum(acc_cplx);
@@ -328,23 +387,21 @@ __global__ void __launch_bounds__(kR2CWarps * 32) r2c_warp_kernel(const R2CParam
 // ------------------------------------------------------------------------------------------------
 // one-sided spectra -> windowed real frames -> overlap-add   (hop = N / 2)
 // ------------------------------------------------------------------------------------------------
+// o_a / o_b: element offsets of the bin in frame a's / frame b's row;  sc0: irfft scale of the bin
 template <int R>
-__device__ __forceinline__ void c2r_load_bin(const C2RParams& P, size_t row_a, size_t row_b, bool va, bool vb, int k,
-                                             float2& d, float2& pn) {
-    constexpr int HALF = Cfg<R>::HALF;
+__device__ __forceinline__ void c2r_load_bin(const C2RParams& P, size_t o_a, size_t o_b, bool va, bool vb, bool edge,
+                                             float sc0, float inv_c, float2& d, float2& pn) {
     float2 p = make_float2(0.f, 0.f), q = p;
-    const bool edge = (k == 0 || k == HALF);
-    const float sc0 = edge ? P.sc_edge : P.sc_int;
     if (va) {
-        p = P.spec[row_a + k];
+        p = P.spec[o_a];
         float sc = sc0;
-        if (P.mask) sc *= pow_fast(fmaxf(P.mask[row_a + k], P.eps), 1.f / P.c);
+        if (P.mask) sc *= pow_w(fmaxf(P.mask[o_a], P.eps), inv_c);
         p.x *= sc; p.y *= sc;
     }
     if (vb) {
-        q = P.spec[row_b + k];
+        q = P.spec[o_b];
         float sc = sc0;
-        if (P.mask) sc *= pow_fast(fmaxf(P.mask[row_b + k], P.eps), 1.f / P.c);
+        if (P.mask) sc *= pow_w(fmaxf(P.mask[o_b], P.eps), inv_c);
         q.x *= sc; q.y *= sc;
     }
     if (edge) { p.y = 0.f; q.y = 0.f; }      // c2r ignores the imaginary part of DC / Nyquist
@@ -374,14 +431,19 @@ __global__ void __launch_bounds__(WARPS * 32) c2r_warp_kernel(const C2RParams P)
         const int jA = lane, jB = lane ? 64 - lane : 32;
         const bool l0 = (lane == 0);
         float2 DA[C::NA + 1], PA[C::NA + 1], DB[C::NBN + 1], PB[C::NBN + 1];
+        const float inv_c = 1.f / P.c;
+        const size_t aA = row_a + (size_t)jA, aB = row_a + (size_t)jB, bA = row_b + (size_t)jA, bB = row_b + (size_t)jB;
 #pragma unroll
-        for (int r = 0; r < C::NA; ++r) c2r_load_bin<R>(P, row_a, row_b, va, vb, jA + 64 * r, DA[r], PA[r]);
+        for (int r = 0; r < C::NA; ++r)
+            c2r_load_bin<R>(P, aA + 64 * r, bA + 64 * r, va, vb, r == 0 && l0, (r == 0 && l0) ? P.sc_edge : P.sc_int, inv_c,
+                            DA[r], PA[r]);
 #pragma unroll
-        for (int r = 0; r < C::NBN; ++r) c2r_load_bin<R>(P, row_a, row_b, va, vb, jB + 64 * r, DB[r], PB[r]);
+        for (int r = 0; r < C::NBN; ++r)
+            c2r_load_bin<R>(P, aB + 64 * r, bB + 64 * r, va, vb, false, P.sc_int, inv_c, DB[r], PB[r]);
         DA[C::NA] = PA[C::NA] = DB[C::NBN] = PB[C::NBN] = make_float2(0.f, 0.f);
-        if (l0) {
-            if (C::XTRA_A) c2r_load_bin<R>(P, row_a, row_b, va, vb, 64 * C::NA, DA[C::NA], PA[C::NA]);
-            else c2r_load_bin<R>(P, row_a, row_b, va, vb, 32 + 64 * C::NBN, DB[C::NBN], PB[C::NBN]);
+        if (l0) {   // Nyquist
+            if (C::XTRA_A) c2r_load_bin<R>(P, aA + 64 * C::NA, bA + 64 * C::NA, va, vb, true, P.sc_edge, inv_c, DA[C::NA], PA[C::NA]);
+            else c2r_load_bin<R>(P, aB + 64 * C::NBN, bB + 64 * C::NBN, va, vb, true, P.sc_edge, inv_c, DB[C::NBN], PB[C::NBN]);
         }
         // lanes >= 1: UA[r] = DA[r], UB[R-1-r] = PA[r];  UB[r] = DB[r], UA[R-1-r] = PB[r]
         // lane 0:     UA[r] = DA[r], UA[R-r]   = PA[r];  UB[r] = DB[r], UB[R-1-r] = PB[r]   (butterflies 0 and 32)
@@ -441,20 +503,22 @@ __global__ void __launch_bounds__(WARPS * 32) c2r_warp_kernel(const C2RParams P)
         const int s = sg ? fb : fa;
         if (!sg && warp == 0) continue;                 // belongs to the previous CTA
         if (s < 0 || s > P.Tf) continue;
+        // (iSTFT: output sample t = tp - HALF, so segment 0 is never written and segment s starts at t = (s - 1) HALF)
+        const int t0 = (MODE == C2R_ISTFT) ? (s - 1) * HALF : s * HALF;
+        const int lim = (MODE == C2R_ISTFT) ? P.length : P.Ltot;
+        if (t0 < 0 || t0 >= lim) continue;
+        float* po = P.out + (size_t)b * lim + t0 + lane;
+        const float* pe = P.env + s * HALF + lane;
+        const bool whole = t0 + HALF <= lim;
 #pragma unroll
         for (int u = 0; u < C::U; ++u)
 #pragma unroll
             for (int m1 = 0; m1 < 4; ++m1) {
                 if (!(C::FULL || lane + 32 * u < C::NB)) continue;
-                const int i = lane + 32 * u + C::NB * m1;
-                const float tot = sg ? (v[u][m1].y + v[u][m1 + 4].x) : (v[u][m1].x + prev_tail[i]);
-                const int tp = s * HALF + i;
-                if (MODE == C2R_ISTFT) {
-                    const int t = tp - HALF;
-                    if (t >= 0 && t < P.length) P.out[(size_t)b * P.length + t] = __fdividef(tot, __ldg(&P.env[tp]));
-                } else {
-                    P.out[(size_t)b * P.Ltot + tp] = tot;
-                }
+                const int i = 32 * u + C::NB * m1;            // (+ lane, folded into the pointers)
+                float tot = sg ? (v[u][m1].y + v[u][m1 + 4].x) : (v[u][m1].x + prev_tail[lane + i]);
+                if (MODE == C2R_ISTFT) tot = __fdividef(tot, __ldg(pe + i));
+                if (whole || t0 + lane + i < lim) po[i] = tot;
             }
     }
     if (MODE == C2R_ISTFT && s0 + 2 * WARPS - 1 > P.Tf) {
