@@ -522,7 +522,9 @@ int launch_r2c_warp(R2CParams& P, cudaStream_t st) {
     const bool pair_sig = (MODE == R2C_TFF || MODE == R2C_MRLOSS);
     const int units = pair_sig ? P.Tf : (P.Tf + 1) / 2;
     dim3 grid((unsigned)ceil_div64(units, wf::kR2CWarps), (unsigned)P.B);
-    const size_t smem = (size_t)wf::kR2CWarps * wf::Cfg<R>::BUF * sizeof(float2);
+    const size_t smem = (size_t)wf::kR2CWarps * wf::R2CSmem<R, MODE>::WARP_FLOATS * sizeof(float);
+    int rc = set_smem(wf::r2c_warp_kernel<R, MODE>, smem);
+    if (rc) return rc;
     wf::r2c_warp_kernel<R, MODE><<<grid, wf::kR2CWarps * 32, smem, st>>>(P);
     LCT_RETURN_IF_LAUNCH_FAILED();
     return 0;

@@ -209,13 +209,44 @@ __device__ __forceinline__ float lg2_w(float x) {
 }
 __device__ __forceinline__ float pow_w(float x, float e) { return ex2_w(e * lg2_w(x)); }
 
+__device__ __forceinline__ void cp_async16_w(float* dst, const float* src) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_w() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_w() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Warp-level async copy of the floats g[0, n) into st[ph, ph + n), ph = (address of g mod 16) / 4, as 16-byte cp.async
+// over the enclosing aligned chunks.  Returns false (nothing issued) when those chunks would leave [lo, hi).
+__device__ __forceinline__ bool stage_copy(float* st, const float* g, int n, const float* lo, const float* hi, int lane) {
+    const int ph = (int)(((uintptr_t)g & 15) >> 2);
+    const float* g0 = g - ph;
+    const int nch = (ph + n + 3) >> 2;
+    if (g0 < lo || g0 + 4 * nch > hi) return false;
+    for (int c = lane; c < nch; c += 32) cp_async16_w(st + 4 * c, g0 + 4 * c);
+    return true;
+}
+__device__ __forceinline__ int stage_phase(const void* g) { return (int)(((uintptr_t)g & 15) >> 2); }
+
+// per-warp shared memory (floats) of the r2c kernel: exchange buffer + (iSTFT adjoint) the staged X / mask rows of the
+// warp's two frames, fetched asynchronously at kernel start and consumed by the epilogue
+template <int R, int MODE> struct R2CSmem {
+    static constexpr int F = Cfg<R>::HALF + 1;
+    static constexpr int XS = 4 * F + 8, MK = 2 * F + 10;
+    static constexpr int STAGE = (MODE == R2C_ISTFT_BWD) ? XS + MK : 0;
+    static constexpr int WARP_FLOATS = 2 * Cfg<R>::BUF + STAGE;
+};
+
 template <int R, int MODE>
 __global__ void __launch_bounds__(kR2CWarps * 32) r2c_warp_kernel(const R2CParams P) {
     using C = Cfg<R>;
+    using SM = R2CSmem<R, MODE>;
     constexpr int N = C::N, HALF = C::HALF, F = HALF + 1;
-    extern __shared__ float2 smem[];
+    extern __shared__ __align__(16) float2 smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float2* buf = smem + (size_t)warp * C::BUF;
+    float* wbase = reinterpret_cast<float*>(smem) + (size_t)warp * SM::WARP_FLOATS;
+    float2* buf = reinterpret_cast<float2*>(wbase);
+    float* st = wbase + 2 * C::BUF;
     const int b = blockIdx.y;
     constexpr bool kPairSig = (MODE == R2C_TFF || MODE == R2C_MRLOSS);
     const int unit = blockIdx.x * kR2CWarps + warp;
@@ -223,6 +254,15 @@ __global__ void __launch_bounds__(kR2CWarps * 32) r2c_warp_kernel(const R2CParam
     const int mb = kPairSig ? unit : ma + 1;
     if (ma >= P.Tf) return;                      // warp uniform; no CTA barrier below
     const bool vb = mb < P.Tf;
+    bool staged = false;
+    if (MODE == R2C_ISTFT_BWD && P.mask && vb) {
+        // the epilogue's X and mask rows (frames ma, ma + 1: contiguous) start travelling now, behind the transform
+        const size_t row = ((size_t)b * P.Tf + ma) * F, tot = (size_t)P.B * P.Tf * F;
+        const float* xs = reinterpret_cast<const float*>(P.xspec);
+        staged = stage_copy(st, xs + 2 * row, 4 * F, xs, xs + 2 * tot, lane) &&
+                 stage_copy(st + SM::XS, P.mask + row, 2 * F, P.mask, P.mask + tot, lane);
+        cp_async_commit_w();
+    }
     const float* xa = P.a + (size_t)b * P.T;
     const float* xb = kPairSig ? P.b + (size_t)b * P.T : xa;
 
@@ -232,7 +272,29 @@ __global__ void __launch_bounds__(kR2CWarps * 32) r2c_warp_kernel(const R2CParam
         const int sa = ma * P.hop - HALF, sb = mb * P.hop - HALF;
         const bool fast = sa >= 0 && sa + N <= P.T && (!vb || (sb >= 0 && sb + N <= P.T));
         float fa[C::U][8], fb[C::U][8];
-        if (MODE == R2C_ISTFT_BWD) {
+        if (MODE == R2C_ISTFT_BWD && vb && P.hop == HALF && sa >= 0 && sa + 3 * HALF <= P.T) {
+            // interior pair of frames (every sample inside [0, T), hence inside the overlap-add buffer): 3 half frames of
+            // gy / envelope, all loads issued before the first division
+            const float* pg = xa + sa + lane;
+            const float* pe = P.env + ma * P.hop + lane;
+#pragma unroll
+            for (int u = 0; u < C::U; ++u) {
+                const bool ok = C::FULL || lane + 32 * u < C::NB;
+                float g[12], e[12];
+#pragma unroll
+                for (int m1 = 0; m1 < 12; ++m1) {
+                    g[m1] = ok ? pg[32 * u + C::NB * m1] : 0.f;
+                    e[m1] = ok ? __ldg(pe + 32 * u + C::NB * m1) : 1.f;
+                }
+#pragma unroll
+                for (int m1 = 0; m1 < 12; ++m1) g[m1] = __fdividef(g[m1], e[m1]);
+#pragma unroll
+                for (int m1 = 0; m1 < 8; ++m1) {
+                    fa[u][m1] = g[m1];
+                    fb[u][m1] = g[m1 + 4];
+                }
+            }
+        } else if (MODE == R2C_ISTFT_BWD) {
             // adjoint of "slice [N/2, N/2 + T) of the overlap-add buffer, divided by the envelope"
             const int Ltot = N + P.hop * (P.Tf - 1);
 #pragma unroll
@@ -304,6 +366,14 @@ __global__ void __launch_bounds__(kR2CWarps * 32) r2c_warp_kernel(const R2CParam
     const size_t dfb = kPairSig ? 0 : F;          // frame b sits one row further (mb = ma + 1)
     float acc_mag = 0.f, acc_cplx = 0.f;
     const bool l0 = (lane == 0);
+    const float2* sx = nullptr;
+    const float* smk = nullptr;
+    if (MODE == R2C_ISTFT_BWD) {
+        cp_async_wait_w();
+        __syncwarp();
+        sx = reinterpret_cast<const float2*>(st + stage_phase(P.xspec + row_a));
+        smk = st + SM::XS + stage_phase(P.mask + row_a);
+    }
     // o: element offset of the bin in frame a's row;  sc: iSTFT-adjoint scale of the bin
     auto emit = [&](const size_t o, float2 zk, float2 zn, float sc) {
         float2 A = make_float2(zk.x + zn.x, zk.y - zn.y);
@@ -340,8 +410,8 @@ __global__ void __launch_bounds__(kR2CWarps * 32) r2c_warp_kernel(const R2CParam
                 const size_t oo = qf ? o + dfb : o;
                 if (P.mask) {
                     // E = X * max(mask, eps)^(1/c)  (apply_mask(compressed=True), stft.py:282-289)
-                    const float2 X = P.xspec[oo];
-                    const float mk = P.mask[oo];
+                    const float2 X = staged ? sx[oo - row_a] : P.xspec[oo];
+                    const float mk = staged ? smk[oo - row_a] : P.mask[oo];
                     const float mc = fmaxf(mk, P.eps);
                     const float inv_c = 1.f / P.c;
                     const float lg = lg2_w(mc);
@@ -387,23 +457,15 @@ __global__ void __launch_bounds__(kR2CWarps * 32) r2c_warp_kernel(const R2CParam
 // ------------------------------------------------------------------------------------------------
 // one-sided spectra -> windowed real frames -> overlap-add   (hop = N / 2)
 // ------------------------------------------------------------------------------------------------
-// o_a / o_b: element offsets of the bin in frame a's / frame b's row;  sc0: irfft scale of the bin
-template <int R>
-__device__ __forceinline__ void c2r_load_bin(const C2RParams& P, size_t o_a, size_t o_b, bool va, bool vb, bool edge,
-                                             float sc0, float inv_c, float2& d, float2& pn) {
-    float2 p = make_float2(0.f, 0.f), q = p;
-    if (va) {
-        p = P.spec[o_a];
-        float sc = sc0;
-        if (P.mask) sc *= pow_w(fmaxf(P.mask[o_a], P.eps), inv_c);
-        p.x *= sc; p.y *= sc;
+// scale, mask and combine the raw bins p (frame a) and q (frame b) into conj Z[k] and conj Z[N - k]
+__device__ __forceinline__ void c2r_combine(float2 p, float2 q, float mka, float mkb, bool has_mask, float eps, float inv_c,
+                                            float sca, float scb, bool edge, float2& d, float2& pn) {
+    if (has_mask) {
+        sca *= pow_w(fmaxf(mka, eps), inv_c);
+        scb *= pow_w(fmaxf(mkb, eps), inv_c);
     }
-    if (vb) {
-        q = P.spec[o_b];
-        float sc = sc0;
-        if (P.mask) sc *= pow_w(fmaxf(P.mask[o_b], P.eps), inv_c);
-        q.x *= sc; q.y *= sc;
-    }
+    p.x *= sca; p.y *= sca;
+    q.x *= scb; q.y *= scb;
     if (edge) { p.y = 0.f; q.y = 0.f; }      // c2r ignores the imaginary part of DC / Nyquist
     // Z = P + iQ (Hermitian extensions); we transform conj(Z) forward and conjugate the result
     d = make_float2(p.x - q.y, -(p.y + q.x));     // conj Z[k]
@@ -432,18 +494,42 @@ __global__ void __launch_bounds__(WARPS * 32) c2r_warp_kernel(const C2RParams P)
         const bool l0 = (lane == 0);
         float2 DA[C::NA + 1], PA[C::NA + 1], DB[C::NBN + 1], PB[C::NBN + 1];
         const float inv_c = 1.f / P.c;
-        const size_t aA = row_a + (size_t)jA, aB = row_a + (size_t)jB, bA = row_b + (size_t)jA, bB = row_b + (size_t)jB;
+        const bool has_mask = P.mask != nullptr;
+        // all loads first (unconditional: a missing frame reads row 0 of the batch and is scaled by 0), then the math:
+        // the kernel is bound by HBM latency, so every lane keeps its 2 x (NA + NBN + 1) bins in flight at once
+        constexpr int NBIN = C::NA + C::NBN + 1;       // A side | B side | Nyquist (read by every lane, used by lane 0)
+        const float2* sa_ = P.spec + row_a;
+        const float2* sb_ = P.spec + row_b;
+        const float* ma_ = has_mask ? P.mask + row_a : nullptr;
+        const float* mb_ = has_mask ? P.mask + row_b : nullptr;
+        float2 rp[NBIN], rq[NBIN];
+        float rma[NBIN], rmb[NBIN];
 #pragma unroll
-        for (int r = 0; r < C::NA; ++r)
-            c2r_load_bin<R>(P, aA + 64 * r, bA + 64 * r, va, vb, r == 0 && l0, (r == 0 && l0) ? P.sc_edge : P.sc_int, inv_c,
-                            DA[r], PA[r]);
+        for (int i = 0; i < NBIN; ++i) {
+            const int k = (i < C::NA) ? jA + 64 * i : (i < C::NA + C::NBN ? jB + 64 * (i - C::NA) : HALF);
+            rp[i] = sa_[k];
+            rq[i] = sb_[k];
+            rma[i] = has_mask ? ma_[k] : 1.f;
+            rmb[i] = has_mask ? mb_[k] : 1.f;
+        }
+        const float za = va ? 1.f : 0.f, zb = vb ? 1.f : 0.f;
+        const float si_a = P.sc_int * za, si_b = P.sc_int * zb, se_a = P.sc_edge * za, se_b = P.sc_edge * zb;
+#pragma unroll
+        for (int r = 0; r < C::NA; ++r) {
+            const bool edge = (r == 0) && l0;
+            c2r_combine(rp[r], rq[r], rma[r], rmb[r], has_mask, P.eps, inv_c, edge ? se_a : si_a, edge ? se_b : si_b, edge,
+                        DA[r], PA[r]);
+        }
 #pragma unroll
         for (int r = 0; r < C::NBN; ++r)
-            c2r_load_bin<R>(P, aB + 64 * r, bB + 64 * r, va, vb, false, P.sc_int, inv_c, DB[r], PB[r]);
-        DA[C::NA] = PA[C::NA] = DB[C::NBN] = PB[C::NBN] = make_float2(0.f, 0.f);
-        if (l0) {   // Nyquist
-            if (C::XTRA_A) c2r_load_bin<R>(P, aA + 64 * C::NA, bA + 64 * C::NA, va, vb, true, P.sc_edge, inv_c, DA[C::NA], PA[C::NA]);
-            else c2r_load_bin<R>(P, aB + 64 * C::NBN, bB + 64 * C::NBN, va, vb, true, P.sc_edge, inv_c, DB[C::NBN], PB[C::NBN]);
+            c2r_combine(rp[C::NA + r], rq[C::NA + r], rma[C::NA + r], rmb[C::NA + r], has_mask, P.eps, inv_c, si_a, si_b,
+                        false, DB[r], PB[r]);
+        {   // Nyquist (lane 0 only uses it)
+            float2 d, pn;
+            c2r_combine(rp[NBIN - 1], rq[NBIN - 1], rma[NBIN - 1], rmb[NBIN - 1], has_mask, P.eps, inv_c, se_a, se_b, true, d, pn);
+            DA[C::NA] = PA[C::NA] = DB[C::NBN] = PB[C::NBN] = make_float2(0.f, 0.f);
+            if (C::XTRA_A) { DA[C::NA] = d; PA[C::NA] = pn; }
+            else { DB[C::NBN] = d; PB[C::NBN] = pn; }
         }
         // lanes >= 1: UA[r] = DA[r], UB[R-1-r] = PA[r];  UB[r] = DB[r], UA[R-1-r] = PB[r]
         // lane 0:     UA[r] = DA[r], UA[R-r]   = PA[r];  UB[r] = DB[r], UB[R-1-r] = PB[r]   (butterflies 0 and 32)
