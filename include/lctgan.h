@@ -146,6 +146,7 @@ LCT_API int lct_dense_wgrad(const void* dyq, const void* xq, float* dw, int64_t 
  * C[M,N] = act(alpha * op(A) op(B) + bias) (+C); out2 = C + res.  ta: A(m,k)=A[k*lda+m]; tb: B(k,n)=B[k*ldb+n] else B[n*ldb+k].
  * Batched over z: A += (z/a_div)*sA, B += (z/b_div)*sB, C/bias/res/out2 += z*s.  ksplit>1: split-K with atomic adds. */
 LCT_API int lct_gemm(const float* A, const float* B, float* C, const float* bias, const float* res, float* out2, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int64_t ldr, int64_t ldo, int ta, int tb, int act, float slope, float alpha, int accumulate, int64_t ksplit, int64_t nbatch, int64_t a_div, int64_t b_div, int64_t sA, int64_t sB, int64_t sC, int64_t sBias, int64_t sRes, int64_t sOut2, cudaStream_t stream);
+LCT_API int lct_set_rowgemm(int on);            /* 1 (default): NT/NN GEMMs with aligned operands run on the fp32-accurate 3xTF32 tensor-core row GEMM (rowgemm.cu); 0: fp32 SIMT */
 LCT_API int lct_set_tensor_core_gemm(int on);   /* 1: lct_gemm runs on TF32 mma.sync (experimental, slower on the skinny generator shapes); 0 (default): fp32 SIMT */
 LCT_API int lct_colsum(const float* X, float* out, int64_t M, int64_t N, int64_t ld, cudaStream_t stream);   /* out[N] += column sums (bias gradients) */
 /* nn.LayerNorm(C) over rows [M,C] (generator.py:126, :132, :238, :244, :577). */
@@ -168,6 +169,13 @@ LCT_API int lct_act_bwd(const float* y, const float* dy, float* dpre, int64_t n,
  * channels-last [B,T,F,C]; each is also the other's data gradient (gmul: multiply by act'(gmul)). */
 LCT_API int lct_gconv(const float* in, const float* w, const float* bias, float* out, const float* gmul, int transposed, int64_t B, int64_t Ti, int64_t Fi, int64_t Cs, int64_t To, int64_t Fo, int64_t Cd, int act, float slope, int gact, float gslope, cudaStream_t stream);
 /* dW[Ca][Cc][2][3] += sum S[b,t,f,a] * Lg[b,t+kt-1,2f+kf-1,c]  (conv: S=dOut, Lg=in; deconv: S=in, Lg=dOut). */
+/* Implicit row-GEMM form of lct_gconv on the tensor cores (3xTF32, fp32-level accuracy; rowgemm.cu).
+ * lct_gconv_weight_image re-arranges a [Cd][Cs][2][3] (transposed = 0) or [Cs][Cd][2][3] (transposed = 1) weight into
+ * the [K][Cd] image(s) the kernel reads (lct_gconv_image_len floats); lct_gconv_mma then equals lct_gconv. */
+LCT_API int lct_gconv_mma_supported(int64_t Cs, int64_t Cd);
+LCT_API int lct_gconv_image_len(int64_t Cs, int64_t Cd);
+LCT_API int lct_gconv_weight_image(const float* w, float* img, int transposed, int64_t Cs, int64_t Cd, cudaStream_t stream);
+LCT_API int lct_gconv_mma(const float* in, const float* img, const float* bias, float* out, const float* gmul, int transposed, int64_t B, int64_t Ti, int64_t Fi, int64_t Cs, int64_t To, int64_t Fo, int64_t Cd, int act, float slope, int gact, float gslope, cudaStream_t stream);
 LCT_API int lct_gconv_wgrad(const float* S, const float* Lg, float* dW, int64_t B, int64_t Ts, int64_t Fs, int64_t Ca, int64_t Tl, int64_t Fl, int64_t Cc, cudaStream_t stream);
 /* h[:, :To, :Fo] + skipN(mag)[:, :To, :Fo] with skipN the 1x1 Conv2d(1->C) (generator.py:484-498, :587-598). */
 LCT_API int lct_skip_add_fwd(const float* h, const float* mag, const float* w, const float* bias, float* out, int64_t B, int64_t Th, int64_t Fh, int64_t Tm, int64_t Fm, int64_t C, cudaStream_t stream);

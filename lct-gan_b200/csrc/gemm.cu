@@ -256,8 +256,22 @@ __global__ void __launch_bounds__(MB_THREADS, 4) gemm_mma_kernel(const GemmParam
 }
 
 int g_gemm_tensor_cores = 0;   // measured slower than the SIMT kernel on the generator's shapes (tools/bench_gemm.py): opt-in
+int g_rowgemm = 1;             // route eligible NT / NN GEMMs to the 3xTF32 row GEMM (rowgemm.cu)
 
 }  // namespace
+
+// rowgemm.cu: launches the 3xTF32 tensor-core row GEMM if the operands qualify (returns 1 and sets *rc), else 0
+int lct_rowgemm_try(const float* A, const float* B, float* C, const float* bias, const float* res, float* out2, int64_t M,
+                    int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int64_t ldr, int64_t ldo, int ta, int tb,
+                    int act, float slope, float alpha, int accumulate, int64_t ksplit, int64_t nbatch, int64_t a_div,
+                    int64_t b_div, int64_t sA, int64_t sB, int64_t sC, int64_t sBias, int64_t sRes, int64_t sOut2,
+                    cudaStream_t st, int* rc);
+
+// 1 (default): NT / NN GEMMs run on the fp32-accurate 3xTF32 row GEMM; 0: fp32 SIMT kernel for everything
+LCT_API int lct_set_rowgemm(int on) {
+    g_rowgemm = on ? 1 : 0;
+    return 0;
+}
 
 // 0 (default): fp32 SIMT GEMM; 1: TF32 mma.sync GEMM (experimental: slower on the generator's skinny shapes)
 LCT_API int lct_set_tensor_core_gemm(int on) {
@@ -277,6 +291,12 @@ LCT_API int lct_gemm(const float* A, const float* B, float* C, const float* bias
         return LCT_EINVAL;
     if (ksplit > 1 && (bias || res || out2 || act != LCT_ACT_NONE || accumulate)) return LCT_EINVAL;
     if (nbatch * ksplit >= 65536) return LCT_EINVAL;
+    if (g_rowgemm && !g_gemm_tensor_cores) {
+        int rc = 0;
+        if (lct_rowgemm_try(A, B, C, bias, res, out2, M, N, K, lda, ldb, ldc, ldr, ldo, ta, tb, act, slope, alpha, accumulate,
+                            ksplit, nbatch, a_div, b_div, sA, sB, sC, sBias, sRes, sOut2, st, &rc))
+            return rc;
+    }
     GemmParams p;
     p.A = A; p.B = B; p.C = C; p.bias = bias; p.res = res; p.out2 = out2;
     p.M = (int)M; p.N = (int)N; p.K = (int)K;

@@ -1,0 +1,380 @@
+// "Row GEMM" on the tensor cores with fp32-level accuracy (3xTF32 error-compensated mma.sync):
+//
+//     C[m, n] = epilogue( sum_k A(m, k) * W(k, n) ),   m < M (34 056 positions at B = 8), n <= 64 per CTA, K = 16 .. 384
+//
+// for the generator's row operators (reference models/generator.py):
+//   * nn.Linear / GRU input projections / attention in- and out-projections and their data gradients
+//     (GRUblockf :104, :133, :138; GRUblockt :219, :245, :248): A(m, :) is a contiguous row;
+//   * encoder Conv2d(k=(2,3), s=(1,2), p=(1,1)) (:461-481) and decoder ConvTranspose2d (:506-529) on channels-last
+//     activations, and each as the data gradient of the other: A(m, :) is gathered on the fly from 2 contiguous runs
+//     (one per time tap: 3 C_s floats for the convolution; C_s / 2 C_s floats for the even / odd output columns of
+//     the transposed convolution) - an implicit GEMM, no im2col buffer.
+//
+// Why this shape: the SIMT kernels these replace were bound by one shared-memory load per FMA (gconv: 190 us for
+// 0.84 GFLOP) or by scalar staging (gemm: 19-73 us for 17-35 MB).  The problems are HBM-sized (3-6 us), so the goal
+// is simply "few issue slots per byte": 128-row tiles staged with 16-byte cp.async (double buffered over K chunks of
+// 32), fragments read conflict free, and every product computed as a_hi b_hi + a_hi b_lo + a_lo b_hi in TF32 with fp32
+// accumulation, which keeps the fp32 parity tolerances (error ~2^-21 per product) at a third of the tensor rate -
+// still far below the memory time.
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128, BN = 64, BK = 32, kThreads = 128;
+constexpr int AS = BK + 4;        // A tile row stride: (4 g + t) mod 32 distinct for g < 8, t < 4
+constexpr int WS_T = BN + 8;      // W tile [k][n] row stride: (8 t + g) mod 32 distinct
+constexpr int WS_N = BK + 4;      // W tile [n][k] row stride
+constexpr int kStages = 2;
+
+enum { RG_LINEAR = 0, RG_CONV = 1, RG_DECONV = 2 };
+
+struct RowGemmParams {
+    const float* A; const float* W; float* C;
+    const float* bias; const float* res; float* out2; const float* gmul;
+    int M, N, K;
+    int lda, ldb, ldc, ldr, ldo, ldg;
+    int tb;                         // W(k, n) = W[k * ldb + n] if tb else W[n * ldb + k]
+    int act; float slope; float alpha; int gact; float gslope;
+    int nbatch, a_div, b_div;
+    int64_t sA, sB, sC, sBias, sRes, sOut2;
+    // gather geometry (RG_CONV / RG_DECONV): in [B, Ti, Fi, Cs] -> out [B, To, Fo, N]
+    int B, Ti, Fi, Cs, To, Fo;
+    int M1, K1;                     // RG_DECONV: rows / K of the odd-column problem (blockIdx.z = 1); W1 its weights
+    const float* W1;
+};
+
+__device__ __forceinline__ void cp16(float* dst, const float* src, bool valid) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+    const int n = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(v));
+    const float r = v - __uint_as_float(hi);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+}
+__device__ __forceinline__ void mma8(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+struct RowMeta {       // per tile row: where its A runs start (element offsets), which are valid, where its output row is
+    int off0, off1;
+    int c0;            // first input column of the runs (may be -1)
+    int flags;         // bit 0: run 0 row valid, bit 1: run 1 row valid, bit 2: row < M
+    int orow;          // output row
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) rowgemm_kernel(const RowGemmParams p) {
+    extern __shared__ __align__(16) float sm[];
+    float* As = sm;                                          // [kStages][BM][AS]
+    float* Wsm = As + kStages * BM * AS;                     // [kStages][max(BK * WS_T, BN * WS_N)]
+    constexpr int WTILE = (BK * WS_T > BN * WS_N) ? BK * WS_T : BN * WS_N;
+    RowMeta* meta = reinterpret_cast<RowMeta*>(Wsm + kStages * WTILE);   // [BM]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int gq = lane >> 2, tq = lane & 3;
+    const int z = blockIdx.z;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+
+    int M = p.M, K = p.K;
+    const float* A = p.A;
+    const float* W = p.W;
+    float* C = p.C;
+    const float* bias = p.bias;
+    const float* res = p.res;
+    float* out2 = p.out2;
+    int par = 0;
+    if (MODE == RG_LINEAR) {
+        A += (int64_t)(z / p.a_div) * p.sA;
+        W += (int64_t)(z / p.b_div) * p.sB;
+        C += (int64_t)z * p.sC;
+        if (bias) bias += (int64_t)z * p.sBias;
+        if (res) res += (int64_t)z * p.sRes;
+        if (out2) out2 += (int64_t)z * p.sOut2;
+    } else if (MODE == RG_DECONV) {
+        par = z;
+        if (par) { M = p.M1; K = p.K1; W = p.W1; }
+    }
+    if (m0 >= M) return;
+
+    // ---- row metadata
+    const int Cs = p.Cs;
+    const int RL = (MODE == RG_CONV) ? 3 * Cs : (MODE == RG_DECONV ? (par ? 2 * Cs : Cs) : K);   // run length (floats)
+    for (int r = tid; r < BM; r += kThreads) {
+        RowMeta mt;
+        const int m = m0 + r;
+        mt.off0 = mt.off1 = 0; mt.c0 = 0; mt.flags = 0; mt.orow = 0;
+        if (m < M) {
+            if (MODE == RG_LINEAR) {
+                mt.off0 = m * p.lda;
+                mt.flags = 1 | 4;
+                mt.orow = m;
+            } else if (MODE == RG_CONV) {
+                const int f = m % p.Fo, bt = m / p.Fo, t = bt % p.To, b = bt / p.To;
+                mt.c0 = 2 * f - 1;
+                const int t0 = t - 1, t1 = t;
+                mt.off0 = ((b * p.Ti + t0) * p.Fi + mt.c0) * Cs;
+                mt.off1 = ((b * p.Ti + t1) * p.Fi + mt.c0) * Cs;
+                mt.flags = ((t0 >= 0 && t0 < p.Ti) ? 1 : 0) | ((t1 >= 0 && t1 < p.Ti) ? 2 : 0) | 4;
+                mt.orow = m;
+            } else {
+                const int Fp = par ? p.Fo / 2 : (p.Fo + 1) / 2;      // output columns of this parity
+                const int fh = m % Fp, bt = m / Fp, t = bt % p.To, b = bt / p.To;
+                mt.c0 = fh;
+                const int t0 = t + 1, t1 = t;                        // kt = 0, 1  ->  input row t + 1 - kt
+                mt.off0 = ((b * p.Ti + t0) * p.Fi + fh) * Cs;
+                mt.off1 = ((b * p.Ti + t1) * p.Fi + fh) * Cs;
+                mt.flags = ((t0 >= 0 && t0 < p.Ti) ? 1 : 0) | ((t1 >= 0 && t1 < p.Ti) ? 2 : 0) | 4;
+                mt.orow = (b * p.To + t) * p.Fo + 2 * fh + par;
+            }
+        }
+        meta[r] = mt;
+    }
+    __syncthreads();
+
+    const int nk = (K + BK - 1) / BK;
+    auto stage = [&](int kc, int sbuf) {
+        const int k0 = kc * BK;
+        float* as = As + sbuf * BM * AS;
+        // A: 128 rows x 8 chunks of 16 bytes; 8 consecutive threads cover 128 contiguous bytes of one row
+#pragma unroll
+        for (int i = 0; i < (BM * BK / 4) / kThreads; ++i) {
+            const int e = tid + i * kThreads;
+            const int r = e >> 3, c4 = e & 7;
+            const int k = k0 + 4 * c4;
+            const RowMeta mt = meta[r];
+            bool ok = (k < K) && (mt.flags & 4);
+            const float* src = A;
+            if (MODE == RG_LINEAR) {
+                src = A + mt.off0 + k;
+            } else {
+                const int run = (k >= RL) ? 1 : 0;
+                const int j = k - run * RL;
+                const int tap = j / Cs;
+                ok = ok && ((mt.flags >> run) & 1) && ((unsigned)(mt.c0 + tap) < (unsigned)p.Fi);
+                src = A + (run ? mt.off1 : mt.off0) + j;
+            }
+            cp16(as + r * AS + 4 * c4, ok ? src : A, ok);
+        }
+        float* ws = Wsm + sbuf * WTILE;
+        if (p.tb) {      // [k][n]: 32 rows x 16 chunks
+#pragma unroll
+            for (int i = 0; i < (BK * BN / 4) / kThreads; ++i) {
+                const int e = tid + i * kThreads;
+                const int kr = e >> 4, c4 = e & 15;
+                const int k = k0 + kr, n = n0 + 4 * c4;
+                const bool ok = (k < K) && (n < p.N);        // N is a multiple of 4 on this path
+                cp16(ws + kr * WS_T + 4 * c4, ok ? W + (int64_t)k * p.ldb + n : W, ok);
+            }
+        } else {         // [n][k]: 64 rows x 8 chunks
+#pragma unroll
+            for (int i = 0; i < (BN * BK / 4) / kThreads; ++i) {
+                const int e = tid + i * kThreads;
+                const int nr = e >> 3, c4 = e & 7;
+                const int k = k0 + 4 * c4, n = n0 + nr;
+                const bool ok = (k < K) && (n < p.N);
+                cp16(ws + nr * WS_N + 4 * c4, ok ? W + (int64_t)n * p.ldb + k : W, ok);
+            }
+        }
+    };
+
+    const int ntiles = min(BN / 8, (p.N - n0 + 7) / 8);      // n-tiles holding real columns (CTA uniform)
+    float acc[2][BN / 8][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < BN / 8; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
+
+    stage(0, 0);
+    cp_commit();
+    for (int kc = 0; kc < nk; ++kc) {
+        const int cur = kc & 1;
+        if (kc + 1 < nk) stage(kc + 1, cur ^ 1);
+        cp_commit();
+        cp_wait<1>();
+        __syncthreads();
+        const float* as = As + cur * BM * AS + (warp * 32) * AS;
+        const float* ws = Wsm + cur * WTILE;
+        const int ksteps = min(BK, K - kc * BK) >> 3;
+        for (int ks = 0; ks < ksteps; ++ks) {
+            const int kk = ks * 8;
+            uint32_t ah[2][4], al[2][4];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                const float* ar = as + (mt * 16 + gq) * AS + kk + tq;
+                split_tf32(ar[0], ah[mt][0], al[mt][0]);
+                split_tf32(ar[8 * AS], ah[mt][1], al[mt][1]);
+                split_tf32(ar[4], ah[mt][2], al[mt][2]);
+                split_tf32(ar[8 * AS + 4], ah[mt][3], al[mt][3]);
+            }
+#pragma unroll
+            for (int nt = 0; nt < BN / 8; ++nt) {
+                if (nt < ntiles) {
+                    float w0, w1;
+                    if (p.tb) {
+                        w0 = ws[(kk + tq) * WS_T + nt * 8 + gq];
+                        w1 = ws[(kk + tq + 4) * WS_T + nt * 8 + gq];
+                    } else {
+                        w0 = ws[(nt * 8 + gq) * WS_N + kk + tq];
+                        w1 = ws[(nt * 8 + gq) * WS_N + kk + tq + 4];
+                    }
+                    uint32_t bh0, bl0, bh1, bl1;
+                    split_tf32(w0, bh0, bl0);
+                    split_tf32(w1, bh1, bl1);
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt) {
+                        mma8(acc[mt][nt], al[mt], bh0, bh1);      // small terms first
+                        mma8(acc[mt][nt], ah[mt], bl0, bl1);
+                        mma8(acc[mt][nt], ah[mt], bh0, bh1);
+                    }
+                }
+            }
+        }
+        __syncthreads();      // everyone done with stage `cur` before it is refilled
+    }
+
+    // ---- epilogue: thread holds rows (gq, gq + 8) of two m-tiles, columns nt * 8 + 2 tq + {0, 1}
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const RowMeta rm = meta[warp * 32 + mt * 16 + gq + 8 * h];
+            if (!(rm.flags & 4)) continue;
+            const int64_t orow = rm.orow;
+#pragma unroll
+            for (int nt = 0; nt < BN / 8; ++nt) {
+                if (nt >= ntiles) continue;
+                const int gn = n0 + nt * 8 + 2 * tq;
+                if (gn >= p.N) continue;          // N is even on this path
+                float v0 = acc[mt][nt][2 * h] * p.alpha, v1 = acc[mt][nt][2 * h + 1] * p.alpha;
+                if (bias) { v0 += bias[gn]; v1 += bias[gn + 1]; }
+                v0 = apply_act(v0, p.act, p.slope);
+                v1 = apply_act(v1, p.act, p.slope);
+                if (p.gmul) {
+                    const float2 g = *reinterpret_cast<const float2*>(p.gmul + orow * p.ldg + gn);
+                    v0 *= act_grad_from_out(g.x, p.gact, p.gslope);
+                    v1 *= act_grad_from_out(g.y, p.gact, p.gslope);
+                }
+                *reinterpret_cast<float2*>(C + orow * p.ldc + gn) = make_float2(v0, v1);
+                if (out2) {
+                    float2 r2 = make_float2(0.f, 0.f);
+                    if (res) r2 = *reinterpret_cast<const float2*>(res + orow * p.ldr + gn);
+                    *reinterpret_cast<float2*>(out2 + orow * p.ldo + gn) = make_float2(v0 + r2.x, v1 + r2.y);
+                }
+            }
+        }
+}
+
+constexpr size_t smem_bytes() {
+    constexpr int WTILE = (BK * WS_T > BN * WS_N) ? BK * WS_T : BN * WS_N;
+    return (size_t)(kStages * BM * AS + kStages * WTILE) * sizeof(float) + BM * sizeof(RowMeta);
+}
+
+template <int MODE>
+int launch(const RowGemmParams& p, int64_t m_max, int gz, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(rowgemm_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes());
+        if (e != cudaSuccess) return (int)e;
+        attr = true;
+    }
+    dim3 grid((unsigned)ceil_div64(m_max, BM), (unsigned)ceil_div64(p.N, BN), (unsigned)gz);
+    rowgemm_kernel<MODE><<<grid, kThreads, smem_bytes(), st>>>(p);
+    LCT_RETURN_IF_LAUNCH_FAILED();
+    return 0;
+}
+
+bool al16(const void* q) { return ((uintptr_t)q & 15) == 0; }
+bool al8(const void* q) { return ((uintptr_t)q & 7) == 0; }
+
+// weight images for the gather forms: conv  img[(kt, kf, s)][d] = w[d][s][kt][kf];
+// deconv even columns img0[(kt, s)][d] = w[s][d][kt][1];  odd columns img1[(kt, e, s)][d] = w[s][d][kt][e ? 0 : 2]
+__global__ void gconv_image_kernel(const float* __restrict__ w, float* __restrict__ img, int Cs, int Cd, int transposed) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 6 * Cs * Cd) return;
+    const int d = idx % Cd;
+    int r = idx / Cd;
+    if (!transposed) {
+        const int s = r % Cs; r /= Cs;
+        const int kf = r % 3, kt = r / 3;
+        img[idx] = w[((size_t)(d * Cs + s) * 2 + kt) * 3 + kf];
+    } else if (r < 2 * Cs) {
+        const int s = r % Cs, kt = r / Cs;
+        img[idx] = w[((size_t)(s * Cd + d) * 2 + kt) * 3 + 1];
+    } else {
+        r -= 2 * Cs;
+        const int s = r % Cs; r /= Cs;
+        const int e = r % 2, kt = r / 2;
+        img[idx] = w[((size_t)(s * Cd + d) * 2 + kt) * 3 + (e ? 0 : 2)];
+    }
+}
+
+}  // namespace
+
+// 1 if lct_rowgemm covers this GEMM (otherwise use lct_gemm's SIMT kernel).  Called by lct_gemm itself.
+int lct_rowgemm_try(const float* A, const float* B, float* C, const float* bias, const float* res, float* out2, int64_t M,
+                    int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int64_t ldr, int64_t ldo, int ta, int tb,
+                    int act, float slope, float alpha, int accumulate, int64_t ksplit, int64_t nbatch, int64_t a_div,
+                    int64_t b_div, int64_t sA, int64_t sB, int64_t sC, int64_t sBias, int64_t sRes, int64_t sOut2,
+                    cudaStream_t st, int* rc) {
+    if (ta || accumulate || ksplit != 1) return 0;
+    if ((K & 7) || (N & 3) || (lda & 3) || (ldb & 3) || (ldc & 1) || (sA & 3) || (sB & 3) || (sC & 1)) return 0;
+    if (!al16(A) || !al16(B) || !al8(C) || M * lda >= (1LL << 31) || nbatch >= 65536) return 0;
+    if (out2 && (!al8(out2) || (ldo & 1) || (sOut2 & 1))) return 0;
+    if (res && (!al8(res) || (ldr & 1) || (sRes & 1))) return 0;
+    RowGemmParams p = {};
+    p.A = A; p.W = B; p.C = C; p.bias = bias; p.res = res; p.out2 = out2;
+    p.M = (int)M; p.N = (int)N; p.K = (int)K;
+    p.lda = (int)lda; p.ldb = (int)ldb; p.ldc = (int)ldc; p.ldr = (int)ldr; p.ldo = (int)ldo;
+    p.tb = tb; p.act = act; p.slope = slope; p.alpha = alpha;
+    p.nbatch = (int)nbatch; p.a_div = (int)a_div; p.b_div = (int)b_div;
+    p.sA = sA; p.sB = sB; p.sC = sC; p.sBias = sBias; p.sRes = sRes; p.sOut2 = sOut2;
+    *rc = launch<RG_LINEAR>(p, M, (int)nbatch, st);
+    return 1;
+}
+
+// Number of floats of the weight image lct_gconv_weight_image writes (6 * Cs * Cd).
+LCT_API int lct_gconv_image_len(int64_t Cs, int64_t Cd) { return (int)(6 * Cs * Cd); }
+
+// transposed = 0: w [Cd][Cs][2][3] (Conv2d weight, or a ConvTranspose2d weight used for its data gradient);
+// transposed = 1: w [Cs][Cd][2][3].  img: 6 * Cs * Cd floats.
+LCT_API int lct_gconv_weight_image(const float* w, float* img, int transposed, int64_t Cs, int64_t Cd, cudaStream_t st) {
+    if (!w || !img || Cs <= 0 || Cd <= 0) return LCT_EINVAL;
+    const int n = (int)(6 * Cs * Cd);
+    gconv_image_kernel<<<(n + 255) / 256, 256, 0, st>>>(w, img, (int)Cs, (int)Cd, transposed);
+    LCT_RETURN_IF_LAUNCH_FAILED();
+    return 0;
+}
+
+// 1 if lct_gconv_mma covers the layer: Cs a multiple of 4 (16-byte taps), Cd a multiple of 4 up to 64
+LCT_API int lct_gconv_mma_supported(int64_t Cs, int64_t Cd) { return (Cs >= 4 && (Cs & 3) == 0 && Cd >= 8 && (Cd & 3) == 0 && Cd <= 64) ? 1 : 0; }
+
+// Same operator as lct_gconv (gen_conv.cu) through the implicit row GEMM; img from lct_gconv_weight_image.
+LCT_API int lct_gconv_mma(const float* in, const float* img, const float* bias, float* out, const float* gmul,
+                          int transposed, int64_t B, int64_t Ti, int64_t Fi, int64_t Cs, int64_t To, int64_t Fo, int64_t Cd,
+                          int act, float slope, int gact, float gslope, cudaStream_t st) {
+    if (!in || !img || !out || B <= 0 || Ti <= 0 || Fi <= 0 || To <= 0 || Fo <= 0 || !lct_gconv_mma_supported(Cs, Cd))
+        return LCT_EINVAL;
+    if (!al16(in) || !al16(img) || !al8(out) || (gmul && !al8(gmul))) return LCT_EUNSUPPORTED;
+    if (B * Ti * Fi * Cs >= (1LL << 31) || B * To * Fo * Cd >= (1LL << 31)) return LCT_EUNSUPPORTED;
+    RowGemmParams p = {};
+    p.A = in; p.C = out; p.bias = bias; p.gmul = gmul;
+    p.N = (int)Cd; p.ldb = (int)Cd; p.ldc = (int)Cd; p.ldg = (int)Cd; p.tb = 1;
+    p.act = act; p.slope = slope; p.alpha = 1.f; p.gact = gact; p.gslope = gslope;
+    p.B = (int)B; p.Ti = (int)Ti; p.Fi = (int)Fi; p.Cs = (int)Cs; p.To = (int)To; p.Fo = (int)Fo;
+    if (!transposed) {
+        p.W = img; p.M = (int)(B * To * Fo); p.K = (int)(6 * Cs);
+        return launch<RG_CONV>(p, p.M, 1, st);
+    }
+    p.W = img; p.M = (int)(B * To * ((Fo + 1) / 2)); p.K = (int)(2 * Cs);
+    p.W1 = img + 2 * Cs * Cd; p.M1 = (int)(B * To * (Fo / 2)); p.K1 = (int)(4 * Cs);
+    return launch<RG_DECONV>(p, p.M > p.M1 ? p.M : p.M1, 2, st);
+}

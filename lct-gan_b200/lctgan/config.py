@@ -7,12 +7,20 @@ dense_tensor_cores = True
 
 
 def set_precision(mode: str) -> None:
-    """"bf16": tensor-core path for the dense contraction (default); "fp32": fp32 SIMT kernels only."""
-    global dense_tensor_cores
+    """"bf16": tensor-core paths (default): tcgen05 bf16 dense contraction, TF32 grouped discriminator convolutions,
+    3xTF32 (error-compensated, ~fp32 accuracy) generator GEMMs / convolutions; "fp32": fp32 SIMT kernels only."""
+    global dense_tensor_cores, gconv_tensor_cores
     if mode not in ("bf16", "fp32"):
         raise ValueError(f"unknown precision mode {mode!r}")
     dense_tensor_cores = (mode == "bf16")
+    gconv_tensor_cores = dense_tensor_cores
+    from ._lib import call_ret
+    call_ret("lct_set_rowgemm", int(dense_tensor_cores))
 
+
+#: Generator encoder / decoder convolutions as implicit row GEMMs on the tensor cores (3xTF32 error-compensated, fp32-level
+#: accuracy, rowgemm.cu).  False = the SIMT kernels of gen_conv.cu.
+gconv_tensor_cores = True
 
 #: Run the independent sub-discriminators (5 periods, 3 scales) on parallel CUDA streams (forked from and joined
 #: to the caller's stream; autograd replays the same streams in backward).  Each sub-discriminator is a chain of

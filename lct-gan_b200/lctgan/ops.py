@@ -404,6 +404,13 @@ def gconv(x, w, bias, out_tf, cd, transposed, act=ACT_NONE, slope=0.2, gmul=None
     B, Ti, Fi, Cs = x.shape
     To, Fo = out_tf
     out = torch.empty(B, To, Fo, cd, dtype=torch.float32, device=x.device)
+    if config.gconv_tensor_cores and call_ret("lct_gconv_mma_supported", Cs, cd):
+        # implicit row GEMM on the tensor cores (3xTF32: fp32-level accuracy); the weight image is a 6*Cs*Cd re-arrangement
+        img = torch.empty(call_ret("lct_gconv_image_len", Cs, cd), dtype=torch.float32, device=x.device)
+        call("lct_gconv_weight_image", w, img, int(transposed), Cs, cd)
+        call("lct_gconv_mma", x, img, bias, out, gmul, int(transposed), B, Ti, Fi, Cs, To, Fo, cd, act, slope, gact,
+             gslope)
+        return out
     call("lct_gconv", x, w, bias, out, gmul, int(transposed), B, Ti, Fi, Cs, To, Fo, cd, act, slope, gact, gslope)
     return out
 
