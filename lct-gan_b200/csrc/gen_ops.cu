@@ -28,6 +28,14 @@ __device__ __forceinline__ int64_t seq_row0(const SeqGeom& g, int seq) {
 }
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+// Gate non-linearities of the GRU recurrence: they sit on the serial per-step dependency chain (33 / 129 steps), so they
+// are written on MUFU.EX2 / MUFU.RCP (4 dependent instructions) instead of expf / tanhf / IEEE division (~60):
+// absolute error ~1e-7, inside the 2e-5 parity bar of the recurrence tests.
+__device__ __forceinline__ float gate_sigmoid(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float gate_tanh(float x) {
+    const float e = __expf(-2.f * fabsf(x));              // in (0, 1]: no overflow
+    return copysignf(__fdividef(1.f - e, 1.f + e), x);
+}
 
 // ------------------------------------------------------------------------------------------
 // LayerNorm over the last dim (C <= 256), one warp per row
@@ -133,6 +141,90 @@ __global__ void ln_bwd_kernel(const float* __restrict__ dy, const float* __restr
     }
 }
 
+// C = 64 (the generator's only width): half a warp per row with 16-byte accesses, the next row pair prefetched while
+// the current one is reduced, parameter gradients kept in registers across rows and reduced once per CTA.
+struct LnRow { float4 d, x, r; float mu, rs; };
+
+__global__ void __launch_bounds__(256) ln_bwd64_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                       const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                       const float* __restrict__ rstd, const float* __restrict__ dres,
+                                                       float* __restrict__ dx, float* __restrict__ dgamma,
+                                                       float* __restrict__ dbeta, int M) {
+    const int lane = threadIdx.x & 31, sub = lane & 15, half = lane >> 4, warp = threadIdx.x >> 5;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int step = 2 * ((gridDim.x * blockDim.x) >> 5);
+    const float4 gm = reinterpret_cast<const float4*>(gamma)[sub];
+    float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag;
+    auto load = [&](int row) {
+        LnRow v;
+        v.d = v.x = v.r = make_float4(0.f, 0.f, 0.f, 0.f);
+        v.mu = 0.f; v.rs = 0.f;
+        if (row < M) {
+            const size_t o = (size_t)row * 16 + sub;
+            v.d = reinterpret_cast<const float4*>(dy)[o];
+            v.x = reinterpret_cast<const float4*>(x)[o];
+            if (dres) v.r = reinterpret_cast<const float4*>(dres)[o];
+            v.mu = mean[row];
+            v.rs = rstd[row];
+        }
+        return v;
+    };
+    int base = 2 * gw;
+    LnRow cur = load(base + half);
+    for (; base < M; base += step) {
+        const LnRow nxt = load(base + step + half);
+        const int row = base + half;
+        float4 xh, g;
+        xh.x = (cur.x.x - cur.mu) * cur.rs; xh.y = (cur.x.y - cur.mu) * cur.rs;
+        xh.z = (cur.x.z - cur.mu) * cur.rs; xh.w = (cur.x.w - cur.mu) * cur.rs;
+        g.x = cur.d.x * gm.x; g.y = cur.d.y * gm.y; g.z = cur.d.z * gm.z; g.w = cur.d.w * gm.w;
+        ag.x = fmaf(cur.d.x, xh.x, ag.x); ag.y = fmaf(cur.d.y, xh.y, ag.y);
+        ag.z = fmaf(cur.d.z, xh.z, ag.z); ag.w = fmaf(cur.d.w, xh.w, ag.w);
+        ab.x += cur.d.x; ab.y += cur.d.y; ab.z += cur.d.z; ab.w += cur.d.w;
+        float s1 = (g.x + g.y) + (g.z + g.w);
+        float s2 = fmaf(g.x, xh.x, g.y * xh.y) + fmaf(g.z, xh.z, g.w * xh.w);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        s1 *= (1.f / 64.f);
+        s2 *= (1.f / 64.f);
+        if (row < M) {
+            float4 v;
+            v.x = cur.rs * (g.x - s1 - xh.x * s2) + cur.r.x;
+            v.y = cur.rs * (g.y - s1 - xh.y * s2) + cur.r.y;
+            v.z = cur.rs * (g.z - s1 - xh.z * s2) + cur.r.z;
+            v.w = cur.rs * (g.w - s1 - xh.w * s2) + cur.r.w;
+            reinterpret_cast<float4*>(dx)[(size_t)row * 16 + sub] = v;
+        }
+        cur = nxt;
+    }
+    // the two rows of the warp, then the 8 warps of the CTA, then one atomic per channel per CTA
+    __shared__ float red[8][128];
+    float a[4] = {ag.x, ag.y, ag.z, ag.w}, bsum[4] = {ab.x, ab.y, ab.z, ab.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        a[i] += __shfl_xor_sync(0xffffffffu, a[i], 16);
+        bsum[i] += __shfl_xor_sync(0xffffffffu, bsum[i], 16);
+    }
+    if (half == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            red[warp][4 * sub + i] = a[i];
+            red[warp][64 + 4 * sub + i] = bsum[i];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        float t = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < 8; ++wv) t += red[wv][threadIdx.x];
+        if (threadIdx.x < 64) atomicAdd(&dgamma[threadIdx.x], t);
+        else atomicAdd(&dbeta[threadIdx.x - 64], t);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // GRU recurrence.  gi: [rows, GD, 48] = W_ih x + b_ih (gates r,z,n), whh: [GD,48,16], bhh: [GD,48],
 // hs: [rows, GD, 16].  GD = groups * dirs, dir = gd % D, dir 1 runs the sequence backwards.
@@ -140,6 +232,7 @@ __global__ void ln_bwd_kernel(const float* __restrict__ dy, const float* __restr
 constexpr int kH = 16;
 constexpr int kGruThreads = 256;
 constexpr int kUnitsPerCta = kGruThreads / kH;
+constexpr int kGruPre = 6;     // recurrence steps whose inputs are in flight
 
 __global__ void __launch_bounds__(kGruThreads) gru_fwd_kernel(const float* __restrict__ gi,
                                                               const float* __restrict__ whh,
@@ -162,34 +255,52 @@ __global__ void __launch_bounds__(kGruThreads) gru_fwd_kernel(const float* __res
     const int64_t row0 = valid ? seq_row0(geo, seq) : 0;
     const int64_t gstride = (int64_t)GD * 3 * kH;
     float h = 0.f;
-    int step = rev ? geo.L - 1 : 0;
+    const int step0 = rev ? geo.L - 1 : 0;
     const int dstep = rev ? -1 : 1;
-    float gr = 0.f, gz = 0.f, gn = 0.f;
-    if (valid) {
-        const float* g0 = gi + (row0 + (int64_t)step * geo.step_stride) * gstride + gd * 3 * kH;
-        gr = g0[j]; gz = g0[kH + j]; gn = g0[2 * kH + j];
-    }
-    for (int s = 0; s < geo.L; ++s, step += dstep) {
-        const int64_t row = row0 + (int64_t)step * geo.step_stride;
-        float ngr = 0.f, ngz = 0.f, ngn = 0.f;
-        if (valid && s + 1 < geo.L) {   // prefetch the next step's input projection
-            const float* g1 = gi + (row + (int64_t)dstep * geo.step_stride) * gstride + gd * 3 * kH;
-            ngr = g1[j]; ngz = g1[kH + j]; ngn = g1[2 * kH + j];
-        }
-        float hr = br, hz = bz, hn = bn;
+    // The input projections of the next kGruPre steps travel while the current step is computed: a step is ~250 cycles
+    // of dependent math, an L2 hit costs 600+, so a one-step look-ahead left every step waiting on its load.
+    float pr[kGruPre], pz[kGruPre], pn[kGruPre];
+    const float* gbase = gi + (row0 + (int64_t)step0 * geo.step_stride) * gstride + gd * 3 * kH + j;
+    const int64_t gstep = (int64_t)dstep * geo.step_stride * gstride;
 #pragma unroll
-        for (int i = 0; i < kH; ++i) {
-            const float hi = __shfl_sync(0xffffffffu, h, i, kH);
-            hr = fmaf(wr[i], hi, hr);
-            hz = fmaf(wz[i], hi, hz);
-            hn = fmaf(wn[i], hi, hn);
+    for (int u = 0; u < kGruPre; ++u) {
+        pr[u] = pz[u] = pn[u] = 0.f;
+        if (valid && u < geo.L) {
+            const float* g0 = gbase + u * gstep;
+            pr[u] = g0[0]; pz[u] = g0[kH]; pn[u] = g0[2 * kH];
         }
-        const float r = sigmoidf_(gr + hr);
-        const float z = sigmoidf_(gz + hz);
-        const float n = tanhf(gn + r * hn);
-        h = (1.f - z) * n + z * h;
-        if (valid) hs[(row * GD + gd) * kH + j] = h;
-        gr = ngr; gz = ngz; gn = ngn;
+    }
+    float* hrow = hs + ((row0 + (int64_t)step0 * geo.step_stride) * GD + gd) * kH + j;
+    const int64_t hstep = (int64_t)dstep * geo.step_stride * GD * kH;
+    for (int s0 = 0; s0 < geo.L; s0 += kGruPre) {
+#pragma unroll
+        for (int u = 0; u < kGruPre; ++u) {
+            const int s = s0 + u;
+            if (s >= geo.L) break;
+            const float gr = pr[u], gz = pz[u], gn = pn[u];
+            if (valid && s + kGruPre < geo.L) {
+                const float* g1 = gbase + (int64_t)(s + kGruPre) * gstep;
+                pr[u] = g1[0]; pz[u] = g1[kH]; pn[u] = g1[2 * kH];
+            }
+            float hr = br, hz = bz, hn = bn, hr2 = 0.f, hz2 = 0.f, hn2 = 0.f;      // two partial sums per gate: half the chain
+#pragma unroll
+            for (int i = 0; i < kH; i += 2) {
+                const float hi = __shfl_sync(0xffffffffu, h, i, kH);
+                const float hj = __shfl_sync(0xffffffffu, h, i + 1, kH);
+                hr = fmaf(wr[i], hi, hr);
+                hz = fmaf(wz[i], hi, hz);
+                hn = fmaf(wn[i], hi, hn);
+                hr2 = fmaf(wr[i + 1], hj, hr2);
+                hz2 = fmaf(wz[i + 1], hj, hz2);
+                hn2 = fmaf(wn[i + 1], hj, hn2);
+            }
+            hr += hr2; hz += hz2; hn += hn2;
+            const float r = gate_sigmoid(gr + hr);
+            const float z = gate_sigmoid(gz + hz);
+            const float n = gate_tanh(gn + r * hn);
+            h = (1.f - z) * n + z * h;
+            if (valid) hrow[(int64_t)s * hstep] = h;
+        }
     }
 }
 
@@ -228,15 +339,28 @@ __global__ void __launch_bounds__(kGruThreads) gru_bwd_kernel(
     int step = rev ? 0 : geo.L - 1;
     const int dstep = rev ? 1 : -1;   // direction of "previous forward step"
     float dh = 0.f;
-    for (int s = geo.L - 1; s >= 0; --s, step += dstep) {
-        const int64_t row = row0 + (int64_t)step * geo.step_stride;
-        float gr = 0.f, gz = 0.f, gn = 0.f, hp = 0.f, dout = 0.f;
-        if (valid) {
-            const float* g0 = gi + row * gstride + gd * 3 * kH;
-            gr = g0[j]; gz = g0[kH + j]; gn = g0[2 * kH + j];
-            if (s > 0) hp = hs[((row + (int64_t)dstep * geo.step_stride) * GD + gd) * kH + j];
-            dout = dh_in[row * ldd + col];
+    // inputs of the next kGruPre steps in flight (see gru_fwd_kernel); it counts steps walked: s = L - 1 - it
+    float qr[kGruPre], qz[kGruPre], qn[kGruPre], qh[kGruPre], qd[kGruPre];
+    auto fetch = [&](int it, float& a, float& b, float& c, float& hpq, float& dq) {
+        a = b = c = hpq = dq = 0.f;
+        if (valid && it < geo.L) {
+            const int64_t rw = row0 + (int64_t)(step + it * dstep) * geo.step_stride;
+            const float* g0 = gi + rw * gstride + gd * 3 * kH;
+            a = g0[j]; b = g0[kH + j]; c = g0[2 * kH + j];
+            if (it < geo.L - 1) hpq = hs[((rw + (int64_t)dstep * geo.step_stride) * GD + gd) * kH + j];
+            dq = dh_in[rw * ldd + col];
         }
+    };
+#pragma unroll
+    for (int u = 0; u < kGruPre; ++u) fetch(u, qr[u], qz[u], qn[u], qh[u], qd[u]);
+    for (int it0 = 0; it0 < geo.L; it0 += kGruPre) {
+#pragma unroll
+    for (int u = 0; u < kGruPre; ++u) {
+        const int it = it0 + u;
+        if (it >= geo.L) break;
+        const int64_t row = row0 + (int64_t)(step + it * dstep) * geo.step_stride;
+        const float gr = qr[u], gz = qz[u], gn = qn[u], hp = qh[u], dout = qd[u];
+        fetch(it + kGruPre, qr[u], qz[u], qn[u], qh[u], qd[u]);
         float hpv[kH];
         float hr = br, hz = bz, hn = bn;
 #pragma unroll
@@ -246,9 +370,9 @@ __global__ void __launch_bounds__(kGruThreads) gru_bwd_kernel(
             hz = fmaf(wz[i], hpv[i], hz);
             hn = fmaf(wn[i], hpv[i], hn);
         }
-        const float r = sigmoidf_(gr + hr);
-        const float z = sigmoidf_(gz + hz);
-        const float n = tanhf(gn + r * hn);
+        const float r = gate_sigmoid(gr + hr);
+        const float z = gate_sigmoid(gz + hz);
+        const float n = gate_tanh(gn + r * hn);
         const float dht = dh + dout;
         const float dn_pre = dht * (1.f - z) * (1.f - n * n);
         const float dz_pre = dht * (hp - n) * z * (1.f - z);
@@ -281,6 +405,7 @@ __global__ void __launch_bounds__(kGruThreads) gru_bwd_kernel(
             }
         }
         dh = dht * z + c[0];
+    }
     }
     __syncthreads();
     if (valid) {
@@ -496,6 +621,14 @@ LCT_API int lct_layernorm_bwd(const float* dy, const float* x, const float* gamm
     if (!dy || !x || !gamma || !mean || !rstd || !dx || !dgamma || !dbeta || M <= 0 || C <= 0 ||
         C > 32 * kLnMaxPerLane)
         return LCT_EINVAL;
+    const auto al16 = [](const void* q) { return ((uintptr_t)q & 15) == 0; };
+    if (C == 64 && al16(dy) && al16(x) && al16(dx) && al16(gamma) && (!dres || al16(dres))) {
+        int64_t ctas = ceil_div64(M, 16);
+        if (ctas > 148 * 3) ctas = 148 * 3;
+        ln_bwd64_kernel<<<(unsigned)ctas, 256, 0, st>>>(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, (int)M);
+        LCT_RETURN_IF_LAUNCH_FAILED();
+        return 0;
+    }
     int64_t blocks = ceil_div64(M * 32, 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
     ln_bwd_kernel<<<(unsigned)blocks, 256, 0, st>>>(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, (int)M, (int)C);

@@ -20,7 +20,7 @@
 
 namespace {
 
-constexpr int BM = 128, BN = 64, BK = 32, kThreads = 128;
+constexpr int BM = 64, BN = 64, BK = 32, kThreads = 128;   // 2 x 2 warps, warp tile 32 x 32
 constexpr int AS = BK + 4;        // A tile row stride: (4 g + t) mod 32 distinct for g < 8, t < 4
 constexpr int WS_T = BN + 8;      // W tile [k][n] row stride: (8 t + g) mod 32 distinct
 constexpr int WS_N = BK + 4;      // W tile [n][k] row stride
@@ -57,7 +57,7 @@ __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) 
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
 }
 __device__ __forceinline__ void mma8(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile(
+    asm(
         "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
         : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
@@ -184,12 +184,14 @@ __global__ void __launch_bounds__(kThreads) rowgemm_kernel(const RowGemmParams p
         }
     };
 
-    const int ntiles = min(BN / 8, (p.N - n0 + 7) / 8);      // n-tiles holding real columns (CTA uniform)
-    float acc[2][BN / 8][4];
+    const int wm = warp >> 1, wn = warp & 1;
+    constexpr int WNT = BN / 16;                             // n-tiles per warp (4)
+    const int ntiles = min(WNT, max(0, (p.N - n0 - wn * 32 + 7) / 8));   // n-tiles of this warp holding real columns
+    float acc[2][WNT][4];
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int nt = 0; nt < BN / 8; ++nt)
+        for (int nt = 0; nt < WNT; ++nt)
 #pragma unroll
             for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
 
@@ -201,7 +203,7 @@ __global__ void __launch_bounds__(kThreads) rowgemm_kernel(const RowGemmParams p
         cp_commit();
         cp_wait<1>();
         __syncthreads();
-        const float* as = As + cur * BM * AS + (warp * 32) * AS;
+        const float* as = As + cur * BM * AS + (wm * 32) * AS;
         const float* ws = Wsm + cur * WTILE;
         const int ksteps = min(BK, K - kc * BK) >> 3;
         for (int ks = 0; ks < ksteps; ++ks) {
@@ -215,28 +217,37 @@ __global__ void __launch_bounds__(kThreads) rowgemm_kernel(const RowGemmParams p
                 split_tf32(ar[4], ah[mt][2], al[mt][2]);
                 split_tf32(ar[8 * AS + 4], ah[mt][3], al[mt][3]);
             }
+            uint32_t bh[WNT][2], bl[WNT][2];
 #pragma unroll
-            for (int nt = 0; nt < BN / 8; ++nt) {
-                if (nt < ntiles) {
-                    float w0, w1;
-                    if (p.tb) {
-                        w0 = ws[(kk + tq) * WS_T + nt * 8 + gq];
-                        w1 = ws[(kk + tq + 4) * WS_T + nt * 8 + gq];
-                    } else {
-                        w0 = ws[(nt * 8 + gq) * WS_N + kk + tq];
-                        w1 = ws[(nt * 8 + gq) * WS_N + kk + tq + 4];
-                    }
-                    uint32_t bh0, bl0, bh1, bl1;
-                    split_tf32(w0, bh0, bl0);
-                    split_tf32(w1, bh1, bl1);
-#pragma unroll
-                    for (int mt = 0; mt < 2; ++mt) {
-                        mma8(acc[mt][nt], al[mt], bh0, bh1);      // small terms first
-                        mma8(acc[mt][nt], ah[mt], bl0, bl1);
-                        mma8(acc[mt][nt], ah[mt], bh0, bh1);
-                    }
+            for (int nt = 0; nt < WNT; ++nt) {
+                const int nc = wn * 32 + nt * 8 + gq;
+                float w0, w1;
+                if (p.tb) {
+                    w0 = ws[(kk + tq) * WS_T + nc];
+                    w1 = ws[(kk + tq + 4) * WS_T + nc];
+                } else {
+                    w0 = ws[nc * WS_N + kk + tq];
+                    w1 = ws[nc * WS_N + kk + tq + 4];
                 }
+                split_tf32(w0, bh[nt][0], bl[nt][0]);
+                split_tf32(w1, bh[nt][1], bl[nt][1]);
             }
+            // the three partial products of every (m-tile, n-tile) as three sweeps: dependent mmas sit 8 apart
+#pragma unroll
+            for (int nt = 0; nt < WNT; ++nt)
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+                    if (nt < ntiles) mma8(acc[mt][nt], al[mt], bh[nt][0], bh[nt][1]);      // small terms first
+#pragma unroll
+            for (int nt = 0; nt < WNT; ++nt)
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+                    if (nt < ntiles) mma8(acc[mt][nt], ah[mt], bl[nt][0], bl[nt][1]);
+#pragma unroll
+            for (int nt = 0; nt < WNT; ++nt)
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt)
+                    if (nt < ntiles) mma8(acc[mt][nt], ah[mt], bh[nt][0], bh[nt][1]);
         }
         __syncthreads();      // everyone done with stage `cur` before it is refilled
     }
@@ -246,13 +257,13 @@ __global__ void __launch_bounds__(kThreads) rowgemm_kernel(const RowGemmParams p
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const RowMeta rm = meta[warp * 32 + mt * 16 + gq + 8 * h];
+            const RowMeta rm = meta[wm * 32 + mt * 16 + gq + 8 * h];
             if (!(rm.flags & 4)) continue;
             const int64_t orow = rm.orow;
 #pragma unroll
-            for (int nt = 0; nt < BN / 8; ++nt) {
+            for (int nt = 0; nt < WNT; ++nt) {
                 if (nt >= ntiles) continue;
-                const int gn = n0 + nt * 8 + 2 * tq;
+                const int gn = n0 + wn * 32 + nt * 8 + 2 * tq;
                 if (gn >= p.N) continue;          // N is even on this path
                 float v0 = acc[mt][nt][2 * h] * p.alpha, v1 = acc[mt][nt][2 * h + 1] * p.alpha;
                 if (bias) { v0 += bias[gn]; v1 += bias[gn + 1]; }
