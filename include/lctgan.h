@@ -131,6 +131,7 @@ LCT_API int lct_conv_post_dgrad(const float* dy, const float* w, float* dx, cons
 /* The dense layer MSD convs.5 (Conv1d 1024->1024, k=5, s=1; discriminators.py:166-196) on tcgen05 tensor cores:
  * bf16 operands staged once per call, fp32 accumulation in TMEM, TMA-fed implicit GEMM (no im2col).
  * lct_dense_supported: 1 if (Cin, Cout multiples of 128, odd K <= 8) and the driver exposes cuTensorMapEncodeTiled. */
+LCT_API int lct_dense_tile_n(int bn);   /* conv-form output tile width: 0 auto (default), 64, 128 */
 LCT_API int lct_dense_supported(int64_t Cin, int64_t Cout, int64_t K);
 LCT_API int lct_dense_debug(int stage);   /* bring-up aid: 0 = normal; 1..3 run only the first stages of the kernel */
 LCT_API int lct_stage_nlc_bf16(const float* x, void* out, int64_t B, int64_t C, int64_t L, int64_t pad, cudaStream_t stream);   /* [B,C,L] f32 -> [B,L+2pad,C] bf16, zero rows between batches */

@@ -272,6 +272,7 @@ int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uin
 }
 
 int g_dense_debug = 0;
+int g_dense_bn = 0;      // output-tile width of the conv form: 0 auto, 64, 128
 
 template <int BN, int STAGES, int EPI>
 int launch_dense(const CUtensorMap& a, const CUtensorMap& b, DenseParams& p, dim3 grid, cudaStream_t st) {
@@ -357,6 +358,13 @@ LCT_API int lct_dense_debug(int stage) {
     return 0;
 }
 
+// conv-form tile width: 0 = auto (default), 64 or 128 (A/B measurements)
+LCT_API int lct_dense_tile_n(int bn) {
+    if (bn != 0 && bn != 64 && bn != 128) return LCT_EINVAL;
+    g_dense_bn = bn;
+    return 0;
+}
+
 LCT_API int lct_dense_supported(int64_t Cin, int64_t Cout, int64_t K) {
     return (Cin % 128 == 0 && Cout % 128 == 0 && K >= 1 && K <= 8 && (K & 1) && get_encode() != nullptr) ? 1 : 0;
 }
@@ -404,14 +412,20 @@ LCT_API int lct_dense_conv(const void* a, const void* w, const float* bias, cons
     CUtensorMap ma, mb;
     int rc = make_map(&ma, a, (uint64_t)R, (uint64_t)Ca, (uint64_t)Ca, BM);
     if (rc) return rc;
-    rc = make_map(&mb, w, (uint64_t)(K * Cn), (uint64_t)Ca, (uint64_t)Ca, 64);
+    // 128 x 128 tiles move 16 KB of operands per 128 x 64 x 64 MACs instead of 24 KB (the layer is bound by the
+    // aggregate L2 -> SM throughput, not by the tensor pipe); 128 x 64 tiles when that would leave SMs without a tile
+    const int64_t mt = ceil_div64(R, BM);
+    int bn = g_dense_bn;
+    if (!bn) bn = (mt * (Cn / 128) >= 100) ? 128 : 64;
+    rc = make_map(&mb, w, (uint64_t)(K * Cn), (uint64_t)Ca, (uint64_t)Ca, (uint32_t)bn);
     if (rc) return rc;
     DenseParams p = {};
     p.kdiv = (int)(Ca / BK); p.nkb = (int)(K * p.kdiv);
     p.a0 = 0; p.a_step1 = 1; p.b0 = 0; p.b_step1 = (int)Cn;
     p.R = (int)R; p.Lp = (int)Lp; p.L = (int)L; p.Cn = (int)Cn;
     p.bias = bias; p.gextra = gextra; p.xact = xact; p.act = act; p.slope = slope; p.out = out;
-    dim3 grid((unsigned)ceil_div64(R, BM), (unsigned)(Cn / 64), 1);
+    dim3 grid((unsigned)mt, (unsigned)(Cn / bn), 1);
+    if (bn == 128) return launch_dense<128, 5, EPI_CONV>(ma, mb, p, grid, st);
     return launch_dense<64, 6, EPI_CONV>(ma, mb, p, grid, st);
 }
 
