@@ -123,7 +123,7 @@ LCT_API int lct_conv_mma_dgrad(const float* dy, const float* w, const float* wim
 LCT_API int lct_conv_mma_wgrad(const float* x, const float* dy, float* dw, float* db, int64_t B, int64_t Cin, int64_t Cout, int64_t G, int64_t K, int64_t S, int64_t pad, int64_t Lin, int64_t P, cudaStream_t stream);
 
 /* conv_post (C -> 1 channel, odd K <= 8, stride 1, pad K/2; discriminators.py:59-66, :188-196): channel-reduction kernels.
- * y [B,1,L,P] must be zeroed by the caller (channel chunks are combined with atomics); dw/db accumulate. */
+ * y [B,1,L,P] is overwritten (each CTA reduces all channels of its positions: no atomics); dw/db accumulate. */
 LCT_API int lct_conv_post_fwd(const float* x, const float* w, const float* bias, float* y, int64_t B, int64_t C, int64_t L, int64_t P, int64_t K, cudaStream_t stream);
 LCT_API int lct_conv_post_wgrad(const float* x, const float* dy, float* dw, float* db, int64_t B, int64_t C, int64_t L, int64_t P, int64_t K, cudaStream_t stream);
 LCT_API int lct_conv_post_dgrad(const float* dy, const float* w, float* dx, const float* gextra, const float* xact, int64_t B, int64_t C, int64_t L, int64_t P, int64_t K, int act, float slope, cudaStream_t stream);

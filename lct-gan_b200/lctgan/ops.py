@@ -303,7 +303,7 @@ def conv1d_fwd(x, w, bias, groups, stride, pad, act=ACT_NONE, slope=0.2, wimg=No
     Cout, K = w.shape[0], w.shape[2]
     Lout = conv_out_len(Lin, K, stride, pad)
     if _is_post(Cout, K, groups, stride, pad) and act == ACT_NONE:
-        y = torch.zeros(B, 1, Lin, P, dtype=torch.float32, device=x.device)
+        y = torch.empty(B, 1, Lin, P, dtype=torch.float32, device=x.device)
         call("lct_conv_post_fwd", x, w, bias, y, B, Cin, Lin, P, K)
         return y
     y = torch.empty(B, Cout, Lout, P, dtype=torch.float32, device=x.device)
