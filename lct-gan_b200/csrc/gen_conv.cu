@@ -187,6 +187,87 @@ __global__ void __launch_bounds__(kThreads) gconv_wgrad_kernel(const GWgradParam
     }
 }
 
+// Register-blocked form of the same reduction: a thread owns a 4 (a) x TC (c) block of (a, c) pairs, i.e. 24 TC
+// accumulators, and per position reads 4 S values and 6 TC Lg values for 24 TC FMAs (the kernel above reads 7 words
+// per 6 FMAs and was bound by shared-memory loads).  Threads that do not fit the pair grid split the f range; the
+// slices meet in shared memory, then one atomic per weight per CTA.
+template <int TC>
+__global__ void __launch_bounds__(kThreads) gconv_wgrad_blk_kernel(const GWgradParams p) {
+    extern __shared__ __align__(16) float sm[];
+    float* Ssm = sm;                                   // [Fs][Ca]
+    float* Lsm = sm + (size_t)p.Fs * p.Ca;             // [2][Fl + 2][Cc]   (one zero column on each side)
+    const int b = blockIdx.y;
+    const int t0 = blockIdx.x * p.rows_per_cta;
+    const int ntc = p.Cc / TC, ntiles = (p.Ca / 4) * ntc, nslices = kThreads / ntiles;
+    const int tile = threadIdx.x % ntiles, slice = threadIdx.x / ntiles;
+    const int a0 = (tile / ntc) * 4, c0 = (tile % ntc) * TC;
+    float acc[4][TC][6];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < TC; ++j)
+#pragma unroll
+            for (int k = 0; k < 6; ++k) acc[i][j][k] = 0.f;
+    const int lrow = (p.Fl + 2) * p.Cc;
+    for (int t = t0; t < min(t0 + p.rows_per_cta, p.Ts); ++t) {
+        __syncthreads();
+        const float* srow = p.S + ((size_t)b * p.Ts + t) * p.Fs * p.Ca;
+        for (int idx = threadIdx.x * 4; idx < p.Fs * p.Ca; idx += kThreads * 4)
+            *reinterpret_cast<float4*>(Ssm + idx) = *reinterpret_cast<const float4*>(srow + idx);
+        for (int idx = threadIdx.x; idx < 2 * lrow; idx += kThreads) {
+            int kt = idx / lrow;
+            int rem = idx - kt * lrow;
+            int fc = rem / p.Cc, c = rem - fc * p.Cc;
+            int fl = fc - 1, tl = t + kt - 1;
+            float v = 0.f;
+            if (fl >= 0 && fl < p.Fl && tl >= 0 && tl < p.Tl) v = p.Lg[(((size_t)b * p.Tl + tl) * p.Fl + fl) * p.Cc + c];
+            Lsm[idx] = v;
+        }
+        __syncthreads();
+        if (slice < nslices) {
+            for (int f = slice; f < p.Fs; f += nslices) {
+                const float4 s4 = *reinterpret_cast<const float4*>(Ssm + f * p.Ca + a0);
+                const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+                for (int kt = 0; kt < 2; ++kt)
+#pragma unroll
+                    for (int kf = 0; kf < 3; ++kf) {
+                        const int col = 2 * f + kf;          // smem column of Lg index 2f + kf - 1
+                        if (col >= p.Fl + 2) continue;
+                        float lv[TC];
+                        const float* lp = Lsm + kt * lrow + col * p.Cc + c0;
+                        if (TC == 4) {
+                            const float4 l4 = *reinterpret_cast<const float4*>(lp);
+                            lv[0] = l4.x; lv[1 % TC] = l4.y; lv[2 % TC] = l4.z; lv[3 % TC] = l4.w;
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < TC; ++j) lv[j] = lp[j];
+                        }
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+#pragma unroll
+                            for (int j = 0; j < TC; ++j) acc[i][j][kt * 3 + kf] = fmaf(sv[i], lv[j], acc[i][j][kt * 3 + kf]);
+                    }
+            }
+        }
+    }
+    __syncthreads();
+    float* red = sm;                                    // [Ca * Cc * 6]
+    const int nred = p.Ca * p.Cc * 6;
+    for (int i = threadIdx.x; i < nred; i += kThreads) red[i] = 0.f;
+    __syncthreads();
+    if (slice < nslices) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < TC; ++j)
+#pragma unroll
+                for (int k = 0; k < 6; ++k) atomicAdd(&red[((a0 + i) * p.Cc + c0 + j) * 6 + k], acc[i][j][k]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nred; i += kThreads) atomicAdd(&p.dW[i], red[i]);
+}
+
 // out[b,t,f,c] = h[b,t,f,c] + mag[b,t,f] * w[c] + bias[c]   on the common low-index corner
 __global__ void skip_add_fwd_kernel(const float* __restrict__ h, const float* __restrict__ mag,
                                     const float* __restrict__ w, const float* __restrict__ bias,
@@ -338,6 +419,37 @@ LCT_API int lct_gconv_wgrad(const float* S, const float* Lg, float* dW, int64_t 
     GWgradParams p;
     p.S = S; p.Lg = Lg; p.dW = dW;
     p.B = (int)B; p.Ts = (int)Ts; p.Fs = (int)Fs; p.Ca = (int)Ca; p.Tl = (int)Tl; p.Fl = (int)Fl; p.Cc = (int)Cc;
+    {
+        // register-blocked kernel: 4 x TC pair blocks must tile the 256 threads
+        const int tc = (Cc % 4 == 0) ? 4 : 1;
+        const int64_t ntiles = (Ca / 4) * (Cc / tc);
+        const bool aligned = ((uintptr_t)S & 15) == 0 && (Ca % 4) == 0 && (Cc == 1 || Cc % 4 == 0);
+        if (aligned && ntiles >= 1 && ntiles <= kThreads && kThreads % ntiles == 0) {
+            int rows = (int)ceil_div64(B * Ts, 296);          // ~2 CTAs per SM: every CTA ends with Ca*Cc*6 atomics
+            if (rows < 1) rows = 1;
+            p.rows_per_cta = rows;
+            size_t smem = ((size_t)Fs * Ca + (size_t)2 * (Fl + 2) * Cc) * sizeof(float);
+            const size_t red = (size_t)Ca * Cc * 6 * sizeof(float);
+            if (smem < red) smem = red;
+            if (smem > 200 * 1024) return LCT_EUNSUPPORTED;
+            dim3 grid((unsigned)ceil_div64(Ts, rows), (unsigned)B);
+            if (tc == 4) {
+                if (smem > 48 * 1024) {
+                    cudaError_t e = cudaFuncSetAttribute(gconv_wgrad_blk_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    if (e != cudaSuccess) return (int)e;
+                }
+                gconv_wgrad_blk_kernel<4><<<grid, kThreads, smem, st>>>(p);
+            } else {
+                if (smem > 48 * 1024) {
+                    cudaError_t e = cudaFuncSetAttribute(gconv_wgrad_blk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    if (e != cudaSuccess) return (int)e;
+                }
+                gconv_wgrad_blk_kernel<1><<<grid, kThreads, smem, st>>>(p);
+            }
+            LCT_RETURN_IF_LAUNCH_FAILED();
+            return 0;
+        }
+    }
     p.rows_per_cta = 2;
     size_t smem = ((size_t)Fs * Ca + (size_t)2 * (Fl + 2) * Cc) * sizeof(float);
     if (smem > 200 * 1024) return LCT_EUNSUPPORTED;

@@ -117,7 +117,8 @@ def _block_fwd(P, pre, x, B, T, F, freq, S):
 
 
 def _split_k(M: int) -> int:
-    return max(1, min(256, (M + 511) // 512))
+    # the weight-gradient GEMMs have 1..3 output tiles: ~133 rows per CTA puts 256+ CTAs on the 148 SMs
+    return max(1, min(256, (M + 127) // 128))
 
 
 class _Side:
@@ -144,7 +145,7 @@ class _Side:
         self.keep.clear()
 
 
-def _block_bwd(P, pre, dout, B, T, F, freq, S, GR, side=None):
+def _block_bwd(P, pre, dout, B, T, F, freq, S, GR, side=None, z=None):
     """dout: [M,64] gradient of the block output.  Fills GR[name] for the block's parameters and
     returns the gradient of the block input."""
     own = side is None
@@ -158,7 +159,8 @@ def _block_bwd(P, pre, dout, B, T, F, freq, S, GR, side=None):
     dev = dout.device
     f32 = dict(dtype=torch.float32, device=dev)
     ks = _split_k(M)
-    z = lambda *shape: torch.zeros(*shape, **f32)
+    if z is None:
+        z = lambda *shape: torch.zeros(*shape, **f32)
 
     # out = seq + lrelu(lin(lin_in))
     dmix = ops.act_bwd(s["mix"], dout, ACT_LRELU, SLOPE)
@@ -214,7 +216,8 @@ def _block_bwd(P, pre, dout, B, T, F, freq, S, GR, side=None):
     # dW_ih[gd] = dgi[:, gd, :]^T @ xn[:, g*16:(g+1)*16]
     with side.fork(dgi):
         dwih = z(GD, 3 * H, H)
-        ops.gemm(dgi, s["xn"], dwih, 3 * H, H, M, lda=GD * 3 * H, ldb=C, ldc=H, ta=True, tb=True, ksplit=ks,
+        ops.gemm(dgi, s["xn"], dwih, 3 * H, H, M, lda=GD * 3 * H, ldb=C, ldc=H, ta=True, tb=True,
+                 ksplit=max(1, 2 * ks // GD),
                  nbatch=GD, a_div=1, b_div=D, sA=3 * H, sB=H, sC=3 * H * H)
     # dxn[:, g] = dgi[:, g, (d,48)] @ [W_ih(g,0); W_ih(g,1)]
     dxn = torch.empty(M, C, **f32)
@@ -289,6 +292,8 @@ def generator_backward(P, mag, mask, gmask, use_sigmoid, S, need_mag_grad=False)
     GR: Dict[str, torch.Tensor] = {}
     dev = mag.device
     f32 = dict(dtype=torch.float32, device=dev)
+    # (one shared zero-filled arena for all accumulators was tried and measured 2 % slower: autograd cannot steal a
+    # gradient that is a view of a larger buffer and clones every one of the 130 of them instead)
     z = lambda *shape: torch.zeros(*shape, **f32)
     enc, dec_in, dec_out = top["enc"], top["dec_in"], top["dec_out"]
     T3, F3 = top["T3"], top["F3"]
@@ -305,7 +310,7 @@ def generator_backward(P, mag, mask, gmask, use_sigmoid, S, need_mag_grad=False)
         Bq, Ti, Fi, Ci = d_in.shape
         Co = w.shape[1]
         with side.fork(dpre):
-            GR[f"deconv{i}.weight"] = ops.gconv_wgrad(d_in, dpre, w.shape)
+            GR[f"deconv{i}.weight"] = ops.gconv_wgrad(d_in, dpre, w.shape, out=z(*w.shape))
             db = z(Co)
             ops.colsum(dpre, db, dpre.numel() // Co, Co, Co)
             GR[f"deconv{i}.bias"] = db
@@ -324,7 +329,7 @@ def generator_backward(P, mag, mask, gmask, use_sigmoid, S, need_mag_grad=False)
     # ---- bottleneck
     dh = dh3.view(M, C)
     for name, freq in reversed(BLOCKS):
-        dh = _block_bwd(P, name, dh, B, T3, F3, freq, S, GR, side)
+        dh = _block_bwd(P, name, dh, B, T3, F3, freq, S, GR, side, z)
     dg0, db0 = z(C), z(C)
     dx3 = ops.layernorm_bwd(dh, enc[2].view(M, C), P["layernorm.weight"], top["mean0"], top["rstd0"], dg0, db0)
     GR["layernorm.weight"], GR["layernorm.bias"] = dg0, db0
@@ -338,7 +343,7 @@ def generator_backward(P, mag, mask, gmask, use_sigmoid, S, need_mag_grad=False)
         xin = inputs[i - 1]
         Co = w.shape[0]
         with side.fork(dpre):
-            GR[f"conv{i}.weight"] = ops.gconv_wgrad(dpre, xin, w.shape)
+            GR[f"conv{i}.weight"] = ops.gconv_wgrad(dpre, xin, w.shape, out=z(*w.shape))
             db = z(Co)
             ops.colsum(dpre, db, dpre.numel() // Co, Co, Co)
             GR[f"conv{i}.bias"] = db

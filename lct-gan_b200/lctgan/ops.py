@@ -415,10 +415,11 @@ def gconv(x, w, bias, out_tf, cd, transposed, act=ACT_NONE, slope=0.2, gmul=None
     return out
 
 
-def gconv_wgrad(S, Lg, w_shape):
+def gconv_wgrad(S, Lg, w_shape, out=None):
+    """`out`: optional pre-zeroed accumulator of shape w_shape."""
     B, Ts, Fs, Ca = S.shape
     _, Tl, Fl, Cc = Lg.shape
-    dW = torch.zeros(w_shape, dtype=torch.float32, device=S.device)
+    dW = out if out is not None else torch.zeros(w_shape, dtype=torch.float32, device=S.device)
     call("lct_gconv_wgrad", S, Lg, dW, B, Ts, Fs, Ca, Tl, Fl, Cc)
     return dW
 
