@@ -194,21 +194,70 @@ def measure_roofline(dev, peaks):
             "traffic": 49.9e6, "traffic_note": "dram__bytes_read+write per launch, ncu --set full "
             "(profiles/ncu_full_r1_roofline_kernels_raw.csv); the 16.4 MB output is still in the 126 MB L2 when the kernel ends",
             "algorithmic_bytes": nbytes, "ms_per_launch": ms, "peak_source": peaks["src"] + " (STREAM-style copy)"}
-    # ---- dense conv forward on tcgen05 (MSD convs.5)
-    B, L, C, K = BATCH, 125, 1024, 5
-    x = torch.randn(B, C, L, 1, generator=g).to(dev)
+    # ---- dense conv forward on tcgen05 (MSD convs.5): the D step pushes clean + enhanced through as one batch of 2B
+    C, K = 1024, 5
     w = (torch.randn(C, C, K, generator=g) / (C * K) ** 0.5).to(dev)
     bias = torch.zeros(C, device=dev)
     wt, _ = ops.stage_dense_weights(w, want_wd=False)
-    xp = ops.stage_nlc_bf16(x, K // 2)
-    flops = 2.0 * B * L * C * C * K
-    ms = _time_kernel(lambda: ops.dense_conv(xp, wt, B, L, C, C, K, bias=bias, act=ops.ACT_LRELU), flush)
-    tf = flops / (ms * 1e-3) / 1e12
-    roof_t = {"kernel": "dense_kernel<64,6,conv> (MSD convs.5 forward: 1024->1024, k=5, B=8, L=125, tcgen05 bf16)",
+    per_shape = {}
+    for Bd in (2 * BATCH, BATCH):
+        L = 125
+        x = torch.randn(Bd, C, L, 1, generator=g).to(dev)
+        xp = ops.stage_nlc_bf16(x, K // 2)
+        flops = 2.0 * Bd * L * C * C * K
+        ms = _time_kernel(lambda: ops.dense_conv(xp, wt, Bd, L, C, C, K, bias=bias, act=ops.ACT_LRELU), flush)
+        per_shape[Bd] = (flops / (ms * 1e-3) / 1e12, ms, flops)
+    tf, ms, flops = per_shape[2 * BATCH]
+    roof_t = {"kernel": "dense_kernel<128,5,conv> (MSD convs.5 forward: 1024->1024, k=5, the D step's batch of 2B=16, L=125, "
+                        "tcgen05 bf16, 128x128 tiles)",
               "bound": "tensor", "achieved": tf, "peak": peaks["tensor"], "unit": "TFLOP/s",
-              "frac": tf / peaks["tensor"], "traffic": 12.6e6, "ms_per_launch": ms,
+              "frac": tf / peaks["tensor"], "traffic": None, "ms_per_launch": ms, "algorithmic_flops": flops,
+              "g_step_shape_B8": {"achieved": per_shape[BATCH][0], "ms_per_launch": per_shape[BATCH][1],
+                                  "frac": per_shape[BATCH][0] / peaks["tensor"], "tiles": "128x64 (144 CTAs)"},
+              "note": "bound by the per-SM TMA / L2 feed (~37 B/clk/SM measured), not by the tensor pipe: see DESIGN.md section 6",
               "peak_source": peaks["src"] + " (burst: kernel timed alone)"}
     return roof, roof_t
+
+
+def measure_frontend_rooflines(dev, peaks):
+    """HBM rooflines of the STFT / iSTFT / spectral-loss kernels (BASELINE north_star: STFT front end and losses profiled
+    separately) at the top of the BASELINE sweep (B = 128, 4 s; at B = 8 x 2 s they are launch-latency sized, 8-15 us).
+    Algorithmic bytes per SURVEY.md section 8d; every launch timed alone with CUDA events, L2 flushed before it."""
+    import torch
+    from lctgan import ops
+    B, T, n_fft, hop = 128, 64000, 512, 256
+    flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
+    x = torch.randn(B, T, device=dev) * 0.1
+    y = torch.randn(B, T, device=dev) * 0.1
+    w = torch.hann_window(n_fft, device=dev)
+    Tf, F = 1 + T // hop, n_fft // 2 + 1
+    spec, _ = ops.stft_fwd(x, w, n_fft, hop, want_mag=True)
+    mask = torch.rand(B, Tf, F, device=dev) * 0.5 + 0.5
+    acc = torch.zeros(2, 64, device=dev)
+    gy = torch.randn(B, T, device=dev)
+    fm_a = [torch.randn(B, 128, 1778, 2, device=dev) for _ in range(2)]
+    cases = [
+        ("stft_magnitude", "wf::r2c_warp_kernel<8,STFT> (ComplexSTFT.forward + magnitude)",
+         lambda: ops.stft_fwd(x, w, n_fft, hop, want_mag=True), 4.0 * (B * T + 3 * B * Tf * F)),
+        ("tf_features", "wf::r2c_warp_kernel<8,TFF> (2 STFT + |.| + IRM^c + mag^c)",
+         lambda: ops.tf_features_fwd(x, y, w, n_fft, hop), 4.0 * (2 * B * T + 3 * B * Tf * F)),
+        ("mask_istft", "wf::c2r_warp_kernel<8,ISTFT> (mask decompression + iSTFT)",
+         lambda: ops.istft_fwd(spec, w, n_fft, hop, T, mask_c=mask), 4.0 * (3 * B * Tf * F + B * T)),
+        ("istft_adjoint_mask_grad", "wf::r2c_warp_kernel<8,ISTFT_BWD> (iSTFT backward + mask gradient)",
+         lambda: ops.istft_bwd(gy, w, n_fft, hop, Tf, xspec=spec, mask_c=mask, want_gspec=False),
+         4.0 * (B * T + 4 * B * Tf * F)),
+        ("mrstft_sums_512", "wf::r2c_warp_kernel<8,MRLOSS> (spectral-loss sums, no spectrogram written)",
+         lambda: ops.mrstft_sums(x, y, w, n_fft, hop, acc), 4.0 * 2 * B * T),
+        ("feature_matching_l1", "mt_kernel<reduce> (L1 over two 58 M-element feature-map pairs)",
+         lambda: ops.mt_reduce(fm_a[:1], fm_a[1:], [1.0], ops.OP_ABS_DIFF), 4.0 * 2 * fm_a[0].numel()),
+    ]
+    out = {"shape": "B=128 x 4 s @ 16 kHz, n_fft 512 / hop 256", "bound": "hbm", "peak": peaks["hbm"], "unit": "GB/s"}
+    for key, kernel, run, nbytes in cases:
+        ms = _time_kernel(run, flush)
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        out[key] = {"kernel": kernel, "achieved": gbs, "frac": gbs / peaks["hbm"], "us_per_launch": ms * 1e3,
+                    "algorithmic_bytes": nbytes}
+    return out
 
 
 def measure_enhance_rtf(dev):
@@ -374,6 +423,7 @@ def main():
     peaks = _peaks()
     roof, roof_t = (None, None) if args.no_roofline else measure_roofline(dev, peaks)
     rtf = None if args.no_roofline else measure_enhance_rtf(dev)
+    roof_fe = None if args.no_roofline else measure_frontend_rooflines(dev, peaks)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         sps, ms, b, cores = cpu_reference_steps(steps=1, warmup=1, budget_s=30.0)
@@ -382,7 +432,7 @@ def main():
                          f"torch CPU ops, {cores} threads)", "ms_per_step": ms}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 tensor-core operands for the dense contraction (fp32 accumulate), f32 elsewhere",
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 (tcgen05 dense contraction) / tf32 (grouped discriminator convolutions) / 3xtf32 (generator GEMMs and convolutions) tensor-core operands with fp32 accumulation; f32 elsewhere",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "gan_loss": args.gan_loss, "parallelism": f"dp{world}", "cuda_graph": graphed is not None, "reuse_enhancer_forward": sargs.reuse_enhancer_forward, "batch_d_step": sargs.batch_d_step, "skip_dead_d_grads": sargs.skip_dead_d_grads, "fused_adamw": not args.torch_optim,
                    "l2": "no explicit flush: one step streams > 2 GB of activations (>> 126 MB L2)"},
@@ -392,6 +442,7 @@ def main():
         "gpu_launches": launches,
         "roofline": roof,
         "roofline_tensor": roof_t,
+        "roofline_frontend": roof_fe,
         "enhance_rtf": rtf,
         "cpu_baseline": cpu,
         "losses_last_step": losses,
