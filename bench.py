@@ -305,6 +305,9 @@ def main():
                     "the fused multi-tensor AdamW kernel (same update rule; SURVEY 8f N2)")
     ap.add_argument("--skip-dead-d-grads", action="store_true", help="do not compute the discriminator weight gradients "
                     "of the G step (the reference computes and discards them); off by default = the reference's work")
+    ap.add_argument("--no-defer-dead-d-grads", action="store_true", help="join the helper streams that finish the (never read) "
+                    "discriminator parameter gradients of the G step inside the discriminators' backward instead of at the "
+                    "end of the G phase")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -342,7 +345,7 @@ def main():
     sargs = StepArgs(gan_loss=args.gan_loss, reuse_enhancer_forward=not args.no_reuse,
                      fake_streams=bool(int(os.environ.get("LCT_FAKE_STREAMS", "0"))),
                      batch_d_step=not args.no_reuse and bool(int(os.environ.get("LCT_BATCH_D", "1"))),
-                     skip_dead_d_grads=args.skip_dead_d_grads)
+                     skip_dead_d_grads=args.skip_dead_d_grads, defer_dead_d_grads=not args.no_defer_dead_d_grads)
 
     noisy_h, clean_h = O.synthetic_batch(BATCH, SEGMENT, seed=1234 + rank)      # synthetic data generator only
     noisy_h, clean_h = noisy_h.pin_memory(), clean_h.pin_memory()
@@ -434,7 +437,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 (tcgen05 dense contraction) / tf32 (grouped discriminator convolutions) / 3xtf32 (generator GEMMs and convolutions) tensor-core operands with fp32 accumulation; f32 elsewhere",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "gan_loss": args.gan_loss, "parallelism": f"dp{world}", "cuda_graph": graphed is not None, "reuse_enhancer_forward": sargs.reuse_enhancer_forward, "batch_d_step": sargs.batch_d_step, "skip_dead_d_grads": sargs.skip_dead_d_grads, "fused_adamw": not args.torch_optim,
+        "config": {"workload": WORKLOAD, "gan_loss": args.gan_loss, "parallelism": f"dp{world}", "cuda_graph": graphed is not None, "reuse_enhancer_forward": sargs.reuse_enhancer_forward, "batch_d_step": sargs.batch_d_step, "skip_dead_d_grads": sargs.skip_dead_d_grads, "defer_dead_d_grads": sargs.defer_dead_d_grads, "fused_adamw": not args.torch_optim,
                    "l2": "no explicit flush: one step streams > 2 GB of activations (>> 126 MB L2)"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,

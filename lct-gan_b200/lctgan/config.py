@@ -28,7 +28,27 @@ gconv_tensor_cores = True
 #: CUDA graph they become parallel branches.
 concurrent_discriminators = True
 
+#: CUDA stream priorities (lower = more urgent; kernel nodes of a captured graph inherit them).  The serial chains that
+#: the step waits for - the generator (priority_generator) and the sub-discriminators' forward / data-gradient chains
+#: (chain_priority) - outrank the helper streams that carry weight-gradient kernels (priority 0), so a wide
+#: weight-gradient grid cannot park its CTAs in front of a critical-path kernel.
+import os as _os
+chain_priority = 0 if _os.environ.get("LCT_NO_PRIORITY") else -1
+priority_generator = -2
+
 _STREAMS = {}
+_GEN_STREAM = {}
+
+
+def generator_stream(device):
+    """The high-priority stream the generator's forward / backward kernels run on."""
+    import torch
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    st = _GEN_STREAM.get(key)
+    if st is None:
+        st = torch.cuda.Stream(device=device, priority=priority_generator)
+        _GEN_STREAM[key] = st
+    return st
 
 
 def side_streams(n: int, device):
@@ -37,7 +57,7 @@ def side_streams(n: int, device):
     key = (device.index if device.index is not None else torch.cuda.current_device())
     pool = _STREAMS.setdefault(key, [])
     while len(pool) < n:
-        pool.append(torch.cuda.Stream(device=device))
+        pool.append(torch.cuda.Stream(device=device, priority=chain_priority))
     return pool[:n]
 
 
@@ -51,6 +71,29 @@ def aux_stream_for(stream):
     key = (stream.device.index, stream.cuda_stream)
     aux = _AUX.get(key)
     if aux is None:
-        aux = torch.cuda.Stream(device=stream.device)
+        aux = torch.cuda.Stream(device=stream.device, priority=0)
         _AUX[key] = aux
     return aux
+
+
+#: G step only (a sub-discriminator whose INPUT requires grad): finish the discriminator parameter gradients - weight
+#: gradient kernels, weight-norm backward and the accumulation into ``.grad`` - on the helper stream and join it when the
+#: caller says so (``join_deferred_param_grads()``, called by lctgan.training at the end of the G phase) instead of at the
+#: end of the sub-discriminator's backward.  train.py computes these gradients and never reads them (the next
+#: ``d_opt.zero_grad`` discards them), so nothing on the critical path waits for them: they overlap the generator's
+#: backward, whose kernels are small.  Values of every ``.grad`` after the join are unchanged.  Off by default because the
+#: gradients are only valid after the join; lctgan.training.StepArgs.defer_dead_d_grads turns it on.
+defer_dead_param_grads = False
+_PENDING = []
+
+
+def join_deferred_param_grads() -> None:
+    """Order the current stream after every deferred parameter-gradient chain and release the tensors kept for them."""
+    import torch
+    if not _PENDING:
+        return
+    cur = torch.cuda.current_stream()
+    for aux, keep in _PENDING:
+        cur.wait_stream(aux)
+        keep.clear()
+    _PENDING.clear()

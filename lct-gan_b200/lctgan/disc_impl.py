@@ -64,6 +64,7 @@ class ConvStackFn(torch.autograd.Function):
         ctx.specs = list(specs)
         ctx.dense = dense
         ctx.skip_param_grads = skip_param_grads
+        ctx.param_objs = params   # the Parameter objects themselves (deferred mode accumulates into their .grad)
         ctx.imgs_d = imgs_d       # (internal buffers, not outputs: safe to keep on ctx)
         ctx.save_for_backward(x4, *fmaps, *weights, *params)
         return tuple(fmaps)
@@ -130,11 +131,33 @@ class ConvStackFn(torch.autograd.Function):
             elif i > 0 and gouts[i - 1] is not None:
                 dpre = ops.act_bwd(inp, gouts[i - 1], ops.ACT_LRELU, LRELU_SLOPE)
         if want_params:
+            gs = [params[3 * i + 1].contiguous() for i in range(n)]
+            vs = [params[3 * i + 2].contiguous() for i in range(n)]
+            if aux is not None and need_x and config.defer_dead_param_grads:
+                # G step: nobody downstream reads these gradients (config.defer_dead_param_grads): finish them on the
+                # helper stream - weight-norm backward and the accumulation into .grad included - and let the caller
+                # join later; autograd gets None for the parameters.
+                with torch.cuda.stream(aux):
+                    dgs, dvs = ops.mt_weight_norm_bwd(gs, vs, dws)
+                    olds, news = [], []
+                    for i in range(n):
+                        for j, t in ((3 * i, dbs[i]), (3 * i + 1, dgs[i]), (3 * i + 2, dvs[i])):
+                            if not need_p[j]:
+                                continue
+                            pobj = ctx.param_objs[j]
+                            if pobj.grad is None:
+                                pobj.grad = t
+                            else:
+                                olds.append(pobj.grad)
+                                news.append(t)
+                    if olds:
+                        torch._foreach_add_(olds, news)
+                keep.extend([x4, *fmaps, *weights, *gs, *vs, *dws, *dbs, *dgs, *dvs, *[g for g in gouts if g is not None]])
+                config._PENDING.append((aux, keep))
+                return (gx, None, None, *gparams)
             if aux is not None:
                 cur.wait_stream(aux)
             keep.clear()
-            gs = [params[3 * i + 1].contiguous() for i in range(n)]
-            vs = [params[3 * i + 2].contiguous() for i in range(n)]
             dgs, dvs = ops.mt_weight_norm_bwd(gs, vs, dws)
             for i in range(n):
                 gparams[3 * i] = dbs[i] if need_p[3 * i] else None

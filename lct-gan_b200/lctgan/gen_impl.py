@@ -13,6 +13,7 @@ through the sigmoid, so the last frames are exactly 0.5.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Sequence, Tuple
 
 import torch
@@ -129,7 +130,7 @@ class _Side:
     def __init__(self, device):
         from . import config
         self.cur = torch.cuda.current_stream(device)
-        self.side = config.side_streams(18, device)[17] if config.concurrent_discriminators else None
+        self.side = config.aux_stream_for(self.cur) if config.concurrent_discriminators else None   # low priority
         self.keep = []
 
     def fork(self, *tensors):
@@ -354,6 +355,21 @@ def generator_backward(P, mag, mask, gmask, use_sigmoid, S, need_mag_grad=False)
     return GR
 
 
+def _on_generator_stream(device, fn):
+    """Run fn on the high-priority generator stream, forked from and joined to the caller's stream (the generator is a
+    serial chain of small kernels: it must not queue behind the wide weight-gradient grids of the discriminators)."""
+    from . import config
+    if not config.concurrent_discriminators or os.environ.get("LCT_NO_PRIORITY"):
+        return fn()
+    cur = torch.cuda.current_stream(device)
+    hp = config.generator_stream(device)
+    hp.wait_stream(cur)
+    with torch.cuda.stream(hp):
+        out = fn()
+    cur.wait_stream(hp)
+    return out
+
+
 class GeneratorFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mag_phys, use_sigmoid, names, *params):
@@ -362,7 +378,7 @@ class GeneratorFn(torch.autograd.Function):
         P = dict(zip(names, params))
         need = any(ctx.needs_input_grad[3:])
         S = {} if need else None
-        mask = generator_forward(P, mag_phys.contiguous(), use_sigmoid, S)
+        mask = _on_generator_stream(mag_phys.device, lambda: generator_forward(P, mag_phys.contiguous(), use_sigmoid, S))
         ctx.S = S
         ctx.names = names
         ctx.use_sigmoid = use_sigmoid
@@ -373,8 +389,8 @@ class GeneratorFn(torch.autograd.Function):
     def backward(ctx, gmask):
         mag_phys, mask, *params = ctx.saved_tensors
         P = dict(zip(ctx.names, params))
-        GR = generator_backward(P, mag_phys.contiguous(), mask, gmask, ctx.use_sigmoid, ctx.S,
-                                ctx.needs_input_grad[0])
+        GR = _on_generator_stream(mag_phys.device, lambda: generator_backward(
+            P, mag_phys.contiguous(), mask, gmask, ctx.use_sigmoid, ctx.S, ctx.needs_input_grad[0]))
         ctx.S = None
         grads = [GR.get(n) if ctx.needs_input_grad[3 + i] else None for i, n in enumerate(ctx.names)]
         return (None, None, None, *grads)

@@ -39,6 +39,10 @@ class StepArgs:
     #: cannot know they are dead: the next d_opt.zero_grad discards them).  Changes no weight and no
     #: loss, but it does change the (unused) .grad the D parameters hold after the step, hence opt-in, default off.
     skip_dead_d_grads: bool = False
+    #: G step: finish the (never read) discriminator parameter gradients on helper streams that are joined at the end of
+    #: the G phase instead of inside the discriminators' backward, so they overlap the generator's backward
+    #: (lctgan.config.defer_dead_param_grads).  Every .grad holds the reference's value once the phase has ended.
+    defer_dead_d_grads: bool = False
 
 
 def _align_tf_targets(irm_c: torch.Tensor, pred_mask_c: torch.Tensor):
@@ -121,7 +125,12 @@ def _phase_g(M, noisy, clean, args: StepArgs, st: dict) -> None:
     adv_loss = L.generator_adv_loss(L._flatten_logits_lists(mpd_fake_g, msd_fake_g), args.gan_loss)
     fm_loss = L.feature_matching_loss(mpd_real_f + msd_real_f, mpd_fake_f + msd_fake_f)
     g_loss = mr_loss + args.lambda_mask * m_loss + args.lambda_adv * (adv_loss + args.lambda_fm * fm_loss)
-    g_loss.backward()
+    config.defer_dead_param_grads = bool(args.defer_dead_d_grads) and noisy.is_cuda
+    try:
+        g_loss.backward()
+    finally:
+        config.defer_dead_param_grads = False
+        config.join_deferred_param_grads()
     st.update(g_loss=g_loss.detach(), mr=mr_loss.detach(), mask=m_loss.detach(), adv=adv_loss.detach(),
               fm=fm_loss.detach())
 

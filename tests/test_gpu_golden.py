@@ -193,3 +193,32 @@ def test_batched_d_step_is_identical(dev, G, gan_loss):
             diff = (p.detach() - q.detach()).abs()
             assert diff.max().item() <= 2.0 * lr * nsteps, k
             assert (diff > 0.05 * lr * nsteps).float().mean().item() <= 1e-3, k
+
+
+def test_deferred_dead_d_grads_leave_the_same_grads(dev, G):
+    """StepArgs.defer_dead_d_grads (the discriminator parameter gradients of the G step finish on helper streams that
+    are joined at the end of the G phase): same losses, same weights and - unlike skip_dead_d_grads - the same .grad
+    on every discriminator parameter after the step (D-step gradient + G-step gradient, as train.py leaves them)."""
+    from lctgan.training import StepArgs, build_models, train_step
+    noisy, clean = (t.to(dev) for t in G["model_inputs"])
+    a = build_models(dev, gan_seed=42)
+    b = build_models(dev, gan_seed=42)
+    base = dict(gan_loss="ls", reuse_enhancer_forward=True, batch_d_step=True)
+    for step in range(2):
+        ra = train_step(*a, noisy, clean, StepArgs(**base))
+        rb = train_step(*b, noisy, clean, StepArgs(**base, defer_dead_d_grads=True))
+        torch.cuda.synchronize()
+        for k in ra:
+            assert abs(ra[k].item() - rb[k].item()) <= 2e-6 * max(1.0, abs(ra[k].item())) + 1e-4 * step, (step, k)
+        if step == 0:      # identical weights on both sides: the accumulated gradients must agree to atomics noise
+            for ma, mb in zip(a[1:3], b[1:3]):
+                for (k, p), q in zip(ma.named_parameters(), mb.parameters()):
+                    assert p.grad is not None and q.grad is not None, k
+                    scale = p.grad.abs().max().item() + 1e-12
+                    assert (p.grad - q.grad).abs().max().item() <= 1e-4 * scale + 1e-9, k
+    lr, nsteps = 2e-4, 2
+    for ma, mb in zip(a[:3], b[:3]):
+        for (k, p), q in zip(ma.named_parameters(), mb.parameters()):
+            diff = (p.detach() - q.detach()).abs()
+            assert diff.max().item() <= 2.0 * lr * nsteps, k
+            assert (diff > 0.05 * lr * nsteps).float().mean().item() <= 1e-3, k
