@@ -47,11 +47,10 @@ struct MmaParams {
     int tiles_per_b, ntiles;
 };
 
-__device__ __forceinline__ uint32_t f2tf32(float v) {
-    uint32_t u;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
-    return u;
-}
+// fp32 -> tf32, round to nearest / ties away (= cvt.rna.tf32.f32 for every finite input): add half a tf32 ulp to the
+// magnitude; the tensor core ignores the 13 low mantissa bits.  cvt.rna itself is emulated on sm_100a as FSETP(|v|<inf)
+// + predicated integer add, twice the instructions (ncu source page of round 1), in the innermost loop.
+__device__ __forceinline__ uint32_t f2tf32(float v) { return __float_as_uint(v) + 0x1000u; }
 __device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                          uint32_t b0, uint32_t b1) {
     asm volatile(
@@ -121,7 +120,7 @@ __device__ __forceinline__ void stage_window(const MmaParams& p, int g, int tile
     }
     for (int kk = threadIdx.x; kk < p.KKpad; kk += kThreads) {
         const int64_t cb = cb0 + (int64_t)chk[kk] * lim;
-        lutd[kk] = lut0[kk] + (int)((cb + e0) & 3);
+        lutd[kk] = (lut0[kk] + (int)((cb + e0) & 3)) * 4;   // byte offset
     }
 }
 
@@ -181,28 +180,33 @@ __global__ void __launch_bounds__(kThreads) conv_mma_kernel(const MmaParams p) {
         chk[kk] = chn;
     }
     __syncthreads();
-    // this thread's accumulator columns: n = nt*8 + 2*tq + c  ->  output channel, row shift (dgrad: phase - pad), bias
-    int col_ch[NT][2], col_r[NT][2];
+    // this thread's accumulator columns: n = nt*8 + 2*tq + c  ->  output offset of the column (channel plane + row
+    // shift; dgrad: phase - pad), row shift for the range check, bias
+    int col_off[NT][2], col_r[NT][2];
+    bool col_ok[NT][2];
     float col_bias[NT][2];
+    const int lo_p = p.Lo * p.P;
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
             const int n = nt * 8 + 2 * tq + c;
-            col_ch[nt][c] = -1;
+            col_ok[nt][c] = n < p.N;
+            col_off[nt][c] = 0;
             col_r[nt][c] = 0;
             col_bias[nt][c] = 0.f;
             if (n < p.N) {
                 if (MODE == MODE_FWD) {
-                    col_ch[nt][c] = g * p.N + n;
+                    col_off[nt][c] = (g * p.N + n) * lo_p;
                     if (p.bias) col_bias[nt][c] = p.bias[g * p.N + n];
                 } else {
                     const int ci = n / p.S;
-                    col_ch[nt][c] = g * p.Cig + ci;
                     col_r[nt][c] = n - ci * p.S - p.opad;
+                    col_off[nt][c] = (g * p.Cig + ci) * lo_p + col_r[nt][c] * p.P;
                 }
             }
         }
+    const bool has_g = p.gextra != nullptr, has_x = p.xact != nullptr;
     int tile = blockIdx.y;
     if (tile < p.ntiles) stage_window(p, g, tile, TP, win0, lutd0, lut0, chk);
     cp_async_commit();
@@ -222,22 +226,24 @@ __global__ void __launch_bounds__(kThreads) conv_mma_kernel(const MmaParams p) {
         const int jtot = p.Q * p.P;
         const int row_first = j0 / p.P;
         // per-thread rows: m-tile mt, half h -> position j0 + warp*16*MTW + mt*16 + gq + 8h
-        int base[MTW][2], rowq[MTW][2], ppos[MTW][2];
+        // abase = window address of the row (LUT entries are byte offsets);  orow = output offset of the row
+        const char* abase[MTW][2];
+        int rowo[MTW][2], orow[MTW][2];
+        bool rok[MTW][2];
 #pragma unroll
         for (int mt = 0; mt < MTW; ++mt)
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int j = j0 + warp * 16 * MTW + mt * 16 + gq + 8 * h;
-                if (j < jtot) {
-                    const int rq = j / p.P, pp = j - rq * p.P;
-                    rowq[mt][h] = rq;
-                    ppos[mt][h] = pp;
-                    base[mt][h] = (rq - row_first) * p.Sg * p.P + pp;
-                } else {
-                    rowq[mt][h] = -1;
-                    ppos[mt][h] = 0;
-                    base[mt][h] = 0;
-                }
+                rok[mt][h] = j < jtot;
+                const int rq = j / p.P, pp = j - rq * p.P;
+                // dgrad gathers with row stride 1: the window offset is linear in j, rows past the end of the map
+                // read (and discard) in-bounds garbage; forward rows past the end are pointed at the window start
+                const int base = MODE == MODE_FWD ? (rok[mt][h] ? (rq - row_first) * p.Sg * p.P + pp : 0)
+                                                  : j - row_first * p.P;
+                abase[mt][h] = reinterpret_cast<const char*>(win + base);
+                rowo[mt][h] = MODE == MODE_FWD ? rq : p.S * rq;
+                orow[mt][h] = rowo[mt][h] * p.P + pp;
             }
         float acc[MTW][NT][4];
 #pragma unroll
@@ -247,51 +253,86 @@ __global__ void __launch_bounds__(kThreads) conv_mma_kernel(const MmaParams p) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
 
-        for (int k0 = 0; k0 < p.KKpad; k0 += 8) {
+        const float* wr0 = wsm + tq * p.NS + gq;
+        const float* wr1 = wr0 + 4 * p.NS;
+        const int wstep = 8 * p.NS;
+        for (int k0 = 0; k0 < p.KKpad; k0 += 8, wr0 += wstep, wr1 += wstep) {
             const int l0 = lut[k0 + tq], l1 = lut[k0 + tq + 4];
             uint32_t a[MTW][4];
+            if (MODE == MODE_FWD) {
 #pragma unroll
-            for (int mt = 0; mt < MTW; ++mt) {
-                a[mt][0] = f2tf32(win[l0 + base[mt][0]]);
-                a[mt][1] = f2tf32(win[l0 + base[mt][1]]);
-                a[mt][2] = f2tf32(win[l1 + base[mt][0]]);
-                a[mt][3] = f2tf32(win[l1 + base[mt][1]]);
+                for (int mt = 0; mt < MTW; ++mt) {
+                    a[mt][0] = f2tf32(*reinterpret_cast<const float*>(abase[mt][0] + l0));
+                    a[mt][1] = f2tf32(*reinterpret_cast<const float*>(abase[mt][1] + l0));
+                    a[mt][2] = f2tf32(*reinterpret_cast<const float*>(abase[mt][0] + l1));
+                    a[mt][3] = f2tf32(*reinterpret_cast<const float*>(abase[mt][1] + l1));
+                }
+            } else {
+                // rows are 8 / 16 / 24 ... floats apart: one address per LUT entry, immediates for the rest
+                const float* a0 = reinterpret_cast<const float*>(abase[0][0] + l0);
+                const float* a1 = reinterpret_cast<const float*>(abase[0][0] + l1);
+#pragma unroll
+                for (int mt = 0; mt < MTW; ++mt) {
+                    a[mt][0] = f2tf32(a0[16 * mt]);
+                    a[mt][1] = f2tf32(a0[16 * mt + 8]);
+                    a[mt][2] = f2tf32(a1[16 * mt]);
+                    a[mt][3] = f2tf32(a1[16 * mt + 8]);
+                }
             }
-            const float* wr = wsm + k0 * p.NS;
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
-                const uint32_t b0 = __float_as_uint(wr[tq * p.NS + nt * 8 + gq]);
-                const uint32_t b1 = __float_as_uint(wr[(tq + 4) * p.NS + nt * 8 + gq]);
+                const uint32_t b0 = __float_as_uint(wr0[nt * 8]);
+                const uint32_t b1 = __float_as_uint(wr1[nt * 8]);
 #pragma unroll
                 for (int mt = 0; mt < MTW; ++mt) mma_tf32(acc[mt][nt], a[mt][0], a[mt][1], a[mt][2], a[mt][3], b0, b1);
             }
         }
-        // ---- epilogue (column -> channel / phase mapping hoisted out of the tile loop: col_ch, col_r)
-        const int lo_p = p.Lo * p.P;
+        // ---- epilogue.  Forward: bias + activation, store.  Data gradient: (+ FM gradient) x act'(saved output):
+        // the loads of one m-tile (2 rows x NT x 2 columns, two tensors) are all issued before the first use
+        // (the first version loaded / used / stored one element at a time and spent half of its stall samples there)
         const int bbase = b * p.Co * lo_p;
+        constexpr int HB = NT <= 2 ? 2 : 1;        // row halves per batch of loads (bounds the registers)
 #pragma unroll
         for (int mt = 0; mt < MTW; ++mt)
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                if (rowq[mt][h] < 0) continue;
-                const int rbase = (MODE == MODE_FWD ? rowq[mt][h] : p.S * rowq[mt][h]);
+            for (int hb = 0; hb < 2; hb += HB) {
+                int idx[HB][NT][2];
+                bool ok[HB][NT][2];
+                float ge[HB][NT][2], xa[HB][NT][2];
 #pragma unroll
-                for (int nt = 0; nt < NT; ++nt)
+                for (int hh = 0; hh < HB; ++hh)
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        if (col_ch[nt][c] < 0) continue;
-                        const int row_o = rbase + col_r[nt][c];
-                        if (MODE != MODE_FWD && (row_o < 0 || row_o >= p.Lo)) continue;
-                        const int idx = bbase + col_ch[nt][c] * lo_p + row_o * p.P + ppos[mt][h];
-                        float v = acc[mt][nt][2 * h + c];
-                        if (MODE == MODE_FWD) {
-                            v = apply_act(v + col_bias[nt][c], p.act, p.slope);
-                        } else {
-                            if (p.gextra) v += p.gextra[idx];
-                            if (p.xact) v *= act_grad_from_out(p.xact[idx], p.act, p.slope);
+                    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            const int h = hb + hh;
+                            bool o = rok[mt][h] && col_ok[nt][c];
+                            if (MODE != MODE_FWD) {
+                                const int row_o = rowo[mt][h] + col_r[nt][c];
+                                o = o && row_o >= 0 && row_o < p.Lo;
+                            }
+                            ok[hh][nt][c] = o;
+                            idx[hh][nt][c] = bbase + col_off[nt][c] + orow[mt][h];
+                            if (MODE != MODE_FWD) {
+                                ge[hh][nt][c] = (o && has_g) ? __ldg(p.gextra + idx[hh][nt][c]) : 0.f;
+                                xa[hh][nt][c] = (o && has_x) ? __ldg(p.xact + idx[hh][nt][c]) : 1.f;
+                            }
                         }
-                        p.out[idx] = v;
-                    }
+#pragma unroll
+                for (int hh = 0; hh < HB; ++hh)
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            float v = acc[mt][nt][2 * (hb + hh) + c];
+                            if (MODE == MODE_FWD) {
+                                v = apply_act(v + col_bias[nt][c], p.act, p.slope);
+                            } else {
+                                v += ge[hh][nt][c];
+                                if (has_x) v *= act_grad_from_out(xa[hh][nt][c], p.act, p.slope);
+                            }
+                            if (ok[hh][nt][c]) p.out[idx[hh][nt][c]] = v;
+                        }
             }
     }
     cp_async_wait_all();
@@ -395,7 +436,7 @@ __global__ void __launch_bounds__(kThreads) conv_mma_wgrad_kernel(const MmaWgrad
         cp_async_commit();
         int lc[NT], sd[MT][2];
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) lc[nt] = lutn[nt] + shw[cin[nt]];
+        for (int nt = 0; nt < NT; ++nt) lc[nt] = (lutn[nt] + shw[cin[nt]]) * 4;      // byte offsets
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
             sd[mt][0] = shd[mt * 16 + gq];
@@ -431,10 +472,12 @@ __global__ void __launch_bounds__(kThreads) conv_mma_wgrad_kernel(const MmaWgrad
                 sdy[mt][1] += v1 + v3;
                 a[mt][0] = f2tf32(v0); a[mt][1] = f2tf32(v1); a[mt][2] = f2tf32(v2); a[mt][3] = f2tf32(v3);
             }
+            const char* wb0 = reinterpret_cast<const char*>(win + bs[0]);
+            const char* wb1 = reinterpret_cast<const char*>(win + bs[1]);
 #pragma unroll
             for (int nt = 0; nt < NT; ++nt) {
-                const uint32_t b0 = f2tf32(win[lc[nt] + bs[0]]);
-                const uint32_t b1 = f2tf32(win[lc[nt] + bs[1]]);
+                const uint32_t b0 = f2tf32(*reinterpret_cast<const float*>(wb0 + lc[nt]));
+                const uint32_t b1 = f2tf32(*reinterpret_cast<const float*>(wb1 + lc[nt]));
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) mma_tf32(acc[mt][nt], a[mt][0], a[mt][1], a[mt][2], a[mt][3], b0, b1);
             }
@@ -493,8 +536,8 @@ int pick_ns(int npad) {
 int g_ctas_per_sm = 6;
 int g_force_mtw = 2;
 
-int grid_y(int G, int ntiles) {
-    int per = (148 * g_ctas_per_sm + G - 1) / G;     // resident CTAs per SM in total
+int grid_y(int G, int ntiles, int ctas_per_sm) {
+    int per = (148 * ctas_per_sm + G - 1) / G;       // resident CTAs per SM in total
     if (per < 1) per = 1;
     if (per > ntiles) per = ntiles;
     return per;
@@ -516,7 +559,13 @@ int launch_mma(MmaParams& p, cudaStream_t st) {
         if (e != cudaSuccess) return (int)e;
     }
     const int G = p.Cx / p.Cxg;
-    dim3 grid((unsigned)G, (unsigned)grid_y(G, p.ntiles));
+    // persistent grid = what is really resident (registers / shared memory may allow fewer CTAs than the target:
+    // a grid sized for more would run a second, mostly idle wave)
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_mma_kernel<MODE, NT, MTW>, kThreads, smem) !=
+            cudaSuccess || occ < 1)
+        occ = 1;
+    dim3 grid((unsigned)G, (unsigned)grid_y(G, p.ntiles, occ < g_ctas_per_sm ? occ : g_ctas_per_sm));
     conv_mma_kernel<MODE, NT, MTW><<<grid, kThreads, smem, st>>>(p);
     LCT_RETURN_IF_LAUNCH_FAILED();
     return 0;
@@ -525,7 +574,6 @@ int launch_mma(MmaParams& p, cudaStream_t st) {
 template <int MODE, int NT>
 int launch_mma_mtw(MmaParams& p, cudaStream_t st) {
     // short layers: 128-position tiles keep more CTAs busy
-    if (g_force_mtw == 1) return launch_mma<MODE, NT, 1>(p, st);
     if (g_force_mtw == 2) return launch_mma<MODE, NT, 2>(p, st);
     if (g_force_mtw == 4) return launch_mma<MODE, NT, 4>(p, st);
     if ((int64_t)p.Q * p.P * p.B * (p.Cx / p.Cxg) < 148 * 256) return launch_mma<MODE, NT, 2>(p, st);

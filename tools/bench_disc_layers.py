@@ -1,0 +1,59 @@
+"""Grouped discriminator convolutions (conv_mma kernels) timed layer by layer from CUDA graphs of 20 launches, on the
+shapes of the D step (batch 2B = 16) or the G step (B = 8):  python tools/bench_disc_layers.py [B]
+
+Prints per layer: forward / data-gradient (with the fused FM-gradient + LeakyReLU' epilogue) / weight-gradient time and
+the achieved GB/s on the algorithmic bytes (fwd: x + y; dgrad: dy + gextra + xact + dx; wgrad: x + dy)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "lct-gan_b200")); sys.path.insert(0, ROOT)
+import torch
+from lctgan import ops
+dev = torch.device("cuda:0")
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+
+
+def gtime(run, n=20):
+    s = torch.cuda.Stream(); s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(3): run()
+    torch.cuda.current_stream().wait_stream(s); torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(n): run()
+    g.replay(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n * 1e3
+
+
+# (name, Cin, Cout, K, S, groups, Lin, P)
+LAYERS = [
+    ("MSD0.convs1", 16, 64, 41, 4, 4, 32000, 1),
+    ("MSD0.convs2", 64, 256, 41, 4, 16, 8000, 1),
+    ("MSD0.convs3", 256, 1024, 41, 4, 64, 2000, 1),
+    ("MSD0.convs4", 1024, 1024, 41, 4, 256, 500, 1),
+    ("MSD1.convs1", 16, 64, 41, 4, 4, 16001, 1),
+    ("MPD2.convs1", 32, 128, 5, 3, 4, 5334, 2),
+    ("MPD2.convs2", 128, 512, 5, 3, 16, 1778, 2),
+    ("MPD2.convs3", 512, 1024, 5, 3, 64, 593, 2),
+    ("MPD2.convs4", 1024, 1024, 5, 1, 64, 198, 2),
+    ("MPD11.convs1", 32, 128, 5, 3, 4, 970, 11),
+    ("MPD11.convs2", 128, 512, 5, 3, 16, 324, 11),
+    ("MPD11.convs3", 512, 1024, 5, 3, 64, 108, 11),
+]
+tot = [0.0, 0.0, 0.0]
+for name, Cin, Cout, K, S, G, Lin, P in LAYERS:
+    pad = K // 2
+    x = torch.randn(B, Cin, Lin, P, device=dev)
+    w = torch.randn(Cout, Cin // G, K, device=dev) * 0.05
+    b = torch.zeros(Cout, device=dev)
+    y = ops.conv1d_fwd(x, w, b, G, S, pad, act=ops.ACT_LRELU)
+    dy = torch.randn_like(y)
+    t_f = gtime(lambda: ops.conv1d_fwd(x, w, b, G, S, pad, act=ops.ACT_LRELU))
+    t_d = gtime(lambda: ops.conv1d_dgrad(dy, w, x.shape, G, S, pad, gextra=x, xact=x, act=ops.ACT_LRELU))
+    t_w = gtime(lambda: ops.conv1d_wgrad(x, dy, w.shape, G, S, pad))
+    bx, by = x.numel() * 4, y.numel() * 4
+    tot[0] += t_f; tot[1] += t_d; tot[2] += t_w
+    print(f"{name:13s} B={B:2d} x {bx/1e6:6.1f} MB y {by/1e6:6.1f} MB: fwd {t_f:6.1f} us ({(bx+by)/t_f/1e3:5.0f} GB/s)  "
+          f"dgrad {t_d:6.1f} us ({(3*bx+by)/t_d/1e3:5.0f} GB/s)  wgrad {t_w:6.1f} us ({(bx+by)/t_w/1e3:5.0f} GB/s)", flush=True)
+print(f"sum: fwd {tot[0]:.1f} us  dgrad {tot[1]:.1f} us  wgrad {tot[2]:.1f} us")
