@@ -22,6 +22,7 @@
 //
 // Precision: TF32 operands (10-bit mantissa), fp32 accumulation - the "bf16 training" configuration of
 // BASELINE.json (configs[2]) at higher operand precision than bf16.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace {
@@ -353,11 +354,17 @@ struct MmaWgradParams {
     int tiles_per_b, ntiles;
 };
 
-template <int MT, int NT>
-__global__ void __launch_bounds__(kThreads) conv_mma_wgrad_kernel(const MmaWgradParams p) {
+// NT n-tiles per warp, NSPLIT warp groups side by side over the (ci, tap) columns: 4 * NSPLIT warps per CTA.  (With all
+// 21 n-tiles of the MSD layers in one warp the kernel needed 195 registers -> 8 resident warps per SM, and it is
+// bound by the latency of its shared-memory gathers; two groups of 11 n-tiles halve the accumulators.)
+template <int MT, int NT, int NSPLIT>
+__global__ void __launch_bounds__(kThreads * NSPLIT) conv_mma_wgrad_kernel(const MmaWgradParams p) {
     extern __shared__ __align__(16) float sm[];
-    constexpr int TP = 128;                       // positions per tile; each warp takes 32 of them
+    constexpr int TP = 128;                       // positions per tile; each position warp takes 32 of them
+    constexpr int NW = 4 * NSPLIT;
+    constexpr int NTH = kThreads * NSPLIT;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int wp = warp & 3, wn = warp >> 2;
     const int gq = lane >> 2, tq = lane & 3;
     const int g = blockIdx.x;
     const int winsz = p.Cig * p.WS;
@@ -371,11 +378,11 @@ __global__ void __launch_bounds__(kThreads) conv_mma_wgrad_kernel(const MmaWgrad
     int* shd0 = shw1 + p.Cig;                         // [2][16*MT] alignment shift of every dY row
     int* shd1 = shd0 + 16 * MT;
 
-    // LUT of this thread's B columns (kk = nt*8 + gq), constant over tiles (the per-tile shift is added below)
+    // LUT of this thread's B columns (kk = (wn*NT + nt)*8 + gq), constant over tiles (the per-tile shift is added below)
     int lutn[NT], cin[NT];
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
-        const int kk = nt * 8 + gq;
+        const int kk = (wn * NT + nt) * 8 + gq;
         int off = 0, ci = 0;
         if (kk < p.KK) {
             ci = kk / p.K;
@@ -404,13 +411,13 @@ __global__ void __launch_bounds__(kThreads) conv_mma_wgrad_kernel(const MmaWgrad
         const int n_e = ((row_last - row_first) * p.S + p.K) * p.P;
         const int e0 = (row_first * p.S - p.pad) * p.P;
         const int lim = p.Lin * p.P;
-        for (int ch = warp; ch < p.Cig; ch += kThreads / 32) {
+        for (int ch = warp; ch < p.Cig; ch += NW) {
             const int64_t cb = ((int64_t)b * p.Cin + (int64_t)g * p.Cig + ch) * lim;
             const int phase = (int)((cb + e0) & 3);
             warp_copy_row(wbuf + ch * p.WS + phase, p.x + cb, e0, n_e, lim, phase, p.x, lane);
             if (lane == 0) shw[ch] = phase;
         }
-        for (int oc = warp; oc < 16 * MT; oc += kThreads / 32) {
+        for (int oc = warp; oc < 16 * MT; oc += NW) {
             const bool chok = oc < p.N;
             const int64_t cb = ((int64_t)b * p.Cout + (int64_t)g * p.N + (chok ? oc : 0)) * jtot;
             const int phase = (int)((cb + j0) & 3);
@@ -443,14 +450,13 @@ __global__ void __launch_bounds__(kThreads) conv_mma_wgrad_kernel(const MmaWgrad
             sd[mt][1] = shd[mt * 16 + gq + 8];
         }
 
-        const int b = tile / p.tiles_per_b, jt = tile - b * p.tiles_per_b;
+        const int jt = tile % p.tiles_per_b;
         const int j0 = jt * TP;
         const int row_first = j0 / p.P;
-        (void)b;
         // this warp's 32 positions: 4 k-steps of 8
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
-            const int pl = warp * 32 + ks * 8;               // tile-local position of this k-step
+            const int pl = wp * 32 + ks * 8;                 // tile-local position of this k-step
             int bs[2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -484,13 +490,13 @@ __global__ void __launch_bounds__(kThreads) conv_mma_wgrad_kernel(const MmaWgrad
         }
     }
     cp_async_wait_all();
-    // ---- flush: reduce the 4 warps' partial tiles in shared memory (the window buffers are free now),
+    // ---- flush: reduce the 4 position warps' partial tiles in shared memory (the window buffers are free now),
     // then one atomic per (weight, CTA)
     __syncthreads();
-    float* red = sm;                                   // [16*MT][NT*8]
-    constexpr int RS = NT * 8;
-    for (int wv = 0; wv < kThreads / 32; ++wv) {
-        if (warp == wv) {
+    float* red = sm;                                   // [16*MT][NT*NSPLIT*8]
+    constexpr int RS = NT * NSPLIT * 8;
+    for (int wv = 0; wv < 4; ++wv) {
+        if (wp == wv) {
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
@@ -500,7 +506,7 @@ __global__ void __launch_bounds__(kThreads) conv_mma_wgrad_kernel(const MmaWgrad
                     for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
                         for (int c = 0; c < 2; ++c) {
-                            const int kk = nt * 8 + 2 * tq + c;
+                            const int kk = (wn * NT + nt) * 8 + 2 * tq + c;
                             if (wv == 0) red[oc * RS + kk] = acc[mt][nt][2 * h + c];
                             else red[oc * RS + kk] += acc[mt][nt][2 * h + c];
                         }
@@ -508,11 +514,11 @@ __global__ void __launch_bounds__(kThreads) conv_mma_wgrad_kernel(const MmaWgrad
         }
         __syncthreads();
     }
-    for (int idx = tid; idx < p.N * p.KK; idx += kThreads) {
+    for (int idx = tid; idx < p.N * p.KK; idx += NTH) {
         const int oc = idx / p.KK, kk = idx - oc * p.KK;
         atomicAdd(&p.dw[((size_t)g * p.N + oc) * p.KK + kk], red[oc * RS + kk]);
     }
-    if (p.db) {
+    if (p.db && wn == 0) {
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
@@ -668,7 +674,14 @@ LCT_API int lct_conv_mma_dgrad(const float* dy, const float* w, const float* wim
     }
 }
 
-template <int MT, int NT>
+// resident CTAs per SM targeted by the weight-gradient grid (LCT_WGRAD_CTAS overrides: tuning experiments)
+int g_wgrad_ctas_per_sm = [] {
+    const char* e = getenv("LCT_WGRAD_CTAS");
+    const int v = e ? atoi(e) : 0;
+    return v > 0 ? v : 3;
+}();
+
+template <int MT, int NT, int NSPLIT>
 int launch_wgrad(MmaWgradParams& p, cudaStream_t st) {
     const int TP = 128;
     const int rows_max = TP / p.P + 2;
@@ -678,19 +691,26 @@ int launch_wgrad(MmaWgradParams& p, cudaStream_t st) {
     p.tiles_per_b = (int)ceil_div64((int64_t)p.Lout * p.P, TP);
     p.ntiles = p.B * p.tiles_per_b;
     size_t smem = ((size_t)2 * p.Cig * p.WS + (size_t)2 * 16 * MT * p.DS + 2 * p.Cig + 2 * 16 * MT) * sizeof(float);
-    if (smem < (size_t)16 * MT * NT * 8 * sizeof(float)) smem = (size_t)16 * MT * NT * 8 * sizeof(float);
+    const size_t red = (size_t)16 * MT * NT * NSPLIT * 8 * sizeof(float);
+    if (smem < red) smem = red;
     if (smem > 200 * 1024) return LCT_EUNSUPPORTED;
     if (smem > 40 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(conv_mma_wgrad_kernel<MT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(conv_mma_wgrad_kernel<MT, NT, NSPLIT>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
     const int G = p.Cin / p.Cig;
-    int gy = (148 * 3 + G - 1) / G;      // fewer, longer-lived CTAs than fwd/dgrad: every CTA ends with N x KK atomics
+    // fewer, longer-lived CTAs than fwd/dgrad (every CTA ends with N x KK atomics), and never more than are resident
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_mma_wgrad_kernel<MT, NT, NSPLIT>, kThreads * NSPLIT,
+                                                      smem) != cudaSuccess || occ < 1)
+        occ = 1;
+    const int per_sm = occ < g_wgrad_ctas_per_sm ? occ : g_wgrad_ctas_per_sm;
+    int gy = (148 * per_sm + G - 1) / G;
     if (gy > p.ntiles) gy = p.ntiles;
     if (gy < 1) gy = 1;
     dim3 grid((unsigned)G, (unsigned)gy);
-    conv_mma_wgrad_kernel<MT, NT><<<grid, kThreads, smem, st>>>(p);
+    conv_mma_wgrad_kernel<MT, NT, NSPLIT><<<grid, kThreads * NSPLIT, smem, st>>>(p);
     LCT_RETURN_IF_LAUNCH_FAILED();
     return 0;
 }
@@ -710,17 +730,17 @@ LCT_API int lct_conv_mma_wgrad(const float* x, const float* dy, float* dw, float
     p.KK = p.Cig * p.K;
     const int nt = (p.KK + 7) / 8;
     const int mt = (p.N + 15) / 16;
-#define LCT_WG(MTV, NTV) return launch_wgrad<MTV, NTV>(p, st)
+#define LCT_WG(MTV, NTV, NSV) return launch_wgrad<MTV, NTV, NSV>(p, st)
     if (mt == 1) {
-        if (nt <= 1) LCT_WG(1, 1);
-        if (nt <= 2) LCT_WG(1, 2);
-        if (nt <= 5) LCT_WG(1, 5);
-        if (nt <= 10) LCT_WG(1, 10);
-        if (nt <= 21) LCT_WG(1, 21);
+        if (nt <= 1) LCT_WG(1, 1, 1);
+        if (nt <= 2) LCT_WG(1, 2, 1);
+        if (nt <= 5) LCT_WG(1, 5, 1);
+        if (nt <= 10) LCT_WG(1, 5, 2);
+        if (nt <= 21) LCT_WG(1, 11, 2);
     } else if (mt == 2) {
-        if (nt <= 1) LCT_WG(2, 1);
-        if (nt <= 5) LCT_WG(2, 5);
-        if (nt <= 10) LCT_WG(2, 10);
+        if (nt <= 1) LCT_WG(2, 1, 1);
+        if (nt <= 5) LCT_WG(2, 5, 1);
+        if (nt <= 10) LCT_WG(2, 5, 2);
     }
 #undef LCT_WG
     return LCT_EUNSUPPORTED;
