@@ -309,6 +309,8 @@ def main():
                     "discriminator parameter gradients of the G step inside the discriminators' backward instead of at the "
                     "end of the G phase")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--profile-range", action="store_true", help="bracket the timed steps with cudaProfilerStart/Stop "
+                    "(for `ncu --profile-from-start off`: the launch list of exactly the timed steps; never a bench value)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -391,11 +393,16 @@ def main():
     _lib.reset_kernel_launches()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if args.profile_range:
+        torch.cuda.cudart().cudaProfilerStart()
     e0.record()
     for _ in range(args.steps):
         out = step(noisy_d, clean_d)
     e1.record()
     barrier()
+    if args.profile_range:
+        torch.cuda.cudart().cudaProfilerStop()
+        return
     launches = _lib.kernel_launches() if graphed is None else graphed.launches_per_step * args.steps
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if rank == 0 else None

@@ -46,6 +46,9 @@ struct MmaParams {
     int KK, KKpad, Npad, NS, WS;
     int act; float slope;
     int tiles_per_b, ntiles;
+    int TPe;                               // positions per tile (dgrad: whole rows of P only, <= the CTA's 64*MTW rows)
+    int ES;                                // dgrad: plane stride of the staged output tile
+    int ot_alias;                          // dgrad: the staged tile fits into (and reuses) a window buffer
 };
 
 // fp32 -> tf32, round to nearest / ties away (= cvt.rna.tf32.f32 for every finite input): add half a tf32 ulp to the
@@ -103,12 +106,12 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // stage the input window of `tile` (all Cxg channels of group g) into `buf` with cp.async and write the tile's
 // gather LUT: lutd[kk] = lut0[kk] + (alignment shift of kk's channel)
-__device__ __forceinline__ void stage_window(const MmaParams& p, int g, int tile, int TP, float* buf, int* lutd,
+__device__ __forceinline__ void stage_window(const MmaParams& p, int g, int tile, float* buf, int* lutd,
                                              const int* lut0, const int* chk) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = tile / p.tiles_per_b, jt = tile - b * p.tiles_per_b;
-    const int j0 = jt * TP;
-    const int jend = min(j0 + TP, p.Q * p.P);
+    const int j0 = jt * p.TPe;
+    const int jend = min(j0 + p.TPe, p.Q * p.P);
     const int row_first = j0 / p.P, row_last = (jend - 1) / p.P;
     const int n_e = ((row_last - row_first) * p.Sg + p.Tspan) * p.P;
     const int e0 = (row_first * p.Sg - p.pad_eff) * p.P;   // flat start inside a channel (may be negative)
@@ -140,6 +143,7 @@ __global__ void __launch_bounds__(kThreads) conv_mma_kernel(const MmaParams p) {
     float* win0 = reinterpret_cast<float*>(lutd1 + p.KKpad);
     const int winsz = p.Cxg * p.WS;
     float* win1 = win0 + winsz;
+    float* otile = win1 + winsz;                                  // dgrad: [Cig][ES] staged output tile
 
     // ---- prologue: this group's weights (tf32-rounded, [kk][n]) and the gather LUT
     if (p.wimg) {
@@ -182,8 +186,8 @@ __global__ void __launch_bounds__(kThreads) conv_mma_kernel(const MmaParams p) {
     }
     __syncthreads();
     // this thread's accumulator columns: n = nt*8 + 2*tq + c  ->  output offset of the column (channel plane + row
-    // shift; dgrad: phase - pad), row shift for the range check, bias
-    int col_off[NT][2], col_r[NT][2];
+    // shift), bias;  dgrad: offset inside the staged output tile
+    int col_off[NT][2];
     bool col_ok[NT][2];
     float col_bias[NT][2];
     const int lo_p = p.Lo * p.P;
@@ -194,22 +198,21 @@ __global__ void __launch_bounds__(kThreads) conv_mma_kernel(const MmaParams p) {
             const int n = nt * 8 + 2 * tq + c;
             col_ok[nt][c] = n < p.N;
             col_off[nt][c] = 0;
-            col_r[nt][c] = 0;
             col_bias[nt][c] = 0.f;
             if (n < p.N) {
                 if (MODE == MODE_FWD) {
                     col_off[nt][c] = (g * p.N + n) * lo_p;
                     if (p.bias) col_bias[nt][c] = p.bias[g * p.N + n];
                 } else {
+                    // offset inside the staged output tile: plane of the in-channel, row shift of the stride phase
                     const int ci = n / p.S;
-                    col_r[nt][c] = n - ci * p.S - p.opad;
-                    col_off[nt][c] = (g * p.Cig + ci) * lo_p + col_r[nt][c] * p.P;
+                    col_off[nt][c] = ci * p.ES + (n - ci * p.S) * p.P;
                 }
             }
         }
     const bool has_g = p.gextra != nullptr, has_x = p.xact != nullptr;
     int tile = blockIdx.y;
-    if (tile < p.ntiles) stage_window(p, g, tile, TP, win0, lutd0, lut0, chk);
+    if (tile < p.ntiles) stage_window(p, g, tile, win0, lutd0, lut0, chk);
     cp_async_commit();
 
     int cur = 0;
@@ -219,17 +222,17 @@ __global__ void __launch_bounds__(kThreads) conv_mma_kernel(const MmaParams p) {
         cp_async_wait_all();
         __syncthreads();                       // window + LUT `cur` (and, first time, the weights) visible to all
         const int nxt = tile + gridDim.y;
-        if (nxt < p.ntiles) stage_window(p, g, nxt, TP, cur ? win0 : win1, cur ? lutd0 : lutd1, lut0, chk);
+        if (nxt < p.ntiles) stage_window(p, g, nxt, cur ? win0 : win1, cur ? lutd0 : lutd1, lut0, chk);
         cp_async_commit();
 
         const int b = tile / p.tiles_per_b, jt = tile - b * p.tiles_per_b;
-        const int j0 = jt * TP;
-        const int jtot = p.Q * p.P;
+        const int j0 = jt * p.TPe;
+        const int jtot = min(p.Q * p.P, j0 + p.TPe);
         const int row_first = j0 / p.P;
         // per-thread rows: m-tile mt, half h -> position j0 + warp*16*MTW + mt*16 + gq + 8h
         // abase = window address of the row (LUT entries are byte offsets);  orow = output offset of the row
         const char* abase[MTW][2];
-        int rowo[MTW][2], orow[MTW][2];
+        int orow[MTW][2];
         bool rok[MTW][2];
 #pragma unroll
         for (int mt = 0; mt < MTW; ++mt)
@@ -243,8 +246,8 @@ __global__ void __launch_bounds__(kThreads) conv_mma_kernel(const MmaParams p) {
                 const int base = MODE == MODE_FWD ? (rok[mt][h] ? (rq - row_first) * p.Sg * p.P + pp : 0)
                                                   : j - row_first * p.P;
                 abase[mt][h] = reinterpret_cast<const char*>(win + base);
-                rowo[mt][h] = MODE == MODE_FWD ? rq : p.S * rq;
-                orow[mt][h] = rowo[mt][h] * p.P + pp;
+                // forward: offset of the row in an output plane;  dgrad: in a plane of the staged tile
+                orow[mt][h] = MODE == MODE_FWD ? rq * p.P + pp : (rq - row_first) * p.S * p.P + pp;
             }
         float acc[MTW][NT][4];
 #pragma unroll
@@ -288,53 +291,73 @@ __global__ void __launch_bounds__(kThreads) conv_mma_kernel(const MmaParams p) {
                 for (int mt = 0; mt < MTW; ++mt) mma_tf32(acc[mt][nt], a[mt][0], a[mt][1], a[mt][2], a[mt][3], b0, b1);
             }
         }
-        // ---- epilogue.  Forward: bias + activation, store.  Data gradient: (+ FM gradient) x act'(saved output):
-        // the loads of one m-tile (2 rows x NT x 2 columns, two tensors) are all issued before the first use
-        // (the first version loaded / used / stored one element at a time and spent half of its stall samples there)
         const int bbase = b * p.Co * lo_p;
-        constexpr int HB = NT <= 2 ? 2 : 1;        // row halves per batch of loads (bounds the registers)
+        if (MODE == MODE_FWD) {
+            // ---- forward epilogue: bias + activation; 8 consecutive positions of a channel per 8 lanes (full sectors)
 #pragma unroll
-        for (int mt = 0; mt < MTW; ++mt)
+            for (int mt = 0; mt < MTW; ++mt)
 #pragma unroll
-            for (int hb = 0; hb < 2; hb += HB) {
-                int idx[HB][NT][2];
-                bool ok[HB][NT][2];
-                float ge[HB][NT][2], xa[HB][NT][2];
-#pragma unroll
-                for (int hh = 0; hh < HB; ++hh)
+                for (int h = 0; h < 2; ++h)
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
                         for (int c = 0; c < 2; ++c) {
-                            const int h = hb + hh;
-                            bool o = rok[mt][h] && col_ok[nt][c];
-                            if (MODE != MODE_FWD) {
-                                const int row_o = rowo[mt][h] + col_r[nt][c];
-                                o = o && row_o >= 0 && row_o < p.Lo;
-                            }
-                            ok[hh][nt][c] = o;
-                            idx[hh][nt][c] = bbase + col_off[nt][c] + orow[mt][h];
-                            if (MODE != MODE_FWD) {
-                                ge[hh][nt][c] = (o && has_g) ? __ldg(p.gextra + idx[hh][nt][c]) : 0.f;
-                                xa[hh][nt][c] = (o && has_x) ? __ldg(p.xact + idx[hh][nt][c]) : 1.f;
-                            }
+                            const float v = apply_act(acc[mt][nt][2 * h + c] + col_bias[nt][c], p.act, p.slope);
+                            if (rok[mt][h] && col_ok[nt][c]) p.out[bbase + col_off[nt][c] + orow[mt][h]] = v;
                         }
+        } else {
+            // ---- data-gradient epilogue.  The accumulator layout scatters a channel's run over lanes (stride-S rows,
+            // 2 of 4 lanes per phase pair): written straight to global memory it cost 3-4x the sectors in loads of the
+            // FM gradient / saved activation and in partial-sector stores, one element at a time.  Instead the tile is
+            // transposed through shared memory (a tile covers whole rows of P, so every in-channel owns ONE contiguous
+            // run of nrows*S*P outputs) and finished by a coalesced pass:  dx = (tile + gextra) * act'(xact), with the
+            // 16 loads of a thread issued before their first use.
+            // the staged tile lives in the window that was just consumed when it fits there (one more barrier), else in
+            // its own buffer
+            float* ot = p.ot_alias ? win : otile;
+            if (p.ot_alias) __syncthreads();
 #pragma unroll
-                for (int hh = 0; hh < HB; ++hh)
+            for (int mt = 0; mt < MTW; ++mt)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-                        for (int c = 0; c < 2; ++c) {
-                            float v = acc[mt][nt][2 * (hb + hh) + c];
-                            if (MODE == MODE_FWD) {
-                                v = apply_act(v + col_bias[nt][c], p.act, p.slope);
-                            } else {
-                                v += ge[hh][nt][c];
-                                if (has_x) v *= act_grad_from_out(xa[hh][nt][c], p.act, p.slope);
-                            }
-                            if (ok[hh][nt][c]) p.out[idx[hh][nt][c]] = v;
-                        }
+                        for (int c = 0; c < 2; ++c)
+                            if (rok[mt][h] && col_ok[nt][c]) ot[col_off[nt][c] + orow[mt][h]] = acc[mt][nt][2 * h + c];
+            __syncthreads();
+            const int nrows = (jtot - j0) / p.P;                  // whole rows (TPe is a multiple of P)
+            const int E = nrows * p.S * p.P;
+            const int total = p.Cig * E;
+            const float inv_e = 1.f / (float)E;
+            const int gpos0 = (p.S * row_first - p.opad) * p.P;   // position of the run's first element in its plane
+            const int cbase = bbase + g * p.Cig * lo_p + gpos0;
+            constexpr int EU = 8;
+            for (int i0 = tid; i0 < total; i0 += EU * kThreads) {
+                float ge[EU], xa[EU];
+                int so[EU], gi[EU];
+                bool ok[EU];
+#pragma unroll
+                for (int q = 0; q < EU; ++q) {
+                    const int i = i0 + q * kThreads;
+                    const int ci = __float2int_rd(((float)i + 0.5f) * inv_e);      // i / E (exact: i < 2^20)
+                    const int e = i - ci * E;
+                    ok[q] = i < total && (gpos0 + e) >= 0 && (gpos0 + e) < lo_p;
+                    so[q] = ci * p.ES + e;
+                    gi[q] = cbase + ci * lo_p + e;
+                    ge[q] = (ok[q] && has_g) ? __ldg(p.gextra + gi[q]) : 0.f;
+                    xa[q] = (ok[q] && has_x) ? __ldg(p.xact + gi[q]) : 1.f;
+                }
+#pragma unroll
+                for (int q = 0; q < EU; ++q)
+                    if (ok[q]) {
+                        float v = ot[so[q]] + ge[q];
+                        if (has_x) v *= act_grad_from_out(xa[q], p.act, p.slope);
+                        p.out[gi[q]] = v;
+                    }
             }
+            // (the next tile's scatter comes after the barrier at the top of the loop: no second barrier needed)
+        }
     }
     cp_async_wait_all();
 }
@@ -543,7 +566,7 @@ int g_ctas_per_sm = 6;
 int g_force_mtw = 2;
 
 int grid_y(int G, int ntiles, int ctas_per_sm) {
-    int per = (148 * ctas_per_sm + G - 1) / G;       // resident CTAs per SM in total
+    int per = 148 * ctas_per_sm / G;                 // rounded down: one CTA too many per group would be a second wave
     if (per < 1) per = 1;
     if (per > ntiles) per = ntiles;
     return per;
@@ -555,9 +578,13 @@ int launch_mma(MmaParams& p, cudaStream_t st) {
     const int rows_max = TP / p.P + 2;
     const int nr_max = (rows_max - 1) * p.Sg + p.Tspan;
     p.WS = (nr_max * p.P + 3 + 3) & ~3;      // + up to 3 floats of alignment shift
-    p.tiles_per_b = (int)ceil_div64((int64_t)p.Q * p.P, TP);
+    p.TPe = MODE == MODE_FWD ? TP : (TP / p.P) * p.P;      // dgrad tiles hold whole rows of P (P <= 16 << TP)
+    p.ES = MODE == MODE_FWD ? 0 : ((TP / p.P) * p.S * p.P) | 1;
+    p.tiles_per_b = (int)ceil_div64((int64_t)p.Q * p.P, p.TPe);
     p.ntiles = p.B * p.tiles_per_b;
-    size_t smem = ((size_t)p.KKpad * p.NS + (size_t)4 * p.KKpad + (size_t)2 * p.Cxg * p.WS) * sizeof(float);
+    p.ot_alias = MODE != MODE_FWD && p.Cig * p.ES <= p.Cxg * p.WS;
+    size_t smem = ((size_t)p.KKpad * p.NS + (size_t)4 * p.KKpad + (size_t)2 * p.Cxg * p.WS +
+                   ((MODE == MODE_FWD || p.ot_alias) ? 0 : (size_t)p.Cig * p.ES)) * sizeof(float);
     if (smem > 200 * 1024) return LCT_EUNSUPPORTED;
     if (smem > 40 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(conv_mma_kernel<MODE, NT, MTW>,
@@ -706,7 +733,7 @@ int launch_wgrad(MmaWgradParams& p, cudaStream_t st) {
                                                       smem) != cudaSuccess || occ < 1)
         occ = 1;
     const int per_sm = occ < g_wgrad_ctas_per_sm ? occ : g_wgrad_ctas_per_sm;
-    int gy = (148 * per_sm + G - 1) / G;
+    int gy = 148 * per_sm / G;                // rounded down: no second wave
     if (gy > p.ntiles) gy = p.ntiles;
     if (gy < 1) gy = 1;
     dim3 grid((unsigned)G, (unsigned)gy);
