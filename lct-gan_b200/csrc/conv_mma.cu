@@ -23,12 +23,27 @@
 // Precision: TF32 operands (10-bit mantissa), fp32 accumulation - the "bf16 training" configuration of
 // BASELINE.json (configs[2]) at higher operand precision than bf16.
 #include <cstdlib>
+#include <type_traits>
 #include "common.cuh"
 
 namespace {
 
 constexpr int kThreads = 128;   // 4 warps
 enum { MODE_FWD = 0, MODE_DGRAD = 1 };
+
+// n / d by multiplication (d small and n * d < 2^32: rows of P, batch index of a tile); d == 1 and the unsafe range
+// fall back to the identity / a real unsigned division.  The signed `j / p.P` sequences were ~20 instructions each,
+// several per thread and tile.
+struct FastDiv { uint32_t mul, d; };
+__device__ __forceinline__ int fdiv(int n, FastDiv f) {
+    return f.d == 1 ? n : (f.mul ? (int)__umulhi((uint32_t)n, f.mul) : (int)((uint32_t)n / f.d));
+}
+FastDiv make_fdiv(int64_t d, int64_t max_n) {
+    FastDiv f;
+    f.d = (uint32_t)d;
+    f.mul = (d > 1 && max_n * d < (1LL << 32)) ? (uint32_t)((1ULL << 32) / (uint64_t)d) + 1u : 0u;
+    return f;
+}
 
 struct MmaParams {
     const float* x;        // gathered tensor  [B][Cx][Lx][P]   (fwd: input, dgrad: dY)
@@ -49,6 +64,7 @@ struct MmaParams {
     int TPe;                               // positions per tile (dgrad: whole rows of P only, <= the CTA's 64*MTW rows)
     int ES;                                // dgrad: plane stride of the staged output tile
     int ot_alias;                          // dgrad: the staged tile fits into (and reuses) a window buffer
+    FastDiv fP, fT;                        // division by P / by tiles_per_b
 };
 
 // fp32 -> tf32, round to nearest / ties away (= cvt.rna.tf32.f32 for every finite input): add half a tf32 ulp to the
@@ -109,10 +125,10 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __device__ __forceinline__ void stage_window(const MmaParams& p, int g, int tile, float* buf, int* lutd,
                                              const int* lut0, const int* chk) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = tile / p.tiles_per_b, jt = tile - b * p.tiles_per_b;
+    const int b = fdiv(tile, p.fT), jt = tile - b * p.tiles_per_b;
     const int j0 = jt * p.TPe;
     const int jend = min(j0 + p.TPe, p.Q * p.P);
-    const int row_first = j0 / p.P, row_last = (jend - 1) / p.P;
+    const int row_first = fdiv(j0, p.fP), row_last = fdiv(jend - 1, p.fP);
     const int n_e = ((row_last - row_first) * p.Sg + p.Tspan) * p.P;
     const int e0 = (row_first * p.Sg - p.pad_eff) * p.P;   // flat start inside a channel (may be negative)
     const int lim = p.Lx * p.P;
@@ -211,6 +227,8 @@ __global__ void __launch_bounds__(kThreads) conv_mma_kernel(const MmaParams p) {
             }
         }
     const bool has_g = p.gextra != nullptr, has_x = p.xact != nullptr;
+    // act'(saved output) = 1 where it is positive, else: LeakyReLU slope / 0 for ReLU / 1 without activation
+    const float dslope = !has_x ? 1.f : (p.act == LCT_ACT_LRELU ? p.slope : (p.act == LCT_ACT_RELU ? 0.f : 1.f));
     int tile = blockIdx.y;
     if (tile < p.ntiles) stage_window(p, g, tile, win0, lutd0, lut0, chk);
     cp_async_commit();
@@ -225,10 +243,10 @@ __global__ void __launch_bounds__(kThreads) conv_mma_kernel(const MmaParams p) {
         if (nxt < p.ntiles) stage_window(p, g, nxt, cur ? win0 : win1, cur ? lutd0 : lutd1, lut0, chk);
         cp_async_commit();
 
-        const int b = tile / p.tiles_per_b, jt = tile - b * p.tiles_per_b;
+        const int b = fdiv(tile, p.fT), jt = tile - b * p.tiles_per_b;
         const int j0 = jt * p.TPe;
         const int jtot = min(p.Q * p.P, j0 + p.TPe);
-        const int row_first = j0 / p.P;
+        const int row_first = fdiv(j0, p.fP);
         // per-thread rows: m-tile mt, half h -> position j0 + warp*16*MTW + mt*16 + gq + 8h
         // abase = window address of the row (LUT entries are byte offsets);  orow = output offset of the row
         const char* abase[MTW][2];
@@ -240,7 +258,7 @@ __global__ void __launch_bounds__(kThreads) conv_mma_kernel(const MmaParams p) {
             for (int h = 0; h < 2; ++h) {
                 const int j = j0 + warp * 16 * MTW + mt * 16 + gq + 8 * h;
                 rok[mt][h] = j < jtot;
-                const int rq = j / p.P, pp = j - rq * p.P;
+                const int rq = fdiv(j, p.fP), pp = j - rq * p.P;
                 // dgrad gathers with row stride 1: the window offset is linear in j, rows past the end of the map
                 // read (and discard) in-bounds garbage; forward rows past the end are pointed at the window start
                 const int base = MODE == MODE_FWD ? (rok[mt][h] ? (rq - row_first) * p.Sg * p.P + pp : 0)
@@ -326,36 +344,55 @@ __global__ void __launch_bounds__(kThreads) conv_mma_kernel(const MmaParams p) {
                         for (int c = 0; c < 2; ++c)
                             if (rok[mt][h] && col_ok[nt][c]) ot[col_off[nt][c] + orow[mt][h]] = acc[mt][nt][2 * h + c];
             __syncthreads();
-            const int nrows = (jtot - j0) / p.P;                  // whole rows (TPe is a multiple of P)
+            const int nrows = fdiv(jtot - j0, p.fP);                // whole rows (TPe is a multiple of P)
             const int E = nrows * p.S * p.P;
-            const int total = p.Cig * E;
-            const float inv_e = 1.f / (float)E;
             const int gpos0 = (p.S * row_first - p.opad) * p.P;   // position of the run's first element in its plane
             const int cbase = bbase + g * p.Cig * lo_p + gpos0;
-            constexpr int EU = 8;
-            for (int i0 = tid; i0 < total; i0 += EU * kThreads) {
-                float ge[EU], xa[EU];
-                int so[EU], gi[EU];
-                bool ok[EU];
+            const float* __restrict__ gep = p.gextra;
+            const float* __restrict__ xap = p.xact;
+            float* __restrict__ outp = p.out;
+            // 4 channels x 2 elements (128 apart) per thread and step.  The loads are unconditional (elements outside the
+            // tile / the map read a valid dummy address) and specialised on which tensors exist, so that the compiler
+            // issues all 16 of them before the first use; only the stores are predicated.  (A predicated version was
+            // compiled into load -> compare -> next load chains.)
+            const int safe = cbase + min(max(-gpos0, 0), lo_p - 1 - gpos0);   // (32-bit offsets: B*C*L*P < 2^31)
+            auto pass = [&](auto HG, auto HX) {
+                constexpr int CU = 4, EU = 2;
+                for (int ci0 = 0; ci0 < p.Cig; ci0 += CU)
+                    for (int e0 = tid; e0 < E; e0 += EU * kThreads) {
+                        float ge[CU][EU], xa[CU][EU];
+                        int gi[CU][EU];
+                        bool ok[CU][EU];
 #pragma unroll
-                for (int q = 0; q < EU; ++q) {
-                    const int i = i0 + q * kThreads;
-                    const int ci = __float2int_rd(((float)i + 0.5f) * inv_e);      // i / E (exact: i < 2^20)
-                    const int e = i - ci * E;
-                    ok[q] = i < total && (gpos0 + e) >= 0 && (gpos0 + e) < lo_p;
-                    so[q] = ci * p.ES + e;
-                    gi[q] = cbase + ci * lo_p + e;
-                    ge[q] = (ok[q] && has_g) ? __ldg(p.gextra + gi[q]) : 0.f;
-                    xa[q] = (ok[q] && has_x) ? __ldg(p.xact + gi[q]) : 1.f;
-                }
+                        for (int q = 0; q < EU; ++q) {
+                            const int e = e0 + q * kThreads;
+                            const bool eok = e < E && (unsigned)(gpos0 + e) < (unsigned)lo_p;
 #pragma unroll
-                for (int q = 0; q < EU; ++q)
-                    if (ok[q]) {
-                        float v = ot[so[q]] + ge[q];
-                        if (has_x) v *= act_grad_from_out(xa[q], p.act, p.slope);
-                        p.out[gi[q]] = v;
+                            for (int u = 0; u < CU; ++u) {
+                                ok[u][q] = eok && (ci0 + u) < p.Cig;
+                                gi[u][q] = ok[u][q] ? cbase + (ci0 + u) * lo_p + e : safe;
+                            }
+                        }
+#pragma unroll
+                        for (int q = 0; q < EU; ++q)
+#pragma unroll
+                            for (int u = 0; u < CU; ++u) {
+                                ge[u][q] = decltype(HG)::value ? __ldg(gep + gi[u][q]) : 0.f;
+                                xa[u][q] = decltype(HX)::value ? __ldg(xap + gi[u][q]) : 1.f;
+                            }
+#pragma unroll
+                        for (int q = 0; q < EU; ++q)
+#pragma unroll
+                            for (int u = 0; u < CU; ++u)
+                                if (ok[u][q])
+                                    outp[gi[u][q]] = (ot[(ci0 + u) * p.ES + e0 + q * kThreads] + ge[u][q]) *
+                                                     (xa[u][q] > 0.f ? 1.f : dslope);
                     }
-            }
+            };
+            if (has_g && has_x) pass(std::true_type{}, std::true_type{});
+            else if (has_x) pass(std::false_type{}, std::true_type{});
+            else if (has_g) pass(std::true_type{}, std::false_type{});
+            else pass(std::false_type{}, std::false_type{});
             // (the next tile's scatter comes after the barrier at the top of the loop: no second barrier needed)
         }
     }
@@ -375,6 +412,7 @@ struct MmaWgradParams {
     int K, S, pad;
     int KK, WS, DS;
     int tiles_per_b, ntiles;
+    FastDiv fP, fT;                        // division by P / by tiles_per_b
 };
 
 // NT n-tiles per warp, NSPLIT warp groups side by side over the (ci, tap) columns: 4 * NSPLIT warps per CTA.  (With all
@@ -427,10 +465,10 @@ __global__ void __launch_bounds__(kThreads * NSPLIT) conv_mma_wgrad_kernel(const
     const int jtot = p.Lout * p.P;
 
     auto stage = [&](int tile, float* wbuf, float* dbuf, int* shw, int* shd) {
-        const int b = tile / p.tiles_per_b, jt = tile - b * p.tiles_per_b;
+        const int b = fdiv(tile, p.fT), jt = tile - b * p.tiles_per_b;
         const int j0 = jt * TP;
         const int jend = min(j0 + TP, jtot);
-        const int row_first = j0 / p.P, row_last = (jend - 1) / p.P;
+        const int row_first = fdiv(j0, p.fP), row_last = fdiv(jend - 1, p.fP);
         const int n_e = ((row_last - row_first) * p.S + p.K) * p.P;
         const int e0 = (row_first * p.S - p.pad) * p.P;
         const int lim = p.Lin * p.P;
@@ -473,9 +511,9 @@ __global__ void __launch_bounds__(kThreads * NSPLIT) conv_mma_wgrad_kernel(const
             sd[mt][1] = shd[mt * 16 + gq + 8];
         }
 
-        const int jt = tile % p.tiles_per_b;
+        const int jt = tile - fdiv(tile, p.fT) * p.tiles_per_b;
         const int j0 = jt * TP;
-        const int row_first = j0 / p.P;
+        const int row_first = fdiv(j0, p.fP);
         // this warp's 32 positions: 4 k-steps of 8
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
@@ -485,7 +523,7 @@ __global__ void __launch_bounds__(kThreads * NSPLIT) conv_mma_wgrad_kernel(const
             for (int h = 0; h < 2; ++h) {
                 const int j = j0 + pl + tq + 4 * h;
                 if (j < jtot) {
-                    const int rq = j / p.P, pp = j - rq * p.P;
+                    const int rq = fdiv(j, p.fP), pp = j - rq * p.P;
                     bs[h] = (rq - row_first) * p.S * p.P + pp;
                 } else {
                     bs[h] = 0;                               // dY is zero there
@@ -582,6 +620,8 @@ int launch_mma(MmaParams& p, cudaStream_t st) {
     p.ES = MODE == MODE_FWD ? 0 : ((TP / p.P) * p.S * p.P) | 1;
     p.tiles_per_b = (int)ceil_div64((int64_t)p.Q * p.P, p.TPe);
     p.ntiles = p.B * p.tiles_per_b;
+    p.fP = make_fdiv(p.P, (int64_t)p.Q * p.P + TP);
+    p.fT = make_fdiv(p.tiles_per_b, p.ntiles);
     p.ot_alias = MODE != MODE_FWD && p.Cig * p.ES <= p.Cxg * p.WS;
     size_t smem = ((size_t)p.KKpad * p.NS + (size_t)4 * p.KKpad + (size_t)2 * p.Cxg * p.WS +
                    ((MODE == MODE_FWD || p.ot_alias) ? 0 : (size_t)p.Cig * p.ES)) * sizeof(float);
@@ -717,6 +757,8 @@ int launch_wgrad(MmaWgradParams& p, cudaStream_t st) {
     p.DS = TP + 4;                           // 132: holds the shift, and 132 mod 32 = 4 spreads the A rows over banks
     p.tiles_per_b = (int)ceil_div64((int64_t)p.Lout * p.P, TP);
     p.ntiles = p.B * p.tiles_per_b;
+    p.fP = make_fdiv(p.P, (int64_t)p.Lout * p.P + TP);
+    p.fT = make_fdiv(p.tiles_per_b, p.ntiles);
     size_t smem = ((size_t)2 * p.Cig * p.WS + (size_t)2 * 16 * MT * p.DS + 2 * p.Cig + 2 * 16 * MT) * sizeof(float);
     const size_t red = (size_t)16 * MT * NT * NSPLIT * 8 * sizeof(float);
     if (smem < red) smem = red;
