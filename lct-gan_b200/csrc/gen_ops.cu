@@ -233,6 +233,11 @@ constexpr int kH = 16;
 constexpr int kGruThreads = 256;
 constexpr int kUnitsPerCta = kGruThreads / kH;
 constexpr int kGruPre = 6;     // recurrence steps whose inputs are in flight
+// backward: 232 registers per thread.  256-thread CTAs meant ONE resident CTA (8 warps) per SM and 3.5 waves = 4 rounds of
+// a latency-bound kernel for the frequency blocks (520 CTAs); 64-thread CTAs capped at 204 registers give 5 per SM (10
+// warps): the same units finish in 3 rounds, and the closing shared-memory reduction has 4 contenders instead of 16.
+constexpr int kGruBwdThreads = 64;
+constexpr int kGruBwdUnits = kGruBwdThreads / kH;
 
 __global__ void __launch_bounds__(kGruThreads) gru_fwd_kernel(const float* __restrict__ gi,
                                                               const float* __restrict__ whh,
@@ -306,19 +311,19 @@ __global__ void __launch_bounds__(kGruThreads) gru_fwd_kernel(const float* __res
 
 // BPTT.  dh_in: [rows, ldd] gradient of the GRU output (column (gd/D)*16 + j, shared by both
 // directions).  Writes dgi [rows, GD, 48]; accumulates dwhh [GD,48,16], dbih [GD,48], dbhh [GD,48].
-__global__ void __launch_bounds__(kGruThreads) gru_bwd_kernel(
+__global__ void __maxnreg__(200) gru_bwd_kernel(
     const float* __restrict__ gi, const float* __restrict__ hs, const float* __restrict__ whh,
     const float* __restrict__ bhh, const float* __restrict__ dh_in, int ldd, float* __restrict__ dgi,
     float* __restrict__ dwhh, float* __restrict__ dbih, float* __restrict__ dbhh, SeqGeom geo, int GD, int D) {
     __shared__ float sW[3 * kH * kH];
     __shared__ float sB[6 * kH];
     const int j = threadIdx.x % kH;
-    const int seq = blockIdx.x * kUnitsPerCta + threadIdx.x / kH;
+    const int seq = blockIdx.x * kGruBwdUnits + threadIdx.x / kH;
     const int gd = blockIdx.y;
     const bool valid = seq < geo.nseq;
     const bool rev = (gd % D) == 1;
-    for (int i = threadIdx.x; i < 3 * kH * kH; i += kGruThreads) sW[i] = 0.f;
-    for (int i = threadIdx.x; i < 6 * kH; i += kGruThreads) sB[i] = 0.f;
+    for (int i = threadIdx.x; i < 3 * kH * kH; i += kGruBwdThreads) sW[i] = 0.f;
+    for (int i = threadIdx.x; i < 6 * kH; i += kGruBwdThreads) sB[i] = 0.f;
     float wr[kH], wz[kH], wn[kH];
     const float* w = whh + (size_t)gd * 3 * kH * kH;
 #pragma unroll
@@ -423,8 +428,8 @@ __global__ void __launch_bounds__(kGruThreads) gru_bwd_kernel(
         atomicAdd(&sB[5 * kH + j], sbn_h);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 3 * kH * kH; i += kGruThreads) atomicAdd(&dwhh[(size_t)gd * 3 * kH * kH + i], sW[i]);
-    for (int i = threadIdx.x; i < 3 * kH; i += kGruThreads) {
+    for (int i = threadIdx.x; i < 3 * kH * kH; i += kGruBwdThreads) atomicAdd(&dwhh[(size_t)gd * 3 * kH * kH + i], sW[i]);
+    for (int i = threadIdx.x; i < 3 * kH; i += kGruBwdThreads) {
         atomicAdd(&dbih[gd * 3 * kH + i], sB[i]);
         atomicAdd(&dbhh[gd * 3 * kH + i], sB[3 * kH + i]);
     }
@@ -514,7 +519,7 @@ __global__ void __launch_bounds__(kAttnMaxThreads) attn_bwd_kernel(const float* 
                                                                 const float* __restrict__ lse,
                                                                 const float* __restrict__ dout,
                                                                 float* __restrict__ dqkv, SeqGeom geo, int H,
-                                                                float scale) {
+                                                                float scale, int parts) {
     extern __shared__ __align__(16) float sm[];
     const int L = geo.L, E = H * kHd;
     float* Qs = sm;                          // [L][16] (pre-scaled)
@@ -523,6 +528,7 @@ __global__ void __launch_bounds__(kAttnMaxThreads) attn_bwd_kernel(const float* 
     float* dOs = Vs + (size_t)L * kHd;
     float* Ls = dOs + (size_t)L * kHd;       // [L] log-sum-exp
     float* Ds = Ls + L;                      // [L] rowsum(dO * O)
+    float* red = Ds + L;                     // parts > 1: [parts][L][33] partial sums
     const int seq = blockIdx.x, h = blockIdx.y;
     const int64_t row0 = seq_row0(geo, seq);
     for (int idx = threadIdx.x; idx < L * kHd; idx += (int)blockDim.x) {
@@ -543,6 +549,70 @@ __global__ void __launch_bounds__(kAttnMaxThreads) attn_bwd_kernel(const float* 
         Ls[t] = lse[row * H + h];
     }
     __syncthreads();
+    if (parts > 1) {
+        // short sequences (the frequency blocks, L = 33): one query per thread would leave half of a 64-thread CTA idle
+        // and every thread with a serial loop over all keys.  `parts` threads share a query (pass A) / key (pass B),
+        // each walking 1/parts of the other axis; the partial sums meet in shared memory.
+        const int part = (int)threadIdx.x / L, i = (int)threadIdx.x - part * L;
+        const bool act = part < parts;
+        const int chunk = (L + parts - 1) / parts;
+        const int t0 = part * chunk, t1 = min(L, t0 + chunk);
+        if (act) {
+            float q[kHd], go[kHd], dq[kHd];
+#pragma unroll
+            for (int d = 0; d < kHd; ++d) { q[d] = Qs[i * kHd + d]; go[d] = dOs[i * kHd + d]; dq[d] = 0.f; }
+            const float li = Ls[i], di = Ds[i];
+            for (int t = t0; t < t1; ++t) {
+                float s = 0.f, dp = 0.f;
+#pragma unroll
+                for (int d = 0; d < kHd; ++d) { s += q[d] * Ks[t * kHd + d]; dp += go[d] * Vs[t * kHd + d]; }
+                const float ds = __expf(s - li) * (dp - di);
+#pragma unroll
+                for (int d = 0; d < kHd; ++d) dq[d] += ds * Ks[t * kHd + d];
+            }
+#pragma unroll
+            for (int d = 0; d < kHd; ++d) red[(part * L + i) * (kHd + 1) + d] = dq[d];      // odd row stride: no bank conflicts
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < L * kHd; idx += (int)blockDim.x) {
+            const int i2 = idx / kHd, d = idx - i2 * kHd;
+            float v = 0.f;
+            for (int pp = 0; pp < parts; ++pp) v += red[(pp * L + i2) * (kHd + 1) + d];
+            dqkv[(row0 + (int64_t)i2 * geo.step_stride) * 3 * E + h * kHd + d] = v * scale;
+        }
+        __syncthreads();
+        if (act) {
+            const int t = i;
+            float k[kHd], v[kHd], dk[kHd], dv[kHd];
+#pragma unroll
+            for (int d = 0; d < kHd; ++d) { k[d] = Ks[t * kHd + d]; v[d] = Vs[t * kHd + d]; dk[d] = dv[d] = 0.f; }
+            for (int i2 = t0; i2 < t1; ++i2) {
+                float s = 0.f, dp = 0.f;
+#pragma unroll
+                for (int d = 0; d < kHd; ++d) { s += Qs[i2 * kHd + d] * k[d]; dp += dOs[i2 * kHd + d] * v[d]; }
+                const float pr = __expf(s - Ls[i2]);
+                const float ds = pr * (dp - Ds[i2]);
+#pragma unroll
+                for (int d = 0; d < kHd; ++d) {
+                    dv[d] += pr * dOs[i2 * kHd + d];
+                    dk[d] += ds * Qs[i2 * kHd + d];
+                }
+            }
+#pragma unroll
+            for (int d = 0; d < kHd; ++d) {
+                red[(part * L + t) * (2 * kHd + 1) + d] = dk[d];
+                red[(part * L + t) * (2 * kHd + 1) + kHd + d] = dv[d];
+            }
+        }
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < L * 2 * kHd; idx += (int)blockDim.x) {
+            const int t2 = idx / (2 * kHd), d = idx - t2 * 2 * kHd;      // d < 16: dK, else dV
+            float v = 0.f;
+            for (int pp = 0; pp < parts; ++pp) v += red[(pp * L + t2) * (2 * kHd + 1) + d];
+            dqkv[(row0 + (int64_t)t2 * geo.step_stride) * 3 * E + E + (d / kHd) * E + h * kHd + (d % kHd)] = v;
+        }
+        return;
+    }
     // pass A: one query per thread -> dQ
     for (int i = threadIdx.x; i < L; i += (int)blockDim.x) {
         float q[kHd], go[kHd], dq[kHd];
@@ -659,8 +729,8 @@ LCT_API int lct_gru_bwd(const float* gi, const float* hs, const float* whh, cons
     if (!gi || !hs || !whh || !bhh || !dh_in || !dgi || !dwhh || !dbih || !dbhh || GD <= 0 || D <= 0 || GD % D ||
         GD >= 65536 || !geom_ok(g, nseq, L, inner, outer_stride, inner_stride, step_stride))
         return LCT_EINVAL;
-    dim3 grid((unsigned)ceil_div64(nseq, kUnitsPerCta), (unsigned)GD);
-    gru_bwd_kernel<<<grid, kGruThreads, 0, st>>>(gi, hs, whh, bhh, dh_in, (int)ldd, dgi, dwhh, dbih, dbhh, g, (int)GD,
+    dim3 grid((unsigned)ceil_div64(nseq, kGruBwdUnits), (unsigned)GD);
+    gru_bwd_kernel<<<grid, kGruBwdThreads, 0, st>>>(gi, hs, whh, bhh, dh_in, (int)ldd, dgi, dwhh, dbih, dbhh, g, (int)GD,
                                                  (int)D);
     LCT_RETURN_IF_LAUNCH_FAILED();
     return 0;
@@ -701,15 +771,19 @@ LCT_API int lct_attn_bwd(const float* qkv, const float* out, const float* lse, c
     if (!qkv || !out || !lse || !dout || !dqkv || heads <= 0 || heads >= 65536 ||
         !geom_ok(g, nseq, L, inner, outer_stride, inner_stride, step_stride))
         return LCT_EINVAL;
-    size_t smem = ((size_t)4 * L * kHd + 2 * L) * sizeof(float);
+    // short sequences: several threads per query / key (see the kernel)
+    int parts = L <= 64 ? (int)(128 / L) : 1;
+    if (parts > 4) parts = 4;
+    if (parts < 1) parts = 1;
+    size_t smem = ((size_t)4 * L * kHd + 2 * L + (parts > 1 ? (size_t)parts * L * (2 * kHd + 1) : 0)) * sizeof(float);
     if (smem > 200 * 1024) return LCT_EUNSUPPORTED;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
     dim3 grid((unsigned)nseq, (unsigned)heads);
-    attn_bwd_kernel<<<grid, attn_threads(L), smem, st>>>(qkv, out, lse, dout, dqkv, g, (int)heads,
-                                                      1.f / sqrtf((float)kHd));
+    attn_bwd_kernel<<<grid, attn_threads(parts * L), smem, st>>>(qkv, out, lse, dout, dqkv, g, (int)heads,
+                                                              1.f / sqrtf((float)kHd), parts);
     LCT_RETURN_IF_LAUNCH_FAILED();
     return 0;
 }

@@ -65,3 +65,32 @@ def test_conv_mma(dev, Cin, Cout, K, S, G, L, P):
     assert rel_err(dw.double(), w64.grad) < 2e-4
     assert rel_err(dw, wr.grad) < 3e-3
     assert rel_err(db, br.grad) < 1e-4
+
+
+@pytest.mark.parametrize("has_g,has_x", [(False, False), (True, False), (False, True)])
+@pytest.mark.parametrize("Cin,Cout,K,S,G,L,P", [(16, 64, 41, 4, 4, 1037, 1), (128, 512, 5, 3, 16, 131, 7),
+                                               (1024, 1024, 5, 1, 64, 3, 11)])
+def test_conv_mma_dgrad_epilogue_variants(dev, Cin, Cout, K, S, G, L, P, has_g, has_x):
+    """The coalesced data-gradient pass is specialised on which of (FM gradient, saved activation) exist; ragged map
+    lengths exercise the short last tile and the rows of the polyphase grid that fall outside the map."""
+    from lctgan import ops
+    gen = torch.Generator().manual_seed(L * 3 + P)
+    B = 2
+    pad = K // 2
+    Lout = (L + 2 * pad - K) // S + 1
+    w = torch.randn(Cout, Cin // G, K, generator=gen) / (Cin // G * K) ** 0.5
+    dy = torch.randn(B, Cout, Lout, P, generator=gen)
+    xact = torch.randn(B, Cin, L, P, generator=gen)
+    gextra = torch.randn(B, Cin, L, P, generator=gen) * 0.1
+    x64 = torch.zeros(B, Cin, L, P, dtype=torch.float64, requires_grad=True)
+    y64 = F.conv2d(x64, _tf32(w).unsqueeze(-1), None, stride=(S, 1), padding=(pad, 0), groups=G)
+    (y64 * _tf32(dy)).sum().backward()
+    ref = x64.grad
+    if has_g:
+        ref = ref + gextra.double()
+    if has_x:
+        ref = ref * torch.where(xact > 0, 1.0, 0.2).double()
+    dx = ops.conv1d_dgrad(dy.to(dev), w.to(dev), (B, Cin, L, P), G, S, pad, gextra=gextra.to(dev) if has_g else None,
+                          xact=xact.to(dev) if has_x else None, act=ops.ACT_LRELU, slope=0.2)
+    assert dx.shape == ref.shape
+    assert rel_err(dx.double(), ref) < 2e-4
