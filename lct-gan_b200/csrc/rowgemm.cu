@@ -51,10 +51,13 @@ __device__ __forceinline__ void cp16(float* dst, const float* src, bool valid) {
 __device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// v = hi + lo with hi = v truncated to tf32 and lo = the exact remainder (< 2^-10 |v|) rounded to tf32 (add half an ulp;
+// the tensor core ignores the 13 low mantissa bits).  3 instructions; the cvt.rna.tf32.f32 pair this replaces is emulated
+// on sm_100a as FSETP + predicated IADD + LOP3 each (7 with the subtraction) and was ~70 % of the main loop's issue slots.
+// Error per product: the dropped lo*lo term and lo's rounding, ~2^-21 relative - unchanged in order of magnitude.
 __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(v));
-    const float r = v - __uint_as_float(hi);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+    hi = __float_as_uint(v) & 0xffffe000u;
+    lo = __float_as_uint(v - __uint_as_float(hi)) + 0x1000u;
 }
 __device__ __forceinline__ void mma8(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm(
