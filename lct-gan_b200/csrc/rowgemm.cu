@@ -16,6 +16,7 @@
 // 32), fragments read conflict free, and every product computed as a_hi b_hi + a_hi b_lo + a_lo b_hi in TF32 with fp32
 // accumulation, which keeps the fp32 parity tolerances (error ~2^-21 per product) at a third of the tensor rate -
 // still far below the memory time.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace {
@@ -306,6 +307,161 @@ int launch(const RowGemmParams& p, int64_t m_max, int gz, cudaStream_t st) {
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Weight gradients of the row operators:  C[m, n] += sum_r A[r, m] * B[r, n]   (both operands row-major over the
+// r = 34 056 positions, C is 48..192 x 16..128 and zero-filled by the caller).  The SIMT split-K kernel these calls used
+// took 30-96 us each (12 per backward, ~0.6 ms on the parameter-gradient stream).  Here every CTA walks 32-row chunks
+// (16-byte cp.async, double buffered) of a slab of rows, multiplies them on the tensor cores (3xTF32, as above) with the
+// output tile held in registers across its 4 warps - WM x WN warps side by side over the output, WK warps interleaved
+// over the rows for the tiny 48 x 16 GRU blocks - and finishes with one atomic per (element, warp).
+// ---------------------------------------------------------------------------------------------------------------
+struct TnParams {
+    const float* A; const float* B; float* C;
+    int M, N, R;                    // output rows / columns, contraction length (positions)
+    int lda, ldb, ldc;
+    int a_div, b_div;
+    int64_t sA, sB, sC;
+};
+
+template <int WM, int WN, int WK, int MT, int NT>
+__global__ void __launch_bounds__(kThreads) rowgemm_tn_kernel(const TnParams p) {
+    static_assert(WM * WN * WK == kThreads / 32, "4 warps");
+    extern __shared__ __align__(16) float sm[];
+    constexpr int RK = 32;                               // rows per chunk
+    constexpr int Mc = WM * MT * 16, Nc = WN * NT * 8;
+    constexpr int SA = Mc + 8, SB = Nc + 8;              // (8 t + g) mod 32 or (24 t + g) mod 32: conflict-free fragments
+    constexpr int STAGE = RK * (SA + SB);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int gq = lane >> 2, tq = lane & 3;
+    const int wk = warp % WK, wn = (warp / WK) % WN, wm = warp / (WK * WN);
+    const int z = blockIdx.y;
+    const float* A = p.A + (int64_t)(z / p.a_div) * p.sA;
+    const float* B = p.B + (int64_t)(z / p.b_div) * p.sB;
+    float* C = p.C + (int64_t)z * p.sC;
+    const int nchunks = (p.R + RK - 1) / RK;
+
+    auto stage = [&](int chunk, float* buf) {
+        const int r0 = chunk * RK;
+        float* as = buf;
+        float* bs = buf + RK * SA;
+        for (int idx = tid; idx < RK * (Mc / 4); idx += kThreads) {
+            const int r = idx / (Mc / 4), c4 = idx - r * (Mc / 4);
+            const bool ok = (r0 + r) < p.R;
+            cp16(as + r * SA + 4 * c4, ok ? A + (int64_t)(r0 + r) * p.lda + 4 * c4 : A, ok);
+        }
+        for (int idx = tid; idx < RK * (Nc / 4); idx += kThreads) {
+            const int r = idx / (Nc / 4), c4 = idx - r * (Nc / 4);
+            const bool ok = (r0 + r) < p.R;
+            cp16(bs + r * SB + 4 * c4, ok ? B + (int64_t)(r0 + r) * p.ldb + 4 * c4 : B, ok);
+        }
+    };
+
+    float acc[MT][NT][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
+
+    int chunk = blockIdx.x;
+    if (chunk < nchunks) stage(chunk, sm);
+    cp_commit();
+    int cur = 0;
+    for (; chunk < nchunks; chunk += gridDim.x, cur ^= 1) {
+        const float* as = sm + cur * STAGE;
+        const float* bs = as + RK * SA;
+        cp_wait<0>();
+        __syncthreads();
+        if (chunk + (int)gridDim.x < nchunks) stage(chunk + gridDim.x, sm + (cur ^ 1) * STAGE);
+        cp_commit();
+#pragma unroll
+        for (int ks = wk; ks < RK / 8; ks += WK) {
+            const float* a0 = as + (ks * 8 + tq) * SA + wm * MT * 16 + gq;
+            const float* b0 = bs + (ks * 8 + tq) * SB + wn * NT * 8 + gq;
+            uint32_t bh[NT][2], bl[NT][2];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                split_tf32(b0[nt * 8], bh[nt][0], bl[nt][0]);
+                split_tf32(b0[4 * SB + nt * 8], bh[nt][1], bl[nt][1]);
+            }
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+                uint32_t ah[4], al[4];
+                split_tf32(a0[mt * 16], ah[0], al[0]);
+                split_tf32(a0[mt * 16 + 8], ah[1], al[1]);
+                split_tf32(a0[4 * SA + mt * 16], ah[2], al[2]);
+                split_tf32(a0[4 * SA + mt * 16 + 8], ah[3], al[3]);
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    mma8(acc[mt][nt], al, bh[nt][0], bh[nt][1]);
+                    mma8(acc[mt][nt], ah, bl[nt][0], bl[nt][1]);
+                    mma8(acc[mt][nt], ah, bh[nt][0], bh[nt][1]);
+                }
+            }
+        }
+    }
+    cp_wait<0>();
+    if (WK > 1) {
+        // the WK row-interleaved warps hold partial sums of the same tile: add them in shared memory first
+        __syncthreads();
+        float* red = sm;                                 // [WK][Mc * Nc]  (<= the stage buffers)
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int m = (wm * MT + mt) * 16 + gq + 8 * (i >> 1);
+                    const int n = (wn * NT + nt) * 8 + 2 * tq + (i & 1);
+                    red[wk * Mc * Nc + m * Nc + n] = acc[mt][nt][i];
+                }
+        __syncthreads();
+        for (int idx = tid; idx < Mc * Nc; idx += kThreads) {
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < WK; ++w) v += red[w * Mc * Nc + idx];
+            const int m = idx / Nc, n = idx - m * Nc;
+            if (m < p.M && n < p.N) atomicAdd(&C[(int64_t)m * p.ldc + n], v);
+        }
+        return;
+    }
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int m = (wm * MT + mt) * 16 + gq + 8 * (i >> 1);
+                const int n = (wn * NT + nt) * 8 + 2 * tq + (i & 1);
+                if (m < p.M && n < p.N) atomicAdd(&C[(int64_t)m * p.ldc + n], acc[mt][nt][i]);
+            }
+}
+
+template <int WM, int WN, int WK, int MT, int NT>
+int launch_tn(const TnParams& p, int nbatch, cudaStream_t st) {
+    constexpr int Mc = WM * MT * 16, Nc = WN * NT * 8;
+    constexpr size_t smem = (size_t)2 * 32 * (Mc + 8 + Nc + 8) * sizeof(float);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(rowgemm_tn_kernel<WM, WN, WK, MT, NT>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    const int nchunks = (p.R + 31) / 32;
+    static_assert(WK == 1 || (size_t)WK * Mc * Nc <= (size_t)2 * 32 * (Mc + 8 + Nc + 8), "reduction fits the stages");
+    // every CTA ends with M x N atomics: one CTA per SM for the large tiles; the 48 x 16 GRU blocks are latency bound
+    // (one k-step per warp and chunk) and want many resident CTAs instead.  LCT_TN_CTAS scales the target (tuning).
+    static const int scale_pct = [] { const char* e = getenv("LCT_TN_CTAS"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 100; }();
+    const int target = (Mc * Nc >= 4096 ? 148 : 148 * 8) * scale_pct / 100;
+    int gx = target / nbatch;
+    if (gx > nchunks) gx = nchunks;
+    if (gx < 1) gx = 1;
+    dim3 grid((unsigned)gx, (unsigned)nbatch);
+    rowgemm_tn_kernel<WM, WN, WK, MT, NT><<<grid, kThreads, smem, st>>>(p);
+    LCT_RETURN_IF_LAUNCH_FAILED();
+    return 0;
+}
+
 bool al16(const void* q) { return ((uintptr_t)q & 15) == 0; }
 bool al8(const void* q) { return ((uintptr_t)q & 7) == 0; }
 
@@ -339,7 +495,24 @@ int lct_rowgemm_try(const float* A, const float* B, float* C, const float* bias,
                     int act, float slope, float alpha, int accumulate, int64_t ksplit, int64_t nbatch, int64_t a_div,
                     int64_t b_div, int64_t sA, int64_t sB, int64_t sC, int64_t sBias, int64_t sRes, int64_t sOut2,
                     cudaStream_t st, int* rc) {
-    if (ta || accumulate || ksplit != 1) return 0;
+    if (ta) {
+        // weight-gradient form C[M x N] += A^T B over K positions (caller zero-fills C: that is the ksplit > 1 contract)
+        if (!tb || ksplit <= 1 || accumulate || bias || res || out2 || act != LCT_ACT_NONE || alpha != 1.f) return 0;
+        if ((lda & 3) || (ldb & 3) || (sA & 3) || (sB & 3) || !al16(A) || !al16(B) || nbatch >= 65536 || K >= (1LL << 30))
+            return 0;
+        TnParams t = {};
+        t.A = A; t.B = B; t.C = C; t.M = (int)M; t.N = (int)N; t.R = (int)K;
+        t.lda = (int)lda; t.ldb = (int)ldb; t.ldc = (int)ldc; t.a_div = (int)a_div; t.b_div = (int)b_div;
+        t.sA = sA; t.sB = sB; t.sC = sC;
+        if (lda < M || ldb < N) return 0;
+        if (M == 64 && N == 128) *rc = launch_tn<1, 4, 1, 4, 4>(t, (int)nbatch, st);
+        else if (M == 64 && N == 64) *rc = launch_tn<2, 2, 1, 2, 4>(t, (int)nbatch, st);
+        else if (M == 192 && N == 64) *rc = launch_tn<4, 1, 1, 3, 8>(t, (int)nbatch, st);
+        else if (M == 48 && N == 16) *rc = launch_tn<1, 1, 4, 3, 2>(t, (int)nbatch, st);
+        else return 0;
+        return 1;
+    }
+    if (accumulate || ksplit != 1) return 0;
     if ((K & 7) || (N & 3) || (lda & 3) || (ldb & 3) || (ldc & 1) || (sA & 3) || (sB & 3) || (sC & 1)) return 0;
     if (!al16(A) || !al16(B) || !al8(C) || M * lda >= (1LL << 31) || nbatch >= 65536) return 0;
     if (out2 && (!al8(out2) || (ldo & 1) || (sOut2 & 1))) return 0;
