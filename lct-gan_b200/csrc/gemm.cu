@@ -267,6 +267,9 @@ int lct_rowgemm_try(const float* A, const float* B, float* C, const float* bias,
                     int64_t b_div, int64_t sA, int64_t sB, int64_t sC, int64_t sBias, int64_t sRes, int64_t sOut2,
                     cudaStream_t st, int* rc);
 
+// (other translation units: is the 3xTF32 tensor-core path selected?)
+int lct_rowgemm_enabled() { return g_rowgemm && !g_gemm_tensor_cores; }
+
 // 1 (default): NT / NN GEMMs run on the fp32-accurate 3xTF32 row GEMM; 0: fp32 SIMT kernel for everything
 LCT_API int lct_set_rowgemm(int on) {
     g_rowgemm = on ? 1 : 0;

@@ -410,12 +410,21 @@ LCT_API int lct_gconv(const float* in, const float* w, const float* bias, float*
     return transposed ? launch_gconv<true>(p, st) : launch_gconv<false>(p, st);
 }
 
+// rowgemm.cu: the same reduction as a 3xTF32 tensor-core TN GEMM with a gathered operand (tensor-core mode)
+int lct_gconv_wgrad_try(const float* S, const float* Lg, float* dW, int64_t B, int64_t Ts, int64_t Fs, int64_t Ca,
+                        int64_t Tl, int64_t Fl, int64_t Cc, cudaStream_t st, int* rc);
+int lct_rowgemm_enabled();      // gemm.cu: lct_set_rowgemm switch (tensor-core mode)
+
 // dW[Ca][Cc][2][3] += sum S[b,t,f,a] * Lg[b,t+kt-1,2f+kf-1,c]   (caller zeroes dW)
 LCT_API int lct_gconv_wgrad(const float* S, const float* Lg, float* dW, int64_t B, int64_t Ts, int64_t Fs, int64_t Ca,
                             int64_t Tl, int64_t Fl, int64_t Cc, cudaStream_t st) {
     if (!S || !Lg || !dW || B <= 0 || B >= 65536 || Ts <= 0 || Fs <= 0 || Ca <= 0 || Tl <= 0 || Fl <= 0 || Cc <= 0)
         return LCT_EINVAL;
     if (Ca * Cc > (int64_t)kWgMaxPairs * kThreads) return LCT_EUNSUPPORTED;
+    if (lct_rowgemm_enabled()) {
+        int rc = 0;
+        if (lct_gconv_wgrad_try(S, Lg, dW, B, Ts, Fs, Ca, Tl, Fl, Cc, st, &rc)) return rc;
+    }
     GWgradParams p;
     p.S = S; p.Lg = Lg; p.dW = dW;
     p.B = (int)B; p.Ts = (int)Ts; p.Fs = (int)Fs; p.Ca = (int)Ca; p.Tl = (int)Tl; p.Fl = (int)Fl; p.Cc = (int)Cc;

@@ -321,9 +321,14 @@ struct TnParams {
     int lda, ldb, ldc;
     int a_div, b_div;
     int64_t sA, sB, sC;
+    // GATHER (weight gradient of the encoder / decoder convolutions, gen_conv.cu lct_gconv_wgrad): row r = (b, t, f) of
+    // the small grid [B, Ts, Fs]; B(r, (kt, kf, c)) = Lg[b, t + kt - 1, 2 f + kf - 1, c] - two contiguous runs of
+    // 3 Cc floats, zero outside the large grid [B, Tl, Fl, Cc]; C[m][(kt*3 + kf) * Cc + c] lands in dW[m][c][kt][kf]
+    int Ts, Fs, Tl, Fl, Cc;
+    uint32_t mulFs, mulTs;          // floor(2^32 / d) + 1: r / Fs and (r / Fs) / Ts by multiply-high (r < 2^22)
 };
 
-template <int WM, int WN, int WK, int MT, int NT>
+template <int WM, int WN, int WK, int MT, int NT, bool GATHER>
 __global__ void __launch_bounds__(kThreads) rowgemm_tn_kernel(const TnParams p) {
     static_assert(WM * WN * WK == kThreads / 32, "4 warps");
     extern __shared__ __align__(16) float sm[];
@@ -351,8 +356,25 @@ __global__ void __launch_bounds__(kThreads) rowgemm_tn_kernel(const TnParams p) 
         }
         for (int idx = tid; idx < RK * (Nc / 4); idx += kThreads) {
             const int r = idx / (Nc / 4), c4 = idx - r * (Nc / 4);
-            const bool ok = (r0 + r) < p.R;
-            cp16(bs + r * SB + 4 * c4, ok ? B + (int64_t)(r0 + r) * p.ldb + 4 * c4 : B, ok);
+            bool ok = (r0 + r) < p.R;
+            const float* src = B;
+            if (GATHER) {
+                const int rg = r0 + r;
+                const int bt = p.Fs == 1 ? rg : (int)__umulhi((uint32_t)rg, p.mulFs);      // b * Ts + t
+                const int f = rg - bt * p.Fs;
+                const int b = p.Ts == 1 ? bt : (int)__umulhi((uint32_t)bt, p.mulTs);
+                const int t = bt - b * p.Ts;
+                const int run = 3 * p.Cc / 4;                  // 16-byte pieces per time tap
+                const int kt = c4 >= run ? 1 : 0;
+                const int o = (c4 - kt * run) * 4;             // float offset inside the run (kf * Cc + c)
+                const int tl = t + kt - 1;
+                const int fl = 2 * f - 1 + o / p.Cc;
+                ok = ok && tl >= 0 && tl < p.Tl && fl >= 0 && fl < p.Fl;
+                if (ok) src = B + (((int64_t)b * p.Tl + tl) * p.Fl + (2 * f - 1)) * p.Cc + o;
+            } else if (ok) {
+                src = B + (int64_t)(r0 + r) * p.ldb + 4 * c4;
+            }
+            cp16(bs + r * SB + 4 * c4, src, ok);
         }
     };
 
@@ -422,7 +444,7 @@ __global__ void __launch_bounds__(kThreads) rowgemm_tn_kernel(const TnParams p) 
 #pragma unroll
             for (int w = 0; w < WK; ++w) v += red[w * Mc * Nc + idx];
             const int m = idx / Nc, n = idx - m * Nc;
-            if (m < p.M && n < p.N) atomicAdd(&C[(int64_t)m * p.ldc + n], v);
+            if (m < p.M && n < p.N) atomicAdd(&C[(int64_t)m * p.ldc + n], v);      // (WK > 1 is never GATHER)
         }
         return;
     }
@@ -434,16 +456,24 @@ __global__ void __launch_bounds__(kThreads) rowgemm_tn_kernel(const TnParams p) 
             for (int i = 0; i < 4; ++i) {
                 const int m = (wm * MT + mt) * 16 + gq + 8 * (i >> 1);
                 const int n = (wn * NT + nt) * 8 + 2 * tq + (i & 1);
-                if (m < p.M && n < p.N) atomicAdd(&C[(int64_t)m * p.ldc + n], acc[mt][nt][i]);
+                if (m < p.M && n < p.N) {
+                    if (GATHER) {
+                        const int k = n / p.Cc, c = n - k * p.Cc;
+                        atomicAdd(&C[((int64_t)m * p.Cc + c) * 6 + k], acc[mt][nt][i]);
+                    } else {
+                        atomicAdd(&C[(int64_t)m * p.ldc + n], acc[mt][nt][i]);
+                    }
+                }
             }
 }
 
-template <int WM, int WN, int WK, int MT, int NT>
+template <int WM, int WN, int WK, int MT, int NT, bool GATHER = false>
 int launch_tn(const TnParams& p, int nbatch, cudaStream_t st) {
+    static_assert(!GATHER || WK == 1, "the gather epilogue is the direct one");
     constexpr int Mc = WM * MT * 16, Nc = WN * NT * 8;
     constexpr size_t smem = (size_t)2 * 32 * (Mc + 8 + Nc + 8) * sizeof(float);
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(rowgemm_tn_kernel<WM, WN, WK, MT, NT>,
+        cudaError_t e = cudaFuncSetAttribute(rowgemm_tn_kernel<WM, WN, WK, MT, NT, GATHER>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
@@ -452,12 +482,12 @@ int launch_tn(const TnParams& p, int nbatch, cudaStream_t st) {
     // every CTA ends with M x N atomics: one CTA per SM for the large tiles; the 48 x 16 GRU blocks are latency bound
     // (one k-step per warp and chunk) and want many resident CTAs instead.  LCT_TN_CTAS scales the target (tuning).
     static const int scale_pct = [] { const char* e = getenv("LCT_TN_CTAS"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 100; }();
-    const int target = (Mc * Nc >= 4096 ? 148 : 148 * 8) * scale_pct / 100;
+    const int target = (Mc * Nc >= 2048 ? 148 : 148 * 8) * scale_pct / 100;
     int gx = target / nbatch;
     if (gx > nchunks) gx = nchunks;
     if (gx < 1) gx = 1;
     dim3 grid((unsigned)gx, (unsigned)nbatch);
-    rowgemm_tn_kernel<WM, WN, WK, MT, NT><<<grid, kThreads, smem, st>>>(p);
+    rowgemm_tn_kernel<WM, WN, WK, MT, NT, GATHER><<<grid, kThreads, smem, st>>>(p);
     LCT_RETURN_IF_LAUNCH_FAILED();
     return 0;
 }
@@ -490,6 +520,24 @@ __global__ void gconv_image_kernel(const float* __restrict__ w, float* __restric
 }  // namespace
 
 // 1 if lct_rowgemm covers this GEMM (otherwise use lct_gemm's SIMT kernel).  Called by lct_gemm itself.
+// Tensor-core form of lct_gconv_wgrad (gen_conv.cu) for the shapes the generator has: (Ca, Cc) = (64, 32), (32, 16).
+// Returns 1 if it handled the call (result code in *rc), 0 if the caller should use its SIMT kernels.
+int lct_gconv_wgrad_try(const float* S, const float* Lg, float* dW, int64_t B, int64_t Ts, int64_t Fs, int64_t Ca,
+                        int64_t Tl, int64_t Fl, int64_t Cc, cudaStream_t st, int* rc) {
+    const int64_t R = B * Ts * Fs;
+    if (!al16(S) || !al16(Lg) || R >= (1LL << 22) || B * Tl * Fl * Cc >= (1LL << 31)) return 0;
+    TnParams t = {};
+    t.A = S; t.B = Lg; t.C = dW; t.M = (int)Ca; t.N = (int)(6 * Cc); t.R = (int)R;
+    t.lda = (int)Ca; t.ldb = 0; t.ldc = 0; t.a_div = 1; t.b_div = 1;
+    t.Ts = (int)Ts; t.Fs = (int)Fs; t.Tl = (int)Tl; t.Fl = (int)Fl; t.Cc = (int)Cc;
+    t.mulFs = (uint32_t)((1ULL << 32) / (uint64_t)Fs) + 1u;
+    t.mulTs = (uint32_t)((1ULL << 32) / (uint64_t)Ts) + 1u;
+    if (Ca == 64 && Cc == 32) *rc = launch_tn<1, 4, 1, 4, 6, true>(t, 1, st);
+    else if (Ca == 32 && Cc == 16) *rc = launch_tn<1, 4, 1, 2, 3, true>(t, 1, st);
+    else return 0;
+    return 1;
+}
+
 int lct_rowgemm_try(const float* A, const float* B, float* C, const float* bias, const float* res, float* out2, int64_t M,
                     int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int64_t ldr, int64_t ldo, int ta, int tb,
                     int act, float slope, float alpha, int accumulate, int64_t ksplit, int64_t nbatch, int64_t a_div,
