@@ -18,6 +18,7 @@
 //   warp 1 lane 0 : MMA issuer     (tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16; tcgen05.commit frees slots)
 //   warp 2        : TMEM allocator (tcgen05.alloc / dealloc)
 //   warps 4..7    : epilogue       (tcgen05.ld 32x32b -> bias / activation / dgrad fusion -> coalesced fp32 stores)
+#include <cstdlib>
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -237,6 +238,124 @@ dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 }
 
 // ---------------------------------------------------------------------------------------------
+// Weight gradient, all K taps of a 128 x 64 (co x ci) block in ONE CTA.  The generic form above gives every tap its own
+// CTA, which then owns every K-th float of dW [Co][Ci][K]: 16 384 scattered 4-byte stores per tile - 95 % of its
+// 78 us (ncu: issue active 2.8 %, stalls barrier / lg_throttle; the 17-33 k-blocks of MMA take ~3 us).  Here the dY
+// tile is loaded once per k-block and multiplied with the K shifted X tiles into K accumulators side by side in TMEM
+// (K * 64 <= 512 columns); an epilogue thread then owns, for its co row, runs of 8 ci x K taps = 40 consecutive floats
+// of dW and writes them as 16-byte stores.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
+}
+
+template <int KT, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+dense_wgrad_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                        const DenseParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    constexpr int BN = 64;
+    constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + KT * B_BYTES;
+    constexpr int TMEM_COLS = 512;
+    static_assert(KT * BN <= TMEM_COLS, "accumulators fit TMEM");
+    uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = reinterpret_cast<uint64_t*>(tiles + (size_t)STAGES * STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    uint64_t* tmem_full = empty + STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "n"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ===== TMA producer: dY tile + the KT shifted X tiles of this k-block =====
+        for (int kb = 0; kb < p.nkb; ++kb) {
+            const int s = kb % STAGES;
+            const uint32_t ph = (kb / STAGES) & 1;
+            mbar_wait(&empty[s], ph ^ 1);
+            mbar_expect_tx(&full[s], STAGE_BYTES);
+            uint8_t* sa = tiles + (size_t)s * STAGE_BYTES;
+            tma_load_2d(sa, &tmA, &full[s], kb * BK, m0);
+#pragma unroll
+            for (int tap = 0; tap < KT; ++tap)
+                tma_load_2d(sa + A_BYTES + tap * B_BYTES, &tmB, &full[s], kb * BK, n0 + tap * p.b_tap_rows);
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===== MMA issuer =====
+        constexpr uint32_t idesc = make_idesc(BM, BN);
+        for (int kb = 0; kb < p.nkb; ++kb) {
+            const int s = kb % STAGES;
+            const uint32_t ph = (kb / STAGES) & 1;
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(tiles + (size_t)s * STAGE_BYTES);
+#pragma unroll
+            for (int tap = 0; tap < KT; ++tap) {
+                const uint32_t sb = sa + A_BYTES + tap * B_BYTES;
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k)
+                    umma(tmem_base + (uint32_t)(tap * BN), make_desc(sa + k * UMMA_K * 2), make_desc(sb + k * UMMA_K * 2),
+                         idesc, (uint32_t)((kb | k) != 0));
+            }
+            umma_commit(&empty[s]);
+        }
+        umma_commit(tmem_full);
+    } else if (warp >= 4) {
+        // ===== epilogue: TMEM lane = co row; 8 ci x KT taps = 8 KT consecutive floats of dW per step =====
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const int q = warp & 3;
+        const int row = m0 + q * 32 + lane;
+        float* orow = p.out + ((size_t)row * p.Ntot + n0) * KT;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 8) {
+            uint32_t v[KT][8];
+#pragma unroll
+            for (int tap = 0; tap < KT; ++tap)
+                tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tap * BN + c0), v[tap]);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            float w[8 * KT];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+#pragma unroll
+                for (int tap = 0; tap < KT; ++tap) w[j * KT + tap] = __uint_as_float(v[tap][j]);
+            float4* o4 = reinterpret_cast<float4*>(orow + (size_t)c0 * KT);      // 16-byte aligned: 8 KT floats per step
+#pragma unroll
+            for (int i = 0; i < 2 * KT; ++i) o4[i] = make_float4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side: tensor maps through the driver entry point (no link-time dependency on libcuda)
 // ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -273,6 +392,8 @@ int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uin
 
 int g_dense_debug = 0;
 int g_dense_bn = 0;      // output-tile width of the conv form: 0 auto, 64, 128
+// weight gradient with all taps in one CTA (default); LCT_DENSE_WGRAD_TAPS=0 selects the one-CTA-per-tap form (A/B tests)
+int g_dense_wgrad_taps = [] { const char* e = getenv("LCT_DENSE_WGRAD_TAPS"); return e ? atoi(e) : 1; }();
 
 template <int BN, int STAGES, int EPI>
 int launch_dense(const CUtensorMap& a, const CUtensorMap& b, DenseParams& p, dim3 grid, cudaStream_t st) {
@@ -437,12 +558,26 @@ LCT_API int lct_dense_wgrad(const void* dyq, const void* xq, float* dw, int64_t 
     CUtensorMap ma, mb;
     int rc = make_map(&ma, dyq, (uint64_t)Co, (uint64_t)pitch, (uint64_t)pitch, BM);
     if (rc) return rc;
-    rc = make_map(&mb, xq, (uint64_t)(K * Ci), (uint64_t)pitch, (uint64_t)pitch, 128);
-    if (rc) return rc;
     DenseParams p = {};
     p.nkb = (int)ceil_div64(pitch, BK); p.kdiv = p.nkb;
     p.a0 = 0; p.a_step1 = 0; p.b0 = 0; p.b_step1 = 0; p.b_tap_rows = (int)Ci;
     p.out = dw; p.Ntot = (int)Ci; p.Ktaps = (int)K;
+    if (K == 5 && g_dense_wgrad_taps && ((uintptr_t)dw & 15) == 0) {
+        // all 5 taps per CTA (see dense_wgrad_taps_kernel)
+        rc = make_map(&mb, xq, (uint64_t)(K * Ci), (uint64_t)pitch, (uint64_t)pitch, 64);
+        if (rc) return rc;
+        constexpr int KT = 5, ST = 3;
+        constexpr size_t smem = (size_t)ST * (BM * BK * 2 + KT * 64 * BK * 2) + 1024 + 256;
+        cudaError_t e = cudaFuncSetAttribute(dense_wgrad_taps_kernel<KT, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        dim3 grid5((unsigned)(Co / BM), (unsigned)(Ci / 64));
+        dense_wgrad_taps_kernel<KT, ST><<<grid5, kThreads, smem, st>>>(ma, mb, p);
+        LCT_RETURN_IF_LAUNCH_FAILED();
+        return 0;
+    }
+    rc = make_map(&mb, xq, (uint64_t)(K * Ci), (uint64_t)pitch, (uint64_t)pitch, 128);
+    if (rc) return rc;
     dim3 grid((unsigned)(Co / BM), (unsigned)(Ci / 128), (unsigned)K);
     return launch_dense<128, 5, EPI_WGRAD>(ma, mb, p, grid, st);
 }

@@ -33,3 +33,24 @@ for B, L in ((8, 125), (16, 125), (8, 63), (16, 32)):
         fl = 2.0 * B * L * C * C * K
         print(f"B={B:2d} L={L:3d} BN={bn:3d}: {us:7.1f} us  {fl / us / 1e6:7.1f} TFLOP/s   max diff vs BN=64 {err:.2e}", flush=True)
 _lib.call_ret("lct_dense_tile_n", 0)
+
+# weight gradient (all taps per CTA by default; LCT_DENSE_WGRAD_TAPS=0: one CTA per tap)
+for B, L in ((8, 125), (16, 125), (16, 63), (16, 32)):
+    x = torch.randn(B, C, L, 1, device=dev)
+    dy = torch.randn(B, C, L, 1, device=dev)
+    Lp = L + K - 1
+    dyq = ops.stage_ncl_bf16(dy, Lp, 0)
+    xq = ops.stage_ncl_bf16(x, Lp, K // 2, copies=K)
+    out = torch.zeros(C, C, K, device=dev)
+    run = lambda: ops.dense_wgrad(dyq, xq, C, C, K, (C, C, K), out=out)
+    for _ in range(3): run()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(20): run()
+    g.replay(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / 20 * 1e3
+    fl = 2.0 * B * L * C * C * K
+    print(f"wgrad B={B:2d} L={L:3d}: {us:6.1f} us  {fl / us / 1e6:6.1f} TFLOP/s", flush=True)
