@@ -191,8 +191,8 @@ def measure_roofline(dev, peaks):
     roof = {"kernel": "conv_mma_kernel<dgrad> (MSD convs.1 data gradient: 64->16 ch, k=41, s=4, groups=4, B=8, L=32000, "
                       "TF32 mma.sync, output tile transposed through shared memory, coalesced fused FM-gradient/LeakyReLU' pass)",
             "bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
-            "traffic": 49.7e6, "traffic_note": "dram__bytes_read+write per launch, ncu --set full "
-            "(profiles/ncu_full_r1_disc_v3_raw.csv); the 16.4 MB output is still in the 126 MB L2 when the kernel ends",
+            "traffic": 49.5e6, "traffic_note": "dram__bytes_read+write per launch, ncu --set full "
+            "(profiles/ncu_full_r1_disc_v4_raw.csv); the 16.4 MB output is still in the 126 MB L2 when the kernel ends",
             "algorithmic_bytes": nbytes, "ms_per_launch": ms, "peak_source": peaks["src"] + " (STREAM-style copy)"}
     # ---- dense conv forward on tcgen05 (MSD convs.5): the D step pushes clean + enhanced through as one batch of 2B
     C, K = 1024, 5
