@@ -76,19 +76,33 @@ __global__ void __launch_bounds__(kThreads) mt_kernel(const Segs S, float* __res
     float acc = 0.f;
     if (vec) {
         const int64_t end4 = start + ((end - start) & ~(int64_t)3);
-        for (int64_t i = start + (int64_t)threadIdx.x * 4; i < end4; i += kThreads * 4) {
-            float4 va = *reinterpret_cast<const float4*>(a + i);
-            float4 vb = has_b ? *reinterpret_cast<const float4*>(b + i) : make_float4(0, 0, 0, 0);
-            if (GRAD) {
-                float4 r;
-                r.x = gs * op_grad(S.op, va.x, vb.x, S.k0, S.k1);
-                r.y = gs * op_grad(S.op, va.y, vb.y, S.k0, S.k1);
-                r.z = gs * op_grad(S.op, va.z, vb.z, S.k0, S.k1);
-                r.w = gs * op_grad(S.op, va.w, vb.w, S.k0, S.k1);
-                *reinterpret_cast<float4*>(g + i) = r;
-            } else {
-                acc += op_val(S.op, va.x, vb.x, S.k0, S.k1) + op_val(S.op, va.y, vb.y, S.k0, S.k1) +
-                       op_val(S.op, va.z, vb.z, S.k0, S.k1) + op_val(S.op, va.w, vb.w, S.k0, S.k1);
+        // 4 float4 per operand in flight per thread (8 independent 16-byte loads before the first use); streaming loads:
+        // every element is read exactly once
+        constexpr int U = 4;
+        for (int64_t i0 = start + (int64_t)threadIdx.x * 4; i0 < end4; i0 += (int64_t)U * kThreads * 4) {
+            float4 va[U], vb[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t i = i0 + (int64_t)u * kThreads * 4;
+                const bool ok = i < end4;
+                va[u] = ok ? __ldcs(reinterpret_cast<const float4*>(a + i)) : make_float4(0, 0, 0, 0);
+                vb[u] = (ok && has_b) ? __ldcs(reinterpret_cast<const float4*>(b + i)) : make_float4(0, 0, 0, 0);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t i = i0 + (int64_t)u * kThreads * 4;
+                if (i >= end4) break;
+                if (GRAD) {
+                    float4 r;
+                    r.x = gs * op_grad(S.op, va[u].x, vb[u].x, S.k0, S.k1);
+                    r.y = gs * op_grad(S.op, va[u].y, vb[u].y, S.k0, S.k1);
+                    r.z = gs * op_grad(S.op, va[u].z, vb[u].z, S.k0, S.k1);
+                    r.w = gs * op_grad(S.op, va[u].w, vb[u].w, S.k0, S.k1);
+                    *reinterpret_cast<float4*>(g + i) = r;
+                } else {
+                    acc += op_val(S.op, va[u].x, vb[u].x, S.k0, S.k1) + op_val(S.op, va[u].y, vb[u].y, S.k0, S.k1) +
+                           op_val(S.op, va[u].z, vb[u].z, S.k0, S.k1) + op_val(S.op, va[u].w, vb[u].w, S.k0, S.k1);
+                }
             }
         }
         for (int64_t i = end4 + threadIdx.x; i < end; i += kThreads) {
