@@ -147,7 +147,7 @@ LCT_API int lct_dense_wgrad(const void* dyq, const void* xq, float* dw, int64_t 
  * C[M,N] = act(alpha * op(A) op(B) + bias) (+C); out2 = C + res.  ta: A(m,k)=A[k*lda+m]; tb: B(k,n)=B[k*ldb+n] else B[n*ldb+k].
  * Batched over z: A += (z/a_div)*sA, B += (z/b_div)*sB, C/bias/res/out2 += z*s.  ksplit>1: split-K with atomic adds. */
 LCT_API int lct_gemm(const float* A, const float* B, float* C, const float* bias, const float* res, float* out2, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc, int64_t ldr, int64_t ldo, int ta, int tb, int act, float slope, float alpha, int accumulate, int64_t ksplit, int64_t nbatch, int64_t a_div, int64_t b_div, int64_t sA, int64_t sB, int64_t sC, int64_t sBias, int64_t sRes, int64_t sOut2, cudaStream_t stream);
-LCT_API int lct_set_rowgemm(int on);            /* 1 (default): NT/NN GEMMs with aligned operands run on the fp32-accurate 3xTF32 tensor-core row GEMM (rowgemm.cu); 0: fp32 SIMT */
+LCT_API int lct_set_rowgemm(int on);            /* 1 (default): NT/NN GEMMs with aligned operands, the TN weight-gradient GEMMs (split-K form) and lct_gconv_wgrad run on the fp32-accurate 3xTF32 tensor-core row GEMMs (rowgemm.cu); 0: fp32 SIMT */
 LCT_API int lct_set_tensor_core_gemm(int on);   /* 1: lct_gemm runs on TF32 mma.sync (experimental, slower on the skinny generator shapes); 0 (default): fp32 SIMT */
 LCT_API int lct_colsum(const float* X, float* out, int64_t M, int64_t N, int64_t ld, cudaStream_t stream);   /* out[N] += column sums (bias gradients) */
 /* nn.LayerNorm(C) over rows [M,C] (generator.py:126, :132, :238, :244, :577). */
