@@ -9,16 +9,21 @@
 //   * per group:  D[position, n] = sum_kk A[position, kk] * W[kk, n]   with A gathered on the fly from a
 //     shared-memory window of the input (no im2col buffer).  Forward: kk = (ci, tap), n = out channel.
 //     Data gradient in polyphase form: kk = (co, t), n = (in channel, stride phase r) with r fastest
-//     (weight tap k = r + S t), so one GEMM produces all S phases and a thread's two accumulator columns are
-//     two consecutive output rows: stores stay coalesced.
-//   * persistent CTAs (one group each, looping over (batch, position tile)) with the next tile's window
-//     prefetched by cp.async (4-byte copies, zero-fill for the padding) while the current one is multiplied:
-//     the staging latency that dominated the SIMT kernels is overlapped.
-//   * m16n8k8 TF32 fragments are read straight from the window (rows = 8 consecutive positions, columns =
-//     4 consecutive taps -> 32 consecutive words for S <= 4: conflict free) and rounded with cvt.rna; weights
-//     are rounded once when the CTA stages them.
-//   * weight gradient: M = out channels, N = (ci, tap), K = positions; each warp keeps the whole dW tile of
-//     its group in registers over its share of the positions and finishes with atomics.
+//     (weight tap k = r + S t), so one GEMM produces all S phases.
+//   * persistent CTAs (one group each, looping over (batch, position tile); grid = the CTAs that are really resident,
+//     rounded down to one wave) with the next tile's window prefetched by 16-byte cp.async (per-channel alignment
+//     shift, zero-fill for the padding) while the current one is multiplied.
+//   * m16n8k8 TF32 fragments are read straight from the window through a LUT of byte offsets (rows = 8 consecutive
+//     positions, columns = 4 consecutive taps -> 32 consecutive words for S <= 4: conflict free; the data gradient's
+//     rows sit at immediate offsets) and rounded to tf32 by one integer add; weights come pre-arranged and pre-rounded
+//     from the weight-norm launch.
+//   * data-gradient epilogue: the accumulator tile is transposed through shared memory so that every in-channel owns
+//     one contiguous run of outputs, then a coalesced pass applies (+ FM gradient) x LeakyReLU'(saved activation)
+//     with 16 unconditional loads in flight per thread.
+//   * weight gradient: M = out channels, N = (ci, tap), K = positions; the dW tile of a group lives in registers,
+//     split by columns over two warp groups when it is wide (8 warps per CTA), and is flushed with one atomic per
+//     (weight, CTA).
+//   (round-1 ncu source pages behind these choices: profiles/README.md)
 //
 // Precision: TF32 operands (10-bit mantissa), fp32 accumulation - the "bf16 training" configuration of
 // BASELINE.json (configs[2]) at higher operand precision than bf16.
@@ -147,7 +152,7 @@ __device__ __forceinline__ void stage_window(const MmaParams& p, int g, int tile
 template <int MODE, int NT, int MTW>
 __global__ void __launch_bounds__(kThreads) conv_mma_kernel(const MmaParams p) {
     extern __shared__ __align__(16) float sm[];
-    constexpr int TP = 32 * MTW * (kThreads / 32) / 2;   // MTW m-tiles of 16 positions per warp
+    // MTW m-tiles of 16 positions per warp: 64 * MTW positions per tile (p.TPe of them used)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int gq = lane >> 2, tq = lane & 3;
     const int g = blockIdx.x;
