@@ -518,6 +518,7 @@ struct WnSegs {
     float* w[kMaxWn];      // fwd: w;  bwd: dv
     float* dg[kMaxWn];
     int row0[kMaxWn + 1];  // prefix sum of rows (out channels)
+    int cta0[kMaxWn + 1];  // prefix sum of CTAs: short rows (<= 128 elements) go four to a CTA, one per warp
     int rowlen[kMaxWn];
     // optional staged weight images for the tensor-core conv kernels (conv_mma.cu); geo = {Cog, K, S, Tmax,
     // KKpad_f, NS_f, KKpad_d, NS_d}
@@ -533,40 +534,59 @@ __device__ __forceinline__ float round_tf32(float v) {
     return __uint_as_float(u);
 }
 
+// One CTA (4 warps) per output channel, or - rows of <= 128 elements: all MPD layers, 5..80 elements - one WARP per
+// output channel, four to a CTA, reduced by shuffles without a barrier (the one-CTA-per-5-element-row form took 17 us
+// for 0.6 MB at the head of every period-discriminator chain).
 template <bool BWD>
 __global__ void __launch_bounds__(128) mt_wnorm_kernel(const WnSegs S) {
     __shared__ float red[32];
     int seg = 0;
-    while (seg + 1 < S.nseg && (int)blockIdx.x >= S.row0[seg + 1]) ++seg;
-    const int co = blockIdx.x - S.row0[seg];
+    while (seg + 1 < S.nseg && (int)blockIdx.x >= S.cta0[seg + 1]) ++seg;
     const int row = S.rowlen[seg];
+    const bool per_warp = row <= 128;
+    const int nrows = S.row0[seg + 1] - S.row0[seg];
+    const int co = per_warp ? ((int)blockIdx.x - S.cta0[seg]) * 4 + ((int)threadIdx.x >> 5) : (int)blockIdx.x - S.cta0[seg];
+    if (co >= nrows) return;                       // (per-warp form only: whole warps leave, nobody waits at a barrier)
+    const int t0 = per_warp ? ((int)threadIdx.x & 31) : (int)threadIdx.x;
+    const int tstep = per_warp ? 32 : (int)blockDim.x;
     const float* vr = S.v[seg] + (size_t)co * row;
+    const float gg = S.g[seg][co];
     float a = 0.f, d = 0.f;
     if (BWD) {
         const float* dr = S.dw[seg] + (size_t)co * row;
-        for (int i = threadIdx.x; i < row; i += blockDim.x) {
+        for (int i = t0; i < row; i += tstep) {
             float vv = vr[i];
             a += vv * vv;
             d += vv * dr[i];
         }
-        const float n2 = block_sum(a, red);
-        const float dot = block_sum(d, red);
+        float n2, dot;
+        if (per_warp) {
+            n2 = warp_sum(a);
+            dot = warp_sum(d);
+            n2 = __shfl_sync(0xffffffffu, n2, 0);
+            dot = __shfl_sync(0xffffffffu, dot, 0);
+        } else {
+            n2 = block_sum(a, red);
+            dot = block_sum(d, red);
+        }
         const float nrm = sqrtf(n2);
-        const float gg = S.g[seg][co];
-        if (threadIdx.x == 0) S.dg[seg][co] = dot / nrm;
+        if (t0 == 0) S.dg[seg][co] = dot / nrm;
         const float k1 = gg / nrm, k2 = dot / n2;
         float* dv = S.w[seg] + (size_t)co * row;
-        for (int i = threadIdx.x; i < row; i += blockDim.x) dv[i] = k1 * (dr[i] - k2 * vr[i]);
+        for (int i = t0; i < row; i += tstep) dv[i] = k1 * (dr[i] - k2 * vr[i]);
     } else {
-        for (int i = threadIdx.x; i < row; i += blockDim.x) a += vr[i] * vr[i];
-        const float sc = S.g[seg][co] / sqrtf(block_sum(a, red));
+        for (int i = t0; i < row; i += tstep) a += vr[i] * vr[i];
+        float n2;
+        if (per_warp) n2 = __shfl_sync(0xffffffffu, warp_sum(a), 0);
+        else n2 = block_sum(a, red);
+        const float sc = gg / sqrtf(n2);
         float* w = S.w[seg] + (size_t)co * row;
         float* imf = S.img_f[seg];
         float* imd = S.img_d[seg];
         const int Cog = S.geo[seg][0], K = S.geo[seg][1], St = S.geo[seg][2], Tmax = S.geo[seg][3];
         const int KKf = S.geo[seg][4], NSf = S.geo[seg][5], KKd = S.geo[seg][6], NSd = S.geo[seg][7];
         const int g = imf ? co / Cog : 0, col = imf ? co - g * Cog : 0;
-        for (int i = threadIdx.x; i < row; i += blockDim.x) {
+        for (int i = t0; i < row; i += tstep) {
             const float v = vr[i] * sc;
             w[i] = v;
             if (imf) {
@@ -586,17 +606,20 @@ int fill_wn(WnSegs& S, const void* const* g, const void* const* v, const void* c
             void* const* dg, const int64_t* rows, const int64_t* rowlen, int64_t nseg, bool bwd) {
     for (int i = 0; i < kMaxWn; ++i) S.img_f[i] = S.img_d[i] = nullptr;
     if (!g || !v || !w || !rows || !rowlen || nseg <= 0 || nseg > kMaxWn || (bwd && (!dw || !dg))) return LCT_EINVAL;
-    int tot = 0;
+    int tot = 0, ctas = 0;
     for (int i = 0; i < nseg; ++i) {
         if (!g[i] || !v[i] || !w[i] || rows[i] <= 0 || rowlen[i] <= 0 || (bwd && (!dw[i] || !dg[i]))) return LCT_EINVAL;
         S.g[i] = (const float*)g[i]; S.v[i] = (const float*)v[i]; S.w[i] = (float*)w[i];
         S.dw[i] = bwd ? (const float*)dw[i] : nullptr; S.dg[i] = bwd ? (float*)dg[i] : nullptr;
         S.row0[i] = tot; S.rowlen[i] = (int)rowlen[i];
+        S.cta0[i] = ctas;
         tot += (int)rows[i];
+        ctas += rowlen[i] <= 128 ? (int)((rows[i] + 3) / 4) : (int)rows[i];
     }
     S.row0[nseg] = tot;
+    S.cta0[nseg] = ctas;
     S.nseg = (int)nseg;
-    return tot;
+    return ctas;
 }
 
 }  // namespace
