@@ -28,6 +28,9 @@ def gtime(run, n=20):
 
 # (name, Cin, Cout, K, S, groups, Lin, P)
 LAYERS = [
+    ("MSD0.convs0", 1, 16, 15, 1, 1, 32000, 1),
+    ("MPD2.convs0", 1, 32, 5, 3, 1, 16000, 2),
+    ("MPD11.convs0", 1, 32, 5, 3, 1, 2910, 11),
     ("MSD0.convs1", 16, 64, 41, 4, 4, 32000, 1),
     ("MSD0.convs2", 64, 256, 41, 4, 16, 8000, 1),
     ("MSD0.convs3", 256, 1024, 41, 4, 64, 2000, 1),
