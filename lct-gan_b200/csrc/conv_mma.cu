@@ -605,7 +605,10 @@ int pick_ns(int npad) {
     return ns;
 }
 
-int g_ctas_per_sm = 6;
+// resident CTAs per SM targeted by the forward / data-gradient grids.  Whole-step A/B on one box (with the wgrad target
+// below at 2): 4 -> 9.975 ms, 5 -> 9.99 ms, 6 (the old default, wgrad 3) -> 10.15 ms; 5 also keeps the standalone
+// kernels at their occupancy limit.
+int g_ctas_per_sm = 5;
 int g_force_mtw = 2;
 
 int grid_y(int G, int ntiles, int ctas_per_sm) {
@@ -750,7 +753,7 @@ LCT_API int lct_conv_mma_dgrad(const float* dy, const float* w, const float* wim
 int g_wgrad_ctas_per_sm = [] {
     const char* e = getenv("LCT_WGRAD_CTAS");
     const int v = e ? atoi(e) : 0;
-    return v > 0 ? v : 3;
+    return v > 0 ? v : 2;      // 2 measured best in the whole step (3: +0.4 .. 1 %)
 }();
 
 template <int MT, int NT, int NSPLIT>
