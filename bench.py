@@ -144,7 +144,11 @@ def run_reference(args):
 # roofline of the dominant kernel, timed live
 # --------------------------------------------------------------------------------------------------
 def _time_kernel(run, flush, iters=10):
-    """Average CUDA-event duration (ms) of one launch, L2 flushed (256 MB write) before every timed launch."""
+    """Average CUDA-event duration (ms) of one launch, L2 flushed (256 MB write) before every timed launch.
+
+    The GPU is parked on a ~200 us spin kernel while the host enqueues [event, launch, event]: without it the event pair
+    also spans the host-side cost of the launch (torch.empty + ctypes, 30-60 us - as long as the kernels themselves) on
+    a box whose CPU is slower than the 256 MB flush, which made the reported fractions jump between runs."""
     import torch
     for _ in range(3):
         run()
@@ -152,6 +156,7 @@ def _time_kernel(run, flush, iters=10):
     times = []
     for _ in range(iters):
         flush.zero_()
+        torch.cuda._sleep(400_000)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         run()
