@@ -457,7 +457,35 @@ __global__ void gru_combine_kernel(const float* __restrict__ x, const float* __r
 // (exponentials are __expf = MUFU.EX2: two instructions instead of ~10 in loops that run L^2 times per head; relative
 // error 2^-21, far inside the 2e-5 parity bar)
 constexpr int kHd = 16;
-constexpr int kAttnMaxThreads = 256;   // block = sequence length rounded up to a warp (one query/key per thread)
+constexpr int kAttnMaxThreads = 256;
+
+// 16-wide head rows as 8 float2 and packed fp32x2 arithmetic (FFMA2, sm_100): the attention loops are issue bound (ncu:
+// 43-57 % issue active at ~ 26 % of the FMA rate), and every multiply-add here comes in pairs over the head dimension,
+// so the packed form halves the FMA instruction count without changing any product or any addition's operands' values
+// (only the order of the 16-term dot-product sums: even / odd lanes first).
+__device__ __forceinline__ void load_row2(const float* p, float2 (&r)[kHd / 2]) {      // p: 16-byte aligned
+    const float4* p4 = reinterpret_cast<const float4*>(p);
+#pragma unroll
+    for (int d4 = 0; d4 < kHd / 4; ++d4) {
+        const float4 v = p4[d4];
+        r[2 * d4] = make_float2(v.x, v.y);
+        r[2 * d4 + 1] = make_float2(v.z, v.w);
+    }
+}
+__device__ __forceinline__ float dot16(const float2 (&a)[kHd / 2], const float2 (&b)[kHd / 2]) {
+    float2 s0 = __fmul2_rn(a[0], b[0]), s1 = __fmul2_rn(a[1], b[1]);
+#pragma unroll
+    for (int i = 2; i < kHd / 2; i += 2) {
+        s0 = __ffma2_rn(a[i], b[i], s0);
+        s1 = __ffma2_rn(a[i + 1], b[i + 1], s1);
+    }
+    return (s0.x + s1.x) + (s0.y + s1.y);
+}
+__device__ __forceinline__ void axpy16(float a, const float2 (&x)[kHd / 2], float2 (&y)[kHd / 2]) {
+    const float2 a2 = make_float2(a, a);
+#pragma unroll
+    for (int i = 0; i < kHd / 2; ++i) y[i] = __ffma2_rn(a2, x[i], y[i]);
+}   // block = sequence length rounded up to a warp (one query/key per thread)
 
 __global__ void __launch_bounds__(kAttnMaxThreads) attn_fwd_kernel(const float* __restrict__ qkv,
                                                                 float* __restrict__ out, float* __restrict__ lse,
@@ -477,39 +505,33 @@ __global__ void __launch_bounds__(kAttnMaxThreads) attn_fwd_kernel(const float* 
     __syncthreads();
     for (int i = threadIdx.x; i < L; i += (int)blockDim.x) {
         const int64_t row = row0 + (int64_t)i * geo.step_stride;
-        float q[kHd], acc[kHd];
+        float2 q[kHd / 2], acc[kHd / 2];
 #pragma unroll
-        for (int d = 0; d < kHd; ++d) {
-            q[d] = qkv[row * 3 * E + h * kHd + d] * scale;
-            acc[d] = 0.f;
+        for (int d = 0; d < kHd / 2; ++d) {
+            q[d] = make_float2(qkv[row * 3 * E + h * kHd + 2 * d] * scale, qkv[row * 3 * E + h * kHd + 2 * d + 1] * scale);
+            acc[d] = make_float2(0.f, 0.f);
         }
         float m = -INFINITY, l = 0.f;
         for (int t = 0; t < L; ++t) {
-            const float4* k4 = reinterpret_cast<const float4*>(Ks + t * kHd);
-            float s = 0.f;
-#pragma unroll
-            for (int d4 = 0; d4 < kHd / 4; ++d4) {
-                float4 kk = k4[d4];
-                s += q[4 * d4] * kk.x + q[4 * d4 + 1] * kk.y + q[4 * d4 + 2] * kk.z + q[4 * d4 + 3] * kk.w;
-            }
+            float2 k2[kHd / 2], v2[kHd / 2];
+            load_row2(Ks + t * kHd, k2);
+            const float s = dot16(q, k2);
             const float mn = fmaxf(m, s);
             const float corr = __expf(m - mn);
             const float pr = __expf(s - mn);
             l = l * corr + pr;
-            const float4* v4 = reinterpret_cast<const float4*>(Vs + t * kHd);
+            load_row2(Vs + t * kHd, v2);
+            const float2 c2 = make_float2(corr, corr), p2 = make_float2(pr, pr);
 #pragma unroll
-            for (int d4 = 0; d4 < kHd / 4; ++d4) {
-                float4 vv = v4[d4];
-                acc[4 * d4] = acc[4 * d4] * corr + pr * vv.x;
-                acc[4 * d4 + 1] = acc[4 * d4 + 1] * corr + pr * vv.y;
-                acc[4 * d4 + 2] = acc[4 * d4 + 2] * corr + pr * vv.z;
-                acc[4 * d4 + 3] = acc[4 * d4 + 3] * corr + pr * vv.w;
-            }
+            for (int d = 0; d < kHd / 2; ++d) acc[d] = __ffma2_rn(p2, v2[d], __fmul2_rn(acc[d], c2));
             m = mn;
         }
         const float inv = 1.f / l;
 #pragma unroll
-        for (int d = 0; d < kHd; ++d) out[row * E + h * kHd + d] = acc[d] * inv;
+        for (int d = 0; d < kHd / 2; ++d) {
+            out[row * E + h * kHd + 2 * d] = acc[d].x * inv;
+            out[row * E + h * kHd + 2 * d + 1] = acc[d].y * inv;
+        }
         lse[row * H + h] = m + logf(l);
     }
 }
@@ -558,20 +580,24 @@ __global__ void __launch_bounds__(kAttnMaxThreads) attn_bwd_kernel(const float* 
         const int chunk = (L + parts - 1) / parts;
         const int t0 = part * chunk, t1 = min(L, t0 + chunk);
         if (act) {
-            float q[kHd], go[kHd], dq[kHd];
+            float2 q[kHd / 2], go[kHd / 2], dq[kHd / 2];
+            load_row2(Qs + i * kHd, q);
+            load_row2(dOs + i * kHd, go);
 #pragma unroll
-            for (int d = 0; d < kHd; ++d) { q[d] = Qs[i * kHd + d]; go[d] = dOs[i * kHd + d]; dq[d] = 0.f; }
+            for (int d = 0; d < kHd / 2; ++d) dq[d] = make_float2(0.f, 0.f);
             const float li = Ls[i], di = Ds[i];
             for (int t = t0; t < t1; ++t) {
-                float s = 0.f, dp = 0.f;
-#pragma unroll
-                for (int d = 0; d < kHd; ++d) { s += q[d] * Ks[t * kHd + d]; dp += go[d] * Vs[t * kHd + d]; }
-                const float ds = __expf(s - li) * (dp - di);
-#pragma unroll
-                for (int d = 0; d < kHd; ++d) dq[d] += ds * Ks[t * kHd + d];
+                float2 k2[kHd / 2], v2[kHd / 2];
+                load_row2(Ks + t * kHd, k2);
+                load_row2(Vs + t * kHd, v2);
+                const float ds = __expf(dot16(q, k2) - li) * (dot16(go, v2) - di);
+                axpy16(ds, k2, dq);
             }
 #pragma unroll
-            for (int d = 0; d < kHd; ++d) red[(part * L + i) * (kHd + 1) + d] = dq[d];      // odd row stride: no bank conflicts
+            for (int d = 0; d < kHd / 2; ++d) {                                 // odd row stride: no bank conflicts
+                red[(part * L + i) * (kHd + 1) + 2 * d] = dq[d].x;
+                red[(part * L + i) * (kHd + 1) + 2 * d + 1] = dq[d].y;
+            }
         }
         __syncthreads();
         for (int idx = threadIdx.x; idx < L * kHd; idx += (int)blockDim.x) {
@@ -583,25 +609,25 @@ __global__ void __launch_bounds__(kAttnMaxThreads) attn_bwd_kernel(const float* 
         __syncthreads();
         if (act) {
             const int t = i;
-            float k[kHd], v[kHd], dk[kHd], dv[kHd];
+            float2 k[kHd / 2], v[kHd / 2], dk[kHd / 2], dv[kHd / 2];
+            load_row2(Ks + t * kHd, k);
+            load_row2(Vs + t * kHd, v);
 #pragma unroll
-            for (int d = 0; d < kHd; ++d) { k[d] = Ks[t * kHd + d]; v[d] = Vs[t * kHd + d]; dk[d] = dv[d] = 0.f; }
+            for (int d = 0; d < kHd / 2; ++d) dk[d] = dv[d] = make_float2(0.f, 0.f);
             for (int i2 = t0; i2 < t1; ++i2) {
-                float s = 0.f, dp = 0.f;
-#pragma unroll
-                for (int d = 0; d < kHd; ++d) { s += Qs[i2 * kHd + d] * k[d]; dp += dOs[i2 * kHd + d] * v[d]; }
-                const float pr = __expf(s - Ls[i2]);
-                const float ds = pr * (dp - Ds[i2]);
-#pragma unroll
-                for (int d = 0; d < kHd; ++d) {
-                    dv[d] += pr * dOs[i2 * kHd + d];
-                    dk[d] += ds * Qs[i2 * kHd + d];
-                }
+                float2 q2[kHd / 2], g2[kHd / 2];
+                load_row2(Qs + i2 * kHd, q2);
+                load_row2(dOs + i2 * kHd, g2);
+                const float pr = __expf(dot16(q2, k) - Ls[i2]);
+                const float ds = pr * (dot16(g2, v) - Ds[i2]);
+                axpy16(pr, g2, dv);
+                axpy16(ds, q2, dk);
             }
 #pragma unroll
-            for (int d = 0; d < kHd; ++d) {
-                red[(part * L + t) * (2 * kHd + 1) + d] = dk[d];
-                red[(part * L + t) * (2 * kHd + 1) + kHd + d] = dv[d];
+            for (int d = 0; d < kHd / 2; ++d) {
+                float* r = red + (part * L + t) * (2 * kHd + 1);
+                r[2 * d] = dk[d].x; r[2 * d + 1] = dk[d].y;
+                r[kHd + 2 * d] = dv[d].x; r[kHd + 2 * d + 1] = dv[d].y;
             }
         }
         __syncthreads();
@@ -615,44 +641,49 @@ __global__ void __launch_bounds__(kAttnMaxThreads) attn_bwd_kernel(const float* 
     }
     // pass A: one query per thread -> dQ
     for (int i = threadIdx.x; i < L; i += (int)blockDim.x) {
-        float q[kHd], go[kHd], dq[kHd];
+        float2 q[kHd / 2], go[kHd / 2], dq[kHd / 2];
+        load_row2(Qs + i * kHd, q);
+        load_row2(dOs + i * kHd, go);
 #pragma unroll
-        for (int d = 0; d < kHd; ++d) { q[d] = Qs[i * kHd + d]; go[d] = dOs[i * kHd + d]; dq[d] = 0.f; }
+        for (int d = 0; d < kHd / 2; ++d) dq[d] = make_float2(0.f, 0.f);
         const float li = Ls[i], di = Ds[i];
         for (int t = 0; t < L; ++t) {
-            float s = 0.f, dp = 0.f;
-#pragma unroll
-            for (int d = 0; d < kHd; ++d) { s += q[d] * Ks[t * kHd + d]; dp += go[d] * Vs[t * kHd + d]; }
-            const float ds = __expf(s - li) * (dp - di);
-#pragma unroll
-            for (int d = 0; d < kHd; ++d) dq[d] += ds * Ks[t * kHd + d];
+            float2 k2[kHd / 2], v2[kHd / 2];
+            load_row2(Ks + t * kHd, k2);
+            load_row2(Vs + t * kHd, v2);
+            const float ds = __expf(dot16(q, k2) - li) * (dot16(go, v2) - di);
+            axpy16(ds, k2, dq);
         }
         const int64_t row = row0 + (int64_t)i * geo.step_stride;
 #pragma unroll
-        for (int d = 0; d < kHd; ++d) dqkv[row * 3 * E + h * kHd + d] = dq[d] * scale;
+        for (int d = 0; d < kHd / 2; ++d) {
+            dqkv[row * 3 * E + h * kHd + 2 * d] = dq[d].x * scale;
+            dqkv[row * 3 * E + h * kHd + 2 * d + 1] = dq[d].y * scale;
+        }
     }
     // pass B: one key per thread -> dK, dV
     for (int t = threadIdx.x; t < L; t += (int)blockDim.x) {
-        float k[kHd], v[kHd], dk[kHd], dv[kHd];
+        float2 k[kHd / 2], v[kHd / 2], dk[kHd / 2], dv[kHd / 2];
+        load_row2(Ks + t * kHd, k);
+        load_row2(Vs + t * kHd, v);
 #pragma unroll
-        for (int d = 0; d < kHd; ++d) { k[d] = Ks[t * kHd + d]; v[d] = Vs[t * kHd + d]; dk[d] = dv[d] = 0.f; }
+        for (int d = 0; d < kHd / 2; ++d) dk[d] = dv[d] = make_float2(0.f, 0.f);
         for (int i = 0; i < L; ++i) {
-            float s = 0.f, dp = 0.f;
-#pragma unroll
-            for (int d = 0; d < kHd; ++d) { s += Qs[i * kHd + d] * k[d]; dp += dOs[i * kHd + d] * v[d]; }
-            const float pr = __expf(s - Ls[i]);
-            const float ds = pr * (dp - Ds[i]);
-#pragma unroll
-            for (int d = 0; d < kHd; ++d) {
-                dv[d] += pr * dOs[i * kHd + d];
-                dk[d] += ds * Qs[i * kHd + d];   // Qs is pre-scaled, so this already carries `scale`
-            }
+            float2 q2[kHd / 2], g2[kHd / 2];
+            load_row2(Qs + i * kHd, q2);
+            load_row2(dOs + i * kHd, g2);
+            const float pr = __expf(dot16(q2, k) - Ls[i]);
+            const float ds = pr * (dot16(g2, v) - Ds[i]);
+            axpy16(pr, g2, dv);
+            axpy16(ds, q2, dk);          // Qs is pre-scaled, so this already carries `scale`
         }
         const int64_t row = row0 + (int64_t)t * geo.step_stride;
 #pragma unroll
-        for (int d = 0; d < kHd; ++d) {
-            dqkv[row * 3 * E + E + h * kHd + d] = dk[d];
-            dqkv[row * 3 * E + 2 * E + h * kHd + d] = dv[d];
+        for (int d = 0; d < kHd / 2; ++d) {
+            dqkv[row * 3 * E + E + h * kHd + 2 * d] = dk[d].x;
+            dqkv[row * 3 * E + E + h * kHd + 2 * d + 1] = dk[d].y;
+            dqkv[row * 3 * E + 2 * E + h * kHd + 2 * d] = dv[d].x;
+            dqkv[row * 3 * E + 2 * E + h * kHd + 2 * d + 1] = dv[d].y;
         }
     }
 }
