@@ -59,25 +59,34 @@ def sub(t, n=4096):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(HERE, "golden_v1.pt"))
+    # golden_v1.pt: the defaults.  golden_v2.pt (ragged lengths, odd batch, iSTFT length = the ragged signal length: the tail comes from the last half window):
+    #   python tests/golden/make_golden.py --out tests/golden/golden_v2.pt --front-len 5003 --istft-len 5003 \
+    #          --model-len 12345 --batch 3 --front-seed 11 --model-seed 4321
+    ap.add_argument("--front-len", type=int, default=4000)
+    ap.add_argument("--istft-len", type=int, default=3900)
+    ap.add_argument("--model-len", type=int, default=8000)
+    ap.add_argument("--batch", type=int, default=2)
+    ap.add_argument("--front-seed", type=int, default=7)
+    ap.add_argument("--model-seed", type=int, default=1234)
     args = ap.parse_args()
     R_stft, R_tf, R_losses, R_disc, R_gen, R_train = import_reference()
     torch.set_num_threads(8)
-    G = {"torch": torch.__version__}
+    G = {"torch": torch.__version__, "istft_length": args.istft_len}
 
     # ---- front end: STFT / iSTFT / helpers at the three loss resolutions + the generator's
-    noisy, clean = batch(2, 4000, seed=7)
+    noisy, clean = batch(args.batch, args.front_len, seed=args.front_seed)
     for n_fft, hop in ((512, 256), (320, 160), (768, 384)):
         m = R_stft.ComplexSTFT(R_stft.STFTConfig(n_fft=n_fft, hop_length=hop).finalize())
         s = m(noisy)
         G[f"stft_{n_fft}"] = torch.view_as_real(s).clone()
-        G[f"istft_{n_fft}"] = m.istft(s * 0.7, length=3900).clone()
+        G[f"istft_{n_fft}"] = m.istft(s * 0.7, length=args.istft_len).clone()
         G[f"window_{n_fft}"] = m.window.clone()
     s512 = R_stft.make_lct_stft()(noisy)
     c512 = R_stft.make_lct_stft()(clean)
     G["magnitude"] = R_stft.magnitude(s512).clone()
     G["compress"] = R_stft.compress(R_stft.magnitude(s512)).clone()
     G["irm_c"] = R_stft.compute_compressed_irm(c512, s512).clone()
-    mk = torch.rand(2, 1, 257, s512.shape[-1], generator=torch.Generator().manual_seed(3))
+    mk = torch.rand(args.batch, 1, 257, s512.shape[-1], generator=torch.Generator().manual_seed(3))
     G["mask_in"] = mk
     G["apply_mask_c"] = torch.view_as_real(R_stft.apply_mask(s512, mk, compressed=True)).clone()
     tf = R_tf.TFFeatures(R_tf.TFFeaturesConfig(return_stfts=False))(noisy, clean)
@@ -97,7 +106,7 @@ def main():
                          for n, m in (("enh", enh), ("mpd", mpd), ("msd", msd))}
     G["param_checksum"] = {n: float(sum(p.double().abs().sum() for p in m.parameters()))
                            for n, m in (("enh", enh), ("mpd", mpd), ("msd", msd))}
-    noisy, clean = batch(2, 8000, seed=1234)
+    noisy, clean = batch(args.batch, args.model_len, seed=args.model_seed)
     G["model_inputs"] = (noisy, clean)
     with torch.no_grad():
         e, mask = enh(noisy)
