@@ -18,9 +18,11 @@ def G(request):
     return torch.load(os.path.join(os.path.dirname(GOLD), request.param), weights_only=False)
 
 
-# Two tests were calibrated on golden_v1 and, on the ragged golden_v2 vectors (added at the very end of round 1), exceed
-# their tolerances in an assertion that could not be examined any more (GPU budget exhausted): they run on v1, and on
-# v2 as non-strict xfail so that the next round sees the outcome.  Every other test here passes on both files.
+# Two tests were calibrated on golden_v1 and exceed their tolerances on the ragged golden_v2 vectors (added at the very
+# end of round 1, GPU budget exhausted): they run on v1, and on v2 as non-strict xfail so that the next round sees the
+# outcome.  Every other test here passes on both files.  Front end: v2 contains a noisy bin of magnitude 7e-5 (v1:
+# 3.7e-3) where |X|^0.3 and the IRM amplify absolute STFT differences - on CPU even a float64-exact DFT rounded to
+# fp32 is 7.5e-5 away from the reference's irm_c there: the bound has to become condition-aware.
 _V2_OPEN = pytest.param("golden_v2.pt", marks=pytest.mark.xfail(
     strict=False, reason="ragged-length vectors: tolerance calibrated on golden_v1 exceeded; open item for round 2"))
 
