@@ -5,7 +5,7 @@ import os
 import pytest
 import torch
 
-from util import rel_err
+from util import rel_err, rel_err_where
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v1.pt")
@@ -53,15 +53,26 @@ def test_front_end_vs_reference_vectors(dev, G12):
     st = ComplexSTFT(STFTConfig()).to(dev)
     s, c = st(noisy), st(clean)
     assert rel_err(magnitude(s), G["magnitude"]) < 1e-5
-    # |X|^0.3 has slope 0.3 |X|^-0.7: the ~1e-6 absolute fp32 differences between two FFTs are amplified ~10x in the
-    # small bins, hence the tolerance of the other compressed quantities below rather than the STFT's
-    assert rel_err(compress(magnitude(s)), G["compress"]) < 5e-5
-    assert rel_err(compute_compressed_irm(c, s), G["irm_c"]) < 5e-5
+    # Compressed quantities: |X|^0.3 has slope 0.3 |X|^-0.7 and the IRM |S|^c / (|X|^c + eps) is unbounded where |X| -> 0,
+    # so the ~1e-6 absolute fp32 differences between two FFTs are amplified in the near-empty bins (even a float64 DFT
+    # rounded to fp32 is 7.5e-5 from the reference's irm_c on golden_v2, 2.8e-6 on the well-conditioned bins).  Tight
+    # bound on the bins where both magnitudes reach 1e-3 of their maximum (> 99.9 % of them), loose bound on all.
+    mag_x, mag_c = G["magnitude"], magnitude(c).cpu()
+    well_x = mag_x >= 1e-3 * mag_x.max()
+    well = well_x & (mag_c >= 1e-3 * mag_c.max())
+    assert well.float().mean().item() > 0.99
+    got = compress(magnitude(s))
+    assert rel_err_where(got, G["compress"], well_x) < 1e-5 and rel_err(got, G["compress"]) < 2e-3
+    got = compute_compressed_irm(c, s)
+    assert rel_err_where(got, G["irm_c"], well) < 5e-5 and rel_err(got, G["irm_c"]) < 2e-3
     assert rel_err(torch.view_as_real(apply_mask(s, G["mask_in"].to(dev), compressed=True).contiguous()),
                    G["apply_mask_c"]) < 1e-5
     tf = TFFeatures(TFFeaturesConfig(return_stfts=False)).to(dev)(noisy, clean)
     for k, v in G["tf_features"].items():
-        assert rel_err(tf[k], v) < 5e-5, k
+        if k == "noisy_mag":
+            assert rel_err(tf[k], v) < 5e-5, k
+        else:
+            assert rel_err_where(tf[k], v, well) < 5e-5 and rel_err(tf[k], v) < 2e-3, k
 
 
 def test_models_vs_reference_vectors(dev, G):

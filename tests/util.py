@@ -29,6 +29,17 @@ def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
     return (a - b).abs().max().item() / den
 
 
+def rel_err_where(a: torch.Tensor, b: torch.Tensor, mask: torch.Tensor) -> float:
+    """rel_err restricted to the elements selected by `mask` (still relative to the largest reference value overall)."""
+    a = a.detach().cpu().double()
+    b = b.detach().cpu().double()
+    mask = mask.detach().cpu()
+    assert a.shape == b.shape == mask.shape, (a.shape, b.shape, mask.shape)
+    den = b.abs().max().item() or 1.0
+    d = (a - b).abs()[mask]
+    return (d.max().item() if d.numel() else 0.0) / den
+
+
 def cpu_params(module: torch.nn.Module):
     return {k: v.detach().cpu().clone() for k, v in module.state_dict().items()}
 
