@@ -53,10 +53,21 @@ def test_front_end_vs_reference_vectors(dev, G12):
     st = ComplexSTFT(STFTConfig()).to(dev)
     s, c = st(noisy), st(clean)
     assert rel_err(magnitude(s), G["magnitude"]) < 1e-5
-    # Compressed quantities: |X|^0.3 has slope 0.3 |X|^-0.7 and the IRM |S|^c / (|X|^c + eps) is unbounded where |X| -> 0,
-    # so the ~1e-6 absolute fp32 differences between two FFTs are amplified in the near-empty bins (even a float64 DFT
-    # rounded to fp32 is 7.5e-5 from the reference's irm_c on golden_v2, 2.8e-6 on the well-conditioned bins).  Tight
-    # bound on the bins where both magnitudes reach 1e-3 of their maximum (> 99.9 % of them), loose bound on all.
+    if "istft_length" not in G:
+        # golden_v1 (well conditioned: smallest noisy bin 3.7e-3): plain bounds, exactly as verified on the GPU in round 1
+        assert rel_err(compress(magnitude(s)), G["compress"]) < 5e-5
+        assert rel_err(compute_compressed_irm(c, s), G["irm_c"]) < 5e-5
+        assert rel_err(torch.view_as_real(apply_mask(s, G["mask_in"].to(dev), compressed=True).contiguous()),
+                       G["apply_mask_c"]) < 1e-5
+        tf = TFFeatures(TFFeaturesConfig(return_stfts=False)).to(dev)(noisy, clean)
+        for k, v in G["tf_features"].items():
+            assert rel_err(tf[k], v) < 5e-5, k
+        return
+    # golden_v2.  Compressed quantities: |X|^0.3 has slope 0.3 |X|^-0.7 and the IRM |S|^c / (|X|^c + eps) is unbounded
+    # where |X| -> 0, so the ~1e-6 absolute fp32 differences between two FFTs are amplified in the near-empty bins (v2 has
+    # one of magnitude 7e-5: even a float64 DFT rounded to fp32 is 7.5e-5 from the reference's irm_c there, 2.8e-6 on the
+    # well-conditioned bins).  Tight bound on the bins where both magnitudes reach 1e-3 of their maximum (> 99.9 % of
+    # them), loose bound on all.  (Logic dry-run on CPU with the fp64-exact oracle path; not yet run on a GPU.)
     mag_x, mag_c = G["magnitude"], magnitude(c).cpu()
     well_x = mag_x >= 1e-3 * mag_x.max()
     well = well_x & (mag_c >= 1e-3 * mag_c.max())
