@@ -4,6 +4,7 @@
 
     python bench.py --gpus 1 --steps 20 --warmup 5            # this framework (lctgan sm_100a kernels)
     python bench.py --impl reference --steps 3 --warmup 1     # the reference's CPU path (oracle port), host cores
+    python bench.py --impl reference-cuda --steps 10          # the same port on stock torch CUDA ops (cuDNN/cuFFT/cuBLAS)
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One "step" is one full D+G iteration of the reference's train_one_epoch loop body (train.py:165-249)
@@ -93,51 +94,131 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------------
-# the reference arm / CPU baseline: the oracle port of the reference's step on the host cores
+# the reference arms: the oracle port of the reference's step on stock torch operators.  Nothing here imports the
+# product package (lctgan): initial weights come from oracle/ref_init.py (stock torch containers, pinned against
+# the reference's own parameter checksums by tests/test_oracle_golden.py).
 # --------------------------------------------------------------------------------------------------
-def cpu_reference_steps(steps, warmup, budget_s=150.0, batch=BATCH):
-    """Time `steps` D+G steps of the CPU oracle (reference algorithm, torch CPU ops, all host threads).
-    Returns (samples_per_s, ms_per_step, sample_batch, cores)."""
+def _config(gan_loss, world):
+    """The workload description shared verbatim by every arm (ours, reference, reference-cuda)."""
+    return {"workload": WORKLOAD if gan_loss == "ls" else WORKLOAD.replace("LS loss", "hinge loss").replace(
+        "configs[2]", "configs[3]"), "gan_loss": gan_loss, "batch_per_gpu": BATCH, "segment_samples": SEGMENT,
+        "parallelism": f"dp{world}", "l2": "no explicit flush: one step streams > 2 GB of activations (>> 126 MB L2)"}
+
+
+def _oracle_state(device):
     import torch
     from oracle import lct_oracle as O
-    from lctgan.training import build_models
-    cores = torch.get_num_threads()
-    enh, mpd, msd, _tf, _mr, _g, _d = build_models("cpu", gan_seed=42)
-    cp = lambda m: {k: v.detach().clone() for k, v in m.state_dict().items()}
-    st = O.StepState(cp(enh), cp(mpd), cp(msd), order_g=[k for k, _ in enh.named_parameters()],
-                     order_d=([k for k, _ in mpd.named_parameters()], [k for k, _ in msd.named_parameters()]))
-    wins = [O.hann_window(n) for n in O.MR_FFT_SIZES]
-    b = batch
-    noisy, clean = O.synthetic_batch(b, SEGMENT, seed=1234)
-    t0 = time.perf_counter()
-    O.train_step(st, noisy, clean, wins, gan_loss="ls", aten_gru=True)     # first (cold) step sizes the sample
-    t_first = time.perf_counter() - t0
-    while b > 1 and (steps + max(warmup - 1, 0)) * t_first * (b / batch) > budget_s:
-        b //= 2
-    noisy, clean = noisy[:b], clean[:b]
-    for _ in range(max(warmup - 1, 0)):
-        O.train_step(st, noisy, clean, wins, gan_loss="ls", aten_gru=True)
+    from oracle import ref_init
+    Pe, Pp, Ps = ref_init.init_state_dicts(42)
+    mv = lambda d: {k: v.to(device) for k, v in d.items()}
+    st = O.StepState(mv(Pe), mv(Pp), mv(Ps), order_g=ref_init.param_order(Pe),
+                     order_d=(ref_init.param_order(Pp), ref_init.param_order(Ps)))
+    wins = [O.hann_window(n).to(device) for n in O.MR_FFT_SIZES]
+    return O, st, wins
+
+
+def reference_steps(steps, warmup, gan_loss="ls", device="cpu", batch=BATCH):
+    """Time `steps` D+G steps of the oracle port (reference algorithm on stock torch operators) after `warmup` untimed
+    ones, batch 8 x 2 s exactly like the product arm.  Returns (samples_per_s, ms_per_step, losses of the first step)."""
+    import torch
+    O, st, wins = _oracle_state(device)
+    noisy, clean = O.synthetic_batch(batch, SEGMENT, seed=1234)
+    noisy, clean = noisy.to(device), clean.to(device)
+    sync = torch.cuda.synchronize if str(device).startswith("cuda") else (lambda: None)
+    first = None
+    for _ in range(warmup):
+        out = O.train_step(st, noisy, clean, wins, gan_loss=gan_loss, aten_gru=True)
+        first = first or out
+    sync()
     t0 = time.perf_counter()
     for _ in range(steps):
-        O.train_step(st, noisy, clean, wins, gan_loss="ls", aten_gru=True)
+        out = O.train_step(st, noisy, clean, wins, gan_loss=gan_loss, aten_gru=True)
+        first = first or out
+    sync()
     dt = (time.perf_counter() - t0) / steps
-    return b / dt, dt * 1e3, b, cores
+    return batch / dt, dt * 1e3, first
+
+
+def reference_rtf(device="cpu"):
+    """BASELINE.md section 3 inference baseline: the reference enhancer (oracle port, eval / no_grad) on the utterances
+    of measure_enhance_rtf (1-10 s, zero-padded to the batch maximum like datasets.py:210-221), batch 1 and 16."""
+    import torch
+    O, st, _ = _oracle_state(device)
+    out = {}
+    gl = torch.Generator().manual_seed(7)
+    for bs in (1, 16):
+        x, lens = _rtf_batch(bs, gl)
+        x = x.to(device)
+        with torch.no_grad():
+            O.enhancer_forward(st.enh, x[:, :16000], aten_gru=True)
+            t0 = time.perf_counter()
+            y, _ = O.enhancer_forward(st.enh, x, aten_gru=True)
+            y = y.cpu()
+            dt = time.perf_counter() - t0
+        out[f"batch{bs}"] = {"rtf": dt / (sum(lens) / 16000.0), "ms": dt * 1e3, "audio_s": sum(lens) / 16000.0}
+    return out
+
+
+def _rtf_batch(bs, gl):
+    import torch
+    lens = torch.randint(16000, 160001, (bs,), generator=gl).tolist()
+    x = torch.zeros(bs, max(lens))
+    for i, n in enumerate(lens):
+        x[i, :n] = torch.randn(n, generator=gl) * 0.1
+    return x, lens
 
 
 def run_reference(args):
+    """`--impl reference` (host CPU, all threads) and `--impl reference-cuda` (stock torch CUDA operators: cuDNN / cuFFT /
+    cuBLAS on the same B200; fp32, or TF32-allowed with --allow-tf32).  Rank 0 alone works; other ranks exit 0."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sps, ms, b, cores = cpu_reference_steps(args.steps, args.warmup)
-    sample = f"{args.steps} timed D+G steps of {b} x 2 s segments (batch {BATCH} workload" + \
-             (", bounded to fit the time budget)" if b != BATCH else ")")
-    line = {"impl": "reference", "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+    import torch
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    cuda = args.impl == "reference-cuda"
+    if cuda:
+        if not torch.cuda.is_available():
+            print(json.dumps({"impl": "reference-cuda", "unavailable": "no CUDA device"}), flush=True)
+            return
+        torch.backends.cuda.matmul.allow_tf32 = bool(args.allow_tf32)
+        torch.backends.cudnn.allow_tf32 = bool(args.allow_tf32)
+        device, cores = "cuda:0", 0
+    else:
+        torch.set_num_threads(os.cpu_count() or 1)        # torchrun exports OMP_NUM_THREADS=1: use every host core
+        device, cores = "cpu", torch.get_num_threads()
+    if args.what == "rtf":
+        print(json.dumps({"impl": args.impl, "what": "enhance_rtf", "cores": cores, "rtf": reference_rtf(device)}),
+              flush=True)
+        return
+    sps, ms, first = reference_steps(args.steps, args.warmup, args.gan_loss, device)
+    where = "host CPU" if not cuda else ("stock torch CUDA ops (cuDNN/cuFFT/cuBLAS), " +
+                                         ("TF32 allowed" if args.allow_tf32 else "fp32"))
+    sample = (f"{args.steps} timed D+G steps of {BATCH} x 2 s segments after {args.warmup} warm-up steps (oracle port of "
+              f"train.py:165-249, {where}" + (f", {cores} threads)" if not cuda else ")"))
+    line = {"impl": args.impl, "metric": METRIC, "value": sps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "device": "host CPU"},
+            "dtype": "f32" if not (cuda and args.allow_tf32) else "tf32", "data": "synthetic",
+            "config": _config(args.gan_loss, world), "device": where,
             "cpu_baseline": {"value": sps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": sps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0, "losses_first_step": {k: first[k] for k in ("d_loss", "g_loss", "mr", "mask", "adv", "fm")}}
     print(json.dumps(line), flush=True)
+
+
+def _sub_bench(extra, timeout=600):
+    """Run another arm of this script in a subprocess (so that the product process never imports the oracle) and return
+    its JSON line."""
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "OMP_NUM_THREADS")}
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__)] + extra, capture_output=True, text=True,
+                           timeout=timeout, env=env)
+        for ln in reversed(r.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)
+        return {"error": (r.stderr or r.stdout)[-400:]}
+    except Exception as e:      # a missing baseline must not lose the product's measurement
+        return {"error": repr(e)}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -268,18 +349,14 @@ def measure_frontend_rooflines(dev, peaks):
 def measure_enhance_rtf(dev):
     """BASELINE.json configs[1]: full-utterance enhancement, synthetic 16 kHz utterances of 1-10 s zero-padded to the
     batch maximum like datasets.py:210-221, batch 1 and 16, eval + no_grad; real-time factor = (enhancer wall time
-    incl. the D2H copy of the waveforms) / (seconds of audio in the batch)."""
+    incl. the H2D copy of the batch and the D2H copy of the waveforms) / (seconds of audio in the batch)."""
     import torch
     from lctgan.training import build_models
     enh = build_models(dev, gan_seed=42)[0].eval()
     gl = torch.Generator().manual_seed(7)
     out = {}
     for bs in (1, 16):
-        lens = torch.randint(16000, 160001, (bs,), generator=gl)
-        T = int(lens.max())
-        x = torch.zeros(bs, T)
-        for i, n in enumerate(lens.tolist()):
-            x[i, :n] = torch.randn(n, generator=gl) * 0.1
+        x, lens = _rtf_batch(bs, gl)
         xh = x.pin_memory()
         with torch.no_grad():
             for _ in range(2):
@@ -290,9 +367,70 @@ def measure_enhance_rtf(dev):
             for _ in range(reps):
                 y = enh(xh.to(dev, non_blocking=True))[0].cpu()
             dt = (time.perf_counter() - t0) / reps
-        out[f"batch{bs}"] = {"rtf": dt / (float(lens.sum()) / 16000.0), "ms": dt * 1e3,
-                             "audio_s": float(lens.sum()) / 16000.0, "padded_to_s": T / 16000.0}
+        out[f"batch{bs}"] = {"rtf": dt / (sum(lens) / 16000.0), "ms": dt * 1e3, "audio_s": sum(lens) / 16000.0,
+                             "padded_to_s": x.shape[1] / 16000.0}
     return out
+
+
+GOLDEN_V3 = os.path.join(ROOT, "tests", "golden", "golden_v3.pt")
+_LOG_KEYS = {"D_loss": "d_loss", "G_loss": "g_loss", "MR": "mr", "Mask": "mask", "Adv": "adv", "FM": "fm"}
+
+
+def parity_check(losses, gan_loss, world, tol_rel):
+    """Step-1 losses of the benchmarked configuration against the reference's own train_one_epoch log at this exact shape
+    (tests/golden/golden_v3.pt, written by tests/golden/make_golden.py --logs-only from the unmodified reference).
+    With N > 1 the discriminator update averages gradients over ranks that hold different data, so only the quantities
+    computed before that update are comparable (d_loss, mr, mask)."""
+    import torch
+    if not os.path.exists(GOLDEN_V3):
+        return {"checked": False, "why": "tests/golden/golden_v3.pt missing"}
+    ref = torch.load(GOLDEN_V3, weights_only=False)[f"train_{gan_loss}"]["logs"][0]
+    keys = list(_LOG_KEYS) if world == 1 else ["D_loss", "MR", "Mask"]
+    worst, bad = 0.0, []
+    for rk in keys:
+        got, want = losses[_LOG_KEYS[rk]], ref[rk]
+        tol = 1.01e-4 + tol_rel * abs(want)          # 4 printed decimals + the stated tensor-core tolerance
+        worst = max(worst, abs(got - want) / tol)
+        if abs(got - want) > tol:
+            bad.append((rk, got, want))
+    return {"checked": True, "ok": not bad, "fixture": "tests/golden/golden_v3.pt (reference train_one_epoch, step 1)",
+            "tolerance": f"|got - ref| <= 1.01e-4 + {tol_rel:g} * |ref|", "worst_over_tolerance": worst,
+            "compared": keys, "got": {k: losses[_LOG_KEYS[k]] for k in keys}, "ref": {k: ref[k] for k in keys},
+            "mismatch": bad}
+
+
+def measure_variant(dev, mode, steps=10, warmup=3):
+    """Throughput of the same step through other paths of this repo (context for the headline):
+    "api_eager"  - the drop-in modules driven the way the unmodified train.py drives them: literal schedule (two enhancer
+                   forwards, four discriminator passes in the D step), torch.optim.AdamW, clip_grad_norm_, no CUDA graph;
+    "fp32"       - the benchmarked schedule (graph, fused AdamW) with every tensor-core path off (fp32 SIMT kernels)."""
+    import torch
+    from lctgan import config
+    from lctgan.training import GraphedTrainStep, StepArgs, build_models, synthetic_batch, train_step
+    noisy, clean = (t.to(dev) for t in synthetic_batch(BATCH, SEGMENT, seed=1234))
+    try:
+        if mode == "api_eager":
+            M = build_models(dev, gan_seed=42)
+            run = lambda: train_step(*M, noisy, clean, StepArgs(gan_loss="ls"))
+        else:
+            config.set_precision("fp32")
+            M = build_models(dev, gan_seed=42, fused_optim=True)
+            g = GraphedTrainStep(*M, noisy, clean, StepArgs(gan_loss="ls", reuse_enhancer_forward=True, batch_d_step=True,
+                                                            defer_dead_d_grads=True), warmup=3)
+            run = g
+        for _ in range(warmup):
+            run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        return {"value": BATCH / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps}
+    finally:
+        config.set_precision("bf16")
 
 
 def main():
@@ -300,12 +438,18 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"])
+    ap.add_argument("--what", default="step", choices=["step", "rtf"], help="reference arms: time the training step or "
+                    "the enhancement real-time factor")
+    ap.add_argument("--allow-tf32", action="store_true", help="reference-cuda: allow TF32 in cuDNN / cuBLAS")
     ap.add_argument("--gan_loss", default="ls", choices=["ls", "hinge"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-comparators", action="store_true", help="skip the torch-CUDA / api_eager / fp32 comparator legs")
     ap.add_argument("--no-reuse", action="store_true", help="run the enhancer forward twice per step like train.py does "
                     "(default: one forward serves the D and the G step: identical values, SURVEY 8f N1)")
+    ap.add_argument("--no-batch-d", action="store_true", help="D step: clean and enhanced as two discriminator passes "
+                    "instead of one batch of 2B")
     ap.add_argument("--torch-optim", action="store_true", help="use torch.optim.AdamW (as train.py builds it) instead of "
                     "the fused multi-tensor AdamW kernel (same update rule; SURVEY 8f N2)")
     ap.add_argument("--skip-dead-d-grads", action="store_true", help="do not compute the discriminator weight gradients "
@@ -317,7 +461,7 @@ def main():
     ap.add_argument("--profile-range", action="store_true", help="bracket the timed steps with cudaProfilerStart/Stop "
                     "(for `ncu --profile-from-start off`: the launch list of exactly the timed steps; never a bench value)")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.impl != "ours":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
 
@@ -335,12 +479,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     from lctgan import _lib
-    if os.environ.get("LCT_MMA_TUNE"):
-        a, b = os.environ["LCT_MMA_TUNE"].split(",")
-        _lib.call_ret("lct_conv_mma_tune", int(a), int(b))
     from lctgan.parallel import FlatGradAllReduce, broadcast_parameters
-    from lctgan.training import GraphedTrainStep, StepArgs, build_models, train_step
-    from oracle import lct_oracle as O
+    from lctgan.training import (GraphedTrainStep, StepArgs, build_models, restore_state, snapshot_state,
+                                 synthetic_batch, train_step)
 
     use_graph = not args.no_graph
     enh, mpd, msd, tf, mr, g_opt, d_opt = build_models(dev, gan_seed=42, capturable=use_graph,
@@ -350,14 +491,14 @@ def main():
     sync_d = FlatGradAllReduce(list(mpd.parameters()) + list(msd.parameters())) if world > 1 else None
     sync_g = FlatGradAllReduce(list(enh.parameters())) if world > 1 else None
     sargs = StepArgs(gan_loss=args.gan_loss, reuse_enhancer_forward=not args.no_reuse,
-                     fake_streams=bool(int(os.environ.get("LCT_FAKE_STREAMS", "0"))),
-                     batch_d_step=not args.no_reuse and bool(int(os.environ.get("LCT_BATCH_D", "1"))),
+                     batch_d_step=not args.no_reuse and not args.no_batch_d,
                      skip_dead_d_grads=args.skip_dead_d_grads, defer_dead_d_grads=not args.no_defer_dead_d_grads)
 
-    noisy_h, clean_h = O.synthetic_batch(BATCH, SEGMENT, seed=1234 + rank)      # synthetic data generator only
+    noisy_h, clean_h = synthetic_batch(BATCH, SEGMENT, seed=1234 + rank)
     noisy_h, clean_h = noisy_h.pin_memory(), clean_h.pin_memory()
     noisy_d, clean_d = noisy_h.to(dev), clean_h.to(dev)
     res_h = torch.empty(6, dtype=torch.float32).pin_memory()
+    snap = snapshot_state([enh, mpd, msd], [g_opt, d_opt])
 
     graphed = None
     if use_graph:
@@ -386,6 +527,12 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             return t.item()
         return ms
+
+    # ---- parity gate: rewind to the seeded initial state (in place: the captured graph keeps its addresses) and compare
+    # the first step of exactly this configuration with the reference's own log at this shape
+    restore_state([enh, mpd, msd], [g_opt, d_opt], snap)
+    first = {k: float(v) for k, v in step(noisy_d, clean_d).items()}
+    parity = parity_check(first, args.gan_loss, world, tol_rel=5e-3) if rank == 0 else None
 
     for _ in range(args.warmup):
         out = step(noisy_d, clean_d)
@@ -439,32 +586,53 @@ def main():
     roof, roof_t = (None, None) if args.no_roofline else measure_roofline(dev, peaks)
     rtf = None if args.no_roofline else measure_enhance_rtf(dev)
     roof_fe = None if args.no_roofline else measure_frontend_rooflines(dev, peaks)
-    cpu = None
+    cpu = torch_cuda = variants = None
     if world == 1 and not args.no_cpu_baseline:
-        sps, ms, b, cores = cpu_reference_steps(steps=1, warmup=1, budget_s=30.0)
-        cpu = {"value": sps, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"1 timed D+G step of {b} x 2 s segments after 1 warm-up step (oracle port of train.py:165-249, "
-                         f"torch CPU ops, {cores} threads)", "ms_per_step": ms}
+        r = _sub_bench(["--impl", "reference", "--steps", "2", "--warmup", "1", "--gan_loss", args.gan_loss])
+        cpu = dict(r.get("cpu_baseline", {}), ms_per_step=r.get("ms_per_step")) if "error" not in r else r
+        if rtf is not None:
+            rr = _sub_bench(["--impl", "reference", "--what", "rtf"])
+            rtf["cpu_reference"] = rr.get("rtf", rr)
+            rtf["cpu_reference_cores"] = rr.get("cores")
+    if world == 1 and not args.no_comparators:
+        # the practical bar: the same algorithm on stock torch CUDA operators on this very GPU
+        torch.cuda.empty_cache()
+        torch_cuda = {}
+        for key, extra in (("fp32", []), ("tf32", ["--allow-tf32"])):
+            r = _sub_bench(["--impl", "reference-cuda", "--steps", "10", "--warmup", "3", "--gan_loss", args.gan_loss] + extra)
+            torch_cuda[key] = {k: r.get(k) for k in ("value", "unit", "ms_per_step", "device", "losses_first_step")} \
+                if "error" not in r else r
+            if "value" in r and r["value"]:
+                torch_cuda[key]["ours_over_this"] = value / r["value"]
+        variants = {m: measure_variant(dev, m) for m in ("api_eager", "fp32")}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 (tcgen05 dense contraction) / tf32 (grouped discriminator convolutions) / 3xtf32 (generator GEMMs and convolutions) tensor-core operands with fp32 accumulation; f32 elsewhere",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "gan_loss": args.gan_loss, "parallelism": f"dp{world}", "cuda_graph": graphed is not None, "reuse_enhancer_forward": sargs.reuse_enhancer_forward, "batch_d_step": sargs.batch_d_step, "skip_dead_d_grads": sargs.skip_dead_d_grads, "defer_dead_d_grads": sargs.defer_dead_d_grads, "fused_adamw": not args.torch_optim,
-                   "l2": "no explicit flush: one step streams > 2 GB of activations (>> 126 MB L2)"},
+        "config": _config(args.gan_loss, world),
+        "schedule": {"cuda_graph": graphed is not None, "reuse_enhancer_forward": sargs.reuse_enhancer_forward,
+                     "batch_d_step": sargs.batch_d_step, "skip_dead_d_grads": sargs.skip_dead_d_grads,
+                     "defer_dead_d_grads": sargs.defer_dead_d_grads, "fused_adamw": not args.torch_optim},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(noisy_h.numel() * 4 * 2), "d2h_bytes_per_step": int(res_h.numel() * 4)},
         "gpu_launches": launches,
+        "parity_check": parity,
         "roofline": roof,
         "roofline_tensor": roof_t,
         "roofline_frontend": roof_fe,
         "enhance_rtf": rtf,
         "cpu_baseline": cpu,
+        "torch_cuda_baseline": torch_cuda,
+        "api_eager": variants["api_eager"] if variants else None,
+        "fp32_mode": variants["fp32"] if variants else None,
         "losses_last_step": losses,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if parity and parity.get("checked") and not parity["ok"]:
+        raise SystemExit(f"parity check failed: {parity['mismatch']}")
 
 
 if __name__ == "__main__":

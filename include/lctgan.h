@@ -115,7 +115,6 @@ LCT_API int lct_conv1d_wgrad(const float* x, const float* dy, float* dw, float* 
 /* The same grouped convolutions on the tensor cores: TF32 mma.sync implicit GEMM, fp32 accumulation, persistent CTAs with
  * cp.async double-buffered input windows (conv_mma.cu).  Same arguments as lct_conv1d_*; lct_conv_mma_supported says
  * whether a layer shape is covered (groups with <= 16 in / <= 32 out channels, stride 1/3/4, Cin/G * K <= 168). */
-LCT_API int lct_conv_mma_tune(int ctas_per_sm, int force_mtw);   /* tuning: CTAs per SM of the persistent grids (default 3); force 2 or 4 m-tiles per warp (0 = auto) */
 LCT_API int lct_conv_mma_supported(int64_t Cin, int64_t Cout, int64_t G, int64_t K, int64_t S, int64_t P);
 LCT_API int lct_conv_mma_image_geometry(int64_t Cin, int64_t Cout, int64_t G, int64_t K, int64_t S, int mode, int64_t* out);   /* out (HOST) = {KKpad, NS} of the staged weight image; mode 0 fwd, 1 dgrad */
 LCT_API int lct_conv_mma_fwd(const float* x, const float* w, const float* wimg, const float* bias, float* y, int64_t B, int64_t Cin, int64_t Cout, int64_t G, int64_t K, int64_t S, int64_t pad, int64_t Lin, int64_t P, int act, float slope, cudaStream_t stream);
@@ -131,9 +130,7 @@ LCT_API int lct_conv_post_dgrad(const float* dy, const float* w, float* dx, cons
 /* The dense layer MSD convs.5 (Conv1d 1024->1024, k=5, s=1; discriminators.py:166-196) on tcgen05 tensor cores:
  * bf16 operands staged once per call, fp32 accumulation in TMEM, TMA-fed implicit GEMM (no im2col).
  * lct_dense_supported: 1 if (Cin, Cout multiples of 128, odd K <= 8) and the driver exposes cuTensorMapEncodeTiled. */
-LCT_API int lct_dense_tile_n(int bn);   /* conv-form output tile width: 0 auto (default), 64, 128 */
 LCT_API int lct_dense_supported(int64_t Cin, int64_t Cout, int64_t K);
-LCT_API int lct_dense_debug(int stage);   /* bring-up aid: 0 = normal; 1..3 run only the first stages of the kernel */
 LCT_API int lct_stage_nlc_bf16(const float* x, void* out, int64_t B, int64_t C, int64_t L, int64_t pad, cudaStream_t stream);   /* [B,C,L] f32 -> [B,L+2pad,C] bf16, zero rows between batches */
 LCT_API int lct_stage_ncl_bf16(const float* x, void* out, float* rowsum, int64_t B, int64_t C, int64_t L, int64_t Lp, int64_t shift, int64_t pitch, int64_t copies, cudaStream_t stream);   /* [B,C,L] f32 -> [copies,C,pitch] bf16, out[k][c][b*Lp+shift-k+l]; rowsum[C] += sums (bias grad) */
 LCT_API int lct_stage_dense_weights(const float* w, void* wt, void* wd, int64_t Co, int64_t Ci, int64_t K, cudaStream_t stream);   /* [Co,Ci,K] f32 -> wt [K,Co,Ci], wd [K,Ci,Co] taps flipped (bf16) */
@@ -200,8 +197,15 @@ LCT_API int lct_mt_max_segments(void);
 /* Fused multi-tensor AdamW (the optimiser train.py:601-610 builds): p/g/m/v are HOST arrays of device
  * pointers (<= lct_mt_adamw_max_segments() tensors per launch), n HOST element counts, step a device float that already
  * holds this update's step number (lct_add_scalar increments it on the stream: CUDA-graph friendly). */
-LCT_API int lct_mt_adamw(void* const* p, const void* const* g, void* const* m, void* const* v, const int64_t* n, int64_t nseg, const float* step, float lr, float beta1, float beta2, float eps, float weight_decay, cudaStream_t stream);
+LCT_API int lct_mt_adamw(void* const* p, const void* const* g, void* const* m, void* const* v, const int64_t* n, int64_t nseg, const float* step, float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale, cudaStream_t stream);
 LCT_API int lct_mt_adamw_max_segments(void);
 LCT_API int lct_add_scalar(float* x, float v, cudaStream_t stream);
+/* torch.nn.utils.clip_grad_norm_ (reference train.py:246-248) in place over <= lct_mt_max_segments() gradient tensors:
+ * total = pre * sqrt(sumsq[0]); g *= pre * min(1, max_norm / (total + 1e-6)).  sumsq: device float = sum of squares of
+ * ALL clipped gradients (lct_mt_reduce op 0); pre folds the 1/world_size of a data-parallel SUM; norm_out optional. */
+LCT_API int lct_mt_clip(void* const* g, const int64_t* n, int64_t nseg, const float* sumsq, float max_norm, float pre, float* norm_out, cudaStream_t stream);
+/* cudaMemsetAsync(p, 0, bytes) on `stream` (a memset node in a captured graph; no kernel).  Replaces the per-tensor
+ * zero-fill kernels of gradient accumulators: one buffer per layer stack, cleared once. */
+LCT_API int lct_memset_zero(void* p, int64_t bytes, cudaStream_t stream);
 
 #endif /* LCTGAN_H_ */

@@ -13,12 +13,14 @@
 
 // every kernel launch in this library is followed by this macro; it also feeds the launch
 // counter behind lct_kernel_launches() (bench.py reports it as gpu_launches).
-extern int g_lct_kernel_launches;
-#define LCT_RETURN_IF_LAUNCH_FAILED()                 \
-    do {                                              \
-        cudaError_t _e = cudaGetLastError();          \
-        if (_e != cudaSuccess) return (int)_e;        \
-        ++g_lct_kernel_launches;                      \
+// (launches come from the main thread and from autograd's backward threads: relaxed atomic)
+#include <atomic>
+extern std::atomic<int> g_lct_kernel_launches;
+#define LCT_RETURN_IF_LAUNCH_FAILED()                                        \
+    do {                                                                     \
+        cudaError_t _e = cudaGetLastError();                                 \
+        if (_e != cudaSuccess) return (int)_e;                               \
+        g_lct_kernel_launches.fetch_add(1, std::memory_order_relaxed);       \
     } while (0)
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -671,13 +671,6 @@ bool shape_ok(int64_t B, int64_t Cin, int64_t Cout, int64_t G, int64_t K, int64_
 
 }  // namespace
 
-// tuning knobs (bring-up / experiments): resident CTAs per SM targeted by the persistent grids, forced m-tiles per warp
-LCT_API int lct_conv_mma_tune(int ctas_per_sm, int force_mtw) {
-    if (ctas_per_sm > 0) g_ctas_per_sm = ctas_per_sm;
-    g_force_mtw = force_mtw;
-    return 0;
-}
-
 // geometry of the staged weight images: mode 0 forward ([Cin/G*K -> pad 8] x NS), mode 1 data gradient
 // ([Cout/G*ceil(K/S) -> pad 8] x NS); out[0] = KKpad, out[1] = NS  (HOST pointer)
 LCT_API int lct_conv_mma_image_geometry(int64_t Cin, int64_t Cout, int64_t G, int64_t K, int64_t S, int mode,

@@ -119,7 +119,6 @@ struct DenseParams {
     float* out;
     // EPI_WGRAD: out is dW [M_total, N_total, K]; tap = blockIdx.z
     int Ntot, Ktaps;
-    int debug;   // bring-up bisection (lct_dense_debug): 1 alloc only, 2 + TMA ring, 3 + MMA, 0 everything
 };
 
 template <int BN, int STAGES, int EPI>
@@ -158,9 +157,7 @@ dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (p.debug == 1) {
-        // allocation / barrier setup only
-    } else if (warp == 0 && lane == 0) {
+    if (warp == 0 && lane == 0) {
         // ===== TMA producer =====
         for (int kb = 0; kb < p.nkb; ++kb) {
             const int s = kb % STAGES;
@@ -180,10 +177,6 @@ dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             const uint32_t ph = (kb / STAGES) & 1;
             mbar_wait(&full[s], ph);
             tc_fence_after();
-            if (p.debug == 2) {   // consume without the tensor core
-                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[s])) : "memory");
-                continue;
-            }
             const uint32_t sa = smem_u32(tiles + (size_t)s * STAGE_BYTES);
             const uint32_t sb = sa + A_BYTES;
 #pragma unroll
@@ -194,15 +187,15 @@ dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
             umma_commit(&empty[s]);          // arrives once these MMAs have consumed the smem slot
         }
-        if (p.debug != 2) umma_commit(tmem_full);              // accumulator complete
-    } else if (warp >= 4 && (p.debug == 0 || p.debug == 3)) {
+        umma_commit(tmem_full);              // accumulator complete
+    } else if (warp >= 4) {
         // ===== epilogue: TMEM lane = tile row; warp (w % 4) owns lanes [32 (w%4), +32) =====
         mbar_wait(tmem_full, 0);
         tc_fence_after();
         const int q = warp & 3;
         const int row = m0 + q * 32 + lane;
 #pragma unroll 1
-        for (int c0 = 0; c0 < (p.debug == 3 ? 0 : BN); c0 += 32) {
+        for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t v[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
             if (EPI == EPI_CONV) {
@@ -390,14 +383,9 @@ int make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uin
     return r == CUDA_SUCCESS ? 0 : LCT_EINVAL;
 }
 
-int g_dense_debug = 0;
-int g_dense_bn = 0;      // output-tile width of the conv form: 0 auto, 64, 128
-// weight gradient with all taps in one CTA (default); LCT_DENSE_WGRAD_TAPS=0 selects the one-CTA-per-tap form (A/B tests)
-int g_dense_wgrad_taps = [] { const char* e = getenv("LCT_DENSE_WGRAD_TAPS"); return e ? atoi(e) : 1; }();
 
 template <int BN, int STAGES, int EPI>
 int launch_dense(const CUtensorMap& a, const CUtensorMap& b, DenseParams& p, dim3 grid, cudaStream_t st) {
-    p.debug = g_dense_debug;
     constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 + 256;
     cudaError_t e = cudaFuncSetAttribute(dense_kernel<BN, STAGES, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
@@ -474,18 +462,6 @@ __global__ void stage_weights_kernel(const float* __restrict__ w, __nv_bfloat16*
 
 }  // namespace
 
-LCT_API int lct_dense_debug(int stage) {
-    g_dense_debug = stage;
-    return 0;
-}
-
-// conv-form tile width: 0 = auto (default), 64 or 128 (A/B measurements)
-LCT_API int lct_dense_tile_n(int bn) {
-    if (bn != 0 && bn != 64 && bn != 128) return LCT_EINVAL;
-    g_dense_bn = bn;
-    return 0;
-}
-
 LCT_API int lct_dense_supported(int64_t Cin, int64_t Cout, int64_t K) {
     return (Cin % 128 == 0 && Cout % 128 == 0 && K >= 1 && K <= 8 && (K & 1) && get_encode() != nullptr) ? 1 : 0;
 }
@@ -536,8 +512,7 @@ LCT_API int lct_dense_conv(const void* a, const void* w, const float* bias, cons
     // 128 x 128 tiles move 16 KB of operands per 128 x 64 x 64 MACs instead of 24 KB (the layer is bound by the
     // aggregate L2 -> SM throughput, not by the tensor pipe); 128 x 64 tiles when that would leave SMs without a tile
     const int64_t mt = ceil_div64(R, BM);
-    int bn = g_dense_bn;
-    if (!bn) bn = (mt * (Cn / 128) >= 100) ? 128 : 64;
+    const int bn = (mt * (Cn / 128) >= 100) ? 128 : 64;
     rc = make_map(&mb, w, (uint64_t)(K * Cn), (uint64_t)Ca, (uint64_t)Ca, (uint32_t)bn);
     if (rc) return rc;
     DenseParams p = {};
@@ -562,7 +537,7 @@ LCT_API int lct_dense_wgrad(const void* dyq, const void* xq, float* dw, int64_t 
     p.nkb = (int)ceil_div64(pitch, BK); p.kdiv = p.nkb;
     p.a0 = 0; p.a_step1 = 0; p.b0 = 0; p.b_step1 = 0; p.b_tap_rows = (int)Ci;
     p.out = dw; p.Ntot = (int)Ci; p.Ktaps = (int)K;
-    if (K == 5 && g_dense_wgrad_taps && ((uintptr_t)dw & 15) == 0) {
+    if (K == 5 && ((uintptr_t)dw & 15) == 0) {
         // all 5 taps per CTA (see dense_wgrad_taps_kernel)
         rc = make_map(&mb, xq, (uint64_t)(K * Ci), (uint64_t)pitch, (uint64_t)pitch, 64);
         if (rc) return rc;

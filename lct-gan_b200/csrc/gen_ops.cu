@@ -487,45 +487,56 @@ __device__ __forceinline__ void axpy16(float a, const float2 (&x)[kHd / 2], floa
     for (int i = 0; i < kHd / 2; ++i) y[i] = __ffma2_rn(a2, x[i], y[i]);
 }   // block = sequence length rounded up to a warp (one query/key per thread)
 
+// One query per thread (blockIdx.z selects the block of queries); keys / values stream through shared memory in chunks
+// of `chunk` rows - the online softmax does not care where a chunk ends - so the sequence length is unbounded
+// (infer.py feeds whole utterances: L = frames + 3 in the time block).
 __global__ void __launch_bounds__(kAttnMaxThreads) attn_fwd_kernel(const float* __restrict__ qkv,
                                                                 float* __restrict__ out, float* __restrict__ lse,
-                                                                SeqGeom geo, int H, float scale) {
+                                                                SeqGeom geo, int H, float scale, int chunk) {
     extern __shared__ __align__(16) float sm[];
     const int L = geo.L, E = H * kHd;
-    float* Ks = sm;                 // [L][16]
-    float* Vs = sm + (size_t)L * kHd;
+    float* Ks = sm;                 // [chunk][16]
+    float* Vs = sm + (size_t)chunk * kHd;
     const int seq = blockIdx.x, h = blockIdx.y;
     const int64_t row0 = seq_row0(geo, seq);
-    for (int idx = threadIdx.x; idx < L * kHd; idx += (int)blockDim.x) {
-        int t = idx / kHd, d = idx - t * kHd;
-        const float* r = qkv + (row0 + (int64_t)t * geo.step_stride) * 3 * E;
-        Ks[idx] = r[E + h * kHd + d];
-        Vs[idx] = r[2 * E + h * kHd + d];
+    const int i = blockIdx.z * (int)blockDim.x + (int)threadIdx.x;
+    const bool valid = i < L;
+    const int64_t row = row0 + (int64_t)(valid ? i : 0) * geo.step_stride;
+    float2 q[kHd / 2], acc[kHd / 2];
+#pragma unroll
+    for (int d = 0; d < kHd / 2; ++d) {
+        q[d] = make_float2(qkv[row * 3 * E + h * kHd + 2 * d] * scale, qkv[row * 3 * E + h * kHd + 2 * d + 1] * scale);
+        acc[d] = make_float2(0.f, 0.f);
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < L; i += (int)blockDim.x) {
-        const int64_t row = row0 + (int64_t)i * geo.step_stride;
-        float2 q[kHd / 2], acc[kHd / 2];
-#pragma unroll
-        for (int d = 0; d < kHd / 2; ++d) {
-            q[d] = make_float2(qkv[row * 3 * E + h * kHd + 2 * d] * scale, qkv[row * 3 * E + h * kHd + 2 * d + 1] * scale);
-            acc[d] = make_float2(0.f, 0.f);
+    float m = -INFINITY, l = 0.f;
+    for (int c0 = 0; c0 < L; c0 += chunk) {
+        const int n = min(chunk, L - c0);
+        if (c0) __syncthreads();                       // everyone is done with the previous chunk
+        for (int idx = threadIdx.x; idx < n * kHd; idx += (int)blockDim.x) {
+            int t = idx / kHd, d = idx - t * kHd;
+            const float* r = qkv + (row0 + (int64_t)(c0 + t) * geo.step_stride) * 3 * E;
+            Ks[idx] = r[E + h * kHd + d];
+            Vs[idx] = r[2 * E + h * kHd + d];
         }
-        float m = -INFINITY, l = 0.f;
-        for (int t = 0; t < L; ++t) {
-            float2 k2[kHd / 2], v2[kHd / 2];
-            load_row2(Ks + t * kHd, k2);
-            const float s = dot16(q, k2);
-            const float mn = fmaxf(m, s);
-            const float corr = __expf(m - mn);
-            const float pr = __expf(s - mn);
-            l = l * corr + pr;
-            load_row2(Vs + t * kHd, v2);
-            const float2 c2 = make_float2(corr, corr), p2 = make_float2(pr, pr);
+        __syncthreads();
+        if (valid) {
+            for (int t = 0; t < n; ++t) {
+                float2 k2[kHd / 2], v2[kHd / 2];
+                load_row2(Ks + t * kHd, k2);
+                const float s = dot16(q, k2);
+                const float mn = fmaxf(m, s);
+                const float corr = __expf(m - mn);
+                const float pr = __expf(s - mn);
+                l = l * corr + pr;
+                load_row2(Vs + t * kHd, v2);
+                const float2 c2 = make_float2(corr, corr), p2 = make_float2(pr, pr);
 #pragma unroll
-            for (int d = 0; d < kHd / 2; ++d) acc[d] = __ffma2_rn(p2, v2[d], __fmul2_rn(acc[d], c2));
-            m = mn;
+                for (int d = 0; d < kHd / 2; ++d) acc[d] = __ffma2_rn(p2, v2[d], __fmul2_rn(acc[d], c2));
+                m = mn;
+            }
         }
+    }
+    if (valid) {
         const float inv = 1.f / l;
 #pragma unroll
         for (int d = 0; d < kHd / 2; ++d) {
@@ -783,14 +794,17 @@ LCT_API int lct_attn_fwd(const float* qkv, float* out, float* lse, int64_t heads
     if (!qkv || !out || !lse || heads <= 0 || heads >= 65536 ||
         !geom_ok(g, nseq, L, inner, outer_stride, inner_stride, step_stride))
         return LCT_EINVAL;
-    size_t smem = (size_t)2 * L * kHd * sizeof(float);
-    if (smem > 200 * 1024) return LCT_EUNSUPPORTED;
+    // keys / values are streamed through shared memory 1024 rows (128 KB) at a time: any L
+    const int chunk = (int)(L < 1024 ? L : 1024);
+    size_t smem = (size_t)2 * chunk * kHd * sizeof(float);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
-    dim3 grid((unsigned)nseq, (unsigned)heads);
-    attn_fwd_kernel<<<grid, attn_threads(L), smem, st>>>(qkv, out, lse, g, (int)heads, 1.f / sqrtf((float)kHd));
+    const int threads = attn_threads(L);
+    dim3 grid((unsigned)nseq, (unsigned)heads, (unsigned)ceil_div64(L, threads));
+    if (grid.z >= 65536) return LCT_EUNSUPPORTED;
+    attn_fwd_kernel<<<grid, threads, smem, st>>>(qkv, out, lse, g, (int)heads, 1.f / sqrtf((float)kHd), chunk);
     LCT_RETURN_IF_LAUNCH_FAILED();
     return 0;
 }

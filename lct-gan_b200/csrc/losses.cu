@@ -170,7 +170,8 @@ struct AdamSegs {
 };
 
 __global__ void __launch_bounds__(kThreads) mt_adamw_kernel(const AdamSegs S, const float* __restrict__ step_ptr,
-                                                            float lr, float b1, float b2, float eps, float wd) {
+                                                            float lr, float b1, float b2, float eps, float wd,
+                                                            float gmul) {
     int lo = 0, hi = S.nseg - 1;
     while (lo < hi) {
         int mid = (lo + hi + 1) >> 1;
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(kThreads) mt_adamw_kernel(const AdamSegs S, co
     float* __restrict__ mm = S.m[seg];
     float* __restrict__ vv = S.v[seg];
     for (int64_t i = start + threadIdx.x; i < end; i += kThreads) {
-        const float g = gg[i];
+        const float g = gg[i] * gmul;
         float p = pp[i] * decay;
         float m = mm[i];
         m = m + (g - m) * (1.f - b1);
@@ -204,6 +205,22 @@ __global__ void __launch_bounds__(kThreads) mt_adamw_kernel(const AdamSegs S, co
 
 __global__ void add_scalar_kernel(float* x, float v) { x[0] += v; }
 
+// torch.nn.utils.clip_grad_norm_ (train.py:246-248) over up to kMaxSeg gradient tensors, in place:
+//   total = pre * sqrt(sumsq),  g <- g * pre * min(1, max_norm / (total + 1e-6))
+// `sumsq` = sum of squares of all gradients (lct_mt_reduce, op 0, k0 = 0); `pre` folds the 1 / world_size of a
+// data-parallel SUM all-reduce into the same pass.  norm_out (optional) receives `total`.
+__global__ void __launch_bounds__(kThreads) mt_clip_kernel(const Segs S, const float* __restrict__ sumsq,
+                                                           float max_norm, float pre, float* __restrict__ norm_out) {
+    const int seg = find_seg(S, blockIdx.x);
+    const int64_t start = (int64_t)(blockIdx.x - S.chunk0[seg]) * kChunk;
+    const int64_t end = min(start + (int64_t)kChunk, S.n[seg]);
+    const float total = sqrtf(sumsq[0]) * pre;
+    const float coef = fminf(1.f, max_norm / (total + 1e-6f)) * pre;
+    float* __restrict__ g = S.g[seg];
+    for (int64_t i = start + threadIdx.x; i < end; i += kThreads) g[i] *= coef;
+    if (norm_out && blockIdx.x == 0 && threadIdx.x == 0) norm_out[0] = total;
+}
+
 }  // namespace
 
 // x[0] += v  (device-side step counter of the fused optimiser, CUDA-graph friendly)
@@ -216,10 +233,11 @@ LCT_API int lct_add_scalar(float* x, float v, cudaStream_t st) {
 
 // One AdamW update (decoupled weight decay, bias correction, torch.optim.AdamW defaults' formulas) of up to 48 tensors
 // per launch.  p/g/m/v: HOST arrays of device pointers, n: HOST array of element counts; step: device float holding
-// the (already incremented) step number.
+// the (already incremented) step number; grad_scale multiplies every gradient as it is read (1 / world size when the
+// gradients hold the SUM of a data-parallel all-reduce; 1 otherwise).
 LCT_API int lct_mt_adamw(void* const* p, const void* const* g, void* const* m, void* const* v, const int64_t* n,
                          int64_t nseg, const float* step, float lr, float beta1, float beta2, float eps,
-                         float weight_decay, cudaStream_t st) {
+                         float weight_decay, float grad_scale, cudaStream_t st) {
     if (!p || !g || !m || !v || !n || !step || nseg <= 0 || nseg > kMaxAdam) return LCT_EINVAL;
     AdamSegs S;
     int chunks = 0;
@@ -232,7 +250,7 @@ LCT_API int lct_mt_adamw(void* const* p, const void* const* g, void* const* m, v
     }
     S.chunk0[nseg] = chunks;
     S.nseg = (int)nseg;
-    mt_adamw_kernel<<<chunks, kThreads, 0, st>>>(S, step, lr, beta1, beta2, eps, weight_decay);
+    mt_adamw_kernel<<<chunks, kThreads, 0, st>>>(S, step, lr, beta1, beta2, eps, weight_decay, grad_scale);
     LCT_RETURN_IF_LAUNCH_FAILED();
     return 0;
 }
@@ -277,3 +295,24 @@ LCT_API int lct_mt_copy(const void* const* src, void* const* dst, const int64_t*
 }
 
 LCT_API int lct_mt_max_segments(void) { return kMaxSeg; }
+
+// In-place gradient clipping by global norm (see mt_clip_kernel).  g: HOST array of device pointers; sumsq: device
+// float holding the sum of squares over ALL gradients being clipped (several launches may share it); norm_out optional.
+LCT_API int lct_mt_clip(void* const* g, const int64_t* n, int64_t nseg, const float* sumsq, float max_norm, float pre,
+                        float* norm_out, cudaStream_t st) {
+    if (!g || !n || !sumsq || nseg <= 0 || nseg > kMaxSeg || !(max_norm > 0.f) || !(pre > 0.f)) return LCT_EINVAL;
+    Segs S;
+    int chunks = 0;
+    for (int i = 0; i < nseg; ++i) {
+        if (!g[i] || n[i] <= 0) return LCT_EINVAL;
+        S.g[i] = (float*)g[i];
+        S.n[i] = n[i];
+        S.chunk0[i] = chunks;
+        chunks += (int)ceil_div64(n[i], kChunk);
+    }
+    S.chunk0[nseg] = chunks;
+    S.nseg = (int)nseg;
+    mt_clip_kernel<<<chunks, kThreads, 0, st>>>(S, sumsq, max_norm, pre, norm_out);
+    LCT_RETURN_IF_LAUNCH_FAILED();
+    return 0;
+}

@@ -54,13 +54,20 @@ class ComplexSTFT(nn.Module):
     def _full_window(self, device) -> torch.Tensor:
         """The window the transform multiplies by: fp32, on `device`, centred-zero-padded to n_fft."""
         w = self.window
-        if w.device != device or w.dtype != torch.float32:
-            w = w.to(device=device, dtype=torch.float32)
         n, wl = self.cfg.n_fft, self.cfg.win_length
-        if wl < n:
-            left = (n - wl) // 2
-            w = torch.nn.functional.pad(w, (left, n - wl - left))
-        return w
+        if w.device == device and w.dtype == torch.float32 and wl >= n:
+            return w
+        # derived window (other device / dtype, or centre-padded): memoised per (buffer address, version, device) so
+        # that repeated calls hand the SAME tensor to the kernels (and to the envelope cache keyed on it)
+        key = (w.data_ptr(), w._version, str(device))
+        memo = self.__dict__.setdefault("_derived_window", {})
+        if memo.get("key") != key:
+            d = w.to(device=device, dtype=torch.float32)
+            if wl < n:
+                left = (n - wl) // 2
+                d = torch.nn.functional.pad(d, (left, n - wl - left))
+            memo.update(key=key, src=w, win=d)
+        return memo["win"]
 
     def forward(self, waveform: torch.Tensor) -> torch.Tensor:
         if waveform.dim() != 2:

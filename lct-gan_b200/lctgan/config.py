@@ -32,8 +32,7 @@ concurrent_discriminators = True
 #: the step waits for - the generator (priority_generator) and the sub-discriminators' forward / data-gradient chains
 #: (chain_priority) - outrank the helper streams that carry weight-gradient kernels (priority 0), so a wide
 #: weight-gradient grid cannot park its CTAs in front of a critical-path kernel.
-import os as _os
-chain_priority = 0 if _os.environ.get("LCT_NO_PRIORITY") else -1
+chain_priority = -1
 priority_generator = -2
 
 _STREAMS = {}

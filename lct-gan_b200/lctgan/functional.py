@@ -216,6 +216,30 @@ class MTLossFn(torch.autograd.Function):
         return (None, None, None, None, None, *ga, *gb)
 
 
+class WeightedSumFn(torch.autograd.Function):
+    """sum_i w_i * s_i over scalar tensors in one launch (and one launch for all the gradients): the loss combinations
+    ``lr + lf`` (losses.py:135) and ``mr + l_mask * m + l_adv * (adv + l_fm * fm)`` (train.py:240-243) without torch's
+    one-kernel-per-scalar-operator chain."""
+
+    @staticmethod
+    def forward(ctx, weights, *scalars):
+        _require_cuda(*scalars)
+        a = [t.reshape(1).contiguous() for t in scalars]
+        ctx.weights = [float(w) for w in weights]
+        ctx.save_for_backward(*a)
+        return ops.mt_reduce(a, None, ctx.weights, ops.OP_SUM).view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        a = list(ctx.saved_tensors)
+        grads = ops.mt_grad(a, None, ctx.weights, ops.OP_SUM, upstream=g.reshape(1).contiguous())
+        return (None, *[gr.view(()) if ctx.needs_input_grad[1 + i] else None for i, gr in enumerate(grads)])
+
+
+def weighted_sum(scalars: Sequence[torch.Tensor], weights: Sequence[float]) -> torch.Tensor:
+    return WeightedSumFn.apply(tuple(weights), *scalars)
+
+
 def mt_loss(op: int, a: Sequence[torch.Tensor], b: Optional[Sequence[torch.Tensor]], scales: Sequence[float],
             k0: float = 0.0, k1: float = 0.0) -> torch.Tensor:
     tensors = list(a) + (list(b) if b is not None else [])
@@ -234,7 +258,7 @@ class MRSTFTLossFn(torch.autograd.Function):
         y = y.contiguous()
         B, T = y_hat.shape
         nres = len(res_cfg)
-        acc = torch.zeros(nres, 2, 64, dtype=torch.float32, device=y_hat.device)   # 64 partial-sum slots per sum
+        acc = ops.zeros((nres, 2, 64), y_hat.device)   # 64 partial-sum slots per sum
         wsum = sum(w for (_, _, w) in res_cfg)
         k_total, k_mag, k_cplx = [], [], []
         for i, ((n_fft, hop, w), win) in enumerate(zip(res_cfg, windows)):

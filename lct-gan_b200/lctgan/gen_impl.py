@@ -13,7 +13,6 @@ through the sigmoid, so the last frames are exactly 0.5.
 """
 from __future__ import annotations
 
-import os
 from typing import Dict, List, Sequence, Tuple
 
 import torch
@@ -161,7 +160,7 @@ def _block_bwd(P, pre, dout, B, T, F, freq, S, GR, side=None, z=None):
     f32 = dict(dtype=torch.float32, device=dev)
     ks = _split_k(M)
     if z is None:
-        z = lambda *shape: torch.zeros(*shape, **f32)
+        z = lambda *shape: ops.zeros(shape, dev)
 
     # out = seq + lrelu(lin(lin_in))
     dmix = ops.act_bwd(s["mix"], dout, ACT_LRELU, SLOPE)
@@ -284,7 +283,7 @@ def generator_forward(P: Dict[str, torch.Tensor], mag: torch.Tensor, use_sigmoid
     return mask
 
 
-def generator_backward(P, mag, mask, gmask, use_sigmoid, S, need_mag_grad=False):
+def generator_backward(P, mag, mask, gmask, use_sigmoid, S, need_mag_grad=False, arena_out=None):
     if need_mag_grad:
         raise RuntimeError("LCTGenerator: gradient w.r.t. the input magnitude is not implemented "
                            "(the training step never needs it: the noisy spectrum is data)")
@@ -293,9 +292,11 @@ def generator_backward(P, mag, mask, gmask, use_sigmoid, S, need_mag_grad=False)
     GR: Dict[str, torch.Tensor] = {}
     dev = mag.device
     f32 = dict(dtype=torch.float32, device=dev)
-    # (one shared zero-filled arena for all accumulators was tried and measured 2 % slower: autograd cannot steal a
-    # gradient that is a view of a larger buffer and clones every one of the 130 of them instead)
-    z = lambda *shape: torch.zeros(*shape, **f32)
+    # every parameter-gradient accumulator of this backward is carved from ONE buffer cleared by one memset (round 1:
+    # ~90 separate torch.zeros fill kernels); the buffer is also what the fused gradient clip reduces over
+    z = ops.Arena(sum((p.numel() + 3) // 4 * 4 for p in P.values()) + 1024, dev)
+    if arena_out is not None:
+        arena_out.append(z.buf)
     enc, dec_in, dec_out = top["enc"], top["dec_in"], top["dec_out"]
     T3, F3 = top["T3"], top["F3"]
     M = B * T3 * F3
@@ -359,7 +360,7 @@ def _on_generator_stream(device, fn):
     """Run fn on the high-priority generator stream, forked from and joined to the caller's stream (the generator is a
     serial chain of small kernels: it must not queue behind the wide weight-gradient grids of the discriminators)."""
     from . import config
-    if not config.concurrent_discriminators or os.environ.get("LCT_NO_PRIORITY"):
+    if not config.concurrent_discriminators:
         return fn()
     cur = torch.cuda.current_stream(device)
     hp = config.generator_stream(device)
@@ -372,25 +373,37 @@ def _on_generator_stream(device, fn):
 
 class GeneratorFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, mag_phys, use_sigmoid, names, *params):
+    def forward(ctx, mag_phys, use_sigmoid, names, owner, keep_state, *params):
+        """owner: the LCTGenerator module (receives ``_grad_arena``, the flat buffer holding the gradients of the last
+        backward); keep_state: torch.is_grad_enabled() at the call site - ``ctx.needs_input_grad`` alone reflects
+        ``requires_grad`` even under no_grad (infer.py, the D step's enhancer pass), where keeping every activation
+        until forward returns would cost the training-size memory peak for nothing."""
         if not mag_phys.is_cuda:
             raise RuntimeError("LCTGenerator (lctgan) is CUDA only (sm_100a); there is no CPU fallback")
         P = dict(zip(names, params))
-        need = any(ctx.needs_input_grad[3:])
+        need = bool(keep_state) and any(ctx.needs_input_grad[5:])
         S = {} if need else None
         mask = _on_generator_stream(mag_phys.device, lambda: generator_forward(P, mag_phys.contiguous(), use_sigmoid, S))
         ctx.S = S
         ctx.names = names
+        ctx.owner = owner
         ctx.use_sigmoid = use_sigmoid
         ctx.save_for_backward(mag_phys, mask, *params)
         return mask
 
     @staticmethod
     def backward(ctx, gmask):
+        if ctx.S is None:
+            raise RuntimeError("LCTGenerator backward: the saved activations are gone - either the forward ran under "
+                               "no_grad, or this is a second backward through the same graph (retain_graph=True is not "
+                               "supported: the activations are released after the first backward)")
         mag_phys, mask, *params = ctx.saved_tensors
         P = dict(zip(ctx.names, params))
+        arena = []
         GR = _on_generator_stream(mag_phys.device, lambda: generator_backward(
-            P, mag_phys.contiguous(), mask, gmask, ctx.use_sigmoid, ctx.S, ctx.needs_input_grad[0]))
+            P, mag_phys.contiguous(), mask, gmask, ctx.use_sigmoid, ctx.S, ctx.needs_input_grad[0], arena))
         ctx.S = None
-        grads = [GR.get(n) if ctx.needs_input_grad[3 + i] else None for i, n in enumerate(ctx.names)]
-        return (None, None, None, *grads)
+        if ctx.owner is not None and arena:
+            ctx.owner._grad_arena = arena[0]
+        grads = [GR.get(n) if ctx.needs_input_grad[5 + i] else None for i, n in enumerate(ctx.names)]
+        return (None, None, None, None, None, *grads)

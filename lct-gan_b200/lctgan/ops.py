@@ -19,7 +19,33 @@ from ._lib import call, call_ret
 ACT_NONE, ACT_LRELU, ACT_RELU = 0, 1, 2
 
 _TW: Dict[Tuple[int, int], torch.Tensor] = {}
-_ENV: Dict[Tuple[int, int, int, int, int], torch.Tensor] = {}
+_ENV: Dict[tuple, list] = {}
+
+
+def zeros(shape, device) -> torch.Tensor:
+    """Zero-filled fp32 tensor: torch.empty + one cudaMemsetAsync on the current stream (a memset node in a captured
+    graph) instead of torch.zeros' fill kernel."""
+    t = torch.empty(shape, dtype=torch.float32, device=device)
+    if t.numel():
+        call("lct_memset_zero", t, t.numel() * 4)
+    return t
+
+
+class Arena:
+    """Bump allocator over ONE zero-filled buffer (one memset) for the many small gradient accumulators of a backward
+    pass; falls back to separate zeroed tensors when exhausted.  Views are 16-byte aligned."""
+
+    def __init__(self, numel: int, device):
+        self.buf = zeros((int(numel),), device)
+        self.off = 0
+
+    def __call__(self, *shape) -> torch.Tensor:
+        n = int(math.prod(shape))
+        if self.off + n > self.buf.numel():
+            return zeros(shape, self.buf.device)
+        v = self.buf[self.off:self.off + n].view(shape)
+        self.off += (n + 3) // 4 * 4
+        return v
 
 
 def _dev_index(t: torch.Tensor) -> int:
@@ -43,16 +69,30 @@ def twiddles(n_fft: int, like: torch.Tensor) -> torch.Tensor:
     return tw
 
 
+_ENV_MAX = 64
+
+
 def ola_envelope(window: torch.Tensor, n_fft: int, hop: int, n_frames: int) -> torch.Tensor:
-    """Overlap-added squared window; cached per (window storage, version, geometry)."""
-    key = (window.data_ptr(), window._version, n_fft, hop, n_frames)
-    env = _ENV.get(key)
-    if env is None:
-        if len(_ENV) > 64:
-            _ENV.clear()
-        env = torch.empty(n_fft + hop * (n_frames - 1), device=window.device, dtype=torch.float32)
-        call("lct_ola_envelope", window, env, n_fft, hop, n_frames)
-        _ENV[key] = env
+    """Overlap-added squared window (iSTFT normalisation), cached.
+
+    The key is (device, window storage address, window version, geometry) and the entry keeps a reference to the window
+    tensor itself, so the address cannot be recycled for another window while the entry lives: a key match implies the
+    same values.  Least-recently-used entries are dropped beyond 64 - except those created or used while a CUDA graph
+    was being captured: the captured graph holds their addresses, so they are pinned for the life of the process."""
+    key = (_dev_index(window), window.data_ptr(), window._version, n_fft, hop, n_frames)
+    capturing = window.is_cuda and torch.cuda.is_current_stream_capturing()
+    ent = _ENV.get(key)
+    if ent is not None:
+        _ENV[key] = _ENV.pop(key)                      # move to the most-recently-used end
+        if capturing:
+            ent[2] = True
+        return ent[1]
+    env = torch.empty(n_fft + hop * (n_frames - 1), device=window.device, dtype=torch.float32)
+    call("lct_ola_envelope", window, env, n_fft, hop, n_frames)
+    _ENV[key] = [window, env, capturing]
+    if len(_ENV) > _ENV_MAX:
+        for k in [k for k, e in _ENV.items() if not e[2]][:len(_ENV) - _ENV_MAX]:
+            del _ENV[k]
     return env
 
 
@@ -244,7 +284,7 @@ def _flat_views(shapes, device, zero=False):
     for n in sizes:
         offs.append(tot)
         tot += (n + 3) // 4 * 4            # keep every view 16-byte aligned
-    flat = (torch.zeros if zero else torch.empty)(tot, dtype=torch.float32, device=device)
+    flat = zeros((tot,), device) if zero else torch.empty(tot, dtype=torch.float32, device=device)
     return [flat[o:o + n].view(s) for o, n, s in zip(offs, sizes, shapes)]
 
 
@@ -333,9 +373,9 @@ def conv1d_wgrad(x, dy, w_shape, groups, stride, pad, want_bias=True, dw=None, d
     B, Cin, Lin, P = x.shape
     Cout, K = w_shape[0], w_shape[2]
     if dw is None:
-        dw = torch.zeros(w_shape, dtype=torch.float32, device=x.device)
+        dw = zeros(tuple(w_shape), x.device)
     if db is None and want_bias:
-        db = torch.zeros(Cout, dtype=torch.float32, device=x.device)
+        db = zeros((Cout,), x.device)
     if _is_post(Cout, K, groups, stride, pad):
         call("lct_conv_post_wgrad", x, dy, dw, db, B, Cin, Lin, P, K)
         return dw, db
@@ -419,7 +459,7 @@ def gconv_wgrad(S, Lg, w_shape, out=None):
     """`out`: optional pre-zeroed accumulator of shape w_shape."""
     B, Ts, Fs, Ca = S.shape
     _, Tl, Fl, Cc = Lg.shape
-    dW = out if out is not None else torch.zeros(w_shape, dtype=torch.float32, device=S.device)
+    dW = out if out is not None else zeros(tuple(w_shape), S.device)
     call("lct_gconv_wgrad", S, Lg, dW, B, Ts, Fs, Ca, Tl, Fl, Cc)
     return dW
 
@@ -480,7 +520,7 @@ def mt_reduce(a: Sequence[torch.Tensor], b: Optional[Sequence[torch.Tensor]], sc
     a = [_flat_ok(t) for t in a]
     b = [_flat_ok(t) for t in b] if b is not None else None
     if out is None:
-        out = torch.zeros(1, dtype=torch.float32, device=a[0].device)
+        out = zeros((1,), a[0].device)
     maxseg = call_ret("lct_mt_max_segments")
     for s in range(0, len(a), maxseg):
         aa = a[s:s + maxseg]

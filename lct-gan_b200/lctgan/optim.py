@@ -13,7 +13,38 @@ import ctypes
 import torch
 from torch.optim import Optimizer
 
+from . import ops
 from ._lib import call, call_ret
+
+
+def clip_grad_norm_(parameters, max_norm: float, arena=None, pre_scale: float = 1.0) -> torch.Tensor:
+    """torch.nn.utils.clip_grad_norm_ (L2, reference train.py:246-248) on the lctgan multi-tensor kernels: one
+    sum-of-squares reduction + one in-place scaling, ``g *= pre_scale * min(1, max_norm / (total + 1e-6))`` with
+    ``total = pre_scale * ||g||`` (pre_scale folds the 1 / world_size of a data-parallel SUM all-reduce).
+
+    `arena`: a flat buffer that holds every gradient and nothing else but zeros (LCTGenerator._grad_arena, written by
+    the generator's backward): the two launches then run over that one buffer instead of ~130 tensors.  Returns the
+    total norm (device tensor, no host sync)."""
+    params = [p for p in parameters if p.grad is not None]
+    if not params:
+        return torch.zeros(())
+    grads = [p.grad for p in params]
+    for g in grads:
+        if not g.is_cuda or g.dtype != torch.float32 or not g.is_contiguous():
+            raise RuntimeError("lctgan clip_grad_norm_: gradients must be contiguous CUDA float32 tensors")
+    if arena is not None:
+        lo, hi = arena.data_ptr(), arena.data_ptr() + arena.numel() * 4
+        if all(lo <= g.data_ptr() and g.data_ptr() + g.numel() * 4 <= hi for g in grads):
+            grads = [arena]
+    sumsq = ops.mt_reduce(grads, None, [1.0] * len(grads), ops.OP_SQ_CONST, k0=0.0)
+    norm = torch.empty(1, dtype=torch.float32, device=grads[0].device)
+    maxseg = call_ret("lct_mt_max_segments")
+    arr = lambda ts: (ctypes.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+    for s in range(0, len(grads), maxseg):
+        chunk = grads[s:s + maxseg]
+        n = (ctypes.c_int64 * len(chunk))(*[t.numel() for t in chunk])
+        call("lct_mt_clip", arr(chunk), n, len(chunk), sumsq, float(max_norm), float(pre_scale), norm)
+    return norm.view(())
 
 
 class FusedAdamW(Optimizer):
@@ -21,6 +52,9 @@ class FusedAdamW(Optimizer):
         if lr < 0.0 or eps < 0.0 or not (0.0 <= betas[0] < 1.0) or not (0.0 <= betas[1] < 1.0) or weight_decay < 0.0:
             raise ValueError("invalid AdamW hyper-parameter")
         super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay))
+        #: multiplies every gradient as it is read (1 / world_size when .grad holds the SUM of a data-parallel
+        #: all-reduce: lctgan.parallel sets it, so no separate division pass exists)
+        self.grad_scale = 1.0
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -35,7 +69,10 @@ class FusedAdamW(Optimizer):
                 continue
             step_t = group.get("_step")
             if step_t is None:
-                step_t = torch.zeros(1, dtype=torch.float32, device=ps[0].device)
+                # fresh optimiser: 0.  After load_state_dict of a torch.optim.AdamW / FusedAdamW checkpoint (train.py:
+                # 639-641) the per-parameter ``step`` entries carry the count: resume the bias correction from there
+                loaded = [float(self.state[p]["step"]) for p in ps if "step" in self.state.get(p, {})]
+                step_t = torch.full((1,), max(loaded) if loaded else 0.0, dtype=torch.float32, device=ps[0].device)
                 group["_step"] = step_t
             for p in ps:
                 if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
@@ -43,10 +80,10 @@ class FusedAdamW(Optimizer):
                 if p.grad.is_sparse:
                     raise RuntimeError("FusedAdamW does not support sparse gradients")
                 st = self.state[p]
-                if not st:
-                    st["step"] = step_t          # shared by the group (every parameter is stepped together)
-                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
-                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                if "exp_avg" not in st:
+                    st["exp_avg"] = ops.zeros(tuple(p.shape), p.device)
+                    st["exp_avg_sq"] = ops.zeros(tuple(p.shape), p.device)
+                st["step"] = step_t              # shared by the group (every parameter is stepped together)
             call("lct_add_scalar", step_t, 1.0)
             b1, b2 = group["betas"]
             for s in range(0, len(ps), maxseg):
@@ -56,5 +93,5 @@ class FusedAdamW(Optimizer):
                 n = (ctypes.c_int64 * len(chunk))(*[p.numel() for p in chunk])
                 call("lct_mt_adamw", arr(chunk), arr(grads), arr([self.state[p]["exp_avg"] for p in chunk]),
                      arr([self.state[p]["exp_avg_sq"] for p in chunk]), n, len(chunk), step_t, float(group["lr"]),
-                     float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]))
+                     float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]), float(self.grad_scale))
         return loss

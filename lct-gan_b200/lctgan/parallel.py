@@ -23,6 +23,8 @@ from . import ops
 class FlatGradAllReduce:
     def __init__(self, params: Iterable[torch.nn.Parameter], group=None):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("FlatGradAllReduce: no parameter requires grad")
         self.group = group
         n = sum(p.numel() for p in self.params)
         dev = self.params[0].device
@@ -46,7 +48,7 @@ class FlatGradAllReduce:
                 dsts.append(v)
         for v in missing:      # a parameter without gradient on this rank still takes part in the average
             v.zero_()
-        if p.is_cuda:
+        if self.flat.is_cuda:
             ops.mt_copy(srcs, dsts)
         else:                  # gloo / CPU path used by the world_size-2 host-logic tests
             for s, d in zip(srcs, dsts):
@@ -65,7 +67,7 @@ class FlatGradAllReduce:
                     back_src.pop()
                     back_dst.pop()
         if back_src:
-            if p.is_cuda:
+            if self.flat.is_cuda:
                 ops.mt_copy(back_src, back_dst)
             else:
                 for s, d in zip(back_src, back_dst):

@@ -13,7 +13,9 @@ import torch
 
 import losses as L
 from models.discriminators import run_discriminators
-from . import config
+from . import config, ops
+from . import functional as LF
+from .optim import clip_grad_norm_
 
 
 @dataclass
@@ -29,8 +31,6 @@ class StepArgs:
     #: With this switch one forward (with grad) serves both - bit-identical values, one forward less - and it runs
     #: on a side stream concurrently with the discriminators' forward on the clean batch (no data dependence).
     reuse_enhancer_forward: bool = False
-    #: (with reuse_enhancer_forward) run the D step's fake chains on streams 8..15 instead of sharing the real chains' streams
-    fake_streams: bool = False
     #: D step: push clean and enhanced through the discriminators as ONE batch of 2B (no BatchNorm / cross-sample op in
     #: the networks, SURVEY 8e, so logits and parameter gradients are identical to two passes): half the launches and
     #: no gradient-accumulation adds; costs the overlap of D(clean) with the enhancer forward.
@@ -63,8 +63,9 @@ def _phase_d(M, noisy, clean, args: StepArgs, st: dict) -> None:
         g_opt.zero_grad(set_to_none=True)
         st["enhanced"], st["mask_c"] = enhancer(noisy)
         st["irm_c"] = tf_features(noisy, clean)["irm_c"]
-        both = torch.cat([clean, st["enhanced"].detach()], dim=0)
         nb = clean.shape[0]
+        both = torch.empty(2 * nb, clean.shape[1], dtype=clean.dtype, device=clean.device)
+        ops.mt_copy([clean.contiguous(), st["enhanced"].detach()], [both[:nb], both[nb:]])
         (pl, _, sl, _), = run_discriminators(mpd, msd, [both])
         mpd_real, mpd_fake = [t[:nb] for t in pl], [t[nb:] for t in pl]
         msd_real, msd_fake = [t[:nb] for t in sl], [t[nb:] for t in sl]
@@ -81,8 +82,7 @@ def _phase_d(M, noisy, clean, args: StepArgs, st: dict) -> None:
         enhanced_for_d = st["enhanced"].detach()
         # (same 8 streams as the real pass: giving the fake chains their own streams was measured 30 % slower - the
         # autograd engine then has to synchronise the two streams at every shared parameter's AccumulateGrad)
-        (mpd_fake, _, msd_fake, _), = run_discriminators(mpd, msd, [enhanced_for_d],
-                                                         first_stream=8 if args.fake_streams else 0)
+        (mpd_fake, _, msd_fake, _), = run_discriminators(mpd, msd, [enhanced_for_d])
     else:
         st["irm_c"] = tf_features(noisy, clean)["irm_c"]
         with torch.no_grad():
@@ -124,7 +124,11 @@ def _phase_g(M, noisy, clean, args: StepArgs, st: dict) -> None:
             _, msd_real_f = msd(clean)
     adv_loss = L.generator_adv_loss(L._flatten_logits_lists(mpd_fake_g, msd_fake_g), args.gan_loss)
     fm_loss = L.feature_matching_loss(mpd_real_f + msd_real_f, mpd_fake_f + msd_fake_f)
-    g_loss = mr_loss + args.lambda_mask * m_loss + args.lambda_adv * (adv_loss + args.lambda_fm * fm_loss)
+    if noisy.is_cuda:   # train.py:240-243 as one kernel (same terms and weights)
+        g_loss = LF.weighted_sum([mr_loss, m_loss, adv_loss, fm_loss],
+                                 [1.0, args.lambda_mask, args.lambda_adv, args.lambda_adv * args.lambda_fm])
+    else:
+        g_loss = mr_loss + args.lambda_mask * m_loss + args.lambda_adv * (adv_loss + args.lambda_fm * fm_loss)
     config.defer_dead_param_grads = bool(args.defer_dead_d_grads) and noisy.is_cuda
     try:
         g_loss.backward()
@@ -135,11 +139,16 @@ def _phase_g(M, noisy, clean, args: StepArgs, st: dict) -> None:
               fm=fm_loss.detach())
 
 
-def _phase_opt_g(M, args: StepArgs) -> None:
+def _phase_opt_g(M, args: StepArgs, pre_scale: float = 1.0) -> None:
     """Gradient clipping + generator update (train.py:246-249)."""
     enhancer, g_opt = M[0], M[5]
     if args.grad_clip > 0.0:
-        torch.nn.utils.clip_grad_norm_(enhancer.parameters(), args.grad_clip)
+        if next(enhancer.parameters()).is_cuda:
+            # fused global-norm clip (SURVEY 8f N2): two launches over the flat buffer the generator's backward wrote
+            clip_grad_norm_(enhancer.parameters(), args.grad_clip, arena=getattr(enhancer.gen, "_grad_arena", None),
+                            pre_scale=pre_scale)
+        else:
+            torch.nn.utils.clip_grad_norm_(enhancer.parameters(), args.grad_clip)
     g_opt.step()
 
 
@@ -167,6 +176,51 @@ def train_step(enhancer, mpd, msd, tf_features, mrstft_loss, g_opt, d_opt, noisy
         after_g_backward()
     _phase_opt_g(M, args)
     return {k: st[k] for k in _OUT_KEYS}
+
+
+def synthetic_batch(batch: int, samples: int, seed: int = 1234):
+    """The synthetic workload of SURVEY.md section 8(d): clean ~ N(0, 0.1^2), noisy = clean + N(0, 0.05^2), drawn on the
+    CPU generator (so that every implementation sees the same waveforms).  Returns (noisy, clean) on the host."""
+    g = torch.Generator().manual_seed(seed)
+    clean = torch.randn(batch, samples, generator=g) * 0.1
+    noisy = clean + torch.randn(batch, samples, generator=g) * 0.05
+    return noisy, clean
+
+
+def snapshot_state(modules, optimizers):
+    """Copies of every parameter / buffer and of the optimisers' state tensors (see restore_state)."""
+    snap = {"mod": [[t.detach().clone() for t in list(m.parameters()) + list(m.buffers())] for m in modules], "opt": []}
+    for o in optimizers:
+        ts = []
+        for group in o.param_groups:
+            if isinstance(group.get("_step"), torch.Tensor):
+                ts.append(group["_step"])
+            for p in group["params"]:
+                ts += [v for v in o.state.get(p, {}).values() if isinstance(v, torch.Tensor)]
+        snap["opt"].append([t.detach().clone() for t in ts])
+    return snap
+
+
+def restore_state(modules, optimizers, snap) -> None:
+    """Write a snapshot_state() back IN PLACE (addresses are unchanged, so a captured GraphedTrainStep keeps working).
+    Optimiser state created after the snapshot (first step) is reset to zero = a freshly built optimiser."""
+    with torch.no_grad():
+        for m, saved in zip(modules, snap["mod"]):
+            for t, s in zip(list(m.parameters()) + list(m.buffers()), saved):
+                t.copy_(s)
+        for o, saved in zip(optimizers, snap["opt"]):
+            ts = []
+            for group in o.param_groups:
+                if isinstance(group.get("_step"), torch.Tensor):
+                    ts.append(group["_step"])
+                for p in group["params"]:
+                    ts += [v for v in o.state.get(p, {}).values() if isinstance(v, torch.Tensor)]
+            if len(saved) == len(ts):
+                for t, s in zip(ts, saved):
+                    t.copy_(s)
+            else:
+                for t in ts:
+                    t.zero_()
 
 
 def build_models(device, gan_seed: Optional[int] = 42, max_time_context: Optional[int] = 200,

@@ -82,7 +82,7 @@ def discriminator_loss(real_logits: Sequence[torch.Tensor], fake_logits: Sequenc
     else:
         lr = LF.mt_loss(_ops.OP_RELU_AFFINE, real, None, _mean_scales(real, n), k0=1.0, k1=-1.0)
         lf = LF.mt_loss(_ops.OP_RELU_AFFINE, fake, None, _mean_scales(fake, n), k0=1.0, k1=1.0)
-    return lr + lf
+    return LF.weighted_sum([lr, lf], [1.0, 1.0]) if lr.is_cuda else lr + lf
 
 
 def generator_adv_loss(fake_logits, loss_type="ls"):

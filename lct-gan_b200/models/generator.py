@@ -40,7 +40,7 @@ class _BlockFn(torch.autograd.Function):
     def forward(ctx, rows, geom, freq, names, *params):
         B, T, F = geom
         P = dict(zip(names, params))
-        S = {} if any(ctx.needs_input_grad) else None
+        S = {} if any(ctx.needs_input_grad) else None     # (released with ctx when no graph is recorded)
         out = _gi._block_fwd(P, "blk", rows.contiguous(), B, T, F, freq, S)
         ctx.S, ctx.geom, ctx.freq, ctx.names = S, geom, freq, names
         ctx.save_for_backward(*params)
@@ -51,6 +51,9 @@ class _BlockFn(torch.autograd.Function):
         P = dict(zip(ctx.names, ctx.saved_tensors))
         B, T, F = ctx.geom
         GR = {}
+        if ctx.S is None:
+            raise RuntimeError("GRU block backward: saved activations already released (second backward through the "
+                               "same graph is not supported)")
         dx = _gi._block_bwd(P, "blk", g.contiguous(), B, T, F, ctx.freq, ctx.S, GR)
         ctx.S = None
         return (dx, None, None, None, *[GR.get(n) for n in ctx.names])
@@ -207,7 +210,8 @@ class LCTGenerator(nn.Module):
     def forward_phys(self, mag_phys: torch.Tensor) -> torch.Tensor:
         """mag_phys: [B, T, F] (the STFT kernels' layout) -> mask [B, T, F]."""
         names, params = self._flat_params()
-        return _gi.GeneratorFn.apply(mag_phys, self.cfg.output_activation == "sigmoid", names, *params)
+        return _gi.GeneratorFn.apply(mag_phys, self.cfg.output_activation == "sigmoid", names, self,
+                                     torch.is_grad_enabled(), *params)
 
     def forward(self, noisy_mag: torch.Tensor) -> torch.Tensor:
         if noisy_mag.dim() != 4 or noisy_mag.size(1) != 1:

@@ -56,6 +56,50 @@ def sub(t, n=4096):
     return f[idx].clone()
 
 
+def train_logs(G, R_train, R_gen, R_disc, R_tf, R_losses, noisy, clean):
+    """Two unmodified train_one_epoch steps (ls and hinge) on one batch: printed losses, gradient norms after the first
+    backward passes and post-step weight checksums."""
+    import argparse as _ap
+    import contextlib
+    import io
+    import re
+    for gan_loss in ("ls", "hinge"):
+        R_train.set_seed(42)
+        enh = R_gen.LCTEnhancer(R_gen.LCTGeneratorConfig(max_time_context=200), c=0.3)
+        mpd = R_disc.MultiPeriodDiscriminator()
+        msd = R_disc.MultiScaleDiscriminator()
+        tfm = R_tf.TFFeatures(R_tf.TFFeaturesConfig(n_fft=512, c=0.3, compress_input=False, return_stfts=False))
+        mr = R_losses.MultiResolutionSTFTLoss(R_losses.MRSTFTLossConfig())
+        g_opt = torch.optim.AdamW(enh.parameters(), lr=2e-4, betas=(0.8, 0.99))
+        d_opt = torch.optim.AdamW(list(mpd.parameters()) + list(msd.parameters()), lr=2e-4, betas=(0.8, 0.99))
+        ns = _ap.Namespace(gan_loss=gan_loss, lambda_fm=1.0, lambda_mask=1.0, lambda_adv=1e-2, grad_clip=5.0,
+                           log_interval=1)
+        logs = []
+        # gradient statistics at the moment each optimiser steps (optimizer pre-hooks: the reference code is untouched):
+        # D gradients of d_loss.backward() alone, enhancer gradients after clip_grad_norm_
+        gstats = {"d": [], "g": []}
+
+        def _stat(key, params):
+            def hook(opt, a, k):
+                gs = [p.grad.double() for p in params if p.grad is not None]
+                gstats[key].append({"l2": float(torch.sqrt(sum((g * g).sum() for g in gs))),
+                                    "sum": float(sum(g.sum() for g in gs)), "abs": float(sum(g.abs().sum() for g in gs))})
+            return hook
+        d_opt.register_step_pre_hook(_stat("d", list(mpd.parameters()) + list(msd.parameters())))
+        g_opt.register_step_pre_hook(_stat("g", list(enh.parameters())))
+        for step in range(2):
+            buf = io.StringIO()
+            with contextlib.redirect_stdout(buf):
+                R_train.train_one_epoch(1, {"train": [{"noisy": noisy, "clean": clean}]}, enh, mpd, msd, tfm, mr, g_opt,
+                                        d_opt, torch.device("cpu"), ns)
+            vals = {k: float(v) for k, v in re.findall(r"(\w+)=(-?[\d.]+)", buf.getvalue())}
+            logs.append(vals)
+        G[f"train_{gan_loss}"] = {"logs": logs, "grad_stats": gstats,
+                                  "enh_checksum": float(sum(p.double().sum() for p in enh.parameters())),
+                                  "msd_checksum": float(sum(p.double().sum() for p in msd.parameters())),
+                                  "mpd_checksum": float(sum(p.double().sum() for p in mpd.parameters()))}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(HERE, "golden_v1.pt"))
@@ -68,10 +112,27 @@ def main():
     ap.add_argument("--batch", type=int, default=2)
     ap.add_argument("--front-seed", type=int, default=7)
     ap.add_argument("--model-seed", type=int, default=1234)
+    # golden_v3.pt: the BASELINE shape (batch 8 x 32000 samples), logs and checksums only (a few KB):
+    #   python tests/golden/make_golden.py --out tests/golden/golden_v3.pt --logs-only --model-len 32000 --batch 8
+    ap.add_argument("--logs-only", action="store_true", help="store only the two-step train_one_epoch logs, the "
+                    "parameter checksums and the recipe of the inputs (not the inputs themselves)")
     args = ap.parse_args()
     R_stft, R_tf, R_losses, R_disc, R_gen, R_train = import_reference()
     torch.set_num_threads(8)
     G = {"torch": torch.__version__, "istft_length": args.istft_len}
+    if args.logs_only:
+        G = {"torch": torch.__version__, "logs_only": True,
+             "input_recipe": {"batch": args.batch, "samples": args.model_len, "seed": args.model_seed,
+                              "formula": "g=Generator().manual_seed(seed); clean=randn(b,t,generator=g)*0.1; "
+                                         "noisy=clean+randn(b,t,generator=g)*0.05"}}
+        noisy, clean = batch(args.batch, args.model_len, seed=args.model_seed)
+        G["input_checksum"] = (float(noisy.double().sum()), float(clean.double().sum()))
+        train_logs(G, R_train, R_gen, R_disc, R_tf, R_losses, noisy, clean)
+        torch.save(G, args.out)
+        print("wrote", args.out, os.path.getsize(args.out), "bytes")
+        for k in ("train_ls", "train_hinge"):
+            print(k, G[k]["logs"])
+        return
 
     # ---- front end: STFT / iSTFT / helpers at the three loss resolutions + the generator's
     noisy, clean = batch(args.batch, args.front_len, seed=args.front_seed)
@@ -130,34 +191,7 @@ def main():
         mrl, det = mr(e, clean)
         G["mrstft"] = (float(mrl), {k: float(v) for k, v in det.items()})
 
-    # ---- two unmodified train_one_epoch steps (ls and hinge) on one batch: losses + post-step weights
-    import argparse as _ap
-    import contextlib
-    import io
-    import re
-    for gan_loss in ("ls", "hinge"):
-        R_train.set_seed(42)
-        enh = R_gen.LCTEnhancer(R_gen.LCTGeneratorConfig(max_time_context=200), c=0.3)
-        mpd = R_disc.MultiPeriodDiscriminator()
-        msd = R_disc.MultiScaleDiscriminator()
-        tfm = R_tf.TFFeatures(R_tf.TFFeaturesConfig(n_fft=512, c=0.3, compress_input=False, return_stfts=False))
-        mr = R_losses.MultiResolutionSTFTLoss(R_losses.MRSTFTLossConfig())
-        g_opt = torch.optim.AdamW(enh.parameters(), lr=2e-4, betas=(0.8, 0.99))
-        d_opt = torch.optim.AdamW(list(mpd.parameters()) + list(msd.parameters()), lr=2e-4, betas=(0.8, 0.99))
-        ns = _ap.Namespace(gan_loss=gan_loss, lambda_fm=1.0, lambda_mask=1.0, lambda_adv=1e-2, grad_clip=5.0,
-                           log_interval=1)
-        logs = []
-        for step in range(2):
-            buf = io.StringIO()
-            with contextlib.redirect_stdout(buf):
-                R_train.train_one_epoch(1, {"train": [{"noisy": noisy, "clean": clean}]}, enh, mpd, msd, tfm, mr, g_opt,
-                                        d_opt, torch.device("cpu"), ns)
-            vals = {k: float(v) for k, v in re.findall(r"(\w+)=(-?[\d.]+)", buf.getvalue())}
-            logs.append(vals)
-        G[f"train_{gan_loss}"] = {"logs": logs,
-                                  "enh_checksum": float(sum(p.double().sum() for p in enh.parameters())),
-                                  "msd_checksum": float(sum(p.double().sum() for p in msd.parameters())),
-                                  "mpd_checksum": float(sum(p.double().sum() for p in mpd.parameters()))}
+    train_logs(G, R_train, R_gen, R_disc, R_tf, R_losses, noisy, clean)
     torch.save(G, args.out)
     print("wrote", args.out, os.path.getsize(args.out), "bytes")
     for k in ("train_ls", "train_hinge"):

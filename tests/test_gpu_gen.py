@@ -171,6 +171,27 @@ def test_attention(dev, freq, T, Fq):
     assert rel_err(ref, mha) < 1e-5
 
 
+def test_attention_forward_long_sequence(dev):
+    """The attention forward streams keys / values through shared memory in chunks, so the time block accepts whole
+    utterances of any length (infer.py; L = frames + 3): 2500 frames = 40 s at hop 256, three chunks of 1024 rows and
+    ten query blocks per (sequence, head).  Round 1 kept all keys in shared memory and refused L > 1600."""
+    from lctgan import gen_impl, ops
+    B, T, Fq = 1, 2500, 2
+    gen = torch.Generator().manual_seed(23)
+    M = B * T * Fq
+    qkv = torch.randn(B, T, Fq, 192, generator=gen)
+    seqs = qkv.permute(0, 2, 1, 3).reshape(B * Fq, T, 192).double()
+    q, k, v = seqs.chunk(3, dim=-1)
+    sp = lambda t: t.reshape(B * Fq, T, 4, 16).permute(0, 2, 1, 3)
+    att = torch.softmax(sp(q) @ sp(k).transpose(-1, -2) / 4.0, dim=-1)
+    ref = (att @ sp(v)).permute(0, 2, 1, 3).reshape(B, Fq, T, 64).permute(0, 2, 1, 3).reshape(M, 64)
+    geo = gen_impl._geom(B, T, Fq, False)
+    out = torch.empty(M, 64, device=dev)
+    lse = torch.empty(M, 4, device=dev)
+    ops.call("lct_attn_fwd", qkv.reshape(M, 192).to(dev), out, lse, 4, geo[0], geo[1], geo[2], geo[3], geo[4], geo[5])
+    assert rel_err(out, ref) < 2e-5
+
+
 @pytest.mark.parametrize("tc", [False, pytest.param(True, marks=pytest.mark.bf16)])   # SIMT fp32 | 3xTF32 tensor-core kernels
 @pytest.mark.parametrize("Ci,Co,T,Fq", [(1, 16, 6, 257), (16, 32, 7, 129), (32, 64, 8, 65), (4, 8, 3, 10)])
 def test_gconv_conv(dev, Ci, Co, T, Fq, tc):

@@ -132,6 +132,44 @@ def test_training_step_matches_reference_train_one_epoch(G, gan_loss):
     assert abs(float(sum(st.mpd[k].double().sum() for k in st.mpd)) - ref["mpd_checksum"]) < 1e-1
 
 
+def test_oracle_stock_init_matches_reference_weights(G):
+    """oracle/ref_init.py (stock torch containers only, no product import - what `bench.py --impl reference` starts
+    from) reproduces the reference's seeded initial weights: keys, shapes and the checksum dumped from the reference."""
+    from oracle import ref_init
+    dicts = dict(zip(("enh", "mpd", "msd"), ref_init.init_state_dicts(42)))
+    for n, d in dicts.items():
+        assert list(d.keys()) == G["state_keys"][n]
+        assert {k: tuple(v.shape) for k, v in d.items()} == G["state_shapes"][n]
+        chk = float(sum(v.double().abs().sum() for k, v in d.items() if not k.endswith("window")))
+        assert abs(chk - G["param_checksum"][n]) <= 1e-9 * G["param_checksum"][n], n
+
+
+def test_oracle_step_at_baseline_shape_matches_golden_v3():
+    """BASELINE configs[0]/[2] shape (batch 8 x 32000 samples, SURVEY.md section 8c known answers): the first oracle step
+    from the stock-container initial weights reproduces the reference's train_one_epoch log (golden_v3.pt, written by
+    make_golden.py --logs-only) and the discriminator / clipped enhancer gradient norms at the optimiser steps."""
+    O = oracle()
+    from oracle import ref_init
+    G3 = torch.load(os.path.join(os.path.dirname(GOLD), "golden_v3.pt"), weights_only=False)
+    r = G3["input_recipe"]
+    assert (r["batch"], r["samples"], r["seed"]) == (8, 32000, 1234)
+    noisy, clean = O.synthetic_batch(r["batch"], r["samples"], seed=r["seed"])
+    assert abs(float(noisy.double().sum()) - G3["input_checksum"][0]) < 1e-6
+    # SURVEY 8c known answers are exactly what the fixture holds
+    assert G3["train_ls"]["logs"][0] == {"D_loss": 0.9975, "G_loss": 2.9402, "MR": 2.715, "Mask": 0.2173, "Adv": 0.7964,
+                                         "FM": 0.005}
+    assert G3["train_hinge"]["logs"][0]["D_loss"] == 2.0 and G3["train_hinge"]["logs"][0]["Adv"] == -0.0025
+    Pe, Pp, Ps = ref_init.init_state_dicts(42)
+    st = O.StepState(Pe, Pp, Ps, order_g=ref_init.param_order(Pe),
+                     order_d=(ref_init.param_order(Pp), ref_init.param_order(Ps)))
+    got = O.train_step(st, noisy, clean, [O.hann_window(n) for n in O.MR_FFT_SIZES], gan_loss="ls", aten_gru=True)
+    names = {"D_loss": "d_loss", "G_loss": "g_loss", "MR": "mr", "Mask": "mask", "Adv": "adv", "FM": "fm"}
+    for ref_k, k in names.items():
+        assert abs(got[k] - G3["train_ls"]["logs"][0][ref_k]) <= 1.01e-4, k
+    assert abs(got["g_grad_norm"] - 0.0) > 5.0          # clip active: pre-clip norm above the 5.0 threshold
+    assert abs(G3["train_ls"]["grad_stats"]["g"][0]["l2"] - 5.0) < 1e-5
+
+
 def test_known_answers_from_survey():
     """integer framing of the discriminators and the AvgPool known answer."""
     O = oracle()

@@ -6,10 +6,8 @@ import torch
 from lctgan import _lib
 from lctgan.training import build_models, StepArgs, _phase_d, _phase_g, _phase_opt_g
 import losses as L
-from oracle import lct_oracle as O
+from lctgan import training as O
 
-if os.environ.get("LCT_MMA_TUNE"):
-    a, b = os.environ["LCT_MMA_TUNE"].split(","); _lib.call_ret("lct_conv_mma_tune", int(a), int(b))
 dev = torch.device("cuda:0")
 enh, mpd, msd, tf, mr, g_opt, d_opt = build_models(dev, 42, capturable=True)
 noisy, clean = (t.to(dev) for t in O.synthetic_batch(8, 32000))

@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.join(ROOT, "lct-gan_b200")); sys.path.insert(0, ROOT)
 import torch
 from lctgan.training import build_models
 import losses as L
-from oracle import lct_oracle as O
+from lctgan import training as O          # synthetic_batch lives with the product
 dev = torch.device("cuda:0")
 enh, mpd, msd, tf, mr, g_opt, d_opt = build_models(dev, 42)
 noisy, clean = (t.to(dev) for t in O.synthetic_batch(8, 32000))

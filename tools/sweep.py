@@ -13,7 +13,7 @@ import torch
 
 def run_case(seg_s, batch, steps, dev):
     from lctgan.training import GraphedTrainStep, StepArgs, build_models
-    from oracle import lct_oracle as O                     # synthetic data generator only
+    from lctgan import training as O          # synthetic_batch lives with the product
     T = int(round(seg_s * 16000))
     torch.cuda.reset_peak_memory_stats(dev)
     enh, mpd, msd, tf, mr, g_opt, d_opt = build_models(dev, gan_seed=42, capturable=True, fused_optim=True)
