@@ -112,6 +112,18 @@ LCT_API int lct_conv1d_dgrad(const float* dy, const float* w, float* dx, const f
 /* dw [Cout,Cin/G,K] and db [Cout] (optional) are accumulated. */
 LCT_API int lct_conv1d_wgrad(const float* x, const float* dy, float* dw, float* db, int64_t B, int64_t Cin, int64_t Cout, int64_t G, int64_t K, int64_t S, int64_t pad, int64_t Lin, int64_t P, cudaStream_t stream);
 
+/* ---- grouped strided convolutions on tcgen05 (csrc/conv_tc.cu): UMMA kind::tf32 with both operands read from shared
+ * memory through descriptors, accumulators in TMEM.  Same operator and tensor layouts as lct_conv1d_* (reference
+ * models/discriminators.py:37-67, :93-98, :166-196, :215-220): x [B,Cin,Lin,P], w [Cout,Cin/G,K], pad = K/2.
+ * Weights are passed as per-layer IMAGES (tf32-rounded, arranged per group in the kernels' shared-memory layout) built
+ * by lct_conv_tc_images for up to 8 layers per launch; geo = HOST array of 6 int64 per layer (Cin, Cout, G, K, S, P). */
+LCT_API int lct_conv_tc_supported(int64_t Cin, int64_t Cout, int64_t G, int64_t K, int64_t S, int64_t P);
+LCT_API int lct_conv_tc_image_len(int64_t Cin, int64_t Cout, int64_t G, int64_t K, int64_t S, int64_t P, int64_t* out);   /* out[0] fwd, out[1] dgrad floats (HOST) */
+LCT_API int lct_conv_tc_images(const void* const* w, void* const* img_f, void* const* img_d, const int64_t* geo, int64_t n, cudaStream_t stream);
+LCT_API int lct_conv_tc_fwd(const float* x, const float* wimg, const float* bias, float* y, int64_t B, int64_t Cin, int64_t Cout, int64_t G, int64_t K, int64_t S, int64_t pad, int64_t Lin, int64_t P, int act, float slope, cudaStream_t stream);
+LCT_API int lct_conv_tc_dgrad(const float* dy, const float* wimg, float* dx, const float* gextra, const float* xact, int64_t B, int64_t Cin, int64_t Cout, int64_t G, int64_t K, int64_t S, int64_t pad, int64_t Lin, int64_t P, int act, float slope, cudaStream_t stream);
+LCT_API int lct_conv_tc_wgrad(const float* x, const float* dy, float* dw, float* db, int64_t B, int64_t Cin, int64_t Cout, int64_t G, int64_t K, int64_t S, int64_t pad, int64_t Lin, int64_t P, cudaStream_t stream);
+
 /* The same grouped convolutions on the tensor cores: TF32 mma.sync implicit GEMM, fp32 accumulation, persistent CTAs with
  * cp.async double-buffered input windows (conv_mma.cu).  Same arguments as lct_conv1d_*; lct_conv_mma_supported says
  * whether a layer shape is covered (groups with <= 16 in / <= 32 out channels, stride 1/3/4, Cin/G * K <= 168). */

@@ -1,0 +1,812 @@
+// Grouped strided convolutions of the waveform discriminators on the 5th-generation tensor cores
+// (tcgen05.mma kind::tf32, accumulators in TMEM), forward + data gradient + weight gradient.
+//
+// Operator (reference models/discriminators.py:37-67, :93-98 PeriodDiscriminator; :166-196, :215-220
+// ScaleDiscriminator): convolution along L of [B, C, L, P] (P = period, 1 for the scale discriminators) with
+// groups, stride S and "same" padding K/2 - Cin/G = 1..16 input and Cout/G = 4..32 output channels per group.
+// These layers are HBM bound (2-40 flop/B); round 1 ran them as mma.sync implicit GEMMs whose A fragments were
+// gathered by the threads and measured them instruction-issue bound (22 warp instructions per m16n8k8 mma, 0.29
+// of the HBM roofline).  tcgen05.mma reads BOTH operands from shared memory through descriptors, so here the
+// threads only move data once (global -> registers -> shared memory, with the tf32 rounding on the way) and one
+// thread issues ~20 MMAs per 128-position tile.
+//
+// The implicit GEMM without im2col.  A tile is 128 consecutive flat output positions m = l * P + p of one
+// (batch, group).  The input window is stored in shared memory as float4 "slots" of 4 channels (a channel QUAD),
+// one PLANE per (stride phase rho, quad):   plane[rho][q][j] = x[4q .. 4q+3][S * u + rho - pad][p],  j = u * P + p.
+// For tap k = S * a + rho the 128 x 4 operand chunk "tap k, quad q" is then the 128 consecutive slots
+// j = m + a * P of plane (rho, q): rows 16 bytes apart - exactly the K-major no-swizzle core-matrix layout of a
+// UMMA shared-memory descriptor (8 rows x 16 bytes contiguous, SBO = 128).  So every (tap, quad) chunk is just a
+// descriptor start address, a K = 8 MMA pairs two chunks through the descriptor's leading byte offset (next quad:
+// LBO = plane pitch; or next tap of the same phase: LBO = 16 P), and overlapping windows cost nothing.
+//   forward        D[m, co]       = sum_{k, ci} X[ci][S l + k - pad][p] W[co][ci][k]           M = positions, N = Cout/G
+//   data gradient  D[(q,p),(ci,r)] = sum_{o, co} dY[co][q + o][p] W[co][ci][r + pad - S o]     N = (Cin/G) x S phases
+//                  dX[ci][S q + r][p] = D;  one GEMM produces all S output phases, fused (+ FM gradient) x LeakyReLU'
+//   weight gradient (MN-major descriptors: positions are the contraction dim, 8 per MMA)
+//                  D_{rho,q}[(a, ci in quad q), co] = sum_m X[ci][S (l + a) + rho - pad][p] dY[co][l][p]
+//                  M = 16 tap slots x 4 channels (M-block stride SBO = 16 P walks the taps of one phase), N = Cout/G;
+//                  accumulators stay in TMEM across all tiles of a persistent CTA, one atomic flush per CTA.
+// Weights arrive pre-arranged and tf32-rounded (round to nearest) as per-group images in exactly the shared-memory
+// layout (lct_conv_tc_images, one launch per layer stack).  Precision contract: TF32 operands rounded to nearest,
+// fp32 accumulation (tests/test_gpu_conv_mma.py: 2e-4 against fp64 on tf32-rounded operands).
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace {
+
+constexpr int kThreads = 128;     // 4 warps: warp w owns TMEM lanes [32 w, 32 w + 32)
+constexpr int kTileM = 128;
+constexpr int kMaxMma = 48;
+enum { MODE_FWD = 0, MODE_DGRAD = 1 };
+
+struct FastDiv { uint32_t mul, d; };
+__host__ __device__ __forceinline__ int fdiv(int n, FastDiv f) {       // n >= 0
+#ifdef __CUDA_ARCH__
+    return f.d == 1 ? n : (int)__umulhi((uint32_t)n, f.mul);
+#else
+    return (int)((uint32_t)n / f.d);
+#endif
+}
+FastDiv make_fdiv(int d) {          // exact for 0 <= n < 2^20 and d <= 64
+    FastDiv f;
+    f.d = (uint32_t)d;
+    f.mul = d > 1 ? (uint32_t)((1ULL << 32) / (uint64_t)d) + 1u : 0u;
+    return f;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Geometry of one layer in one mode; the MMA enumeration is a pure function of it (host and device agree).
+// ---------------------------------------------------------------------------------------------------------
+struct Geom {
+    int mode;            // MODE_FWD / MODE_DGRAD
+    int S, K, pad, P;
+    int cig, cog;        // conv input / output channels per group
+    int ca, nqa;         // channels of the A operand per group (fwd: cig, dgrad: cog) and its quads
+    int ncol, Npad;      // real / padded (multiple of 16) GEMM columns (fwd: cog, dgrad: cig * S)
+    int nphase;          // planes per quad (fwd: S stride phases, dgrad: 1)
+    int o_min;           // dgrad: tap offsets o = o_min .. o_min + ntap[0] - 1 (l = q + o)
+    int ntap[4];         // taps per phase
+    int by_tap;          // 1: a K = 8 MMA pairs taps (t, t + 1) of one quad (nqa == 1); 0: quads (2 i, 2 i + 1) of one tap
+    int tapmax;          // slots of look-ahead per plane, in taps (by_tap: rounded up to even)
+    int nmma;
+};
+
+__host__ __device__ inline int phase_mmas(const Geom& g, int ph) {
+    return g.by_tap ? (g.ntap[ph] + 1) / 2 : g.ntap[ph] * (g.nqa / 2);
+}
+// MMA j -> (phase, first tap, first quad); chunk 1 is (tap + 1, quad) if by_tap (valid iff tap + 1 < ntap) else (tap, quad + 1)
+__host__ __device__ inline void decode_mma(const Geom& g, int j, int& ph, int& tap, int& quad) {
+    ph = 0;
+    while (ph < g.nphase - 1 && j >= phase_mmas(g, ph)) { j -= phase_mmas(g, ph); ++ph; }
+    if (g.by_tap) { tap = 2 * j; quad = 0; }
+    else { const int h = g.nqa / 2; tap = j / h; quad = 2 * (j - tap * h); }
+}
+
+bool make_geom(Geom& g, int mode, int64_t Cin, int64_t Cout, int64_t G, int64_t K, int64_t S, int64_t pad, int64_t P) {
+    if (G <= 0 || Cin % G || Cout % G || S < 1 || S > 4 || K < 1 || K > 64 || P < 1 || P > 16 || pad != K / 2) return false;
+    g = Geom{};
+    g.mode = mode; g.S = (int)S; g.K = (int)K; g.pad = (int)pad; g.P = (int)P;
+    g.cig = (int)(Cin / G); g.cog = (int)(Cout / G);
+    if (g.cig > 16 || g.cog > 32) return false;
+    if (mode == MODE_FWD) {
+        g.ca = g.cig; g.ncol = g.cog; g.nphase = g.S; g.o_min = 0;
+        for (int r = 0; r < g.S; ++r) g.ntap[r] = r < g.K ? (g.K - 1 - r) / g.S + 1 : 0;
+    } else {
+        g.ca = g.cog; g.ncol = g.cig * g.S; g.nphase = 1;
+        // k = r + pad - S o in [0, K) for some phase r in [0, S): o from ceil((pad - K + 1) / S) to floor((S - 1 + pad) / S)
+        const int lo = g.pad - g.K + 1;
+        g.o_min = lo >= 0 ? (lo + g.S - 1) / g.S : -((-lo) / g.S);
+        const int o_max = (g.S - 1 + g.pad) / g.S;
+        g.ntap[0] = o_max - g.o_min + 1;
+    }
+    g.nqa = (g.ca + 3) / 4;
+    if (g.nqa != 1 && (g.nqa & 1)) return false;
+    g.by_tap = g.nqa == 1;
+    g.Npad = (g.ncol + 15) & ~15;
+    if (g.Npad > 32) return false;
+    g.tapmax = 0;
+    g.nmma = 0;
+    for (int ph = 0; ph < g.nphase; ++ph) {
+        if (g.ntap[ph] > g.tapmax) g.tapmax = g.ntap[ph];
+        g.nmma += phase_mmas(g, ph);
+    }
+    if (g.by_tap) g.tapmax = (g.tapmax + 1) & ~1;
+    return g.nmma >= 1 && g.nmma <= kMaxMma;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Weight images: per group, per MMA j a [2 chunks][Npad rows][4] block (K-major, SBO = 128, LBO = 16 Npad bytes)
+// ---------------------------------------------------------------------------------------------------------
+struct ImgJob {
+    Geom g;
+    const float* w;      // [Cout][cig][K]
+    float* img;          // [G][nmma][2][Npad][4]
+    int G;
+};
+constexpr int kMaxImgJobs = 16;
+struct ImgJobs { ImgJob job[kMaxImgJobs]; int n; };
+
+__global__ void __launch_bounds__(256) tc_image_kernel(const ImgJobs J) {
+    const ImgJob& jb = J.job[blockIdx.y];
+    const Geom& g = jb.g;
+    const int per_group = g.nmma * 2 * g.Npad * 4;
+    const int64_t total = (int64_t)jb.G * per_group;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int grp = (int)(idx / per_group);
+        int r = (int)(idx - (int64_t)grp * per_group);
+        const int e = r & 3; r >>= 2;
+        const int n = r % g.Npad; r /= g.Npad;
+        const int c = r & 1;
+        const int j = r >> 1;
+        int ph, tap, quad;
+        decode_mma(g, j, ph, tap, quad);
+        bool valid = true;
+        if (c) {
+            if (g.by_tap) { ++tap; valid = tap < g.ntap[ph]; }
+            else ++quad;
+        }
+        float v = 0.f;
+        const int ch = 4 * quad + e;        // channel of the A operand inside the group
+        if (valid && n < g.ncol && ch < g.ca) {
+            if (g.mode == MODE_FWD) {
+                const int k = g.S * tap + ph;
+                v = jb.w[((int64_t)(grp * g.cog + n) * g.cig + ch) * g.K + k];
+            } else {
+                const int ci = n / g.S, rr = n - ci * g.S;
+                const int k = rr + g.pad - g.S * (g.o_min + tap);
+                if (k >= 0 && k < g.K) v = jb.w[((int64_t)(grp * g.cog + ch) * g.cig + ci) * g.K + k];
+            }
+        }
+        jb.img[idx] = tc::tf32_rna(v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Operand staging: global [B][C][Ls][P] fp32 -> registers -> tf32-rounded float4 slots in shared memory
+// ---------------------------------------------------------------------------------------------------------
+struct SrcMap {
+    const float* src;
+    int C, Ls, P;        // channels of the tensor, its length along L, period
+    int Sg, ishift;      // source position of (row u, phase rho): i = Sg * u + rho + ishift
+    int nch;             // real channels per group (the rest of the last quad is zero)
+    int nslots;          // slots to fill per plane
+    int PP;              // plane pitch in bytes
+    FastDiv fP, fS;
+};
+
+template <int NQ, int NIT>
+struct Staged { float v[NIT][NQ * 4]; };
+
+// issue the loads of one tile (coalesced: consecutive threads read consecutive floats of every channel row)
+template <int NQ, int NIT>
+__device__ __forceinline__ void stage_load(Staged<NQ, NIT>& R, const SrcMap& s, int b, int cbase, int m0) {
+    const int u0 = fdiv(m0, s.fP), p0 = m0 - u0 * s.P;
+    const int nrows = fdiv(p0 + s.nslots + s.P - 1, s.fP);
+    const int nE = s.Sg * nrows * s.P;
+    const int ibase = s.Sg * u0 + s.ishift;
+    const int64_t chs = (int64_t)s.Ls * s.P;
+    const float* row0 = s.src + ((int64_t)b * s.C + cbase) * chs + (int64_t)ibase * s.P;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        const int e = (int)threadIdx.x + kThreads * it;
+        const int ir = fdiv(e, s.fP);
+        const int i = ibase + ir;
+        const bool ok = e < nE && i >= 0 && i < s.Ls;
+#pragma unroll
+        for (int c = 0; c < NQ * 4; ++c) R.v[it][c] = (ok && c < s.nch) ? __ldg(row0 + c * chs + e) : 0.f;
+    }
+}
+
+// round to tf32 and store as float4 slots: plane (rho, q) at `base` + (rho * NQ + q) * PP, slot j at + 16 j
+template <int NQ, int NIT>
+__device__ __forceinline__ void stage_store(const Staged<NQ, NIT>& R, const SrcMap& s, uint8_t* base, int m0) {
+    const int u0 = fdiv(m0, s.fP), p0 = m0 - u0 * s.P;
+    const int nrows = fdiv(p0 + s.nslots + s.P - 1, s.fP);
+    const int nE = s.Sg * nrows * s.P;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        const int e = (int)threadIdx.x + kThreads * it;
+        const int ir = fdiv(e, s.fP);
+        const int p = e - ir * s.P;
+        const int du = fdiv(ir, s.fS), rho = ir - du * s.Sg;
+        const int j = du * s.P + p - p0;
+        if (e < nE && j >= 0 && j < s.nslots) {
+            uint8_t* dst = base + (size_t)(rho * NQ) * s.PP + (size_t)j * 16;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q)
+                *reinterpret_cast<float4*>(dst + (size_t)q * s.PP) =
+                    make_float4(tc::tf32_rna(R.v[it][4 * q]), tc::tf32_rna(R.v[it][4 * q + 1]),
+                                tc::tf32_rna(R.v[it][4 * q + 2]), tc::tf32_rna(R.v[it][4 * q + 3]));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// forward / data gradient
+// ---------------------------------------------------------------------------------------------------------
+// data-gradient epilogue of 16 accumulator columns [C0, C0 + 16) of one tile row (q, p): column n = ci * S + r is
+// dX[ci][S q + r][p]; fused (+ FM gradient) x LeakyReLU'(saved activation).  S and C0 are compile-time so that the
+// column -> (ci, r) split costs nothing; VEC: S == 4, P == 1, 16-byte aligned rows -> one float4 per (row, channel).
+template <int S, int C0, bool VEC>
+__device__ __forceinline__ void dgrad_store16(const uint32_t (&v)[16], int ncol, int q, int Lin, int P, int64_t base,
+                                              int64_t chs, const float* __restrict__ gextra,
+                                              const float* __restrict__ xact, float* __restrict__ out, int act,
+                                              float slope) {
+    if (VEC) {
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+            const int col = C0 + 4 * c4;
+            if (col < ncol) {
+                const int64_t idx = base + (int64_t)(col / 4) * chs;
+                float4 a = make_float4(__uint_as_float(v[4 * c4]), __uint_as_float(v[4 * c4 + 1]),
+                                       __uint_as_float(v[4 * c4 + 2]), __uint_as_float(v[4 * c4 + 3]));
+                if (gextra) {
+                    const float4 ge = __ldcs(reinterpret_cast<const float4*>(gextra + idx));
+                    a.x += ge.x; a.y += ge.y; a.z += ge.z; a.w += ge.w;
+                }
+                if (xact) {
+                    const float4 xa = __ldcs(reinterpret_cast<const float4*>(xact + idx));
+                    a.x *= act_grad_from_out(xa.x, act, slope); a.y *= act_grad_from_out(xa.y, act, slope);
+                    a.z *= act_grad_from_out(xa.z, act, slope); a.w *= act_grad_from_out(xa.w, act, slope);
+                }
+                *reinterpret_cast<float4*>(out + idx) = a;
+            }
+        }
+        return;
+    }
+#pragma unroll
+    for (int n = 0; n < 16; ++n) {
+        const int col = C0 + n;
+        const int ci = col / S, r = col - ci * S;       // compile-time after unrolling
+        if (col < ncol && S * q + r < Lin) {
+            const int64_t idx = base + (int64_t)ci * chs + (int64_t)r * P;
+            float a = __uint_as_float(v[n]);
+            if (gextra) a += gextra[idx];
+            if (xact) a *= act_grad_from_out(xact[idx], act, slope);
+            out[idx] = a;
+        }
+    }
+}
+
+struct ConvParams {
+    Geom g;
+    SrcMap a;                // the gathered tensor (fwd: x, dgrad: dY)
+    const float* wimg;       // [G][nmma][2][Npad][4]
+    float* out;              // fwd: y [B][Cout][Lout][P]; dgrad: dx [B][Cin][Lin][P]
+    const float* bias;       // fwd (optional)
+    const float* gextra;     // dgrad (optional)
+    const float* xact;       // dgrad (optional)
+    int B, Cin, Cout, Lin, Lout;
+    int Mtot;                // flat rows per batch (fwd: Lout * P; dgrad: ceil(Lin / S) * P)
+    int tiles_per_b, ntiles;
+    int a_bytes, b_bytes;    // shared-memory sizes of the A planes and of the weight image
+    int act; float slope;
+    int vec_ok;              // dgrad: dx / gextra / xact are 16-byte aligned
+    FastDiv fT;
+};
+
+template <int MODE, int NQ, int NIT>
+__global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* A = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    uint8_t* Bw = A + p.a_bytes;
+    uint64_t* descs = reinterpret_cast<uint64_t*>(Bw + p.b_bytes);     // [nmma][2]
+    float* bias_s = reinterpret_cast<float*>(descs + 2 * kMaxMma);     // [32]
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(bias_s + 32);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+
+    const Geom& g = p.g;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = blockIdx.x;
+    const int cbase_a = grp * g.ca;
+
+    // ---- one-time setup: barrier, TMEM, weight image, descriptors, bias
+    if (threadIdx.x == 0) {
+        tc::mbar_init(mbar, 1);
+        tc::mbar_fence_init();
+    }
+    if (warp == 0) tc::tmem_alloc<32>(tmem_slot);
+    {
+        const float4* src = reinterpret_cast<const float4*>(p.wimg + (size_t)grp * (p.b_bytes / 4));
+        float4* dst = reinterpret_cast<float4*>(Bw);
+        for (int i = threadIdx.x; i < p.b_bytes / 16; i += kThreads) dst[i] = __ldg(src + i);
+    }
+    for (int j = threadIdx.x; j < g.nmma; j += kThreads) {
+        int ph, tap, quad;
+        decode_mma(g, j, ph, tap, quad);
+        const uint32_t a_addr = tc::smem_u32(A) + (uint32_t)((ph * g.nqa + quad) * p.a.PP + tap * g.P * 16);
+        const uint32_t lbo = g.by_tap ? (uint32_t)(g.P * 16) : (uint32_t)p.a.PP;
+        descs[2 * j] = tc::smem_desc(a_addr, lbo, 128);
+        descs[2 * j + 1] = tc::smem_desc(tc::smem_u32(Bw) + (uint32_t)(j * g.Npad * 32), (uint32_t)(g.Npad * 16), 128);
+    }
+    if (threadIdx.x < 32) {
+        const int n = threadIdx.x;
+        bias_s[n] = (MODE == MODE_FWD && p.bias && n < g.cog) ? p.bias[grp * g.cog + n] : 0.f;
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t idesc = tc::idesc_tf32(kTileM, g.Npad, 0, 0);
+
+    Staged<NQ, NIT> R;
+    int tile = blockIdx.y;
+    uint32_t phase = 0;
+    if (tile < p.ntiles) {
+        const int b = fdiv(tile, p.fT);
+        stage_load<NQ, NIT>(R, p.a, b, cbase_a, (tile - b * p.tiles_per_b) * kTileM);
+    }
+    while (tile < p.ntiles) {
+        const int b = fdiv(tile, p.fT);
+        const int m0 = (tile - b * p.tiles_per_b) * kTileM;
+        stage_store<NQ, NIT>(R, p.a, A, m0);
+        tc::fence_proxy_async_smem();            // st.shared (generic proxy) -> tcgen05.mma operand reads (async proxy)
+        __syncthreads();
+        const int next = tile + gridDim.y;
+        if (next < p.ntiles) {                   // next tile's loads fly during this tile's MMAs and epilogue
+            const int nb = fdiv(next, p.fT);
+            stage_load<NQ, NIT>(R, p.a, nb, cbase_a, (next - nb * p.tiles_per_b) * kTileM);
+        }
+        if (threadIdx.x == 0) {
+            tc::fence_after_sync();
+            for (int j = 0; j < g.nmma; ++j) tc::umma_tf32(tmem_base, descs[2 * j], descs[2 * j + 1], idesc, (uint32_t)(j != 0));
+            tc::umma_commit(mbar);
+        }
+        tc::mbar_wait(mbar, phase);
+        phase ^= 1;
+        tc::fence_after_sync();
+
+        // ---- epilogue: TMEM lane = tile row
+        const int m = m0 + warp * 32 + lane;
+        const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+        if (MODE == MODE_FWD) {
+            const int64_t LoP = (int64_t)p.Mtot;
+            float* yb = p.out + ((int64_t)b * p.Cout + (int64_t)grp * g.cog) * LoP + m;
+            for (int c0 = 0; c0 < g.Npad; c0 += 16) {
+                uint32_t v[16];
+                tc::tmem_ld16(trow + (uint32_t)c0, v);
+                tc::tmem_ld_wait();
+                if (m < p.Mtot) {
+#pragma unroll
+                    for (int n = 0; n < 16; ++n)
+                        if (c0 + n < g.cog)
+                            yb[(int64_t)(c0 + n) * LoP] = apply_act(__uint_as_float(v[n]) + bias_s[c0 + n], p.act, p.slope);
+                }
+            }
+        } else {
+            // row m = (q, p): dX[ci][S q + r][p] for the S phases r (columns n = ci * S + r)
+            const int q = fdiv(m, p.a.fP), pp = m - q * g.P;
+            const int64_t chs = (int64_t)p.Lin * g.P;
+            const int64_t base = ((int64_t)b * p.Cin + (int64_t)grp * g.cig) * chs + (int64_t)(g.S * q) * g.P + pp;
+            const bool vec = g.S == 4 && g.P == 1 && (p.Lin & 3) == 0 && p.vec_ok;
+#define LCT_DG(SV, C0V, VV) dgrad_store16<SV, C0V, VV>(v, g.ncol, q, p.Lin, g.P, base, chs, p.gextra, p.xact, p.out, p.act, p.slope)
+            {
+                uint32_t v[16];
+                tc::tmem_ld16(trow, v);
+                tc::tmem_ld_wait();
+                if (m < p.Mtot) {
+                    if (vec) LCT_DG(4, 0, true);
+                    else if (g.S == 4) LCT_DG(4, 0, false);
+                    else if (g.S == 3) LCT_DG(3, 0, false);
+                    else if (g.S == 2) LCT_DG(2, 0, false);
+                    else LCT_DG(1, 0, false);
+                }
+            }
+            if (g.Npad > 16) {
+                uint32_t v[16];
+                tc::tmem_ld16(trow + 16u, v);
+                tc::tmem_ld_wait();
+                if (m < p.Mtot) {
+                    if (vec) LCT_DG(4, 16, true);
+                    else if (g.S == 4) LCT_DG(4, 16, false);
+                    else if (g.S == 3) LCT_DG(3, 16, false);
+                    else if (g.S == 2) LCT_DG(2, 16, false);
+                    else LCT_DG(1, 16, false);
+                }
+            }
+#undef LCT_DG
+        }
+        tc::fence_before_sync();
+        __syncthreads();                          // every warp has drained TMEM; the A planes may be overwritten
+        tc::fence_after_sync();
+        tile = next;
+    }
+    if (warp == 0) tc::tmem_dealloc<32>(tmem_base);
+}
+
+int g_tc_ctas_per_sm = 6;
+
+template <int MODE, int NQ, int NIT>
+int launch_conv(ConvParams& p, int G, cudaStream_t st) {
+    const size_t smem = 128 + (size_t)p.a_bytes + p.b_bytes + 2 * kMaxMma * 8 + 32 * 4 + 16;
+    if (smem > 200 * 1024) return LCT_EUNSUPPORTED;
+    auto kern = conv_tc_kernel<MODE, NQ, NIT>;
+    static bool attr_set = false;           // per instantiation
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem) != cudaSuccess || occ < 1) occ = 1;
+    if (occ > g_tc_ctas_per_sm) occ = g_tc_ctas_per_sm;
+    int gy = 148 * occ / G;                 // persistent: one wave of resident CTAs
+    if (gy > p.ntiles) gy = p.ntiles;
+    if (gy < 1) gy = 1;
+    if (gy > 65535) gy = 65535;
+    kern<<<dim3((unsigned)G, (unsigned)gy), kThreads, smem, st>>>(p);
+    LCT_RETURN_IF_LAUNCH_FAILED();
+    return 0;
+}
+
+// fill the staging map + shared-memory sizes; returns the NIT needed (0 if unsupported)
+int setup_conv(ConvParams& p, const Geom& g, const float* src, int Csrc, int Ls) {
+    p.g = g;
+    SrcMap& a = p.a;
+    a.src = src; a.C = Csrc; a.Ls = Ls; a.P = g.P;
+    a.Sg = g.mode == MODE_FWD ? g.S : 1;
+    a.ishift = g.mode == MODE_FWD ? -g.pad : g.o_min;
+    a.nch = g.ca;
+    a.nslots = kTileM + g.tapmax * g.P;
+    const int padmod = a.Sg == 4 ? 32 : (a.Sg == 3 ? 48 : (a.Sg == 2 ? 64 : 0));   // spreads the planes over the banks
+    a.PP = ((a.nslots * 16 + 127) & ~127) + padmod;
+    a.fP = make_fdiv(g.P); a.fS = make_fdiv(a.Sg);
+    p.a_bytes = (g.nphase * g.nqa * a.PP + 127) & ~127;
+    p.b_bytes = g.nmma * g.Npad * 32;
+    // elements per tile and channel: Sg * rows * P with rows <= ceil((P - 1 + nslots) / P)
+    const int rows = (g.P - 1 + a.nslots + g.P - 1) / g.P;
+    const int nE = a.Sg * rows * g.P;
+    return (nE + kThreads - 1) / kThreads;
+}
+
+template <int MODE>
+int dispatch_conv(ConvParams& p, int G, int nit, cudaStream_t st) {
+    const int nq = p.g.nqa;
+    if (nit <= 2) {
+        if (nq == 1) return launch_conv<MODE, 1, 2>(p, G, st);
+        if (nq == 2) return launch_conv<MODE, 2, 2>(p, G, st);
+        if (nq == 4) return launch_conv<MODE, 4, 2>(p, G, st);
+        if (nq == 8) return launch_conv<MODE, 8, 2>(p, G, st);
+    } else if (nit <= 3) {
+        if (nq == 1) return launch_conv<MODE, 1, 3>(p, G, st);
+        if (nq == 2) return launch_conv<MODE, 2, 3>(p, G, st);
+        if (nq == 4) return launch_conv<MODE, 4, 3>(p, G, st);
+        if (nq == 8) return launch_conv<MODE, 8, 3>(p, G, st);
+    } else if (nit <= 5) {
+        if (nq == 1) return launch_conv<MODE, 1, 5>(p, G, st);
+        if (nq == 2) return launch_conv<MODE, 2, 5>(p, G, st);
+        if (nq == 4) return launch_conv<MODE, 4, 5>(p, G, st);
+    }
+    return LCT_EUNSUPPORTED;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// weight gradient
+// ---------------------------------------------------------------------------------------------------------
+struct WgradParams {
+    Geom g;                  // the FORWARD geometry of the layer (phases / taps of x)
+    SrcMap x, dy;
+    float* dw;               // [Cout][cig][K], accumulated
+    float* db;               // [Cout] (optional), accumulated
+    int B, Cin, Cout, Lin, Lout, Mtot;
+    int tiles_per_b, ntiles;
+    int x_bytes, dy_bytes;
+    int nqd, N;              // channel quads of dY per group; MMA N = Cout/G rounded up to 8
+    FastDiv fT;
+};
+
+// like stage_store, for the dY tile, + per-thread bias-gradient partial sums (fp32, before rounding)
+template <int NQ, int NIT>
+__device__ __forceinline__ void stage_store_dy(const Staged<NQ, NIT>& R, const SrcMap& s, uint8_t* base, int m0,
+                                               float (&dbacc)[NQ * 4]) {
+    const int u0 = fdiv(m0, s.fP), p0 = m0 - u0 * s.P;
+    const int nrows = fdiv(p0 + s.nslots + s.P - 1, s.fP);
+    const int nE = nrows * s.P;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        const int e = (int)threadIdx.x + kThreads * it;
+        const int j = e - p0;
+        if (e < nE && j >= 0 && j < s.nslots) {
+            uint8_t* dst = base + (size_t)j * 16;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                *reinterpret_cast<float4*>(dst + (size_t)q * s.PP) =
+                    make_float4(tc::tf32_rna(R.v[it][4 * q]), tc::tf32_rna(R.v[it][4 * q + 1]),
+                                tc::tf32_rna(R.v[it][4 * q + 2]), tc::tf32_rna(R.v[it][4 * q + 3]));
+#pragma unroll
+                for (int c = 0; c < 4; ++c) dbacc[4 * q + c] += R.v[it][4 * q + c];
+            }
+        }
+    }
+}
+
+template <int NQX, int NITX, int NQD, int TCOLS>
+__global__ void __launch_bounds__(kThreads) conv_tc_wgrad_kernel(const WgradParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* X = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    uint8_t* DY = X + p.x_bytes;
+    float* dbs = reinterpret_cast<float*>(DY + p.dy_bytes);     // [32]
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(dbs + 32);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+
+    const Geom& g = p.g;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = blockIdx.x;
+    if (threadIdx.x == 0) {
+        tc::mbar_init(mbar, 1);
+        tc::mbar_fence_init();
+    }
+    if (warp == 0) tc::tmem_alloc<TCOLS>(tmem_slot);
+    if (threadIdx.x < 32) dbs[threadIdx.x] = 0.f;
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    // M = 64 (16 tap slots x 4 channels of one quad), N = p.N output channels, both operands MN-major
+    const uint32_t idesc = tc::idesc_tf32(64, p.N, 1, 1);
+    const uint32_t x_addr = tc::smem_u32(X), dy_addr = tc::smem_u32(DY);
+    const uint32_t sbo_x = (uint32_t)(g.P * 16);                       // next tap of the phase = P slots further
+    const uint32_t sbo_dy = NQD > 1 ? (uint32_t)p.dy.PP : 0u;          // next channel quad (one quad: N blocks alias it)
+    const int nacc = g.S * NQX;
+
+    Staged<NQX, NITX> Rx;
+    Staged<NQD, 2> Rd;
+    float dbacc[NQD * 4];
+#pragma unroll
+    for (int c = 0; c < NQD * 4; ++c) dbacc[c] = 0.f;
+
+    int tile = blockIdx.y;
+    uint32_t phase = 0;
+    bool first = true;
+    if (tile < p.ntiles) {
+        const int b = fdiv(tile, p.fT);
+        const int m0 = (tile - b * p.tiles_per_b) * kTileM;
+        stage_load<NQX, NITX>(Rx, p.x, b, grp * g.cig, m0);
+        stage_load<NQD, 2>(Rd, p.dy, b, grp * g.cog, m0);
+    }
+    while (tile < p.ntiles) {
+        const int b = fdiv(tile, p.fT);
+        const int m0 = (tile - b * p.tiles_per_b) * kTileM;
+        stage_store<NQX, NITX>(Rx, p.x, X, m0);
+        stage_store_dy<NQD, 2>(Rd, p.dy, DY, m0, dbacc);
+        tc::fence_proxy_async_smem();
+        __syncthreads();
+        const int next = tile + gridDim.y;
+        if (next < p.ntiles) {
+            const int nb = fdiv(next, p.fT);
+            const int nm0 = (next - nb * p.tiles_per_b) * kTileM;
+            stage_load<NQX, NITX>(Rx, p.x, nb, grp * g.cig, nm0);
+            stage_load<NQD, 2>(Rd, p.dy, nb, grp * g.cog, nm0);
+        }
+        if (threadIdx.x == 0) {
+            tc::fence_after_sync();
+            for (int a = 0; a < nacc; ++a) {                 // accumulator a = (phase rho, x quad): plane index a
+                const uint64_t dx0 = tc::smem_desc(x_addr + (uint32_t)(a * p.x.PP), 0, sbo_x);
+                const uint64_t dd0 = tc::smem_desc(dy_addr, 0, sbo_dy);
+                const uint32_t tcol = tmem_base + (uint32_t)(a * p.N);
+#pragma unroll 4
+                for (int ks = 0; ks < kTileM / 8; ++ks)      // 8 positions per MMA: + 8 slots = + 128 bytes (>> 4 = 8)
+                    tc::umma_tf32(tcol, dx0 + (uint64_t)(8 * ks), dd0 + (uint64_t)(8 * ks), idesc,
+                                  (uint32_t)(!(first && ks == 0)));
+            }
+            tc::umma_commit(mbar);
+        }
+        first = false;
+        tc::mbar_wait(mbar, phase);              // the MMAs have consumed this tile's planes
+        phase ^= 1;
+        tile = next;
+    }
+    tc::fence_after_sync();
+
+    // ---- flush: accumulator rows live in lanes 0..15 of every 32-lane quadrant (M = 64 data-path layout):
+    // row = 16 * warp + lane = 4 * tap + channel-in-quad
+    if (!first) {
+        const int tap = 4 * warp + (lane >> 2), e = lane & 3;
+        for (int a = 0; a < nacc; ++a) {
+            const int rho = a / NQX, qx = a - rho * NQX;
+            const int ci = 4 * qx + e, k = g.S * tap + rho;
+            const bool rowok = lane < 16 && tap < g.ntap[rho] && ci < g.cig;
+            for (int c0 = 0; c0 < p.N; c0 += 8) {
+                uint32_t v[8];
+                tc::tmem_ld8(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * p.N + c0), v);
+                tc::tmem_ld_wait();
+                if (rowok) {
+#pragma unroll
+                    for (int n = 0; n < 8; ++n)
+                        if (c0 + n < g.cog)
+                            atomicAdd(p.dw + ((int64_t)(grp * g.cog + c0 + n) * g.cig + ci) * g.K + k, __uint_as_float(v[n]));
+                }
+            }
+        }
+        if (p.db) {
+#pragma unroll
+            for (int c = 0; c < NQD * 4; ++c) {
+                const float sum = warp_sum(dbacc[c]);
+                if (lane == 0 && c < g.cog) atomicAdd(&dbs[c], sum);
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (!first && p.db && threadIdx.x < g.cog) atomicAdd(p.db + grp * g.cog + threadIdx.x, dbs[threadIdx.x]);
+    if (warp == 0) {
+        tc::fence_after_sync();
+        tc::tmem_dealloc<TCOLS>(tmem_base);
+    }
+}
+
+int g_tc_wgrad_ctas_per_sm = 2;
+
+template <int NQX, int NITX, int NQD, int TCOLS>
+int launch_wgrad(WgradParams& p, int G, cudaStream_t st) {
+    const size_t smem = 128 + (size_t)p.x_bytes + p.dy_bytes + 32 * 4 + 16;
+    if (smem > 200 * 1024) return LCT_EUNSUPPORTED;
+    auto kern = conv_tc_wgrad_kernel<NQX, NITX, NQD, TCOLS>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem) != cudaSuccess || occ < 1) occ = 1;
+    if (occ > 512 / TCOLS) occ = 512 / TCOLS;          // TMEM columns are a per-SM resource too
+    if (occ > g_tc_wgrad_ctas_per_sm) occ = g_tc_wgrad_ctas_per_sm;
+    int gy = 148 * occ / G;
+    if (gy > p.ntiles) gy = p.ntiles;
+    if (gy < 1) gy = 1;
+    if (gy > 65535) gy = 65535;
+    kern<<<dim3((unsigned)G, (unsigned)gy), kThreads, smem, st>>>(p);
+    LCT_RETURN_IF_LAUNCH_FAILED();
+    return 0;
+}
+
+bool dims_ok(int64_t B, int64_t Cin, int64_t Cout, int64_t Lin, int64_t Lout, int64_t P) {
+    return B > 0 && B < 65536 && Lin > 0 && Lout > 0 && Lin * P < (1LL << 19) && B * Cin * Lin * P < (1LL << 31) &&
+           B * Cout * Lout * P < (1LL << 31);
+}
+
+}  // namespace
+
+// 1 if the tcgen05 kernels cover this layer (grouped / first layers of the MPD and MSD stacks)
+LCT_API int lct_conv_tc_supported(int64_t Cin, int64_t Cout, int64_t G, int64_t K, int64_t S, int64_t P) {
+    Geom gf, gd;
+    if (!make_geom(gf, MODE_FWD, Cin, Cout, G, K, S, K / 2, P) || !make_geom(gd, MODE_DGRAD, Cin, Cout, G, K, S, K / 2, P))
+        return 0;
+    ConvParams p = {};
+    if (setup_conv(p, gf, nullptr, 0, 1) > 5 || setup_conv(p, gd, nullptr, 0, 1) > 5) return 0;
+    if (gd.nqa == 8 && setup_conv(p, gd, nullptr, 0, 1) > 3) return 0;
+    return 1;
+}
+
+// floats of the per-layer weight image: out[0] forward, out[1] data gradient (HOST pointer)
+LCT_API int lct_conv_tc_image_len(int64_t Cin, int64_t Cout, int64_t G, int64_t K, int64_t S, int64_t P, int64_t* out) {
+    Geom gf, gd;
+    if (!out || !make_geom(gf, MODE_FWD, Cin, Cout, G, K, S, K / 2, P) || !make_geom(gd, MODE_DGRAD, Cin, Cout, G, K, S, K / 2, P))
+        return LCT_EINVAL;
+    out[0] = G * (int64_t)gf.nmma * gf.Npad * 8;
+    out[1] = G * (int64_t)gd.nmma * gd.Npad * 8;
+    return 0;
+}
+
+// Build the forward (img_f[i]) and / or data-gradient (img_d[i]) images of n <= 8 layers in one launch.
+// w[i]: fp32 [Cout][Cin/G][K]; geo: HOST array of 6 int64 per layer (Cin, Cout, G, K, S, P); NULL image = skip.
+LCT_API int lct_conv_tc_images(const void* const* w, void* const* img_f, void* const* img_d, const int64_t* geo,
+                               int64_t n, cudaStream_t st) {
+    if (!w || !geo || n <= 0 || 2 * n > kMaxImgJobs) return LCT_EINVAL;
+    ImgJobs J;
+    J.n = 0;
+    int64_t maxtot = 0;
+    for (int i = 0; i < n; ++i) {
+        const int64_t* q = geo + 6 * i;
+        for (int mode = 0; mode < 2; ++mode) {
+            void* img = mode == MODE_FWD ? (img_f ? img_f[i] : nullptr) : (img_d ? img_d[i] : nullptr);
+            if (!img) continue;
+            if (!w[i]) return LCT_EINVAL;
+            ImgJob& jb = J.job[J.n];
+            if (!make_geom(jb.g, mode, q[0], q[1], q[2], q[3], q[4], q[3] / 2, q[5])) return LCT_EINVAL;
+            jb.w = (const float*)w[i]; jb.img = (float*)img; jb.G = (int)q[2];
+            const int64_t tot = q[2] * (int64_t)jb.g.nmma * jb.g.Npad * 8;
+            if (tot > maxtot) maxtot = tot;
+            ++J.n;
+        }
+    }
+    if (J.n == 0) return 0;
+    int gx = (int)ceil_div64(maxtot, 256 * 4);
+    if (gx > 592) gx = 592;
+    if (gx < 1) gx = 1;
+    tc_image_kernel<<<dim3((unsigned)gx, (unsigned)J.n), 256, 0, st>>>(J);
+    LCT_RETURN_IF_LAUNCH_FAILED();
+    return 0;
+}
+
+LCT_API int lct_conv_tc_fwd(const float* x, const float* wimg, const float* bias, float* y, int64_t B, int64_t Cin,
+                            int64_t Cout, int64_t G, int64_t K, int64_t S, int64_t pad, int64_t Lin, int64_t P, int act,
+                            float slope, cudaStream_t st) {
+    Geom g;
+    if (!x || !wimg || !y || !make_geom(g, MODE_FWD, Cin, Cout, G, K, S, pad, P)) return LCT_EINVAL;
+    const int64_t Lout = (Lin + 2 * pad - K) / S + 1;
+    if (Lin + 2 * pad < K || !dims_ok(B, Cin, Cout, Lin, Lout, P)) return LCT_EINVAL;
+    ConvParams p = {};
+    const int nit = setup_conv(p, g, x, (int)Cin, (int)Lin);
+    p.wimg = wimg; p.out = y; p.bias = bias; p.act = act; p.slope = slope;
+    p.B = (int)B; p.Cin = (int)Cin; p.Cout = (int)Cout; p.Lin = (int)Lin; p.Lout = (int)Lout;
+    p.Mtot = (int)(Lout * P);
+    p.tiles_per_b = (p.Mtot + kTileM - 1) / kTileM;
+    p.ntiles = p.B * p.tiles_per_b;
+    p.fT = make_fdiv(p.tiles_per_b);
+    if (p.ntiles >= (1 << 20)) return LCT_EUNSUPPORTED;
+    return dispatch_conv<MODE_FWD>(p, (int)G, nit, st);
+}
+
+LCT_API int lct_conv_tc_dgrad(const float* dy, const float* wimg, float* dx, const float* gextra, const float* xact,
+                              int64_t B, int64_t Cin, int64_t Cout, int64_t G, int64_t K, int64_t S, int64_t pad,
+                              int64_t Lin, int64_t P, int act, float slope, cudaStream_t st) {
+    Geom g;
+    if (!dy || !wimg || !dx || !make_geom(g, MODE_DGRAD, Cin, Cout, G, K, S, pad, P)) return LCT_EINVAL;
+    const int64_t Lout = (Lin + 2 * pad - K) / S + 1;
+    if (Lin + 2 * pad < K || !dims_ok(B, Cin, Cout, Lin, Lout, P)) return LCT_EINVAL;
+    ConvParams p = {};
+    const int nit = setup_conv(p, g, dy, (int)Cout, (int)Lout);
+    p.wimg = wimg; p.out = dx; p.gextra = gextra; p.xact = xact; p.act = act; p.slope = slope;
+    p.B = (int)B; p.Cin = (int)Cin; p.Cout = (int)Cout; p.Lin = (int)Lin; p.Lout = (int)Lout;
+    p.Mtot = (int)(((Lin + S - 1) / S) * P);
+    p.vec_ok = (((uintptr_t)dx | (uintptr_t)gextra | (uintptr_t)xact) & 15) == 0;
+    p.tiles_per_b = (p.Mtot + kTileM - 1) / kTileM;
+    p.ntiles = p.B * p.tiles_per_b;
+    p.fT = make_fdiv(p.tiles_per_b);
+    if (p.ntiles >= (1 << 20)) return LCT_EUNSUPPORTED;
+    return dispatch_conv<MODE_DGRAD>(p, (int)G, nit, st);
+}
+
+// dw [Cout][Cin/G][K] and db [Cout] (optional) are ACCUMULATED (the caller zeroes them): one atomic per weight and CTA
+LCT_API int lct_conv_tc_wgrad(const float* x, const float* dy, float* dw, float* db, int64_t B, int64_t Cin, int64_t Cout,
+                              int64_t G, int64_t K, int64_t S, int64_t pad, int64_t Lin, int64_t P, cudaStream_t st) {
+    Geom g;
+    if (!x || !dy || !dw || !make_geom(g, MODE_FWD, Cin, Cout, G, K, S, pad, P)) return LCT_EINVAL;
+    const int64_t Lout = (Lin + 2 * pad - K) / S + 1;
+    if (Lin + 2 * pad < K || !dims_ok(B, Cin, Cout, Lin, Lout, P)) return LCT_EINVAL;
+    int tapmax = 0;
+    for (int r = 0; r < g.S; ++r) tapmax = g.ntap[r] > tapmax ? g.ntap[r] : tapmax;
+    if (tapmax > 16) return LCT_EUNSUPPORTED;           // M = 64 = 16 tap slots x one channel quad
+    WgradParams p = {};
+    p.g = g;
+    p.dw = dw; p.db = db;
+    p.B = (int)B; p.Cin = (int)Cin; p.Cout = (int)Cout; p.Lin = (int)Lin; p.Lout = (int)Lout;
+    p.Mtot = (int)(Lout * P);
+    p.tiles_per_b = (p.Mtot + kTileM - 1) / kTileM;
+    p.ntiles = p.B * p.tiles_per_b;
+    p.fT = make_fdiv(p.tiles_per_b);
+    if (p.ntiles >= (1 << 20)) return LCT_EUNSUPPORTED;
+    // x planes [rho][quad]: filled up to the taps that exist, allocated for the 16 tap slots an M = 64 operand spans
+    SrcMap& sx = p.x;
+    sx.src = x; sx.C = (int)Cin; sx.Ls = (int)Lin; sx.P = g.P; sx.Sg = g.S; sx.ishift = -g.pad; sx.nch = g.cig;
+    sx.nslots = kTileM + tapmax * g.P;
+    const int padmod = g.S == 4 ? 32 : (g.S == 3 ? 48 : (g.S == 2 ? 64 : 0));
+    sx.PP = (((kTileM + 16 * g.P) * 16 + 127) & ~127) + padmod;
+    sx.fP = make_fdiv(g.P); sx.fS = make_fdiv(g.S);
+    p.x_bytes = (g.S * g.nqa * sx.PP + 127) & ~127;
+    const int rows = (g.P - 1 + sx.nslots + g.P - 1) / g.P;
+    const int nitx = (g.S * rows * g.P + kThreads - 1) / kThreads;
+    // dY planes [quad]: 128 slots
+    SrcMap& sd = p.dy;
+    sd.src = dy; sd.C = (int)Cout; sd.Ls = (int)Lout; sd.P = g.P; sd.Sg = 1; sd.ishift = 0; sd.nch = g.cog;
+    sd.nslots = kTileM; sd.PP = kTileM * 16; sd.fP = make_fdiv(g.P); sd.fS = make_fdiv(1);
+    p.nqd = (g.cog + 3) / 4;
+    p.N = (g.cog + 7) & ~7;
+    p.dy_bytes = (p.nqd > 2 ? p.nqd : 2) * sd.PP;
+    const int rowsd = (g.P - 1 + kTileM + g.P - 1) / g.P;
+    if (rowsd * g.P > 2 * kThreads) return LCT_EUNSUPPORTED;
+    const int tcols = g.S * g.nqa * p.N;
+    const int nqx = g.nqa;
+#define LCT_WG(NQXV, NITV, NQDV, TC) return launch_wgrad<NQXV, NITV, NQDV, TC>(p, (int)G, st)
+    if (nqx == 1 && p.nqd == 4 && nitx <= 2 && tcols <= 32) LCT_WG(1, 2, 4, 32);
+    if (nqx == 1 && p.nqd == 4 && nitx <= 5 && tcols <= 64) LCT_WG(1, 5, 4, 64);
+    if (nqx == 1 && p.nqd == 1 && nitx <= 5 && tcols <= 32) LCT_WG(1, 5, 1, 32);
+    if (nqx == 1 && p.nqd == 8 && nitx <= 5 && tcols <= 128) LCT_WG(1, 5, 8, 128);
+    if (nqx == 2 && p.nqd == 8 && nitx <= 5 && tcols <= 256) LCT_WG(2, 5, 8, 256);
+    if (nqx == 2 && p.nqd == 4 && nitx <= 5 && tcols <= 128) LCT_WG(2, 5, 4, 128);
+    if (nqx == 4 && p.nqd == 4 && nitx <= 2 && tcols <= 64) LCT_WG(4, 2, 4, 64);
+#undef LCT_WG
+    return LCT_EUNSUPPORTED;
+}

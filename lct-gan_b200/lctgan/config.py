@@ -6,6 +6,12 @@
 dense_tensor_cores = True
 
 
+#: Tensor-core mode only: the grouped / first-layer discriminator convolutions on tcgen05 (conv_tc.cu: UMMA kind::tf32,
+#: operands read from shared memory through descriptors, accumulators in TMEM).  False = the round-1 TF32 mma.sync
+#: kernels (conv_mma.cu), kept for A/B measurements.
+grouped_conv_tcgen05 = True
+
+
 def set_precision(mode: str) -> None:
     """"bf16": tensor-core paths (default): tcgen05 bf16 dense contraction, TF32 grouped discriminator convolutions,
     3xTF32 (error-compensated, ~fp32 accuracy) generator GEMMs / convolutions; "fp32": fp32 SIMT kernels only."""

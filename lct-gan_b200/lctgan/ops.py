@@ -266,10 +266,76 @@ def weight_norm_bwd(g, v, dw):
     return dg, dv
 
 
+def _use_tc(cin, cout, k, groups, stride, pad, P):
+    """Grouped / first layers go to the tcgen05 TF32 kernels (conv_tc.cu) in tensor-core mode."""
+    return (config.dense_tensor_cores and config.grouped_conv_tcgen05 and pad == k // 2 and
+            bool(call_ret("lct_conv_tc_supported", cin, cout, groups, k, stride, P)))
+
+
 def _use_mma(cin, cout, k, groups, stride, pad, P):
-    """Grouped layers go to the TF32 tensor-core kernels unless exact-fp32 mode is selected."""
-    return (config.dense_tensor_cores and pad == k // 2 and
+    """The round-1 TF32 mma.sync kernels (conv_mma.cu): only when the tcgen05 path is switched off."""
+    return (config.dense_tensor_cores and not config.grouped_conv_tcgen05 and pad == k // 2 and
             bool(call_ret("lct_conv_mma_supported", cin, cout, groups, k, stride, P)))
+
+
+def conv_tc_images(ws, specs, P, want_f=True, want_d=True):
+    """Weight images of the tcgen05 grouped convolutions for the layers of one stack that those kernels cover, ONE
+    launch: ws[i] [Cout, Cin/G, K] normalised weights, specs[i] = (k, stride, pad, groups).  Returns (imgs_f, imgs_d)
+    with None for the layers that run elsewhere (conv_post, the dense layer)."""
+    n = len(ws)
+    imgs_f, imgs_d = [None] * n, [None] * n
+    idx, shapes = [], []
+    buf = (ctypes.c_int64 * 2)()
+    for i, (k, s, pad, g) in enumerate(specs):
+        cout, cig = ws[i].shape[0], ws[i].shape[1]
+        if not _use_tc(cig * g, cout, k, g, s, pad, P) or _is_post(cout, k, g, s, pad):
+            continue
+        call_ret("lct_conv_tc_image_len", cig * g, cout, g, k, s, P, buf)
+        idx.append(i)
+        shapes += [(int(buf[0]),), (int(buf[1]),)]
+    if not idx:
+        return imgs_f, imgs_d
+    views = _flat_views(shapes, ws[0].device)
+    maxn = 8
+    for c0 in range(0, len(idx), maxn):
+        part = idx[c0:c0 + maxn]
+        geo = []
+        for i in part:
+            k, s, pad, g = specs[i]
+            geo += [ws[i].shape[1] * g, ws[i].shape[0], g, k, s, P]
+        f = [views[2 * (c0 + j)] if want_f else None for j in range(len(part))]
+        d = [views[2 * (c0 + j) + 1] if want_d else None for j in range(len(part))]
+        arr = lambda ts: (ctypes.c_void_p * len(ts))(*[t.data_ptr() if t is not None else None for t in ts])
+        call("lct_conv_tc_images", _ptr_array([ws[i].contiguous() for i in part]), arr(f), arr(d),
+             (ctypes.c_int64 * len(geo))(*geo), len(part))
+        for j, i in enumerate(part):
+            imgs_f[i], imgs_d[i] = f[j], d[j]
+    return imgs_f, imgs_d
+
+
+def conv_tc_fwd(x, img, bias, Cout, groups, K, stride, pad, act=ACT_NONE, slope=0.2):
+    B, Cin, Lin, P = x.shape
+    y = torch.empty(B, Cout, conv_out_len(Lin, K, stride, pad), P, dtype=torch.float32, device=x.device)
+    call("lct_conv_tc_fwd", x, img, bias, y, B, Cin, Cout, groups, K, stride, pad, Lin, P, act, slope)
+    return y
+
+
+def conv_tc_dgrad(dy, img_d, x_shape, Cout, groups, K, stride, pad, gextra=None, xact=None, act=ACT_NONE, slope=0.2):
+    B, Cin, Lin, P = x_shape
+    dx = torch.empty(B, Cin, Lin, P, dtype=torch.float32, device=dy.device)
+    call("lct_conv_tc_dgrad", dy, img_d, dx, gextra, xact, B, Cin, Cout, groups, K, stride, pad, Lin, P, act, slope)
+    return dx
+
+
+def conv_tc_wgrad(x, dy, w_shape, groups, stride, pad, dw=None, db=None, want_bias=True):
+    B, Cin, Lin, P = x.shape
+    Cout, K = w_shape[0], w_shape[2]
+    if dw is None:
+        dw = zeros(tuple(w_shape), x.device)
+    if db is None and want_bias:
+        db = zeros((Cout,), x.device)
+    call("lct_conv_tc_wgrad", x, dy, dw, db, B, Cin, Cout, groups, K, stride, pad, Lin, P)
+    return dw, db
 
 
 def _is_post(cout, k, groups, stride, pad):
@@ -298,6 +364,10 @@ def mt_weight_norm_fwd(gs, vs, specs=None, P=1):
     rowlen = (ctypes.c_int64 * n)(*[v.numel() // v.shape[0] for v in vs])
     imgs_f, imgs_d = [None] * n, [None] * n
     pf = pd = geo = None
+    if specs is not None and config.dense_tensor_cores and config.grouped_conv_tcgen05:
+        call("lct_mt_weight_norm_fwd", _ptr_array(gs), _ptr_array(vs), _ptr_array(ws), rows, rowlen, None, None, None, n)
+        imgs_f, imgs_d = conv_tc_images(ws, specs, P)
+        return ws, imgs_f, imgs_d
     if specs is not None and config.dense_tensor_cores:
         shapes, idxs, geos = [], [], [0] * (8 * n)
         buf = (ctypes.c_int64 * 2)()
@@ -346,6 +416,10 @@ def conv1d_fwd(x, w, bias, groups, stride, pad, act=ACT_NONE, slope=0.2, wimg=No
         y = torch.empty(B, 1, Lin, P, dtype=torch.float32, device=x.device)
         call("lct_conv_post_fwd", x, w, bias, y, B, Cin, Lin, P, K)
         return y
+    if _use_tc(Cin, Cout, K, groups, stride, pad, P):
+        if wimg is None:
+            wimg = conv_tc_images([w.reshape(Cout, Cin // groups, K)], [(K, stride, pad, groups)], P, want_d=False)[0][0]
+        return conv_tc_fwd(x, wimg, bias, Cout, groups, K, stride, pad, act, slope)
     y = torch.empty(B, Cout, Lout, P, dtype=torch.float32, device=x.device)
     if _use_mma(Cin, Cout, K, groups, stride, pad, P):
         call("lct_conv_mma_fwd", x, w, wimg, bias, y, B, Cin, Cout, groups, K, stride, pad, Lin, P, act, slope)
@@ -360,6 +434,11 @@ def conv1d_dgrad(dy, w, x_shape, groups, stride, pad, gextra=None, xact=None, ac
     dx = torch.empty(B, Cin, Lin, P, dtype=torch.float32, device=dy.device)
     if _is_post(Cout, K, groups, stride, pad):
         call("lct_conv_post_dgrad", dy, w, dx, gextra, xact, B, Cin, Lin, P, K, act, slope)
+        return dx
+    if _use_tc(Cin, Cout, K, groups, stride, pad, P):
+        if wimg is None:
+            wimg = conv_tc_images([w.reshape(Cout, Cin // groups, K)], [(K, stride, pad, groups)], P, want_f=False)[1][0]
+        call("lct_conv_tc_dgrad", dy, wimg, dx, gextra, xact, B, Cin, Cout, groups, K, stride, pad, Lin, P, act, slope)
         return dx
     if _use_mma(Cin, Cout, K, groups, stride, pad, P):
         call("lct_conv_mma_dgrad", dy, w, wimg, dx, gextra, xact, B, Cin, Cout, groups, K, stride, pad, Lin, P, act, slope)
@@ -378,6 +457,9 @@ def conv1d_wgrad(x, dy, w_shape, groups, stride, pad, want_bias=True, dw=None, d
         db = zeros((Cout,), x.device)
     if _is_post(Cout, K, groups, stride, pad):
         call("lct_conv_post_wgrad", x, dy, dw, db, B, Cin, Lin, P, K)
+        return dw, db
+    if _use_tc(Cin, Cout, K, groups, stride, pad, P):
+        call("lct_conv_tc_wgrad", x, dy, dw, db, B, Cin, Cout, groups, K, stride, pad, Lin, P)
         return dw, db
     if _use_mma(Cin, Cout, K, groups, stride, pad, P):
         call("lct_conv_mma_wgrad", x, dy, dw, db, B, Cin, Cout, groups, K, stride, pad, Lin, P)

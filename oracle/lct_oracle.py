@@ -223,7 +223,9 @@ def gru_direction_aten(x, w_ih, w_hh, b_ih, b_hh, reverse=False):
     if reverse:
         x = x.flip(1)
     h0 = x.new_zeros(1, x.shape[0], w_hh.shape[1])
-    y, _ = torch._VF.gru(x, h0, [w_ih, w_hh, b_ih, b_hh], True, 1, 0.0, False, False, True)
+    # (train flag: no dropout here, so it changes nothing on the CPU; cuDNN's GRU only records what its backward needs
+    # in training mode - the oracle also runs on stock CUDA operators as bench.py's `--impl reference-cuda` comparator)
+    y, _ = torch._VF.gru(x, h0, [w_ih, w_hh, b_ih, b_hh], True, 1, 0.0, torch.is_grad_enabled(), False, True)
     return y.flip(1) if reverse else y
 
 
