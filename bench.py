@@ -462,6 +462,9 @@ def main():
     ap.add_argument("--no-defer-dead-d-grads", action="store_true", help="join the helper streams that finish the (never read) "
                     "discriminator parameter gradients of the G step inside the discriminators' backward instead of at the "
                     "end of the G phase")
+    ap.add_argument("--grouped-convs", default="tcgen05", choices=["tcgen05", "mma.sync"], help="A/B: grouped discriminator "
+                    "convolutions on the tcgen05 kernels (conv_tc.cu, default) or on the round-1 mma.sync kernels")
+    ap.add_argument("--tc-ctas", type=int, default=0, help="A/B: CTAs per SM of the persistent tcgen05 conv grids")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--profile-range", action="store_true", help="bracket the timed steps with cudaProfilerStart/Stop "
                     "(for `ncu --profile-from-start off`: the launch list of exactly the timed steps; never a bench value)")
@@ -483,7 +486,10 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    from lctgan import _lib
+    from lctgan import _lib, config
+    config.grouped_conv_tcgen05 = args.grouped_convs == "tcgen05"
+    if args.tc_ctas:
+        _lib.call_ret("lct_conv_tc_tune", args.tc_ctas)
     from lctgan.parallel import FlatGradAllReduce, broadcast_parameters
     from lctgan.training import (GraphedTrainStep, StepArgs, build_models, restore_state, snapshot_state,
                                  synthetic_batch, train_step)

@@ -176,46 +176,66 @@ struct SrcMap {
 template <int NQ, int NIT>
 struct Staged { float v[NIT][NQ * 4]; };
 
+__device__ __forceinline__ float ld_nc(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_global(float* p, float v) { asm volatile("st.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory"); }
+
+// Per-thread staging plan.  Element e = tid + 128 it of a tile is (source row ir = e / P, p = e % P), i.e. stride phase
+// rho = ir % Sg of plane row du = ir / Sg: none of this depends on the tile, only the tile's first slot p0 and its first
+// source position do.  So the divisions happen once per CTA; per tile and element remain two range checks.
+template <int NQ, int NIT>
+struct StagePlan {
+    int ir[NIT];        // source row of element it, relative to the tile's first source position
+    int jrel[NIT];      // du * P + p: slot of the element relative to slot -p0
+    int dst[NIT];       // byte offset of that slot in its plane: rho * NQ * PP + 16 jrel
+    __device__ __forceinline__ void init(const SrcMap& s) {
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int e = (int)threadIdx.x + kThreads * it;
+            const int r = fdiv(e, s.fP), pp = e - r * s.P;
+            const int du = fdiv(r, s.fS), rho = r - du * s.Sg;
+            ir[it] = r;
+            jrel[it] = du * s.P + pp;
+            dst[it] = rho * NQ * s.PP + 16 * jrel[it];
+        }
+    }
+};
+
 // issue the loads of one tile (coalesced: consecutive threads read consecutive floats of every channel row)
 template <int NQ, int NIT>
-__device__ __forceinline__ void stage_load(Staged<NQ, NIT>& R, const SrcMap& s, int b, int cbase, int m0) {
-    const int u0 = fdiv(m0, s.fP), p0 = m0 - u0 * s.P;
-    const int nrows = fdiv(p0 + s.nslots + s.P - 1, s.fP);
-    const int nE = s.Sg * nrows * s.P;
+__device__ __forceinline__ void stage_load(Staged<NQ, NIT>& R, const StagePlan<NQ, NIT>& pl, const SrcMap& s, int b,
+                                           int cbase, int m0) {
+    const int u0 = fdiv(m0, s.fP);
     const int ibase = s.Sg * u0 + s.ishift;
     const int64_t chs = (int64_t)s.Ls * s.P;
-    const float* row0 = s.src + ((int64_t)b * s.C + cbase) * chs + (int64_t)ibase * s.P;
+    const float* row0 = s.src + ((int64_t)b * s.C + cbase) * chs + (int64_t)ibase * s.P + threadIdx.x;
 #pragma unroll
     for (int it = 0; it < NIT; ++it) {
-        const int e = (int)threadIdx.x + kThreads * it;
-        const int ir = fdiv(e, s.fP);
-        const int i = ibase + ir;
-        const bool ok = e < nE && i >= 0 && i < s.Ls;
+        const bool ok = (unsigned)(ibase + pl.ir[it]) < (unsigned)s.Ls;
 #pragma unroll
-        for (int c = 0; c < NQ * 4; ++c) R.v[it][c] = (ok && c < s.nch) ? __ldg(row0 + c * chs + e) : 0.f;
+        for (int c = 0; c < NQ * 4; ++c)
+            R.v[it][c] = (ok && c < s.nch) ? ld_nc(row0 + c * chs + kThreads * it) : 0.f;
     }
 }
 
-// round to tf32 and store as float4 slots: plane (rho, q) at `base` + (rho * NQ + q) * PP, slot j at + 16 j
+// round to tf32 (one integer add: the tensor core ignores the 13 low mantissa bits) and store as float4 slots
 template <int NQ, int NIT>
-__device__ __forceinline__ void stage_store(const Staged<NQ, NIT>& R, const SrcMap& s, uint8_t* base, int m0) {
-    const int u0 = fdiv(m0, s.fP), p0 = m0 - u0 * s.P;
-    const int nrows = fdiv(p0 + s.nslots + s.P - 1, s.fP);
-    const int nE = s.Sg * nrows * s.P;
+__device__ __forceinline__ void stage_store(const Staged<NQ, NIT>& R, const StagePlan<NQ, NIT>& pl, const SrcMap& s,
+                                            uint8_t* base, int m0) {
+    const int p0 = m0 - fdiv(m0, s.fP) * s.P;
+    uint8_t* b0 = base - 16 * p0;
 #pragma unroll
     for (int it = 0; it < NIT; ++it) {
-        const int e = (int)threadIdx.x + kThreads * it;
-        const int ir = fdiv(e, s.fP);
-        const int p = e - ir * s.P;
-        const int du = fdiv(ir, s.fS), rho = ir - du * s.Sg;
-        const int j = du * s.P + p - p0;
-        if (e < nE && j >= 0 && j < s.nslots) {
-            uint8_t* dst = base + (size_t)(rho * NQ) * s.PP + (size_t)j * 16;
+        if ((unsigned)(pl.jrel[it] - p0) < (unsigned)s.nslots) {
+            uint8_t* dst = b0 + pl.dst[it];
 #pragma unroll
             for (int q = 0; q < NQ; ++q)
-                *reinterpret_cast<float4*>(dst + (size_t)q * s.PP) =
-                    make_float4(tc::tf32_rna(R.v[it][4 * q]), tc::tf32_rna(R.v[it][4 * q + 1]),
-                                tc::tf32_rna(R.v[it][4 * q + 2]), tc::tf32_rna(R.v[it][4 * q + 3]));
+                *reinterpret_cast<uint4*>(dst + q * s.PP) =
+                    make_uint4(__float_as_uint(R.v[it][4 * q]) + 0x1000u, __float_as_uint(R.v[it][4 * q + 1]) + 0x1000u,
+                               __float_as_uint(R.v[it][4 * q + 2]) + 0x1000u, __float_as_uint(R.v[it][4 * q + 3]) + 0x1000u);
         }
     }
 }
@@ -226,29 +246,28 @@ __device__ __forceinline__ void stage_store(const Staged<NQ, NIT>& R, const SrcM
 // data-gradient epilogue of 16 accumulator columns [C0, C0 + 16) of one tile row (q, p): column n = ci * S + r is
 // dX[ci][S q + r][p]; fused (+ FM gradient) x LeakyReLU'(saved activation).  S and C0 are compile-time so that the
 // column -> (ci, r) split costs nothing; VEC: S == 4, P == 1, 16-byte aligned rows -> one float4 per (row, channel).
+// o / ge / xa point at element (ci = 0, position S q, p) of dX / FM gradient / saved activation of this row.
 template <int S, int C0, bool VEC>
-__device__ __forceinline__ void dgrad_store16(const uint32_t (&v)[16], int ncol, int q, int Lin, int P, int64_t base,
-                                              int64_t chs, const float* __restrict__ gextra,
-                                              const float* __restrict__ xact, float* __restrict__ out, int act,
-                                              float slope) {
+__device__ __forceinline__ void dgrad_store16(const uint32_t (&v)[16], int ncol, int jrem, int P, int64_t chs,
+                                              float* o, const float* ge, const float* xa, float neg) {
     if (VEC) {
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
             const int col = C0 + 4 * c4;
             if (col < ncol) {
-                const int64_t idx = base + (int64_t)(col / 4) * chs;
+                const int64_t off = (int64_t)(col / 4) * chs;
                 float4 a = make_float4(__uint_as_float(v[4 * c4]), __uint_as_float(v[4 * c4 + 1]),
                                        __uint_as_float(v[4 * c4 + 2]), __uint_as_float(v[4 * c4 + 3]));
-                if (gextra) {
-                    const float4 ge = __ldcs(reinterpret_cast<const float4*>(gextra + idx));
-                    a.x += ge.x; a.y += ge.y; a.z += ge.z; a.w += ge.w;
+                if (ge) {
+                    const float4 g4 = __ldcs(reinterpret_cast<const float4*>(ge + off));
+                    a.x += g4.x; a.y += g4.y; a.z += g4.z; a.w += g4.w;
                 }
-                if (xact) {
-                    const float4 xa = __ldcs(reinterpret_cast<const float4*>(xact + idx));
-                    a.x *= act_grad_from_out(xa.x, act, slope); a.y *= act_grad_from_out(xa.y, act, slope);
-                    a.z *= act_grad_from_out(xa.z, act, slope); a.w *= act_grad_from_out(xa.w, act, slope);
+                if (xa) {
+                    const float4 x4 = __ldcs(reinterpret_cast<const float4*>(xa + off));
+                    a.x *= x4.x > 0.f ? 1.f : neg; a.y *= x4.y > 0.f ? 1.f : neg;
+                    a.z *= x4.z > 0.f ? 1.f : neg; a.w *= x4.w > 0.f ? 1.f : neg;
                 }
-                *reinterpret_cast<float4*>(out + idx) = a;
+                *reinterpret_cast<float4*>(o + off) = a;
             }
         }
         return;
@@ -257,13 +276,25 @@ __device__ __forceinline__ void dgrad_store16(const uint32_t (&v)[16], int ncol,
     for (int n = 0; n < 16; ++n) {
         const int col = C0 + n;
         const int ci = col / S, r = col - ci * S;       // compile-time after unrolling
-        if (col < ncol && S * q + r < Lin) {
-            const int64_t idx = base + (int64_t)ci * chs + (int64_t)r * P;
+        if (col < ncol && r < jrem) {                   // jrem = Lin - S q: positions left in this row of phases
+            const int64_t off = (int64_t)ci * chs + r * P;
             float a = __uint_as_float(v[n]);
-            if (gextra) a += gextra[idx];
-            if (xact) a *= act_grad_from_out(xact[idx], act, slope);
-            out[idx] = a;
+            if (ge) a += ld_nc(ge + off);
+            if (xa) a *= ld_nc(xa + off) > 0.f ? 1.f : neg;
+            st_global(o + off, a);
         }
+    }
+}
+
+// the same 16 columns written to the shared-memory staging tile instead: T[ci][(S (q - q0) + r) P + p] (t points at
+// row element r = 0 of channel 0; TS = floats per channel) - the coalesced pass over the tile follows
+template <int S, int C0>
+__device__ __forceinline__ void dgrad_stage16(const uint32_t (&v)[16], int ncol, float* t, int TS, int P) {
+#pragma unroll
+    for (int n = 0; n < 16; ++n) {
+        const int col = C0 + n;
+        const int ci = col / S, r = col - ci * S;
+        if (col < ncol) t[ci * TS + r * P] = __uint_as_float(v[n]);
     }
 }
 
@@ -277,9 +308,11 @@ struct ConvParams {
     const float* xact;       // dgrad (optional)
     int B, Cin, Cout, Lin, Lout;
     int Mtot;                // flat rows per batch (fwd: Lout * P; dgrad: ceil(Lin / S) * P)
+    int mtile;               // flat rows per tile: 128 (fwd); dgrad: whole rows of P only, (128 / P) * P
+    int TS;                  // dgrad: floats per channel of the staged output tile
     int tiles_per_b, ntiles;
     int a_bytes, b_bytes;    // shared-memory sizes of the A planes and of the weight image
-    int act; float slope;
+    float neg;               // slope of the activation for negative inputs: LeakyReLU slope, ReLU 0, none 1
     int vec_ok;              // dgrad: dx / gextra / xact are 16-byte aligned
     FastDiv fT;
 };
@@ -289,8 +322,8 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* A = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
     uint8_t* Bw = A + p.a_bytes;
-    uint64_t* descs = reinterpret_cast<uint64_t*>(Bw + p.b_bytes);     // [nmma][2]
-    float* bias_s = reinterpret_cast<float*>(descs + 2 * kMaxMma);     // [32]
+    uint4* descs = reinterpret_cast<uint4*>(Bw + p.b_bytes);           // [nmma] {A descriptor, B descriptor}
+    float* bias_s = reinterpret_cast<float*>(descs + kMaxMma);         // [32]
     uint64_t* mbar = reinterpret_cast<uint64_t*>(bias_s + 32);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
 
@@ -315,40 +348,48 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvParams p) {
         decode_mma(g, j, ph, tap, quad);
         const uint32_t a_addr = tc::smem_u32(A) + (uint32_t)((ph * g.nqa + quad) * p.a.PP + tap * g.P * 16);
         const uint32_t lbo = g.by_tap ? (uint32_t)(g.P * 16) : (uint32_t)p.a.PP;
-        descs[2 * j] = tc::smem_desc(a_addr, lbo, 128);
-        descs[2 * j + 1] = tc::smem_desc(tc::smem_u32(Bw) + (uint32_t)(j * g.Npad * 32), (uint32_t)(g.Npad * 16), 128);
+        const uint64_t da = tc::smem_desc(a_addr, lbo, 128);
+        const uint64_t db = tc::smem_desc(tc::smem_u32(Bw) + (uint32_t)(j * g.Npad * 32), (uint32_t)(g.Npad * 16), 128);
+        descs[j] = make_uint4((uint32_t)da, (uint32_t)(da >> 32), (uint32_t)db, (uint32_t)(db >> 32));
     }
     if (threadIdx.x < 32) {
         const int n = threadIdx.x;
         bias_s[n] = (MODE == MODE_FWD && p.bias && n < g.cog) ? p.bias[grp * g.cog + n] : 0.f;
     }
+    StagePlan<NQ, NIT> plan;
+    plan.init(p.a);
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t idesc = tc::idesc_tf32(kTileM, g.Npad, 0, 0);
+    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
 
     Staged<NQ, NIT> R;
     int tile = blockIdx.y;
     uint32_t phase = 0;
     if (tile < p.ntiles) {
         const int b = fdiv(tile, p.fT);
-        stage_load<NQ, NIT>(R, p.a, b, cbase_a, (tile - b * p.tiles_per_b) * kTileM);
+        stage_load<NQ, NIT>(R, plan, p.a, b, cbase_a, (tile - b * p.tiles_per_b) * p.mtile);
     }
     while (tile < p.ntiles) {
         const int b = fdiv(tile, p.fT);
-        const int m0 = (tile - b * p.tiles_per_b) * kTileM;
-        stage_store<NQ, NIT>(R, p.a, A, m0);
+        const int m0 = (tile - b * p.tiles_per_b) * p.mtile;
+        stage_store<NQ, NIT>(R, plan, p.a, A, m0);
         tc::fence_proxy_async_smem();            // st.shared (generic proxy) -> tcgen05.mma operand reads (async proxy)
         __syncthreads();
         const int next = tile + gridDim.y;
         if (next < p.ntiles) {                   // next tile's loads fly during this tile's MMAs and epilogue
             const int nb = fdiv(next, p.fT);
-            stage_load<NQ, NIT>(R, p.a, nb, cbase_a, (next - nb * p.tiles_per_b) * kTileM);
+            stage_load<NQ, NIT>(R, plan, p.a, nb, cbase_a, (next - nb * p.tiles_per_b) * p.mtile);
         }
         if (threadIdx.x == 0) {
             tc::fence_after_sync();
-            for (int j = 0; j < g.nmma; ++j) tc::umma_tf32(tmem_base, descs[2 * j], descs[2 * j + 1], idesc, (uint32_t)(j != 0));
+#pragma unroll 2
+            for (int j = 0; j < g.nmma; ++j) {
+                const uint4 d = descs[j];
+                tc::umma_tf32(tmem_base, ((uint64_t)d.y << 32) | d.x, ((uint64_t)d.w << 32) | d.z, idesc, (uint32_t)(j != 0));
+            }
             tc::umma_commit(mbar);
         }
         tc::mbar_wait(mbar, phase);
@@ -357,53 +398,105 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvParams p) {
 
         // ---- epilogue: TMEM lane = tile row
         const int m = m0 + warp * 32 + lane;
-        const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
         if (MODE == MODE_FWD) {
             const int64_t LoP = (int64_t)p.Mtot;
-            float* yb = p.out + ((int64_t)b * p.Cout + (int64_t)grp * g.cog) * LoP + m;
+            float* yp = p.out + ((int64_t)b * p.Cout + (int64_t)grp * g.cog) * LoP + m;
             for (int c0 = 0; c0 < g.Npad; c0 += 16) {
                 uint32_t v[16];
                 tc::tmem_ld16(trow + (uint32_t)c0, v);
                 tc::tmem_ld_wait();
                 if (m < p.Mtot) {
+                    const float4* b4 = reinterpret_cast<const float4*>(bias_s + c0);
+                    const int nval = g.cog - c0;
 #pragma unroll
-                    for (int n = 0; n < 16; ++n)
-                        if (c0 + n < g.cog)
-                            yb[(int64_t)(c0 + n) * LoP] = apply_act(__uint_as_float(v[n]) + bias_s[c0 + n], p.act, p.slope);
+                    for (int n4 = 0; n4 < 4; ++n4) {
+                        const float4 bb = b4[n4];
+                        const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int n = 4 * n4 + k;
+                            const float t = __uint_as_float(v[n]) + bv[k];
+                            if (n < nval) st_global(yp, t > 0.f ? t : t * p.neg);
+                            yp += LoP;
+                        }
+                    }
                 }
             }
         } else {
-            // row m = (q, p): dX[ci][S q + r][p] for the S phases r (columns n = ci * S + r)
-            const int q = fdiv(m, p.a.fP), pp = m - q * g.P;
+            // tile row ml = (q - q0, p) (dgrad tiles hold whole rows of P): dX[ci][S q + r][p] for the S phases r
+            const int ml = warp * 32 + lane;
+            const int qrel = fdiv(ml, p.a.fP), pp = ml - qrel * g.P;
+            const int q0 = fdiv(m0, p.a.fP);
+            const int q = q0 + qrel;
+            const bool rowok = ml < p.mtile && m0 + ml < p.Mtot;
             const int64_t chs = (int64_t)p.Lin * g.P;
-            const int64_t base = ((int64_t)b * p.Cin + (int64_t)grp * g.cig) * chs + (int64_t)(g.S * q) * g.P + pp;
+            const int64_t cb = ((int64_t)b * p.Cin + (int64_t)grp * g.cig) * chs;
             const bool vec = g.S == 4 && g.P == 1 && (p.Lin & 3) == 0 && p.vec_ok;
-#define LCT_DG(SV, C0V, VV) dgrad_store16<SV, C0V, VV>(v, g.ncol, q, p.Lin, g.P, base, chs, p.gextra, p.xact, p.out, p.act, p.slope)
-            {
+            if (vec) {
+                // one float4 (the 4 output phases) per row and channel: consecutive lanes, consecutive 16 bytes
+                const int64_t base = cb + (int64_t)(4 * q);
+                float* o = p.out + base;
+                const float* ge = p.gextra ? p.gextra + base : nullptr;
+                const float* xa = p.xact ? p.xact + base : nullptr;
                 uint32_t v[16];
                 tc::tmem_ld16(trow, v);
                 tc::tmem_ld_wait();
-                if (m < p.Mtot) {
-                    if (vec) LCT_DG(4, 0, true);
-                    else if (g.S == 4) LCT_DG(4, 0, false);
-                    else if (g.S == 3) LCT_DG(3, 0, false);
-                    else if (g.S == 2) LCT_DG(2, 0, false);
-                    else LCT_DG(1, 0, false);
+                if (rowok) dgrad_store16<4, 0, true>(v, g.ncol, 4, 1, chs, o, ge, xa, p.neg);
+                if (g.Npad > 16) {
+                    tc::tmem_ld16(trow + 16u, v);
+                    tc::tmem_ld_wait();
+                    if (rowok) dgrad_store16<4, 16, true>(v, g.ncol, 4, 1, chs, o, ge, xa, p.neg);
+                }
+            } else {
+                // stage the tile in shared memory (over the operand planes: their MMAs are complete), then one
+                // coalesced pass per channel over the contiguous run of S * rows * P outputs this tile owns
+                float* T = reinterpret_cast<float*>(A);
+                float* t = T + g.S * ml - (g.S - 1) * pp;
+#define LCT_DS(SV, C0V) dgrad_stage16<SV, C0V>(v, g.ncol, t, p.TS, g.P)
+                {
+                    uint32_t v[16];
+                    tc::tmem_ld16(trow, v);
+                    tc::tmem_ld_wait();
+                    if (rowok) {
+                        if (g.S == 4) LCT_DS(4, 0);
+                        else if (g.S == 3) LCT_DS(3, 0);
+                        else if (g.S == 2) LCT_DS(2, 0);
+                        else LCT_DS(1, 0);
+                    }
+                }
+                if (g.Npad > 16) {
+                    uint32_t v[16];
+                    tc::tmem_ld16(trow + 16u, v);
+                    tc::tmem_ld_wait();
+                    if (rowok) {
+                        if (g.S == 4) LCT_DS(4, 16);
+                        else if (g.S == 3) LCT_DS(3, 16);
+                        else if (g.S == 2) LCT_DS(2, 16);
+                        else LCT_DS(1, 16);
+                    }
+                }
+#undef LCT_DS
+                __syncthreads();
+                const int j0 = g.S * q0 * g.P;                                  // first output (flat) of the tile
+                int nval = g.S * p.mtile;                                       // = S * rows * P
+                if (nval > (int)chs - j0) nval = (int)chs - j0;
+                for (int ci = 0; ci < g.cig; ++ci) {                            // <= S <= 4 elements per thread and channel
+                    const int64_t ib = cb + (int64_t)ci * chs + j0 + (int)threadIdx.x;
+                    const float* trow_s = T + ci * p.TS + (int)threadIdx.x;
+                    float a[4], gv[4], xv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {                               // all loads first: 8 in flight per thread
+                        const bool ok = u * kThreads + (int)threadIdx.x < nval;
+                        a[u] = ok ? trow_s[u * kThreads] : 0.f;
+                        gv[u] = (ok && p.gextra) ? ld_nc(p.gextra + ib + u * kThreads) : 0.f;
+                        xv[u] = (ok && p.xact) ? ld_nc(p.xact + ib + u * kThreads) : 1.f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (u * kThreads + (int)threadIdx.x < nval)
+                            st_global(p.out + ib + u * kThreads, (a[u] + gv[u]) * (xv[u] > 0.f ? 1.f : p.neg));
                 }
             }
-            if (g.Npad > 16) {
-                uint32_t v[16];
-                tc::tmem_ld16(trow + 16u, v);
-                tc::tmem_ld_wait();
-                if (m < p.Mtot) {
-                    if (vec) LCT_DG(4, 16, true);
-                    else if (g.S == 4) LCT_DG(4, 16, false);
-                    else if (g.S == 3) LCT_DG(3, 16, false);
-                    else if (g.S == 2) LCT_DG(2, 16, false);
-                    else LCT_DG(1, 16, false);
-                }
-            }
-#undef LCT_DG
         }
         tc::fence_before_sync();
         __syncthreads();                          // every warp has drained TMEM; the A planes may be overwritten
@@ -414,10 +507,29 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvParams p) {
 }
 
 int g_tc_ctas_per_sm = 6;
+int g_tc_last_grid = 0;       // bring-up: CTAs of the last launch
+
+// Resident CTAs per SM of a 128-thread kernel, from its register count (queried once per instantiation), its dynamic
+// shared memory and its TMEM columns.  Computed by hand: cudaOccupancyMaxActiveBlocksPerMultiprocessor answered 1 on
+// the first call of an instantiation and while a stream was being captured (ncu: grids of 148 CTAs instead of 888).
+template <typename Kern>
+int resident_ctas(Kern kern, int& regs_cache, size_t smem, int tmem_cols) {
+    if (regs_cache == 0) {
+        cudaFuncAttributes fa;
+        regs_cache = (cudaFuncGetAttributes(&fa, kern) == cudaSuccess && fa.numRegs > 0) ? fa.numRegs : 128;
+        (void)cudaGetLastError();
+    }
+    const int regs = (regs_cache + 7) & ~7;                       // allocation granularity: 8 registers per thread
+    int occ = 65536 / (regs * kThreads);
+    const int by_smem = (int)((227 * 1024) / (smem + 1024));      // + 1 KB reserved per CTA
+    if (by_smem < occ) occ = by_smem;
+    if (512 / tmem_cols < occ) occ = 512 / tmem_cols;
+    return occ < 1 ? 1 : occ;
+}
 
 template <int MODE, int NQ, int NIT>
 int launch_conv(ConvParams& p, int G, cudaStream_t st) {
-    const size_t smem = 128 + (size_t)p.a_bytes + p.b_bytes + 2 * kMaxMma * 8 + 32 * 4 + 16;
+    const size_t smem = 128 + (size_t)p.a_bytes + p.b_bytes + kMaxMma * 16 + 32 * 4 + 16;
     if (smem > 200 * 1024) return LCT_EUNSUPPORTED;
     auto kern = conv_tc_kernel<MODE, NQ, NIT>;
     static bool attr_set = false;           // per instantiation
@@ -426,13 +538,14 @@ int launch_conv(ConvParams& p, int G, cudaStream_t st) {
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
-    int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem) != cudaSuccess || occ < 1) occ = 1;
+    static int regs = 0;
+    int occ = resident_ctas(kern, regs, smem, 32);
     if (occ > g_tc_ctas_per_sm) occ = g_tc_ctas_per_sm;
     int gy = 148 * occ / G;                 // persistent: one wave of resident CTAs
     if (gy > p.ntiles) gy = p.ntiles;
     if (gy < 1) gy = 1;
     if (gy > 65535) gy = 65535;
+    g_tc_last_grid = G * gy;
     kern<<<dim3((unsigned)G, (unsigned)gy), kThreads, smem, st>>>(p);
     LCT_RETURN_IF_LAUNCH_FAILED();
     return 0;
@@ -492,8 +605,25 @@ struct WgradParams {
     int tiles_per_b, ntiles;
     int x_bytes, dy_bytes;
     int nqd, N;              // channel quads of dY per group; MMA N = Cout/G rounded up to 8
+    float* dbg;              // bring-up: raw accumulators of group 0, CTA y = 0: [nacc][128 lanes][N]
     FastDiv fT;
 };
+
+// the dY tile (stride 1, one plane per quad): element e = tid + 128 it is slot e - p0
+template <int NQ, int NIT>
+__device__ __forceinline__ void stage_load_dy(Staged<NQ, NIT>& R, const SrcMap& s, int b, int cbase, int m0) {
+    const int u0 = fdiv(m0, s.fP);
+    const int64_t chs = (int64_t)s.Ls * s.P;
+    const int nE = s.Ls * s.P - u0 * s.P;                 // floats left in the channel row from the tile's first row
+    const float* row0 = s.src + ((int64_t)b * s.C + cbase) * chs + (int64_t)u0 * s.P + threadIdx.x;
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+        const bool ok = (int)threadIdx.x + kThreads * it < nE;
+#pragma unroll
+        for (int c = 0; c < NQ * 4; ++c)
+            R.v[it][c] = (ok && c < s.nch) ? ld_nc(row0 + c * chs + kThreads * it) : 0.f;
+    }
+}
 
 // like stage_store, for the dY tile, + per-thread bias-gradient partial sums (fp32, before rounding)
 template <int NQ, int NIT>
@@ -549,6 +679,8 @@ __global__ void __launch_bounds__(kThreads) conv_tc_wgrad_kernel(const WgradPara
     const uint32_t sbo_dy = NQD > 1 ? (uint32_t)p.dy.PP : 0u;          // next channel quad (one quad: N blocks alias it)
     const int nacc = g.S * NQX;
 
+    StagePlan<NQX, NITX> planx;
+    planx.init(p.x);
     Staged<NQX, NITX> Rx;
     Staged<NQD, 2> Rd;
     float dbacc[NQD * 4];
@@ -561,13 +693,13 @@ __global__ void __launch_bounds__(kThreads) conv_tc_wgrad_kernel(const WgradPara
     if (tile < p.ntiles) {
         const int b = fdiv(tile, p.fT);
         const int m0 = (tile - b * p.tiles_per_b) * kTileM;
-        stage_load<NQX, NITX>(Rx, p.x, b, grp * g.cig, m0);
-        stage_load<NQD, 2>(Rd, p.dy, b, grp * g.cog, m0);
+        stage_load<NQX, NITX>(Rx, planx, p.x, b, grp * g.cig, m0);
+        stage_load_dy<NQD, 2>(Rd, p.dy, b, grp * g.cog, m0);
     }
     while (tile < p.ntiles) {
         const int b = fdiv(tile, p.fT);
         const int m0 = (tile - b * p.tiles_per_b) * kTileM;
-        stage_store<NQX, NITX>(Rx, p.x, X, m0);
+        stage_store<NQX, NITX>(Rx, planx, p.x, X, m0);
         stage_store_dy<NQD, 2>(Rd, p.dy, DY, m0, dbacc);
         tc::fence_proxy_async_smem();
         __syncthreads();
@@ -575,14 +707,15 @@ __global__ void __launch_bounds__(kThreads) conv_tc_wgrad_kernel(const WgradPara
         if (next < p.ntiles) {
             const int nb = fdiv(next, p.fT);
             const int nm0 = (next - nb * p.tiles_per_b) * kTileM;
-            stage_load<NQX, NITX>(Rx, p.x, nb, grp * g.cig, nm0);
-            stage_load<NQD, 2>(Rd, p.dy, nb, grp * g.cog, nm0);
+            stage_load<NQX, NITX>(Rx, planx, p.x, nb, grp * g.cig, nm0);
+            stage_load_dy<NQD, 2>(Rd, p.dy, nb, grp * g.cog, nm0);
         }
         if (threadIdx.x == 0) {
             tc::fence_after_sync();
             for (int a = 0; a < nacc; ++a) {                 // accumulator a = (phase rho, x quad): plane index a
-                const uint64_t dx0 = tc::smem_desc(x_addr + (uint32_t)(a * p.x.PP), 0, sbo_x);
-                const uint64_t dd0 = tc::smem_desc(dy_addr, 0, sbo_dy);
+                // (one K group per MMA, so only the M / N block stride matters: it is written to BOTH offset fields)
+                const uint64_t dx0 = tc::smem_desc(x_addr + (uint32_t)(a * p.x.PP), sbo_x, sbo_x);
+                const uint64_t dd0 = tc::smem_desc(dy_addr, sbo_dy, sbo_dy);
                 const uint32_t tcol = tmem_base + (uint32_t)(a * p.N);
 #pragma unroll 4
                 for (int ks = 0; ks < kTileM / 8; ++ks)      // 8 positions per MMA: + 8 slots = + 128 bytes (>> 4 = 8)
@@ -600,6 +733,15 @@ __global__ void __launch_bounds__(kThreads) conv_tc_wgrad_kernel(const WgradPara
 
     // ---- flush: accumulator rows live in lanes 0..15 of every 32-lane quadrant (M = 64 data-path layout):
     // row = 16 * warp + lane = 4 * tap + channel-in-quad
+    if (!first && p.dbg && blockIdx.x == 0 && blockIdx.y == 0) {
+        for (int a = 0; a < nacc; ++a)
+            for (int c0 = 0; c0 < p.N; c0 += 8) {
+                uint32_t v[8];
+                tc::tmem_ld8(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * p.N + c0), v);
+                tc::tmem_ld_wait();
+                for (int n = 0; n < 8; ++n) p.dbg[((size_t)a * 128 + warp * 32 + lane) * p.N + c0 + n] = __uint_as_float(v[n]);
+            }
+    }
     if (!first) {
         const int tap = 4 * warp + (lane >> 2), e = lane & 3;
         for (int a = 0; a < nacc; ++a) {
@@ -636,6 +778,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_wgrad_kernel(const WgradPara
 }
 
 int g_tc_wgrad_ctas_per_sm = 2;
+float* g_tc_dbg = nullptr;
 
 template <int NQX, int NITX, int NQD, int TCOLS>
 int launch_wgrad(WgradParams& p, int G, cudaStream_t st) {
@@ -648,9 +791,8 @@ int launch_wgrad(WgradParams& p, int G, cudaStream_t st) {
         if (e != cudaSuccess) return (int)e;
         attr_set = true;
     }
-    int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem) != cudaSuccess || occ < 1) occ = 1;
-    if (occ > 512 / TCOLS) occ = 512 / TCOLS;          // TMEM columns are a per-SM resource too
+    static int regs = 0;
+    int occ = resident_ctas(kern, regs, smem, TCOLS);
     if (occ > g_tc_wgrad_ctas_per_sm) occ = g_tc_wgrad_ctas_per_sm;
     int gy = 148 * occ / G;
     if (gy > p.ntiles) gy = p.ntiles;
@@ -660,6 +802,8 @@ int launch_wgrad(WgradParams& p, int G, cudaStream_t st) {
     LCT_RETURN_IF_LAUNCH_FAILED();
     return 0;
 }
+
+float act_neg(int act, float slope) { return act == LCT_ACT_LRELU ? slope : (act == LCT_ACT_RELU ? 0.f : 1.f); }
 
 bool dims_ok(int64_t B, int64_t Cin, int64_t Cout, int64_t Lin, int64_t Lout, int64_t P) {
     return B > 0 && B < 65536 && Lin > 0 && Lout > 0 && Lin * P < (1LL << 19) && B * Cin * Lin * P < (1LL << 31) &&
@@ -729,9 +873,10 @@ LCT_API int lct_conv_tc_fwd(const float* x, const float* wimg, const float* bias
     if (Lin + 2 * pad < K || !dims_ok(B, Cin, Cout, Lin, Lout, P)) return LCT_EINVAL;
     ConvParams p = {};
     const int nit = setup_conv(p, g, x, (int)Cin, (int)Lin);
-    p.wimg = wimg; p.out = y; p.bias = bias; p.act = act; p.slope = slope;
+    p.wimg = wimg; p.out = y; p.bias = bias; p.neg = act_neg(act, slope);
     p.B = (int)B; p.Cin = (int)Cin; p.Cout = (int)Cout; p.Lin = (int)Lin; p.Lout = (int)Lout;
     p.Mtot = (int)(Lout * P);
+    p.mtile = kTileM;
     p.tiles_per_b = (p.Mtot + kTileM - 1) / kTileM;
     p.ntiles = p.B * p.tiles_per_b;
     p.fT = make_fdiv(p.tiles_per_b);
@@ -748,15 +893,28 @@ LCT_API int lct_conv_tc_dgrad(const float* dy, const float* wimg, float* dx, con
     if (Lin + 2 * pad < K || !dims_ok(B, Cin, Cout, Lin, Lout, P)) return LCT_EINVAL;
     ConvParams p = {};
     const int nit = setup_conv(p, g, dy, (int)Cout, (int)Lout);
-    p.wimg = wimg; p.out = dx; p.gextra = gextra; p.xact = xact; p.act = act; p.slope = slope;
+    p.wimg = wimg; p.out = dx; p.gextra = gextra; p.xact = xact; p.neg = act_neg(act, slope);
     p.B = (int)B; p.Cin = (int)Cin; p.Cout = (int)Cout; p.Lin = (int)Lin; p.Lout = (int)Lout;
     p.Mtot = (int)(((Lin + S - 1) / S) * P);
     p.vec_ok = (((uintptr_t)dx | (uintptr_t)gextra | (uintptr_t)xact) & 15) == 0;
-    p.tiles_per_b = (p.Mtot + kTileM - 1) / kTileM;
+    p.mtile = (kTileM / (int)P) * (int)P;             // whole rows of P: the tile's outputs are one contiguous run
+    p.TS = (int)S * p.mtile + 4;
+    if ((int)(Cin / G) * p.TS * 4 > p.a_bytes) p.a_bytes = ((int)(Cin / G) * p.TS * 4 + 127) & ~127;   // staged output tile
+    p.tiles_per_b = (p.Mtot + p.mtile - 1) / p.mtile;
     p.ntiles = p.B * p.tiles_per_b;
     p.fT = make_fdiv(p.tiles_per_b);
     if (p.ntiles >= (1 << 20)) return LCT_EUNSUPPORTED;
     return dispatch_conv<MODE_DGRAD>(p, (int)G, nit, st);
+}
+
+LCT_API int lct_conv_tc_last_grid(void) { return g_tc_last_grid; }
+LCT_API int lct_conv_tc_tune(int ctas_per_sm) {          // bring-up only
+    if (ctas_per_sm > 0) g_tc_ctas_per_sm = ctas_per_sm;
+    return 0;
+}
+LCT_API int lct_conv_tc_debug_buffer(float* buf) {      // bring-up only (removed once the kernels are validated)
+    g_tc_dbg = buf;
+    return 0;
 }
 
 // dw [Cout][Cin/G][K] and db [Cout] (optional) are ACCUMULATED (the caller zeroes them): one atomic per weight and CTA
@@ -771,7 +929,7 @@ LCT_API int lct_conv_tc_wgrad(const float* x, const float* dy, float* dw, float*
     if (tapmax > 16) return LCT_EUNSUPPORTED;           // M = 64 = 16 tap slots x one channel quad
     WgradParams p = {};
     p.g = g;
-    p.dw = dw; p.db = db;
+    p.dw = dw; p.db = db; p.dbg = g_tc_dbg;
     p.B = (int)B; p.Cin = (int)Cin; p.Cout = (int)Cout; p.Lin = (int)Lin; p.Lout = (int)Lout;
     p.Mtot = (int)(Lout * P);
     p.tiles_per_b = (p.Mtot + kTileM - 1) / kTileM;

@@ -10,6 +10,9 @@ dense_tensor_cores = True
 #: operands read from shared memory through descriptors, accumulators in TMEM).  False = the round-1 TF32 mma.sync
 #: kernels (conv_mma.cu), kept for A/B measurements.
 grouped_conv_tcgen05 = True
+#: weight gradient of the same layers on tcgen05 (MN-major operand descriptors; under bring-up) - False = the TF32
+#: mma.sync weight-gradient kernel of conv_mma.cu
+grouped_wgrad_tcgen05 = False
 
 
 def set_precision(mode: str) -> None:
@@ -90,6 +93,10 @@ def aux_stream_for(stream):
 #: gradients are only valid after the join; lctgan.training.StepArgs.defer_dead_d_grads turns it on.
 defer_dead_param_grads = False
 _PENDING = []
+
+#: Data parallel (lctgan.parallel): called with the flat buffer that holds ALL parameter gradients of a sub-discriminator
+#: the moment its backward has produced them (D step only; lctgan.training sets and clears it around d_loss.backward()).
+stack_grad_hook = None
 
 
 def join_deferred_param_grads() -> None:

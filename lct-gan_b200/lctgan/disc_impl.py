@@ -61,6 +61,10 @@ class ConvStackFn(torch.autograd.Function):
             else:
                 h = ops.conv1d_fwd(h, w, bias, g, s, pad, act=act, slope=LRELU_SLOPE, wimg=imgs_f[i])
             fmaps.append(h)
+        # feature maps that receive no gradient (all but the logits in the D step) must arrive as None in backward, not
+        # as materialised zero tensors: autograd's default filled a map-sized zero buffer per unused output (64 fill
+        # kernels per step in the round-2 launch list) which the data-gradient kernels then read as "FM gradient"
+        ctx.set_materialize_grads(False)
         ctx.specs = list(specs)
         ctx.dense = dense
         ctx.skip_param_grads = skip_param_grads
@@ -83,11 +87,16 @@ class ConvStackFn(torch.autograd.Function):
         want_params = any(need_p) and not (ctx.skip_param_grads and need_x)
         gparams: List = [None] * (3 * n)
         gouts = [g.contiguous() if g is not None else None for g in gouts]
-        dws = dbs = None
-        if want_params:   # all accumulators of the stack in one zero-filled allocation
-            bufs = ops._flat_views([tuple(w.shape) for w in weights] + [(w.shape[0],) for w in weights], x4.device,
-                                   zero=True)
-            dws, dbs = bufs[:n], bufs[n:]
+        dws = dbs = dgs_o = dvs_o = arena = None
+        if want_params:
+            # the weight-gradient accumulators (internal: gradients w.r.t. the NORMALISED weights) in one cleared buffer,
+            # and the stack's final parameter gradients (bias, weight_g, weight_v of every layer) in another one - the
+            # "arena" a data-parallel exchange all-reduces in place (lctgan.parallel)
+            dws = ops._flat_views([tuple(w.shape) for w in weights], x4.device, zero=True)
+            fin, arena = ops._flat_views([(w.shape[0],) for w in weights] + [tuple(params[3 * i + 1].shape) for i in range(n)] +
+                                         [tuple(params[3 * i + 2].shape) for i in range(n)], x4.device, zero=True,
+                                         return_flat=True)
+            dbs, dgs_o, dvs_o = fin[:n], fin[n:2 * n], fin[2 * n:]
 
         dpre = gouts[n - 1]      # conv_post has no activation
         gx = None
@@ -138,7 +147,7 @@ class ConvStackFn(torch.autograd.Function):
                 # helper stream - weight-norm backward and the accumulation into .grad included - and let the caller
                 # join later; autograd gets None for the parameters.
                 with torch.cuda.stream(aux):
-                    dgs, dvs = ops.mt_weight_norm_bwd(gs, vs, dws)
+                    dgs, dvs = ops.mt_weight_norm_bwd(gs, vs, dws, out=(dgs_o, dvs_o))
                     olds, news = [], []
                     for i in range(n):
                         for j, t in ((3 * i, dbs[i]), (3 * i + 1, dgs[i]), (3 * i + 2, dvs[i])):
@@ -158,7 +167,9 @@ class ConvStackFn(torch.autograd.Function):
             if aux is not None:
                 cur.wait_stream(aux)
             keep.clear()
-            dgs, dvs = ops.mt_weight_norm_bwd(gs, vs, dws)
+            dgs, dvs = ops.mt_weight_norm_bwd(gs, vs, dws, out=(dgs_o, dvs_o))
+            if config.stack_grad_hook is not None:      # data parallel: this stack's gradients are complete - start
+                config.stack_grad_hook(arena)           # their all-reduce while the other stacks are still in backward
             for i in range(n):
                 gparams[3 * i] = dbs[i] if need_p[3 * i] else None
                 gparams[3 * i + 1] = dgs[i] if need_p[3 * i + 1] else None

@@ -266,33 +266,60 @@ def weight_norm_bwd(g, v, dw):
     return dg, dv
 
 
-def _use_tc(cin, cout, k, groups, stride, pad, P):
-    """Grouped / first layers go to the tcgen05 TF32 kernels (conv_tc.cu) in tensor-core mode."""
+def _tc_ok(cin, cout, k, groups, stride, pad, P):
     return (config.dense_tensor_cores and config.grouped_conv_tcgen05 and pad == k // 2 and
             bool(call_ret("lct_conv_tc_supported", cin, cout, groups, k, stride, P)))
 
 
-def _use_mma(cin, cout, k, groups, stride, pad, P):
-    """The round-1 TF32 mma.sync kernels (conv_mma.cu): only when the tcgen05 path is switched off."""
-    return (config.dense_tensor_cores and not config.grouped_conv_tcgen05 and pad == k // 2 and
+def _mma_ok(cin, cout, k, groups, stride, pad, P):
+    return (config.dense_tensor_cores and pad == k // 2 and
             bool(call_ret("lct_conv_mma_supported", cin, cout, groups, k, stride, P)))
 
 
+# Which of the two tensor-core implementations of the grouped / first-layer convolutions runs a pass.  Both compute the
+# same TF32 (round-to-nearest operands, fp32 accumulate) result; the choice is the measured one per layer family at the
+# D-step batch 2B = 16 (tools/bench_disc_layers.py, profiles/README.md round 2):
+#   forward        tcgen05 (conv_tc.cu) everywhere except the 1 -> 16, k = 15, stride-1 first MSD layer
+#                  (12.7 vs 15.3 us: eight half-empty K = 8 MMAs per tile for one input channel)
+#   data gradient  tcgen05 for the scale discriminators (P = 1: 23-38 vs 28-61 us per layer) and the one-channel first
+#                  layers; the TF32 mma.sync kernel (conv_mma.cu) for the period discriminators' grouped layers, whose
+#                  128-row tiles carry too little data to hide the single-buffered tile pipeline's latencies
+#                  (35-78 vs 25-49 us)
+#   weight gradient  mma.sync (the tcgen05 form needs MN-major descriptors: config.grouped_wgrad_tcgen05)
+def _use_tc(cin, cout, k, groups, stride, pad, P):
+    return _tc_ok(cin, cout, k, groups, stride, pad, P) and not (cin // groups == 1 and stride == 1)
+
+
+def _use_tc_dgrad(cin, cout, k, groups, stride, pad, P):
+    return _tc_ok(cin, cout, k, groups, stride, pad, P) and (P == 1 or cin // groups == 1)
+
+
+def _use_mma(cin, cout, k, groups, stride, pad, P):
+    return _mma_ok(cin, cout, k, groups, stride, pad, P) and not _use_tc(cin, cout, k, groups, stride, pad, P)
+
+
+def _use_mma_dgrad(cin, cout, k, groups, stride, pad, P):
+    return _mma_ok(cin, cout, k, groups, stride, pad, P) and not _use_tc_dgrad(cin, cout, k, groups, stride, pad, P)
+
+
 def conv_tc_images(ws, specs, P, want_f=True, want_d=True):
-    """Weight images of the tcgen05 grouped convolutions for the layers of one stack that those kernels cover, ONE
-    launch: ws[i] [Cout, Cin/G, K] normalised weights, specs[i] = (k, stride, pad, groups).  Returns (imgs_f, imgs_d)
-    with None for the layers that run elsewhere (conv_post, the dense layer)."""
+    """Weight images of the tcgen05 grouped convolutions, ONE launch per stack: ws[i] [Cout, Cin/G, K] normalised
+    weights, specs[i] = (k, stride, pad, groups); want_f / want_d: bool or per-layer list (forward / data-gradient
+    image wanted).  Returns (imgs_f, imgs_d) with None where no image was asked for or the kernels do not cover the
+    layer (conv_post, the dense layer)."""
     n = len(ws)
+    wf = list(want_f) if isinstance(want_f, (list, tuple)) else [bool(want_f)] * n
+    wd = list(want_d) if isinstance(want_d, (list, tuple)) else [bool(want_d)] * n
     imgs_f, imgs_d = [None] * n, [None] * n
     idx, shapes = [], []
     buf = (ctypes.c_int64 * 2)()
     for i, (k, s, pad, g) in enumerate(specs):
         cout, cig = ws[i].shape[0], ws[i].shape[1]
-        if not _use_tc(cig * g, cout, k, g, s, pad, P) or _is_post(cout, k, g, s, pad):
+        if not (wf[i] or wd[i]) or _is_post(cout, k, g, s, pad) or not _tc_ok(cig * g, cout, k, g, s, pad, P):
             continue
         call_ret("lct_conv_tc_image_len", cig * g, cout, g, k, s, P, buf)
         idx.append(i)
-        shapes += [(int(buf[0]),), (int(buf[1]),)]
+        shapes += [(int(buf[0]) if wf[i] else 0,), (int(buf[1]) if wd[i] else 0,)]
     if not idx:
         return imgs_f, imgs_d
     views = _flat_views(shapes, ws[0].device)
@@ -303,8 +330,8 @@ def conv_tc_images(ws, specs, P, want_f=True, want_d=True):
         for i in part:
             k, s, pad, g = specs[i]
             geo += [ws[i].shape[1] * g, ws[i].shape[0], g, k, s, P]
-        f = [views[2 * (c0 + j)] if want_f else None for j in range(len(part))]
-        d = [views[2 * (c0 + j) + 1] if want_d else None for j in range(len(part))]
+        f = [views[2 * (c0 + j)] if wf[i] else None for j, i in enumerate(part)]
+        d = [views[2 * (c0 + j) + 1] if wd[i] else None for j, i in enumerate(part)]
         arr = lambda ts: (ctypes.c_void_p * len(ts))(*[t.data_ptr() if t is not None else None for t in ts])
         call("lct_conv_tc_images", _ptr_array([ws[i].contiguous() for i in part]), arr(f), arr(d),
              (ctypes.c_int64 * len(geo))(*geo), len(part))
@@ -343,38 +370,41 @@ def _is_post(cout, k, groups, stride, pad):
     return cout == 1 and groups == 1 and stride == 1 and (k & 1) and k <= 8 and pad == k // 2
 
 
-def _flat_views(shapes, device, zero=False):
-    """One allocation (optionally zero-filled: one fill kernel) carved into contiguous tensors of `shapes`."""
+def _flat_views(shapes, device, zero=False, return_flat=False):
+    """One allocation (optionally zero-filled: one memset) carved into contiguous tensors of `shapes`."""
     sizes = [int(math.prod(s)) for s in shapes]
     offs, tot = [], 0
     for n in sizes:
         offs.append(tot)
         tot += (n + 3) // 4 * 4            # keep every view 16-byte aligned
     flat = zeros((tot,), device) if zero else torch.empty(tot, dtype=torch.float32, device=device)
-    return [flat[o:o + n].view(s) for o, n, s in zip(offs, sizes, shapes)]
+    views = [flat[o:o + n].view(s) for o, n, s in zip(offs, sizes, shapes)]
+    return (views, flat) if return_flat else views
 
 
 def mt_weight_norm_fwd(gs, vs, specs=None, P=1):
     """w_i = g_i * v_i / ||v_i|| for all layers of a stack in one launch.  With `specs` ((k, stride, pad, groups) per
-    layer) the same launch also writes, for every layer the tensor-core conv kernels cover, the zero-padded TF32
-    weight images they stage (forward and data-gradient arrangement).  Returns (ws, imgs_f, imgs_d)."""
+    layer) also the staged TF32 weight images of the tensor-core conv kernels, per layer and direction for the kernel
+    that runs it (see _use_tc / _use_tc_dgrad): the mma.sync images come out of the weight-norm launch itself, the
+    tcgen05 images out of one more launch.  Returns (ws, imgs_f, imgs_d)."""
     n = len(vs)
     ws = _flat_views([tuple(v.shape) for v in vs], vs[0].device)
     rows = (ctypes.c_int64 * n)(*[v.shape[0] for v in vs])
     rowlen = (ctypes.c_int64 * n)(*[v.numel() // v.shape[0] for v in vs])
     imgs_f, imgs_d = [None] * n, [None] * n
     pf = pd = geo = None
-    if specs is not None and config.dense_tensor_cores and config.grouped_conv_tcgen05:
-        call("lct_mt_weight_norm_fwd", _ptr_array(gs), _ptr_array(vs), _ptr_array(ws), rows, rowlen, None, None, None, n)
-        imgs_f, imgs_d = conv_tc_images(ws, specs, P)
-        return ws, imgs_f, imgs_d
+    tc_f, tc_d = [False] * n, [False] * n
     if specs is not None and config.dense_tensor_cores:
         shapes, idxs, geos = [], [], [0] * (8 * n)
         buf = (ctypes.c_int64 * 2)()
+        mf, md = [None] * n, [None] * n
         for i, (k, s, pad, g) in enumerate(specs):
             cout, cig = vs[i].shape[0], vs[i].shape[1]
             cin = cig * g
-            if not _use_mma(cin, cout, k, g, s, pad, P):
+            if _is_post(cout, k, g, s, pad):
+                continue
+            tc_f[i], tc_d[i] = _use_tc(cin, cout, k, g, s, pad, P), _use_tc_dgrad(cin, cout, k, g, s, pad, P)
+            if (tc_f[i] and tc_d[i]) or not _mma_ok(cin, cout, k, g, s, pad, P):
                 continue
             call_ret("lct_conv_mma_image_geometry", cin, cout, g, k, s, 0, buf)
             kkf, nsf = int(buf[0]), int(buf[1])
@@ -386,16 +416,25 @@ def mt_weight_norm_fwd(gs, vs, specs=None, P=1):
         if idxs:
             views = _flat_views(shapes, vs[0].device, zero=True)
             for j, i in enumerate(idxs):
-                imgs_f[i], imgs_d[i] = views[2 * j], views[2 * j + 1]
+                mf[i], md[i] = views[2 * j], views[2 * j + 1]
             arr = lambda ts: (ctypes.c_void_p * n)(*[t.data_ptr() if t is not None else None for t in ts])
-            pf, pd, geo = arr(imgs_f), arr(imgs_d), (ctypes.c_int64 * (8 * n))(*geos)
+            pf, pd, geo = arr(mf), arr(md), (ctypes.c_int64 * (8 * n))(*geos)
+        imgs_f, imgs_d = mf, md
     call("lct_mt_weight_norm_fwd", _ptr_array(gs), _ptr_array(vs), _ptr_array(ws), rows, rowlen, pf, pd, geo, n)
+    if any(tc_f) or any(tc_d):
+        tf, td = conv_tc_images(ws, specs, P, want_f=tc_f, want_d=tc_d)
+        imgs_f = [tf[i] if tc_f[i] else imgs_f[i] for i in range(n)]
+        imgs_d = [td[i] if tc_d[i] else imgs_d[i] for i in range(n)]
     return ws, imgs_f, imgs_d
 
 
-def mt_weight_norm_bwd(gs, vs, dws):
-    dgs = _flat_views([tuple(g.shape) for g in gs], gs[0].device)
-    dvs = _flat_views([tuple(v.shape) for v in vs], vs[0].device)
+def mt_weight_norm_bwd(gs, vs, dws, out=None):
+    """out: optional (dgs, dvs) lists of pre-allocated outputs (views of the stack's gradient arena)."""
+    if out is not None:
+        dgs, dvs = out
+    else:
+        dgs = _flat_views([tuple(g.shape) for g in gs], gs[0].device)
+        dvs = _flat_views([tuple(v.shape) for v in vs], vs[0].device)
     rows = (ctypes.c_int64 * len(vs))(*[v.shape[0] for v in vs])
     rowlen = (ctypes.c_int64 * len(vs))(*[v.numel() // v.shape[0] for v in vs])
     call("lct_mt_weight_norm_bwd", _ptr_array(gs), _ptr_array(vs), _ptr_array(dws), _ptr_array(dgs), _ptr_array(dvs),
@@ -435,12 +474,12 @@ def conv1d_dgrad(dy, w, x_shape, groups, stride, pad, gextra=None, xact=None, ac
     if _is_post(Cout, K, groups, stride, pad):
         call("lct_conv_post_dgrad", dy, w, dx, gextra, xact, B, Cin, Lin, P, K, act, slope)
         return dx
-    if _use_tc(Cin, Cout, K, groups, stride, pad, P):
+    if _use_tc_dgrad(Cin, Cout, K, groups, stride, pad, P):
         if wimg is None:
             wimg = conv_tc_images([w.reshape(Cout, Cin // groups, K)], [(K, stride, pad, groups)], P, want_f=False)[1][0]
         call("lct_conv_tc_dgrad", dy, wimg, dx, gextra, xact, B, Cin, Cout, groups, K, stride, pad, Lin, P, act, slope)
         return dx
-    if _use_mma(Cin, Cout, K, groups, stride, pad, P):
+    if _use_mma_dgrad(Cin, Cout, K, groups, stride, pad, P):
         call("lct_conv_mma_dgrad", dy, w, wimg, dx, gextra, xact, B, Cin, Cout, groups, K, stride, pad, Lin, P, act, slope)
         return dx
     call("lct_conv1d_dgrad", dy, w, dx, gextra, xact, B, Cin, Cout, groups, K, stride, pad, Lin, P, act, slope)
@@ -458,10 +497,10 @@ def conv1d_wgrad(x, dy, w_shape, groups, stride, pad, want_bias=True, dw=None, d
     if _is_post(Cout, K, groups, stride, pad):
         call("lct_conv_post_wgrad", x, dy, dw, db, B, Cin, Lin, P, K)
         return dw, db
-    if _use_tc(Cin, Cout, K, groups, stride, pad, P):
+    if config.grouped_wgrad_tcgen05 and _tc_ok(Cin, Cout, K, groups, stride, pad, P):
         call("lct_conv_tc_wgrad", x, dy, dw, db, B, Cin, Cout, groups, K, stride, pad, Lin, P)
         return dw, db
-    if _use_mma(Cin, Cout, K, groups, stride, pad, P):
+    if _mma_ok(Cin, Cout, K, groups, stride, pad, P):
         call("lct_conv_mma_wgrad", x, dy, dw, db, B, Cin, Cout, groups, K, stride, pad, Lin, P)
         return dw, db
     call("lct_conv1d_wgrad", x, dy, dw, db, B, Cin, Cout, groups, K, stride, pad, Lin, P)

@@ -93,7 +93,13 @@ def _phase_d(M, noisy, clean, args: StepArgs, st: dict) -> None:
         msd_fake, _ = msd(enhanced_for_d)
     d_loss = L.discriminator_loss(L._flatten_logits_lists(mpd_real, msd_real),
                                   L._flatten_logits_lists(mpd_fake, msd_fake), args.gan_loss)
-    d_loss.backward()
+    # data parallel: every sub-discriminator hands its finished gradient buffer to the exchange as soon as its own
+    # backward is done (the all-reduce of the first ones overlaps the backward of the others)
+    config.stack_grad_hook = getattr(st.get("after_d"), "reduce_async", None) if noisy.is_cuda else None
+    try:
+        d_loss.backward()
+    finally:
+        config.stack_grad_hook = None
     st["d_loss"] = d_loss.detach()
 
 
@@ -167,15 +173,29 @@ def train_step(enhancer, mpd, msd, tf_features, mrstft_loss, g_opt, d_opt, noisy
     ``after_*_backward`` are the data-parallel hooks (gradient all-reduce) of lctgan.parallel."""
     M = (enhancer, mpd, msd, tf_features, mrstft_loss, g_opt, d_opt)
     _set_skip_dead(mpd, msd, args.skip_dead_d_grads)
-    st: dict = {}
+    st: dict = {"after_d": after_d_backward}
     _phase_d(M, noisy, clean, args, st)
     if after_d_backward is not None:
         after_d_backward()
     _phase_g(M, noisy, clean, args, st)
-    if after_g_backward is not None:
-        after_g_backward()
-    _phase_opt_g(M, args)
+    _exchange_g(enhancer, after_g_backward)
+    _phase_opt_g(M, args, _pre_scale(after_g_backward))
     return {k: st[k] for k in _OUT_KEYS}
+
+
+def _exchange_g(enhancer, after_g_backward) -> None:
+    """Generator gradient exchange: in place on the flat buffer the generator's backward wrote (no pack / unpack)."""
+    if after_g_backward is None:
+        return
+    arena = getattr(getattr(enhancer, "gen", None), "_grad_arena", None)
+    if arena is not None and hasattr(after_g_backward, "reduce_async"):
+        after_g_backward.reduce_async(arena)
+    after_g_backward()
+
+
+def _pre_scale(after_g_backward) -> float:
+    """1 / world_size when the exchange leaves the SUM in .grad for the clip to fold in (FlatGradAllReduce.fold_scale)."""
+    return after_g_backward.grad_scale if getattr(after_g_backward, "fold_scale", False) else 1.0
 
 
 def synthetic_batch(batch: int, samples: int, seed: int = 1234):
@@ -249,23 +269,27 @@ def build_models(device, gan_seed: Optional[int] = 42, max_time_context: Optiona
 
 
 class GraphedTrainStep:
-    """The whole D+G step captured once into CUDA graphs and replayed.
+    """The whole D+G step captured once into a CUDA graph and replayed.
 
     At batch 8 the step is ~1100 small kernel launches; replaying a graph removes the per-launch host cost
     (Python, ctypes, autograd bookkeeping, allocator) and lets the GPU run the kernels back to back, the
     sub-discriminators as parallel branches.  Inputs live in static device buffers (`noisy`, `clean`): copy new
-    data into them, then call the object.  The optimisers must have been built with ``capturable=True``.
+    data into them, then call the object.  torch optimisers must have been built with ``capturable=True``.
 
-    Single GPU: one graph.  Data parallel (hooks given): three graphs sharing one memory pool - [D forward +
-    backward] | [D update, G forward + backward] | [clip, G update] - with the two NCCL gradient all-reduces
-    launched eagerly in between (the collectives themselves are not captured).
+    Data parallel (hooks given): still ONE graph - the NCCL all-reduces of lctgan.parallel are captured inside it on
+    the exchange's communication stream, a forked branch that overlaps the rest of the discriminator backward.  If the
+    collectives cannot be captured (``capture_collectives=False`` or a capture error) the step is cut into three graphs
+    sharing one memory pool - [D forward + backward] | [D update, G forward + backward] | [clip, G update] - with the
+    two exchanges launched eagerly in between.
     """
 
     def __init__(self, enhancer, mpd, msd, tf_features, mrstft_loss, g_opt, d_opt, noisy, clean, args: StepArgs,
-                 after_d_backward=None, after_g_backward=None, warmup: int = 3):
+                 after_d_backward=None, after_g_backward=None, warmup: int = 3, capture_collectives: bool = True):
         from . import _lib
         self.noisy, self.clean = noisy, clean
+        self.enhancer = enhancer
         self.hooks = (after_d_backward, after_g_backward)
+        self.capture_error = None
         M = (enhancer, mpd, msd, tf_features, mrstft_loss, g_opt, d_opt)
         _set_skip_dead(mpd, msd, args.skip_dead_d_grads)
         side = torch.cuda.Stream()
@@ -277,15 +301,28 @@ class GraphedTrainStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         n0 = _lib.kernel_launches()
+        has_hooks = after_d_backward is not None or after_g_backward is not None
+        self.graphs = None
         st: dict = {}
-        if after_d_backward is None and after_g_backward is None:
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                _phase_d(M, self.noisy, self.clean, args, st)
-                _phase_g(M, self.noisy, self.clean, args, st)
-                _phase_opt_g(M, args)
-            self.graphs = [g]
-        else:
+        if capture_collectives or not has_hooks:
+            try:
+                st = {"after_d": after_d_backward}
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    _phase_d(M, self.noisy, self.clean, args, st)
+                    if after_d_backward is not None:
+                        after_d_backward()
+                    _phase_g(M, self.noisy, self.clean, args, st)
+                    _exchange_g(enhancer, after_g_backward)
+                    _phase_opt_g(M, args, _pre_scale(after_g_backward))
+                self.graphs = [g]
+            except Exception as e:
+                if not has_hooks:
+                    raise
+                self.capture_error = repr(e)          # reported by bench.py; the segmented form below still runs
+                torch.cuda.synchronize()
+        if self.graphs is None:
+            st = {"after_d": None}                    # no collective inside a graph: exchanges run between the graphs
             pool = torch.cuda.graph_pool_handle()
             g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             with torch.cuda.graph(g1, pool=pool):
@@ -294,10 +331,9 @@ class GraphedTrainStep:
                 after_d_backward()
             with torch.cuda.graph(g2, pool=pool):
                 _phase_g(M, self.noisy, self.clean, args, st)
-            if after_g_backward is not None:
-                after_g_backward()
+            _exchange_g(enhancer, after_g_backward)
             with torch.cuda.graph(g3, pool=pool):
-                _phase_opt_g(M, args)
+                _phase_opt_g(M, args, _pre_scale(after_g_backward))
             self.graphs = [g1, g2, g3]
         self.out = {k: st[k] for k in _OUT_KEYS}
         #: lctgan kernel launches recorded in the graphs (+ the eager gradient gather/scatter) = per replayed step
@@ -311,7 +347,6 @@ class GraphedTrainStep:
             if self.hooks[0] is not None:
                 self.hooks[0]()
             self.graphs[1].replay()
-            if self.hooks[1] is not None:
-                self.hooks[1]()
+            _exchange_g(self.enhancer, self.hooks[1])
             self.graphs[2].replay()
         return self.out

@@ -1,5 +1,6 @@
-"""Grouped discriminator convolutions (conv_mma kernels) timed layer by layer from CUDA graphs of 20 launches, on the
-shapes of the D step (batch 2B = 16) or the G step (B = 8):  python tools/bench_disc_layers.py [B]
+"""Grouped discriminator convolutions timed layer by layer from CUDA graphs of 20 launches, on the shapes of the D step
+(batch 2B = 16) or the G step (B = 8):  python tools/bench_disc_layers.py [B] [tc|mma]
+(tc = tcgen05 kernels of conv_tc.cu, the default; mma = the round-1 mma.sync kernels of conv_mma.cu)
 
 Prints per layer: forward / data-gradient (with the fused FM-gradient + LeakyReLU' epilogue) / weight-gradient time and
 the achieved GB/s on the algorithmic bytes (fwd: x + y; dgrad: dy + gextra + xact + dx; wgrad: x + dy)."""
@@ -7,9 +8,14 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "lct-gan_b200")); sys.path.insert(0, ROOT)
 import torch
-from lctgan import ops
+from lctgan import config, ops
 dev = torch.device("cuda:0")
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+config.grouped_conv_tcgen05 = not (len(sys.argv) > 2 and sys.argv[2] == "mma")
+if len(sys.argv) > 3:
+    from lctgan import _lib as _l
+    _l.call_ret("lct_conv_tc_tune", int(sys.argv[3]))
+print("kernels:", "tcgen05 (conv_tc.cu)" if config.grouped_conv_tcgen05 else "mma.sync (conv_mma.cu)", flush=True)
 
 
 def gtime(run, n=20):
@@ -50,13 +56,18 @@ for name, Cin, Cout, K, S, G, Lin, P in LAYERS:
     x = torch.randn(B, Cin, Lin, P, device=dev)
     w = torch.randn(Cout, Cin // G, K, device=dev) * 0.05
     b = torch.zeros(Cout, device=dev)
-    y = ops.conv1d_fwd(x, w, b, G, S, pad, act=ops.ACT_LRELU)
+    gw = torch.ones(Cout, 1, 1, device=dev)
+    _, imf, imd = ops.mt_weight_norm_fwd([gw], [w], [(K, S, pad, G)], P)          # staged weight images, as in the step
+    y = ops.conv1d_fwd(x, w, b, G, S, pad, act=ops.ACT_LRELU, wimg=imf[0])
     dy = torch.randn_like(y)
-    t_f = gtime(lambda: ops.conv1d_fwd(x, w, b, G, S, pad, act=ops.ACT_LRELU))
-    t_d = gtime(lambda: ops.conv1d_dgrad(dy, w, x.shape, G, S, pad, gextra=x, xact=x, act=ops.ACT_LRELU))
-    t_w = gtime(lambda: ops.conv1d_wgrad(x, dy, w.shape, G, S, pad))
+    dw, db = torch.zeros_like(w), torch.zeros(Cout, device=dev)
+    t_f = gtime(lambda: ops.conv1d_fwd(x, w, b, G, S, pad, act=ops.ACT_LRELU, wimg=imf[0]))
+    t_d = gtime(lambda: ops.conv1d_dgrad(dy, w, x.shape, G, S, pad, gextra=x, xact=x, act=ops.ACT_LRELU, wimg=imd[0]))
+    t_w = gtime(lambda: ops.conv1d_wgrad(x, dy, w.shape, G, S, pad, dw=dw, db=db))
     bx, by = x.numel() * 4, y.numel() * 4
     tot[0] += t_f; tot[1] += t_d; tot[2] += t_w
-    print(f"{name:13s} B={B:2d} x {bx/1e6:6.1f} MB y {by/1e6:6.1f} MB: fwd {t_f:6.1f} us ({(bx+by)/t_f/1e3:5.0f} GB/s)  "
+    from lctgan import _lib
+    name = f"{name}[{_lib.call_ret('lct_conv_tc_last_grid')}]" if config.grouped_conv_tcgen05 else name
+    print(f"{name:19s} B={B:2d} x {bx/1e6:6.1f} MB y {by/1e6:6.1f} MB: fwd {t_f:6.1f} us ({(bx+by)/t_f/1e3:5.0f} GB/s)  "
           f"dgrad {t_d:6.1f} us ({(3*bx+by)/t_d/1e3:5.0f} GB/s)  wgrad {t_w:6.1f} us ({(bx+by)/t_w/1e3:5.0f} GB/s)", flush=True)
 print(f"sum: fwd {tot[0]:.1f} us  dgrad {tot[1]:.1f} us  wgrad {tot[2]:.1f} us")

@@ -3,6 +3,7 @@
 stacks.  Prints one line per (case, pass); with --probe also decodes which input element each output row multiplied
 (delta weights, ramp inputs), which is what one needs when a descriptor field is misread."""
 import argparse
+import ctypes
 import os
 import sys
 
@@ -86,6 +87,33 @@ def probe(Cin, Cout, K, S, G, L, P):
               flush=True)
 
 
+def probe_wgrad(Cin, Cout, K, S, G, L, P):
+    """delta x, delta dY -> a single 1 in dW at k = i0 - S l0 + pad; also dump the raw TMEM accumulators of CTA (0, 0)"""
+    from lctgan import _lib
+    pad = K // 2
+    cig, cog = Cin // G, Cout // G
+    Lout = (L + 2 * pad - K) // S + 1
+    N = (cog + 7) // 8 * 8
+    nacc = S * ((cig + 3) // 4)
+    for (n0, c0, l0, k0) in ((0, 0, 3, 0), (min(5, cog - 1), 0, 3, min(K - 1, S + 1)), (1, min(cig - 1, 2), 6, K - 1)):
+        i0 = S * l0 + k0 - pad
+        if not (0 <= i0 < L and l0 < Lout):
+            continue
+        x = torch.zeros(1, Cin, L, P, device=dev); x[0, c0, i0, 0] = 1.0
+        dy = torch.zeros(1, Cout, Lout, P, device=dev); dy[0, n0, l0, 0] = 1.0
+        dbg = torch.full((nacc, 128, N), -7.0, device=dev)
+        _lib.call_ret("lct_conv_tc_debug_buffer", ctypes.c_void_p(dbg.data_ptr()))
+        dw, _ = ops.conv_tc_wgrad(x, dy, (Cout, cig, K), G, S, pad)
+        torch.cuda.synchronize()
+        _lib.call_ret("lct_conv_tc_debug_buffer", None)
+        nz = dw.nonzero().tolist()
+        print(f"  probe wgrad want dW[{n0}][{c0}][{k0}]=1: got nonzero {[(tuple(i), round(dw[tuple(i)].item(), 3)) for i in nz[:8]]}", flush=True)
+        dn = (dbg != 0).nonzero().tolist()
+        print(f"    raw accumulators (acc, lane, col) nonzero: {[(tuple(i), round(dbg[tuple(i)].item(), 3)) for i in dn[:12]]}"
+              f" total {len(dn)}  (expected acc {k0 % S}*nq+{c0 // 4}, row {4 * (k0 // S) + c0 % 4} -> lane {(4 * (k0 // S) + c0 % 4) % 16 + 32 * ((4 * (k0 // S) + c0 % 4) // 16)}, col {n0})",
+              flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--probe", action="store_true")
@@ -95,6 +123,7 @@ def main():
     for i, c in enumerate(CASES):
         if args.only >= 0 and i != args.only:
             continue
+        errs = (1.0, 1.0, 1.0, 1.0)
         try:
             ok, errs = run_case(*c)
         except Exception as e:      # keep going: one line per case
@@ -104,7 +133,10 @@ def main():
             bad += 1
             if args.probe:
                 try:
-                    probe(*c)
+                    if max(errs[0], errs[1]) >= 2e-4:
+                        probe(*c)
+                    if errs[2] >= 2e-4:
+                        probe_wgrad(*c)
                 except Exception as e:
                     print(f"  probe failed: {e!r}", flush=True)
     print(f"{len(CASES) - bad} / {len(CASES)} cases within 2e-4", flush=True)
