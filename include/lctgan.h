@@ -223,4 +223,13 @@ LCT_API int lct_mt_clip(void* const* g, const int64_t* n, int64_t nseg, const fl
  * zero-fill kernels of gradient accumulators: one buffer per layer stack, cleared once. */
 LCT_API int lct_memset_zero(void* p, int64_t bytes, cudaStream_t stream);
 
+/* ---- callers on either side of the hot path (csrc/pipeline.cu) ----
+ * lct_si_sdr: out[b] = SI-SDR (dB) of est[b, :L] against ref[b, :L], L = min(lengths[b], T_ref, T_est), both zero-mean over
+ * that span (reference train.py:261-282 _si_sdr_torch, there one call + host sync per utterance); lengths (device int64)
+ * optional.  lct_crop_segments: out[b, t] = src[offset[b] + start[b] + t] while start[b] + t < end[b], else 0 - the loader's
+ * segment cropping (datasets/datasets.py:131-156 _crop_pair) and collate_fn zero padding (:187-230) on utterances packed in
+ * one device buffer; offset / end / start: device int64 [B]; clean side optional. */
+LCT_API int lct_si_sdr(const float* ref, const float* est, const int64_t* lengths, float* out, int64_t B, int64_t T_ref, int64_t T_est, float eps, cudaStream_t stream);
+LCT_API int lct_crop_segments(const float* noisy, const float* clean, const int64_t* offset_n, const int64_t* offset_c, const int64_t* end_n, const int64_t* end_c, const int64_t* start, float* out_n, float* out_c, int64_t B, int64_t T, cudaStream_t stream);
+
 #endif /* LCTGAN_H_ */

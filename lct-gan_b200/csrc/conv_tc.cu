@@ -127,13 +127,13 @@ struct ImgJobs { ImgJob job[kMaxImgJobs]; int n; };
 
 __global__ void __launch_bounds__(256) tc_image_kernel(const ImgJobs J) {
     const ImgJob& jb = J.job[blockIdx.y];
-    const Geom& g = jb.g;
-    const int per_group = g.nmma * 2 * g.Npad * 4;
+    const Geom g = jb.g;
+    const int per_group = g.nmma * 2 * g.Npad;             // float4 rows per group: [mma j][chunk c][row n]
     const int64_t total = (int64_t)jb.G * per_group;
+    float4* img4 = reinterpret_cast<float4*>(jb.img);
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
         const int grp = (int)(idx / per_group);
         int r = (int)(idx - (int64_t)grp * per_group);
-        const int e = r & 3; r >>= 2;
         const int n = r % g.Npad; r /= g.Npad;
         const int c = r & 1;
         const int j = r >> 1;
@@ -144,19 +144,25 @@ __global__ void __launch_bounds__(256) tc_image_kernel(const ImgJobs J) {
             if (g.by_tap) { ++tap; valid = tap < g.ntap[ph]; }
             else ++quad;
         }
-        float v = 0.f;
-        const int ch = 4 * quad + e;        // channel of the A operand inside the group
-        if (valid && n < g.ncol && ch < g.ca) {
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (valid && n < g.ncol) {
             if (g.mode == MODE_FWD) {
                 const int k = g.S * tap + ph;
-                v = jb.w[((int64_t)(grp * g.cog + n) * g.cig + ch) * g.K + k];
+                const float* w = jb.w + ((int64_t)(grp * g.cog + n) * g.cig) * g.K + k;
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (4 * quad + e < g.ca) v[e] = w[(int64_t)(4 * quad + e) * g.K];
             } else {
                 const int ci = n / g.S, rr = n - ci * g.S;
                 const int k = rr + g.pad - g.S * (g.o_min + tap);
-                if (k >= 0 && k < g.K) v = jb.w[((int64_t)(grp * g.cog + ch) * g.cig + ci) * g.K + k];
+                if (k >= 0 && k < g.K) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (4 * quad + e < g.ca) v[e] = jb.w[((int64_t)(grp * g.cog + 4 * quad + e) * g.cig + ci) * g.K + k];
+                }
             }
         }
-        jb.img[idx] = tc::tf32_rna(v);
+        img4[idx] = make_float4(tc::tf32_rna(v[0]), tc::tf32_rna(v[1]), tc::tf32_rna(v[2]), tc::tf32_rna(v[3]));
     }
 }
 
@@ -856,7 +862,7 @@ LCT_API int lct_conv_tc_images(const void* const* w, void* const* img_f, void* c
         }
     }
     if (J.n == 0) return 0;
-    int gx = (int)ceil_div64(maxtot, 256 * 4);
+    int gx = (int)ceil_div64(maxtot / 4, 256);
     if (gx > 592) gx = 592;
     if (gx < 1) gx = 1;
     tc_image_kernel<<<dim3((unsigned)gx, (unsigned)J.n), 256, 0, st>>>(J);

@@ -34,18 +34,37 @@ def _use_dense(x_shape, w_shape, k, s, g) -> bool:
 LayerSpec = Tuple[int, int, int, int]
 
 
+def prepare_stack(specs: Sequence[LayerSpec], params: Sequence[torch.Tensor], P: int, need_dgrad: bool = True) -> dict:
+    """Everything a stack's passes derive from its WEIGHTS alone: the normalised weights (one batched weight-norm
+    launch), the staged TF32 images of the tensor-core conv kernels and the bf16 images of the dense tcgen05 layer.
+    A pure function of the parameters, so two passes over different inputs under the same weights (the G step's real
+    and fake passes, train.py:221-227) share one preparation - models.discriminators.run_discriminators does that."""
+    n = len(specs)
+    with torch.no_grad():
+        gs = [params[3 * i + 1].contiguous() for i in range(n)]
+        vs = [params[3 * i + 2].contiguous() for i in range(n)]
+        weights, imgs_f, imgs_d = ops.mt_weight_norm_fwd(gs, vs, specs, P)
+        wt, wd = {}, {}
+        for i, (k, s, pad, g) in enumerate(specs):
+            w = weights[i]
+            if _use_dense((1, w.shape[1] * g, 1, P), w.shape, k, s, g) and pad == k // 2:
+                wt[i], wd[i] = ops.stage_dense_weights(w, want_wt=True, want_wd=need_dgrad)
+    return dict(weights=weights, imgs_f=imgs_f, imgs_d=imgs_d, wt=wt, wd=wd)
+
+
 class ConvStackFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x4, specs: Sequence[LayerSpec], skip_param_grads: bool, *params):
-        """x4: [B, 1, L, P]; params: (bias, weight_g, weight_v) per layer.  Returns all feature maps."""
+    def forward(ctx, x4, specs: Sequence[LayerSpec], skip_param_grads: bool, prep, *params):
+        """x4: [B, 1, L, P]; params: (bias, weight_g, weight_v) per layer; prep: prepare_stack(...) of the same
+        parameters or None (prepared here).  Returns all feature maps."""
         if not x4.is_cuda:
             raise RuntimeError("lctgan discriminators are CUDA only (sm_100a); there is no CPU fallback")
         n = len(specs)
         assert len(params) == 3 * n
         x4 = x4.contiguous()
-        gs = [params[3 * i + 1].contiguous() for i in range(n)]
-        vs = [params[3 * i + 2].contiguous() for i in range(n)]
-        weights, imgs_f, imgs_d = ops.mt_weight_norm_fwd(gs, vs, specs, x4.shape[3])
+        if prep is None:
+            prep = prepare_stack(specs, params, x4.shape[3], need_dgrad=False)
+        weights, imgs_f, imgs_d = prep["weights"], prep["imgs_f"], prep["imgs_d"]
         fmaps: List[torch.Tensor] = []
         h = x4
         dense: List[int] = []
@@ -53,10 +72,9 @@ class ConvStackFn(torch.autograd.Function):
             bias, w = params[3 * i], weights[i]
             last = i == n - 1
             act = ops.ACT_NONE if last else ops.ACT_LRELU
-            if _use_dense(h.shape, w.shape, k, s, g) and pad == k // 2:
-                wt, _ = ops.stage_dense_weights(w, want_wt=True, want_wd=False)
-                h = ops.dense_conv(ops.stage_nlc_bf16(h, pad), wt, h.shape[0], h.shape[2], w.shape[1], w.shape[0], k,
-                                   bias=bias, act=act, slope=LRELU_SLOPE)
+            if i in prep["wt"]:
+                h = ops.dense_conv(ops.stage_nlc_bf16(h, pad), prep["wt"][i], h.shape[0], h.shape[2], w.shape[1],
+                                   w.shape[0], k, bias=bias, act=act, slope=LRELU_SLOPE)
                 dense.append(i)
             else:
                 h = ops.conv1d_fwd(h, w, bias, g, s, pad, act=act, slope=LRELU_SLOPE, wimg=imgs_f[i])
@@ -70,6 +88,7 @@ class ConvStackFn(torch.autograd.Function):
         ctx.skip_param_grads = skip_param_grads
         ctx.param_objs = params   # the Parameter objects themselves (deferred mode accumulates into their .grad)
         ctx.imgs_d = imgs_d       # (internal buffers, not outputs: safe to keep on ctx)
+        ctx.dense_wd = prep["wd"]
         ctx.save_for_backward(x4, *fmaps, *weights, *params)
         return tuple(fmaps)
 
@@ -83,7 +102,7 @@ class ConvStackFn(torch.autograd.Function):
         weights = saved[1 + n:1 + 2 * n]
         params = saved[1 + 2 * n:]
         need_x = ctx.needs_input_grad[0]
-        need_p = [ctx.needs_input_grad[3 + j] for j in range(3 * n)]
+        need_p = [ctx.needs_input_grad[4 + j] for j in range(3 * n)]
         want_params = any(need_p) and not (ctx.skip_param_grads and need_x)
         gparams: List = [None] * (3 * n)
         gouts = [g.contiguous() if g is not None else None for g in gouts]
@@ -125,7 +144,9 @@ class ConvStackFn(torch.autograd.Function):
                         dyq = ops.stage_ncl_bf16(dpre, Lp, 0, rowsum=dbs[i])
                         xq = ops.stage_ncl_bf16(inp, Lp, pad, copies=k)
                         ops.dense_wgrad(dyq, xq, Co_, Ci_, k, weights[i].shape, out=dws[i])
-                _, wd = ops.stage_dense_weights(weights[i], want_wt=False, want_wd=True)
+                wd = ctx.dense_wd.get(i)
+                if wd is None:
+                    _, wd = ops.stage_dense_weights(weights[i], want_wt=False, want_wd=True)
                 dpre = ops.dense_conv(ops.stage_nlc_bf16(dpre, pad), wd, B_, L_, Co_, Ci_, k, gextra=gouts[i - 1],
                                       xact=inp, act=ops.ACT_LRELU, slope=LRELU_SLOPE)
             elif dpre is not None:
@@ -163,7 +184,7 @@ class ConvStackFn(torch.autograd.Function):
                         torch._foreach_add_(olds, news)
                 keep.extend([x4, *fmaps, *weights, *gs, *vs, *dws, *dbs, *dgs, *dvs, *[g for g in gouts if g is not None]])
                 config._PENDING.append((aux, keep))
-                return (gx, None, None, *gparams)
+                return (gx, None, None, None, *gparams)
             if aux is not None:
                 cur.wait_stream(aux)
             keep.clear()
@@ -174,9 +195,9 @@ class ConvStackFn(torch.autograd.Function):
                 gparams[3 * i] = dbs[i] if need_p[3 * i] else None
                 gparams[3 * i + 1] = dgs[i] if need_p[3 * i + 1] else None
                 gparams[3 * i + 2] = dvs[i] if need_p[3 * i + 2] else None
-        return (gx, None, None, *gparams)
+        return (gx, None, None, None, *gparams)
 
 
 def conv_stack(x4: torch.Tensor, specs: Sequence[LayerSpec], params: Sequence[torch.Tensor],
-               skip_param_grads: bool = False) -> List[torch.Tensor]:
-    return list(ConvStackFn.apply(x4, tuple(specs), skip_param_grads, *params))
+               skip_param_grads: bool = False, prep: dict = None) -> List[torch.Tensor]:
+    return list(ConvStackFn.apply(x4, tuple(specs), skip_param_grads, prep, *params))

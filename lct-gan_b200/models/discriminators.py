@@ -18,20 +18,39 @@ from torch.nn.utils import spectral_norm, weight_norm
 
 from lctgan import config as _cfg
 from lctgan import functional as LF
-from lctgan.disc_impl import conv_stack
+from lctgan.disc_impl import conv_stack, prepare_stack
 
 
 def _run_concurrently(discs, inputs, no_grad=None, first_stream=0):
     """Evaluate discs[i](inputs[i]) for all i, each on its own CUDA stream (fork/join around the caller's stream).
-    no_grad[i] evaluates that call under torch.no_grad()."""
+    no_grad[i] evaluates that call under torch.no_grad().  A sub-discriminator that appears more than once (the G step
+    runs every one on the clean and on the enhanced batch) prepares its weights - weight norm, staged conv images - ONCE,
+    on the stream of its first call; the later calls wait for that event and reuse the buffers."""
     x0 = inputs[0]
     flags = no_grad if no_grad is not None else [False] * len(discs)
+    shared = {id(d) for d in discs if sum(1 for e in discs if e is d) > 1 and x0.is_cuda}
+    preps = {}
 
-    def call(d, x, ng):
-        if ng:
-            with torch.no_grad():
-                return d(x)
-        return d(x)
+    def call(d, x, ng, stream=None):
+        if id(d) in shared:
+            if id(d) not in preps:
+                prep = d.prepare(need_dgrad=not all(f for e, f in zip(discs, flags) if e is d))
+                ev = torch.cuda.Event() if stream is not None else None
+                if ev is not None:
+                    ev.record(stream)
+                preps[id(d)] = (prep, ev, stream)
+            else:
+                prep, ev, s0 = preps[id(d)]
+                if ev is not None and stream is not None and stream != s0:
+                    stream.wait_event(ev)
+            d._prep = preps[id(d)][0]
+        try:
+            if ng:
+                with torch.no_grad():
+                    return d(x)
+            return d(x)
+        finally:
+            d._prep = None
 
     if not (_cfg.concurrent_discriminators and x0.is_cuda and len(discs) > 1):
         return [call(d, x, ng) for d, x, ng in zip(discs, inputs, flags)]
@@ -41,7 +60,7 @@ def _run_concurrently(discs, inputs, no_grad=None, first_stream=0):
     for i, (d, x, s, ng) in enumerate(zip(discs, inputs, streams, flags)):
         s.wait_stream(cur)
         with torch.cuda.stream(s):
-            out[i] = call(d, x, ng)
+            out[i] = call(d, x, ng, s)
     for s in streams:
         cur.wait_stream(s)
     return out
@@ -104,12 +123,18 @@ class _SubDiscriminator(nn.Module):
     #: when True, the (discarded) discriminator weight gradients of the generator step are not computed
     #: if the input waveform itself requires grad.  Default False = the reference's exact behaviour.
     skip_param_grads_when_input_requires_grad = False
+    #: weight preparation shared between several passes of one run_discriminators call (set and cleared there)
+    _prep = None
+
+    def prepare(self, need_dgrad: bool = True) -> dict:
+        return prepare_stack(self._specs, _stack_params(self), getattr(self, "period", 1), need_dgrad=need_dgrad)
 
     def _run(self, x4: torch.Tensor) -> Tuple[torch.Tensor, List[torch.Tensor]]:
         if self._spectral:
             raise RuntimeError("use_spectral_norm=True is not supported by the lctgan kernels "
                                "(the reference's train.py never enables it)")
-        fmaps = conv_stack(x4, self._specs, _stack_params(self), self.skip_param_grads_when_input_requires_grad)
+        fmaps = conv_stack(x4, self._specs, _stack_params(self), self.skip_param_grads_when_input_requires_grad,
+                           prep=self._prep)
         return fmaps[-1], fmaps
 
 

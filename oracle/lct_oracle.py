@@ -581,6 +581,50 @@ def train_step(st: StepState, noisy: torch.Tensor, clean: torch.Tensor, mr_windo
             "adv": float(adv), "fm": float(fm), "g_grad_norm": float(gnorm) if gnorm is not None else float("nan")}
 
 
+# --------------------------------------------------------------------------------------
+# Callers on either side of the path
+# --------------------------------------------------------------------------------------
+
+def si_sdr(reference: torch.Tensor, estimate: torch.Tensor, eps: float = 1e-8) -> float:
+    """train.py:261-282 `_si_sdr_torch` for one (reference, estimate) pair of 1-D tensors."""
+    n = min(reference.shape[-1], estimate.shape[-1])
+    reference, estimate = reference[..., :n], estimate[..., :n]
+    reference = reference - reference.mean()
+    estimate = estimate - estimate.mean()
+    scale = torch.sum(reference * estimate) / (torch.sum(reference ** 2) + eps)
+    s_target = scale * reference
+    e_noise = estimate - s_target
+    return float(10.0 * torch.log10((torch.sum(s_target ** 2) + eps) / (torch.sum(e_noise ** 2) + eps)))
+
+
+def crop_pair(noisy: torch.Tensor, clean: torch.Tensor, segment_length: Optional[int], random_segment: bool,
+              generator: Optional[torch.Generator] = None):
+    """datasets/datasets.py:131-156 `LCTScpDataset._crop_pair`: same start for both waveforms; items no longer than the
+    segment are returned whole (the reference draws from the global generator; `generator` makes the draw explicit)."""
+    if segment_length is None:
+        return noisy, clean
+    m = min(noisy.shape[-1], clean.shape[-1])
+    if m <= segment_length:
+        return noisy, clean
+    max_start = m - segment_length
+    start = int(torch.randint(low=0, high=max_start + 1, size=(1,), generator=generator).item()) if random_segment \
+        else max_start // 2
+    return noisy[..., start:start + segment_length], clean[..., start:start + segment_length]
+
+
+def collate(items):
+    """datasets/datasets.py:187-230 `collate_fn` on a list of (noisy, clean) pairs: zero padding to the longest waveform
+    of the batch (either side), "lengths" = the noisy lengths."""
+    ln = torch.tensor([n.shape[-1] for n, _ in items], dtype=torch.long)
+    lc = torch.tensor([c.shape[-1] for _, c in items], dtype=torch.long)
+    T = int(max(ln.max(), lc.max()))
+    pn, pc = torch.zeros(len(items), T), torch.zeros(len(items), T)
+    for i, (n, c) in enumerate(items):
+        pn[i, :n.shape[-1]] = n
+        pc[i, :c.shape[-1]] = c
+    return {"noisy": pn, "clean": pc, "lengths": ln}
+
+
 def synthetic_batch(batch: int, samples: int, seed: int = 1234):
     """clean ~ N(0, 0.1^2), noisy = clean + N(0, 0.05^2), CPU generator."""
     g = torch.Generator().manual_seed(seed)

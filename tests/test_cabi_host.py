@@ -187,3 +187,93 @@ def test_data_parallel_gradient_exchange_gloo_world2(tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, o
         assert f"rank {r} ok" in o
+
+
+def test_length_buckets_and_crop_starts_host_logic():
+    """Host logic of the N3 / N4 rows: buckets cover every utterance once with bounded padding; the crop starts follow
+    `_crop_pair` (datasets/datasets.py:131-156) draw for draw - checked against the oracle restatement, which
+    tests/test_oracle_golden.py pins against the reference's own class."""
+    import torch
+    from lctgan.inference import length_buckets
+    from lctgan.pipeline import crop_starts
+    from util import oracle
+    O = oracle()
+    lens = [16000, 160000, 48000, 47000, 16001, 90000, 91000, 30000, 15999]
+    b = length_buckets(lens, max_batch=3, max_pad_ratio=1.1)
+    assert sorted(i for g in b for i in g) == list(range(len(lens)))
+    for g in b:
+        assert len(g) <= 3 and max(lens[i] for i in g) <= 1.1 * min(lens[i] for i in g)
+    assert length_buckets([5, 5, 5, 5], max_batch=16) == [[0, 1, 2, 3]]
+    # crop starts: same generator stream as the reference's per-item draws
+    gen = torch.Generator().manual_seed(11)
+    items = [(torch.randn(n, generator=gen), torch.randn(m, generator=gen))
+             for n, m in ((50000, 50000), (20000, 20000), (40000, 39000), (32000, 32000), (32001, 32005))]
+    ln = torch.tensor([a.shape[-1] for a, _ in items]); lc = torch.tensor([c.shape[-1] for _, c in items])
+    for random_segment in (True, False):
+        g1, g2 = torch.Generator().manual_seed(3), torch.Generator().manual_seed(3)
+        starts = crop_starts(ln, lc, 32000, random_segment, g1)
+        for i, (a, c) in enumerate(items):
+            ca, cc = O.crop_pair(a, c, 32000, random_segment, g2)
+            s = int(starts[i])
+            if min(a.shape[-1], c.shape[-1]) <= 32000:
+                assert s == 0 and ca.shape == a.shape
+            else:
+                assert torch.equal(ca, a[s:s + 32000]) and torch.equal(cc, c[s:s + 32000])
+    assert crop_starts(ln, lc, None, True).tolist() == [0] * 5
+
+
+_DP_HOOK_WORKER = r'''
+import os, sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import torch, torch.distributed as dist
+from lctgan.parallel import BackwardEndExchange, broadcast_parameters
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+torch.manual_seed(5)
+G = torch.nn.Linear(6, 6)                       # stands for the enhancer
+D = torch.nn.Sequential(torch.nn.Linear(6, 4), torch.nn.Tanh(), torch.nn.Linear(4, 1))      # a discriminator
+broadcast_parameters([G, D])
+Gr, Dr = torch.nn.Linear(6, 6), torch.nn.Sequential(torch.nn.Linear(6, 4), torch.nn.Tanh(), torch.nn.Linear(4, 1))
+Gr.load_state_dict(G.state_dict()); Dr.load_state_dict(D.state_dict())
+ex = BackwardEndExchange(G, [D])
+gen = torch.Generator().manual_seed(3)
+X = torch.randn(8, 6, generator=gen); Y = torch.randn(8, 6, generator=gen)
+xs, ys = X[rank * 4:(rank + 1) * 4], Y[rank * 4:(rank + 1) * 4]
+# --- the loop body of train_one_epoch, unmodified in structure (train.py:177-249): D step ...
+with torch.no_grad():
+    fake = G(xs)
+d_loss = ((D(ys) - 1) ** 2).mean() + (D(fake) ** 2).mean()
+d_loss.backward()                                # <- the exchange fires here, at the end of this backward
+assert ex.exchanges == {"g": 0, "d": 1}, ex.exchanges
+with torch.no_grad():
+    fr = Gr(X)
+(((Dr(Y) - 1) ** 2).mean() + (Dr(fr) ** 2).mean()).backward()
+for p, q in zip(D.parameters(), Dr.parameters()):
+    assert torch.allclose(p.grad, q.grad, atol=1e-6)
+d_before = [p.grad.clone() for p in D.parameters()]
+# --- ... G step: the backward reaches G AND D; only G is exchanged (the D gradients it produces are dead)
+g_loss = ((D(G(xs)) - 1) ** 2).mean()
+g_loss.backward()
+assert ex.exchanges == {"g": 1, "d": 1}, ex.exchanges
+((Dr(Gr(X)) - 1) ** 2).mean().backward()
+for p, q in zip(G.parameters(), Gr.parameters()):
+    assert torch.allclose(p.grad, q.grad, atol=1e-6)            # averaged BEFORE clip_grad_norm_ would run
+torch.nn.utils.clip_grad_norm_(G.parameters(), 5.0)
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_backward_end_exchange_for_the_unmodified_loop_gloo_world2(tmp_path):
+    """lctgan.parallel.BackwardEndExchange: data parallelism for the reference's unmodified train_one_epoch - the
+    exchange fires from an end-of-backward autograd callback (after d_loss.backward(), and after g_loss.backward()
+    before the clip), generator passes never exchange the dead discriminator gradients (SURVEY.md section 8e)."""
+    script = tmp_path / "dp_hook_worker.py"
+    script.write_text(_DP_HOOK_WORKER % (os.path.join(ROOT, "lct-gan_b200"), ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, o
+        assert f"rank {r} ok" in o

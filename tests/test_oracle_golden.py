@@ -220,3 +220,46 @@ def test_oracle_against_live_reference():
             del sys.modules[k]
         sys.modules.update(saved)
         sys.path[:] = path0
+
+
+@pytest.mark.skipif(not os.path.isdir(os.environ.get("LCT_REF", "/root/reference")),
+                    reason="reference checkout not present (it does not travel to the GPU box)")
+def test_oracle_tail_and_loader_helpers_against_live_reference():
+    """The oracle restatements of the callers either side of the path against the reference's own
+    code: `_si_sdr_torch` (train.py:261-282), `LCTScpDataset._crop_pair` (datasets.py:131-156), `collate_fn` (:187-230)."""
+    import importlib.util
+    import sys
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(os.path.dirname(GOLD), "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    saved = {k: v for k, v in sys.modules.items() if k.split(".")[0] in ("datasets", "models", "losses", "train")}
+    path0 = list(sys.path)
+    try:
+        R_stft, R_tf, R_losses, R_disc, R_gen, R_train = mg.import_reference()
+        import datasets.datasets as R_data
+        O = oracle()
+        g = torch.Generator().manual_seed(5)
+        ref, est = torch.randn(30000, generator=g) * 0.1 + 0.01, torch.randn(29000, generator=g) * 0.1
+        est = est + 0.7 * ref[:29000]
+        assert abs(O.si_sdr(ref, est) - R_train._si_sdr_torch(ref, est)) < 1e-4
+        ds = R_data.LCTScpDataset.__new__(R_data.LCTScpDataset)            # no files: only the cropping method is used
+        items = [(torch.randn(50000, generator=g), torch.randn(50000, generator=g)),
+                 (torch.randn(20000, generator=g), torch.randn(20000, generator=g)),
+                 (torch.randn(40000, generator=g), torch.randn(39000, generator=g))]
+        for random_segment in (True, False):
+            ds.segment_length, ds.random_segment = 32000, random_segment
+            torch.manual_seed(9)
+            want = [ds._crop_pair(a, c) for a, c in items]
+            torch.manual_seed(9)
+            got = [O.crop_pair(a, c, 32000, random_segment) for a, c in items]
+            for (wa, wc), (ga, gc) in zip(want, got):
+                assert torch.equal(wa, ga) and torch.equal(wc, gc)
+        batch = R_data.collate_fn([{"id": str(i), "noisy": a, "clean": c, "sr": 16000} for i, (a, c) in enumerate(want)])
+        mine = O.collate(want)
+        for k in ("noisy", "clean", "lengths"):
+            assert torch.equal(batch[k], mine[k]), k
+    finally:
+        for k in [k for k in sys.modules if k.split(".")[0] in ("datasets", "models", "losses", "train")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+        sys.path[:] = path0
