@@ -247,13 +247,20 @@ def _time_kernel(run, flush, iters=10):
     return sum(times) / len(times)
 
 
+#: dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel (ncu --set full, B = 8 instance:
+#: profiles/ncu_full_r2_conv_tc_raw.csv); None until that capture exists
+ROOFLINE_TRAFFIC_BYTES = None
+
+
 def measure_roofline(dev, peaks):
-    """Rooflines of the two kernels that matter, each timed alone with CUDA events on the launching stream:
+    """Rooflines of the kernels that matter, each timed alone with CUDA events on the launching stream:
 
     roofline        - the kernel family that dominates the step's GPU time (profiles/): the grouped discriminator
-                      convolutions on TF32 mma.sync, here the heaviest instance, the data gradient of MSD convs.1
-                      (16 -> 64 channels, k 41, stride 4, 4 groups, B = 8, L = 32000).  HBM bound (AI ~ 40 flop/B):
-                      algorithmic bytes = dY + FM gradient + saved activation read, dX written = 4 x 16.4 MB.
+                      convolutions; as in round 1 the instance is the data gradient of MSD convs.1 (16 -> 64 channels,
+                      k 41, stride 4, 4 groups, B = 8, L = 32000), now on tcgen05 (conv_tc.cu).  HBM bound (AI ~ 40
+                      flop/B): algorithmic bytes = dY + FM gradient + saved activation read, dX written = 4 x 16.4 MB.
+    roofline_family - forward / data gradient / weight gradient of the same layer at B = 8 and at the D step's 2B = 16,
+                      and of an MPD layer, with the kernel that runs each (tcgen05 or mma.sync, lctgan/ops.py).
     roofline_tensor - the one contraction above the ridge, MSD convs.5 (1024 -> 1024, k 5) on tcgen05:
                       algorithmic FLOPs = 2 B L Cin Cout K = 10.49 GFLOP.
     """
@@ -261,25 +268,49 @@ def measure_roofline(dev, peaks):
     from lctgan import ops
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
     g = torch.Generator(device="cpu").manual_seed(0)
-    # ---- grouped conv dgrad (MSD convs.1)
-    B, Cin, Cout, K, S, G, L = BATCH, 16, 64, 41, 4, 4, 32000
-    Lout = (L + 2 * (K // 2) - K) // S + 1
-    dy = torch.randn(B, Cout, Lout, 1, generator=g).to(dev)
-    w = (torch.randn(Cout, Cin // G, K, generator=g) / 13.0).to(dev)
-    xact = torch.randn(B, Cin, L, 1, generator=g).to(dev)
-    gextra = torch.randn(B, Cin, L, 1, generator=g).to(dev)
-    gw = torch.ones(Cout, 1, 1, device=dev)
-    _, _, imgs_d = ops.mt_weight_norm_fwd([gw], [w], [(K, S, K // 2, G)], 1)       # staged weight image, as in the step
-    ms = _time_kernel(lambda: ops.conv1d_dgrad(dy, w, (B, Cin, L, 1), G, S, K // 2, gextra=gextra, xact=xact,
-                                                act=ops.ACT_LRELU, wimg=imgs_d[0]), flush)
-    nbytes = 4.0 * (dy.numel() + 3 * xact.numel())
-    gbs = nbytes / (ms * 1e-3) / 1e9
-    roof = {"kernel": "conv_mma_kernel<dgrad> (MSD convs.1 data gradient: 64->16 ch, k=41, s=4, groups=4, B=8, L=32000, "
-                      "TF32 mma.sync, output tile transposed through shared memory, coalesced fused FM-gradient/LeakyReLU' pass)",
-            "bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
-            "traffic": 49.5e6, "traffic_note": "dram__bytes_read+write per launch, ncu --set full "
-            "(profiles/ncu_full_r1_disc_v4_raw.csv); the 16.4 MB output is still in the 126 MB L2 when the kernel ends",
-            "algorithmic_bytes": nbytes, "ms_per_launch": ms, "peak_source": peaks["src"] + " (STREAM-style copy)"}
+    family = {}
+    roof = None
+    for tag, (Bq, Cin, Cout, K, S, G, L, P) in (("msd_convs1_B8", (BATCH, 16, 64, 41, 4, 4, 32000, 1)),
+                                               ("msd_convs1_2B16", (2 * BATCH, 16, 64, 41, 4, 4, 32000, 1)),
+                                               ("mpd2_convs2_2B16", (2 * BATCH, 128, 512, 5, 3, 16, 1778, 2))):
+        pad = K // 2
+        Lout = (L + 2 * pad - K) // S + 1
+        x = torch.randn(Bq, Cin, L, P, generator=g).to(dev)
+        dy = torch.randn(Bq, Cout, Lout, P, generator=g).to(dev)
+        w = (torch.randn(Cout, Cin // G, K, generator=g) / (Cin // G * K) ** 0.5).to(dev)
+        bias = torch.zeros(Cout, device=dev)
+        gextra = torch.randn(Bq, Cin, L, P, generator=g).to(dev)
+        gw = torch.ones(Cout, 1, 1, device=dev)
+        _, imf, imd = ops.mt_weight_norm_fwd([gw], [w], [(K, S, pad, G)], P)      # staged weight images, as in the step
+        dw, db = torch.zeros_like(w), torch.zeros(Cout, device=dev)
+        runs = {
+            "fwd": (lambda: ops.conv1d_fwd(x, w, bias, G, S, pad, act=ops.ACT_LRELU, wimg=imf[0]),
+                    4.0 * (x.numel() + dy.numel()), "tcgen05" if ops._use_tc(Cin, Cout, K, G, S, pad, P) else "mma.sync"),
+            "dgrad": (lambda: ops.conv1d_dgrad(dy, w, (Bq, Cin, L, P), G, S, pad, gextra=gextra, xact=x,
+                                               act=ops.ACT_LRELU, wimg=imd[0]),
+                      4.0 * (dy.numel() + 3 * x.numel()),
+                      "tcgen05" if ops._use_tc_dgrad(Cin, Cout, K, G, S, pad, P) else "mma.sync"),
+            "wgrad": (lambda: ops.conv1d_wgrad(x, dy, w.shape, G, S, pad, dw=dw, db=db), 4.0 * (x.numel() + dy.numel()),
+                      "mma.sync"),
+        }
+        family[tag] = {}
+        for name, (run, nbytes, kern) in runs.items():
+            ms = _time_kernel(run, flush)
+            gbs = nbytes / (ms * 1e-3) / 1e9
+            family[tag][name] = {"kernel": kern, "us_per_launch": ms * 1e3, "achieved": gbs, "frac": gbs / peaks["hbm"],
+                                 "algorithmic_bytes": nbytes}
+            if tag == "msd_convs1_B8" and name == "dgrad":
+                roof = {"kernel": "conv_tc_kernel<dgrad> (MSD convs.1 data gradient: 64->16 ch, k=41, s=4, groups=4, B=8, "
+                                  "L=32000; tcgen05.mma kind::tf32 implicit GEMM over channel-quad planes in shared memory, "
+                                  "accumulators in TMEM, fused FM-gradient / LeakyReLU' epilogue with one float4 per row and "
+                                  "channel)",
+                        "bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
+                        "traffic": ROOFLINE_TRAFFIC_BYTES, "traffic_note": "dram__bytes_read+write per launch, ncu --set full "
+                        "(profiles/ncu_full_r2_conv_tc_raw.csv); the 16.4 MB output is still in the 126 MB L2 when the "
+                        "kernel ends",
+                        "algorithmic_bytes": nbytes, "ms_per_launch": ms, "peak_source": peaks["src"] + " (STREAM-style copy)",
+                        "bound_note": "above ~0.5 the tcgen05 form is bound by the tensor core's shared-memory operand "
+                                      "fetch (one 4 KB A tile per K = 8 MMA, N = 16), see DESIGN.md section 6"}
     # ---- dense conv forward on tcgen05 (MSD convs.5): the D step pushes clean + enhanced through as one batch of 2B
     C, K = 1024, 5
     w = (torch.randn(C, C, K, generator=g) / (C * K) ** 0.5).to(dev)
@@ -302,6 +333,7 @@ def measure_roofline(dev, peaks):
                                   "frac": per_shape[BATCH][0] / peaks["tensor"], "tiles": "128x64 (144 CTAs)"},
               "note": "bound by the per-SM TMA / L2 feed (~37 B/clk/SM measured), not by the tensor pipe: see DESIGN.md section 6",
               "peak_source": peaks["src"] + " (burst: kernel timed alone)"}
+    roof["family"] = family
     return roof, roof_t
 
 
@@ -464,7 +496,8 @@ def main():
                     "end of the G phase")
     ap.add_argument("--grouped-convs", default="tcgen05", choices=["tcgen05", "mma.sync"], help="A/B: grouped discriminator "
                     "convolutions on the tcgen05 kernels (conv_tc.cu, default) or on the round-1 mma.sync kernels")
-    ap.add_argument("--tc-ctas", type=int, default=0, help="A/B: CTAs per SM of the persistent tcgen05 conv grids")
+    ap.add_argument("--no-capture-nccl", action="store_true", help="N > 1: keep the NCCL all-reduces out of the CUDA graph "
+                    "(three graphs with eager exchanges in between) instead of capturing them inside the single graph")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--profile-range", action="store_true", help="bracket the timed steps with cudaProfilerStart/Stop "
                     "(for `ncu --profile-from-start off`: the launch list of exactly the timed steps; never a bench value)")
@@ -488,8 +521,6 @@ def main():
 
     from lctgan import _lib, config
     config.grouped_conv_tcgen05 = args.grouped_convs == "tcgen05"
-    if args.tc_ctas:
-        _lib.call_ret("lct_conv_tc_tune", args.tc_ctas)
     from lctgan.parallel import FlatGradAllReduce, broadcast_parameters
     from lctgan.training import (GraphedTrainStep, StepArgs, build_models, restore_state, snapshot_state,
                                  synthetic_batch, train_step)
@@ -499,8 +530,14 @@ def main():
                                                        fused_optim=not args.torch_optim)
     if world > 1:
         broadcast_parameters([enh, mpd, msd])
-    sync_d = FlatGradAllReduce(list(mpd.parameters()) + list(msd.parameters())) if world > 1 else None
-    sync_g = FlatGradAllReduce(list(enh.parameters())) if world > 1 else None
+    # data parallel: in-place all-reduce (SUM) of the gradient arenas the backward passes write, started per
+    # sub-discriminator as soon as its backward is done; the 1 / world_size is folded into the consumers (fused AdamW
+    # for the discriminators, the global-norm clip for the enhancer) - lctgan/parallel.py
+    fold = world > 1 and not args.torch_optim
+    sync_d = FlatGradAllReduce(list(mpd.parameters()) + list(msd.parameters()), fold_scale=fold) if world > 1 else None
+    sync_g = FlatGradAllReduce(list(enh.parameters()), fold_scale=fold) if world > 1 else None
+    if fold:
+        d_opt.grad_scale = sync_d.grad_scale
     sargs = StepArgs(gan_loss=args.gan_loss, reuse_enhancer_forward=not args.no_reuse,
                      batch_d_step=not args.no_reuse and not args.no_batch_d,
                      skip_dead_d_grads=args.skip_dead_d_grads, defer_dead_d_grads=not args.no_defer_dead_d_grads)
@@ -516,7 +553,7 @@ def main():
         # the whole D+G step (forward, backward, clip, both AdamW updates) as one CUDA graph over static buffers
         # (with N > 1: three graphs with the two NCCL gradient all-reduces launched eagerly in between)
         graphed = GraphedTrainStep(enh, mpd, msd, tf, mr, g_opt, d_opt, noisy_d, clean_d, sargs, after_d_backward=sync_d,
-                                   after_g_backward=sync_g, warmup=3)
+                                   after_g_backward=sync_g, warmup=3, capture_collectives=not args.no_capture_nccl)
 
     def step(n, c):
         if graphed is not None:
@@ -595,6 +632,7 @@ def main():
         return
     peaks = _peaks()
     roof, roof_t = (None, None) if args.no_roofline else measure_roofline(dev, peaks)
+    roof_family = roof.pop("family", None) if roof else None
     rtf = None if args.no_roofline else measure_enhance_rtf(dev)
     roof_fe = None if args.no_roofline else measure_frontend_rooflines(dev, peaks)
     cpu = torch_cuda = variants = None
@@ -621,7 +659,9 @@ def main():
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 (tcgen05 dense contraction) / tf32 (grouped discriminator convolutions) / 3xtf32 (generator GEMMs and convolutions) tensor-core operands with fp32 accumulation; f32 elsewhere",
         "data": "synthetic",
         "config": _config(args.gan_loss, world),
-        "schedule": {"cuda_graph": graphed is not None, "reuse_enhancer_forward": sargs.reuse_enhancer_forward,
+        "schedule": {"cuda_graph": graphed is not None, "graphs": len(graphed.graphs) if graphed is not None else 0,
+                     "nccl_captured": bool(graphed is not None and world > 1 and len(graphed.graphs) == 1),
+                     "capture_error": getattr(graphed, "capture_error", None), "reuse_enhancer_forward": sargs.reuse_enhancer_forward,
                      "batch_d_step": sargs.batch_d_step, "skip_dead_d_grads": sargs.skip_dead_d_grads,
                      "defer_dead_d_grads": sargs.defer_dead_d_grads, "fused_adamw": not args.torch_optim},
         "clocks": clocks,
@@ -630,6 +670,7 @@ def main():
         "gpu_launches": launches,
         "parity_check": parity,
         "roofline": roof,
+        "roofline_family": roof_family,
         "roofline_tensor": roof_t,
         "roofline_frontend": roof_fe,
         "enhance_rtf": rtf,

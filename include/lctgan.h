@@ -122,10 +122,6 @@ LCT_API int lct_conv_tc_image_len(int64_t Cin, int64_t Cout, int64_t G, int64_t 
 LCT_API int lct_conv_tc_images(const void* const* w, void* const* img_f, void* const* img_d, const int64_t* geo, int64_t n, cudaStream_t stream);
 LCT_API int lct_conv_tc_fwd(const float* x, const float* wimg, const float* bias, float* y, int64_t B, int64_t Cin, int64_t Cout, int64_t G, int64_t K, int64_t S, int64_t pad, int64_t Lin, int64_t P, int act, float slope, cudaStream_t stream);
 LCT_API int lct_conv_tc_dgrad(const float* dy, const float* wimg, float* dx, const float* gextra, const float* xact, int64_t B, int64_t Cin, int64_t Cout, int64_t G, int64_t K, int64_t S, int64_t pad, int64_t Lin, int64_t P, int act, float slope, cudaStream_t stream);
-LCT_API int lct_conv_tc_debug_buffer(float* buf);
-LCT_API int lct_conv_tc_last_grid(void);
-LCT_API int lct_conv_tc_tune(int ctas_per_sm);
-LCT_API int lct_conv_tc_wgrad(const float* x, const float* dy, float* dw, float* db, int64_t B, int64_t Cin, int64_t Cout, int64_t G, int64_t K, int64_t S, int64_t pad, int64_t Lin, int64_t P, cudaStream_t stream);
 
 /* The same grouped convolutions on the tensor cores: TF32 mma.sync implicit GEMM, fp32 accumulation, persistent CTAs with
  * cp.async double-buffered input windows (conv_mma.cu).  Same arguments as lct_conv1d_*; lct_conv_mma_supported says

@@ -1,5 +1,5 @@
 // Grouped strided convolutions of the waveform discriminators on the 5th-generation tensor cores
-// (tcgen05.mma kind::tf32, accumulators in TMEM), forward + data gradient + weight gradient.
+// (tcgen05.mma kind::tf32, accumulators in TMEM): forward and data gradient.
 //
 // Operator (reference models/discriminators.py:37-67, :93-98 PeriodDiscriminator; :166-196, :215-220
 // ScaleDiscriminator): convolution along L of [B, C, L, P] (P = period, 1 for the scale discriminators) with
@@ -21,10 +21,11 @@
 //   forward        D[m, co]       = sum_{k, ci} X[ci][S l + k - pad][p] W[co][ci][k]           M = positions, N = Cout/G
 //   data gradient  D[(q,p),(ci,r)] = sum_{o, co} dY[co][q + o][p] W[co][ci][r + pad - S o]     N = (Cin/G) x S phases
 //                  dX[ci][S q + r][p] = D;  one GEMM produces all S output phases, fused (+ FM gradient) x LeakyReLU'
-//   weight gradient (MN-major descriptors: positions are the contraction dim, 8 per MMA)
-//                  D_{rho,q}[(a, ci in quad q), co] = sum_m X[ci][S (l + a) + rho - pad][p] dY[co][l][p]
-//                  M = 16 tap slots x 4 channels (M-block stride SBO = 16 P walks the taps of one phase), N = Cout/G;
-//                  accumulators stay in TMEM across all tiles of a persistent CTA, one atomic flush per CTA.
+//   weight gradient: stays on the TF32 mma.sync kernel of conv_mma.cu.  Positions are its contraction dimension, so the
+//                  window operand would have to be MN-major (taps x channels contiguous per position); tools/umma_probe.cu
+//                  shows that tcgen05.mma kind::tf32 returns exact zeros for ANY MN-major operand in the no-swizzle
+//                  layout (K-major is exact for M = 64 and 128), and the K-major alternative needs four shifted copies
+//                  of every phase plane and reads 3 x the forward's operand bytes per tile - slower than mma.sync.
 // Weights arrive pre-arranged and tf32-rounded (round to nearest) as per-group images in exactly the shared-memory
 // layout (lct_conv_tc_images, one launch per layer stack).  Precision contract: TF32 operands rounded to nearest,
 // fp32 accumulation (tests/test_gpu_conv_mma.py: 2e-4 against fp64 on tf32-rounded operands).
@@ -338,6 +339,17 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvParams p) {
     const int grp = blockIdx.x;
     const int cbase_a = grp * g.ca;
 
+    // ---- the first tile's global loads go out before anything else: they fly during the set-up below
+    StagePlan<NQ, NIT> plan;
+    plan.init(p.a);
+    Staged<NQ, NIT> R0;
+    const int gstep = (int)gridDim.y;
+    int t0 = blockIdx.y;
+    if (t0 < p.ntiles) {
+        const int b = fdiv(t0, p.fT);
+        stage_load<NQ, NIT>(R0, plan, p.a, b, cbase_a, (t0 - b * p.tiles_per_b) * p.mtile);
+    }
+
     // ---- one-time setup: barrier, TMEM, weight image, descriptors, bias
     if (threadIdx.x == 0) {
         tc::mbar_init(mbar, 1);
@@ -362,8 +374,6 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvParams p) {
         const int n = threadIdx.x;
         bias_s[n] = (MODE == MODE_FWD && p.bias && n < g.cog) ? p.bias[grp * g.cog + n] : 0.f;
     }
-    StagePlan<NQ, NIT> plan;
-    plan.init(p.a);
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
@@ -371,21 +381,20 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvParams p) {
     const uint32_t idesc = tc::idesc_tf32(kTileM, g.Npad, 0, 0);
     const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
 
-    Staged<NQ, NIT> R;
-    int tile = blockIdx.y;
     uint32_t phase = 0;
-    if (tile < p.ntiles) {
-        const int b = fdiv(tile, p.fT);
-        stage_load<NQ, NIT>(R, plan, p.a, b, cbase_a, (tile - b * p.tiles_per_b) * p.mtile);
-    }
-    while (tile < p.ntiles) {
+    // One tile: registers -> shared memory, MMAs, epilogue.  `R` holds the tile's staged loads; as soon as they are in
+    // shared memory the same registers receive the next tile's loads, which fly during this tile's MMAs and epilogue.
+    // (A second register set = loads two tiles ahead was measured SLOWER, 263 -> 318 us over the 15 forward layers of
+    // tools/bench_disc_layers.py: the extra 30-60 registers cost one or two of the 4-6 resident CTAs per SM, and it is
+    // those CTAs that overlap one tile's MMA wait with another's loads.)
+    auto process = [&](Staged<NQ, NIT>& R, const int tile) {
         const int b = fdiv(tile, p.fT);
         const int m0 = (tile - b * p.tiles_per_b) * p.mtile;
         stage_store<NQ, NIT>(R, plan, p.a, A, m0);
         tc::fence_proxy_async_smem();            // st.shared (generic proxy) -> tcgen05.mma operand reads (async proxy)
         __syncthreads();
-        const int next = tile + gridDim.y;
-        if (next < p.ntiles) {                   // next tile's loads fly during this tile's MMAs and epilogue
+        const int next = tile + gstep;
+        if (next < p.ntiles) {
             const int nb = fdiv(next, p.fT);
             stage_load<NQ, NIT>(R, plan, p.a, nb, cbase_a, (next - nb * p.tiles_per_b) * p.mtile);
         }
@@ -507,13 +516,15 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvParams p) {
         tc::fence_before_sync();
         __syncthreads();                          // every warp has drained TMEM; the A planes may be overwritten
         tc::fence_after_sync();
-        tile = next;
+    };
+    while (t0 < p.ntiles) {
+        process(R0, t0);
+        t0 += gstep;
     }
     if (warp == 0) tc::tmem_dealloc<32>(tmem_base);
 }
 
 int g_tc_ctas_per_sm = 6;
-int g_tc_last_grid = 0;       // bring-up: CTAs of the last launch
 
 // Resident CTAs per SM of a 128-thread kernel, from its register count (queried once per instantiation), its dynamic
 // shared memory and its TMEM columns.  Computed by hand: cudaOccupancyMaxActiveBlocksPerMultiprocessor answered 1 on
@@ -547,11 +558,12 @@ int launch_conv(ConvParams& p, int G, cudaStream_t st) {
     static int regs = 0;
     int occ = resident_ctas(kern, regs, smem, 32);
     if (occ > g_tc_ctas_per_sm) occ = g_tc_ctas_per_sm;
-    int gy = 148 * occ / G;                 // persistent: one wave of resident CTAs
+    int gy = 148 * occ / G;                 // persistent: at most one wave of resident CTAs
     if (gy > p.ntiles) gy = p.ntiles;
     if (gy < 1) gy = 1;
     if (gy > 65535) gy = 65535;
-    g_tc_last_grid = G * gy;
+    const int rounds = (p.ntiles + gy - 1) / gy;            // every CTA of a group gets the same number of tiles (+- 1):
+    gy = (p.ntiles + rounds - 1) / rounds;                  // 504 tiles on 222 CTAs would be 3 rounds at 76 % fill
     kern<<<dim3((unsigned)G, (unsigned)gy), kThreads, smem, st>>>(p);
     LCT_RETURN_IF_LAUNCH_FAILED();
     return 0;
@@ -598,216 +610,6 @@ int dispatch_conv(ConvParams& p, int G, int nit, cudaStream_t st) {
     return LCT_EUNSUPPORTED;
 }
 
-
-// ---------------------------------------------------------------------------------------------------------
-// weight gradient
-// ---------------------------------------------------------------------------------------------------------
-struct WgradParams {
-    Geom g;                  // the FORWARD geometry of the layer (phases / taps of x)
-    SrcMap x, dy;
-    float* dw;               // [Cout][cig][K], accumulated
-    float* db;               // [Cout] (optional), accumulated
-    int B, Cin, Cout, Lin, Lout, Mtot;
-    int tiles_per_b, ntiles;
-    int x_bytes, dy_bytes;
-    int nqd, N;              // channel quads of dY per group; MMA N = Cout/G rounded up to 8
-    float* dbg;              // bring-up: raw accumulators of group 0, CTA y = 0: [nacc][128 lanes][N]
-    FastDiv fT;
-};
-
-// the dY tile (stride 1, one plane per quad): element e = tid + 128 it is slot e - p0
-template <int NQ, int NIT>
-__device__ __forceinline__ void stage_load_dy(Staged<NQ, NIT>& R, const SrcMap& s, int b, int cbase, int m0) {
-    const int u0 = fdiv(m0, s.fP);
-    const int64_t chs = (int64_t)s.Ls * s.P;
-    const int nE = s.Ls * s.P - u0 * s.P;                 // floats left in the channel row from the tile's first row
-    const float* row0 = s.src + ((int64_t)b * s.C + cbase) * chs + (int64_t)u0 * s.P + threadIdx.x;
-#pragma unroll
-    for (int it = 0; it < NIT; ++it) {
-        const bool ok = (int)threadIdx.x + kThreads * it < nE;
-#pragma unroll
-        for (int c = 0; c < NQ * 4; ++c)
-            R.v[it][c] = (ok && c < s.nch) ? ld_nc(row0 + c * chs + kThreads * it) : 0.f;
-    }
-}
-
-// like stage_store, for the dY tile, + per-thread bias-gradient partial sums (fp32, before rounding)
-template <int NQ, int NIT>
-__device__ __forceinline__ void stage_store_dy(const Staged<NQ, NIT>& R, const SrcMap& s, uint8_t* base, int m0,
-                                               float (&dbacc)[NQ * 4]) {
-    const int u0 = fdiv(m0, s.fP), p0 = m0 - u0 * s.P;
-    const int nrows = fdiv(p0 + s.nslots + s.P - 1, s.fP);
-    const int nE = nrows * s.P;
-#pragma unroll
-    for (int it = 0; it < NIT; ++it) {
-        const int e = (int)threadIdx.x + kThreads * it;
-        const int j = e - p0;
-        if (e < nE && j >= 0 && j < s.nslots) {
-            uint8_t* dst = base + (size_t)j * 16;
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) {
-                *reinterpret_cast<float4*>(dst + (size_t)q * s.PP) =
-                    make_float4(tc::tf32_rna(R.v[it][4 * q]), tc::tf32_rna(R.v[it][4 * q + 1]),
-                                tc::tf32_rna(R.v[it][4 * q + 2]), tc::tf32_rna(R.v[it][4 * q + 3]));
-#pragma unroll
-                for (int c = 0; c < 4; ++c) dbacc[4 * q + c] += R.v[it][4 * q + c];
-            }
-        }
-    }
-}
-
-template <int NQX, int NITX, int NQD, int TCOLS>
-__global__ void __launch_bounds__(kThreads) conv_tc_wgrad_kernel(const WgradParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* X = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
-    uint8_t* DY = X + p.x_bytes;
-    float* dbs = reinterpret_cast<float*>(DY + p.dy_bytes);     // [32]
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(dbs + 32);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
-
-    const Geom& g = p.g;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int grp = blockIdx.x;
-    if (threadIdx.x == 0) {
-        tc::mbar_init(mbar, 1);
-        tc::mbar_fence_init();
-    }
-    if (warp == 0) tc::tmem_alloc<TCOLS>(tmem_slot);
-    if (threadIdx.x < 32) dbs[threadIdx.x] = 0.f;
-    tc::fence_before_sync();
-    __syncthreads();
-    tc::fence_after_sync();
-    const uint32_t tmem_base = *tmem_slot;
-    // M = 64 (16 tap slots x 4 channels of one quad), N = p.N output channels, both operands MN-major
-    const uint32_t idesc = tc::idesc_tf32(64, p.N, 1, 1);
-    const uint32_t x_addr = tc::smem_u32(X), dy_addr = tc::smem_u32(DY);
-    const uint32_t sbo_x = (uint32_t)(g.P * 16);                       // next tap of the phase = P slots further
-    const uint32_t sbo_dy = NQD > 1 ? (uint32_t)p.dy.PP : 0u;          // next channel quad (one quad: N blocks alias it)
-    const int nacc = g.S * NQX;
-
-    StagePlan<NQX, NITX> planx;
-    planx.init(p.x);
-    Staged<NQX, NITX> Rx;
-    Staged<NQD, 2> Rd;
-    float dbacc[NQD * 4];
-#pragma unroll
-    for (int c = 0; c < NQD * 4; ++c) dbacc[c] = 0.f;
-
-    int tile = blockIdx.y;
-    uint32_t phase = 0;
-    bool first = true;
-    if (tile < p.ntiles) {
-        const int b = fdiv(tile, p.fT);
-        const int m0 = (tile - b * p.tiles_per_b) * kTileM;
-        stage_load<NQX, NITX>(Rx, planx, p.x, b, grp * g.cig, m0);
-        stage_load_dy<NQD, 2>(Rd, p.dy, b, grp * g.cog, m0);
-    }
-    while (tile < p.ntiles) {
-        const int b = fdiv(tile, p.fT);
-        const int m0 = (tile - b * p.tiles_per_b) * kTileM;
-        stage_store<NQX, NITX>(Rx, planx, p.x, X, m0);
-        stage_store_dy<NQD, 2>(Rd, p.dy, DY, m0, dbacc);
-        tc::fence_proxy_async_smem();
-        __syncthreads();
-        const int next = tile + gridDim.y;
-        if (next < p.ntiles) {
-            const int nb = fdiv(next, p.fT);
-            const int nm0 = (next - nb * p.tiles_per_b) * kTileM;
-            stage_load<NQX, NITX>(Rx, planx, p.x, nb, grp * g.cig, nm0);
-            stage_load_dy<NQD, 2>(Rd, p.dy, nb, grp * g.cog, nm0);
-        }
-        if (threadIdx.x == 0) {
-            tc::fence_after_sync();
-            for (int a = 0; a < nacc; ++a) {                 // accumulator a = (phase rho, x quad): plane index a
-                // (one K group per MMA, so only the M / N block stride matters: it is written to BOTH offset fields)
-                const uint64_t dx0 = tc::smem_desc(x_addr + (uint32_t)(a * p.x.PP), sbo_x, sbo_x);
-                const uint64_t dd0 = tc::smem_desc(dy_addr, sbo_dy, sbo_dy);
-                const uint32_t tcol = tmem_base + (uint32_t)(a * p.N);
-#pragma unroll 4
-                for (int ks = 0; ks < kTileM / 8; ++ks)      // 8 positions per MMA: + 8 slots = + 128 bytes (>> 4 = 8)
-                    tc::umma_tf32(tcol, dx0 + (uint64_t)(8 * ks), dd0 + (uint64_t)(8 * ks), idesc,
-                                  (uint32_t)(!(first && ks == 0)));
-            }
-            tc::umma_commit(mbar);
-        }
-        first = false;
-        tc::mbar_wait(mbar, phase);              // the MMAs have consumed this tile's planes
-        phase ^= 1;
-        tile = next;
-    }
-    tc::fence_after_sync();
-
-    // ---- flush: accumulator rows live in lanes 0..15 of every 32-lane quadrant (M = 64 data-path layout):
-    // row = 16 * warp + lane = 4 * tap + channel-in-quad
-    if (!first && p.dbg && blockIdx.x == 0 && blockIdx.y == 0) {
-        for (int a = 0; a < nacc; ++a)
-            for (int c0 = 0; c0 < p.N; c0 += 8) {
-                uint32_t v[8];
-                tc::tmem_ld8(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * p.N + c0), v);
-                tc::tmem_ld_wait();
-                for (int n = 0; n < 8; ++n) p.dbg[((size_t)a * 128 + warp * 32 + lane) * p.N + c0 + n] = __uint_as_float(v[n]);
-            }
-    }
-    if (!first) {
-        const int tap = 4 * warp + (lane >> 2), e = lane & 3;
-        for (int a = 0; a < nacc; ++a) {
-            const int rho = a / NQX, qx = a - rho * NQX;
-            const int ci = 4 * qx + e, k = g.S * tap + rho;
-            const bool rowok = lane < 16 && tap < g.ntap[rho] && ci < g.cig;
-            for (int c0 = 0; c0 < p.N; c0 += 8) {
-                uint32_t v[8];
-                tc::tmem_ld8(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * p.N + c0), v);
-                tc::tmem_ld_wait();
-                if (rowok) {
-#pragma unroll
-                    for (int n = 0; n < 8; ++n)
-                        if (c0 + n < g.cog)
-                            atomicAdd(p.dw + ((int64_t)(grp * g.cog + c0 + n) * g.cig + ci) * g.K + k, __uint_as_float(v[n]));
-                }
-            }
-        }
-        if (p.db) {
-#pragma unroll
-            for (int c = 0; c < NQD * 4; ++c) {
-                const float sum = warp_sum(dbacc[c]);
-                if (lane == 0 && c < g.cog) atomicAdd(&dbs[c], sum);
-            }
-        }
-    }
-    tc::fence_before_sync();
-    __syncthreads();
-    if (!first && p.db && threadIdx.x < g.cog) atomicAdd(p.db + grp * g.cog + threadIdx.x, dbs[threadIdx.x]);
-    if (warp == 0) {
-        tc::fence_after_sync();
-        tc::tmem_dealloc<TCOLS>(tmem_base);
-    }
-}
-
-int g_tc_wgrad_ctas_per_sm = 2;
-float* g_tc_dbg = nullptr;
-
-template <int NQX, int NITX, int NQD, int TCOLS>
-int launch_wgrad(WgradParams& p, int G, cudaStream_t st) {
-    const size_t smem = 128 + (size_t)p.x_bytes + p.dy_bytes + 32 * 4 + 16;
-    if (smem > 200 * 1024) return LCT_EUNSUPPORTED;
-    auto kern = conv_tc_wgrad_kernel<NQX, NITX, NQD, TCOLS>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return (int)e;
-        attr_set = true;
-    }
-    static int regs = 0;
-    int occ = resident_ctas(kern, regs, smem, TCOLS);
-    if (occ > g_tc_wgrad_ctas_per_sm) occ = g_tc_wgrad_ctas_per_sm;
-    int gy = 148 * occ / G;
-    if (gy > p.ntiles) gy = p.ntiles;
-    if (gy < 1) gy = 1;
-    if (gy > 65535) gy = 65535;
-    kern<<<dim3((unsigned)G, (unsigned)gy), kThreads, smem, st>>>(p);
-    LCT_RETURN_IF_LAUNCH_FAILED();
-    return 0;
-}
 
 float act_neg(int act, float slope) { return act == LCT_ACT_LRELU ? slope : (act == LCT_ACT_RELU ? 0.f : 1.f); }
 
@@ -911,66 +713,4 @@ LCT_API int lct_conv_tc_dgrad(const float* dy, const float* wimg, float* dx, con
     p.fT = make_fdiv(p.tiles_per_b);
     if (p.ntiles >= (1 << 20)) return LCT_EUNSUPPORTED;
     return dispatch_conv<MODE_DGRAD>(p, (int)G, nit, st);
-}
-
-LCT_API int lct_conv_tc_last_grid(void) { return g_tc_last_grid; }
-LCT_API int lct_conv_tc_tune(int ctas_per_sm) {          // bring-up only
-    if (ctas_per_sm > 0) g_tc_ctas_per_sm = ctas_per_sm;
-    return 0;
-}
-LCT_API int lct_conv_tc_debug_buffer(float* buf) {      // bring-up only (removed once the kernels are validated)
-    g_tc_dbg = buf;
-    return 0;
-}
-
-// dw [Cout][Cin/G][K] and db [Cout] (optional) are ACCUMULATED (the caller zeroes them): one atomic per weight and CTA
-LCT_API int lct_conv_tc_wgrad(const float* x, const float* dy, float* dw, float* db, int64_t B, int64_t Cin, int64_t Cout,
-                              int64_t G, int64_t K, int64_t S, int64_t pad, int64_t Lin, int64_t P, cudaStream_t st) {
-    Geom g;
-    if (!x || !dy || !dw || !make_geom(g, MODE_FWD, Cin, Cout, G, K, S, pad, P)) return LCT_EINVAL;
-    const int64_t Lout = (Lin + 2 * pad - K) / S + 1;
-    if (Lin + 2 * pad < K || !dims_ok(B, Cin, Cout, Lin, Lout, P)) return LCT_EINVAL;
-    int tapmax = 0;
-    for (int r = 0; r < g.S; ++r) tapmax = g.ntap[r] > tapmax ? g.ntap[r] : tapmax;
-    if (tapmax > 16) return LCT_EUNSUPPORTED;           // M = 64 = 16 tap slots x one channel quad
-    WgradParams p = {};
-    p.g = g;
-    p.dw = dw; p.db = db; p.dbg = g_tc_dbg;
-    p.B = (int)B; p.Cin = (int)Cin; p.Cout = (int)Cout; p.Lin = (int)Lin; p.Lout = (int)Lout;
-    p.Mtot = (int)(Lout * P);
-    p.tiles_per_b = (p.Mtot + kTileM - 1) / kTileM;
-    p.ntiles = p.B * p.tiles_per_b;
-    p.fT = make_fdiv(p.tiles_per_b);
-    if (p.ntiles >= (1 << 20)) return LCT_EUNSUPPORTED;
-    // x planes [rho][quad]: filled up to the taps that exist, allocated for the 16 tap slots an M = 64 operand spans
-    SrcMap& sx = p.x;
-    sx.src = x; sx.C = (int)Cin; sx.Ls = (int)Lin; sx.P = g.P; sx.Sg = g.S; sx.ishift = -g.pad; sx.nch = g.cig;
-    sx.nslots = kTileM + tapmax * g.P;
-    const int padmod = g.S == 4 ? 32 : (g.S == 3 ? 48 : (g.S == 2 ? 64 : 0));
-    sx.PP = (((kTileM + 16 * g.P) * 16 + 127) & ~127) + padmod;
-    sx.fP = make_fdiv(g.P); sx.fS = make_fdiv(g.S);
-    p.x_bytes = (g.S * g.nqa * sx.PP + 127) & ~127;
-    const int rows = (g.P - 1 + sx.nslots + g.P - 1) / g.P;
-    const int nitx = (g.S * rows * g.P + kThreads - 1) / kThreads;
-    // dY planes [quad]: 128 slots
-    SrcMap& sd = p.dy;
-    sd.src = dy; sd.C = (int)Cout; sd.Ls = (int)Lout; sd.P = g.P; sd.Sg = 1; sd.ishift = 0; sd.nch = g.cog;
-    sd.nslots = kTileM; sd.PP = kTileM * 16; sd.fP = make_fdiv(g.P); sd.fS = make_fdiv(1);
-    p.nqd = (g.cog + 3) / 4;
-    p.N = (g.cog + 7) & ~7;
-    p.dy_bytes = (p.nqd > 2 ? p.nqd : 2) * sd.PP;
-    const int rowsd = (g.P - 1 + kTileM + g.P - 1) / g.P;
-    if (rowsd * g.P > 2 * kThreads) return LCT_EUNSUPPORTED;
-    const int tcols = g.S * g.nqa * p.N;
-    const int nqx = g.nqa;
-#define LCT_WG(NQXV, NITV, NQDV, TC) return launch_wgrad<NQXV, NITV, NQDV, TC>(p, (int)G, st)
-    if (nqx == 1 && p.nqd == 4 && nitx <= 2 && tcols <= 32) LCT_WG(1, 2, 4, 32);
-    if (nqx == 1 && p.nqd == 4 && nitx <= 5 && tcols <= 64) LCT_WG(1, 5, 4, 64);
-    if (nqx == 1 && p.nqd == 1 && nitx <= 5 && tcols <= 32) LCT_WG(1, 5, 1, 32);
-    if (nqx == 1 && p.nqd == 8 && nitx <= 5 && tcols <= 128) LCT_WG(1, 5, 8, 128);
-    if (nqx == 2 && p.nqd == 8 && nitx <= 5 && tcols <= 256) LCT_WG(2, 5, 8, 256);
-    if (nqx == 2 && p.nqd == 4 && nitx <= 5 && tcols <= 128) LCT_WG(2, 5, 4, 128);
-    if (nqx == 4 && p.nqd == 4 && nitx <= 2 && tcols <= 64) LCT_WG(4, 2, 4, 64);
-#undef LCT_WG
-    return LCT_EUNSUPPORTED;
 }

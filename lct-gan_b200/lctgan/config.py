@@ -10,9 +10,6 @@ dense_tensor_cores = True
 #: operands read from shared memory through descriptors, accumulators in TMEM).  False = the round-1 TF32 mma.sync
 #: kernels (conv_mma.cu), kept for A/B measurements.
 grouped_conv_tcgen05 = True
-#: weight gradient of the same layers on tcgen05 (MN-major operand descriptors; under bring-up) - False = the TF32
-#: mma.sync weight-gradient kernel of conv_mma.cu
-grouped_wgrad_tcgen05 = False
 
 
 def set_precision(mode: str) -> None:

@@ -285,7 +285,8 @@ def _mma_ok(cin, cout, k, groups, stride, pad, P):
 #                  layers; the TF32 mma.sync kernel (conv_mma.cu) for the period discriminators' grouped layers, whose
 #                  128-row tiles carry too little data to hide the single-buffered tile pipeline's latencies
 #                  (35-78 vs 25-49 us)
-#   weight gradient  mma.sync (the tcgen05 form needs MN-major descriptors: config.grouped_wgrad_tcgen05)
+#   weight gradient  mma.sync: positions are the contraction dimension, which needs an MN-major window operand, and
+#                  tcgen05.mma kind::tf32 returns zeros for MN-major no-swizzle operands (tools/umma_probe.cu)
 def _use_tc(cin, cout, k, groups, stride, pad, P):
     return _tc_ok(cin, cout, k, groups, stride, pad, P) and not (cin // groups == 1 and stride == 1)
 
@@ -352,17 +353,6 @@ def conv_tc_dgrad(dy, img_d, x_shape, Cout, groups, K, stride, pad, gextra=None,
     dx = torch.empty(B, Cin, Lin, P, dtype=torch.float32, device=dy.device)
     call("lct_conv_tc_dgrad", dy, img_d, dx, gextra, xact, B, Cin, Cout, groups, K, stride, pad, Lin, P, act, slope)
     return dx
-
-
-def conv_tc_wgrad(x, dy, w_shape, groups, stride, pad, dw=None, db=None, want_bias=True):
-    B, Cin, Lin, P = x.shape
-    Cout, K = w_shape[0], w_shape[2]
-    if dw is None:
-        dw = zeros(tuple(w_shape), x.device)
-    if db is None and want_bias:
-        db = zeros((Cout,), x.device)
-    call("lct_conv_tc_wgrad", x, dy, dw, db, B, Cin, Cout, groups, K, stride, pad, Lin, P)
-    return dw, db
 
 
 def _is_post(cout, k, groups, stride, pad):
@@ -496,9 +486,6 @@ def conv1d_wgrad(x, dy, w_shape, groups, stride, pad, want_bias=True, dw=None, d
         db = zeros((Cout,), x.device)
     if _is_post(Cout, K, groups, stride, pad):
         call("lct_conv_post_wgrad", x, dy, dw, db, B, Cin, Lin, P, K)
-        return dw, db
-    if config.grouped_wgrad_tcgen05 and _tc_ok(Cin, Cout, K, groups, stride, pad, P):
-        call("lct_conv_tc_wgrad", x, dy, dw, db, B, Cin, Cout, groups, K, stride, pad, Lin, P)
         return dw, db
     if _mma_ok(Cin, Cout, K, groups, stride, pad, P):
         call("lct_conv_mma_wgrad", x, dy, dw, db, B, Cin, Cout, groups, K, stride, pad, Lin, P)

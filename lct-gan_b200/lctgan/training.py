@@ -155,6 +155,10 @@ def _phase_opt_g(M, args: StepArgs, pre_scale: float = 1.0) -> None:
                             pre_scale=pre_scale)
         else:
             torch.nn.utils.clip_grad_norm_(enhancer.parameters(), args.grad_clip)
+    elif pre_scale != 1.0:
+        # no clip to fold the data-parallel 1 / world_size into: one pass over the gradient buffer instead
+        clip_grad_norm_(enhancer.parameters(), float("inf"), arena=getattr(enhancer.gen, "_grad_arena", None),
+                        pre_scale=pre_scale)
     g_opt.step()
 
 

@@ -12,9 +12,6 @@ from lctgan import config, ops
 dev = torch.device("cuda:0")
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 config.grouped_conv_tcgen05 = not (len(sys.argv) > 2 and sys.argv[2] == "mma")
-if len(sys.argv) > 3:
-    from lctgan import _lib as _l
-    _l.call_ret("lct_conv_tc_tune", int(sys.argv[3]))
 print("kernels:", "tcgen05 (conv_tc.cu)" if config.grouped_conv_tcgen05 else "mma.sync (conv_mma.cu)", flush=True)
 
 
@@ -66,8 +63,6 @@ for name, Cin, Cout, K, S, G, Lin, P in LAYERS:
     t_w = gtime(lambda: ops.conv1d_wgrad(x, dy, w.shape, G, S, pad, dw=dw, db=db))
     bx, by = x.numel() * 4, y.numel() * 4
     tot[0] += t_f; tot[1] += t_d; tot[2] += t_w
-    from lctgan import _lib
-    name = f"{name}[{_lib.call_ret('lct_conv_tc_last_grid')}]" if config.grouped_conv_tcgen05 else name
     print(f"{name:19s} B={B:2d} x {bx/1e6:6.1f} MB y {by/1e6:6.1f} MB: fwd {t_f:6.1f} us ({(bx+by)/t_f/1e3:5.0f} GB/s)  "
           f"dgrad {t_d:6.1f} us ({(3*bx+by)/t_d/1e3:5.0f} GB/s)  wgrad {t_w:6.1f} us ({(bx+by)/t_w/1e3:5.0f} GB/s)", flush=True)
 print(f"sum: fwd {tot[0]:.1f} us  dgrad {tot[1]:.1f} us  wgrad {tot[2]:.1f} us")

@@ -7,10 +7,11 @@ sys.path.insert(0, os.path.join(ROOT, "lct-gan_b200")); sys.path.insert(0, ROOT)
 import torch
 from lctgan import ops
 dev = torch.device("cuda:0")
-B = 16
-LAYERS = ((16, 64, 41, 4, 4, 32000, 1), (512, 1024, 5, 3, 64, 593, 2))
+# (B, Cin, Cout, K, S, G, Lin, P): bench.py's roofline instance (MSD convs.1 at B = 8), the same layer at the D step's 2B = 16
+# and an MPD layer (forward on tcgen05, data gradient on mma.sync)
+LAYERS = ((8, 16, 64, 41, 4, 4, 32000, 1), (16, 16, 64, 41, 4, 4, 32000, 1), (16, 512, 1024, 5, 3, 64, 593, 2))
 state = []
-for (Cin, Cout, K, S, G, Lin, P) in LAYERS:
+for (B, Cin, Cout, K, S, G, Lin, P) in LAYERS:
     pad = K // 2
     x = torch.randn(B, Cin, Lin, P, device=dev)
     w = torch.randn(Cout, Cin // G, K, device=dev) * 0.05
@@ -18,10 +19,11 @@ for (Cin, Cout, K, S, G, Lin, P) in LAYERS:
     gw = torch.ones(Cout, 1, 1, device=dev)
     _, imf, imd = ops.mt_weight_norm_fwd([gw], [w], [(K, S, pad, G)], P)
     y = ops.conv1d_fwd(x, w, b, G, S, pad, act=ops.ACT_LRELU, wimg=imf[0])
-    state.append((x, w, b, imf, imd, torch.randn_like(y), (G, S, pad)))
-for rep in range(2):          # launches 0-3: warm-up pass; 4-7 (+4 of the set-up above = skip 8): profiled
-    for (x, w, b, imf, imd, dy, (G, S, pad)) in state:
+    state.append((x, w, b, imf, imd, torch.randn_like(y), torch.randn_like(x), (G, S, pad)))
+for rep in range(2):          # first pass: warm-up (instruction cache, launch-configuration caches); second: profiled
+    for (x, w, b, imf, imd, dy, ge, (G, S, pad)) in state:
         y = ops.conv1d_fwd(x, w, b, G, S, pad, act=ops.ACT_LRELU, wimg=imf[0])
-        dx = ops.conv1d_dgrad(dy, w, x.shape, G, S, pad, gextra=x, xact=x, act=ops.ACT_LRELU, wimg=imd[0])
+        dx = ops.conv1d_dgrad(dy, w, x.shape, G, S, pad, gextra=ge, xact=x, act=ops.ACT_LRELU, wimg=imd[0])
+        dw, db = ops.conv1d_wgrad(x, dy, w.shape, G, S, pad)
 torch.cuda.synchronize()
 print("done")
