@@ -164,9 +164,9 @@ LCT_API int lct_layernorm_bwd(const float* dy, const float* x, const float* gamm
 /* The recurrent part of the 4 (x2 directions) nn.GRU(16,16) of a block (generator.py:94-110, :211-222).
  * gi [rows,GD,48] = W_ih x + b_ih; whh [GD,48,16]; bhh [GD,48]; hs [rows,GD,16].  gd = group*D + dir, dir 1 = reverse.
  * Sequence s starts at row (s/inner)*outer_stride + (s%inner)*inner_stride and steps by step_stride rows. */
-LCT_API int lct_gru_fwd(const float* gi, const float* whh, const float* bhh, float* hs, int64_t nseq, int64_t L, int64_t GD, int64_t D, int64_t inner, int64_t outer_stride, int64_t inner_stride, int64_t step_stride, cudaStream_t stream);
+LCT_API int lct_gru_fwd(const float* gi, const float* whh, const float* bhh, float* hs, float* gsave, float* hprev, int64_t nseq, int64_t L, int64_t GD, int64_t D, int64_t inner, int64_t outer_stride, int64_t inner_stride, int64_t step_stride, cudaStream_t stream);
 /* BPTT: dh_in [rows,ldd] (column (gd/D)*16+j) -> dgi [rows,GD,48]; dwhh/dbih/dbhh accumulated. */
-LCT_API int lct_gru_bwd(const float* gi, const float* hs, const float* whh, const float* bhh, const float* dh_in, int64_t ldd, float* dgi, float* dwhh, float* dbih, float* dbhh, int64_t nseq, int64_t L, int64_t GD, int64_t D, int64_t inner, int64_t outer_stride, int64_t inner_stride, int64_t step_stride, cudaStream_t stream);
+LCT_API int lct_gru_bwd(const float* gsave, const float* hprev, const float* whh, const float* dh_in, int64_t ldd, float* dgi, float* dgh, int64_t nseq, int64_t L, int64_t GD, int64_t D, int64_t inner, int64_t outer_stride, int64_t inner_stride, int64_t step_stride, cudaStream_t stream);
 /* seq = x + sum_dir hs (generator.py:105-107, :128);  gsum (optional, row stride ldg) = the GRU output alone. */
 LCT_API int lct_gru_combine(const float* x, const float* hs, float* seq, float* gsum, int64_t ldg, int64_t M, int64_t G, int64_t D, cudaStream_t stream);
 /* softmax(q k^T / 4) v per head of nn.MultiheadAttention(64,4) (generator.py:133, :245); qkv [rows,3*16*heads]. */

@@ -25,6 +25,28 @@ extern std::atomic<int> g_lct_kernel_launches;
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// Resident CTAs per SM of a kernel, from its register count (queried once per instantiation: pass a static int as
+// cache), its threads, its dynamic shared memory and its TMEM columns (0 = none).  Computed by hand for the persistent
+// grids: cudaOccupancyMaxActiveBlocksPerMultiprocessor answered 1 on the first call of an instantiation and while a
+// stream was being captured (ncu, round 2: grids of 148 CTAs instead of 888).
+template <typename Kern>
+static inline int lct_resident_ctas(Kern kern, int& regs_cache, int threads, size_t smem, int tmem_cols) {
+    if (regs_cache == 0) {
+        cudaFuncAttributes fa;
+        regs_cache = (cudaFuncGetAttributes(&fa, kern) == cudaSuccess && fa.numRegs > 0) ? fa.numRegs : 128;
+        (void)cudaGetLastError();
+    }
+    const int regs = (regs_cache + 7) & ~7;                        // allocation granularity: 8 registers per thread
+    const int warps = (threads + 31) / 32;
+    int occ = 65536 / (regs * 32 * warps);
+    const int by_smem = (int)((227 * 1024) / (smem + 1024));      // + 1 KB reserved per CTA
+    if (by_smem < occ) occ = by_smem;
+    if (64 / warps < occ) occ = 64 / warps;
+    if (tmem_cols > 0 && 512 / tmem_cols < occ) occ = 512 / tmem_cols;
+    if (occ > 32) occ = 32;
+    return occ < 1 ? 1 : occ;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

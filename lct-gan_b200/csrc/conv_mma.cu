@@ -642,10 +642,8 @@ int launch_mma(MmaParams& p, cudaStream_t st) {
     const int G = p.Cx / p.Cxg;
     // persistent grid = what is really resident (registers / shared memory may allow fewer CTAs than the target:
     // a grid sized for more would run a second, mostly idle wave)
-    int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_mma_kernel<MODE, NT, MTW>, kThreads, smem) !=
-            cudaSuccess || occ < 1)
-        occ = 1;
+    static int regs = 0;                    // per instantiation
+    const int occ = lct_resident_ctas(conv_mma_kernel<MODE, NT, MTW>, regs, kThreads, smem, 0);
     dim3 grid((unsigned)G, (unsigned)grid_y(G, p.ntiles, occ < g_ctas_per_sm ? occ : g_ctas_per_sm));
     conv_mma_kernel<MODE, NT, MTW><<<grid, kThreads, smem, st>>>(p);
     LCT_RETURN_IF_LAUNCH_FAILED();
@@ -771,10 +769,8 @@ int launch_wgrad(MmaWgradParams& p, cudaStream_t st) {
     }
     const int G = p.Cin / p.Cig;
     // fewer, longer-lived CTAs than fwd/dgrad (every CTA ends with N x KK atomics), and never more than are resident
-    int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_mma_wgrad_kernel<MT, NT, NSPLIT>, kThreads * NSPLIT,
-                                                      smem) != cudaSuccess || occ < 1)
-        occ = 1;
+    static int regs = 0;                    // per instantiation
+    const int occ = lct_resident_ctas(conv_mma_wgrad_kernel<MT, NT, NSPLIT>, regs, kThreads * NSPLIT, smem, 0);
     const int per_sm = occ < g_wgrad_ctas_per_sm ? occ : g_wgrad_ctas_per_sm;
     int gy = 148 * per_sm / G;                // rounded down: no second wave
     if (gy > p.ntiles) gy = p.ntiles;

@@ -254,41 +254,47 @@ __device__ __forceinline__ void stage_store(const Staged<NQ, NIT>& R, const Stag
 // dX[ci][S q + r][p]; fused (+ FM gradient) x LeakyReLU'(saved activation).  S and C0 are compile-time so that the
 // column -> (ci, r) split costs nothing; VEC: S == 4, P == 1, 16-byte aligned rows -> one float4 per (row, channel).
 // o / ge / xa point at element (ci = 0, position S q, p) of dX / FM gradient / saved activation of this row.
-template <int S, int C0, bool VEC>
-__device__ __forceinline__ void dgrad_store16(const uint32_t (&v)[16], int ncol, int jrem, int P, int64_t chs,
-                                              float* o, const float* ge, const float* xa, float neg) {
-    if (VEC) {
+// The fused operands of the vector epilogue (S == 4, P == 1): FM gradient and saved activation of the <= 4 input channels
+// a tile row touches, one float4 (the 4 output phases) each.  They are requested BEFORE the wait on the tile's MMAs, all
+// at once, as 16-byte cp.async copies into the thread's own shared-memory slots (no registers held while they travel):
+// issued inside the epilogue - one channel at a time, behind the previous channel's store - they cost a DRAM round trip
+// per channel and tile with nothing else in flight.  Slot (array k, channel c, thread t) = fs[(k * 4 + c) * 128 + t].
+constexpr int kFusedBytes = 2 * 4 * kThreads * 16;
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tc::smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ void dgrad_fused_request(float4* fs, int nci, int64_t chs, const float* ge, const float* xa) {
 #pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-            const int col = C0 + 4 * c4;
-            if (col < ncol) {
-                const int64_t off = (int64_t)(col / 4) * chs;
-                float4 a = make_float4(__uint_as_float(v[4 * c4]), __uint_as_float(v[4 * c4 + 1]),
-                                       __uint_as_float(v[4 * c4 + 2]), __uint_as_float(v[4 * c4 + 3]));
-                if (ge) {
-                    const float4 g4 = __ldcs(reinterpret_cast<const float4*>(ge + off));
-                    a.x += g4.x; a.y += g4.y; a.z += g4.z; a.w += g4.w;
-                }
-                if (xa) {
-                    const float4 x4 = __ldcs(reinterpret_cast<const float4*>(xa + off));
-                    a.x *= x4.x > 0.f ? 1.f : neg; a.y *= x4.y > 0.f ? 1.f : neg;
-                    a.z *= x4.z > 0.f ? 1.f : neg; a.w *= x4.w > 0.f ? 1.f : neg;
-                }
-                *reinterpret_cast<float4*>(o + off) = a;
-            }
-        }
-        return;
+    for (int c = 0; c < 4; ++c) {
+        if (ge && c < nci) cp_async16(fs + c * kThreads + threadIdx.x, ge + (int64_t)c * chs);
+        if (xa && c < nci) cp_async16(fs + (4 + c) * kThreads + threadIdx.x, xa + (int64_t)c * chs);
     }
+    cp_async_commit();
+}
+
+// data-gradient epilogue of 16 accumulator columns [C0, C0 + 16) of one tile row (q, p): column n = ci * S + r is
+// dX[ci][S q + r][p]; fused (+ FM gradient) x LeakyReLU'(saved activation).  Vector form: S == 4, P == 1, 16-byte aligned
+// rows -> one float4 per (row, channel); o points at element (ci = 0, position 4 q) of dX.
+__device__ __forceinline__ void dgrad_store16_vec(const uint32_t (&v)[16], int ncol, int64_t chs, float* o, const float4* fs,
+                                                  bool has_g, bool has_x, float neg) {
 #pragma unroll
-    for (int n = 0; n < 16; ++n) {
-        const int col = C0 + n;
-        const int ci = col / S, r = col - ci * S;       // compile-time after unrolling
-        if (col < ncol && r < jrem) {                   // jrem = Lin - S q: positions left in this row of phases
-            const int64_t off = (int64_t)ci * chs + r * P;
-            float a = __uint_as_float(v[n]);
-            if (ge) a += ld_nc(ge + off);
-            if (xa) a *= ld_nc(xa + off) > 0.f ? 1.f : neg;
-            st_global(o + off, a);
+    for (int ci = 0; ci < 4; ++ci) {
+        if (4 * ci < ncol) {
+            float4 a = make_float4(__uint_as_float(v[4 * ci]), __uint_as_float(v[4 * ci + 1]), __uint_as_float(v[4 * ci + 2]),
+                                   __uint_as_float(v[4 * ci + 3]));
+            if (has_g) {
+                const float4 g4 = fs[ci * kThreads + threadIdx.x];
+                a.x += g4.x; a.y += g4.y; a.z += g4.z; a.w += g4.w;
+            }
+            if (has_x) {
+                const float4 x4 = fs[(4 + ci) * kThreads + threadIdx.x];
+                a.x *= x4.x > 0.f ? 1.f : neg; a.y *= x4.y > 0.f ? 1.f : neg;
+                a.z *= x4.z > 0.f ? 1.f : neg; a.w *= x4.w > 0.f ? 1.f : neg;
+            }
+            *reinterpret_cast<float4*>(o + (int64_t)ci * chs) = a;
         }
     }
 }
@@ -322,6 +328,7 @@ struct ConvParams {
     float neg;               // slope of the activation for negative inputs: LeakyReLU slope, ReLU 0, none 1
     int vec_ok;              // dgrad: dx / gextra / xact are 16-byte aligned
     FastDiv fT;
+    uint16_t aoff[kMaxMma];  // MMA j: offset of its first A chunk from the start of the planes, in 16-byte units
 };
 
 template <int MODE, int NQ, int NIT>
@@ -329,13 +336,14 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* A = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
     uint8_t* Bw = A + p.a_bytes;
-    uint4* descs = reinterpret_cast<uint4*>(Bw + p.b_bytes);           // [nmma] {A descriptor, B descriptor}
-    float* bias_s = reinterpret_cast<float*>(descs + kMaxMma);         // [32]
+    float* bias_s = reinterpret_cast<float*>(Bw + p.b_bytes);          // [32]
     uint64_t* mbar = reinterpret_cast<uint64_t*>(bias_s + 32);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+    float4* fused = reinterpret_cast<float4*>(tmem_slot + 2);          // [2][4][128] float4, vector data-gradient epilogue only
 
     const Geom& g = p.g;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp_u = tc::warp_uniform_id();
     const int grp = blockIdx.x;
     const int cbase_a = grp * g.ca;
 
@@ -361,15 +369,6 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvParams p) {
         float4* dst = reinterpret_cast<float4*>(Bw);
         for (int i = threadIdx.x; i < p.b_bytes / 16; i += kThreads) dst[i] = __ldg(src + i);
     }
-    for (int j = threadIdx.x; j < g.nmma; j += kThreads) {
-        int ph, tap, quad;
-        decode_mma(g, j, ph, tap, quad);
-        const uint32_t a_addr = tc::smem_u32(A) + (uint32_t)((ph * g.nqa + quad) * p.a.PP + tap * g.P * 16);
-        const uint32_t lbo = g.by_tap ? (uint32_t)(g.P * 16) : (uint32_t)p.a.PP;
-        const uint64_t da = tc::smem_desc(a_addr, lbo, 128);
-        const uint64_t db = tc::smem_desc(tc::smem_u32(Bw) + (uint32_t)(j * g.Npad * 32), (uint32_t)(g.Npad * 16), 128);
-        descs[j] = make_uint4((uint32_t)da, (uint32_t)(da >> 32), (uint32_t)db, (uint32_t)(db >> 32));
-    }
     if (threadIdx.x < 32) {
         const int n = threadIdx.x;
         bias_s[n] = (MODE == MODE_FWD && p.bias && n < g.cog) ? p.bias[grp * g.cog + n] : 0.f;
@@ -379,6 +378,11 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvParams p) {
     tc::fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t idesc = tc::idesc_tf32(kTileM, g.Npad, 0, 0);
+    // MMA j reads A chunks at planes + 16 aoff[j] (second chunk LBO further: next quad's plane, or next tap = 16 P bytes)
+    // and its [2][Npad][4] block of the weight image; only the start-address field of the descriptors changes
+    const uint64_t da0 = tc::smem_desc(tc::smem_u32(A), g.by_tap ? (uint32_t)(g.P * 16) : (uint32_t)p.a.PP, 128);
+    const uint64_t db0 = tc::smem_desc(tc::smem_u32(Bw), (uint32_t)(g.Npad * 16), 128);
+    const uint32_t bstep = (uint32_t)(g.Npad * 2);                      // 32 Npad bytes per MMA, in 16-byte units
     const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
 
     uint32_t phase = 0;
@@ -393,19 +397,36 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvParams p) {
         stage_store<NQ, NIT>(R, plan, p.a, A, m0);
         tc::fence_proxy_async_smem();            // st.shared (generic proxy) -> tcgen05.mma operand reads (async proxy)
         __syncthreads();
+        // one elected lane of warp 0 (a warp-uniform branch, so the descriptors stay in uniform registers and the MMAs
+        // go out back to back: see tc::elect_one) issues the tile's MMAs; the tensor core works from here on
+        if (warp_u == 0) {
+            if (tc::elect_one()) {
+                tc::fence_after_sync();
+#pragma unroll 4
+                for (int j = 0; j < g.nmma; ++j)
+                    tc::umma_tf32(tmem_base, da0 + (uint64_t)p.aoff[j], db0 + (uint64_t)((uint32_t)j * bstep), idesc,
+                                  (uint32_t)(j != 0));
+                tc::umma_commit(mbar);
+            }
+            __syncwarp();
+        }
         const int next = tile + gstep;
         if (next < p.ntiles) {
             const int nb = fdiv(next, p.fT);
             stage_load<NQ, NIT>(R, plan, p.a, nb, cbase_a, (next - nb * p.tiles_per_b) * p.mtile);
         }
-        if (threadIdx.x == 0) {
-            tc::fence_after_sync();
-#pragma unroll 2
-            for (int j = 0; j < g.nmma; ++j) {
-                const uint4 d = descs[j];
-                tc::umma_tf32(tmem_base, ((uint64_t)d.y << 32) | d.x, ((uint64_t)d.w << 32) | d.z, idesc, (uint32_t)(j != 0));
-            }
-            tc::umma_commit(mbar);
+        // data gradient, vector epilogue: tile row ml = q - q0 (P == 1); its fused operands are requested now and
+        // travel during the MMAs
+        const int64_t chs = (int64_t)p.Lin * g.P;
+        const bool vec = MODE == MODE_DGRAD && g.S == 4 && g.P == 1 && g.ncol <= 16 && (p.Lin & 3) == 0 && p.vec_ok;
+        int64_t vbase = 0;
+        bool vrow = false;
+        if (vec) {
+            const int ml = warp * 32 + lane;
+            vrow = m0 + ml < p.Mtot;
+            vbase = ((int64_t)b * p.Cin + (int64_t)grp * g.cig) * chs + 4 * (int64_t)(m0 + ml);
+            if (vrow)
+                dgrad_fused_request(fused, g.cig, chs, p.gextra ? p.gextra + vbase : nullptr, p.xact ? p.xact + vbase : nullptr);
         }
         tc::mbar_wait(mbar, phase);
         phase ^= 1;
@@ -438,33 +459,22 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvParams p) {
                 }
             }
         } else {
-            // tile row ml = (q - q0, p) (dgrad tiles hold whole rows of P): dX[ci][S q + r][p] for the S phases r
-            const int ml = warp * 32 + lane;
-            const int qrel = fdiv(ml, p.a.fP), pp = ml - qrel * g.P;
-            const int q0 = fdiv(m0, p.a.fP);
-            const int q = q0 + qrel;
-            const bool rowok = ml < p.mtile && m0 + ml < p.Mtot;
-            const int64_t chs = (int64_t)p.Lin * g.P;
-            const int64_t cb = ((int64_t)b * p.Cin + (int64_t)grp * g.cig) * chs;
-            const bool vec = g.S == 4 && g.P == 1 && (p.Lin & 3) == 0 && p.vec_ok;
             if (vec) {
                 // one float4 (the 4 output phases) per row and channel: consecutive lanes, consecutive 16 bytes
-                const int64_t base = cb + (int64_t)(4 * q);
-                float* o = p.out + base;
-                const float* ge = p.gextra ? p.gextra + base : nullptr;
-                const float* xa = p.xact ? p.xact + base : nullptr;
                 uint32_t v[16];
                 tc::tmem_ld16(trow, v);
                 tc::tmem_ld_wait();
-                if (rowok) dgrad_store16<4, 0, true>(v, g.ncol, 4, 1, chs, o, ge, xa, p.neg);
-                if (g.Npad > 16) {
-                    tc::tmem_ld16(trow + 16u, v);
-                    tc::tmem_ld_wait();
-                    if (rowok) dgrad_store16<4, 16, true>(v, g.ncol, 4, 1, chs, o, ge, xa, p.neg);
-                }
+                cp_async_wait_all();
+                if (vrow) dgrad_store16_vec(v, g.ncol, chs, p.out + vbase, fused, p.gextra != nullptr, p.xact != nullptr, p.neg);
             } else {
-                // stage the tile in shared memory (over the operand planes: their MMAs are complete), then one
+                // tile row ml = (q - q0, p) (dgrad tiles hold whole rows of P): dX[ci][S q + r][p] for the S phases r.
+                // Stage the tile in shared memory (over the operand planes: their MMAs are complete), then one
                 // coalesced pass per channel over the contiguous run of S * rows * P outputs this tile owns
+                const int ml = warp * 32 + lane;
+                const int qrel = fdiv(ml, p.a.fP), pp = ml - qrel * g.P;
+                const int q0 = fdiv(m0, p.a.fP);
+                const bool rowok = ml < p.mtile && m0 + ml < p.Mtot;
+                const int64_t cb = ((int64_t)b * p.Cin + (int64_t)grp * g.cig) * chs;
                 float* T = reinterpret_cast<float*>(A);
                 float* t = T + g.S * ml - (g.S - 1) * pp;
 #define LCT_DS(SV, C0V) dgrad_stage16<SV, C0V>(v, g.ncol, t, p.TS, g.P)
@@ -526,27 +536,10 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvParams p) {
 
 int g_tc_ctas_per_sm = 6;
 
-// Resident CTAs per SM of a 128-thread kernel, from its register count (queried once per instantiation), its dynamic
-// shared memory and its TMEM columns.  Computed by hand: cudaOccupancyMaxActiveBlocksPerMultiprocessor answered 1 on
-// the first call of an instantiation and while a stream was being captured (ncu: grids of 148 CTAs instead of 888).
-template <typename Kern>
-int resident_ctas(Kern kern, int& regs_cache, size_t smem, int tmem_cols) {
-    if (regs_cache == 0) {
-        cudaFuncAttributes fa;
-        regs_cache = (cudaFuncGetAttributes(&fa, kern) == cudaSuccess && fa.numRegs > 0) ? fa.numRegs : 128;
-        (void)cudaGetLastError();
-    }
-    const int regs = (regs_cache + 7) & ~7;                       // allocation granularity: 8 registers per thread
-    int occ = 65536 / (regs * kThreads);
-    const int by_smem = (int)((227 * 1024) / (smem + 1024));      // + 1 KB reserved per CTA
-    if (by_smem < occ) occ = by_smem;
-    if (512 / tmem_cols < occ) occ = 512 / tmem_cols;
-    return occ < 1 ? 1 : occ;
-}
-
 template <int MODE, int NQ, int NIT>
 int launch_conv(ConvParams& p, int G, cudaStream_t st) {
-    const size_t smem = 128 + (size_t)p.a_bytes + p.b_bytes + kMaxMma * 16 + 32 * 4 + 16;
+    const bool vec = MODE == MODE_DGRAD && p.g.S == 4 && p.g.P == 1 && p.g.ncol <= 16 && (p.Lin & 3) == 0 && p.vec_ok;
+    const size_t smem = 128 + (size_t)p.a_bytes + p.b_bytes + 32 * 4 + 32 + (vec ? kFusedBytes : 0);
     if (smem > 200 * 1024) return LCT_EUNSUPPORTED;
     auto kern = conv_tc_kernel<MODE, NQ, NIT>;
     static bool attr_set = false;           // per instantiation
@@ -556,7 +549,7 @@ int launch_conv(ConvParams& p, int G, cudaStream_t st) {
         attr_set = true;
     }
     static int regs = 0;
-    int occ = resident_ctas(kern, regs, smem, 32);
+    int occ = lct_resident_ctas(kern, regs, kThreads, smem, 32);
     if (occ > g_tc_ctas_per_sm) occ = g_tc_ctas_per_sm;
     int gy = 148 * occ / G;                 // persistent: at most one wave of resident CTAs
     if (gy > p.ntiles) gy = p.ntiles;
@@ -583,6 +576,11 @@ int setup_conv(ConvParams& p, const Geom& g, const float* src, int Csrc, int Ls)
     a.fP = make_fdiv(g.P); a.fS = make_fdiv(a.Sg);
     p.a_bytes = (g.nphase * g.nqa * a.PP + 127) & ~127;
     p.b_bytes = g.nmma * g.Npad * 32;
+    for (int j = 0; j < g.nmma; ++j) {
+        int ph, tap, quad;
+        decode_mma(g, j, ph, tap, quad);
+        p.aoff[j] = (uint16_t)(((ph * g.nqa + quad) * a.PP + tap * g.P * 16) >> 4);
+    }
     // elements per tile and channel: Sg * rows * P with rows <= ceil((P - 1 + nslots) / P)
     const int rows = (g.P - 1 + a.nslots + g.P - 1) / g.P;
     const int nE = a.Sg * rows * g.P;

@@ -23,6 +23,7 @@
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace {
 
@@ -133,6 +134,7 @@ dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp_u = tc::warp_uniform_id();
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
     const int tap = (EPI == EPI_WGRAD) ? blockIdx.z : 0;
 
@@ -157,7 +159,7 @@ dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0 && lane == 0) {
+    if (warp_u == 0 && tc::elect_one()) {
         // ===== TMA producer =====
         for (int kb = 0; kb < p.nkb; ++kb) {
             const int s = kb % STAGES;
@@ -169,8 +171,8 @@ dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             tma_load_2d(sa, &tmA, &full[s], p.a0 + kin * BK, m0 + kout * p.a_step1);
             tma_load_2d(sa + A_BYTES, &tmB, &full[s], p.b0 + kin * BK, n0 + kout * p.b_step1 + tap * p.b_tap_rows);
         }
-    } else if (warp == 1 && lane == 0) {
-        // ===== MMA issuer =====
+    } else if (warp_u == 1 && tc::elect_one()) {
+        // ===== MMA issuer (one elected lane of a warp-uniform branch: operands stay in uniform registers) =====
         constexpr uint32_t idesc = make_idesc(BM, BN);
         for (int kb = 0; kb < p.nkb; ++kb) {
             const int s = kb % STAGES;
@@ -188,7 +190,7 @@ dense_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             umma_commit(&empty[s]);          // arrives once these MMAs have consumed the smem slot
         }
         umma_commit(tmem_full);              // accumulator complete
-    } else if (warp >= 4) {
+    } else if (warp_u >= 4) {
         // ===== epilogue: TMEM lane = tile row; warp (w % 4) owns lanes [32 (w%4), +32) =====
         mbar_wait(tmem_full, 0);
         tc_fence_after();
@@ -260,6 +262,7 @@ dense_wgrad_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp_u = tc::warp_uniform_id();
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
 
     if (threadIdx.x == 0) {
@@ -283,7 +286,7 @@ dense_wgrad_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0 && lane == 0) {
+    if (warp_u == 0 && tc::elect_one()) {
         // ===== TMA producer: dY tile + the KT shifted X tiles of this k-block =====
         for (int kb = 0; kb < p.nkb; ++kb) {
             const int s = kb % STAGES;
@@ -296,8 +299,8 @@ dense_wgrad_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             for (int tap = 0; tap < KT; ++tap)
                 tma_load_2d(sa + A_BYTES + tap * B_BYTES, &tmB, &full[s], kb * BK, n0 + tap * p.b_tap_rows);
         }
-    } else if (warp == 1 && lane == 0) {
-        // ===== MMA issuer =====
+    } else if (warp_u == 1 && tc::elect_one()) {
+        // ===== MMA issuer (one elected lane of a warp-uniform branch: operands stay in uniform registers) =====
         constexpr uint32_t idesc = make_idesc(BM, BN);
         for (int kb = 0; kb < p.nkb; ++kb) {
             const int s = kb % STAGES;
@@ -316,7 +319,7 @@ dense_wgrad_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             umma_commit(&empty[s]);
         }
         umma_commit(tmem_full);
-    } else if (warp >= 4) {
+    } else if (warp_u >= 4) {
         // ===== epilogue: TMEM lane = co row; 8 ci x KT taps = 8 KT consecutive floats of dW per step =====
         mbar_wait(tmem_full, 0);
         tc_fence_after();

@@ -242,6 +242,7 @@ constexpr int kGruBwdUnits = kGruBwdThreads / kH;
 __global__ void __launch_bounds__(kGruThreads) gru_fwd_kernel(const float* __restrict__ gi,
                                                               const float* __restrict__ whh,
                                                               const float* __restrict__ bhh, float* __restrict__ hs,
+                                                              float* __restrict__ gsave, float* __restrict__ hprev,
                                                               SeqGeom geo, int GD, int D) {
     const int j = threadIdx.x % kH;
     const int seq = blockIdx.x * kUnitsPerCta + threadIdx.x / kH;
@@ -277,6 +278,11 @@ __global__ void __launch_bounds__(kGruThreads) gru_fwd_kernel(const float* __res
     }
     float* hrow = hs + ((row0 + (int64_t)step0 * geo.step_stride) * GD + gd) * kH + j;
     const int64_t hstep = (int64_t)dstep * geo.step_stride * GD * kH;
+    // training: the gates (r, z, n) and the recurrent part of the candidate (hn = W_hn h + b_hn) of every step, and the
+    // state each step started from, go out for the backward (which then neither recomputes a 16 x 48 mat-vec per step nor
+    // accumulates dW_hh in registers: profiles round 1, gru_bwd_kernel 129-156 us at 200-232 registers)
+    float* grow = gsave ? gsave + ((row0 + (int64_t)step0 * geo.step_stride) * GD + gd) * 4 * kH + j : nullptr;
+    float* prow = hprev ? hprev + ((row0 + (int64_t)step0 * geo.step_stride) * GD + gd) * kH + j : nullptr;
     for (int s0 = 0; s0 < geo.L; s0 += kGruPre) {
 #pragma unroll
         for (int u = 0; u < kGruPre; ++u) {
@@ -303,27 +309,32 @@ __global__ void __launch_bounds__(kGruThreads) gru_fwd_kernel(const float* __res
             const float r = gate_sigmoid(gr + hr);
             const float z = gate_sigmoid(gz + hz);
             const float n = gate_tanh(gn + r * hn);
+            if (valid && grow) {
+                float* g4 = grow + (int64_t)s * hstep * 4;
+                g4[0] = r; g4[kH] = z; g4[2 * kH] = n; g4[3 * kH] = hn;
+                prow[(int64_t)s * hstep] = h;
+            }
             h = (1.f - z) * n + z * h;
             if (valid) hrow[(int64_t)s * hstep] = h;
         }
     }
 }
 
-// BPTT.  dh_in: [rows, ldd] gradient of the GRU output (column (gd/D)*16 + j, shared by both
-// directions).  Writes dgi [rows, GD, 48]; accumulates dwhh [GD,48,16], dbih [GD,48], dbhh [GD,48].
-__global__ void __maxnreg__(200) gru_bwd_kernel(
-    const float* __restrict__ gi, const float* __restrict__ hs, const float* __restrict__ whh,
-    const float* __restrict__ bhh, const float* __restrict__ dh_in, int ldd, float* __restrict__ dgi,
-    float* __restrict__ dwhh, float* __restrict__ dbih, float* __restrict__ dbhh, SeqGeom geo, int GD, int D) {
-    __shared__ float sW[3 * kH * kH];
-    __shared__ float sB[6 * kH];
+// BPTT from the saved gates.  dh_in: [rows, ldd] gradient of the GRU output (column (gd/D)*16 + j, shared by both
+// directions).  Writes dgi [rows, GD, 48] = gradient of the input projections (dr, dz, dn pre-activation) and
+// dgh [rows, GD, 48] = gradient of the recurrent projections (dr, dz, dn * r); the parameter gradients are GEMMs /
+// column sums over those two arrays (dW_hh = dgh^T hprev, db_ih = colsum dgi, db_hh = colsum dgh: lctgan/gen_impl.py).
+// Per step and lane: 6 loads, the gate derivatives, a 16 x 48 transposed mat-vec (W_hh^T dgate) reduce-scattered over
+// the 16 lanes of the unit - no gate recomputation, no dW_hh accumulation (round 1: ~420 instructions per step).
+__global__ void __launch_bounds__(kGruBwdThreads) gru_bwd_kernel(
+    const float* __restrict__ gsave, const float* __restrict__ hprev, const float* __restrict__ whh,
+    const float* __restrict__ dh_in, int ldd, float* __restrict__ dgi, float* __restrict__ dgh, SeqGeom geo, int GD,
+    int D) {
     const int j = threadIdx.x % kH;
     const int seq = blockIdx.x * kGruBwdUnits + threadIdx.x / kH;
     const int gd = blockIdx.y;
     const bool valid = seq < geo.nseq;
     const bool rev = (gd % D) == 1;
-    for (int i = threadIdx.x; i < 3 * kH * kH; i += kGruBwdThreads) sW[i] = 0.f;
-    for (int i = threadIdx.x; i < 6 * kH; i += kGruBwdThreads) sB[i] = 0.f;
     float wr[kH], wz[kH], wn[kH];
     const float* w = whh + (size_t)gd * 3 * kH * kH;
 #pragma unroll
@@ -332,52 +343,35 @@ __global__ void __maxnreg__(200) gru_bwd_kernel(
         wz[i] = w[(1 * kH + j) * kH + i];
         wn[i] = w[(2 * kH + j) * kH + i];
     }
-    const float br = bhh[gd * 3 * kH + j], bz = bhh[gd * 3 * kH + kH + j], bn = bhh[gd * 3 * kH + 2 * kH + j];
-    float ar[kH], az[kH], an[kH];
-#pragma unroll
-    for (int i = 0; i < kH; ++i) ar[i] = az[i] = an[i] = 0.f;
-    float sbr = 0.f, sbz = 0.f, sbn_i = 0.f, sbn_h = 0.f;
     const int64_t row0 = valid ? seq_row0(geo, seq) : 0;
     const int64_t gstride = (int64_t)GD * 3 * kH;
     const int col = (gd / D) * kH + j;
     // walk the recurrence backwards: forward order was step = rev ? L-1..0 : 0..L-1
-    int step = rev ? 0 : geo.L - 1;
+    const int step = rev ? 0 : geo.L - 1;
     const int dstep = rev ? 1 : -1;   // direction of "previous forward step"
     float dh = 0.f;
-    // inputs of the next kGruPre steps in flight (see gru_fwd_kernel); it counts steps walked: s = L - 1 - it
-    float qr[kGruPre], qz[kGruPre], qn[kGruPre], qh[kGruPre], qd[kGruPre];
-    auto fetch = [&](int it, float& a, float& b, float& c, float& hpq, float& dq) {
-        a = b = c = hpq = dq = 0.f;
+    // inputs of the next kGruPre steps in flight (see gru_fwd_kernel); `it` counts steps walked
+    float qr[kGruPre], qz[kGruPre], qn[kGruPre], qm[kGruPre], qh[kGruPre], qd[kGruPre];
+    auto fetch = [&](int it, float& r, float& z, float& n, float& hn, float& hp, float& dq) {
+        r = z = n = hn = hp = dq = 0.f;
         if (valid && it < geo.L) {
             const int64_t rw = row0 + (int64_t)(step + it * dstep) * geo.step_stride;
-            const float* g0 = gi + rw * gstride + gd * 3 * kH;
-            a = g0[j]; b = g0[kH + j]; c = g0[2 * kH + j];
-            if (it < geo.L - 1) hpq = hs[((rw + (int64_t)dstep * geo.step_stride) * GD + gd) * kH + j];
+            const float* g4 = gsave + (rw * GD + gd) * 4 * kH + j;
+            r = g4[0]; z = g4[kH]; n = g4[2 * kH]; hn = g4[3 * kH];
+            hp = hprev[(rw * GD + gd) * kH + j];
             dq = dh_in[rw * ldd + col];
         }
     };
 #pragma unroll
-    for (int u = 0; u < kGruPre; ++u) fetch(u, qr[u], qz[u], qn[u], qh[u], qd[u]);
+    for (int u = 0; u < kGruPre; ++u) fetch(u, qr[u], qz[u], qn[u], qm[u], qh[u], qd[u]);
     for (int it0 = 0; it0 < geo.L; it0 += kGruPre) {
 #pragma unroll
     for (int u = 0; u < kGruPre; ++u) {
         const int it = it0 + u;
         if (it >= geo.L) break;
         const int64_t row = row0 + (int64_t)(step + it * dstep) * geo.step_stride;
-        const float gr = qr[u], gz = qz[u], gn = qn[u], hp = qh[u], dout = qd[u];
-        fetch(it + kGruPre, qr[u], qz[u], qn[u], qh[u], qd[u]);
-        float hpv[kH];
-        float hr = br, hz = bz, hn = bn;
-#pragma unroll
-        for (int i = 0; i < kH; ++i) {
-            hpv[i] = __shfl_sync(0xffffffffu, hp, i, kH);
-            hr = fmaf(wr[i], hpv[i], hr);
-            hz = fmaf(wz[i], hpv[i], hz);
-            hn = fmaf(wn[i], hpv[i], hn);
-        }
-        const float r = gate_sigmoid(gr + hr);
-        const float z = gate_sigmoid(gz + hz);
-        const float n = gate_tanh(gn + r * hn);
+        const float r = qr[u], z = qz[u], n = qn[u], hn = qm[u], hp = qh[u], dout = qd[u];
+        fetch(it + kGruPre, qr[u], qz[u], qn[u], qm[u], qh[u], qd[u]);
         const float dht = dh + dout;
         const float dn_pre = dht * (1.f - z) * (1.f - n * n);
         const float dz_pre = dht * (hp - n) * z * (1.f - z);
@@ -386,16 +380,12 @@ __global__ void __maxnreg__(200) gru_bwd_kernel(
         if (valid) {
             float* d0 = dgi + row * gstride + gd * 3 * kH;
             d0[j] = dr_pre; d0[kH + j] = dz_pre; d0[2 * kH + j] = dn_pre;
+            float* d1 = dgh + row * gstride + gd * 3 * kH;
+            d1[j] = dr_pre; d1[kH + j] = dz_pre; d1[2 * kH + j] = dhn;
         }
-        sbr += dr_pre; sbz += dz_pre; sbn_i += dn_pre; sbn_h += dhn;
         float c[kH];
 #pragma unroll
-        for (int i = 0; i < kH; ++i) {
-            ar[i] = fmaf(dr_pre, hpv[i], ar[i]);
-            az[i] = fmaf(dz_pre, hpv[i], az[i]);
-            an[i] = fmaf(dhn, hpv[i], an[i]);
-            c[i] = wr[i] * dr_pre + wz[i] * dz_pre + wn[i] * dhn;
-        }
+        for (int i = 0; i < kH; ++i) c[i] = wr[i] * dr_pre + wz[i] * dz_pre + wn[i] * dhn;
         // reduce-scatter c[] over the 16 lanes of the unit: lane i ends with sum_j c_j[i]
 #pragma unroll
         for (int off = kH / 2, len = kH / 2; off >= 1; off >>= 1, len >>= 1) {
@@ -411,27 +401,6 @@ __global__ void __maxnreg__(200) gru_bwd_kernel(
         }
         dh = dht * z + c[0];
     }
-    }
-    __syncthreads();
-    if (valid) {
-#pragma unroll
-        for (int i = 0; i < kH; ++i) {
-            atomicAdd(&sW[(0 * kH + j) * kH + i], ar[i]);
-            atomicAdd(&sW[(1 * kH + j) * kH + i], az[i]);
-            atomicAdd(&sW[(2 * kH + j) * kH + i], an[i]);
-        }
-        atomicAdd(&sB[j], sbr);
-        atomicAdd(&sB[kH + j], sbz);
-        atomicAdd(&sB[2 * kH + j], sbn_i);
-        atomicAdd(&sB[3 * kH + j], sbr);
-        atomicAdd(&sB[4 * kH + j], sbz);
-        atomicAdd(&sB[5 * kH + j], sbn_h);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 3 * kH * kH; i += kGruBwdThreads) atomicAdd(&dwhh[(size_t)gd * 3 * kH * kH + i], sW[i]);
-    for (int i = threadIdx.x; i < 3 * kH; i += kGruBwdThreads) {
-        atomicAdd(&dbih[gd * 3 * kH + i], sB[i]);
-        atomicAdd(&dbhh[gd * 3 * kH + i], sB[3 * kH + i]);
     }
 }
 
@@ -750,30 +719,31 @@ LCT_API int lct_layernorm_bwd(const float* dy, const float* x, const float* gamm
     return 0;
 }
 
-LCT_API int lct_gru_fwd(const float* gi, const float* whh, const float* bhh, float* hs, int64_t nseq, int64_t L,
-                        int64_t GD, int64_t D, int64_t inner, int64_t outer_stride, int64_t inner_stride,
-                        int64_t step_stride, cudaStream_t st) {
+// gsave [rows, GD, 4, 16] (r, z, n, W_hn h + b_hn) and hprev [rows, GD, 16] (state each step started from) are optional
+// outputs for the backward: pass both or neither
+LCT_API int lct_gru_fwd(const float* gi, const float* whh, const float* bhh, float* hs, float* gsave, float* hprev,
+                        int64_t nseq, int64_t L, int64_t GD, int64_t D, int64_t inner, int64_t outer_stride,
+                        int64_t inner_stride, int64_t step_stride, cudaStream_t st) {
     SeqGeom g;
-    if (!gi || !whh || !bhh || !hs || GD <= 0 || D <= 0 || GD % D || GD >= 65536 ||
-        !geom_ok(g, nseq, L, inner, outer_stride, inner_stride, step_stride))
+    if (!gi || !whh || !bhh || !hs || (gsave == nullptr) != (hprev == nullptr) || GD <= 0 || D <= 0 || GD % D ||
+        GD >= 65536 || !geom_ok(g, nseq, L, inner, outer_stride, inner_stride, step_stride))
         return LCT_EINVAL;
     dim3 grid((unsigned)ceil_div64(nseq, kUnitsPerCta), (unsigned)GD);
-    gru_fwd_kernel<<<grid, kGruThreads, 0, st>>>(gi, whh, bhh, hs, g, (int)GD, (int)D);
+    gru_fwd_kernel<<<grid, kGruThreads, 0, st>>>(gi, whh, bhh, hs, gsave, hprev, g, (int)GD, (int)D);
     LCT_RETURN_IF_LAUNCH_FAILED();
     return 0;
 }
 
-LCT_API int lct_gru_bwd(const float* gi, const float* hs, const float* whh, const float* bhh, const float* dh_in,
-                        int64_t ldd, float* dgi, float* dwhh, float* dbih, float* dbhh, int64_t nseq, int64_t L,
-                        int64_t GD, int64_t D, int64_t inner, int64_t outer_stride, int64_t inner_stride,
-                        int64_t step_stride, cudaStream_t st) {
+// dgi / dgh [rows, GD, 48]: gradients of the input / recurrent gate projections (see gru_bwd_kernel)
+LCT_API int lct_gru_bwd(const float* gsave, const float* hprev, const float* whh, const float* dh_in, int64_t ldd,
+                        float* dgi, float* dgh, int64_t nseq, int64_t L, int64_t GD, int64_t D, int64_t inner,
+                        int64_t outer_stride, int64_t inner_stride, int64_t step_stride, cudaStream_t st) {
     SeqGeom g;
-    if (!gi || !hs || !whh || !bhh || !dh_in || !dgi || !dwhh || !dbih || !dbhh || GD <= 0 || D <= 0 || GD % D ||
-        GD >= 65536 || !geom_ok(g, nseq, L, inner, outer_stride, inner_stride, step_stride))
+    if (!gsave || !hprev || !whh || !dh_in || !dgi || !dgh || GD <= 0 || D <= 0 || GD % D || GD >= 65536 ||
+        !geom_ok(g, nseq, L, inner, outer_stride, inner_stride, step_stride))
         return LCT_EINVAL;
     dim3 grid((unsigned)ceil_div64(nseq, kGruBwdUnits), (unsigned)GD);
-    gru_bwd_kernel<<<grid, kGruBwdThreads, 0, st>>>(gi, hs, whh, bhh, dh_in, (int)ldd, dgi, dwhh, dbih, dbhh, g, (int)GD,
-                                                 (int)D);
+    gru_bwd_kernel<<<grid, kGruBwdThreads, 0, st>>>(gsave, hprev, whh, dh_in, (int)ldd, dgi, dgh, g, (int)GD, (int)D);
     LCT_RETURN_IF_LAUNCH_FAILED();
     return 0;
 }

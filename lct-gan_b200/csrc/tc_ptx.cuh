@@ -7,6 +7,18 @@ namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// ---- single-thread issue -------------------------------------------------------------------------
+// tcgen05.mma / TMA instructions take their operands from UNIFORM registers.  Issued under `if (threadIdx.x == 0)` the
+// compiler cannot prove the operands warp-uniform and wraps EVERY instruction in an ELECT / R2UR / BRA.U.ANY loop:
+// tools/umma_rate.cu measured 220-260 cycles per MMA that way against 49 (M = 128, N = 16) when a whole warp takes a
+// provably uniform branch (`warp_uniform_id() == k`) and one lane is chosen with elect.sync.
+__device__ __forceinline__ int warp_uniform_id() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+__device__ __forceinline__ bool elect_one() {      // all 32 lanes of the warp must be converged here
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---- mbarrier ------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

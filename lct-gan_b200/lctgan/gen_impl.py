@@ -83,7 +83,10 @@ def _block_fwd(P, pre, x, B, T, F, freq, S):
     ops.gemm(xn, wih, gi, M, 3 * H, H, lda=C, ldb=H, ldc=GD * 3 * H, bias=bih, nbatch=GD, a_div=D, sA=H,
              sB=3 * H * H, sC=3 * H, sBias=3 * H)
     hs = torch.empty(M, GD, H, **f32)
-    ops.call("lct_gru_fwd", gi, whh, bhh, hs, geo[0], geo[1], GD, D, geo[2], geo[3], geo[4], geo[5])
+    # training: every step's gates and starting state are kept, the backward is then a pure chain of gate derivatives
+    gsave = torch.empty(M, GD, 4 * H, **f32) if S is not None else None
+    hprev = torch.empty(M, GD, H, **f32) if S is not None else None
+    ops.call("lct_gru_fwd", gi, whh, bhh, hs, gsave, hprev, geo[0], geo[1], GD, D, geo[2], geo[3], geo[4], geo[5])
     seq = torch.empty(M, C, **f32)
     cat = torch.empty(M, 2 * C, **f32) if freq else None
     ops.call("lct_gru_combine", x, hs, seq, cat, 2 * C, M, G, D)
@@ -111,8 +114,9 @@ def _block_fwd(P, pre, x, B, T, F, freq, S):
                  act=ACT_LRELU, slope=SLOPE, res=seq, ldr=C, out2=out, ldo=C)
         lin_in = a2
     if S is not None:
-        S[pre] = dict(x=x, xn=xn, mean1=mean1, rstd1=rstd1, gi=gi, hs=hs, seq=seq, sn=sn, mean2=mean2, rstd2=rstd2,
-                      qkv=qkv, ao=ao, lse=lse, mix=mix, lin_in=lin_in, wih=wih, whh=whh, bhh=bhh, geo=geo, D=D)
+        S[pre] = dict(x=x, xn=xn, mean1=mean1, rstd1=rstd1, seq=seq, sn=sn, mean2=mean2, rstd2=rstd2,
+                      qkv=qkv, ao=ao, lse=lse, mix=mix, lin_in=lin_in, wih=wih, whh=whh, gsave=gsave, hprev=hprev, geo=geo,
+                      D=D)
     return out
 
 
@@ -210,15 +214,19 @@ def _block_bwd(P, pre, dout, B, T, F, freq, S, GR, side=None, z=None):
     else:
         dgru = dseq
     dgi = torch.empty(M, GD, 3 * H, **f32)
-    dwhh, dbih, dbhh = z(GD, 3 * H, H), z(GD, 3 * H), z(GD, 3 * H)
-    ops.call("lct_gru_bwd", s["gi"], s["hs"], s["whh"], s["bhh"], dgru, C, dgi, dwhh, dbih, dbhh, geo[0], geo[1], GD, D,
-             geo[2], geo[3], geo[4], geo[5])
-    # dW_ih[gd] = dgi[:, gd, :]^T @ xn[:, g*16:(g+1)*16]
-    with side.fork(dgi):
-        dwih = z(GD, 3 * H, H)
-        ops.gemm(dgi, s["xn"], dwih, 3 * H, H, M, lda=GD * 3 * H, ldb=C, ldc=H, ta=True, tb=True,
-                 ksplit=max(1, 2 * ks // GD),
+    dgh = torch.empty(M, GD, 3 * H, **f32)
+    ops.call("lct_gru_bwd", s["gsave"], s["hprev"], s["whh"], dgru, C, dgi, dgh, geo[0], geo[1], GD, D, geo[2], geo[3],
+             geo[4], geo[5])
+    # dW_ih[gd] = dgi[:, gd, :]^T @ xn[:, g*16:(g+1)*16];  dW_hh[gd] = dgh[:, gd, :]^T @ hprev[:, gd, :];  biases = column sums
+    with side.fork(dgi, dgh):
+        ksg = max(1, 2 * ks // GD)
+        dwih, dwhh, dbih, dbhh = z(GD, 3 * H, H), z(GD, 3 * H, H), z(GD, 3 * H), z(GD, 3 * H)
+        ops.gemm(dgi, s["xn"], dwih, 3 * H, H, M, lda=GD * 3 * H, ldb=C, ldc=H, ta=True, tb=True, ksplit=ksg,
                  nbatch=GD, a_div=1, b_div=D, sA=3 * H, sB=H, sC=3 * H * H)
+        ops.gemm(dgh, s["hprev"], dwhh, 3 * H, H, M, lda=GD * 3 * H, ldb=GD * H, ldc=H, ta=True, tb=True, ksplit=ksg,
+                 nbatch=GD, a_div=1, b_div=1, sA=3 * H, sB=H, sC=3 * H * H)
+        ops.colsum(dgi, dbih, M, GD * 3 * H, GD * 3 * H)
+        ops.colsum(dgh, dbhh, M, GD * 3 * H, GD * 3 * H)
     # dxn[:, g] = dgi[:, g, (d,48)] @ [W_ih(g,0); W_ih(g,1)]
     dxn = torch.empty(M, C, **f32)
     ops.gemm(dgi, s["wih"], dxn, M, H, D * 3 * H, lda=GD * 3 * H, ldb=H, ldc=C, tb=True, nbatch=G, sA=D * 3 * H,

@@ -101,7 +101,14 @@ def test_gru_recurrence(dev, freq):
     ops.gemm(xd, wih.to(dev), gi, M, 48, 16, lda=64, ldb=16, ldc=GD * 48, bias=bih.to(dev), nbatch=GD, a_div=D, sA=16,
              sB=48 * 16, sC=48, sBias=48)
     hs = torch.empty(M, GD, 16, device=dev)
-    ops.call("lct_gru_fwd", gi, whh.to(dev), bhh.to(dev), hs, geo[0], geo[1], GD, D, geo[2], geo[3], geo[4], geo[5])
+    gsave = torch.empty(M, GD, 64, device=dev)
+    hprev = torch.empty(M, GD, 16, device=dev)
+    ops.call("lct_gru_fwd", gi, whh.to(dev), bhh.to(dev), hs, gsave, hprev, geo[0], geo[1], GD, D, geo[2], geo[3], geo[4],
+             geo[5])
+    hs_inf = torch.empty(M, GD, 16, device=dev)          # inference form: no saved gates, same states
+    ops.call("lct_gru_fwd", gi, whh.to(dev), bhh.to(dev), hs_inf, None, None, geo[0], geo[1], GD, D, geo[2], geo[3],
+             geo[4], geo[5])
+    assert torch.equal(hs, hs_inf)
     # bring the reference into [B,T,F] row order
     if freq:
         hs_ref_rows = hs_ref.reshape(M, GD, 16)
@@ -111,11 +118,16 @@ def test_gru_recurrence(dev, freq):
         gy_rows = gy.reshape(B, Fq, T, 64).permute(0, 2, 1, 3).reshape(M, 64)
     assert rel_err(hs, hs_ref_rows) < 2e-5
     dgi = torch.empty(M, GD, 48, device=dev)
+    dgh = torch.empty(M, GD, 48, device=dev)
     dwhh = torch.zeros(GD, 48, 16, device=dev)
     dbih = torch.zeros(GD, 48, device=dev)
     dbhh = torch.zeros(GD, 48, device=dev)
-    ops.call("lct_gru_bwd", gi, hs, whh.to(dev), bhh.to(dev), gy_rows.contiguous().to(dev), 64, dgi, dwhh, dbih, dbhh,
-             geo[0], geo[1], GD, D, geo[2], geo[3], geo[4], geo[5])
+    ops.call("lct_gru_bwd", gsave, hprev, whh.to(dev), gy_rows.contiguous().to(dev), 64, dgi, dgh, geo[0], geo[1], GD, D,
+             geo[2], geo[3], geo[4], geo[5])
+    ops.gemm(dgh, hprev, dwhh, 48, 16, M, lda=GD * 48, ldb=GD * 16, ldc=16, ta=True, tb=True, ksplit=2, nbatch=GD,
+             a_div=1, b_div=1, sA=48, sB=16, sC=48 * 16)
+    ops.colsum(dgi, dbih, M, GD * 48, GD * 48)
+    ops.colsum(dgh, dbhh, M, GD * 48, GD * 48)
     assert rel_err(dwhh, leaves[2].grad) < 1e-4
     assert rel_err(dbih, leaves[3].grad) < 1e-4
     assert rel_err(dbhh, leaves[4].grad) < 1e-4
