@@ -499,6 +499,11 @@ def main():
     ap.add_argument("--no-capture-nccl", action="store_true", help="N > 1: keep the NCCL all-reduces out of the CUDA graph "
                     "(three graphs with eager exchanges in between) instead of capturing them inside the single graph")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--late-ctas", type=int, default=None, help=argparse.SUPPRESS)
+    ap.add_argument("--late-streams", type=int, default=None, help=argparse.SUPPRESS)
+    ap.add_argument("--timeline", default=None, metavar="TRACE.json", help="record 2 steps with torch.profiler (CUPTI kernel "
+                    "activity: start, duration and stream of every kernel of the replayed graph) into a chrome trace and "
+                    "exit; tools/timeline_summary.py reads it")
     ap.add_argument("--profile-range", action="store_true", help="bracket the timed steps with cudaProfilerStart/Stop "
                     "(for `ncu --profile-from-start off`: the launch list of exactly the timed steps; never a bench value)")
     args = ap.parse_args()
@@ -521,6 +526,10 @@ def main():
 
     from lctgan import _lib, config
     config.grouped_conv_tcgen05 = args.grouped_convs == "tcgen05"
+    if args.late_ctas is not None:
+        config.late_param_grad_ctas = args.late_ctas
+    if args.late_streams is not None:
+        config.late_param_grad_streams = args.late_streams
     from lctgan.parallel import FlatGradAllReduce, broadcast_parameters
     from lctgan.training import (GraphedTrainStep, StepArgs, build_models, restore_state, snapshot_state,
                                  synthetic_batch, train_step)
@@ -585,6 +594,15 @@ def main():
     for _ in range(args.warmup):
         out = step(noisy_d, clean_d)
     barrier()
+
+    if args.timeline:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(2):
+                step(noisy_d, clean_d)
+            torch.cuda.synchronize()
+        prof.export_chrome_trace(args.timeline)
+        return
 
     # ---- device-resident throughput
     sampler = ClockSampler(local)

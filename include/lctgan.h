@@ -130,6 +130,8 @@ LCT_API int lct_conv_mma_supported(int64_t Cin, int64_t Cout, int64_t G, int64_t
 LCT_API int lct_conv_mma_image_geometry(int64_t Cin, int64_t Cout, int64_t G, int64_t K, int64_t S, int mode, int64_t* out);   /* out (HOST) = {KKpad, NS} of the staged weight image; mode 0 fwd, 1 dgrad */
 LCT_API int lct_conv_mma_fwd(const float* x, const float* w, const float* wimg, const float* bias, float* y, int64_t B, int64_t Cin, int64_t Cout, int64_t G, int64_t K, int64_t S, int64_t pad, int64_t Lin, int64_t P, int act, float slope, cudaStream_t stream);
 LCT_API int lct_conv_mma_dgrad(const float* dy, const float* w, const float* wimg, float* dx, const float* gextra, const float* xact, int64_t B, int64_t Cin, int64_t Cout, int64_t G, int64_t K, int64_t S, int64_t pad, int64_t Lin, int64_t P, int act, float slope, cudaStream_t stream);
+/* weight-gradient grids launched from now on target n resident CTAs per SM (0: default 2): the G step's dead gradients run with 1 beside the generator's backward */
+LCT_API int lct_set_wgrad_ctas(int n);
 LCT_API int lct_conv_mma_wgrad(const float* x, const float* dy, float* dw, float* db, int64_t B, int64_t Cin, int64_t Cout, int64_t G, int64_t K, int64_t S, int64_t pad, int64_t Lin, int64_t P, cudaStream_t stream);
 
 /* conv_post (C -> 1 channel, odd K <= 8, stride 1, pad K/2; discriminators.py:59-66, :188-196): channel-reduction kernels.

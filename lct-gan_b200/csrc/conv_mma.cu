@@ -740,12 +740,9 @@ LCT_API int lct_conv_mma_dgrad(const float* dy, const float* w, const float* wim
     }
 }
 
-// resident CTAs per SM targeted by the weight-gradient grid (LCT_WGRAD_CTAS overrides: tuning experiments)
-int g_wgrad_ctas_per_sm = [] {
-    const char* e = getenv("LCT_WGRAD_CTAS");
-    const int v = e ? atoi(e) : 0;
-    return v > 0 ? v : 2;      // 2 measured best in the whole step (3: +0.4 .. 1 %)
-}();
+// resident CTAs per SM targeted by the weight-gradient grid: 2 measured best in the whole step (3: +0.4 .. 1 %);
+// lct_set_wgrad_ctas(1) while the G step's dead gradients run beside the generator's backward (lctgan/config.py)
+int g_wgrad_ctas_per_sm = 2;
 
 template <int MT, int NT, int NSPLIT>
 int launch_wgrad(MmaWgradParams& p, cudaStream_t st) {
@@ -810,4 +807,11 @@ LCT_API int lct_conv_mma_wgrad(const float* x, const float* dy, float* dw, float
     }
 #undef LCT_WG
     return LCT_EUNSUPPORTED;
+}
+
+// n >= 1: weight-gradient grids of lct_conv_mma_wgrad launched from now on target n resident CTAs per SM; 0: the default.
+LCT_API int lct_set_wgrad_ctas(int n) {
+    if (n < 0 || n > 8) return LCT_EINVAL;
+    g_wgrad_ctas_per_sm = n > 0 ? n : 2;
+    return 0;
 }

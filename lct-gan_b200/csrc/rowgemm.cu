@@ -480,10 +480,8 @@ int launch_tn(const TnParams& p, int nbatch, cudaStream_t st) {
     const int nchunks = (p.R + 31) / 32;
     static_assert(WK == 1 || (size_t)WK * Mc * Nc <= (size_t)2 * 32 * (Mc + 8 + Nc + 8), "reduction fits the stages");
     // every CTA ends with M x N atomics: one CTA per SM for the large tiles; the 48 x 16 GRU blocks are latency bound
-    // (one k-step per warp and chunk) and want many resident CTAs instead.  LCT_TN_CTAS scales the target (tuning).
-    static const int scale_pct = [] { const char* e = getenv("LCT_TN_CTAS"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 100; }();
-    static const int gather_pct = [] { const char* e = getenv("LCT_TN_GATHER_CTAS"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 100; }();
-    const int target = (Mc * Nc >= 2048 ? 148 : 148 * 8) * scale_pct / 100 * (GATHER ? gather_pct : 100) / 100;
+    // (one k-step per warp and chunk) and want many resident CTAs instead.
+    const int target = Mc * Nc >= 2048 ? 148 : 148 * 8;
     int gx = target / nbatch;
     if (gx > nchunks) gx = nchunks;
     if (gx < 1) gx = 1;

@@ -81,15 +81,53 @@ def aux_stream_for(stream):
     return aux
 
 
-#: G step only (a sub-discriminator whose INPUT requires grad): finish the discriminator parameter gradients - weight
-#: gradient kernels, weight-norm backward and the accumulation into ``.grad`` - on the helper stream and join it when the
-#: caller says so (``join_deferred_param_grads()``, called by lctgan.training at the end of the G phase) instead of at the
-#: end of the sub-discriminator's backward.  train.py computes these gradients and never reads them (the next
-#: ``d_opt.zero_grad`` discards them), so nothing on the critical path waits for them: they overlap the generator's
-#: backward, whose kernels are small.  Values of every ``.grad`` after the join are unchanged.  Off by default because the
-#: gradients are only valid after the join; lctgan.training.StepArgs.defer_dead_d_grads turns it on.
+#: G step only (a sub-discriminator whose INPUT requires grad): do not run the discriminator parameter gradients - weight
+#: gradient kernels, weight-norm backward and the accumulation into ``.grad`` - inside the sub-discriminator's backward.
+#: train.py computes these gradients and never reads them (the next ``d_opt.zero_grad`` discards them), so nothing on the
+#: critical path waits for them.  The backward hands them over as one closure per sub-discriminator (``defer``); they are
+#: launched on low-priority helper streams when the generator's backward begins (``launch_deferred_param_grads``, called by
+#: lctgan.gen_impl) - its chain of small kernels leaves most SMs idle - and joined at the end of the G phase
+#: (``join_deferred_param_grads``, called by lctgan.training).  Launched earlier, as soon as their inputs exist, the wide
+#: weight-gradient grids sat in front of the loss-gradient / iSTFT-backward kernels the generator's backward waits for
+#: (CUPTI timeline, profiles/timeline_r2_*.txt: 0.7 ms).  Values of every ``.grad`` after the join are unchanged.  Off by
+#: default because the gradients are only valid after the join; lctgan.training.StepArgs.defer_dead_d_grads turns it on.
 defer_dead_param_grads = False
-_PENDING = []
+_LATE = []        # closures not launched yet
+_PENDING = []     # (helper stream, closure) launched, not joined yet
+_LATE_STREAMS = {}
+late_param_grad_streams = 3
+late_param_grad_ctas = 1
+
+
+def defer(fn) -> None:
+    """`fn()` enqueues, on the current stream, everything one sub-discriminator owes its parameters."""
+    _LATE.append(fn)
+
+
+def launch_deferred_param_grads() -> None:
+    """Start the deferred parameter-gradient work behind the current point of the current stream."""
+    import torch
+    if not _LATE:
+        return
+    cur = torch.cuda.current_stream()
+    key = (cur.device.index, cur.cuda_stream)
+    pool = _LATE_STREAMS.setdefault(key, [])
+    while len(pool) < late_param_grad_streams:
+        pool.append(torch.cuda.Stream(device=cur.device, priority=0))
+    for st in pool:
+        st.wait_stream(cur)
+    from ._lib import call_ret
+    call_ret("lct_set_wgrad_ctas", late_param_grad_ctas)     # narrow grids: the generator's kernels need the other half of an SM
+    try:
+        for i, fn in enumerate(_LATE):
+            st = pool[i % len(pool)]
+            with torch.cuda.stream(st):
+                fn()
+            _PENDING.append((st, fn))
+    finally:
+        call_ret("lct_set_wgrad_ctas", 0)
+        _LATE.clear()
+
 
 #: Data parallel (lctgan.parallel): called with the flat buffer that holds ALL parameter gradients of a sub-discriminator
 #: the moment its backward has produced them (D step only; lctgan.training sets and clears it around d_loss.backward()).
@@ -99,10 +137,10 @@ stack_grad_hook = None
 def join_deferred_param_grads() -> None:
     """Order the current stream after every deferred parameter-gradient chain and release the tensors kept for them."""
     import torch
+    launch_deferred_param_grads()
     if not _PENDING:
         return
     cur = torch.cuda.current_stream()
-    for aux, keep in _PENDING:
-        cur.wait_stream(aux)
-        keep.clear()
+    for st in {id(st): st for st, _ in _PENDING}.values():
+        cur.wait_stream(st)
     _PENDING.clear()

@@ -52,11 +52,43 @@ def prepare_stack(specs: Sequence[LayerSpec], params: Sequence[torch.Tensor], P:
     return dict(weights=weights, imgs_f=imgs_f, imgs_d=imgs_d, wt=wt, wd=wd)
 
 
+def stack_forward(x4: torch.Tensor, specs: Sequence[LayerSpec], params: Sequence[torch.Tensor], prep: dict,
+                  fmaps: List[torch.Tensor] = None, lo: int = 0, hi: int = None) -> List[torch.Tensor]:
+    """The stack's kernels for rows [lo, hi) of the batch x4 [B, 1, L, P]; every feature map is a buffer for the WHOLE
+    batch (allocated here when `fmaps` is None) of which only those rows are written.  Batch slices of the [B, C, L, P]
+    maps are contiguous, so a batch can be pushed through in parts - the D step's clean half while the generator is
+    still producing the enhanced half (models.discriminators.begin_split_forward) - and differentiated in one piece."""
+    n = len(specs)
+    B = x4.shape[0]
+    hi = B if hi is None else hi
+    weights, imgs_f = prep["weights"], prep["imgs_f"]
+    alloc = fmaps is None
+    if alloc:
+        fmaps = []
+    h_full = x4
+    for i, (k, s, pad, g) in enumerate(specs):
+        bias, w = params[3 * i], weights[i]
+        act = ops.ACT_NONE if i == n - 1 else ops.ACT_LRELU
+        Lin, P = h_full.shape[2], h_full.shape[3]
+        if alloc:
+            fmaps.append(torch.empty(B, w.shape[0], ops.conv_out_len(Lin, k, s, pad), P, dtype=torch.float32,
+                                     device=x4.device))
+        h, out = h_full[lo:hi], fmaps[i][lo:hi]
+        if i in prep["wt"]:
+            ops.dense_conv(ops.stage_nlc_bf16(h, pad), prep["wt"][i], hi - lo, Lin, w.shape[1], w.shape[0], k, bias=bias,
+                           act=act, slope=LRELU_SLOPE, out=out)
+        else:
+            ops.conv1d_fwd(h, w, bias, g, s, pad, act=act, slope=LRELU_SLOPE, wimg=imgs_f[i], out=out)
+        h_full = fmaps[i]
+    return fmaps
+
+
 class ConvStackFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x4, specs: Sequence[LayerSpec], skip_param_grads: bool, prep, *params):
         """x4: [B, 1, L, P]; params: (bias, weight_g, weight_v) per layer; prep: prepare_stack(...) of the same
-        parameters or None (prepared here).  Returns all feature maps."""
+        parameters or None (prepared here); prep["partial"] = (feature-map buffers, rows already done) continues a
+        forward that stack_forward began on the first rows of the batch.  Returns all feature maps."""
         if not x4.is_cuda:
             raise RuntimeError("lctgan discriminators are CUDA only (sm_100a); there is no CPU fallback")
         n = len(specs)
@@ -64,21 +96,10 @@ class ConvStackFn(torch.autograd.Function):
         x4 = x4.contiguous()
         if prep is None:
             prep = prepare_stack(specs, params, x4.shape[3], need_dgrad=False)
-        weights, imgs_f, imgs_d = prep["weights"], prep["imgs_f"], prep["imgs_d"]
-        fmaps: List[torch.Tensor] = []
-        h = x4
-        dense: List[int] = []
-        for i, (k, s, pad, g) in enumerate(specs):
-            bias, w = params[3 * i], weights[i]
-            last = i == n - 1
-            act = ops.ACT_NONE if last else ops.ACT_LRELU
-            if i in prep["wt"]:
-                h = ops.dense_conv(ops.stage_nlc_bf16(h, pad), prep["wt"][i], h.shape[0], h.shape[2], w.shape[1],
-                                   w.shape[0], k, bias=bias, act=act, slope=LRELU_SLOPE)
-                dense.append(i)
-            else:
-                h = ops.conv1d_fwd(h, w, bias, g, s, pad, act=act, slope=LRELU_SLOPE, wimg=imgs_f[i])
-            fmaps.append(h)
+        weights, imgs_d = prep["weights"], prep["imgs_d"]
+        done, lo = prep.get("partial") or (None, 0)
+        fmaps = stack_forward(x4, specs, params, prep, done, lo, x4.shape[0])
+        dense: List[int] = [i for i in range(n) if i in prep["wt"]]
         # feature maps that receive no gradient (all but the logits in the D step) must arrive as None in backward, not
         # as materialised zero tensors: autograd's default filled a map-sized zero buffer per unused output (64 fill
         # kernels per step in the round-2 launch list) which the data-gradient kernels then read as "FM gradient"
@@ -131,6 +152,18 @@ class ConvStackFn(torch.autograd.Function):
             aux.wait_stream(cur)
             return torch.cuda.stream(aux)
 
+        # G step: nobody downstream reads the parameter gradients (config.defer_dead_param_grads): collect the work and
+        # hand it to config.defer() - it runs later, beside the generator's backward
+        late = bool(want_params and need_x and config.defer_dead_param_grads and x4.is_cuda)
+        jobs = []
+
+        def param_work(t, fn):
+            if late:
+                jobs.append(fn)
+            else:
+                with on_aux(t):
+                    fn()
+
         for i in range(n - 1, -1, -1):
             k, s, pad, g = specs[i]
             inp = x4 if i == 0 else fmaps[i - 1]
@@ -139,11 +172,12 @@ class ConvStackFn(torch.autograd.Function):
                 B_, Ci_, L_ = inp.shape[0], inp.shape[1], inp.shape[2]
                 Co_ = weights[i].shape[0]
                 if want_params:
-                    with on_aux(dpre):
+                    def dense_w(dpre=dpre, inp=inp, i=i, k=k, pad=pad, L_=L_, Co_=Co_, Ci_=Ci_):
                         Lp = L_ + k - 1
                         dyq = ops.stage_ncl_bf16(dpre, Lp, 0, rowsum=dbs[i])
                         xq = ops.stage_ncl_bf16(inp, Lp, pad, copies=k)
                         ops.dense_wgrad(dyq, xq, Co_, Ci_, k, weights[i].shape, out=dws[i])
+                    param_work(dpre, dense_w)
                 wd = ctx.dense_wd.get(i)
                 if wd is None:
                     _, wd = ops.stage_dense_weights(weights[i], want_wt=False, want_wd=True)
@@ -151,8 +185,9 @@ class ConvStackFn(torch.autograd.Function):
                                       xact=inp, act=ops.ACT_LRELU, slope=LRELU_SLOPE)
             elif dpre is not None:
                 if want_params:
-                    with on_aux(dpre):
+                    def conv_w(dpre=dpre, inp=inp, i=i, g=g, s=s, pad=pad):
                         ops.conv1d_wgrad(inp, dpre, weights[i].shape, g, s, pad, want_bias=True, dw=dws[i], db=dbs[i])
+                    param_work(dpre, conv_w)
                 if i > 0:
                     dpre = ops.conv1d_dgrad(dpre, weights[i], inp.shape, g, s, pad, gextra=gouts[i - 1], xact=inp,
                                             act=ops.ACT_LRELU, slope=LRELU_SLOPE, wimg=ctx.imgs_d[i])
@@ -163,18 +198,20 @@ class ConvStackFn(torch.autograd.Function):
         if want_params:
             gs = [params[3 * i + 1].contiguous() for i in range(n)]
             vs = [params[3 * i + 2].contiguous() for i in range(n)]
-            if aux is not None and need_x and config.defer_dead_param_grads:
-                # G step: nobody downstream reads these gradients (config.defer_dead_param_grads): finish them on the
-                # helper stream - weight-norm backward and the accumulation into .grad included - and let the caller
-                # join later; autograd gets None for the parameters.
-                with torch.cuda.stream(aux):
+            if late:
+                param_objs = ctx.param_objs
+
+                def finish():
+                    # weight gradients, weight-norm backward and the accumulation into .grad; autograd got None
+                    for fn in jobs:
+                        fn()
                     dgs, dvs = ops.mt_weight_norm_bwd(gs, vs, dws, out=(dgs_o, dvs_o))
                     olds, news = [], []
                     for i in range(n):
                         for j, t in ((3 * i, dbs[i]), (3 * i + 1, dgs[i]), (3 * i + 2, dvs[i])):
                             if not need_p[j]:
                                 continue
-                            pobj = ctx.param_objs[j]
+                            pobj = param_objs[j]
                             if pobj.grad is None:
                                 pobj.grad = t
                             else:
@@ -182,8 +219,8 @@ class ConvStackFn(torch.autograd.Function):
                                 news.append(t)
                     if olds:
                         torch._foreach_add_(olds, news)
-                keep.extend([x4, *fmaps, *weights, *gs, *vs, *dws, *dbs, *dgs, *dvs, *[g for g in gouts if g is not None]])
-                config._PENDING.append((aux, keep))
+
+                config.defer(finish)
                 return (gx, None, None, None, *gparams)
             if aux is not None:
                 cur.wait_stream(aux)

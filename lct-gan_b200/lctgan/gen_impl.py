@@ -408,6 +408,11 @@ class GeneratorFn(torch.autograd.Function):
         mag_phys, mask, *params = ctx.saved_tensors
         P = dict(zip(ctx.names, params))
         arena = []
+        if mag_phys.is_cuda:
+            # the G step's dead discriminator parameter gradients (lctgan.config.defer) start here: the chain of small
+            # kernels below leaves most of the GPU idle
+            from . import config
+            config.launch_deferred_param_grads()
         GR = _on_generator_stream(mag_phys.device, lambda: generator_backward(
             P, mag_phys.contiguous(), mask, gmask, ctx.use_sigmoid, ctx.S, ctx.needs_input_grad[0], arena))
         ctx.S = None

@@ -341,9 +341,10 @@ def conv_tc_images(ws, specs, P, want_f=True, want_d=True):
     return imgs_f, imgs_d
 
 
-def conv_tc_fwd(x, img, bias, Cout, groups, K, stride, pad, act=ACT_NONE, slope=0.2):
+def conv_tc_fwd(x, img, bias, Cout, groups, K, stride, pad, act=ACT_NONE, slope=0.2, out=None):
     B, Cin, Lin, P = x.shape
-    y = torch.empty(B, Cout, conv_out_len(Lin, K, stride, pad), P, dtype=torch.float32, device=x.device)
+    y = out if out is not None else torch.empty(B, Cout, conv_out_len(Lin, K, stride, pad), P, dtype=torch.float32,
+                                                device=x.device)
     call("lct_conv_tc_fwd", x, img, bias, y, B, Cin, Cout, groups, K, stride, pad, Lin, P, act, slope)
     return y
 
@@ -436,20 +437,23 @@ def conv_out_len(lin, k, s, pad):
     return (lin + 2 * pad - k) // s + 1
 
 
-def conv1d_fwd(x, w, bias, groups, stride, pad, act=ACT_NONE, slope=0.2, wimg=None):
-    """x [B,Cin,Lin,P], w [Cout,Cin/G,K] (any trailing singleton dims) -> [B,Cout,Lout,P]."""
+def conv1d_fwd(x, w, bias, groups, stride, pad, act=ACT_NONE, slope=0.2, wimg=None, out=None):
+    """x [B,Cin,Lin,P], w [Cout,Cin/G,K] (any trailing singleton dims) -> [B,Cout,Lout,P] (written into `out` if given:
+    a contiguous batch slice of a larger buffer)."""
     B, Cin, Lin, P = x.shape
     Cout, K = w.shape[0], w.shape[2]
     Lout = conv_out_len(Lin, K, stride, pad)
+    if out is not None and (tuple(out.shape) != (B, Cout, Lout, P) or not out.is_contiguous()):
+        raise ValueError(f"conv1d_fwd: out has shape {tuple(out.shape)}, expected contiguous {(B, Cout, Lout, P)}")
     if _is_post(Cout, K, groups, stride, pad) and act == ACT_NONE:
-        y = torch.empty(B, 1, Lin, P, dtype=torch.float32, device=x.device)
+        y = out if out is not None else torch.empty(B, 1, Lin, P, dtype=torch.float32, device=x.device)
         call("lct_conv_post_fwd", x, w, bias, y, B, Cin, Lin, P, K)
         return y
     if _use_tc(Cin, Cout, K, groups, stride, pad, P):
         if wimg is None:
             wimg = conv_tc_images([w.reshape(Cout, Cin // groups, K)], [(K, stride, pad, groups)], P, want_d=False)[0][0]
-        return conv_tc_fwd(x, wimg, bias, Cout, groups, K, stride, pad, act, slope)
-    y = torch.empty(B, Cout, Lout, P, dtype=torch.float32, device=x.device)
+        return conv_tc_fwd(x, wimg, bias, Cout, groups, K, stride, pad, act, slope, out=out)
+    y = out if out is not None else torch.empty(B, Cout, Lout, P, dtype=torch.float32, device=x.device)
     if _use_mma(Cin, Cout, K, groups, stride, pad, P):
         call("lct_conv_mma_fwd", x, w, wimg, bias, y, B, Cin, Cout, groups, K, stride, pad, Lin, P, act, slope)
         return y
@@ -694,8 +698,11 @@ def stage_dense_weights(w, want_wt=True, want_wd=True):
     return wt, wd
 
 
-def dense_conv(a_staged, w_staged, B, L, Ca, Cn, K, bias=None, gextra=None, xact=None, act=ACT_NONE, slope=0.2):
-    out = torch.empty(B, Cn, L, 1, dtype=torch.float32, device=a_staged.device)
+def dense_conv(a_staged, w_staged, B, L, Ca, Cn, K, bias=None, gextra=None, xact=None, act=ACT_NONE, slope=0.2, out=None):
+    if out is None:
+        out = torch.empty(B, Cn, L, 1, dtype=torch.float32, device=a_staged.device)
+    elif tuple(out.shape) != (B, Cn, L, 1) or not out.is_contiguous():
+        raise ValueError(f"dense_conv: out has shape {tuple(out.shape)}, expected contiguous {(B, Cn, L, 1)}")
     call("lct_dense_conv", a_staged, w_staged, bias, gextra, xact, out, B, L, Ca, Cn, K, act, slope)
     return out
 

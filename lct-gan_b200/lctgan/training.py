@@ -12,7 +12,7 @@ from typing import Dict, Optional
 import torch
 
 import losses as L
-from models.discriminators import run_discriminators
+from models.discriminators import begin_split_forward, finish_split_forward, run_discriminators
 from . import config, ops
 from . import functional as LF
 from .optim import clip_grad_norm_
@@ -61,12 +61,14 @@ def _phase_d(M, noisy, clean, args: StepArgs, st: dict) -> None:
     d_opt.zero_grad(set_to_none=True)
     if args.reuse_enhancer_forward and args.batch_d_step and noisy.is_cuda:
         g_opt.zero_grad(set_to_none=True)
+        # [clean; enhanced] goes through every sub-discriminator as ONE batch of 2B (one autograd node, one backward),
+        # but in two parts: the clean half - and the weight preparation - need nothing from the generator, so they run
+        # on the side streams while the generator's forward (a chain of small kernels) has the GPU to itself
+        nb = clean.shape[0]
+        early = begin_split_forward(mpd, msd, clean.contiguous())
         st["enhanced"], st["mask_c"] = enhancer(noisy)
         st["irm_c"] = tf_features(noisy, clean)["irm_c"]
-        nb = clean.shape[0]
-        both = torch.empty(2 * nb, clean.shape[1], dtype=clean.dtype, device=clean.device)
-        ops.mt_copy([clean.contiguous(), st["enhanced"].detach()], [both[:nb], both[nb:]])
-        (pl, _, sl, _), = run_discriminators(mpd, msd, [both])
+        pl, _, sl, _ = finish_split_forward(mpd, msd, st["enhanced"], early)
         mpd_real, mpd_fake = [t[:nb] for t in pl], [t[nb:] for t in pl]
         msd_real, msd_fake = [t[:nb] for t in sl], [t[nb:] for t in sl]
     elif args.reuse_enhancer_forward and noisy.is_cuda:

@@ -18,7 +18,8 @@ from torch.nn.utils import spectral_norm, weight_norm
 
 from lctgan import config as _cfg
 from lctgan import functional as LF
-from lctgan.disc_impl import conv_stack, prepare_stack
+from lctgan import ops
+from lctgan.disc_impl import conv_stack, prepare_stack, stack_forward
 
 
 def _run_concurrently(discs, inputs, no_grad=None, first_stream=0):
@@ -105,6 +106,59 @@ def run_discriminators(mpd, msd, waves, no_grad=None, first_stream=0):
         out.append(([t[0] for t in r[:np_]], [t[1] for t in r[:np_]], [t[0] for t in r[np_:]], [t[1] for t in r[np_:]]))
     return out
 
+def begin_split_forward(mpd, msd, first_half, first_stream=0):
+    """Scheduling helper (not part of the reference API) for a pass over a batch whose second half does not exist yet:
+    the D step evaluates every sub-discriminator on [clean; enhanced] (train.py:188-193) and only `clean` is known while
+    the generator runs.  On its own side stream (forked from the caller's stream HERE) every sub-discriminator prepares
+    its weights and pushes `first_half` through its kernels into feature-map buffers sized for the whole batch.
+    Returns the state finish_split_forward() continues from; nothing is joined yet."""
+    discs = list(mpd.discriminators) + list(msd.discriminators)
+    inputs = [first_half] * len(mpd.discriminators) + _msd_inputs(msd, first_half)
+    cur = torch.cuda.current_stream(first_half.device)
+    streams = _cfg.side_streams(first_stream + len(discs), first_half.device)[first_stream:]
+    state = []
+    for d, x, s in zip(discs, inputs, streams):
+        s.wait_stream(cur)
+        with torch.cuda.stream(s), torch.no_grad():
+            prep = d.prepare(need_dgrad=False)
+            xa = d._input4(x).contiguous()
+            nb = xa.shape[0]
+            x4 = torch.empty(2 * nb, *xa.shape[1:], dtype=xa.dtype, device=xa.device)
+            ops.mt_copy([xa], [x4[:nb]])
+            fmaps = stack_forward(x4, d._specs, _stack_params(d), prep, None, 0, nb)
+        # (x is kept: the pooled scale inputs were allocated on the caller's stream, which is NOT joined with s before
+        # finish_split_forward - released here, their memory could be handed out again while s still reads it)
+        state.append((prep, x4, fmaps, nb, x))
+    return state
+
+
+def finish_split_forward(mpd, msd, second_half, state, first_stream=0):
+    """Second half of begin_split_forward's batch (no gradient flows into the waveform: the D step's detached enhanced
+    batch).  Returns (period logits, period feature maps, scale logits, scale feature maps) of the WHOLE batch, each
+    sub-discriminator one autograd node over it, exactly like run_discriminators(mpd, msd, [cat(first, second)])."""
+    discs = list(mpd.discriminators) + list(msd.discriminators)
+    second_half = second_half.detach()
+    inputs = [second_half] * len(mpd.discriminators) + _msd_inputs(msd, second_half)
+    cur = torch.cuda.current_stream(second_half.device)
+    streams = _cfg.side_streams(first_stream + len(discs), second_half.device)[first_stream:]
+    res = []
+    for d, x, s, (prep, x4, fmaps, nb, _) in zip(discs, inputs, streams, state):
+        s.wait_stream(cur)
+        with torch.cuda.stream(s):
+            with torch.no_grad():
+                xb = d._input4(x).contiguous()
+                ops.mt_copy([xb], [x4[nb:]])
+            d._prep = dict(prep, partial=(fmaps, nb))
+            try:
+                res.append(d._finish(*d._run(x4)))
+            finally:
+                d._prep = None
+    for s in streams:
+        cur.wait_stream(s)
+    np_ = len(mpd.discriminators)
+    return ([t[0] for t in res[:np_]], [t[1] for t in res[:np_]], [t[0] for t in res[np_:]], [t[1] for t in res[np_:]])
+
+
 # (out_channels, kernel, stride, groups)
 _PERIOD_LAYERS = ((32, 5, 3, 1), (128, 5, 3, 4), (512, 5, 3, 16), (1024, 5, 3, 64), (1024, 5, 1, 64))
 _SCALE_LAYERS = ((16, 15, 1, 1), (64, 41, 4, 4), (256, 41, 4, 16), (1024, 41, 4, 64), (1024, 41, 4, 256),
@@ -128,6 +182,9 @@ class _SubDiscriminator(nn.Module):
 
     def prepare(self, need_dgrad: bool = True) -> dict:
         return prepare_stack(self._specs, _stack_params(self), getattr(self, "period", 1), need_dgrad=need_dgrad)
+
+    def _finish(self, logits, fmaps):
+        return logits, fmaps
 
     def _run(self, x4: torch.Tensor) -> Tuple[torch.Tensor, List[torch.Tensor]]:
         if self._spectral:
@@ -159,7 +216,7 @@ class PeriodDiscriminator(_SubDiscriminator):
         self._specs = tuple(specs)
         self.activation = nn.LeakyReLU(0.2, inplace=True)
 
-    def forward(self, x: torch.Tensor) -> Tuple[torch.Tensor, List[torch.Tensor]]:
+    def _input4(self, x: torch.Tensor) -> torch.Tensor:
         if x.dim() == 2:
             x = x.unsqueeze(1)
         B, C, T = x.shape
@@ -169,7 +226,10 @@ class PeriodDiscriminator(_SubDiscriminator):
             pad = self.period - (T % self.period)
             x2 = LF.ReflectPadRightFn.apply(x2, pad)
             T = T + pad
-        return self._run(x2.reshape(B, 1, T // self.period, self.period))
+        return x2.reshape(B, 1, T // self.period, self.period)
+
+    def forward(self, x: torch.Tensor) -> Tuple[torch.Tensor, List[torch.Tensor]]:
+        return self._run(self._input4(x))
 
 
 class MultiPeriodDiscriminator(nn.Module):
@@ -201,15 +261,20 @@ class ScaleDiscriminator(_SubDiscriminator):
         self._specs = tuple(specs)
         self.activation = nn.LeakyReLU(0.2, inplace=True)
 
-    def forward(self, x: torch.Tensor) -> Tuple[torch.Tensor, List[torch.Tensor]]:
+    def _input4(self, x: torch.Tensor) -> torch.Tensor:
         if x.dim() == 2:
             x = x.unsqueeze(1)
         B, C, T = x.shape
         assert C == 1, "ScaleDiscriminator expects shape [B, 1, T] or [B, T]."
-        logits, fmaps = self._run(x.reshape(B, 1, T, 1))
+        return x.reshape(B, 1, T, 1)
+
+    def _finish(self, logits, fmaps):
         # the kernels carry a trailing period axis of 1; hand back the reference's [B, C, L] shapes
         fmaps = [f.squeeze(-1) for f in fmaps]
         return fmaps[-1], fmaps
+
+    def forward(self, x: torch.Tensor) -> Tuple[torch.Tensor, List[torch.Tensor]]:
+        return self._finish(*self._run(self._input4(x)))
 
 
 class MultiScaleDiscriminator(nn.Module):
