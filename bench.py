@@ -247,9 +247,33 @@ def _time_kernel(run, flush, iters=10):
     return sum(times) / len(times)
 
 
-#: dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel (ncu --set full, B = 8 instance:
-#: profiles/ncu_full_r2_conv_tc_raw.csv); None until that capture exists
-ROOFLINE_TRAFFIC_BYTES = None
+def _time_kernel_stream(run, nsets, iters=5):
+    """Average CUDA-event duration (ms) of one launch inside a stream of launches: `run(i)` works on the i-th of `nsets`
+    DISTINCT operand sets whose total size exceeds the 126 MB L2 several times, so every launch finds its inputs in HBM
+    without a flush between launches; one event pair brackets the nsets launches (GPU parked on a spin kernel while the
+    host enqueues them).  This is how the kernel runs inside the step: launch latency and the ramp-down of the previous
+    grid are hidden by the next launch, which the launch-alone number of _time_kernel pays in full."""
+    import torch
+    for i in range(nsets):
+        run(i)
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(iters):
+        torch.cuda._sleep(2_000_000)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(nsets):
+            run(i)
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1) / nsets)
+    return sum(times) / len(times)
+
+
+#: dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel (ncu --set full of the B = 8 instance
+#: with distinct FM-gradient / activation buffers: profiles/ncu_full_r2_conv_tc_v2_raw.csv, 49.24 MB read + 0.60 MB
+#: written back before the kernel ends)
+ROOFLINE_TRAFFIC_BYTES = 49.84e6
 
 
 def measure_roofline(dev, peaks):
@@ -294,11 +318,24 @@ def measure_roofline(dev, peaks):
                       "mma.sync"),
         }
         family[tag] = {}
+        # the same three passes over NS distinct operand sets (NS x the layer's bytes >> L2), launched back to back
+        NS = 8 if Bq == BATCH else 4
+        xs = [x] + [torch.randn_like(x) for _ in range(NS - 1)]
+        dys = [dy] + [torch.randn_like(dy) for _ in range(NS - 1)]
+        ges = [gextra] + [torch.randn_like(gextra) for _ in range(NS - 1)]
+        streams = {
+            "fwd": lambda i: ops.conv1d_fwd(xs[i], w, bias, G, S, pad, act=ops.ACT_LRELU, wimg=imf[0]),
+            "dgrad": lambda i: ops.conv1d_dgrad(dys[i], w, (Bq, Cin, L, P), G, S, pad, gextra=ges[i], xact=xs[i],
+                                                act=ops.ACT_LRELU, wimg=imd[0]),
+            "wgrad": lambda i: ops.conv1d_wgrad(xs[i], dys[i], w.shape, G, S, pad, dw=dw, db=db),
+        }
         for name, (run, nbytes, kern) in runs.items():
-            ms = _time_kernel(run, flush)
+            ms_alone = _time_kernel(run, flush)
+            ms = _time_kernel_stream(streams[name], NS)
             gbs = nbytes / (ms * 1e-3) / 1e9
             family[tag][name] = {"kernel": kern, "us_per_launch": ms * 1e3, "achieved": gbs, "frac": gbs / peaks["hbm"],
-                                 "algorithmic_bytes": nbytes}
+                                 "algorithmic_bytes": nbytes, "us_launched_alone": ms_alone * 1e3,
+                                 "frac_launched_alone": nbytes / (ms_alone * 1e-3) / 1e9 / peaks["hbm"]}
             if tag == "msd_convs1_B8" and name == "dgrad":
                 roof = {"kernel": "conv_tc_kernel<dgrad> (MSD convs.1 data gradient: 64->16 ch, k=41, s=4, groups=4, B=8, "
                                   "L=32000; tcgen05.mma kind::tf32 implicit GEMM over channel-quad planes in shared memory, "
@@ -306,11 +343,16 @@ def measure_roofline(dev, peaks):
                                   "channel)",
                         "bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
                         "traffic": ROOFLINE_TRAFFIC_BYTES, "traffic_note": "dram__bytes_read+write per launch, ncu --set full "
-                        "(profiles/ncu_full_r2_conv_tc_raw.csv); the 16.4 MB output is still in the 126 MB L2 when the "
+                        "(profiles/ncu_full_r2_conv_tc_v2_raw.csv); the 16.4 MB output is still in the 126 MB L2 when the "
                         "kernel ends",
                         "algorithmic_bytes": nbytes, "ms_per_launch": ms, "peak_source": peaks["src"] + " (STREAM-style copy)",
-                        "bound_note": "above ~0.5 the tcgen05 form is bound by the tensor core's shared-memory operand "
-                                      "fetch (one 4 KB A tile per K = 8 MMA, N = 16), see DESIGN.md section 6"}
+                        "timing": f"CUDA events around {NS} back-to-back launches over {NS} distinct operand sets "
+                                  f"({NS * nbytes / 1e6:.0f} MB >> 126 MB L2, no flush needed), as the kernel runs inside the "
+                                  "step; launched alone after a 256 MB L2 flush: ms_launched_alone",
+                        "ms_launched_alone": ms_alone, "frac_launched_alone": nbytes / (ms_alone * 1e-3) / 1e9 / peaks["hbm"],
+                        "bound_note": "22 K = 8 MMAs of N = 16 per 128-row tile: tools/umma_rate.cu measures 48.6 cycles per "
+                                      "such MMA (32 of them the 4 KB A-operand fetch from shared memory), i.e. a tensor-pipe "
+                                      "floor of 7.4 us for this launch against 10 us of HBM time, see DESIGN.md section 6"}
     # ---- dense conv forward on tcgen05 (MSD convs.5): the D step pushes clean + enhanced through as one batch of 2B
     C, K = 1024, 5
     w = (torch.randn(C, C, K, generator=g) / (C * K) ** 0.5).to(dev)
@@ -499,8 +541,6 @@ def main():
     ap.add_argument("--no-capture-nccl", action="store_true", help="N > 1: keep the NCCL all-reduces out of the CUDA graph "
                     "(three graphs with eager exchanges in between) instead of capturing them inside the single graph")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--late-ctas", type=int, default=None, help=argparse.SUPPRESS)
-    ap.add_argument("--late-streams", type=int, default=None, help=argparse.SUPPRESS)
     ap.add_argument("--timeline", default=None, metavar="TRACE.json", help="record 2 steps with torch.profiler (CUPTI kernel "
                     "activity: start, duration and stream of every kernel of the replayed graph) into a chrome trace and "
                     "exit; tools/timeline_summary.py reads it")
@@ -526,10 +566,6 @@ def main():
 
     from lctgan import _lib, config
     config.grouped_conv_tcgen05 = args.grouped_convs == "tcgen05"
-    if args.late_ctas is not None:
-        config.late_param_grad_ctas = args.late_ctas
-    if args.late_streams is not None:
-        config.late_param_grad_streams = args.late_streams
     from lctgan.parallel import FlatGradAllReduce, broadcast_parameters
     from lctgan.training import (GraphedTrainStep, StepArgs, build_models, restore_state, snapshot_state,
                                  synthetic_batch, train_step)

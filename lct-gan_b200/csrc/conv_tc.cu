@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvParams p) {
         tc::mbar_init(mbar, 1);
         tc::mbar_fence_init();
     }
-    if (warp == 0) tc::tmem_alloc<32>(tmem_slot);
+    if (warp == 0) tc::tmem_alloc<64>(tmem_slot);       // two accumulator buffers of <= 32 columns
     {
         const float4* src = reinterpret_cast<const float4*>(p.wimg + (size_t)grp * (p.b_bytes / 4));
         float4* dst = reinterpret_cast<float4*>(Bw);
@@ -383,28 +383,34 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvParams p) {
     const uint64_t da0 = tc::smem_desc(tc::smem_u32(A), g.by_tap ? (uint32_t)(g.P * 16) : (uint32_t)p.a.PP, 128);
     const uint64_t db0 = tc::smem_desc(tc::smem_u32(Bw), (uint32_t)(g.Npad * 16), 128);
     const uint32_t bstep = (uint32_t)(g.Npad * 2);                      // 32 Npad bytes per MMA, in 16-byte units
-    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
 
-    uint32_t phase = 0;
-    // One tile: registers -> shared memory, MMAs, epilogue.  `R` holds the tile's staged loads; as soon as they are in
-    // shared memory the same registers receive the next tile's loads, which fly during this tile's MMAs and epilogue.
-    // (A second register set = loads two tiles ahead was measured SLOWER, 263 -> 318 us over the 15 forward layers of
-    // tools/bench_disc_layers.py: the extra 30-60 registers cost one or two of the 4-6 resident CTAs per SM, and it is
-    // those CTAs that overlap one tile's MMA wait with another's loads.)
-    auto process = [&](Staged<NQ, NIT>& R, const int tile) {
+    const int64_t chs = (int64_t)p.Lin * g.P;
+    const bool vec = MODE == MODE_DGRAD && g.S == 4 && g.P == 1 && g.ncol <= 16 && (p.Lin & 3) == 0 && p.vec_ok;
+    // The forward and the vector data gradient keep nothing in the operand planes after their MMAs, so they run two
+    // tiles deep: accumulators alternate between two TMEM buffers, and tile i + 1 is staged and its MMAs issued BEFORE
+    // the epilogue of tile i - the tensor core works through the epilogue's loads and stores.  The staged data-gradient
+    // epilogue re-uses the planes as its output tile and keeps the simple order.
+    const bool deep = MODE == MODE_FWD || vec;
+
+    // registers -> shared memory, MMAs into TMEM buffer `buf`, then the next tile's loads into the same registers (they
+    // fly during this tile's MMAs and epilogue).  (A second register set = loads two tiles ahead was measured SLOWER:
+    // the extra 30-60 registers cost one or two of the 4-6 resident CTAs per SM.)
+    auto stage = [&](Staged<NQ, NIT>& R, const int tile, const uint32_t buf) {
         const int b = fdiv(tile, p.fT);
         const int m0 = (tile - b * p.tiles_per_b) * p.mtile;
         stage_store<NQ, NIT>(R, plan, p.a, A, m0);
         tc::fence_proxy_async_smem();            // st.shared (generic proxy) -> tcgen05.mma operand reads (async proxy)
+        tc::fence_before_sync();                 // (deep: this thread's tcgen05.ld of the buffer being re-used are done)
         __syncthreads();
         // one elected lane of warp 0 (a warp-uniform branch, so the descriptors stay in uniform registers and the MMAs
         // go out back to back: see tc::elect_one) issues the tile's MMAs; the tensor core works from here on
         if (warp_u == 0) {
             if (tc::elect_one()) {
                 tc::fence_after_sync();
+                const uint32_t td = tmem_base + buf * 32u;
 #pragma unroll 4
                 for (int j = 0; j < g.nmma; ++j)
-                    tc::umma_tf32(tmem_base, da0 + (uint64_t)p.aoff[j], db0 + (uint64_t)((uint32_t)j * bstep), idesc,
+                    tc::umma_tf32(td, da0 + (uint64_t)p.aoff[j], db0 + (uint64_t)((uint32_t)j * bstep), idesc,
                                   (uint32_t)(j != 0));
                 tc::umma_commit(mbar);
             }
@@ -415,23 +421,24 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvParams p) {
             const int nb = fdiv(next, p.fT);
             stage_load<NQ, NIT>(R, plan, p.a, nb, cbase_a, (next - nb * p.tiles_per_b) * p.mtile);
         }
-        // data gradient, vector epilogue: tile row ml = q - q0 (P == 1); its fused operands are requested now and
-        // travel during the MMAs
-        const int64_t chs = (int64_t)p.Lin * g.P;
-        const bool vec = MODE == MODE_DGRAD && g.S == 4 && g.P == 1 && g.ncol <= 16 && (p.Lin & 3) == 0 && p.vec_ok;
-        int64_t vbase = 0;
-        bool vrow = false;
-        if (vec) {
-            const int ml = warp * 32 + lane;
-            vrow = m0 + ml < p.Mtot;
-            vbase = ((int64_t)b * p.Cin + (int64_t)grp * g.cig) * chs + 4 * (int64_t)(m0 + ml);
-            if (vrow)
-                dgrad_fused_request(fused, g.cig, chs, p.gextra ? p.gextra + vbase : nullptr, p.xact ? p.xact + vbase : nullptr);
+    };
+    // data gradient, vector epilogue: tile row ml = q - q0 (P == 1); the fused operands of the row travel as cp.async
+    // copies while the tile's MMAs run
+    auto request_fused = [&](const int tile) {
+        const int b = fdiv(tile, p.fT);
+        const int m0 = (tile - b * p.tiles_per_b) * p.mtile;
+        const int ml = warp * 32 + lane;
+        if (m0 + ml < p.Mtot) {
+            const int64_t vbase = ((int64_t)b * p.Cin + (int64_t)grp * g.cig) * chs + 4 * (int64_t)(m0 + ml);
+            dgrad_fused_request(fused, g.cig, chs, p.gextra ? p.gextra + vbase : nullptr, p.xact ? p.xact + vbase : nullptr);
         }
-        tc::mbar_wait(mbar, phase);
-        phase ^= 1;
-        tc::fence_after_sync();
-
+    };
+    auto epilogue = [&](const int tile, const uint32_t buf) {
+        const int b = fdiv(tile, p.fT);
+        const int m0 = (tile - b * p.tiles_per_b) * p.mtile;
+        const uint32_t trow = tmem_base + buf * 32u + ((uint32_t)(warp * 32) << 16);
+        const int64_t vbase = ((int64_t)b * p.Cin + (int64_t)grp * g.cig) * chs + 4 * (int64_t)(m0 + warp * 32 + lane);
+        const bool vrow = m0 + warp * 32 + lane < p.Mtot;
         // ---- epilogue: TMEM lane = tile row
         const int m = m0 + warp * 32 + lane;
         if (MODE == MODE_FWD) {
@@ -523,15 +530,36 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvParams p) {
                 }
             }
         }
-        tc::fence_before_sync();
-        __syncthreads();                          // every warp has drained TMEM; the A planes may be overwritten
-        tc::fence_after_sync();
     };
-    while (t0 < p.ntiles) {
-        process(R0, t0);
-        t0 += gstep;
+
+    uint32_t phase = 0, buf = 0;
+    int tile = t0;
+    if (tile < p.ntiles) {
+        stage(R0, tile, 0);
+        if (vec) request_fused(tile);
     }
-    if (warp == 0) tc::tmem_dealloc<32>(tmem_base);
+    while (tile < p.ntiles) {
+        const int next = tile + gstep;
+        tc::mbar_wait(mbar, phase);
+        phase ^= 1;
+        tc::fence_after_sync();
+        if (deep) {
+            if (next < p.ntiles) stage(R0, next, buf ^ 1u);
+            epilogue(tile, buf);
+            if (vec && next < p.ntiles) request_fused(next);      // (after the epilogue has read this tile's slots)
+            buf ^= 1u;
+        } else {
+            epilogue(tile, 0);
+            tc::fence_before_sync();
+            __syncthreads();                      // every warp has drained TMEM and the staged output tile
+            tc::fence_after_sync();
+            if (next < p.ntiles) stage(R0, next, 0);
+        }
+        tile = next;
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<64>(tmem_base);
 }
 
 int g_tc_ctas_per_sm = 6;
@@ -549,7 +577,7 @@ int launch_conv(ConvParams& p, int G, cudaStream_t st) {
         attr_set = true;
     }
     static int regs = 0;
-    int occ = lct_resident_ctas(kern, regs, kThreads, smem, 32);
+    int occ = lct_resident_ctas(kern, regs, kThreads, smem, 64);
     if (occ > g_tc_ctas_per_sm) occ = g_tc_ctas_per_sm;
     int gy = 148 * occ / G;                 // persistent: at most one wave of resident CTAs
     if (gy > p.ntiles) gy = p.ntiles;

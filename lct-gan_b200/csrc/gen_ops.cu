@@ -261,6 +261,9 @@ __global__ void __launch_bounds__(kGruThreads) gru_fwd_kernel(const float* __res
     const int64_t row0 = valid ? seq_row0(geo, seq) : 0;
     const int64_t gstride = (int64_t)GD * 3 * kH;
     float h = 0.f;
+    __shared__ __align__(16) float hbuf[2][kGruThreads];
+    hbuf[0][threadIdx.x] = 0.f;
+    __syncwarp();
     const int step0 = rev ? geo.L - 1 : 0;
     const int dstep = rev ? -1 : 1;
     // The input projections of the next kGruPre steps travel while the current step is computed: a step is ~250 cycles
@@ -294,16 +297,20 @@ __global__ void __launch_bounds__(kGruThreads) gru_fwd_kernel(const float* __res
                 pr[u] = g1[0]; pz[u] = g1[kH]; pn[u] = g1[2 * kH];
             }
             float hr = br, hz = bz, hn = bn, hr2 = 0.f, hz2 = 0.f, hn2 = 0.f;      // two partial sums per gate: half the chain
+            // the unit's 16 state values come back as four broadcast 16-byte shared-memory loads (written at the end of
+            // the previous step).  32 shuffles per step and lane - one warp-shuffle per clock and SM, 16 warps resident -
+            // were ~500 of the step's ~900 cycles
+            const float4* h4 = reinterpret_cast<const float4*>(hbuf[s & 1] + (threadIdx.x & ~(kH - 1)));
+            const float4 q0 = h4[0], q1 = h4[1], q2 = h4[2], q3 = h4[3];
+            const float hv[kH] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
 #pragma unroll
             for (int i = 0; i < kH; i += 2) {
-                const float hi = __shfl_sync(0xffffffffu, h, i, kH);
-                const float hj = __shfl_sync(0xffffffffu, h, i + 1, kH);
-                hr = fmaf(wr[i], hi, hr);
-                hz = fmaf(wz[i], hi, hz);
-                hn = fmaf(wn[i], hi, hn);
-                hr2 = fmaf(wr[i + 1], hj, hr2);
-                hz2 = fmaf(wz[i + 1], hj, hz2);
-                hn2 = fmaf(wn[i + 1], hj, hn2);
+                hr = fmaf(wr[i], hv[i], hr);
+                hz = fmaf(wz[i], hv[i], hz);
+                hn = fmaf(wn[i], hv[i], hn);
+                hr2 = fmaf(wr[i + 1], hv[i + 1], hr2);
+                hz2 = fmaf(wz[i + 1], hv[i + 1], hz2);
+                hn2 = fmaf(wn[i + 1], hv[i + 1], hn2);
             }
             hr += hr2; hz += hz2; hn += hn2;
             const float r = gate_sigmoid(gr + hr);
@@ -315,6 +322,8 @@ __global__ void __launch_bounds__(kGruThreads) gru_fwd_kernel(const float* __res
                 prow[(int64_t)s * hstep] = h;
             }
             h = (1.f - z) * n + z * h;
+            hbuf[(s + 1) & 1][threadIdx.x] = h;        // (the other buffer: this step's readers may still be loading)
+            __syncwarp();
             if (valid) hrow[(int64_t)s * hstep] = h;
         }
     }

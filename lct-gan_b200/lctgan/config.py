@@ -10,6 +10,8 @@ dense_tensor_cores = True
 #: operands read from shared memory through descriptors, accumulators in TMEM).  False = the round-1 TF32 mma.sync
 #: kernels (conv_mma.cu), kept for A/B measurements.
 grouped_conv_tcgen05 = True
+#: ... including the data gradient of the period discriminators' grouped layers (P > 1: staged epilogue)
+tc_dgrad_periods = False
 
 
 def set_precision(mode: str) -> None:

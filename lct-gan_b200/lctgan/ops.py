@@ -23,8 +23,8 @@ _ENV: Dict[tuple, list] = {}
 
 
 def zeros(shape, device) -> torch.Tensor:
-    """Zero-filled fp32 tensor: torch.empty + one cudaMemsetAsync on the current stream (a memset node in a captured
-    graph) instead of torch.zeros' fill kernel."""
+    """Zero-filled fp32 tensor: torch.empty + lct_memset_zero (one 16-byte-store kernel of this library on the current
+    stream, which keeps the stream's priority inside a captured graph) instead of torch.zeros' fill kernel."""
     t = torch.empty(shape, dtype=torch.float32, device=device)
     if t.numel():
         call("lct_memset_zero", t, t.numel() * 4)
@@ -32,7 +32,7 @@ def zeros(shape, device) -> torch.Tensor:
 
 
 class Arena:
-    """Bump allocator over ONE zero-filled buffer (one memset) for the many small gradient accumulators of a backward
+    """Bump allocator over ONE zero-filled buffer (one clearing launch) for the many small gradient accumulators of a backward
     pass; falls back to separate zeroed tensors when exhausted.  Views are 16-byte aligned."""
 
     def __init__(self, numel: int, device):
@@ -292,7 +292,7 @@ def _use_tc(cin, cout, k, groups, stride, pad, P):
 
 
 def _use_tc_dgrad(cin, cout, k, groups, stride, pad, P):
-    return _tc_ok(cin, cout, k, groups, stride, pad, P) and (P == 1 or cin // groups == 1)
+    return _tc_ok(cin, cout, k, groups, stride, pad, P) and (P == 1 or cin // groups == 1 or config.tc_dgrad_periods)
 
 
 def _use_mma(cin, cout, k, groups, stride, pad, P):

@@ -109,3 +109,20 @@ def test_validate_mirror_and_prefetcher(dev):
     for want, have in zip(batches, PinnedPrefetcher(batches, dev)):
         assert have["noisy"].is_cuda and torch.equal(have["noisy"].cpu(), want["noisy"])
         assert torch.equal(have["clean"].cpu(), want["clean"]) and torch.equal(have["lengths"], want["lengths"])
+
+
+def test_memset_zero_any_alignment_and_length(dev):
+    """lct_memset_zero (the library's own clearing kernel): every byte of [p, p + bytes), nothing outside, for unaligned
+    starts and lengths around its 16-byte store width."""
+    from lctgan import _lib
+    buf = torch.empty(4096 + 64, dtype=torch.uint8, device=dev)
+    for off in (0, 1, 3, 4, 15, 16, 17):
+        for n in (1, 2, 15, 16, 17, 31, 33, 255, 1024, 4000):
+            buf.fill_(0xAB)
+            _lib.call("lct_memset_zero", buf.data_ptr() + off, n)
+            h = buf.cpu()
+            assert int(h[off:off + n].max()) == 0, (off, n)
+            assert bool((h[:off] == 0xAB).all()) and bool((h[off + n:] == 0xAB).all()), (off, n)
+    big = torch.full((3 * 1024 * 1024 + 5,), 7.0, device=dev)
+    _lib.call("lct_memset_zero", big[1:], (big.numel() - 1) * 4)
+    assert float(big[0]) == 7.0 and float(big[1:].abs().max()) == 0.0

@@ -12,6 +12,7 @@ from lctgan import config, ops
 dev = torch.device("cuda:0")
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 config.grouped_conv_tcgen05 = not (len(sys.argv) > 2 and sys.argv[2] == "mma")
+config.tc_dgrad_periods = len(sys.argv) > 2 and sys.argv[2] == "tcall"
 print("kernels:", "tcgen05 (conv_tc.cu)" if config.grouped_conv_tcgen05 else "mma.sync (conv_mma.cu)", flush=True)
 
 
