@@ -512,6 +512,19 @@ def measure_variant(dev, mode, steps=10, warmup=3):
         config.set_precision("bf16")
 
 
+def _leave(world, code):
+    """End of a data-parallel rank.  The step's CUDA graph holds captured NCCL kernels; tearing the communicator down
+    under it (dist.destroy_process_group, or the interpreter's own shutdown order) was measured to block for minutes
+    after the result line had been printed.  Everything is flushed and the device idle, so the rank leaves at once."""
+    if world <= 1:
+        return
+    import torch
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(code)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -681,8 +694,7 @@ def main():
     losses = {k: float(v) for k, v in zip(("d_loss", "g_loss", "mr", "mask", "adv", "fm"), res_h.tolist())}
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _leave(world, 0)
         return
     peaks = _peaks()
     roof, roof_t = (None, None) if args.no_roofline else measure_roofline(dev, peaks)
@@ -735,10 +747,12 @@ def main():
         "losses_last_step": losses,
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
-    if parity and parity.get("checked") and not parity["ok"]:
-        raise SystemExit(f"parity check failed: {parity['mismatch']}")
+    bad = bool(parity and parity.get("checked") and not parity["ok"])
+    if bad:
+        print(f"parity check failed: {parity['mismatch']}", file=sys.stderr, flush=True)
+    _leave(world, 1 if bad else 0)
+    if bad:
+        raise SystemExit(1)
 
 
 if __name__ == "__main__":
