@@ -482,7 +482,10 @@ def measure_variant(dev, mode, steps=10, warmup=3):
     """Throughput of the same step through other paths of this repo (context for the headline):
     "api_eager"  - the drop-in modules driven the way the unmodified train.py drives them: literal schedule (two enhancer
                    forwards, four discriminator passes in the D step), torch.optim.AdamW, clip_grad_norm_, no CUDA graph;
-    "fp32"       - the benchmarked schedule (graph, fused AdamW) with every tensor-core path off (fp32 SIMT kernels)."""
+    "fp32"       - the benchmarked schedule (graph, fused AdamW) with every tensor-core path off (fp32 SIMT kernels);
+    "skip_dead"  - the benchmarked schedule without the discriminator parameter gradients of the G step, which train.py
+                   computes and never reads (StepArgs.skip_dead_d_grads: same weights and losses at every step).  NOT
+                   the headline - the headline computes them like the reference does - but it says what they cost."""
     import torch
     from lctgan import config
     from lctgan.training import GraphedTrainStep, StepArgs, build_models, synthetic_batch, train_step
@@ -492,10 +495,12 @@ def measure_variant(dev, mode, steps=10, warmup=3):
             M = build_models(dev, gan_seed=42)
             run = lambda: train_step(*M, noisy, clean, StepArgs(gan_loss="ls"))
         else:
-            config.set_precision("fp32")
+            if mode == "fp32":
+                config.set_precision("fp32")
             M = build_models(dev, gan_seed=42, fused_optim=True)
             g = GraphedTrainStep(*M, noisy, clean, StepArgs(gan_loss="ls", reuse_enhancer_forward=True, batch_d_step=True,
-                                                            defer_dead_d_grads=True), warmup=3)
+                                                            skip_dead_d_grads=mode == "skip_dead",
+                                                            defer_dead_d_grads=mode != "skip_dead"), warmup=3)
             run = g
         for _ in range(warmup):
             run()
@@ -719,7 +724,7 @@ def main():
                 if "error" not in r else r
             if "value" in r and r["value"]:
                 torch_cuda[key]["ours_over_this"] = value / r["value"]
-        variants = {m: measure_variant(dev, m) for m in ("api_eager", "fp32")}
+        variants = {m: measure_variant(dev, m) for m in ("api_eager", "fp32", "skip_dead")}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16 (tcgen05 dense contraction) / tf32 (grouped discriminator convolutions) / 3xtf32 (generator GEMMs and convolutions) tensor-core operands with fp32 accumulation; f32 elsewhere",
@@ -744,6 +749,7 @@ def main():
         "torch_cuda_baseline": torch_cuda,
         "api_eager": variants["api_eager"] if variants else None,
         "fp32_mode": variants["fp32"] if variants else None,
+        "without_dead_d_grads": variants["skip_dead"] if variants else None,
         "losses_last_step": losses,
     }
     print(json.dumps(line), flush=True)
