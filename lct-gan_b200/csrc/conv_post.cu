@@ -3,8 +3,8 @@
 //
 // With a single output channel the generic [positions x out-channels] register tile has nothing to
 // tile over and the grid collapses to a handful of CTAs, so this layer gets its own kernels: it is
-// a pure HBM-bound channel reduction (AI ~ 1.5 flop/B).  Forward gives every CTA 16 positions and all
-// input channels (partial sums over 16 channel groups meet in shared memory); wgrad gives every warp one
+// a pure HBM-bound channel reduction (AI ~ 1.5 flop/B).  Forward gives every CTA up to 512 positions and a
+// slice of the input channels (a warp reads whole channel rows, lane = position); wgrad gives every warp one
 // input channel and reduces over positions with shuffles; dgrad is an elementwise outer product
 // with the fused (feature-matching gradient + LeakyReLU') epilogue of the generic dgrad kernel.
 #include "common.cuh"
@@ -13,51 +13,62 @@ namespace {
 
 constexpr int kT = 256;
 constexpr int kMaxK = 8;
-// forward: FP positions per CTA (8 / 4 / 2, chosen so that even the short maps give every SM a CTA), kT / FP channel
-// groups per CTA (channel c goes to group c % FG)
+constexpr int kPT = 512;            // forward: positions per CTA (16 per lane)
 
-// y[b, j] = bias + sum_{ci} sum_k w[ci][k] * x[b, ci, l + k - pad, p].
-// One CTA owns FP consecutive positions of one batch row and ALL input channels: thread (g, pos) walks the channels
-// c = g, g + FG, ... with 8 channels x K taps of independent loads in flight, the FG partial sums meet in shared
-// memory, and y is written exactly once (the first version split the channels over CTAs and finished with 64 atomics
-// per output element: 49 us for a 26 MB read; this form needs neither the atomics nor a zero-filled output).
+// y[b, j] = bias + sum_{ci} sum_k w[ci][k] * x[b, ci, l + k - pad, p],  j = l P + p.
+// The maps are short and deep (125 .. 400 positions x 1024 channels at 2 s), and contiguous along j only.  A CTA owns
+// up to 512 positions of one batch row and a SLICE of the channels; a warp walks its channels row by row, lane = position,
+// so every load instruction reads 128 consecutive bytes of one channel row (tap k is the same row shifted by (k - pad) P
+// floats: j' = j + (k - pad) P keeps p, and l' is inside [0, L) exactly when j' is inside [0, L P)).  The 8 warps' sums
+// meet in shared memory and one atomicAdd per position and CTA adds the slice to y (zero-filled by the launcher).
+// (Round 1 gave a CTA 8 positions and all channels: 32-byte pieces of 1024 different rows per CTA - 21 us for 13 MB.)
 // (KT = compile-time tap count, 3 for conv_post; 0 = run-time K up to kMaxK with predicated taps)
-template <int kFP, int KT>
+__global__ void post_zero_kernel(float* __restrict__ y, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = 0.f;
+}
+
+template <int KT>
 __global__ void __launch_bounds__(kT) post_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                       const float* __restrict__ bias, float* __restrict__ y, int C,
-                                                      int L, int P, int K, int pad) {
-    constexpr int kFG = kT / kFP;
+                                                      int L, int P, int K, int pad, int cs) {
     constexpr int KK = KT > 0 ? KT : kMaxK;
-    extern __shared__ float ws[];            // [C * K] weights, then [kFG][kFP] partial sums
-    float* red = ws + C * K;
-    const int b = blockIdx.y;
-    for (int i = threadIdx.x; i < C * K; i += kT) ws[i] = w[i];
-    __syncthreads();
+    constexpr int NI = kPT / 32;
+    __shared__ float red[kT / 32][kPT];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.z;
     const int jtot = L * P;
-    const int pos = threadIdx.x % kFP, g = threadIdx.x / kFP;
-    const int j = blockIdx.x * kFP + pos;
-    float acc = 0.f;
-    if (j < jtot) {
-        const int l = j / P;
-        bool ok[KK];
+    const int j0 = blockIdx.x * kPT;
+    const int c0 = blockIdx.y * cs, c1 = min(C, c0 + cs);
+    float acc[NI];
 #pragma unroll
-        for (int k = 0; k < KK; ++k) ok[k] = k < K && (l + k - pad) >= 0 && (l + k - pad) < L;
-        const float* xb = x + (size_t)b * C * jtot + j;
-#pragma unroll 16
-        for (int c = g; c < C; c += kFG) {
-            const float* xc = xb + (size_t)c * jtot;
+    for (int i = 0; i < NI; ++i) acc[i] = 0.f;
+    const float* xb = x + (size_t)b * C * jtot;
+    for (int c = c0 + warp; c < c1; c += kT / 32) {
+        const float* xc = xb + (size_t)c * jtot;
+        float wk[KK];
 #pragma unroll
-            for (int k = 0; k < KK; ++k)
-                if (ok[k]) acc = fmaf(ws[c * K + k], __ldg(xc + (k - pad) * P), acc);
+        for (int k = 0; k < KK; ++k) wk[k] = k < K ? __ldg(w + (size_t)c * K + k) : 0.f;
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            const int j = j0 + lane + 32 * i;
+#pragma unroll
+            for (int k = 0; k < KK; ++k) {
+                const int jj = j + (k - pad) * P;
+                if (k < K && j < jtot && (unsigned)jj < (unsigned)jtot) acc[i] = fmaf(wk[k], __ldg(xc + jj), acc[i]);
+            }
         }
     }
-    red[g * kFP + pos] = acc;
-    __syncthreads();
-    if (threadIdx.x < kFP && blockIdx.x * kFP + threadIdx.x < jtot) {
-        float s = bias ? bias[0] : 0.f;
 #pragma unroll
-        for (int i = 0; i < kFG; ++i) s += red[i * kFP + threadIdx.x];
-        y[(size_t)b * jtot + blockIdx.x * kFP + threadIdx.x] = s;
+    for (int i = 0; i < NI; ++i) red[warp][lane + 32 * i] = acc[i];
+    __syncthreads();
+    for (int t = threadIdx.x; t < kPT; t += kT) {
+        if (j0 + t < jtot) {
+            float s = (blockIdx.y == 0 && bias) ? bias[0] : 0.f;
+#pragma unroll
+            for (int q = 0; q < kT / 32; ++q) s += red[q][t];
+            atomicAdd(&y[(size_t)b * jtot + j0 + t], s);
+        }
     }
 }
 
@@ -146,25 +157,26 @@ bool ok_shape(int64_t B, int64_t C, int64_t L, int64_t P, int64_t K) {
 
 }  // namespace
 
-// y [B,1,L,P] = conv(x [B,C,L,P], w [1,C,K]) + bias, stride 1, pad K/2   (y is overwritten: no zero fill needed)
+// y [B,1,L,P] = conv(x [B,C,L,P], w [1,C,K]) + bias, stride 1, pad K/2   (y is overwritten: cleared here, then the
+// channel slices are added with one atomic per position and slice)
 LCT_API int lct_conv_post_fwd(const float* x, const float* w, const float* bias, float* y, int64_t B, int64_t C,
                               int64_t L, int64_t P, int64_t K, cudaStream_t st) {
     if (!x || !w || !y || !ok_shape(B, C, L, P, K)) return LCT_EINVAL;
-    const size_t smem = ((size_t)C * K + kT) * sizeof(float);
-    if (smem > 40 * 1024) return LCT_EUNSUPPORTED;
     const int64_t jtot = L * P;
-#define LCT_POST_FWD(FP)                                                                                        \
-    do {                                                                                                        \
-        dim3 grid((unsigned)ceil_div64(jtot, FP), (unsigned)B);                                                 \
-        if (K == 3) post_fwd_kernel<FP, 3><<<grid, kT, smem, st>>>(x, w, bias, y, (int)C, (int)L, (int)P, 3, 1); \
-        else post_fwd_kernel<FP, 0><<<grid, kT, smem, st>>>(x, w, bias, y, (int)C, (int)L, (int)P, (int)K, (int)(K / 2)); \
-    } while (0)
-    // 8 positions = one 32-byte sector per (channel, group); fewer positions per CTA on the short maps so that every SM
-    // still gets a few CTAs (the kernel is bound by load latency: per-thread chains must be short and numerous)
-    if (ceil_div64(jtot, 8) * B >= 296) LCT_POST_FWD(8);
-    else if (ceil_div64(jtot, 4) * B >= 296) LCT_POST_FWD(4);
-    else LCT_POST_FWD(2);
-#undef LCT_POST_FWD
+    const int64_t ntile = ceil_div64(jtot, kPT);
+    // enough channel slices for ~2 CTAs per SM, at least one channel per warp
+    int64_t slices = ceil_div64(296, B * ntile);
+    if (slices > C / (kT / 32)) slices = C / (kT / 32);
+    if (slices < 1) slices = 1;
+    int64_t cs = ceil_div64(C, slices);
+    cs = ceil_div64(cs, kT / 32) * (kT / 32);
+    slices = ceil_div64(C, cs);
+    if (slices > 65535 || B > 65535) return LCT_EUNSUPPORTED;
+    post_zero_kernel<<<(unsigned)ceil_div64(B * jtot, 256), 256, 0, st>>>(y, B * jtot);
+    LCT_RETURN_IF_LAUNCH_FAILED();
+    dim3 grid((unsigned)ntile, (unsigned)slices, (unsigned)B);
+    if (K == 3) post_fwd_kernel<3><<<grid, kT, 0, st>>>(x, w, bias, y, (int)C, (int)L, (int)P, 3, 1, (int)cs);
+    else post_fwd_kernel<0><<<grid, kT, 0, st>>>(x, w, bias, y, (int)C, (int)L, (int)P, (int)K, (int)(K / 2), (int)cs);
     LCT_RETURN_IF_LAUNCH_FAILED();
     return 0;
 }

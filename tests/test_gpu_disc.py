@@ -73,6 +73,9 @@ CONV_CASES = [
     (256, 1024, 41, 4, 64, 125, 1), (1024, 1024, 41, 4, 256, 32, 1), (1024, 1024, 5, 1, 1, 8, 1),
     (1024, 1, 3, 1, 1, 8, 1),
     (6, 9, 4, 2, 3, 701, 2), (4, 4, 7, 1, 1, 1300, 1), (8, 8, 3, 3, 2, 5, 1),
+    # conv_post shapes beyond one 512-position tile, with few channels (fewer than one per warp), and a 5-tap kernel
+    (1024, 1, 3, 1, 1, 198, 2), (1024, 1, 3, 1, 1, 300, 2), (64, 1, 3, 1, 1, 1100, 1), (5, 1, 3, 1, 1, 37, 11),
+    (24, 1, 5, 1, 1, 50, 3),
 ]
 
 

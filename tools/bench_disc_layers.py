@@ -47,6 +47,9 @@ LAYERS = [
     ("MPD11.convs1", 32, 128, 5, 3, 4, 970, 11),
     ("MPD11.convs2", 128, 512, 5, 3, 16, 324, 11),
     ("MPD11.convs3", 512, 1024, 5, 3, 64, 108, 11),
+    ("MPD2.conv_post", 1024, 1, 3, 1, 1, 198, 2),
+    ("MPD11.conv_post", 1024, 1, 3, 1, 1, 36, 11),
+    ("MSD0.conv_post", 1024, 1, 3, 1, 1, 125, 1),
 ]
 tot = [0.0, 0.0, 0.0]
 for name, Cin, Cout, K, S, G, Lin, P in LAYERS:
@@ -56,10 +59,11 @@ for name, Cin, Cout, K, S, G, Lin, P in LAYERS:
     b = torch.zeros(Cout, device=dev)
     gw = torch.ones(Cout, 1, 1, device=dev)
     _, imf, imd = ops.mt_weight_norm_fwd([gw], [w], [(K, S, pad, G)], P)          # staged weight images, as in the step
-    y = ops.conv1d_fwd(x, w, b, G, S, pad, act=ops.ACT_LRELU, wimg=imf[0])
+    act = ops.ACT_NONE if Cout == 1 else ops.ACT_LRELU          # conv_post has no activation
+    y = ops.conv1d_fwd(x, w, b, G, S, pad, act=act, wimg=imf[0])
     dy = torch.randn_like(y)
     dw, db = torch.zeros_like(w), torch.zeros(Cout, device=dev)
-    t_f = gtime(lambda: ops.conv1d_fwd(x, w, b, G, S, pad, act=ops.ACT_LRELU, wimg=imf[0]))
+    t_f = gtime(lambda: ops.conv1d_fwd(x, w, b, G, S, pad, act=act, wimg=imf[0]))
     t_d = gtime(lambda: ops.conv1d_dgrad(dy, w, x.shape, G, S, pad, gextra=x, xact=x, act=ops.ACT_LRELU, wimg=imd[0]))
     t_w = gtime(lambda: ops.conv1d_wgrad(x, dy, w.shape, G, S, pad, dw=dw, db=db))
     bx, by = x.numel() * 4, y.numel() * 4
