@@ -180,26 +180,52 @@ __global__ void __launch_bounds__(kThreads) mt_adamw_kernel(const AdamSegs S, co
     const int seg = lo;
     const int64_t start = (int64_t)(blockIdx.x - S.chunk0[seg]) * kChunk;
     const int64_t end = min(start + (int64_t)kChunk, S.n[seg]);
-    const double t = (double)step_ptr[0];                       // already incremented for this step
-    const float bc1 = (float)(1.0 - pow((double)b1, t));
-    const float bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, t));
+    // bias corrections in double like torch.optim.AdamW - by ONE thread per CTA: two double-precision pow() in every
+    // thread cost more than the 16 elements the thread then updates
+    __shared__ float corr[2];
+    if (threadIdx.x == 0) {
+        const double t = (double)step_ptr[0];                   // already incremented for this step
+        corr[0] = (float)(1.0 - pow((double)b1, t));
+        corr[1] = (float)sqrt(1.0 - pow((double)b2, t));
+    }
+    __syncthreads();
+    const float bc1 = corr[0], bc2_sqrt = corr[1];
     const float step_size = lr / bc1;
     const float decay = 1.f - lr * wd;
     float* __restrict__ pp = S.p[seg];
     const float* __restrict__ gg = S.g[seg];
     float* __restrict__ mm = S.m[seg];
     float* __restrict__ vv = S.v[seg];
-    for (int64_t i = start + threadIdx.x; i < end; i += kThreads) {
-        const float g = gg[i] * gmul;
-        float p = pp[i] * decay;
-        float m = mm[i];
+    auto upd = [&](float& p, float gr, float& m, float& v) {
+        const float g = gr * gmul;
+        p *= decay;
         m = m + (g - m) * (1.f - b1);
-        const float v = b2 * vv[i] + (1.f - b2) * g * g;
+        v = b2 * v + (1.f - b2) * g * g;
         const float denom = sqrtf(v) / bc2_sqrt + eps;
         p -= step_size * (m / denom);
-        pp[i] = p;
-        mm[i] = m;
-        vv[i] = v;
+    };
+    const bool vec = (((uintptr_t)pp | (uintptr_t)gg | (uintptr_t)mm | (uintptr_t)vv) & 15) == 0;   // (kChunk % 4 == 0)
+    int64_t i = start + 4 * (int64_t)threadIdx.x;
+    if (vec) {
+        for (; i + 3 < end; i += 4 * kThreads) {
+            float4 p4 = *reinterpret_cast<const float4*>(pp + i);
+            const float4 g4 = *reinterpret_cast<const float4*>(gg + i);
+            float4 m4 = *reinterpret_cast<const float4*>(mm + i);
+            float4 v4 = *reinterpret_cast<const float4*>(vv + i);
+            upd(p4.x, g4.x, m4.x, v4.x); upd(p4.y, g4.y, m4.y, v4.y);
+            upd(p4.z, g4.z, m4.z, v4.z); upd(p4.w, g4.w, m4.w, v4.w);
+            *reinterpret_cast<float4*>(pp + i) = p4;
+            *reinterpret_cast<float4*>(mm + i) = m4;
+            *reinterpret_cast<float4*>(vv + i) = v4;
+        }
+    }
+    // scalar form: unaligned tensors, and the < 4 elements at the end of a tensor (at most one thread gets there)
+    for (; i < end; i += vec ? end : 4 * kThreads) {
+        for (int64_t e = i; e < min(i + 4, end); ++e) {
+            float p = pp[e], m = mm[e], v = vv[e];
+            upd(p, gg[e], m, v);
+            pp[e] = p; mm[e] = m; vv[e] = v;
+        }
     }
 }
 

@@ -96,12 +96,24 @@ def ptr(t):
     return t.data_ptr()
 
 
+# the raw handle of the current stream without building a torch.cuda.Stream object per kernel call (the eager path makes
+# ~1 100 calls per training step)
+_RAW_STREAM = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_GET_DEVICE = getattr(torch._C, "_cuda_getDevice", None)
+
+
+def _current_stream_handle() -> int:
+    if _RAW_STREAM is not None and _GET_DEVICE is not None:
+        return _RAW_STREAM(_GET_DEVICE())
+    return torch.cuda.current_stream().cuda_stream
+
+
 def call(name: str, *args):
     """Invoke ``name`` on the current CUDA stream; tensors are passed as raw device pointers."""
-    fn, wants_stream = lib().fns[name]
+    fn, wants_stream = (_LIB or lib()).fns[name]
     conv = [ptr(a) if isinstance(a, torch.Tensor) else a for a in args]
     if wants_stream:
-        conv.append(torch.cuda.current_stream().cuda_stream)
+        conv.append(_current_stream_handle())
     rc = fn(*conv)
     if rc != 0:
         if rc > 0:

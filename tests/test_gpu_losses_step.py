@@ -129,6 +129,11 @@ def test_fused_adamw_matches_torch(dev):
     shapes = [(1024, 4, 41), (64,), (3, 5, 2, 1), (1,), (100001,)] * 12       # > 48 tensors: several launches
     pa = [torch.randn(s, generator=g).to(dev).requires_grad_(True) for s in shapes]
     pb = [p.detach().clone().requires_grad_(True) for p in pa]
+    # + a parameter that starts 4 bytes off a 16-byte boundary (the kernel's scalar form) on both sides
+    base = torch.randn(5003, generator=g).to(dev)
+    pa.append(base.clone()[1:].detach().requires_grad_(True))
+    pb.append(base.clone()[1:].detach().requires_grad_(True))
+    assert pb[-1].data_ptr() % 16 == 4
     oa = torch.optim.AdamW(pa, lr=2e-4, betas=(0.8, 0.99))
     ob = FusedAdamW(pb, lr=2e-4, betas=(0.8, 0.99))
     for step in range(4):
