@@ -266,14 +266,25 @@ def weight_norm_bwd(g, v, dw):
     return dg, dv
 
 
+_SUPPORTED: Dict[tuple, bool] = {}      # (entry point, layer geometry) -> the library's answer (pure functions of the shape)
+
+
+def _supported(fn: str, *geom) -> bool:
+    key = (fn,) + geom
+    r = _SUPPORTED.get(key)
+    if r is None:
+        r = _SUPPORTED[key] = bool(call_ret(fn, *geom))
+    return r
+
+
 def _tc_ok(cin, cout, k, groups, stride, pad, P):
     return (config.dense_tensor_cores and config.grouped_conv_tcgen05 and pad == k // 2 and
-            bool(call_ret("lct_conv_tc_supported", cin, cout, groups, k, stride, P)))
+            _supported("lct_conv_tc_supported", cin, cout, groups, k, stride, P))
 
 
 def _mma_ok(cin, cout, k, groups, stride, pad, P):
     return (config.dense_tensor_cores and pad == k // 2 and
-            bool(call_ret("lct_conv_mma_supported", cin, cout, groups, k, stride, P)))
+            _supported("lct_conv_mma_supported", cin, cout, groups, k, stride, P))
 
 
 # Which of the two tensor-core implementations of the grouped / first-layer convolutions runs a pass.  Both compute the
