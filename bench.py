@@ -559,6 +559,8 @@ def main():
     ap.add_argument("--no-capture-nccl", action="store_true", help="N > 1: keep the NCCL all-reduces out of the CUDA graph "
                     "(three graphs with eager exchanges in between) instead of capturing them inside the single graph")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--dp-same-data", action="store_true", help="validation aid: every rank gets rank 0's batch, so the "
+                    "averaged gradients - and losses_last_step - must equal the single-GPU run's")
     ap.add_argument("--timeline", default=None, metavar="TRACE.json", help="record 2 steps with torch.profiler (CUPTI kernel "
                     "activity: start, duration and stream of every kernel of the replayed graph) into a chrome trace and "
                     "exit; tools/timeline_summary.py reads it")
@@ -605,7 +607,7 @@ def main():
                      batch_d_step=not args.no_reuse and not args.no_batch_d,
                      skip_dead_d_grads=args.skip_dead_d_grads, defer_dead_d_grads=not args.no_defer_dead_d_grads)
 
-    noisy_h, clean_h = synthetic_batch(BATCH, SEGMENT, seed=1234 + rank)
+    noisy_h, clean_h = synthetic_batch(BATCH, SEGMENT, seed=1234 + (0 if args.dp_same_data else rank))
     noisy_h, clean_h = noisy_h.pin_memory(), clean_h.pin_memory()
     noisy_d, clean_d = noisy_h.to(dev), clean_h.to(dev)
     res_h = torch.empty(6, dtype=torch.float32).pin_memory()
