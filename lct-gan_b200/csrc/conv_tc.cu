@@ -263,6 +263,9 @@ constexpr int kFusedBytes = 2 * 4 * kThreads * 16;
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tc::smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(tc::smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
@@ -325,6 +328,7 @@ struct ConvParams {
     int TS;                  // dgrad: floats per channel of the staged output tile
     int tiles_per_b, ntiles;
     int a_bytes, b_bytes;    // shared-memory sizes of the A planes and of the weight image
+    int fused_bytes;         // dgrad: vector epilogue: the two prefetched operands; staged epilogue: output tile + the two
     float neg;               // slope of the activation for negative inputs: LeakyReLU slope, ReLU 0, none 1
     int vec_ok;              // dgrad: dx / gextra / xact are 16-byte aligned
     FastDiv fT;
@@ -386,11 +390,13 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvParams p) {
 
     const int64_t chs = (int64_t)p.Lin * g.P;
     const bool vec = MODE == MODE_DGRAD && g.S == 4 && g.P == 1 && g.ncol <= 16 && (p.Lin & 3) == 0 && p.vec_ok;
-    // The forward and the vector data gradient keep nothing in the operand planes after their MMAs, so they run two
-    // tiles deep: accumulators alternate between two TMEM buffers, and tile i + 1 is staged and its MMAs issued BEFORE
-    // the epilogue of tile i - the tensor core works through the epilogue's loads and stores.  The staged data-gradient
-    // epilogue re-uses the planes as its output tile and keeps the simple order.
-    const bool deep = MODE == MODE_FWD || vec;
+    // Two tiles deep: accumulators alternate between two TMEM buffers, and tile i + 1 is staged and its MMAs issued
+    // BEFORE the epilogue of tile i - the tensor core works through the epilogue's loads and stores (nothing of tile i
+    // lives in the operand planes after its MMAs: the staged data-gradient epilogue has its own output tile).
+    const bool has_fused = MODE == MODE_DGRAD && (p.gextra != nullptr || p.xact != nullptr);
+    float* Tst = reinterpret_cast<float*>(fused);                 // staged epilogue: [cig][TS] output tile,
+    float* Gst = Tst + g.cig * p.TS;                              //   prefetched FM gradient,
+    float* Xst = Gst + g.cig * p.TS;                              //   prefetched saved activation
 
     // registers -> shared memory, MMAs into TMEM buffer `buf`, then the next tile's loads into the same registers (they
     // fly during this tile's MMAs and epilogue).  (A second register set = loads two tiles ahead was measured SLOWER:
@@ -427,11 +433,44 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvParams p) {
     auto request_fused = [&](const int tile) {
         const int b = fdiv(tile, p.fT);
         const int m0 = (tile - b * p.tiles_per_b) * p.mtile;
-        const int ml = warp * 32 + lane;
-        if (m0 + ml < p.Mtot) {
-            const int64_t vbase = ((int64_t)b * p.Cin + (int64_t)grp * g.cig) * chs + 4 * (int64_t)(m0 + ml);
-            dgrad_fused_request(fused, g.cig, chs, p.gextra ? p.gextra + vbase : nullptr, p.xact ? p.xact + vbase : nullptr);
+        if (vec) {
+            const int ml = warp * 32 + lane;
+            if (m0 + ml < p.Mtot) {
+                const int64_t vbase = ((int64_t)b * p.Cin + (int64_t)grp * g.cig) * chs + 4 * (int64_t)(m0 + ml);
+                dgrad_fused_request(fused, g.cig, chs, p.gextra ? p.gextra + vbase : nullptr,
+                                    p.xact ? p.xact + vbase : nullptr);
+            }
+            return;
         }
+        // staged epilogue: the tile's contiguous output run of every channel, nval = S * rows * P elements starting at
+        // any alignment.  The shared-memory copy is shifted by the run's phase modulo 16 bytes (element t lives at
+        // [ci * TS + phase + t], TS % 4 == 0), so the body moves 16 bytes per cp.async and only head and tail go by 4
+        const int j0 = g.S * fdiv(m0, p.a.fP) * g.P;
+        int nval = g.S * p.mtile;
+        if (nval > (int)chs - j0) nval = (int)chs - j0;
+        const int64_t cb = ((int64_t)b * p.Cin + (int64_t)grp * g.cig) * chs + j0;
+        for (int ci = 0; ci < g.cig; ++ci) {
+            const int64_t e0 = cb + (int64_t)ci * chs;
+            const int phase = p.vec_ok ? (int)(e0 & 3) : 0;
+            const int h0 = p.vec_ok ? min((4 - phase) & 3, nval) : nval;         // 4-byte head (everything if unaligned)
+            const int nvec = (nval - h0) >> 2;
+            float* gd = Gst + ci * p.TS + phase;
+            float* xd = Xst + ci * p.TS + phase;
+            for (int t = (int)threadIdx.x; t < h0; t += kThreads) {
+                if (p.gextra) cp_async4(gd + t, p.gextra + e0 + t);
+                if (p.xact) cp_async4(xd + t, p.xact + e0 + t);
+            }
+            for (int v = (int)threadIdx.x; v < nvec; v += kThreads) {
+                const int t = h0 + 4 * v;
+                if (p.gextra) cp_async16(gd + t, p.gextra + e0 + t);
+                if (p.xact) cp_async16(xd + t, p.xact + e0 + t);
+            }
+            for (int t = h0 + 4 * nvec + (int)threadIdx.x; t < nval; t += kThreads) {
+                if (p.gextra) cp_async4(gd + t, p.gextra + e0 + t);
+                if (p.xact) cp_async4(xd + t, p.xact + e0 + t);
+            }
+        }
+        cp_async_commit();
     };
     auto epilogue = [&](const int tile, const uint32_t buf) {
         const int b = fdiv(tile, p.fT);
@@ -475,14 +514,14 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvParams p) {
                 if (vrow) dgrad_store16_vec(v, g.ncol, chs, p.out + vbase, fused, p.gextra != nullptr, p.xact != nullptr, p.neg);
             } else {
                 // tile row ml = (q - q0, p) (dgrad tiles hold whole rows of P): dX[ci][S q + r][p] for the S phases r.
-                // Stage the tile in shared memory (over the operand planes: their MMAs are complete), then one
-                // coalesced pass per channel over the contiguous run of S * rows * P outputs this tile owns
+                // Stage the tile in shared memory, then one coalesced pass per channel over the contiguous run of
+                // S * rows * P outputs this tile owns; the fused operands of that run were prefetched by cp.async
                 const int ml = warp * 32 + lane;
                 const int qrel = fdiv(ml, p.a.fP), pp = ml - qrel * g.P;
                 const int q0 = fdiv(m0, p.a.fP);
                 const bool rowok = ml < p.mtile && m0 + ml < p.Mtot;
                 const int64_t cb = ((int64_t)b * p.Cin + (int64_t)grp * g.cig) * chs;
-                float* T = reinterpret_cast<float*>(A);
+                float* T = Tst;
                 float* t = T + g.S * ml - (g.S - 1) * pp;
 #define LCT_DS(SV, C0V) dgrad_stage16<SV, C0V>(v, g.ncol, t, p.TS, g.P)
                 {
@@ -508,25 +547,24 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvParams p) {
                     }
                 }
 #undef LCT_DS
+                cp_async_wait_all();                                            // (this thread's own requests)
                 __syncthreads();
                 const int j0 = g.S * q0 * g.P;                                  // first output (flat) of the tile
                 int nval = g.S * p.mtile;                                       // = S * rows * P
                 if (nval > (int)chs - j0) nval = (int)chs - j0;
                 for (int ci = 0; ci < g.cig; ++ci) {                            // <= S <= 4 elements per thread and channel
                     const int64_t ib = cb + (int64_t)ci * chs + j0 + (int)threadIdx.x;
-                    const float* trow_s = T + ci * p.TS + (int)threadIdx.x;
-                    float a[4], gv[4], xv[4];
+                    const int so = ci * p.TS + (int)threadIdx.x;
+                    const int sp = so + (p.vec_ok ? (int)((cb + (int64_t)ci * chs + j0) & 3) : 0);   // (see request_fused)
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {                               // all loads first: 8 in flight per thread
-                        const bool ok = u * kThreads + (int)threadIdx.x < nval;
-                        a[u] = ok ? trow_s[u * kThreads] : 0.f;
-                        gv[u] = (ok && p.gextra) ? ld_nc(p.gextra + ib + u * kThreads) : 0.f;
-                        xv[u] = (ok && p.xact) ? ld_nc(p.xact + ib + u * kThreads) : 1.f;
+                    for (int u = 0; u < 4; ++u) {
+                        if (u * kThreads + (int)threadIdx.x < nval) {
+                            float a = T[so + u * kThreads];
+                            if (p.gextra) a += Gst[sp + u * kThreads];
+                            if (p.xact) a *= Xst[sp + u * kThreads] > 0.f ? 1.f : p.neg;
+                            st_global(p.out + ib + u * kThreads, a);
+                        }
                     }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (u * kThreads + (int)threadIdx.x < nval)
-                            st_global(p.out + ib + u * kThreads, (a[u] + gv[u]) * (xv[u] > 0.f ? 1.f : p.neg));
                 }
             }
         }
@@ -536,25 +574,17 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvParams p) {
     int tile = t0;
     if (tile < p.ntiles) {
         stage(R0, tile, 0);
-        if (vec) request_fused(tile);
+        if (has_fused) request_fused(tile);
     }
     while (tile < p.ntiles) {
         const int next = tile + gstep;
         tc::mbar_wait(mbar, phase);
         phase ^= 1;
         tc::fence_after_sync();
-        if (deep) {
-            if (next < p.ntiles) stage(R0, next, buf ^ 1u);
-            epilogue(tile, buf);
-            if (vec && next < p.ntiles) request_fused(next);      // (after the epilogue has read this tile's slots)
-            buf ^= 1u;
-        } else {
-            epilogue(tile, 0);
-            tc::fence_before_sync();
-            __syncthreads();                      // every warp has drained TMEM and the staged output tile
-            tc::fence_after_sync();
-            if (next < p.ntiles) stage(R0, next, 0);
-        }
+        if (next < p.ntiles) stage(R0, next, buf ^ 1u);
+        epilogue(tile, buf);
+        if (has_fused && next < p.ntiles) request_fused(next);        // (after the epilogue has read this tile's slots)
+        buf ^= 1u;
         tile = next;
     }
     tc::fence_before_sync();
@@ -567,7 +597,8 @@ int g_tc_ctas_per_sm = 6;
 template <int MODE, int NQ, int NIT>
 int launch_conv(ConvParams& p, int G, cudaStream_t st) {
     const bool vec = MODE == MODE_DGRAD && p.g.S == 4 && p.g.P == 1 && p.g.ncol <= 16 && (p.Lin & 3) == 0 && p.vec_ok;
-    const size_t smem = 128 + (size_t)p.a_bytes + p.b_bytes + 32 * 4 + 32 + (vec ? kFusedBytes : 0);
+    p.fused_bytes = MODE != MODE_DGRAD ? 0 : (vec ? kFusedBytes : 3 * p.g.cig * p.TS * 4);
+    const size_t smem = 128 + (size_t)p.a_bytes + p.b_bytes + 32 * 4 + 32 + (size_t)p.fused_bytes;
     if (smem > 200 * 1024) return LCT_EUNSUPPORTED;
     auto kern = conv_tc_kernel<MODE, NQ, NIT>;
     static bool attr_set = false;           // per instantiation
@@ -732,8 +763,7 @@ LCT_API int lct_conv_tc_dgrad(const float* dy, const float* wimg, float* dx, con
     p.Mtot = (int)(((Lin + S - 1) / S) * P);
     p.vec_ok = (((uintptr_t)dx | (uintptr_t)gextra | (uintptr_t)xact) & 15) == 0;
     p.mtile = (kTileM / (int)P) * (int)P;             // whole rows of P: the tile's outputs are one contiguous run
-    p.TS = (int)S * p.mtile + 4;
-    if ((int)(Cin / G) * p.TS * 4 > p.a_bytes) p.a_bytes = ((int)(Cin / G) * p.TS * 4 + 127) & ~127;   // staged output tile
+    p.TS = ((int)S * p.mtile + 4 + 3) & ~3;      // + 3 floats of alignment shift for the prefetched operands, multiple of 4
     p.tiles_per_b = (p.Mtot + p.mtile - 1) / p.mtile;
     p.ntiles = p.B * p.tiles_per_b;
     p.fT = make_fdiv(p.tiles_per_b);

@@ -11,6 +11,17 @@ from util import rel_err
 pytestmark = [pytest.mark.gpu, pytest.mark.bf16]
 
 
+@pytest.fixture(autouse=True, params=["default", "tcgen05_period_dgrad"])
+def _dgrad_kernel_choice(request):
+    """Every case runs with the shipped per-layer kernel choice and with the period discriminators' data gradient forced
+    onto the tcgen05 kernel as well (lctgan.config.tc_dgrad_periods: its staged, cp.async-prefetched epilogue)."""
+    from lctgan import config
+    old = config.tc_dgrad_periods
+    config.tc_dgrad_periods = request.param != "default"
+    yield
+    config.tc_dgrad_periods = old
+
+
 def _tf32(t):
     """round-to-nearest (ties away) to 10 mantissa bits, like cvt.rna.tf32.f32"""
     i = t.contiguous().view(torch.int32)
