@@ -423,10 +423,13 @@ struct MmaWgradParams {
 // NT n-tiles per warp, NSPLIT warp groups side by side over the (ci, tap) columns: 4 * NSPLIT warps per CTA.  (With all
 // 21 n-tiles of the MSD layers in one warp the kernel needed 195 registers -> 8 resident warps per SM, and it is
 // bound by the latency of its shared-memory gathers; two groups of 11 n-tiles halve the accumulators.)
-template <int MT, int NT, int NSPLIT>
+// TP = positions per tile (128 or 256): the longer tile halves the barriers and window halos per position and won
+// 15-25 % on the k = 41 scale layers and the 512 -> 1024 period layer, and lost as much on the short maps and on the
+// two-m-tile period layers (tools/bench_disc_layers.py) - chosen per layer in launch_wgrad
+template <int MT, int NT, int NSPLIT, int TP>
 __global__ void __launch_bounds__(kThreads * NSPLIT) conv_mma_wgrad_kernel(const MmaWgradParams p) {
     extern __shared__ __align__(16) float sm[];
-    constexpr int TP = 128;                       // positions per tile; each position warp takes 32 of them
+    // TP positions per tile; each position warp takes a quarter of them
     constexpr int NW = 4 * NSPLIT;
     constexpr int NTH = kThreads * NSPLIT;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -519,10 +522,10 @@ __global__ void __launch_bounds__(kThreads * NSPLIT) conv_mma_wgrad_kernel(const
         const int jt = tile - fdiv(tile, p.fT) * p.tiles_per_b;
         const int j0 = jt * TP;
         const int row_first = fdiv(j0, p.fP);
-        // this warp's 32 positions: 4 k-steps of 8
+        // this warp's TP / 4 positions in k-steps of 8
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-            const int pl = wp * 32 + ks * 8;                 // tile-local position of this k-step
+        for (int ks = 0; ks < TP / 32; ++ks) {
+            const int pl = wp * (TP / 4) + ks * 8;           // tile-local position of this k-step
             int bs[2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -744,13 +747,12 @@ LCT_API int lct_conv_mma_dgrad(const float* dy, const float* w, const float* wim
 // lct_set_wgrad_ctas(1) while the G step's dead gradients run beside the generator's backward (lctgan/config.py)
 int g_wgrad_ctas_per_sm = 2;
 
-template <int MT, int NT, int NSPLIT>
-int launch_wgrad(MmaWgradParams& p, cudaStream_t st) {
-    const int TP = 128;
+template <int MT, int NT, int NSPLIT, int TP>
+int launch_wgrad_tp(MmaWgradParams& p, cudaStream_t st) {
     const int rows_max = TP / p.P + 2;
     const int nr_max = (rows_max - 1) * p.S + p.K;
     p.WS = (nr_max * p.P + 3 + 3) & ~3;      // + up to 3 floats of alignment shift
-    p.DS = TP + 4;                           // 132: holds the shift, and 132 mod 32 = 4 spreads the A rows over banks
+    p.DS = TP + 4;                           // 132 / 260: holds the shift, and DS mod 32 = 4 spreads the A rows over banks
     p.tiles_per_b = (int)ceil_div64((int64_t)p.Lout * p.P, TP);
     p.ntiles = p.B * p.tiles_per_b;
     p.fP = make_fdiv(p.P, (int64_t)p.Lout * p.P + TP);
@@ -759,23 +761,31 @@ int launch_wgrad(MmaWgradParams& p, cudaStream_t st) {
     const size_t red = (size_t)16 * MT * NT * NSPLIT * 8 * sizeof(float);
     if (smem < red) smem = red;
     if (smem > 200 * 1024) return LCT_EUNSUPPORTED;
+    auto kern = conv_mma_wgrad_kernel<MT, NT, NSPLIT, TP>;
     if (smem > 40 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(conv_mma_wgrad_kernel<MT, NT, NSPLIT>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
     const int G = p.Cin / p.Cig;
     // fewer, longer-lived CTAs than fwd/dgrad (every CTA ends with N x KK atomics), and never more than are resident
     static int regs = 0;                    // per instantiation
-    const int occ = lct_resident_ctas(conv_mma_wgrad_kernel<MT, NT, NSPLIT>, regs, kThreads * NSPLIT, smem, 0);
+    const int occ = lct_resident_ctas(kern, regs, kThreads * NSPLIT, smem, 0);
     const int per_sm = occ < g_wgrad_ctas_per_sm ? occ : g_wgrad_ctas_per_sm;
     int gy = 148 * per_sm / G;                // rounded down: no second wave
     if (gy > p.ntiles) gy = p.ntiles;
     if (gy < 1) gy = 1;
     dim3 grid((unsigned)G, (unsigned)gy);
-    conv_mma_wgrad_kernel<MT, NT, NSPLIT><<<grid, kThreads * NSPLIT, smem, st>>>(p);
+    kern<<<grid, kThreads * NSPLIT, smem, st>>>(p);
     LCT_RETURN_IF_LAUNCH_FAILED();
     return 0;
+}
+
+template <int MT, int NT, int NSPLIT>
+int launch_wgrad(MmaWgradParams& p, cudaStream_t st) {
+    // 256-position tiles where they were measured faster (see the kernel), 128 elsewhere
+    constexpr bool kLongOk = (MT == 1 && NT == 11) || (MT == 1 && NT == 5 && NSPLIT == 1);
+    if (kLongOk && (int64_t)p.Lout * p.P >= 384) return launch_wgrad_tp<MT, NT, NSPLIT, kLongOk ? 256 : 128>(p, st);
+    return launch_wgrad_tp<MT, NT, NSPLIT, 128>(p, st);
 }
 
 // dw [Cout][Cin/G][K] and db [Cout] (optional) are accumulated (caller zeroes)
