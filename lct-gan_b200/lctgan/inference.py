@@ -55,24 +55,64 @@ def _i64(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
-def length_buckets(lengths: Sequence[int], max_batch: int = 16, max_pad_ratio: float = 1.1) -> List[List[int]]:
-    """Indices grouped into batches: sorted by length (longest first), a bucket is closed when it holds `max_batch`
-    utterances or when the next (shorter) utterance would be padded by more than `max_pad_ratio` x its own length."""
+#: What one more enhancer call costs, in samples of audio it could have processed instead: on B200 a call is ~0.9 ms of
+#: launch-latency-bound fixed time plus ~0.07 ms per second of (padded) audio in the batch (bench.py enhance_rtf: 1.6 ms for
+#: 1 x 9.7 s, 11.8 ms for 16 x 9.9 s), i.e. ~13 s of audio at 16 kHz.  Splitting a batch pays only if it saves more padding.
+CALL_OVERHEAD_SAMPLES = 13 * 16000
+
+
+def length_buckets(lengths: Sequence[int], max_batch: int = 16, max_pad_ratio: float = None,
+                   call_overhead: int = CALL_OVERHEAD_SAMPLES) -> List[List[int]]:
+    """Indices grouped into batches, longest first, minimising  sum over batches of (call_overhead + rows x longest row)
+    - the samples the enhancer processes, padding included, plus the fixed cost of every call - by dynamic programming
+    over the length-sorted order (an optimal grouping is contiguous in it).  At most `max_batch` utterances per batch;
+    `max_pad_ratio` (optional) additionally forbids padding an utterance beyond that multiple of its own length."""
     order = sorted(range(len(lengths)), key=lambda i: -int(lengths[i]))
+    L = [int(lengths[i]) for i in order]
+    n = len(L)
+    INF = float("inf")
+    best = [0.0] + [INF] * n          # best[i]: cost of the first i (longest) utterances
+    cut = [0] * (n + 1)
+    for i in range(1, n + 1):
+        for j in range(max(0, i - max_batch), i):             # batch = sorted positions j .. i-1, longest = L[j]
+            if max_pad_ratio is not None and L[j] > max_pad_ratio * max(L[i - 1], 1):
+                continue
+            c = best[j] + call_overhead + (i - j) * L[j]
+            if c < best[i]:
+                best[i], cut[i] = c, j
     buckets: List[List[int]] = []
-    cur: List[int] = []
-    for i in order:
-        if cur and (len(cur) >= max_batch or int(lengths[cur[0]]) > max_pad_ratio * max(int(lengths[i]), 1)):
-            buckets.append(cur)
-            cur = []
-        cur.append(i)
-    if cur:
-        buckets.append(cur)
-    return buckets
+    i = n
+    while i > 0:
+        buckets.append(order[cut[i]:i])
+        i = cut[i]
+    return buckets[::-1]
+
+
+_PINNED: dict = {}
+_DEVICE: dict = {}
+
+
+def _device_slot(device, slot: int, rows: int, cols: int) -> torch.Tensor:
+    key = (str(device), slot)
+    buf = _DEVICE.get(key)
+    if buf is None or buf.numel() < rows * cols:
+        buf = torch.empty(max(rows * cols, 1), dtype=torch.float32, device=device)
+        _DEVICE[key] = buf
+    return buf[:rows * cols].view(rows, cols)
+
+
+
+def _pinned(tag: str, rows: int, cols: int) -> torch.Tensor:
+    """A pinned [rows, cols] fp32 staging buffer, grown on demand and kept (cudaHostAlloc costs ~1 ms a call)."""
+    buf = _PINNED.get(tag)
+    if buf is None or buf.numel() < rows * cols:
+        buf = torch.empty(max(rows * cols, 1), dtype=torch.float32).pin_memory()
+        _PINNED[tag] = buf
+    return buf[:rows * cols].view(rows, cols)
 
 
 @torch.no_grad()
-def enhance_utterances(enhancer, waves: Sequence[torch.Tensor], max_batch: int = 16, max_pad_ratio: float = 1.1,
+def enhance_utterances(enhancer, waves: Sequence[torch.Tensor], max_batch: int = 16, max_pad_ratio: float = None,
                        device=None) -> List[torch.Tensor]:
     """Enhance variable-length utterances (1-D float tensors on the host) and return the enhanced waveforms (host, true
     lengths, input order).  infer.py:142-157 per bucket: pad -> enhancer -> crop; buckets by `length_buckets`."""
@@ -83,27 +123,47 @@ def enhance_utterances(enhancer, waves: Sequence[torch.Tensor], max_batch: int =
     cur = torch.cuda.current_stream(device)
     out: List[Optional[torch.Tensor]] = [None] * len(waves)
 
-    def stage(bucket):                      # host: collate_fn's zero padding into pinned memory; device copy on `copy`
+    in_events = [None, None]
+    used_events = [None, None]              # enhancer done with the device slot
+
+    def stage(k):                           # host: collate_fn's zero padding into pinned memory; device copy on `copy`
+        bucket, slot = buckets[k], k % 2
+        if in_events[slot] is not None:
+            in_events[slot].synchronize()   # the copy that last read this pinned slot (two buckets ago) is done
         T = lens[bucket[0]]
-        h = torch.zeros(len(bucket), T, dtype=torch.float32).pin_memory()
+        h = _pinned(f"in{slot}", len(bucket), T)
+        h.zero_()
         for r, i in enumerate(bucket):
             h[r, :lens[i]] = waves[i].reshape(-1).float()
+        d = _device_slot(device, slot, len(bucket), T)      # (kept between calls: no allocator traffic per bucket)
         with torch.cuda.stream(copy):
-            d = h.to(device, non_blocking=True)
+            if used_events[slot] is not None:
+                copy.wait_event(used_events[slot])
+            d.copy_(h, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(copy)
-        return h, d, ev
+        in_events[slot] = ev
+        return d, ev
 
-    pending = []                            # (bucket, pinned result, event)
-    nxt = stage(buckets[0]) if buckets else None
+    # one pinned result buffer for all buckets (read on the host only after the last copy has landed)
+    sizes = [len(bk) * lens[bk[0]] for bk in buckets]
+    outbuf = _pinned("out", 1, sum(sizes)).view(-1)
+    pending = []                            # (bucket, pinned result view, event)
+    nxt = stage(0) if buckets else None
+    off = 0
     for k, bucket in enumerate(buckets):
-        h, d, ev = nxt
-        nxt = stage(buckets[k + 1]) if k + 1 < len(buckets) else None        # overlaps the enhancer below
+        d, ev = nxt
+        nxt = stage(k + 1) if k + 1 < len(buckets) else None                 # overlaps the enhancer below
         cur.wait_event(ev)
         y, _ = enhancer(d)
         done = torch.cuda.Event()
         done.record(cur)
-        res = torch.empty(y.shape, dtype=torch.float32).pin_memory()
+        used_events[k % 2] = done
+        if y.shape[1] == lens[bucket[0]]:
+            res = outbuf[off:off + sizes[k]].view(len(bucket), lens[bucket[0]])
+        else:                               # (an enhancer that changes the length: its own pinned buffer)
+            res = torch.empty(y.shape, dtype=torch.float32).pin_memory()
+        off += sizes[k]
         with torch.cuda.stream(copy):
             copy.wait_event(done)
             res.copy_(y, non_blocking=True)

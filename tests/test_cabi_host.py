@@ -204,6 +204,24 @@ def test_length_buckets_and_crop_starts_host_logic():
     for g in b:
         assert len(g) <= 3 and max(lens[i] for i in g) <= 1.1 * min(lens[i] for i in g)
     assert length_buckets([5, 5, 5, 5], max_batch=16) == [[0, 1, 2, 3]]
+    # default policy: minimum of (padded samples processed + a fixed cost per enhancer call).  With a huge call cost
+    # everything that fits goes into one batch; with none, equal lengths still share a batch and nothing is padded
+    one = length_buckets(lens, max_batch=16, call_overhead=10 ** 9)
+    assert len(one) == 1 and sorted(one[0]) == list(range(len(lens)))
+    free = length_buckets(lens + [16000], max_batch=16, call_overhead=0)
+    assert sorted(i for g in free for i in g) == list(range(len(lens) + 1))
+    assert all(len({(lens + [16000])[i] for i in g}) == 1 for g in free)
+    # optimality against brute force over all contiguous splits of the sorted order (small case)
+    import itertools
+    ls = [9, 7, 7, 4, 3, 3, 1]
+    def cost(groups, ov):
+        return sum(ov + len(g) * max(ls[i] for i in g) for g in groups)
+    for ov in (0, 2, 5, 50):
+        got = length_buckets(ls, max_batch=4, call_overhead=ov)
+        bestc = min(cost([list(range(a, b)) for a, b in zip((0,) + cuts, cuts + (len(ls),))], ov)
+                    for r in range(len(ls)) for cuts in itertools.combinations(range(1, len(ls)), r)
+                    if all(b - a <= 4 for a, b in zip((0,) + cuts, cuts + (len(ls),))))
+        assert cost(got, ov) == bestc and all(len(g) <= 4 for g in got), (ov, got)
     # crop starts: same generator stream as the reference's per-item draws
     gen = torch.Generator().manual_seed(11)
     items = [(torch.randn(n, generator=gen), torch.randn(m, generator=gen))
