@@ -343,7 +343,9 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const ConvParams p) {
     float* bias_s = reinterpret_cast<float*>(Bw + p.b_bytes);          // [32]
     uint64_t* mbar = reinterpret_cast<uint64_t*>(bias_s + 32);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
-    float4* fused = reinterpret_cast<float4*>(tmem_slot + 2);          // [2][4][128] float4, vector data-gradient epilogue only
+    // data gradient only (p.fused_bytes): vector epilogue [2][4][128] float4 of prefetched operands; staged epilogue
+    // [3][cig][TS] floats = output tile, prefetched FM gradient, prefetched saved activation
+    float4* fused = reinterpret_cast<float4*>(tmem_slot + 2);
 
     const Geom& g = p.g;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
