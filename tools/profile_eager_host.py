@@ -1,5 +1,9 @@
+"""Host-side profile (cProfile, top functions by own time) of the drop-in modules driven eagerly, the way the unmodified
+train.py drives them (literal schedule, no CUDA graph): where the ~40 ms per step of the `api_eager` bench figure go.
+    python tools/profile_eager_host.py"""
 import sys, os, cProfile, pstats, io
-sys.path.insert(0, "/root/repo/lct-gan_b200"); sys.path.insert(0, "/root/repo")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "lct-gan_b200")); sys.path.insert(0, ROOT)
 import torch
 from lctgan.training import StepArgs, build_models, synthetic_batch, train_step
 dev = torch.device("cuda:0")
