@@ -424,8 +424,9 @@ struct MmaWgradParams {
 // 21 n-tiles of the MSD layers in one warp the kernel needed 195 registers -> 8 resident warps per SM, and it is
 // bound by the latency of its shared-memory gathers; two groups of 11 n-tiles halve the accumulators.)
 // TP = positions per tile (128 or 256): the longer tile halves the barriers and window halos per position and won
-// 15-25 % on the k = 41 scale layers and the 512 -> 1024 period layer, and lost as much on the short maps and on the
-// two-m-tile period layers (tools/bench_disc_layers.py) - chosen per layer in launch_wgrad
+// 15-20 % on the k = 41 scale layers; it lost as much on the short maps and on the two-m-tile period layers, and on the
+// 512 -> 1024 period layer its shared memory (84 KB) costs more resident CTAs than it gains (36 us against 29 us with
+// four 128-position CTAs per SM; tools/bench_disc_layers.py) - chosen per layer in launch_wgrad
 template <int MT, int NT, int NSPLIT, int TP>
 __global__ void __launch_bounds__(kThreads * NSPLIT) conv_mma_wgrad_kernel(const MmaWgradParams p) {
     extern __shared__ __align__(16) float sm[];
@@ -770,7 +771,10 @@ int launch_wgrad_tp(MmaWgradParams& p, cudaStream_t st) {
     // fewer, longer-lived CTAs than fwd/dgrad (every CTA ends with N x KK atomics), and never more than are resident
     static int regs = 0;                    // per instantiation
     const int occ = lct_resident_ctas(kern, regs, kThreads * NSPLIT, smem, 0);
-    const int per_sm = occ < g_wgrad_ctas_per_sm ? occ : g_wgrad_ctas_per_sm;
+    // the target counts 8-warp CTAs; the 4-warp instantiations (NSPLIT == 1) get twice as many for the same warps per SM
+    // (ncu: 11 % of the warp slots occupied with 2 x 4 warps)
+    const int want = g_wgrad_ctas_per_sm * (NSPLIT == 1 ? 2 : 1);
+    const int per_sm = occ < want ? occ : want;
     int gy = 148 * per_sm / G;                // rounded down: no second wave
     if (gy > p.ntiles) gy = p.ntiles;
     if (gy < 1) gy = 1;
@@ -783,7 +787,7 @@ int launch_wgrad_tp(MmaWgradParams& p, cudaStream_t st) {
 template <int MT, int NT, int NSPLIT>
 int launch_wgrad(MmaWgradParams& p, cudaStream_t st) {
     // 256-position tiles where they were measured faster (see the kernel), 128 elsewhere
-    constexpr bool kLongOk = (MT == 1 && NT == 11) || (MT == 1 && NT == 5 && NSPLIT == 1);
+    constexpr bool kLongOk = (MT == 1 && NT == 11);
     if (kLongOk && (int64_t)p.Lout * p.P >= 384) return launch_wgrad_tp<MT, NT, NSPLIT, kLongOk ? 256 : 128>(p, st);
     return launch_wgrad_tp<MT, NT, NSPLIT, 128>(p, st);
 }
