@@ -126,3 +126,22 @@ def test_memset_zero_any_alignment_and_length(dev):
     big = torch.full((3 * 1024 * 1024 + 5,), 7.0, device=dev)
     _lib.call("lct_memset_zero", big[1:], (big.numel() - 1) * 4)
     assert float(big[0]) == 7.0 and float(big[1:].abs().max()) == 0.0
+
+
+def test_axpby_scalar_and_vector_forms(dev):
+    """lct_axpby (out = ka a + kb b; b optional; out may alias an input): the 16-byte form for large aligned buffers, the
+    element form otherwise - exact against torch in fp32."""
+    from lctgan import _lib
+    g = torch.Generator().manual_seed(5)
+    for n in (1, 7, 4095, 4096, 4099, 100003):
+        for off in (0, 1):
+            a = torch.randn(n + 4, generator=g).to(dev)[off:off + n]
+            b = torch.randn(n + 4, generator=g).to(dev)[off:off + n]
+            want = 0.5 * a - 2.0 * b
+            out = torch.empty(n + 4, device=dev)[off:off + n]
+            _lib.call("lct_axpby", a.data_ptr(), b.data_ptr(), out.data_ptr(), n, 0.5, -2.0)
+            assert torch.equal(out, want), (n, off)
+            _lib.call("lct_axpby", a.data_ptr(), b.data_ptr(), a.data_ptr(), n, 0.5, -2.0)      # in place
+            assert torch.equal(a, want), (n, off)
+            _lib.call("lct_axpby", b.data_ptr(), None, out.data_ptr(), n, 3.0, 0.0)
+            assert torch.equal(out, 3.0 * b), (n, off)
