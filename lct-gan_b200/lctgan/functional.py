@@ -216,6 +216,47 @@ class MTLossFn(torch.autograd.Function):
         return (None, None, None, None, None, *ga, *gb)
 
 
+class DLossBatchedFn(torch.autograd.Function):
+    """discriminator_loss (losses.py:68-85) over logits that hold [real; fake] in ONE batch (rows [0, nb) real): the two
+    terms are reduced from the two batch halves inside the node and the backward writes both halves of one gradient
+    tensor.  Slicing the logits in autograd instead (t[:nb], t[nb:]) costs a zero fill, a copy and an add per logits
+    tensor and half in backward: ~55 tiny torch kernels between the loss and the start of the D backward."""
+
+    @staticmethod
+    def forward(ctx, loss_type, nb, *logits):
+        _require_cuda(*logits)
+        ts = [t.contiguous() for t in logits]
+        n = max(len(ts), 1)
+        real, fake = [t[:nb] for t in ts], [t[nb:] for t in ts]
+        sr = [1.0 / (t.numel() * n) for t in real]
+        sf = [1.0 / (t.numel() * n) for t in fake]
+        if loss_type == "ls":
+            cfg = ((ops.OP_SQ_CONST, 1.0, 0.0), (ops.OP_SQ_CONST, 0.0, 0.0))
+        elif loss_type == "hinge":
+            cfg = ((ops.OP_RELU_AFFINE, 1.0, -1.0), (ops.OP_RELU_AFFINE, 1.0, 1.0))
+        else:
+            raise ValueError(f"Unknown loss_type: {loss_type}")
+        out = ops.mt_reduce(real, None, sr, cfg[0][0], cfg[0][1], cfg[0][2])
+        ops.mt_reduce(fake, None, sf, cfg[1][0], cfg[1][1], cfg[1][2], out=out)
+        ctx.cfg, ctx.nb, ctx.scales = cfg, nb, (sr, sf)
+        ctx.save_for_backward(*ts)
+        return out.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        ts = list(ctx.saved_tensors)
+        nb, (sr, sf), cfg = ctx.nb, ctx.scales, ctx.cfg
+        grads = [torch.empty_like(t) for t in ts]
+        up = g.reshape(1).contiguous()
+        ops.mt_grad([t[:nb] for t in ts], None, sr, cfg[0][0], cfg[0][1], cfg[0][2], upstream=up, out=[x[:nb] for x in grads])
+        ops.mt_grad([t[nb:] for t in ts], None, sf, cfg[1][0], cfg[1][1], cfg[1][2], upstream=up, out=[x[nb:] for x in grads])
+        return (None, None, *[gr if ctx.needs_input_grad[2 + i] else None for i, gr in enumerate(grads)])
+
+
+def d_loss_batched(logits: Sequence[torch.Tensor], nb: int, loss_type: str = "ls") -> torch.Tensor:
+    return DLossBatchedFn.apply(loss_type, nb, *logits)
+
+
 class WeightedSumFn(torch.autograd.Function):
     """sum_i w_i * s_i over scalar tensors in one launch (and one launch for all the gradients): the loss combinations
     ``lr + lf`` (losses.py:135) and ``mr + l_mask * m + l_adv * (adv + l_fm * fm)`` (train.py:240-243) without torch's

@@ -655,10 +655,12 @@ def mt_reduce(a: Sequence[torch.Tensor], b: Optional[Sequence[torch.Tensor]], sc
 
 
 def mt_grad(a: Sequence[torch.Tensor], b: Optional[Sequence[torch.Tensor]], scale: Sequence[float], op: int,
-            k0: float = 0.0, k1: float = 0.0, upstream: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
+            k0: float = 0.0, k1: float = 0.0, upstream: Optional[torch.Tensor] = None,
+            out: Optional[Sequence[torch.Tensor]] = None) -> List[torch.Tensor]:
+    """g_i = upstream * scale_i * d op(a_i, b_i) / d a_i; `out`: pre-allocated g_i (e.g. slices of larger buffers)."""
     a = [_flat_ok(t) for t in a]
     b = [_flat_ok(t) for t in b] if b is not None else None
-    g = [torch.empty_like(t) for t in a]
+    g = [_flat_ok(t) for t in out] if out is not None else [torch.empty_like(t) for t in a]
     maxseg = call_ret("lct_mt_max_segments")
     for s in range(0, len(a), maxseg):
         aa = a[s:s + maxseg]

@@ -59,6 +59,7 @@ def _phase_d(M, noisy, clean, args: StepArgs, st: dict) -> None:
     """TF features + discriminator forward/backward (train.py:171-199)."""
     enhancer, mpd, msd, tf_features, mrstft_loss, g_opt, d_opt = M
     d_opt.zero_grad(set_to_none=True)
+    batched_logits = None
     if args.reuse_enhancer_forward and args.batch_d_step and noisy.is_cuda:
         g_opt.zero_grad(set_to_none=True)
         # [clean; enhanced] goes through every sub-discriminator as ONE batch of 2B (one autograd node, one backward),
@@ -69,8 +70,7 @@ def _phase_d(M, noisy, clean, args: StepArgs, st: dict) -> None:
         st["enhanced"], st["mask_c"] = enhancer(noisy)
         st["irm_c"] = tf_features(noisy, clean)["irm_c"]
         pl, _, sl, _ = finish_split_forward(mpd, msd, st["enhanced"], early)
-        mpd_real, mpd_fake = [t[:nb] for t in pl], [t[nb:] for t in pl]
-        msd_real, msd_fake = [t[:nb] for t in sl], [t[nb:] for t in sl]
+        batched_logits = list(pl) + list(sl)        # rows [0, nb) real, [nb, 2 nb) fake: one loss node, no slicing
     elif args.reuse_enhancer_forward and noisy.is_cuda:
         g_opt.zero_grad(set_to_none=True)
         cur = torch.cuda.current_stream()
@@ -93,8 +93,11 @@ def _phase_d(M, noisy, clean, args: StepArgs, st: dict) -> None:
         mpd_fake, _ = mpd(enhanced_for_d)
         msd_real, _ = msd(clean)
         msd_fake, _ = msd(enhanced_for_d)
-    d_loss = L.discriminator_loss(L._flatten_logits_lists(mpd_real, msd_real),
-                                  L._flatten_logits_lists(mpd_fake, msd_fake), args.gan_loss)
+    if batched_logits is not None:
+        d_loss = LF.d_loss_batched(batched_logits, nb, args.gan_loss)
+    else:
+        d_loss = L.discriminator_loss(L._flatten_logits_lists(mpd_real, msd_real),
+                                      L._flatten_logits_lists(mpd_fake, msd_fake), args.gan_loss)
     # data parallel: every sub-discriminator hands its finished gradient buffer to the exchange as soon as its own
     # backward is done (the all-reduce of the first ones overlaps the backward of the others)
     config.stack_grad_hook = getattr(st.get("after_d"), "reduce_async", None) if noisy.is_cuda else None
