@@ -66,8 +66,10 @@ def _phase_d(M, noisy, clean, args: StepArgs, st: dict) -> None:
         # but in two parts: the clean half - and the weight preparation - need nothing from the generator, so they run
         # on the side streams while the generator's forward (a chain of small kernels) has the GPU to itself
         nb = clean.shape[0]
-        early = begin_split_forward(mpd, msd, clean.contiguous())
-        st["enhanced"], st["mask_c"] = enhancer(noisy)
+        start = torch.cuda.Event()
+        start.record(torch.cuda.current_stream())
+        st["enhanced"], st["mask_c"] = enhancer(noisy)      # enqueued first, so that the graph launches it first
+        early = begin_split_forward(mpd, msd, clean.contiguous(), after=start)
         st["irm_c"] = tf_features(noisy, clean)["irm_c"]
         pl, _, sl, _ = finish_split_forward(mpd, msd, st["enhanced"], early)
         batched_logits = list(pl) + list(sl)        # rows [0, nb) real, [nb, 2 nb) fake: one loss node, no slicing

@@ -106,19 +106,36 @@ def run_discriminators(mpd, msd, waves, no_grad=None, first_stream=0):
         out.append(([t[0] for t in r[:np_]], [t[1] for t in r[:np_]], [t[0] for t in r[np_:]], [t[1] for t in r[np_:]]))
     return out
 
-def begin_split_forward(mpd, msd, first_half, first_stream=0):
+def begin_split_forward(mpd, msd, first_half, first_stream=0, after=None):
     """Scheduling helper (not part of the reference API) for a pass over a batch whose second half does not exist yet:
     the D step evaluates every sub-discriminator on [clean; enhanced] (train.py:188-193) and only `clean` is known while
     the generator runs.  On its own side stream (forked from the caller's stream HERE) every sub-discriminator prepares
     its weights and pushes `first_half` through its kernels into feature-map buffers sized for the whole batch.
-    Returns the state finish_split_forward() continues from; nothing is joined yet."""
+    Returns the state finish_split_forward() continues from; nothing is joined yet.
+    `after` (a CUDA event recorded earlier on the caller's stream): fork from THAT point instead of the stream's current
+    one - the caller may then enqueue the generator first (a captured graph launches ready branches in the order they
+    were created: enqueued second, the generator's first kernel was measured waiting 0.49 ms behind this pass although
+    nothing but creation order made it wait) and still have this pass depend on nothing the generator does."""
     discs = list(mpd.discriminators) + list(msd.discriminators)
-    inputs = [first_half] * len(mpd.discriminators) + _msd_inputs(msd, first_half)
     cur = torch.cuda.current_stream(first_half.device)
     streams = _cfg.side_streams(first_stream + len(discs), first_half.device)[first_stream:]
+    fork = (lambda s: s.wait_event(after)) if after is not None else (lambda s: s.wait_stream(cur))
+    if after is not None:
+        # the pooled inputs of the scale discriminators are made on the first scale stream, not on the caller's
+        s0 = streams[len(mpd.discriminators)]
+        fork(s0)
+        with torch.cuda.stream(s0), torch.no_grad():
+            pooled = _msd_inputs(msd, first_half)
+            pooled_ev = torch.cuda.Event()
+            pooled_ev.record(s0)
+    else:
+        pooled, pooled_ev = _msd_inputs(msd, first_half), None
+    inputs = [first_half] * len(mpd.discriminators) + pooled
     state = []
-    for d, x, s in zip(discs, inputs, streams):
-        s.wait_stream(cur)
+    for k, (d, x, s) in enumerate(zip(discs, inputs, streams)):
+        fork(s)
+        if pooled_ev is not None and k > len(mpd.discriminators):
+            s.wait_event(pooled_ev)
         with torch.cuda.stream(s), torch.no_grad():
             prep = d.prepare(need_dgrad=False)
             xa = d._input4(x).contiguous()
