@@ -120,12 +120,19 @@ def _phase_g(M, noisy, clean, args: StepArgs, st: dict) -> None:
         g_opt.zero_grad(set_to_none=True)
         enhanced, mask_c = enhancer(noisy)
     if args.reuse_enhancer_forward and noisy.is_cuda:
+        # the spectral and mask losses need nothing from the discriminators: a dozen small kernels that run on a side
+        # stream beside the 16 chains (and their backward beside the D data gradients) instead of after them
+        cur = torch.cuda.current_stream()
+        side = config.side_streams(20, noisy.device)[19]
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            mr_loss, _ = mrstft_loss(enhanced, clean)
+            irm_al, pred_al = _align_tf_targets(st["irm_c"], mask_c[:, 0])
+            m_loss = L.mask_mse_loss(pred_al, irm_al)
         # real feature maps (no grad) and the generator's fake pass are independent: 16 chains at once
         (_, mpd_real_f, _, msd_real_f), (mpd_fake_g, mpd_fake_f, msd_fake_g, msd_fake_f) = \
             run_discriminators(mpd, msd, [clean, enhanced], no_grad=[True, False])
-        mr_loss, _ = mrstft_loss(enhanced, clean)
-        irm_al, pred_al = _align_tf_targets(st["irm_c"], mask_c[:, 0])
-        m_loss = L.mask_mse_loss(pred_al, irm_al)
+        cur.wait_stream(side)
     else:
         mr_loss, _ = mrstft_loss(enhanced, clean)
         irm_al, pred_al = _align_tf_targets(st["irm_c"], mask_c[:, 0])
