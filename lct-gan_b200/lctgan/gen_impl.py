@@ -133,7 +133,7 @@ class _Side:
     def __init__(self, device):
         from . import config
         self.cur = torch.cuda.current_stream(device)
-        self.side = config.aux_stream_for(self.cur) if config.concurrent_discriminators else None   # low priority
+        self.side = config.generator_side_stream(device) if config.concurrent_discriminators else None
         self.keep = []
 
     def fork(self, *tensors):
