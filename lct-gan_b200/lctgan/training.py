@@ -110,7 +110,7 @@ def _phase_d(M, noisy, clean, args: StepArgs, st: dict) -> None:
     st["d_loss"] = d_loss.detach()
 
 
-def _phase_g(M, noisy, clean, args: StepArgs, st: dict) -> None:
+def _phase_g(M, noisy, clean, args: StepArgs, st: dict, join_dead: bool = True) -> None:
     """Discriminator update + generator forward/backward (train.py:200-245)."""
     enhancer, mpd, msd, tf_features, mrstft_loss, g_opt, d_opt = M
     d_opt.step()
@@ -154,7 +154,8 @@ def _phase_g(M, noisy, clean, args: StepArgs, st: dict) -> None:
         g_loss.backward()
     finally:
         config.defer_dead_param_grads = False
-        config.join_deferred_param_grads()
+        if join_dead:      # (join_dead=False: the caller joins after the generator's optimiser step, which they can overlap)
+            config.join_deferred_param_grads()
     st.update(g_loss=g_loss.detach(), mr=mr_loss.detach(), mask=m_loss.detach(), adv=adv_loss.detach(),
               fm=fm_loss.detach())
 
@@ -195,9 +196,12 @@ def train_step(enhancer, mpd, msd, tf_features, mrstft_loss, g_opt, d_opt, noisy
     _phase_d(M, noisy, clean, args, st)
     if after_d_backward is not None:
         after_d_backward()
-    _phase_g(M, noisy, clean, args, st)
-    _exchange_g(enhancer, after_g_backward)
-    _phase_opt_g(M, args, _pre_scale(after_g_backward))
+    try:
+        _phase_g(M, noisy, clean, args, st, join_dead=False)
+        _exchange_g(enhancer, after_g_backward)
+        _phase_opt_g(M, args, _pre_scale(after_g_backward))
+    finally:
+        config.join_deferred_param_grads()     # the dead D gradients touch nothing the clip / generator update reads
     return {k: st[k] for k in _OUT_KEYS}
 
 
@@ -330,9 +334,10 @@ class GraphedTrainStep:
                     _phase_d(M, self.noisy, self.clean, args, st)
                     if after_d_backward is not None:
                         after_d_backward()
-                    _phase_g(M, self.noisy, self.clean, args, st)
+                    _phase_g(M, self.noisy, self.clean, args, st, join_dead=False)
                     _exchange_g(enhancer, after_g_backward)
                     _phase_opt_g(M, args, _pre_scale(after_g_backward))
+                    config.join_deferred_param_grads()
                 self.graphs = [g]
             except Exception as e:
                 if not has_hooks:
