@@ -252,6 +252,23 @@ __global__ void __launch_bounds__(kThreads) conv_mma_kernel(const MmaParams p) {
         const int j0 = jt * p.TPe;
         const int jtot = min(p.Q * p.P, j0 + p.TPe);
         const int row_first = fdiv(j0, p.fP);
+        if (MODE == MODE_DGRAD && (has_g || has_x)) {
+            // The epilogue below reads the FM gradient / saved activation of this tile's output run in 2-4 dependent
+            // rounds (16 loads per thread each): ask the L2 for those lines now, so that the rounds cost L2 hits instead
+            // of DRAM round trips with nothing else of this CTA in flight (ncu: long_scoreboard was the top stall).
+            const int nrows_p = fdiv(jtot - j0, p.fP);
+            const int E_p = nrows_p * p.S * p.P;
+            const int gpos_p = (p.S * row_first - p.opad) * p.P;
+            const int lo_c = max(gpos_p, 0), hi_c = min(gpos_p + E_p, lo_p);          // the run, clipped to the map
+            const int cb_p = b * p.Co * lo_p + g * p.Cig * lo_p;
+            const int lines = (hi_c - lo_c + 31) / 32 + 1;     // 128-byte lines per channel (+ 1: the run is not aligned)
+            for (int i = tid; i < p.Cig * lines; i += kThreads) {
+                const int ci = i / lines, ln = i - ci * lines;
+                const int off = cb_p + ci * lo_p + min(lo_c + 32 * ln, hi_c - 1);
+                if (has_g) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.gextra + off));
+                if (has_x) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.xact + off));
+            }
+        }
         // per-thread rows: m-tile mt, half h -> position j0 + warp*16*MTW + mt*16 + gq + 8h
         // abase = window address of the row (LUT entries are byte offsets);  orow = output offset of the row
         const char* abase[MTW][2];
