@@ -22,7 +22,7 @@ from lctgan import ops
 from lctgan.disc_impl import conv_stack, prepare_stack, stack_forward
 
 
-def _run_concurrently(discs, inputs, no_grad=None, first_stream=0):
+def _run_concurrently(discs, inputs, no_grad=None, first_stream=0, post=None):
     """Evaluate discs[i](inputs[i]) for all i, each on its own CUDA stream (fork/join around the caller's stream).
     no_grad[i] evaluates that call under torch.no_grad().  A sub-discriminator that appears more than once (the G step
     runs every one on the clean and on the enhanced batch) prepares its weights - weight norm, staged conv images - ONCE,
@@ -54,14 +54,26 @@ def _run_concurrently(discs, inputs, no_grad=None, first_stream=0):
             d._prep = None
 
     if not (_cfg.concurrent_discriminators and x0.is_cuda and len(discs) > 1):
-        return [call(d, x, ng) for d, x, ng in zip(discs, inputs, flags)]
+        out = []
+        for i, (d, x, ng) in enumerate(zip(discs, inputs, flags)):
+            out.append(call(d, x, ng))
+            if post is not None:
+                post(i, out, None, None)
+        return out
     cur = torch.cuda.current_stream(x0.device)
     streams = _cfg.side_streams(first_stream + len(discs), x0.device)[first_stream:]
     out = [None] * len(discs)
+    done = [None] * len(discs)
     for i, (d, x, s, ng) in enumerate(zip(discs, inputs, streams, flags)):
         s.wait_stream(cur)
         with torch.cuda.stream(s):
             out[i] = call(d, x, ng, s)
+            if post is not None:
+                # post(i, outputs so far, this call's stream, done events of the earlier calls): work that follows call i
+                # on ITS stream, before the join (e.g. the feature-matching term of one sub-discriminator)
+                done[i] = torch.cuda.Event()
+                done[i].record(s)
+                post(i, out, s, done)
     for s in streams:
         cur.wait_stream(s)
     return out
@@ -80,7 +92,7 @@ def _msd_inputs(msd, x):
     return inputs
 
 
-def run_discriminators(mpd, msd, waves, no_grad=None, first_stream=0):
+def run_discriminators(mpd, msd, waves, no_grad=None, first_stream=0, post=None):
     """Scheduling helper (not part of the reference API): evaluate `mpd(w)` and `msd(w)` for every waveform w in
     `waves` with ALL 8 * len(waves) sub-discriminators forked at once instead of one module call after the other.
     Returns [(mpd_logits, mpd_fmaps, msd_logits, msd_fmaps) per waveform]; values are identical to the module calls."""
@@ -98,7 +110,7 @@ def run_discriminators(mpd, msd, waves, no_grad=None, first_stream=0):
         discs += list(msd.discriminators)
         inputs += mi
         ng += [f] * len(msd.discriminators)
-    res = _run_concurrently(discs, inputs, ng, first_stream)
+    res = _run_concurrently(discs, inputs, ng, first_stream, post=post)
     out, per = [], len(mpd.discriminators) + len(msd.discriminators)
     for k in range(len(waves)):
         r = res[k * per:(k + 1) * per]
